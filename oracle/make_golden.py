@@ -1,0 +1,225 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz by executing the UNMODIFIED reference
+(/root/reference, CPU, through oracle/ref_loader.py).  Run in the build container:
+
+    python oracle/make_golden.py
+
+The fixtures hold explicit inputs and the reference's outputs, so consumers need neither the
+reference tree nor a matching RNG.  Everything is float32/int64 unless noted.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+MU = torch.tensor([-4.27, -4.31, -3.95])
+MAXB = torch.tensor([4.28, 4.27, 2.37])
+SIGMA = ((MAXB - MU) ** 2).sum().sqrt()          # train_hash2.py:119
+
+
+def npz(name, **kw):
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name), **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v))
+                                                    for k, v in kw.items()})
+    print("wrote", name, {k: tuple(np.asarray(v.detach() if torch.is_tensor(v) else v).shape) for k, v in kw.items()})
+
+
+def build(ref, L, T, n_max, seed, table_scale):
+    torch.manual_seed(seed)
+    with ref_loader.quiet():
+        enc = ref.hash_encoding.HashEncoder(N_min=16, N_max=n_max, L=L, F=2, T=T, dim=3, mu=MU, sigma=SIGMA, device="cpu")
+        mlp = ref.test_hash.MLP_3D(num_sig=2, num_col=2, L=L, F=2, d_view=24, max_bound=ref.Bound(MAXB), min_bound=ref.Bound(MU))
+        pe = ref.encoder.PositionalEncoder(3, 4)
+    pe.sinus_in = pe.sinus_in.cpu()
+    with torch.no_grad():
+        for e in enc.Embedding_list:
+            e.weight.mul_(table_scale)           # "trained-like" magnitudes; init is U(-1e-4,1e-4) (hash_encoding.py:32)
+    return enc, mlp, pe
+
+
+def points(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = MU + torch.rand(n, 3, generator=g) * (MAXB - MU)
+    x[:8] = MU - torch.rand(8, 3, generator=g)              # outside the bbox: negative cells / negative frac (Q4)
+    x[8] = MU                                               # exactly on the corner
+    x[9] = MAXB
+    return x
+
+
+def gold_hash(ref):
+    for tag, L, T in (("pow2", 16, 1024), ("npow2", 4, 1000)):
+        enc, _, _ = build(ref, L, T, 2048.0, 11, 1e4)
+        x = points(257, 3)
+        tables = torch.stack([e.weight.detach().clone() for e in enc.Embedding_list])
+        scales = torch.stack([(enc.N_min * enc.b ** i).float() for i in range(L)])
+        idx = []
+        for i in range(L):                                   # hash_encoding.py:153-162, index part only
+            un_x = ((x - enc.mu) / enc.sigma) * scales[i]
+            x_val = torch.stack([un_x.long(), un_x.long() + 1], dim=-1)[..., None, :, :]
+            bm = enc.bin_mask.reshape((1,) + (8, 3))
+            idx.append(enc.hash_func(torch.where(bm, x_val[..., 0], x_val[..., 1]), T))
+        with ref_loader.quiet():
+            y = enc(x)
+            y16 = enc(x.half())
+        dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(4))
+        y.backward(dy)
+        g = torch.stack([e.weight.grad for e in enc.Embedding_list])
+        npz(f"hash_{tag}.npz", x=x, tables=tables, mu=MU, sigma=SIGMA, scales=scales, n_min=16, n_max=2048.0,
+            idx=torch.stack(idx), y=y.detach(), y_from_f16=y16.detach(), dy=dy, dtables=g)
+
+
+def gold_mlp_dir(ref):
+    _, mlp, pe = build(ref, 16, 64, 2048.0, 12, 1.0)
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        mlp.sig_model[4].bias[0] += 1.0                      # so LeakyReLU sees both signs
+    d = torch.nn.functional.normalize(torch.randn(96, 3, generator=g), dim=-1)
+    enc_d = pe(d).reshape(96, -1)
+    enc_d16 = pe(d.half()).reshape(96, -1)
+    npz("dir.npz", d=d, enc=enc_d, enc_from_f16=enc_d16.float())
+    feat = torch.randn(96, 32, generator=g).requires_grad_()
+    dirs = enc_d.clone().requires_grad_()
+    with ref_loader.quiet():
+        out = mlp(feat, dirs)
+        dens = mlp(feat)
+    dout = torch.randn(out.shape, generator=g)
+    out.backward(dout)
+    kw = {k.replace(".", "__"): v.detach() for k, v in mlp.state_dict().items()}
+    kw.update({"grad__" + k.replace(".", "__"): v.grad for k, v in mlp.named_parameters()})
+    npz("mlp.npz", feat=feat.detach(), dirs=dirs.detach(), out=out.detach(), density_only=dens.detach(), dout=dout,
+        dfeat=feat.grad, ddirs=dirs.grad, **kw)
+
+
+def gold_composite(ref):
+    g = torch.Generator().manual_seed(6)
+    R, S = 48, 40
+    t = torch.linspace(2.0, 6.0, S) + torch.rand(S, generator=g) * 4.0 / S
+    rgb = torch.randn(R, S, 3, generator=g).requires_grad_()
+    sig = (torch.randn(R, S, generator=g) * 6)
+    sig[0, :6] = -25.0                                       # exercises the -10 clamp (helper.py:76)
+    sig[1] = sig[1].abs() * 20                               # saturating ray: T underflows
+    sig = sig.requires_grad_()
+    dn = 1 + torch.rand(R, 1, generator=g)
+    C, w, _ = ref.helper.calc_color(t=t, rgb=rgb, sigma=sig * 1.0, dir_norm=dn, device="cpu")
+    gC = torch.randn(R, 3, generator=g)
+    C.backward(gC)
+    npz("composite.npz", t=t, rgb=rgb.detach(), sigma=sig.detach(), dir_norm=dn, C=C.detach(), w=w.detach()[..., 0],
+        gC=gC, drgb=rgb.grad, dsigma=sig.grad)
+    # per-ray depths (the fine pass hands calc_color an (R,2S) t)
+    t2 = torch.sort(2 + 4 * torch.rand(R, S, generator=g), dim=-1).values
+    rgb2 = torch.randn(R, S, 3, generator=g).requires_grad_()
+    sig2 = (torch.randn(R, S, generator=g) * 6).requires_grad_()
+    C2, w2, _ = ref.helper.calc_color(t=t2, rgb=rgb2, sigma=sig2 * 1.0, dir_norm=dn, device="cpu")
+    C2.backward(gC)
+    npz("composite_perray.npz", t=t2, rgb=rgb2.detach(), sigma=sig2.detach(), dir_norm=dn, C=C2.detach(),
+        w=w2.detach()[..., 0], gC=gC, drgb=rgb2.grad, dsigma=sig2.grad)
+    # hierarchical sampling (helper.py:23-51): replay the two torch.rand draws
+    ro = torch.randn(R, 3, generator=g)
+    rd = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    near, far = torch.tensor(2.0), torch.tensor(6.0)
+    torch.manual_seed(21)
+    with ref_loader.quiet():
+        rays_f, t_f = ref.helper.hierarchical_sampling(ro, rd, z_vals=t, weights=w.detach().clone(), n_samples=S,
+                                                       tn=near, tf=far, device="cpu")
+    torch.manual_seed(21)
+    u_rs = torch.rand(R, S)
+    u_s = torch.rand(S)
+    npz("hier.npz", w=w.detach()[..., 0], t=t, near=2.0, far=6.0, u_rs=u_rs, u_s=u_s, rays_o=ro, rays_d=rd,
+        t_fine=t_f, rays_fine=rays_f)
+
+
+def gold_volrender(ref):
+    L, T, S, R = 16, 1024, 24, 40
+    enc, mlp, pe = build(ref, L, T, 2048.0, 13, 3e3)
+    with torch.no_grad():
+        mlp.sig_model[4].bias[0] += 1.5
+    near, far = torch.tensor(2.0), torch.tensor(6.0)
+    vr = ref.vol_renderer.Volume_Renderer(H=8, W=8, K=torch.eye(3), near=near, far=far, device="cpu", Pos_encode=enc,
+                                          Dir_encode=pe, max_dim=64, sigma_val=SIGMA, mu=MU)
+    g = torch.Generator().manual_seed(8)
+    ro = torch.tensor([[0.5, -0.3, 4.0]]).repeat(R, 1) + 0.05 * torch.randn(R, 3, generator=g)
+    rd = torch.nn.functional.normalize(-ro + 0.6 * torch.randn(R, 3, generator=g), dim=-1)
+    dn = 1 + 0.2 * torch.rand(R, 1, generator=g)
+    gt = torch.rand(R, 3, generator=g)
+    kw = dict(rays_o=ro, rays_d=rd, dir_norm=dn, gt=gt, mu=MU, sigma=SIGMA, near=2.0, far=6.0,
+              tables=torch.stack([e.weight.detach().clone() for e in enc.Embedding_list]),
+              scales=torch.stack([(enc.N_min * enc.b ** i).float() for i in range(L)]))
+    kw.update({"mlp__" + k.replace(".", "__"): v.detach().clone() for k, v in mlp.state_dict().items()})
+    for hier in (False, True):
+        tag = "hier" if hier else "coarse"
+        for prm in list(enc.parameters()) + list(mlp.parameters()):
+            prm.grad = None
+        torch.manual_seed(31)
+        with ref_loader.quiet():
+            Cr, Cf, _ = vr.vol_render(mlp, rd, ro, num_samples=S, update_mask=False, dir_norm=dn, hierarchical=hier)
+        loss = torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)   # train_hash2.py:221,177
+        loss.backward()
+        torch.manual_seed(31)
+        kw[f"{tag}__u_t"] = torch.rand(S)
+        if hier:
+            kw[f"{tag}__u_rs"] = torch.rand(R, S)
+            kw[f"{tag}__u_s"] = torch.rand(S)
+        kw[f"{tag}__Cr"] = Cr.detach()
+        kw[f"{tag}__Cf"] = Cf.detach()
+        kw[f"{tag}__loss"] = loss.detach()
+        kw[f"{tag}__dtables"] = torch.stack([e.weight.grad for e in enc.Embedding_list])
+        for k, v in mlp.named_parameters():
+            kw[f"{tag}__grad__" + k.replace(".", "__")] = v.grad.clone()
+    npz("volrender.npz", **kw)
+
+
+def gold_grid(ref):
+    """nerf2mesh.py:27-40,69-86 on a 12^3 grid (the script itself needs torchmcubes/open3d, absent here;
+    the statements below are the same calls on the same objects)."""
+    L, T, res = 16, 1024, 12
+    enc, mlp, pe = build(ref, L, T, 2048.0, 14, 5e3)
+    min_b, max_b = MU.numpy(), MAXB.numpy()
+    x = np.linspace(min_b[0], max_b[0], res)
+    y = np.linspace(min_b[1], max_b[1], res)
+    z = np.linspace(min_b[2], max_b[2], res)
+    X, Y, Z = np.meshgrid(x, y, z)
+    grid = torch.stack([torch.tensor(X.reshape(-1)), torch.tensor(Y.reshape(-1)), torch.tensor(Z.reshape(-1))], dim=1).to(torch.float16)
+    view = torch.zeros_like(grid, dtype=torch.float16)
+    view[..., 2] = 1.0
+    with torch.no_grad(), ref_loader.quiet():
+        out = mlp(enc(grid), pe(view).reshape(view.shape[0], -1))
+    kw = dict(min_bound=min_b, max_bound=max_b, res=res, grid_f16=grid.float(), out=out.reshape(res, res, res, 4),
+              mu=MU, sigma=SIGMA, tables=torch.stack([e.weight.detach().clone() for e in enc.Embedding_list]),
+              scales=torch.stack([(enc.N_min * enc.b ** i).float() for i in range(L)]))
+    kw.update({"mlp__" + k.replace(".", "__"): v.detach().clone() for k, v in mlp.state_dict().items()})
+    npz("grid.npz", **kw)
+
+
+def gold_rays(ref):
+    """get_od / find_bounding_box (helper.py:176-208,109-141) for a 3-camera 6x5 rig with int64 K (Q14)."""
+    H, W = 5, 6
+    K = torch.from_numpy(np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1]]))
+    K[0, 0] = 7.9
+    K[1, 1] = 7.9
+    K[0, 2] = W / 2
+    K[1, 2] = H / 2
+    g = torch.Generator().manual_seed(9)
+    c2w = torch.eye(4).repeat(3, 1, 1)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, 3, generator=g))
+    c2w[:, :3, :3] = q
+    c2w[:, :3, 3] = torch.randn(3, 3, generator=g) * 2
+    o, d, n = ref.helper.get_od(H, W, K, c2w)
+    loader = [(None, c2w[i:i + 2], None) for i in (0, 2)]
+    with ref_loader.quiet():
+        mx, mn = ref.helper.find_bounding_box(loader, near=torch.tensor(2.0), far=torch.tensor(6.0), K=K)
+    npz("rays.npz", H=H, W=W, K=K, c2w=c2w, rays_o=o, rays_d=d, dir_norm=n, max_bound=mx, min_bound=mn)
+
+
+if __name__ == "__main__":
+    ref = ref_loader.load()
+    gold_hash(ref)
+    gold_mlp_dir(ref)
+    gold_composite(ref)
+    gold_volrender(ref)
+    gold_grid(ref)
+    gold_rays(ref)

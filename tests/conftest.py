@@ -1,0 +1,43 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def mlp_params(g, prefix=""):
+    """state-dict style dict from a fixture whose keys use '__' for '.'."""
+    out = {}
+    for k, v in g.items():
+        if k.startswith(prefix) and ("sig_model" in k or "col_model" in k) and "grad" not in k:
+            out[k[len(prefix):].replace("__", ".")] = v
+    return out
+
+
+@pytest.fixture
+def golden():
+    return load_golden
