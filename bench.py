@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement: train rays/s of one train_hash2.py-shaped step (hash encode -> field MLP ->
+alpha compositing, forward + backward) on B200, through the reference-facing drop-in API.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # our arm (one JSON line)
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1   # the reference's algorithm on host cores
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # weak scaling, rays sharded
+
+A "step" = Volume_Renderer.vol_render(...) + MSE(Cr)+MSE(Cf) + loss.backward() on one batch of synthetic rays
+(BASELINE.json configs[1]: 4096 rays x 128 samples, L=16 F=2 T=2^19, lego-shaped 800x800 scene).  The optimiser
+step is not part of the metric; gradient buffers are re-zeroed inside the step.
+
+value   : rays/s with the ray batch already resident in HBM, timed with CUDA events per step, L2 flushed between
+          steps (the 64 MiB table would otherwise sit in the 126 MB L2), max over ranks.
+e2e     : same step driven from pinned HOST buffers: H2D of (rays_o, rays_d, dir_norm, gt) and a D2H read of the
+          loss inside the timed region, wall clock.
+roofline: the dominant kernel's algorithmic bytes / its mean CUDA-event duration inside the timed steps.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic bytes per sample point, L=16 F=2 fp32
+BYTES_PER_POINT = {
+    "hbr_hash_encode_fwd": 1164, "hbr_hash_encode_bwd": 1164, "hbr_mlp_fwd_f32": 144, "hbr_mlp_bwd_f32": 272,
+    "hbr_mlp_fwd_tc": 144, "hbr_mlp_bwd_tc": 272, "hbr_composite_fwd": 16, "hbr_composite_bwd": 32,
+    "hbr_field_fwd": 1040, "hbr_field_bwd": 1040,
+}
+STEP_BYTES_PER_POINT = 2792
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# synthetic lego-shaped scene: cameras on the upper hemisphere, radius 4.0311, looking at the origin
+# ---------------------------------------------------------------------------------------------------------------
+def make_cameras(n_views: int, seed: int = 0) -> torch.Tensor:
+    rng = np.random.default_rng(seed)
+    c2w = np.zeros((n_views, 4, 4), dtype=np.float32)
+    for v in range(n_views):
+        th = rng.uniform(0, 2 * np.pi)
+        ph = rng.uniform(0.05, 0.5 * np.pi - 0.05)                      # elevation
+        pos = 4.0311 * np.array([np.cos(ph) * np.cos(th), np.cos(ph) * np.sin(th), np.sin(ph)])
+        z = pos / np.linalg.norm(pos)                                    # camera looks down -z (helper.py:201)
+        x = np.cross([0, 0, 1.0], z)
+        x /= np.linalg.norm(x)
+        y = np.cross(z, x)
+        c2w[v, :3, 0], c2w[v, :3, 1], c2w[v, :3, 2], c2w[v, :3, 3] = x, y, z, pos
+        c2w[v, 3, 3] = 1
+    return torch.from_numpy(c2w)
+
+
+def intrinsics(H: int, W: int):
+    focal = 0.5 * W / math.tan(0.5 * 0.6911112070083618)                # dataset.py:26
+    K = torch.from_numpy(np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1]]))    # int64, train_hash2.py:67-72 (Q14)
+    K[0, 0], K[1, 1], K[0, 2], K[1, 2] = focal, focal, W / 2, H / 2
+    return K
+
+
+def rays_for_pixels(c2w, K, view, px, py):
+    """get_od (helper.py:176-208) evaluated for selected pixels only."""
+    i = (px - K[0, 2]) / K[0, 0]
+    j = (py - K[1, 2]) / K[1, 1]
+    dirs = torch.stack((i, -j, -torch.ones_like(i)), dim=-1).float()
+    R = c2w[view, :3, :3]
+    d = torch.einsum("nij,nj->ni", R, dirs)
+    n = torch.norm(d, dim=-1, keepdim=True)
+    return c2w[view, :3, 3].clone(), d / n, n
+
+
+def scene_bbox(c2w, K, H, W, near, far):
+    """find_bounding_box (helper.py:109-141) over the image borders (the extremes of a pinhole frustum)."""
+    xs = torch.arange(0, W, 8)
+    ys = torch.arange(0, H, 8)
+    px = torch.cat([xs, xs, torch.zeros_like(ys), torch.full_like(ys, W - 1)]).float()
+    py = torch.cat([torch.zeros_like(xs), torch.full_like(xs, H - 1), ys, ys]).float()
+    mn = torch.full((3,), 1e7)
+    mx = torch.full((3,), -1e7)
+    for v in range(c2w.shape[0]):
+        o, d, _ = rays_for_pixels(c2w, K, torch.full((px.shape[0],), v, dtype=torch.long), px, py)
+        for tt in (near, far + 1.5):
+            p = o + d * tt
+            mn, mx = torch.minimum(mn, p.min(0).values), torch.maximum(mx, p.max(0).values)
+    return mx, mn
+
+
+def make_batches(c2w, K, H, W, n_rays, n_batches, seed):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n_batches):
+        view = torch.randint(0, c2w.shape[0], (n_rays,), generator=g)
+        px = torch.randint(0, W, (n_rays,), generator=g).float()
+        py = torch.randint(0, H, (n_rays,), generator=g).float()
+        o, d, n = rays_for_pixels(c2w, K, view, px, py)
+        gt = torch.stack([0.5 + 0.5 * torch.sin(px / 37.0), 0.5 + 0.5 * torch.cos(py / 23.0), (px + py) / (H + W)], dim=-1)
+        out.append((o.contiguous(), d.contiguous(), n.contiguous(), gt.float().contiguous()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        if not sm:
+            return None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k] == "Active" for r in self.rows)]
+        mx = max(int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit())
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's algorithm on host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_step_rays_per_s(args, steps, warmup, rays):
+    from oracle import port
+    torch.set_num_threads(os.cpu_count())
+    H = W = 200
+    c2w, K = make_cameras(100, 0), intrinsics(H, W)
+    mx, mn = scene_bbox(c2w, K, H, W, args.near, args.far)
+    sigma = ((mx - mn) ** 2).sum().sqrt()
+    L, F, T = 16, 2, 2 ** args.hash_size
+    g = torch.Generator().manual_seed(0)
+    tables = ((torch.rand(L, T, F, generator=g) * 2 - 1)).requires_grad_()
+    params = {k: v.requires_grad_() for k, v in port.mlp_init(seed=0).items()}
+    scales = port.level_scales(16, float(args.max_res), L)
+    batches = make_batches(c2w, K, H, W, rays, 2, 1)
+    near, far = torch.tensor(args.near), torch.tensor(args.far)
+    times = []
+    for k in range(warmup + steps):
+        o, d, n, gt = batches[k % len(batches)]
+        t0 = time.perf_counter()
+        tt = port.strat_t(near, far, args.samples, torch.rand(args.samples))
+        u_rs = torch.rand(rays, args.samples) if args.hierarchical else None
+        u_s = torch.rand(args.samples) if args.hierarchical else None
+        Cr, Cf, _ = port.vol_render(params, tables, mn, sigma, scales, d, o, tt, n, 4, args.hierarchical, near, far, u_rs, u_s)
+        loss = torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)
+        loss.backward()
+        tables.grad = None
+        for v in params.values():
+            v.grad = None
+        if k >= warmup:
+            times.append(time.perf_counter() - t0)
+    return rays / (sum(times) / len(times)), sum(times) / len(times)
+
+
+def workload_name(args, rays):
+    return (f"train_hash2-shaped step: {rays} rays x {args.samples} samples/ray, L=16 F=2 T=2^{args.hash_size}, N_max={args.max_res}, "
+            f"lego-shaped synthetic {args.res}x{args.res} x{args.views} views, hierarchical={args.hierarchical}, fwd+bwd "
+            f"(encode+MLP+composite), no optimiser step")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rays = args.cpu_rays
+    v, sec = cpu_step_rays_per_s(args, args.steps, max(args.warmup, 1), rays)
+    line = {
+        "impl": "reference", "metric": "train_rays_per_sec", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, args.rays)},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{rays} rays x {args.samples} samples per step of the same synthetic scene (200x200 views), fwd+bwd, "
+                                   f"torch-CPU restatement of the reference (oracle/port.py)"},
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import human_body_reconstruction_b200 as hbr
+    from human_body_reconstruction_b200 import _lib, dist as hdist
+    import torch.distributed as tdist
+
+    rank, world = hdist.init_from_env("nccl")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    H = W = args.res
+    c2w, K = make_cameras(args.views, 0), intrinsics(H, W)
+    mx, mn = scene_bbox(c2w, K, H, W, args.near, args.far)
+    sigma = ((mx - mn) ** 2).sum().sqrt()
+    L, F, T = 16, 2, 2 ** args.hash_size
+    torch.manual_seed(0)                                                  # identical parameters on every rank
+    enc = hbr.HashEncoder(N_min=16, N_max=float(args.max_res), L=L, F=F, T=T, dim=3, mu=mn.to(dev), sigma=sigma.to(dev))
+    with torch.no_grad():
+        for e in enc.Embedding_list:
+            e.weight.mul_(1e4)                                            # trained-like magnitudes U(-1,1)
+    mlp = hbr.MLP_3D(num_sig=2, num_col=2, L=L, F=F, d_view=24, max_bound=mx, min_bound=mn)
+    enc, mlp = enc.to(dev), mlp.to(dev)
+    nerf = torch.nn.DataParallel(mlp, device_ids=[local])                 # as train_hash2.py:127 does
+    pe = hbr.PositionalEncoder(3, 4)
+    near, far = torch.tensor(args.near), torch.tensor(args.far)
+    vr = hbr.Volume_Renderer(H=H, W=W, K=K, near=near, far=far, device=dev, Pos_encode=enc, Dir_encode=pe, max_dim=2 ** 10,
+                             sigma_val=sigma, mu=mn)
+    reducer = hdist.GradAllReduce(enc, mlp) if world > 1 else None
+    rays = args.rays                                                       # per GPU (weak scaling)
+    host = [tuple(t.pin_memory() for t in b) for b in make_batches(c2w, K, H, W, rays, 4, 100 + rank)]
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+    params = list(enc.parameters()) + list(mlp.parameters())
+    flush = torch.empty(512 * 1024 * 1024 // 4, device=dev) if args.l2 == "flush" else None
+    amp = args.precision == "bf16"
+
+    def step(batch):
+        o, d, n, gt = batch
+        for p in params:
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            Cr, Cf, _ = vr.vol_render(nerf, d, o, num_samples=args.samples, update_mask=False, dir_norm=n,
+                                      hierarchical=args.hierarchical)
+            loss = torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step(resident[k % len(resident)])
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    _lib.STATS.reset()
+    _lib.STATS.timing = True
+    ev = []
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        if flush is not None:
+            flush.zero_()                                                  # evict L2 (outside the timed events)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(resident[k % len(resident)])
+        e1.record()
+        ev.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    _lib.STATS.timing = False
+    launches = _lib.STATS.launches
+    kern = _lib.STATS.summary()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # end to end: pinned host batch -> H2D -> step -> loss.item()
+    e2e_s = 0.0
+    for k in range(args.steps):
+        if flush is not None:
+            flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        batch = tuple(t.to(dev, non_blocking=True) for t in host[k % len(host)])
+        loss = step(batch)
+        loss_val = loss.item()
+        e2e_s += time.perf_counter() - t0
+    barrier()
+    clk = clocks.stop()
+
+    tms = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        tdist.all_reduce(tms, op=tdist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(tms[0]), float(tms[1])
+    if rank != 0:
+        return
+    pts_per_ray = args.samples * (3 if args.hierarchical else 1)
+    n_pts = rays * pts_per_ray
+    total_rays = rays * world * args.steps
+    value = total_rays / (dev_ms / 1e3)
+    peak, peak_src = measured_peaks()
+    # dominant kernel
+    tot = {k: c * m for k, (c, m) in kern.items()}
+    dom = max(tot, key=tot.get)
+    calls_per_step = kern[dom][0] / args.steps
+    pts_per_launch = n_pts / calls_per_step
+    achieved = BYTES_PER_POINT.get(dom, 0) * pts_per_launch / (kern[dom][1] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(dom)
+    step_achieved = STEP_BYTES_PER_POINT * n_pts / (dev_ms / args.steps * 1e-3) / 1e9
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    line = {
+        "metric": "train_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16 MLP / f32 encoder+compositor" if amp else "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, rays), "rays_per_gpu": rays, "l2": "flushed between timed steps (512 MiB write)"
+                   if flush is not None else "warm", "parallelism": f"dp{world} (rays sharded, table+MLP grads all-reduced)"},
+        "e2e": {"value": total_rays / (e2e_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_point": BYTES_PER_POINT.get(dom),
+                     "mean_launch_ms": kern[dom][1]},
+        "step_roofline": {"algorithmic_bytes_per_point": STEP_BYTES_PER_POINT, "achieved": step_achieved, "frac": step_achieved / peak,
+                          "unit": "GB/s"},
+        "kernels_ms": {k: {"launches_per_step": c / args.steps, "mean_ms": m} for k, (c, m) in sorted(kern.items())},
+        "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
+        "clocks": clk, "last_loss": loss_val,
+    }
+    if "hbr_hash_encode_fwd" in kern:
+        c, m = kern["hbr_hash_encode_fwd"]
+        line["hash_encode_mpts_per_s"] = (n_pts / (c / args.steps)) / (m * 1e-3) / 1e6
+    if reducer is not None:
+        line["allreduce_bytes_per_step"] = reducer.bytes_reduced // max(1, args.steps * 2 + args.warmup)
+    if world == 1 and not args.no_cpu_baseline:
+        v, sec = cpu_step_rays_per_s(args, 3, 1, args.cpu_rays)
+        line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{args.cpu_rays} rays x {args.samples} samples per step (BASELINE config 1 shape, 200x200 views), "
+                                          f"1 warm-up + 3 timed fwd+bwd steps of oracle/port.py (torch CPU, {os.cpu_count()} threads)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        tdist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rays", type=int, default=4096, help="rays per GPU per step")
+    ap.add_argument("--samples", type=int, default=128)
+    ap.add_argument("--hash-size", type=int, default=19)
+    ap.add_argument("--max-res", type=float, default=2048.0)
+    ap.add_argument("--res", type=int, default=800)
+    ap.add_argument("--views", type=int, default=100)
+    ap.add_argument("--near", type=float, default=2.0)
+    ap.add_argument("--far", type=float, default=6.0)
+    ap.add_argument("--hierarchical", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--l2", default="flush", choices=["flush", "warm"])
+    ap.add_argument("--cpu-rays", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device for the b200 arm (there is no CPU fallback)")
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

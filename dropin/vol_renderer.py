@@ -1,0 +1,9 @@
+"""Reference-named module: `vol_renderer` of RishabhSri14/Human-Body-Reconstruction, served by the B200 package.
+Put this directory first on PYTHONPATH and the reference's train_hash2.py / nerf2mesh.py import it unchanged."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from human_body_reconstruction_b200.vol_renderer import *  # noqa: F401,F403
+from human_body_reconstruction_b200.encoder import *  # noqa: F401,F403  (vol_renderer.py:8 `from encoder import *`)
+from human_body_reconstruction_b200.helper import *  # noqa: F401,F403   (vol_renderer.py:11 `from helper import *`)
+import torch, numpy as np, torch.nn as nn, time  # noqa: F401,E401
+from typing import Tuple, Optional  # noqa: F401

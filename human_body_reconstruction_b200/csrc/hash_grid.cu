@@ -1,0 +1,297 @@
+// Multiresolution hash-grid encoder: forward gather, backward warp-aggregated scatter-add, index probe.
+// Replaces HashEncoder.forward (hash_encoding.py:146-170) and its autograd (16 x embedding_dense_backward).
+//
+// Mapping (both directions): CTA = 128 consecutive points x all levels, 256 threads; thread (p, g) owns
+// point p and the levels l = g, g+2, ...  A warp is 32 CONSECUTIVE points -- when the caller is the
+// volume renderer these are consecutive samples of one ray, which share cells on the coarse levels
+// (SURVEY appendix C): the forward gathers coalesce into few L1 lines and the backward merges runs of
+// equal cells with shuffles before issuing one red.global.add.v2.f32 per distinct entry.
+// Rows of y / dy cross shared memory so global traffic is full 128-byte lines.
+#include "common.cuh"
+
+namespace hbr {
+
+constexpr int kTilePts = 128;
+constexpr int kHashThreads = 256;
+
+template <int F> struct FeatVec;
+template <> struct FeatVec<1> { using type = float; };
+template <> struct FeatVec<2> { using type = float2; };
+template <> struct FeatVec<4> { using type = float4; };
+
+template <int F>
+__device__ __forceinline__ void load_feat(const float* __restrict__ base, uint32_t idx, float v[F]) {
+  if (F == 1) {
+    v[0] = __ldg(base + idx);
+  } else if (F == 2) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(base) + idx);
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(base) + idx);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+}
+
+template <int F>
+__device__ __forceinline__ void red_feat(float* base, uint32_t idx, const float v[F]) {
+  if (F == 1) {
+    atomicAdd(base + idx, v[0]);
+  } else if (F == 2) {
+    atomicAdd(reinterpret_cast<float2*>(base) + idx, make_float2(v[0], v[1]));      // red.global.add.v2.f32
+  } else {
+    atomicAdd(reinterpret_cast<float4*>(base) + idx, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+template <typename XT>
+__device__ __forceinline__ void load_point(const XT* __restrict__ x, long long gp, long long n, float p[3]) {
+  if (gp < n) {
+    p[0] = load_coord(x + gp * 3 + 0);
+    p[1] = load_coord(x + gp * 3 + 1);
+    p[2] = load_coord(x + gp * 3 + 2);
+  } else {
+    p[0] = p[1] = p[2] = 0.f;
+  }
+}
+
+// ---- forward ------------------------------------------------------------------------------------------
+template <int F, bool POW2, typename XT>
+__global__ void __launch_bounds__(kHashThreads)
+hash_fwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__ table, float* __restrict__ y,
+                long long y_stride, const __grid_constant__ HashGeom g) {
+  extern __shared__ float tile[];                    // [kTilePts][pitch]
+  const int C = g.L * F;
+  const int pitch = C | 1;                           // odd pitch: conflict-free column writes
+  const int p = threadIdx.x & (kTilePts - 1);
+  const int grp = threadIdx.x >> 7;
+  const long long base = (long long)blockIdx.x * kTilePts;
+  float pt[3];
+  load_point(x, base + p, n, pt);
+
+#pragma unroll 2
+  for (int l = grp; l < g.L; l += 2) {
+    const float s = g.scale[l];
+    long long ix, iy, iz;
+    float fx, fy, fz;
+    cell_of(pt[0], g.mu[0], g.sigma, s, ix, fx);
+    cell_of(pt[1], g.mu[1], g.sigma, s, iy, fy);
+    cell_of(pt[2], g.mu[2], g.sigma, s, iz, fz);
+    uint32_t idx[8];
+    corner_indices<POW2>(ix, iy, iz, g.T, idx);
+    const float* lvl = table + (size_t)l * g.T * F;
+    float v[8][F];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) load_feat<F>(lvl, idx[c], v[c]);          // 8 independent gathers in flight
+    float w[8];
+    corner_weights(fx, fy, fz, w);
+    // sum over corners in index order, multiply and add rounded separately (hash_encoding.py:144)
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      float acc = __fmul_rn(v[0][f], w[0]);
+#pragma unroll
+      for (int c = 1; c < 8; ++c) acc = __fadd_rn(acc, __fmul_rn(v[c][f], w[c]));
+      tile[p * pitch + l * F + f] = acc;
+    }
+  }
+  __syncthreads();
+  const int cols = C + g.E;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < kTilePts; r += kHashThreads / 32) {
+    const long long gp = base + r;
+    if (gp >= n) break;
+    for (int c = lane; c < cols; c += 32) y[gp * y_stride + c] = c < C ? tile[r * pitch + c] : 0.f;
+  }
+}
+
+// ---- backward -----------------------------------------------------------------------------------------
+template <int F, bool POW2, typename XT>
+__global__ void __launch_bounds__(kHashThreads)
+hash_bwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__ dy, long long dy_stride,
+                float* __restrict__ dtable, const __grid_constant__ HashGeom g) {
+  extern __shared__ float tile[];
+  const int C = g.L * F;
+  const int pitch = C | 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long base = (long long)blockIdx.x * kTilePts;
+  for (int r = warp; r < kTilePts; r += kHashThreads / 32) {
+    const long long gp = base + r;
+    for (int c = lane; c < C; c += 32) tile[r * pitch + c] = gp < n ? __ldg(dy + gp * dy_stride + c) : 0.f;
+  }
+  const int p = threadIdx.x & (kTilePts - 1);
+  const int grp = threadIdx.x >> 7;
+  const bool valid = base + p < n;
+  float pt[3];
+  load_point(x, base + p, n, pt);
+  __syncthreads();
+
+  for (int l = grp; l < g.L; l += 2) {
+    const float s = g.scale[l];
+    long long ix, iy, iz;
+    float fx, fy, fz;
+    cell_of(pt[0], g.mu[0], g.sigma, s, ix, fx);
+    cell_of(pt[1], g.mu[1], g.sigma, s, iy, fy);
+    cell_of(pt[2], g.mu[2], g.sigma, s, iz, fz);
+    float w[8];
+    corner_weights(fx, fy, fz, w);
+    float gy[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) gy[f] = tile[p * pitch + l * F + f];
+    float val[8][F];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int f = 0; f < F; ++f) val[c][f] = w[c] * gy[f];
+
+    // Runs of consecutive lanes in the same cell (a ray crosses a cell in one contiguous stretch).
+    const long long pix = __shfl_up_sync(kFull, ix, 1);
+    const long long piy = __shfl_up_sync(kFull, iy, 1);
+    const long long piz = __shfl_up_sync(kFull, iz, 1);
+    const int pvalid = __shfl_up_sync(kFull, (int)valid, 1);
+    const bool head = lane == 0 || !valid || !pvalid || pix != ix || piy != iy || piz != iz;
+    const unsigned heads = __ballot_sync(kFull, head);
+    if (heads != kFull) {
+      const unsigned above = lane == 31 ? 0u : (heads & (0xfffffffeu << lane));
+      const int end = above ? (__ffs(above) - 1) : 32;                    // first lane of the next run
+      const int maxrun = __reduce_max_sync(kFull, head ? end - lane : 0);
+      for (int d = 1; d < maxrun; d <<= 1) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            const float t = __shfl_down_sync(kFull, val[c][f], d);
+            if (lane + d < end) val[c][f] += t;
+          }
+      }
+    }
+    if (head && valid) {
+      uint32_t idx[8];
+      corner_indices<POW2>(ix, iy, iz, g.T, idx);
+      float* lvl = dtable + (size_t)l * g.T * F;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) red_feat<F>(lvl, idx[c], val[c]);
+    }
+  }
+}
+
+// ---- parity probe: indices and weights ------------------------------------------------------------------
+template <bool POW2, typename XT>
+__global__ void hash_idx_kernel(const XT* __restrict__ x, long long n, int32_t* __restrict__ idx_out,
+                                float* __restrict__ w_out, const __grid_constant__ HashGeom g) {
+  const long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = blockIdx.y;
+  if (gp >= n) return;
+  float pt[3];
+  load_point(x, gp, n, pt);
+  long long ix, iy, iz;
+  float fx, fy, fz;
+  const float s = g.scale[l];
+  cell_of(pt[0], g.mu[0], g.sigma, s, ix, fx);
+  cell_of(pt[1], g.mu[1], g.sigma, s, iy, fy);
+  cell_of(pt[2], g.mu[2], g.sigma, s, iz, fz);
+  uint32_t idx[8];
+  corner_indices<POW2>(ix, iy, iz, g.T, idx);
+  float w[8];
+  corner_weights(fx, fy, fz, w);
+  const size_t o = ((size_t)l * n + gp) * 8;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (idx_out) idx_out[o + c] = (int32_t)idx[c];
+    if (w_out) w_out[o + c] = w[c];
+  }
+}
+
+static int check_geom(const hbr_hash_geom* g) {
+  HBR_REQUIRE(g != nullptr, "geom is NULL");
+  HBR_REQUIRE(g->L >= 1 && g->L <= HBR_MAX_LEVELS, "L=%d out of range [1,%d]", g->L, HBR_MAX_LEVELS);
+  HBR_REQUIRE(g->F == 1 || g->F == 2 || g->F == 4, "F=%d unsupported (1, 2 or 4)", g->F);
+  HBR_REQUIRE(g->T >= 1 && g->T <= (1u << 30), "T=%u out of range", g->T);
+  HBR_REQUIRE(g->E >= 0, "E=%d negative", g->E);
+  return HBR_OK;
+}
+
+template <int F, bool POW2, typename XT>
+static int launch_fwd(const void* x, int64_t n, const float* table, const HashGeom& g, float* y, int64_t ys, cudaStream_t st) {
+  const size_t smem = (size_t)kTilePts * ((g.L * F) | 1) * sizeof(float);
+  HBR_CUDA(cudaFuncSetAttribute(hash_fwd_kernel<F, POW2, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  hash_fwd_kernel<F, POW2, XT><<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(
+      static_cast<const XT*>(x), n, table, y, ys, g);
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
+template <int F, bool POW2, typename XT>
+static int launch_bwd(const void* x, int64_t n, const float* dy, int64_t ds, const HashGeom& g, float* dt, cudaStream_t st) {
+  const size_t smem = (size_t)kTilePts * ((g.L * F) | 1) * sizeof(float);
+  HBR_CUDA(cudaFuncSetAttribute(hash_bwd_kernel<F, POW2, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  hash_bwd_kernel<F, POW2, XT><<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(
+      static_cast<const XT*>(x), n, dy, ds, dt, g);
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
+
+#define HBR_DISPATCH_HASH(FN, ...)                                                             \
+  do {                                                                                         \
+    const bool p2 = is_pow2(g.T);                                                              \
+    const bool h = x_dtype == HBR_F16;                                                         \
+    switch (g.F) {                                                                             \
+      case 1:                                                                                  \
+        return p2 ? (h ? FN<1, true, __half>(__VA_ARGS__) : FN<1, true, float>(__VA_ARGS__))   \
+                  : (h ? FN<1, false, __half>(__VA_ARGS__) : FN<1, false, float>(__VA_ARGS__)); \
+      case 2:                                                                                  \
+        return p2 ? (h ? FN<2, true, __half>(__VA_ARGS__) : FN<2, true, float>(__VA_ARGS__))   \
+                  : (h ? FN<2, false, __half>(__VA_ARGS__) : FN<2, false, float>(__VA_ARGS__)); \
+      default:                                                                                 \
+        return p2 ? (h ? FN<4, true, __half>(__VA_ARGS__) : FN<4, true, float>(__VA_ARGS__))   \
+                  : (h ? FN<4, false, __half>(__VA_ARGS__) : FN<4, false, float>(__VA_ARGS__)); \
+    }                                                                                          \
+  } while (0)
+
+}  // namespace hbr
+
+using namespace hbr;
+
+extern "C" int hbr_hash_encode_fwd(const void* x, int x_dtype, int64_t n, const float* table,
+                                   const hbr_hash_geom* geom, float* y, int64_t y_stride, void* stream) {
+  if (int rc = check_geom(geom)) return rc;
+  HBR_REQUIRE(x_dtype == HBR_F32 || x_dtype == HBR_F16, "x_dtype %d", x_dtype);
+  HBR_REQUIRE(n >= 0 && n < (1LL << 40), "n=%lld", (long long)n);
+  if (n == 0) return HBR_OK;
+  HBR_REQUIRE(x && table && y, "NULL pointer");
+  HBR_REQUIRE(y_stride >= geom->L * geom->F + geom->E, "y_stride %lld too small", (long long)y_stride);
+  HBR_REQUIRE((uintptr_t)table % 16 == 0, "table must be 16-byte aligned");
+  const HashGeom g = to_device_geom(*geom);
+  HBR_DISPATCH_HASH(launch_fwd, x, n, table, g, y, y_stride, as_stream(stream));
+}
+
+extern "C" int hbr_hash_encode_bwd(const void* x, int x_dtype, int64_t n, const float* dy, int64_t dy_stride,
+                                   const hbr_hash_geom* geom, float* dtable, void* stream) {
+  if (int rc = check_geom(geom)) return rc;
+  HBR_REQUIRE(x_dtype == HBR_F32 || x_dtype == HBR_F16, "x_dtype %d", x_dtype);
+  HBR_REQUIRE(n >= 0 && n < (1LL << 40), "n=%lld", (long long)n);
+  if (n == 0) return HBR_OK;
+  HBR_REQUIRE(x && dy && dtable, "NULL pointer");
+  HBR_REQUIRE(dy_stride >= geom->L * geom->F, "dy_stride %lld too small", (long long)dy_stride);
+  HBR_REQUIRE((uintptr_t)dtable % 16 == 0, "dtable must be 16-byte aligned");
+  const HashGeom g = to_device_geom(*geom);
+  HBR_DISPATCH_HASH(launch_bwd, x, n, dy, dy_stride, g, dtable, as_stream(stream));
+}
+
+extern "C" int hbr_hash_indices(const void* x, int x_dtype, int64_t n, const hbr_hash_geom* geom,
+                                int32_t* idx, float* w, void* stream) {
+  if (int rc = check_geom(geom)) return rc;
+  HBR_REQUIRE(x_dtype == HBR_F32 || x_dtype == HBR_F16, "x_dtype %d", x_dtype);
+  if (n == 0) return HBR_OK;
+  HBR_REQUIRE(x && (idx || w), "NULL pointer");
+  const HashGeom g = to_device_geom(*geom);
+  const dim3 grid((unsigned)ceil_div(n, 256), g.L);
+  cudaStream_t st = as_stream(stream);
+  const bool p2 = is_pow2(g.T);
+  if (x_dtype == HBR_F16) {
+    if (p2) hash_idx_kernel<true, __half><<<grid, 256, 0, st>>>((const __half*)x, n, idx, w, g);
+    else hash_idx_kernel<false, __half><<<grid, 256, 0, st>>>((const __half*)x, n, idx, w, g);
+  } else {
+    if (p2) hash_idx_kernel<true, float><<<grid, 256, 0, st>>>((const float*)x, n, idx, w, g);
+    else hash_idx_kernel<false, float><<<grid, 256, 0, st>>>((const float*)x, n, idx, w, g);
+  }
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}

@@ -1,0 +1,279 @@
+"""Tensor-level wrappers over the C ABI (include/hbr.h) and the autograd glue.
+
+Everything here takes CUDA tensors and raises on anything else -- there is no CPU path.
+The wrappers allocate outputs/scratch with torch (caching allocator, current stream) and pass raw
+pointers; the native library never allocates.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+HAS_TC = False   # flipped on once csrc/mlp_tc.cu is linked in
+
+from ._lib import HBR_F16, HBR_F32, HashGeom, MlpDims, check, lib, ptr, require_cuda, stream
+
+
+# ------------------------------------------------------------------------------------------------------
+# geometry helpers
+# ------------------------------------------------------------------------------------------------------
+def make_geom(mu, sigma, scales: Sequence[float], L: int, F: int, T: int, E: int = 0) -> HashGeom:
+    g = HashGeom()
+    for i in range(3):
+        g.mu[i] = float(mu[i])
+    g.sigma = float(sigma)
+    g.L, g.F, g.E, g.T = int(L), int(F), int(E), int(T)
+    for i in range(L):
+        g.scale[i] = float(scales[i])
+    return g
+
+
+def _xdtype(x: torch.Tensor) -> int:
+    if x.dtype == torch.float32:
+        return HBR_F32
+    if x.dtype == torch.float16:
+        return HBR_F16
+    raise TypeError(f"positions must be float32 or float16, got {x.dtype}")
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------
+# hash grid
+# ------------------------------------------------------------------------------------------------------
+def hash_encode_fwd(x: torch.Tensor, table: torch.Tensor, geom: HashGeom) -> torch.Tensor:
+    require_cuda(x, table)
+    x = x.contiguous()
+    n = x.shape[0]
+    cols = geom.L * geom.F + geom.E
+    y = torch.empty((n, cols), device=x.device, dtype=torch.float32)
+    check(lib().hbr_hash_encode_fwd(ptr(x), _xdtype(x), n, ptr(table), C.byref(geom), ptr(y), cols, stream()))
+    return y
+
+
+def hash_encode_bwd(x: torch.Tensor, dy: torch.Tensor, geom: HashGeom, dtable: torch.Tensor) -> None:
+    """dtable (L,T,F) fp32 is accumulated into."""
+    require_cuda(x, dy, dtable)
+    x = x.contiguous()
+    dy = _f32c(dy)
+    check(lib().hbr_hash_encode_bwd(ptr(x), _xdtype(x), x.shape[0], ptr(dy), dy.stride(0), C.byref(geom), ptr(dtable),
+                                    stream()))
+
+
+def hash_indices(x: torch.Tensor, geom: HashGeom, want_w: bool = True):
+    require_cuda(x)
+    x = x.contiguous()
+    n = x.shape[0]
+    idx = torch.empty((geom.L, n, 8), device=x.device, dtype=torch.int32)
+    w = torch.empty((geom.L, n, 8), device=x.device, dtype=torch.float32) if want_w else None
+    check(lib().hbr_hash_indices(ptr(x), _xdtype(x), n, C.byref(geom), ptr(idx), ptr(w), stream()))
+    return idx, w
+
+
+# ------------------------------------------------------------------------------------------------------
+# direction encoding, sample positions, occupancy
+# ------------------------------------------------------------------------------------------------------
+def dir_encode(d: torch.Tensor, num_freq: int) -> torch.Tensor:
+    require_cuda(d)
+    d = d.contiguous()
+    n, dim = d.shape
+    out = torch.empty((n, dim * 2 * num_freq), device=d.device, dtype=torch.float32)
+    check(lib().hbr_dir_encode(ptr(d), _xdtype(d), n, dim, num_freq, ptr(out), stream()))
+    return out
+
+
+def ray_points(rays_o: torch.Tensor, rays_d: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    require_cuda(rays_o, rays_d, t)
+    rays_o, rays_d, t = _f32c(rays_o), _f32c(rays_d), _f32c(t)
+    R = rays_o.shape[0]
+    S = t.shape[-1]
+    pts = torch.empty((R, S, 3), device=rays_o.device, dtype=torch.float32)
+    check(lib().hbr_ray_points(ptr(rays_o), ptr(rays_d), ptr(t), 0 if t.dim() == 1 else S, R, S, ptr(pts), stream()))
+    return pts
+
+
+def occupancy_mask(pts: torch.Tensor, grid: torch.Tensor, mu, sigma: float) -> torch.Tensor:
+    require_cuda(pts, grid)
+    pts = _f32c(pts)
+    n = pts.numel() // 3
+    mask = torch.empty(pts.shape[:-1], device=pts.device, dtype=torch.bool)
+    mu3 = (C.c_float * 3)(*[float(v) for v in mu])
+    check(lib().hbr_occupancy_mask(ptr(pts), n, ptr(grid), grid.shape[0], mu3, float(sigma), ptr(mask), stream()))
+    return mask
+
+
+# ------------------------------------------------------------------------------------------------------
+# compositing / hierarchical sampling
+# ------------------------------------------------------------------------------------------------------
+def _dn_args(dir_norm, R, device):
+    if torch.is_tensor(dir_norm):
+        if dir_norm.numel() == 1:
+            return None, float(dir_norm)
+        dn = _f32c(dir_norm.reshape(-1))
+        if dn.shape[0] != R:
+            raise ValueError(f"dir_norm has {dn.shape[0]} rows, expected {R}")
+        return dn.to(device), 1.0
+    return None, float(dir_norm)
+
+
+def composite_fwd(t, rgb, rgb_stride, sigma, sigma_stride, dir_norm, mask, R, S, want_w=True):
+    dn, dns = _dn_args(dir_norm, R, t.device)
+    Cc = torch.empty((R, 3), device=t.device, dtype=torch.float32)
+    w = torch.empty((R, S), device=t.device, dtype=torch.float32) if want_w else None
+    check(lib().hbr_composite_fwd(ptr(t), 0 if t.dim() == 1 else S, ptr(rgb), rgb_stride, ptr(sigma), sigma_stride,
+                                  ptr(dn), dns, ptr(mask), R, S, ptr(Cc), ptr(w), stream()))
+    return Cc, w
+
+
+def composite_bwd(t, rgb, rgb_stride, sigma, sigma_stride, dir_norm, mask, R, S, gC, drgb, drgb_stride, dsig, dsig_stride):
+    dn, dns = _dn_args(dir_norm, R, t.device)
+    check(lib().hbr_composite_bwd(ptr(t), 0 if t.dim() == 1 else S, ptr(rgb), rgb_stride, ptr(sigma), sigma_stride,
+                                  ptr(dn), dns, ptr(mask), R, S, ptr(gC), ptr(drgb), drgb_stride, ptr(dsig), dsig_stride,
+                                  stream()))
+
+
+class CompositePacked(torch.autograd.Function):
+    """calc_color on the MLP's packed (R*S,4) [rgb,sigma] output -> (C (R,3), w (R,S)); w carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, out4, t, dir_norm, mask, R, S):
+        require_cuda(out4, t)
+        out4 = _f32c(out4)
+        t = _f32c(t)
+        Cc, w = composite_fwd(t, out4, 4, out4[:, 3:], 4, dir_norm, mask, R, S)
+        ctx.save_for_backward(out4, t, dir_norm if torch.is_tensor(dir_norm) else None, mask)
+        ctx.dn_scalar = None if torch.is_tensor(dir_norm) else dir_norm
+        ctx.RS = (R, S)
+        ctx.mark_non_differentiable(w)
+        return Cc, w
+
+    @staticmethod
+    def backward(ctx, gC, _gw):
+        out4, t, dn, mask = ctx.saved_tensors
+        dn = dn if dn is not None else ctx.dn_scalar
+        R, S = ctx.RS
+        d4 = torch.empty_like(out4)
+        composite_bwd(t, out4, 4, out4[:, 3:], 4, dn, mask, R, S, _f32c(gC), d4, 4, d4[:, 3:], 4)
+        return d4, None, None, None, None, None
+
+
+class CompositeSplit(torch.autograd.Function):
+    """calc_color on separate rgb (R,S,3) / sigma (R,S) tensors (the free-function API of helper.py)."""
+
+    @staticmethod
+    def forward(ctx, rgb, sigma, t, dir_norm, mask):
+        require_cuda(rgb, sigma, t)
+        rgb, sigma, t = _f32c(rgb), _f32c(sigma), _f32c(t)
+        R, S = sigma.shape
+        Cc, w = composite_fwd(t, rgb, 3, sigma, 1, dir_norm, mask, R, S)
+        ctx.save_for_backward(rgb, sigma, t, dir_norm if torch.is_tensor(dir_norm) else None, mask)
+        ctx.dn_scalar = None if torch.is_tensor(dir_norm) else dir_norm
+        ctx.mark_non_differentiable(w)
+        return Cc, w
+
+    @staticmethod
+    def backward(ctx, gC, _gw):
+        rgb, sigma, t, dn, mask = ctx.saved_tensors
+        dn = dn if dn is not None else ctx.dn_scalar
+        R, S = sigma.shape
+        drgb = torch.empty_like(rgb)
+        dsig = torch.empty_like(sigma)
+        composite_bwd(t, rgb, 3, sigma, 1, dn, mask, R, S, _f32c(gC), drgb, 3, dsig, 1)
+        return drgb, dsig, None, None, None
+
+
+def hier_sample(w: torch.Tensor, t: torch.Tensor, u: torch.Tensor, cand: torch.Tensor, clamp_in_place=False) -> torch.Tensor:
+    require_cuda(w, t, u, cand)
+    R, S = w.shape
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    t, u, cand = _f32c(t), _f32c(u), _f32c(cand)
+    tf = torch.empty((R, 2 * S), device=w.device, dtype=torch.float32)
+    check(lib().hbr_hier_sample(ptr(w), ptr(t), ptr(u), ptr(cand), R, S, 1 if clamp_in_place else 0, ptr(tf), stream()))
+    return tf
+
+
+# ------------------------------------------------------------------------------------------------------
+# MLP (fp32 CUDA-core path)
+# ------------------------------------------------------------------------------------------------------
+def mlp_act_rows() -> int:
+    return int(lib().hbr_mlp_act_floats())
+
+
+def mlp_fwd_f32(feat, dirs, dir_group, params, dims: MlpDims, keep_act: bool):
+    require_cuda(feat, params)
+    feat = _f32c(feat)
+    n = feat.shape[0]
+    out = torch.empty((n, 4 if dirs is not None else 1), device=feat.device, dtype=torch.float32)
+    act = torch.empty((mlp_act_rows(), n), device=feat.device, dtype=torch.float32) if keep_act else None
+    check(lib().hbr_mlp_fwd_f32(ptr(feat), feat.stride(0), ptr(dirs), dir_group, n, ptr(params), C.byref(dims), ptr(out),
+                                ptr(act), stream()))
+    return out, act
+
+
+def mlp_bwd_f32(feat, dirs, dir_group, params, dims: MlpDims, dout, act, want_dfeat, want_ddirs, dparams):
+    n = feat.shape[0]
+    dz = torch.empty_like(act)
+    dfeat = torch.empty((n, dims.in0), device=feat.device, dtype=torch.float32) if want_dfeat else None
+    ddirs = torch.zeros_like(dirs) if want_ddirs else None
+    check(lib().hbr_mlp_bwd_f32(ptr(feat), feat.stride(0), ptr(dirs), dir_group, n, ptr(params), C.byref(dims), ptr(dout),
+                                ptr(act), ptr(dz), ptr(dfeat), dims.in0, ptr(ddirs), ptr(dparams), stream()))
+    return dfeat, ddirs
+
+
+# ------------------------------------------------------------------------------------------------------
+# density grid + marching cubes
+# ------------------------------------------------------------------------------------------------------
+def grid_points(min_bound, max_bound, res: int, p0: int, count: int, device) -> torch.Tensor:
+    mn = (C.c_double * 3)(*[float(v) for v in min_bound])
+    mx = (C.c_double * 3)(*[float(v) for v in max_bound])
+    pts = torch.empty((count, 3), device=device, dtype=torch.float16)
+    with torch.cuda.device(pts.device):
+        check(lib().hbr_grid_points(mn, mx, res, p0, count, ptr(pts), stream()))
+    return pts
+
+
+def grid_density(min_bound, max_bound, res, p0, count, table, geom, params, dims, dir_enc, chunk=1 << 20):
+    require_cuda(table, params)
+    mn = (C.c_double * 3)(*[float(v) for v in min_bound])
+    mx = (C.c_double * 3)(*[float(v) for v in max_bound])
+    chunk = max(1, min(chunk, count))
+    dev = table.device
+    out = torch.empty((count, 4) if dir_enc is not None else (count,), device=dev, dtype=torch.float32)
+    pts = torch.empty((chunk, 3), device=dev, dtype=torch.float16)
+    feat = torch.empty((chunk, dims.in0), device=dev, dtype=torch.float32)
+    check(lib().hbr_grid_density(mn, mx, res, p0, count, ptr(table), C.byref(geom), ptr(params), C.byref(dims),
+                                 ptr(dir_enc), ptr(out), ptr(pts), ptr(feat), chunk, stream()))
+    return out
+
+
+def mc_count(density: torch.Tensor, iso: float, i_begin: int = 0, i_end: Optional[int] = None):
+    require_cuda(density)
+    density = _f32c(density)
+    n0, n1, n2 = density.shape
+    i_end = n0 if i_end is None else i_end
+    counts = torch.zeros(2, device=density.device, dtype=torch.int64)
+    check(lib().hbr_mc_count(ptr(density), n0, n1, n2, float(iso), i_begin, i_end, ptr(counts), stream()))
+    return counts
+
+
+def mc_emit(density: torch.Tensor, iso: float, n_verts: int, n_faces: int):
+    require_cuda(density)
+    density = _f32c(density)
+    n0, n1, n2 = density.shape
+    dev = density.device
+    edge_id = torch.empty((3, n0, n1, n2), device=dev, dtype=torch.int32)
+    verts = torch.empty((max(n_verts, 1), 3), device=dev, dtype=torch.float32)
+    faces = torch.empty((max(n_faces, 1), 3), device=dev, dtype=torch.int32)
+    cursors = torch.zeros(2, device=dev, dtype=torch.int64)
+    check(lib().hbr_mc_emit(ptr(density), n0, n1, n2, float(iso), 0, n0, ptr(edge_id), ptr(verts), n_verts, ptr(faces),
+                            n_faces, ptr(cursors), stream()))
+    return verts[:n_verts], faces[:n_faces], cursors

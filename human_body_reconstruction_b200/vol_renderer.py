@@ -1,0 +1,182 @@
+"""Drop-in for the reference's vol_renderer.py: `Volume_Renderer` (vol_renderer.py:88-245).
+
+`vol_render(model, rays_d, rays_o, num_samples, t, update_mask, dir_norm, hierarchical) -> (Cr, Cf, norm)`
+(note: rays_d BEFORE rays_o, as in the reference).  When the position encoder is the native `HashEncoder`,
+the direction encoder the native `PositionalEncoder` and the model the native `MLP_3D` (optionally inside
+`nn.DataParallel` on one device), the whole pass runs on the sm_100a kernels: sample positions, occupancy
+lookup, hash encode, field MLP (one direction row per RAY instead of the reference's S-fold repeat),
+compositing and the hierarchical resampler.  Any other callable falls back to the reference's data flow
+(encode -> model(rays[mask], dirs[mask]) -> scatter) with only sampling/compositing on our kernels.
+The legacy classic-NeRF MLP class (vol_renderer.py:12-86) is not part of the hot path and is not provided.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .encoder import PositionalEncoder
+from .hash_encoding import HashEncoder
+from .helper import calc_color, hierarchical_sampling, strat_sampler
+from .test_hash import MLP_3D
+
+
+def _unwrap(model):
+    if isinstance(model, nn.DataParallel) and len(model.device_ids) <= 1:
+        return model.module
+    return model
+
+
+class Volume_Renderer:
+    def __init__(self, H, W, K, near=0., far=1., device=None, Pos_encode=None, Dir_encode=None, max_dim=1024,
+                 sigma_val=torch.as_tensor(1), mu=torch.as_tensor(0), use_sdf: Optional[bool] = False,
+                 var_model: Optional[nn.Module] = None):
+        self.H, self.W, self.K = H, W, K
+        self.near, self.far = near, far
+        self.device = device
+        if device is None:
+            self.device = "cuda" if torch.cuda.is_available() else "cpu"
+        self.coods_x, self.coords_y = torch.meshgrid(torch.arange(W, device=self.device), torch.arange(H, device=self.device),
+                                                     indexing="xy")
+        self.Pos_encode = Pos_encode
+        self.Dir_encode = Dir_encode
+        self.grid_size = max_dim // 4
+        g = self.grid_size
+        self.bool_grid = torch.ones((g, g, g), device=self.device, dtype=torch.bool)      # vol_renderer.py:107
+        self.sigma_val = sigma_val.to(self.device)
+        self.mu = mu.to(self.device)
+        self.epislon = 1e-5
+        self.tmp_arr = torch.zeros((g, g, g), device=self.device, dtype=torch.int8)
+        self.reset_mask = False
+        self.use_sdf = use_sdf
+        self.var_model = var_model
+        self._grid_state = (None, True)           # (bool_grid._version, all_true)
+        self._host_norm = None
+
+    # -- occupancy grid (vol_renderer.py:116-140) --------------------------------------------------------------
+    def update_grid(self, points: torch.Tensor, alpha: torch.Tensor):
+        points = (points - self.mu) / self.sigma_val
+        points = (points * self.grid_size).long()
+        alpha[alpha <= 0] = 0
+        self.tmp_arr[points[..., 0], points[..., 1], points[..., 2]] += torch.ceil(alpha).int()
+        if torch.sum(self.tmp_arr > 0) == 0:
+            self.bool_grid[...] = True
+        else:
+            self.bool_grid[self.tmp_arr > 0] = True
+        self.tmp_arr[self.tmp_arr > 0] = 0
+
+    def _norm_host(self):
+        if self._host_norm is None:
+            mu = self.mu.detach().reshape(-1).float().cpu().tolist()
+            if len(mu) == 1:
+                mu = mu * 3
+            self._host_norm = (mu, float(self.sigma_val.detach().cpu()))
+        return self._host_norm
+
+    def get_mask(self, points: torch.Tensor) -> torch.Tensor:
+        mu, sig = self._norm_host()
+        return ops.occupancy_mask(points, self.bool_grid, mu, sig)
+
+    def _grid_all_true(self) -> bool:
+        ver = self.bool_grid._version
+        if self._grid_state[0] != (ver, self.bool_grid.data_ptr()):
+            self._grid_state = ((ver, self.bool_grid.data_ptr()), bool(self.bool_grid.all()))   # one sync per grid edit
+        return self._grid_state[1]
+
+    # -- the hot path ----------------------------------------------------------------------------------------
+    def _native(self, model):
+        m = _unwrap(model)
+        ok = (isinstance(self.Pos_encode, HashEncoder) and isinstance(self.Dir_encode, PositionalEncoder)
+              and isinstance(m, MLP_3D) and m._native and not m.use_sdf and not self.use_sdf)
+        return m if ok else None
+
+    def _field_pass(self, mlp, rays_o, rays_d, t, dir_enc, dir_norm, mask_needed):
+        """positions -> encoder -> MLP -> compositing for depths t ((S,) shared or (R,S) per ray)."""
+        R, S = rays_o.shape[0], t.shape[-1]
+        pts = ops.ray_points(rays_o, rays_d, t).view(-1, 3)
+        mask = self.get_mask(pts) if mask_needed else None
+        feat = self.Pos_encode(pts)
+        out4 = mlp.field(feat, dir_enc, S)
+        Cc, w = ops.CompositePacked.apply(out4, t, dir_norm, mask, R, S)
+        return Cc, w
+
+    def vol_render(self, model, rays_d: torch.Tensor, rays_o: torch.Tensor, num_samples=100,
+                   t: Optional[torch.Tensor] = None, update_mask=False, dir_norm=1, hierarchical=True,
+                   _u=None, _u_cand=None) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+        if not rays_d.is_cuda:
+            raise RuntimeError("Volume_Renderer.vol_render needs CUDA tensors (there is no CPU fallback)")
+        near, far = self.near, self.far
+        device = "cuda"
+        if t is None:
+            t = strat_sampler(near, far, num_samples, device=rays_d.device)                 # RNG draw #1
+        mlp = self._native(model)
+        if mlp is None:
+            return self._generic(model, rays_d, rays_o, t, update_mask, dir_norm, hierarchical, _u, _u_cand)
+
+        rays_o = rays_o.float().contiguous()
+        rays_d = rays_d.float().contiguous()
+        dir_enc = self.Dir_encode(rays_d)                                                      # (R, 2*3*num_freq), once per ray
+        if update_mask is True:
+            if self.reset_mask is True:                                                        # vol_renderer.py:201-203
+                self.bool_grid[...] = False
+                self.reset_mask = False
+            mask_needed = False
+        else:
+            mask_needed = not self._grid_all_true()
+        Cr, w = self._field_pass(mlp, rays_o, rays_d, t, dir_enc, dir_norm, mask_needed)
+        if hierarchical is True:
+            _, t_fine = hierarchical_sampling(rays_o, rays_d, z_vals=t, weights=w, n_samples=t.shape[-1], tn=near, tf=far,
+                                              device=device, _u=_u, _u_cand=_u_cand)           # RNG draws #2, #3
+            Cf, _ = self._field_pass(mlp, rays_o, rays_d, t_fine, dir_enc, dir_norm, False)    # the fine pass never masks (:237)
+        else:
+            Cf = Cr
+        return Cr, Cf, None
+
+    def _generic(self, model, rays_d, rays_o, t, update_mask, dir_norm, hierarchical, _u, _u_cand):
+        """Reference data flow for foreign encoders / models (vol_renderer.py:165-245)."""
+        Pos_encode, Dir_encode = self.Pos_encode, self.Dir_encode
+        if Pos_encode is None:
+            raise ValueError("ERROR: No positional encoding")                               # :191-192
+        num_samples = t.shape[-1]
+
+        def run(tt, masked):
+            pts = ops.ray_points(rays_o, rays_d, tt)
+            R, S = pts.shape[0], pts.shape[1]
+            flat = pts.reshape(-1, 3)
+            dirs = rays_d[..., None, :].repeat(1, S, 1).reshape(-1, 3)
+            enc = Pos_encode(flat)
+            enc = enc.reshape(enc.shape[0], -1)
+            if Dir_encode is not None:
+                dirs = Dir_encode(dirs)
+                dirs = dirs.reshape(dirs.shape[0], -1)
+            if masked:
+                mask = self.get_mask(flat)
+                mo = model(enc[mask], dirs[mask])
+                sigma = torch.zeros((R * S, 1), device=flat.device, dtype=mo.dtype)
+                rgb = torch.zeros((R * S, 3), device=flat.device, dtype=mo.dtype)
+                sigma[mask] = mo[..., 3:4]
+                rgb[mask] = mo[..., 0:3]
+            else:
+                mo = model(enc, dirs)
+                sigma, rgb = mo[..., 3:4], mo[..., 0:3]
+            return calc_color(t=tt, rgb=rgb.reshape(R, S, -1), sigma=sigma.reshape(R, S), dir_norm=dir_norm,
+                              use_sdf=self.use_sdf, var_model=self.var_model, rays=flat, model=model, encoder=Pos_encode)
+
+        if update_mask is True and self.reset_mask is True:
+            self.bool_grid[...] = False
+            self.reset_mask = False
+        Cr, wts, norm = run(t, update_mask is not True)
+        if hierarchical is True:
+            _, t_fine = hierarchical_sampling(rays_o, rays_d, z_vals=t, weights=wts, n_samples=num_samples, tn=self.near,
+                                              tf=self.far, _u=_u, _u_cand=_u_cand)
+            Cf, _, norm = run(t_fine, False)
+        else:
+            Cf = Cr
+        return Cr, Cf, norm
+
+
+def make_batch(in_rays: torch.Tensor, batch_size: int) -> list:
+    """vol_renderer.py:249-256."""
+    return [in_rays[i:i + batch_size].to("cpu") for i in range(0, in_rays.shape[0], batch_size)]

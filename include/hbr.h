@@ -1,0 +1,169 @@
+/*
+ * hbr.h -- C ABI of libhbr_b200.so: the B200 (sm_100a) implementation of the NeRF hot path of
+ * RishabhSri14/Human-Body-Reconstruction.
+ *
+ * The reference is pure Python; the binding a maintainer adds on the reference side is a ctypes
+ * stub.  Every entry point replaces one reference interface, cited as
+ * file:line into the reference tree.  Conventions:
+ *   - plain C: raw pointers + sizes, no torch / C++ types in any signature;
+ *   - pointers are DEVICE pointers unless the parameter name ends in _host; the library never
+ *     allocates, frees or synchronises: callers own every buffer (PyTorch caching allocator) and
+ *     pass the stream (cudaStream_t as void*) the work is enqueued on;
+ *   - return 0 on success, a negative hbr_status otherwise; hbr_last_error() gives the message
+ *     (thread local).  Nothing throws, nothing exits.  There is no CPU fallback: calling without a
+ *     CUDA device returns HBR_ERR_CUDA;
+ *   - entry points are re-entrant and stateless (safe on different devices/streams concurrently).
+ */
+#ifndef HBR_B200_H_
+#define HBR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HBR_ABI_VERSION 1
+#define HBR_MAX_LEVELS 32
+
+typedef enum {
+  HBR_OK = 0,
+  HBR_ERR_ARG = -1,       /* bad argument (shape, alignment, unsupported configuration) */
+  HBR_ERR_CUDA = -2,      /* CUDA runtime error (message holds cudaGetErrorString) */
+  HBR_ERR_UNSUPPORTED = -3
+} hbr_status;
+
+typedef enum { HBR_F32 = 0, HBR_F16 = 1 } hbr_dtype;
+
+/* Geometry of a HashEncoder instance: hash_encoding.py:6-39.
+ * scale[l] = N_min * b**l is computed by the HOST with the reference's torch expression
+ * (hash_encoding.py:13,153) and handed over; the kernels never recompute it. */
+typedef struct {
+  float mu[3];                    /* bbox minimum, hash_encoding.py:21 / train_hash2.py:117 */
+  float sigma;                    /* bbox diagonal (scalar), hash_encoding.py:20 / train_hash2.py:119 */
+  int32_t L;                      /* levels */
+  int32_t F;                      /* features per entry: 1, 2 or 4 */
+  int32_t E;                      /* extra zero columns appended to the output, hash_encoding.py:148 */
+  uint32_t T;                     /* entries per level (any T; power-of-two takes the uint32 fast path) */
+  float scale[HBR_MAX_LEVELS];
+} hbr_hash_geom;
+
+/* Shape of MLP_3D(num_sig=2, num_col=2, h_size=64): test_hash.py:21-51.
+ * Parameters live in ONE flat fp32 buffer in state_dict order:
+ *   sig_model.0.{weight(64,in0),bias(64)} sig_model.2.{(64,64),(64)} sig_model.4.{(16,64),(16)}
+ *   col_model.0.{(64,15+d_view),(64)}     col_model.2.{(64,64),(64)} col_model.4.{(3,64),(3)}      */
+typedef struct {
+  int32_t in0;                    /* L*F+E, <= 64 */
+  int32_t d_view;                 /* direction-encoding width, 15+d_view <= 64 */
+} hbr_mlp_dims;
+
+int hbr_abi_version(void);
+const char* hbr_last_error(void);
+/* number of floats in the flat MLP parameter buffer for these dims */
+int64_t hbr_mlp_param_count(const hbr_mlp_dims* dims);
+/* floats per point of the activation / pre-activation-gradient scratch used by the fp32 MLP */
+int64_t hbr_mlp_act_floats(void);
+
+/* ---- a2/a3/a4: HashEncoder.forward, hash_encoding.py:146-170 ------------------------------------
+ * x: (n,3) row-major, fp32 or fp16 (nerf2mesh.py:40 feeds fp16).  table: (L,T,F) fp32.
+ * y: n rows of L*F+E floats, row pitch y_stride floats. */
+int hbr_hash_encode_fwd(const void* x, int x_dtype, int64_t n, const float* table,
+                        const hbr_hash_geom* geom_host, float* y, int64_t y_stride, void* stream);
+
+/* a5: autograd of the above (16 x embedding_dense_backward): dtable[l,h,:] += w * dy[:, lF:(l+1)F].
+ * dtable (L,T,F) fp32 is ACCUMULATED into (caller zeroes it). */
+int hbr_hash_encode_bwd(const void* x, int x_dtype, int64_t n, const float* dy, int64_t dy_stride,
+                        const hbr_hash_geom* geom_host, float* dtable, void* stream);
+
+/* Parity probe: the hash indices hash_encoding.py:161-162 computes (hash_func, :41-55), and the
+ * n-linear weights of :142-143.  idx: (L,n,8) int32, w: (L,n,8) fp32 (either may be NULL). */
+int hbr_hash_indices(const void* x, int x_dtype, int64_t n, const hbr_hash_geom* geom_host,
+                     int32_t* idx, float* w, void* stream);
+
+/* ---- a6: PositionalEncoder.forward, encoder.py:25-32 ---------------------------------------------
+ * d: (n,dim) -> out (n, dim*2*num_freq) fp32: per component sin(2 d k), k<num_freq, then cos.
+ * With x_dtype = HBR_F16 the intermediate products and the result are rounded to fp16 like the
+ * reference's fp16 tensor ops (nerf2mesh.py:69-81), then widened. */
+int hbr_dir_encode(const void* d, int d_dtype, int64_t n, int dim, int num_freq, float* out, void* stream);
+
+/* ---- a7: MLP_3D.forward / backward in fp32 (CUDA cores), test_hash.py:52-77 ----------------------
+ * feat (n,in0) pitch feat_stride; dirs (n_dirs_rows, d_view): row index = point / dir_group, so one
+ * row per ray serves its S samples (vol_renderer.py:177-183 repeats it; dir_group = S) -- pass
+ * dir_group = 1 for a per-point tensor.  dirs == NULL gives the density-only branch (test_hash.py:77).
+ * out (n,4) = [rgb, density]  (or (n,1) density when dirs == NULL).
+ * act: optional (hbr_mlp_act_floats(), n) scratch that keeps the activations for the backward pass. */
+int hbr_mlp_fwd_f32(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
+                    const float* params, const hbr_mlp_dims* dims, float* out, float* act, void* stream);
+
+/* dout (n,4).  dparams (flat, same layout as params) is ACCUMULATED into.  dfeat (n,in0) and
+ * ddirs (n/dir_group, d_view; accumulated with atomics, caller zeroes; may be NULL) are written.
+ * act is the buffer hbr_mlp_fwd_f32 filled; dz is scratch of the same size. */
+int hbr_mlp_bwd_f32(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
+                    const float* params, const hbr_mlp_dims* dims, const float* dout, const float* act,
+                    float* dz, float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams, void* stream);
+
+/* ---- a9: sample positions, vol_renderer.py:165 / helper.py:48 -------------------------------------
+ * pts[r,s,:] = o[r,:] + d[r,:]*t  (separate multiply and add).  t is (S) shared (t_ray_stride = 0)
+ * or (R,S) per ray (t_ray_stride = S). */
+int hbr_ray_points(const float* rays_o, const float* rays_d, const float* t, int64_t t_ray_stride,
+                   int64_t R, int64_t S, float* pts, void* stream);
+
+/* a9: Volume_Renderer.get_mask, vol_renderer.py:133-140: mask[p] = grid[((p-mu)/sigma*G).long()],
+ * negative cells wrap (Python indexing).  grid: G^3 bytes (torch.bool). */
+int hbr_occupancy_mask(const float* pts, int64_t n, const uint8_t* grid, int G, const float* mu3_host,
+                       float sigma, uint8_t* mask, void* stream);
+
+/* ---- a10: calc_color (NeRF mode), helper.py:53-107, and its backward ------------------
+ * One warp per ray.  rgb/sigma are addressed as rgb[(r*S+s)*rgb_stride + c], sigma[(r*S+s)*sigma_stride]
+ * so both the reference's separate (R,S,3)/(R,S) tensors (strides 3,1) and the MLP's packed (R*S,4)
+ * output (rgb = out, sigma = out+3, strides 4,4) are accepted.  dir_norm: (R) or NULL (=> scalar).
+ * mask: optional (R*S) bytes; masked-out samples contribute sigma = rgb = 0 (vol_renderer.py:213-216).
+ * C (R,3), w (R,S). */
+int hbr_composite_fwd(const float* t, int64_t t_ray_stride, const float* rgb, int64_t rgb_stride,
+                      const float* sigma, int64_t sigma_stride, const float* dir_norm, float dir_norm_scalar,
+                      const uint8_t* mask, int64_t R, int64_t S, float* C, float* w, void* stream);
+int hbr_composite_bwd(const float* t, int64_t t_ray_stride, const float* rgb, int64_t rgb_stride,
+                      const float* sigma, int64_t sigma_stride, const float* dir_norm, float dir_norm_scalar,
+                      const uint8_t* mask, int64_t R, int64_t S, const float* gC,
+                      float* drgb, int64_t drgb_stride, float* dsigma, int64_t dsigma_stride, void* stream);
+
+/* ---- a11: hierarchical_sampling, helper.py:23-51 --------------------------------------------------
+ * w (R,S) coarse weights (negatives treated as 0; written back clamped when clamp_in_place != 0,
+ * helper.py:36), t (S) coarse depths, u (R,S) uniforms (draw #2), cand (S) candidate depths
+ * rand(S)*(tf-tn)+tn (draw #3, helper.py:43).  t_fine (R,2S): sorted merge of t and cand[inds]. */
+int hbr_hier_sample(float* w, const float* t, const float* u, const float* cand, int64_t R, int64_t S,
+                    int clamp_in_place, float* t_fine, void* stream);
+
+/* ---- a13: nerf2mesh.py:27-40,69-86 density grid -----------------------------------------------------
+ * Grid point p = (i*res + j)*res + k  <->  (x[j], y[i], z[k]) with x,y,z = np.linspace(min,max,res)
+ * evaluated in float64 (numpy 1.23 semantics, Nerf.yml:119) and rounded to fp16 (nerf2mesh.py:31-40).
+ * hbr_grid_points writes the fp16 positions of flat range [p0, p0+count) as (count,3) halfs. */
+int hbr_grid_points(const double* min3_host, const double* max3_host, int res, int64_t p0, int64_t count,
+                    void* pts_f16, void* stream);
+/* Evaluates the field on [p0, p0+count) in chunks: fp16 positions -> fp32 encoder -> fp32 MLP with the
+ * single encoded view direction dir_enc (1, d_view) = PositionalEncoder((0,0,1) fp16) (nerf2mesh.py:69-70,81).
+ * out: count rows of 4 floats [rgb, density]; with dir_enc == NULL, count floats (density only).
+ * pts_scratch: (chunk,3) halfs, feat_scratch: (chunk, L*F+E) floats.  z-slab / multi-GPU sharding = one
+ * [p0, p0+count) range per rank. */
+int hbr_grid_density(const double* min3_host, const double* max3_host, int res, int64_t p0, int64_t count,
+                     const float* table, const hbr_hash_geom* geom_host, const float* params,
+                     const hbr_mlp_dims* dims, const float* dir_enc, float* out, void* pts_scratch,
+                     float* feat_scratch, int64_t chunk, void* stream);
+
+/* ---- a14: marching cubes at iso over density (n0,n1,n2) fp32, inside test d < iso -------------------
+ * Cells i in [i_begin, i_end) along axis 0 (slab ownership for multi-GPU).  counts[0] = vertices
+ * (grid edges owned by the slab whose end points straddle iso), counts[1] = triangles.  counts is a
+ * 2 x uint64 device buffer the caller zeroes. */
+int hbr_mc_count(const float* density, int n0, int n1, int n2, float iso, int i_begin, int i_end,
+                 unsigned long long* counts, void* stream);
+/* Emits welded vertices (grid-index coordinates, axis order 0,1,2) and triangles.  edge_id is a
+ * (3, n0, n1, n2) int32 scratch.  cursors: 2 x uint64 device counters the caller zeroes. verts has
+ * room for max_verts x 3 floats, faces for max_faces x 3 int32. */
+int hbr_mc_emit(const float* density, int n0, int n1, int n2, float iso, int i_begin, int i_end,
+                int32_t* edge_id, float* verts, int64_t max_verts, int32_t* faces, int64_t max_faces,
+                unsigned long long* cursors, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HBR_B200_H_ */

@@ -315,10 +315,12 @@ def get_od(H: int, W: int, K: torch.Tensor, c2w: torch.Tensor):
     return rays_o, rays_d / n, n
 
 
-def bounding_box(c2ws: torch.Tensor, H, W, K, near: float, far: float):
-    """find_bounding_box (helper.py:109-141): bbox of ray points at depths {near, far+1.5}.
+def bounding_box(c2ws: torch.Tensor, K, near: float, far: float):
+    """find_bounding_box (helper.py:109-141): bbox of ray points at depths {near, far+1.5}; the image
+    size is re-derived as W=2*K[0,2], H=2*K[1,2] from the (integer) principal point (:114-115).
     Returns (max_bound, min_bound) like the reference."""
     t = torch.tensor([near, far + 1.5], dtype=torch.float64)
+    W, H = 2 * K[0, 2], 2 * K[1, 2]
     o, d, _ = get_od(H, W, K, c2ws)
     pts = (o[..., None, :] + d[..., None, :] * t[None, :, None]).reshape(-1, 3)
     return pts.max(0).values.to(torch.float32), pts.min(0).values.to(torch.float32)

@@ -1,0 +1,352 @@
+"""GPU parity tests (-m gpu): the sm_100a kernels, called through the C ABI (ctypes -> libhbr_b200.so), against
+(a) the committed outputs of the reference (tests/golden) and (b) oracle/port.py on seeded inputs.
+
+Tolerances (BASELINE.json north_star): hash indices bit-exact; features / colours / gradients 1e-5 relative in
+fp32; 1e-2 for the bf16 tensor-core MLP.  Scatter-add gradients are compared norm-wise (float atomics reorder
+sums)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, mlp_params
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def hbr():
+    import human_body_reconstruction_b200 as h
+    return h
+
+
+def make_encoder(g, E=0):
+    h = hbr()
+    L, T, F = g["tables"].shape
+    enc = h.HashEncoder(N_min=int(g["n_min"]) if "n_min" in g else 16, N_max=float(g["n_max"]) if "n_max" in g else 2048.0,
+                        L=L, F=F, T=T, E=E, dim=3, mu=g["mu"].to(DEV), sigma=g["sigma"].to(DEV))
+    enc.load_state_dict({f"Embedding_list.{i}.weight": g["tables"][i] for i in range(L)})
+    return enc.to(DEV)
+
+
+def make_mlp(params):
+    h = hbr()
+    m = h.MLP_3D(num_sig=2, num_col=2, L=16, F=2, d_view=24, max_bound=torch.ones(3), min_bound=-torch.ones(3))
+    m.load_state_dict(params)
+    return m.to(DEV)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["pow2", "npow2"])
+def test_hash_golden(tag):
+    g = load_golden(f"hash_{tag}.npz")
+    enc = make_encoder(g)
+    assert enc.level_scales() == [float(s) for s in g["scales"]]
+    x = g["x"].to(DEV)
+    idx, w = enc.hash_indices(x)
+    assert torch.equal(idx.cpu().long(), g["idx"]), "hash indices must be bit-exact"
+    y = enc(x)
+    assert torch.allclose(y.cpu(), g["y"], rtol=1e-5, atol=1e-7)
+    y16 = enc(x.half())
+    assert torch.allclose(y16.cpu(), g["y_from_f16"], rtol=1e-5, atol=1e-7)
+    y.backward(g["dy"].to(DEV))
+    grad = torch.stack([e.weight.grad for e in enc.Embedding_list]).cpu()
+    assert rel(grad, g["dtables"]) < 1e-5
+    # per-entry check against the fp64 oracle accumulation
+    _, oi, ow = port.hash_encode(g["x"], g["tables"], g["mu"], g["sigma"], g["scales"], return_aux=True)
+    g64 = port.hash_encode_bwd(g["dy"], oi, ow, g["tables"].shape[1], g["tables"].shape[2])
+    assert torch.allclose(grad.double(), g64, rtol=1e-4, atol=1e-5 * float(g64.abs().max()))
+
+
+def test_hash_extra_columns_and_empty():
+    g = load_golden("hash_pow2.npz")
+    enc = make_encoder(g, E=3)
+    y = enc(g["x"].to(DEV))
+    assert y.shape == (257, 35) and torch.count_nonzero(y[:, 32:]) == 0
+    assert torch.allclose(y[:, :32].cpu(), g["y"], rtol=1e-5, atol=1e-7)
+    assert enc(torch.zeros((0, 3), device=DEV)).shape == (0, 35)
+
+
+@pytest.mark.parametrize("T,F", [(2 ** 14, 2), (2 ** 12, 4), (5000, 1), (2 ** 19, 2)])
+def test_hash_vs_oracle_random(T, F):
+    h = hbr()
+    torch.manual_seed(T + F)
+    L, N = 16, 3000
+    mu, sigma = torch.tensor([-4.27, -4.31, -3.95]), torch.tensor(13.66)
+    enc = h.HashEncoder(N_min=16, N_max=2048.0, L=L, F=F, T=T, dim=3, mu=mu.to(DEV), sigma=sigma.to(DEV))
+    with torch.no_grad():
+        for e in enc.Embedding_list:
+            e.weight.copy_(torch.randn(T, F))
+    tables = torch.stack([e.weight.detach().clone() for e in enc.Embedding_list])
+    enc = enc.to(DEV)
+    # points laid out as rays (consecutive samples share cells -> exercises the run-merging scatter)
+    o = torch.tensor([0.3, -0.2, 4.0]) + 0.05 * torch.randn(30, 3)
+    d = torch.nn.functional.normalize(-o + 0.4 * torch.randn(30, 3), dim=-1)
+    t = torch.linspace(2, 6, 100)
+    x = (o[:, None, :] + d[:, None, :] * t[None, :, None]).reshape(-1, 3)
+    scales = port.level_scales(16, 2048.0, L)
+    y_ref, oi, ow = port.hash_encode(x, tables, mu, sigma, scales, return_aux=True)
+    idx, w = enc.hash_indices(x.to(DEV))
+    assert torch.equal(idx.cpu().long(), oi)
+    assert torch.allclose(w.cpu(), ow, rtol=1e-6, atol=1e-7)
+    y = enc(x.to(DEV))
+    assert torch.allclose(y.cpu(), y_ref, rtol=1e-5, atol=1e-6)
+    dy = torch.randn_like(y_ref)
+    y.backward(dy.to(DEV))
+    grad = torch.stack([e.weight.grad for e in enc.Embedding_list]).cpu()
+    g64 = port.hash_encode_bwd(dy, oi, ow, T, F)
+    assert rel(grad, g64) < 1e-5
+    assert N == x.shape[0]
+
+
+def test_hash_full_size_properties():
+    """BASELINE config 2 size (4096 rays x 128 samples, T=2^19): size-independent invariants.
+    corner weights sum to 1  =>  (i) an all-ones table encodes to all-ones, (ii) sum_h dtable[l,h,f] = sum_p dy[p,lF+f]."""
+    h = hbr()
+    L, F, T, R, S = 16, 2, 2 ** 19, 4096, 128
+    mu, sigma = torch.tensor([-4.27, -4.31, -3.95], device=DEV), torch.tensor(13.66, device=DEV)
+    enc = h.HashEncoder(N_min=16, N_max=2048.0, L=L, F=F, T=T, dim=3, mu=mu, sigma=sigma).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    o = torch.tensor([0.0, 0.0, 4.03], device=DEV) + 0.3 * torch.randn(R, 3, device=DEV, generator=g)
+    d = torch.nn.functional.normalize(-o + 0.8 * torch.randn(R, 3, device=DEV, generator=g), dim=-1)
+    t = torch.linspace(2, 6, S, device=DEV)
+    x = h.ops.ray_points(o, d, t).view(-1, 3)
+    with torch.no_grad():
+        for e in enc.Embedding_list:
+            e.weight.fill_(1.0)
+    y = enc(x)
+    assert y.shape == (R * S, 32)
+    assert float((y - 1).abs().max()) < 1e-5
+    dy = torch.randn(R * S, 32, device=DEV, generator=g)
+    y.backward(dy)
+    grad = torch.stack([e.weight.grad for e in enc.Embedding_list])          # (L,T,F)
+    lhs = grad.double().sum(dim=1).reshape(-1)
+    rhs = dy.double().sum(dim=0)
+    assert float((lhs - rhs).abs().max()) < 1e-5 * float(dy.double().abs().sum(dim=0).max()) + 1e-3
+    # linearity of the scatter: backward(2*dy) == 2*backward(dy)
+    for e in enc.Embedding_list:
+        e.weight.grad = None
+    enc(x).backward(2 * dy)
+    grad2 = torch.stack([e.weight.grad for e in enc.Embedding_list])
+    assert rel(grad2, 2 * grad) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_dir_encode():
+    g = load_golden("dir.npz")
+    h = hbr()
+    pe = h.PositionalEncoder(3, 4)
+    out = pe(g["d"].to(DEV))
+    assert out.shape == (96, 24)
+    assert torch.allclose(out.cpu(), g["enc"], rtol=1e-5, atol=2e-7)
+    out16 = pe(g["d"].half().to(DEV))
+    assert out16.dtype == torch.float16
+    assert torch.allclose(out16.float().cpu(), g["enc_from_f16"], rtol=0, atol=1e-3)
+
+
+def test_mlp_fp32_golden():
+    g = load_golden("mlp.npz")
+    m = make_mlp(mlp_params(g))
+    feat = g["feat"].to(DEV).requires_grad_()
+    dirs = g["dirs"].to(DEV).requires_grad_()
+    out = m(feat, dirs)
+    assert torch.allclose(out.cpu(), g["out"], rtol=1e-5, atol=1e-6)
+    with torch.no_grad():
+        assert torch.allclose(m(g["feat"].to(DEV)).cpu(), g["density_only"], rtol=1e-5, atol=1e-6)
+    out.backward(g["dout"].to(DEV))
+    assert rel(feat.grad, g["dfeat"]) < 1e-5
+    assert rel(dirs.grad, g["ddirs"]) < 1e-5
+    for k, p in m.named_parameters():
+        assert rel(p.grad, g["grad__" + k.replace(".", "__")]) < 1e-5, k
+
+
+def test_mlp_fp32_vs_oracle_grouped_dirs():
+    """One direction row per ray (dir_group = S) must equal the reference's S-fold repeated directions."""
+    torch.manual_seed(3)
+    p = port.mlp_init(seed=5)
+    m = make_mlp(p)
+    R, S = 37, 19
+    feat = torch.randn(R * S, 32)
+    dirs = port.dir_encode(torch.nn.functional.normalize(torch.randn(R, 3), dim=-1), 4)
+    pr = {k: v.clone().requires_grad_() for k, v in p.items()}
+    ref = port.mlp_forward(pr, feat, dirs[:, None, :].repeat(1, S, 1).reshape(R * S, -1))
+    f = feat.to(DEV).requires_grad_()
+    out = m.field(f, dirs.to(DEV), S, use_tc=False)
+    assert torch.allclose(out.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
+    dout = torch.randn(R * S, 4)
+    ref.backward(dout)
+    out.backward(dout.to(DEV))
+    for k, q in m.named_parameters():
+        assert rel(q.grad, pr[k].grad) < 1e-5, k
+
+
+@pytest.mark.parametrize("name", ["composite.npz", "composite_perray.npz"])
+def test_composite_golden(name):
+    g = load_golden(name)
+    h = hbr()
+    rgb = g["rgb"].to(DEV).requires_grad_()
+    sig = g["sigma"].to(DEV).requires_grad_()
+    C, w, _ = h.helper.calc_color(t=g["t"].to(DEV), rgb=rgb, sigma=sig, dir_norm=g["dir_norm"].to(DEV))
+    assert w.shape == g["w"].shape + (1,)
+    assert torch.allclose(C.cpu(), g["C"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(w[..., 0].cpu(), g["w"], rtol=1e-5, atol=1e-7)
+    C.backward(g["gC"].to(DEV))
+    assert torch.allclose(rgb.grad.cpu(), g["drgb"], rtol=1e-5, atol=1e-7)
+    d64 = port.composite_bwd(*(g[k].double() for k in ("t", "rgb", "sigma", "dir_norm", "gC")))[1]
+    assert rel(sig.grad, d64) < 1e-5
+    assert (sig.grad.cpu()[g["sigma"] < -10] == 0).all()
+
+
+@pytest.mark.parametrize("S", [1, 31, 128, 200, 512, 700])
+def test_composite_vs_oracle_sizes(S):
+    torch.manual_seed(S)
+    h = hbr()
+    R = 50
+    t = torch.sort(2 + 4 * torch.rand(R, S), dim=-1).values
+    rgb, sig, dn, gC = torch.randn(R, S, 3), torch.randn(R, S) * 3, 1 + torch.rand(R, 1), torch.randn(R, 3)
+    C_ref, w_ref = port.composite(t, rgb, sig, dn)
+    rg, sg = rgb.to(DEV).requires_grad_(), sig.to(DEV).requires_grad_()
+    C, w, _ = h.helper.calc_color(t=t.to(DEV), rgb=rg, sigma=sg, dir_norm=dn.to(DEV))
+    assert torch.allclose(C.cpu(), C_ref, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(w[..., 0].cpu(), w_ref, rtol=1e-5, atol=1e-6)
+    C.backward(gC.to(DEV))
+    d64 = port.composite_bwd(t.double(), rgb.double(), sig.double(), dn.double(), gC.double())
+    assert rel(rg.grad, d64[0]) < 1e-5 and rel(sg.grad, d64[1]) < 1e-5
+
+
+def test_hier_sample_golden():
+    g = load_golden("hier.npz")
+    h = hbr()
+    w = g["w"].to(DEV).clone()
+    w[0, 0] = -1.0                                   # negative weights are zeroed in place (helper.py:36)
+    wr = g["w"].clone()
+    wr[0, 0] = -1.0
+    rays, tf = h.helper.hierarchical_sampling(g["rays_o"].to(DEV), g["rays_d"].to(DEV), z_vals=g["t"].to(DEV), weights=w[..., None],
+                                              n_samples=g["t"].shape[0], tn=float(g["near"]), tf=float(g["far"]),
+                                              _u=g["u_rs"].to(DEV), _u_cand=g["u_s"].to(DEV))
+    ref = port.hier_sample(wr, g["t"], g["near"], g["far"], g["u_rs"], g["u_s"])
+    assert float(w[0, 0]) == 0.0
+    mism = (tf.cpu() != ref).any(dim=-1).float().mean()
+    assert mism <= 0.05, f"{mism} of rays differ"            # cdf ulp flips only
+    assert (tf[:, 1:] >= tf[:, :-1]).all()
+    same = (tf.cpu() == ref).all(dim=-1)
+    assert torch.allclose(rays.cpu()[same], port.ray_points(g["rays_o"], g["rays_d"], ref)[same], rtol=1e-6, atol=1e-6)
+
+
+def build_renderer(g, max_dim=64):
+    h = hbr()
+    enc = make_encoder(g)
+    mlp = make_mlp(mlp_params(g, "mlp__"))
+    pe = h.PositionalEncoder(3, 4)
+    vr = h.Volume_Renderer(H=8, W=8, K=torch.eye(3), near=torch.tensor(float(g["near"])), far=torch.tensor(float(g["far"])),
+                           device=DEV, Pos_encode=enc, Dir_encode=pe, max_dim=max_dim, sigma_val=g["sigma"], mu=g["mu"])
+    return vr, enc, mlp
+
+
+@pytest.mark.parametrize("tag", ["coarse", "hier"])
+@pytest.mark.parametrize("wrap", [False, True])
+def test_vol_render_golden(tag, wrap):
+    g = load_golden("volrender.npz")
+    vr, enc, mlp = build_renderer(g)
+    model = torch.nn.DataParallel(mlp) if wrap else mlp
+    S = g[f"{tag}__u_t"].shape[0]
+    t = port.strat_t(g["near"], g["far"], S, g[f"{tag}__u_t"]).to(DEV)
+    hier = tag == "hier"
+    kw = dict(_u=g["hier__u_rs"].to(DEV), _u_cand=g["hier__u_s"].to(DEV)) if hier else {}
+    Cr, Cf, norm = vr.vol_render(model, g["rays_d"].to(DEV), g["rays_o"].to(DEV), num_samples=S, t=t, update_mask=False,
+                                 dir_norm=g["dir_norm"].to(DEV), hierarchical=hier, **kw)
+    assert norm is None
+    assert torch.allclose(Cr.cpu(), g[f"{tag}__Cr"], rtol=1e-5, atol=1e-6)
+    bad = ~torch.isclose(Cf.cpu(), g[f"{tag}__Cf"], rtol=1e-5, atol=1e-6).all(dim=-1)
+    assert bad.float().mean() <= 0.05
+    if bad.any():
+        pytest.skip("a cdf ulp flip changed a fine sample; gradient comparison not meaningful")
+    gt = g["gt"].to(DEV)
+    loss = torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)
+    assert abs(float(loss) - float(g[f"{tag}__loss"])) < 1e-5 * float(g[f"{tag}__loss"])
+    loss.backward()
+    grad = torch.stack([e.weight.grad for e in enc.Embedding_list])
+    assert rel(grad, g[f"{tag}__dtables"]) < 1e-5
+    for k, p in mlp.named_parameters():
+        assert rel(p.grad, g[f"{tag}__grad__" + k.replace(".", "__")]) < 2e-5, k
+
+
+def test_vol_render_masked_and_generic_agree():
+    """Occupancy-masked samples: the native path and the reference-style generic path give the same colours."""
+    g = load_golden("volrender.npz")
+    vr, enc, mlp = build_renderer(g, max_dim=64)
+    torch.manual_seed(0)
+    vr.bool_grid[...] = torch.rand(vr.bool_grid.shape, device=DEV) > 0.4
+    S = 24
+    t = port.strat_t(g["near"], g["far"], S, g["coarse__u_t"]).to(DEV)
+    args = (g["rays_d"].to(DEV), g["rays_o"].to(DEV))
+    Cn, _, _ = vr.vol_render(mlp, *args, num_samples=S, t=t, dir_norm=g["dir_norm"].to(DEV), hierarchical=False)
+    wrapped = lambda x, d: mlp(x, d)                        # a foreign callable -> generic path
+    Cg, _, _ = vr.vol_render(wrapped, *args, num_samples=S, t=t, dir_norm=g["dir_norm"].to(DEV), hierarchical=False)
+    assert torch.allclose(Cn, Cg, rtol=1e-5, atol=1e-6)
+    pts = port.ray_points(g["rays_o"], g["rays_d"], t.cpu()).reshape(-1, 3)
+    m_ref = port.occupancy_mask(pts, vr.bool_grid.cpu(), g["mu"], g["sigma"])
+    assert torch.equal(vr.get_mask(pts.to(DEV)).cpu(), m_ref)
+    Cr_ref, _, _ = port.vol_render(mlp_params(g, "mlp__"), g["tables"], g["mu"], g["sigma"], g["scales"], g["rays_d"], g["rays_o"],
+                                   t.cpu(), g["dir_norm"], bool_grid=vr.bool_grid.cpu())
+    assert torch.allclose(Cn.cpu(), Cr_ref, rtol=1e-5, atol=1e-6)
+
+
+def test_grid_query_golden():
+    g = load_golden("grid.npz")
+    h = hbr()
+    enc = make_encoder(g)
+    mlp = make_mlp(mlp_params(g, "mlp__"))
+    pe = h.PositionalEncoder(3, 4)
+    res = int(g["res"])
+    mn, mx = g["min_bound"].double().tolist(), g["max_bound"].double().tolist()
+    pts = h.ops.grid_points(mn, mx, res, 0, res ** 3, DEV)
+    assert torch.equal(pts.float().cpu(), g["grid_f16"]), "fp16 grid positions must be bit-exact"
+    out = h.mesh.density_grid(enc, torch.nn.DataParallel(mlp), pe, mn, mx, res, chunk=500)
+    assert torch.allclose(out.cpu(), g["out"], rtol=1e-5, atol=1e-6)
+    dens = h.mesh.density_grid(enc, mlp, None, mn, mx, res)
+    assert torch.allclose(dens.cpu(), g["out"][..., 3], rtol=1e-5, atol=1e-6)
+    slab = h.mesh.density_grid(enc, mlp, None, mn, mx, res, i_begin=5, i_end=9)
+    assert torch.equal(slab, dens[5:9])
+
+
+@pytest.mark.parametrize("shape", [(9, 8, 7), (33, 20, 41), (1, 5, 5), (64, 64, 64)])
+def test_marching_cubes_counts(shape):
+    h = hbr()
+    rng = np.random.default_rng(shape[0])
+    d = rng.normal(30, 4, size=shape).astype(np.float32)
+    iso = 30.0
+    dt = torch.from_numpy(d).to(DEV)
+    nv, nt = h.mesh.marching_cubes_counts(dt, iso)
+    assert nv == port.mc_crossing_edges(d, iso)
+    if min(shape) > 1:
+        from oracle.mc_tables import NUM_TRIS
+        assert nt == int(np.asarray(NUM_TRIS)[port.mc_case_index(d, iso)].sum())
+    # slab ownership: counts over disjoint slabs add up (multi-GPU sharding rule)
+    cuts = [0, shape[0] // 3, shape[0] // 2, shape[0]]
+    parts = [h.mesh.marching_cubes_counts(dt, iso, a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert sum(p[0] for p in parts) == nv and sum(p[1] for p in parts) == nt
+    verts, faces = h.mesh.marching_cubes(dt, iso)
+    assert verts.shape == (nv, 3) and faces.shape == (nt, 3)
+    if nt:
+        assert int(faces.min()) >= 0 and int(faces.max()) < nv
+        assert torch.unique(faces).numel() == nv                 # every welded vertex is referenced
+        # each vertex lies on its grid edge, at the iso crossing
+        v = verts.cpu().numpy()
+        frac = v - np.floor(v)
+        assert ((frac > 0).sum(axis=1) <= 1).all()
+
+
+def test_no_cpu_fallback():
+    h = hbr()
+    enc = h.HashEncoder(N_min=16, N_max=2048.0, L=2, F=2, T=64, dim=3, mu=torch.zeros(3), sigma=torch.tensor(1.0), device="cpu")
+    with pytest.raises(RuntimeError):
+        enc(torch.zeros(4, 3))
+    with pytest.raises(RuntimeError):
+        h.helper.calc_color(torch.zeros(4), torch.zeros(2, 4, 3), torch.zeros(2, 4), 1.0)

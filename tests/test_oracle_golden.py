@@ -115,7 +115,7 @@ def test_rays_and_bbox():
     g = load_golden("rays.npz")
     o, d, n = port.get_od(int(g["H"]), int(g["W"]), g["K"], g["c2w"])
     assert torch.equal(o, g["rays_o"]) and torch.equal(d, g["rays_d"]) and torch.equal(n, g["dir_norm"])
-    mx, mn = port.bounding_box(g["c2w"], int(g["H"]), int(g["W"]), g["K"], 2.0, 6.0)
+    mx, mn = port.bounding_box(g["c2w"], g["K"], 2.0, 6.0)
     assert torch.allclose(mx, g["max_bound"]) and torch.allclose(mn, g["min_bound"])
 
 
