@@ -27,7 +27,7 @@ class _MlpFn(torch.autograd.Function):
     def forward(ctx, feat, dirs, dir_group, mlp, use_tc, *params):
         flat = mlp._flat_params()
         dims = mlp._dims()
-        train = torch.is_grad_enabled() and (feat.requires_grad or dirs.requires_grad or any(p.requires_grad for p in params))
+        train = any(ctx.needs_input_grad)
         feat = feat.float().contiguous()
         dirs = dirs.float().contiguous()
         if use_tc:

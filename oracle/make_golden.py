@@ -134,43 +134,61 @@ def gold_composite(ref):
 
 
 def gold_volrender(ref):
+    """Full vol_render + loss + backward.  ReLU / LeakyReLU kinks make the gradient discontinuous in the
+    pre-activations: a fixture with a pre-activation within rounding distance of 0 would pin an arbitrary mask
+    choice, not arithmetic.  Seeds are therefore scanned until every pre-activation of both passes is at least
+    2e-6 away from 0 (GPU/CPU pre-activations differ by ~3e-8), which makes the 1e-5 gradient tolerance of the GPU tests well-posed."""
     L, T, S, R = 16, 1024, 24, 40
-    enc, mlp, pe = build(ref, L, T, 2048.0, 13, 3e3)
-    with torch.no_grad():
-        mlp.sig_model[4].bias[0] += 1.5
     near, far = torch.tensor(2.0), torch.tensor(6.0)
-    vr = ref.vol_renderer.Volume_Renderer(H=8, W=8, K=torch.eye(3), near=near, far=far, device="cpu", Pos_encode=enc,
-                                          Dir_encode=pe, max_dim=64, sigma_val=SIGMA, mu=MU)
-    g = torch.Generator().manual_seed(8)
-    ro = torch.tensor([[0.5, -0.3, 4.0]]).repeat(R, 1) + 0.05 * torch.randn(R, 3, generator=g)
-    rd = torch.nn.functional.normalize(-ro + 0.6 * torch.randn(R, 3, generator=g), dim=-1)
-    dn = 1 + 0.2 * torch.rand(R, 1, generator=g)
-    gt = torch.rand(R, 3, generator=g)
-    kw = dict(rays_o=ro, rays_d=rd, dir_norm=dn, gt=gt, mu=MU, sigma=SIGMA, near=2.0, far=6.0,
-              tables=torch.stack([e.weight.detach().clone() for e in enc.Embedding_list]),
-              scales=torch.stack([(enc.N_min * enc.b ** i).float() for i in range(L)]))
-    kw.update({"mlp__" + k.replace(".", "__"): v.detach().clone() for k, v in mlp.state_dict().items()})
-    for hier in (False, True):
-        tag = "hier" if hier else "coarse"
-        for prm in list(enc.parameters()) + list(mlp.parameters()):
-            prm.grad = None
-        torch.manual_seed(31)
-        with ref_loader.quiet():
-            Cr, Cf, _ = vr.vol_render(mlp, rd, ro, num_samples=S, update_mask=False, dir_norm=dn, hierarchical=hier)
-        loss = torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)   # train_hash2.py:221,177
-        loss.backward()
-        torch.manual_seed(31)
-        kw[f"{tag}__u_t"] = torch.rand(S)
-        if hier:
-            kw[f"{tag}__u_rs"] = torch.rand(R, S)
-            kw[f"{tag}__u_s"] = torch.rand(S)
-        kw[f"{tag}__Cr"] = Cr.detach()
-        kw[f"{tag}__Cf"] = Cf.detach()
-        kw[f"{tag}__loss"] = loss.detach()
-        kw[f"{tag}__dtables"] = torch.stack([e.weight.grad for e in enc.Embedding_list])
-        for k, v in mlp.named_parameters():
-            kw[f"{tag}__grad__" + k.replace(".", "__")] = v.grad.clone()
-    npz("volrender.npz", **kw)
+    for seed in range(39, 400):
+        enc, mlp, pe = build(ref, L, T, 2048.0, seed, 3e3)
+        with torch.no_grad():
+            mlp.sig_model[4].bias[0] += 1.5
+        margin = [1e9]
+
+        def hook(_m, _i, out, margin=margin, idx=None):
+            margin[0] = min(margin[0], float(out.detach().abs().min()))
+        hs = [m.register_forward_hook(hook) for m in (mlp.sig_model[0], mlp.sig_model[2], mlp.col_model[0], mlp.col_model[2])]
+        hs.append(mlp.sig_model[4].register_forward_hook(lambda _m, _i, out: margin.__setitem__(0, min(margin[0], float(out.detach()[:, 0].abs().min())))))
+        vr = ref.vol_renderer.Volume_Renderer(H=8, W=8, K=torch.eye(3), near=near, far=far, device="cpu", Pos_encode=enc,
+                                              Dir_encode=pe, max_dim=64, sigma_val=SIGMA, mu=MU)
+        g = torch.Generator().manual_seed(8)
+        ro = torch.tensor([[0.5, -0.3, 4.0]]).repeat(R, 1) + 0.05 * torch.randn(R, 3, generator=g)
+        rd = torch.nn.functional.normalize(-ro + 0.6 * torch.randn(R, 3, generator=g), dim=-1)
+        dn = 1 + 0.2 * torch.rand(R, 1, generator=g)
+        gt = torch.rand(R, 3, generator=g)
+        kw = dict(rays_o=ro, rays_d=rd, dir_norm=dn, gt=gt, mu=MU, sigma=SIGMA, near=2.0, far=6.0, seed=seed,
+                  tables=torch.stack([e.weight.detach().clone() for e in enc.Embedding_list]),
+                  scales=torch.stack([(enc.N_min * enc.b ** i).float() for i in range(L)]))
+        kw.update({"mlp__" + k.replace(".", "__"): v.detach().clone() for k, v in mlp.state_dict().items()})
+        for hier in (False, True):
+            tag = "hier" if hier else "coarse"
+            for prm in list(enc.parameters()) + list(mlp.parameters()):
+                prm.grad = None
+            torch.manual_seed(31)
+            with ref_loader.quiet():
+                Cr, Cf, _ = vr.vol_render(mlp, rd, ro, num_samples=S, update_mask=False, dir_norm=dn, hierarchical=hier)
+            loss = torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)   # train_hash2.py:221,177
+            loss.backward()
+            torch.manual_seed(31)
+            kw[f"{tag}__u_t"] = torch.rand(S)
+            if hier:
+                kw[f"{tag}__u_rs"] = torch.rand(R, S)
+                kw[f"{tag}__u_s"] = torch.rand(S)
+            kw[f"{tag}__Cr"] = Cr.detach()
+            kw[f"{tag}__Cf"] = Cf.detach()
+            kw[f"{tag}__loss"] = loss.detach()
+            kw[f"{tag}__dtables"] = torch.stack([e.weight.grad for e in enc.Embedding_list])
+            for k, v in mlp.named_parameters():
+                kw[f"{tag}__grad__" + k.replace(".", "__")] = v.grad.clone()
+        for h_ in hs:
+            h_.remove()
+        if margin[0] >= 2e-6:
+            print("seed", seed, "min |pre-activation|", margin[0])
+            kw["kink_margin"] = margin[0]
+            npz("volrender.npz", **kw)
+            return
+    raise RuntimeError("no seed found")
 
 
 def gold_grid(ref):

@@ -26,6 +26,21 @@ def hbr():
     return h
 
 
+def check_composite(C, w, C_ref, w_ref, rgb):
+    """1e-5 relative to the magnitude of the terms of each ray: sigma may be negative (LeakyReLU, clamp at -10), so
+    transmittance can exceed 1 and C = sum_s w_s rgb_s cancels heavily; element-wise relative error is meaningless."""
+    C, w = C.detach().cpu(), w.detach().cpu()
+    scale = (w_ref.abs()[..., None] * rgb.abs()).sum(1)
+    assert ((C - C_ref).abs() <= 1e-5 * scale + 1e-6).all()
+    assert ((w - w_ref).abs() <= 1e-5 * w_ref.abs().max(dim=1, keepdim=True).values + 1e-7).all()
+
+
+def check_rows(a, b, tol=1e-5):
+    a, b = a.detach().double().cpu().flatten(1), b.detach().double().cpu().flatten(1)
+    err = (a - b).norm(dim=1)
+    assert (err <= tol * b.norm(dim=1) + 1e-12).all(), float((err / (b.norm(dim=1) + 1e-30)).max())
+
+
 def make_encoder(g, E=0):
     h = hbr()
     L, T, F = g["tables"].shape
@@ -194,12 +209,12 @@ def test_composite_golden(name):
     sig = g["sigma"].to(DEV).requires_grad_()
     C, w, _ = h.helper.calc_color(t=g["t"].to(DEV), rgb=rgb, sigma=sig, dir_norm=g["dir_norm"].to(DEV))
     assert w.shape == g["w"].shape + (1,)
-    assert torch.allclose(C.cpu(), g["C"], rtol=1e-5, atol=1e-6)
-    assert torch.allclose(w[..., 0].cpu(), g["w"], rtol=1e-5, atol=1e-7)
+    check_composite(C, w[..., 0], g["C"], g["w"], g["rgb"])
     C.backward(g["gC"].to(DEV))
-    assert torch.allclose(rgb.grad.cpu(), g["drgb"], rtol=1e-5, atol=1e-7)
+    check_rows(rgb.grad, g["drgb"])
     d64 = port.composite_bwd(*(g[k].double() for k in ("t", "rgb", "sigma", "dir_norm", "gC")))[1]
-    assert rel(sig.grad, d64) < 1e-5
+    check_rows(sig.grad, d64)
+    assert rel(sig.grad, g["dsigma"]) < 1e-5
     assert (sig.grad.cpu()[g["sigma"] < -10] == 0).all()
 
 
@@ -213,11 +228,11 @@ def test_composite_vs_oracle_sizes(S):
     C_ref, w_ref = port.composite(t, rgb, sig, dn)
     rg, sg = rgb.to(DEV).requires_grad_(), sig.to(DEV).requires_grad_()
     C, w, _ = h.helper.calc_color(t=t.to(DEV), rgb=rg, sigma=sg, dir_norm=dn.to(DEV))
-    assert torch.allclose(C.cpu(), C_ref, rtol=1e-5, atol=1e-5)
-    assert torch.allclose(w[..., 0].cpu(), w_ref, rtol=1e-5, atol=1e-6)
+    check_composite(C, w[..., 0], C_ref, w_ref, rgb)
     C.backward(gC.to(DEV))
     d64 = port.composite_bwd(t.double(), rgb.double(), sig.double(), dn.double(), gC.double())
-    assert rel(rg.grad, d64[0]) < 1e-5 and rel(sg.grad, d64[1]) < 1e-5
+    check_rows(rg.grad, d64[0])
+    check_rows(sg.grad, d64[1])
 
 
 def test_hier_sample_golden():
