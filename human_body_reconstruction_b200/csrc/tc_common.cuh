@@ -1,0 +1,130 @@
+// tcgen05 / TMEM / mbarrier primitives for sm_100a, written as inline PTX.
+// Shared-memory operand layout used everywhere in this library: the UMMA "no-swizzle" canonical layout.
+//   A [rows x cols] bf16 tile is stored as 8x8 "core matrices" (8 rows x 16 bytes, contiguous 128 B):
+//     byte_offset(r, c) = (c % 8) * 2 + (r % 8) * 16 + (r / 8) * 128 + (c / 8) * (rows / 8) * 128
+//   i.e. core matrices are contiguous along the row dimension, column groups of 8 are (rows*16) bytes apart.
+//   The same bytes can be handed to the tensor core in two ways:
+//     K-major  operand (rows = M|N index, cols = K index):  SBO = 128, LBO = rows*16, one K=16 step = 2*LBO
+//     MN-major operand (cols = M|N index, rows = K index):  SBO = rows*16, LBO = 128, one K=16 step = 256 B
+//   so an activation tile written once serves as the K-major A operand of the forward / dgrad GEMMs and as the
+//   MN-major operand of the weight-gradient GEMM (reduction over the point dimension) without a transpose.
+#pragma once
+#include "common.cuh"
+
+namespace hbr {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- shared memory matrix descriptor (SM100 "version 1", no swizzle) -------------------------------------------
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                      // descriptor version for tcgen05
+  return d;                                    // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+}
+
+// ---- instruction descriptor: kind::f16, bf16 x bf16 -> fp32 -------------------------------------------------------
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4)                             // D format: f32
+         | (1u << 7)                           // A format: bf16
+         | (1u << 10)                          // B format: bf16
+         | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16)
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+
+// all previously issued tcgen05.mma of this thread arrive on the mbarrier when complete
+__device__ __forceinline__ void commit(uint64_t* mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+               :: "r"(smem_u32(mbar)) : "memory");
+}
+
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// ---- TMEM allocation (one full warp executes these) --------------------------------------------------------------
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(smem_slot)), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(taddr), "n"(NCOLS) : "memory");
+}
+
+// ---- mbarrier ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* mbar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+  while (!mbar_try_wait(mbar, parity)) {
+  }
+}
+
+// ---- TMEM -> registers: this thread's lane, N consecutive 32-bit columns ------------------------------------------
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// N columns (multiple of 16) starting at taddr; issues all loads, then one wait
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v) {
+  static_assert(N % 16 == 0, "N must be a multiple of 16");
+#pragma unroll
+  for (int i = 0; i < N; i += 16) tmem_ld16(taddr + i, v + i);
+  tmem_ld_wait();
+}
+
+// ---- canonical no-swizzle tile addressing -------------------------------------------------------------------------
+// byte offset of the 16-byte chunk holding columns [8*cg, 8*cg+8) of row r in a tile with `rows` rows
+__device__ __forceinline__ uint32_t chunk_off(int r, int cg, int rows) {
+  return (uint32_t)((r & 7) * 16 + (r >> 3) * 128 + cg * rows * 16);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+
+// store 8 consecutive columns (one chunk) of this thread's row
+__device__ __forceinline__ void store_chunk(uint8_t* tile, int r, int cg, int rows, const float* v8) {
+  uint4 q;
+  q.x = pack_bf16(v8[0], v8[1]); q.y = pack_bf16(v8[2], v8[3]);
+  q.z = pack_bf16(v8[4], v8[5]); q.w = pack_bf16(v8[6], v8[7]);
+  *reinterpret_cast<uint4*>(tile + chunk_off(r, cg, rows)) = q;
+}
+
+}  // namespace tc
+}  // namespace hbr

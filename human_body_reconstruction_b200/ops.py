@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-HAS_TC = False   # flipped on once csrc/mlp_tc.cu is linked in
+HAS_TC = True    # csrc/mlp_tc.cu (tcgen05) is linked in
 
 from ._lib import HBR_F16, HBR_F32, HashGeom, MlpDims, check, lib, ptr, require_cuda, stream
 
@@ -227,6 +227,31 @@ def mlp_bwd_f32(feat, dirs, dir_group, params, dims: MlpDims, dout, act, want_df
     check(lib().hbr_mlp_bwd_f32(ptr(feat), feat.stride(0), ptr(dirs), dir_group, n, ptr(params), C.byref(dims), ptr(dout),
                                 ptr(act), ptr(dz), ptr(dfeat), dims.in0, ptr(ddirs), ptr(dparams), stream()))
     return dfeat, ddirs
+
+
+def mlp_fwd_tc(feat, dirs, dir_group, params, dims: MlpDims, keep_act: bool = False):
+    """bf16 tensor-core forward; keeps nothing (the backward recomputes), returns (out, None)."""
+    require_cuda(feat, dirs, params)
+    n = feat.shape[0]
+    out = torch.empty((n, 4), device=feat.device, dtype=torch.float32)
+    check(lib().hbr_mlp_fwd_tc(ptr(feat), feat.stride(0), ptr(dirs), dir_group, n, ptr(params), C.byref(dims), ptr(out),
+                               stream()))
+    return out, None
+
+
+def mlp_bwd_tc(feat, dirs, dir_group, params, dims: MlpDims, dout, act, want_dfeat, want_ddirs, dparams):
+    n = feat.shape[0]
+    dfeat = torch.empty((n, dims.in0), device=feat.device, dtype=torch.float32) if want_dfeat else None
+    ddirs = torch.zeros_like(dirs) if want_ddirs else None
+    check(lib().hbr_mlp_bwd_tc(ptr(feat), feat.stride(0), ptr(dirs), dir_group, n, ptr(params), C.byref(dims), ptr(dout),
+                               ptr(dfeat), dims.in0, ptr(ddirs), ptr(dparams), stream()))
+    return dfeat, ddirs
+
+
+def debug_umma(mode: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int) -> torch.Tensor:
+    D = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    check(lib().hbr_debug_umma(mode, ptr(A.contiguous()), ptr(B.contiguous()), ptr(D), N, K, stream()))
+    return D
 
 
 # ------------------------------------------------------------------------------------------------------

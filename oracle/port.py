@@ -375,3 +375,51 @@ def mc_case_index(density: np.ndarray, iso: float) -> np.ndarray:
         sl = ins[dx:dx + density.shape[0] - 1, dy:dy + density.shape[1] - 1, dz:dz + density.shape[2] - 1]
         idx |= (sl.astype(np.uint8) << v)
     return idx
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 tensor-core numerics of MLP_3D, emulated in torch (checker for csrc/mlp_tc.cu)
+# ------------------------------------------------------------------------------------------------
+def _bf(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def mlp_bf16_emulation(p: Dict[str, torch.Tensor], feat: torch.Tensor, dirs: torch.Tensor, dout: Optional[torch.Tensor] = None):
+    """MLP_3D forward (and backward when dout is given) with the tensor-core kernel's rounding points:
+    weights, layer inputs and pre-activation gradients rounded to bf16, products/accumulation/bias/activations in
+    fp32, the layer-3 vector (density + 15 features) and the outputs NOT rounded.  Returns out (N,4) and, with
+    dout, (dfeat, grads dict).  Not a reference restatement -- a numerics model of our own kernel, used to test it
+    tightly; the reference-facing tolerance (1e-2, BASELINE.json) is checked against mlp_forward."""
+    W = {k: _bf(v) if k.endswith("weight") else v for k, v in p.items()}
+    x0 = _bf(feat)
+    h1p = x0 @ W["sig_model.0.weight"].T + W["sig_model.0.bias"]
+    h1 = _bf(torch.relu(h1p))
+    h2p = h1 @ W["sig_model.2.weight"].T + W["sig_model.2.bias"]
+    h2 = _bf(torch.relu(h2p))
+    o = h2 @ W["sig_model.4.weight"].T + W["sig_model.4.bias"]
+    cin = _bf(torch.cat((o[:, 1:], dirs), dim=-1))
+    c1p = cin @ W["col_model.0.weight"].T + W["col_model.0.bias"]
+    c1 = _bf(torch.relu(c1p))
+    c2p = c1 @ W["col_model.2.weight"].T + W["col_model.2.bias"]
+    c2 = _bf(torch.relu(c2p))
+    pre = c2 @ W["col_model.4.weight"].T + W["col_model.4.bias"]
+    out = torch.cat((Fnn.elu(pre), Fnn.leaky_relu(o[:, 0:1], 0.01)), dim=-1)
+    if dout is None:
+        return out
+    g = {}
+    dz6 = _bf(dout[:, :3] * torch.where(pre > 0, torch.ones_like(pre), torch.exp(pre)))
+    g["col_model.4.weight"], g["col_model.4.bias"] = dz6.T @ c2, dz6.sum(0)
+    dz5 = _bf((dz6 @ W["col_model.4.weight"]) * (c2p > 0))
+    g["col_model.2.weight"], g["col_model.2.bias"] = dz5.T @ c1, dz5.sum(0)
+    dz4 = _bf((dz5 @ W["col_model.2.weight"]) * (c1p > 0))
+    g["col_model.0.weight"], g["col_model.0.bias"] = dz4.T @ cin, dz4.sum(0)
+    dcin = dz4 @ W["col_model.0.weight"]
+    d_o = torch.cat((dout[:, 3:4] * torch.where(o[:, 0:1] > 0, 1.0, 0.01), dcin[:, :15]), dim=-1)
+    dz3 = _bf(d_o)
+    g["sig_model.4.weight"], g["sig_model.4.bias"] = dz3.T @ h2, dz3.sum(0)
+    dz2 = _bf((dz3 @ W["sig_model.4.weight"]) * (h2p > 0))
+    g["sig_model.2.weight"], g["sig_model.2.bias"] = dz2.T @ h1, dz2.sum(0)
+    dz1 = _bf((dz2 @ W["sig_model.2.weight"]) * (h1p > 0))
+    g["sig_model.0.weight"], g["sig_model.0.bias"] = dz1.T @ x0, dz1.sum(0)
+    dfeat = dz1 @ W["sig_model.0.weight"]
+    return out, dfeat, g, dcin[:, 15:]

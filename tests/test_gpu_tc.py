@@ -1,0 +1,135 @@
+"""GPU tests (-m gpu) of the tcgen05 / TMEM MLP (csrc/mlp_tc.cu).
+
+Three layers of evidence:
+  1. the three UMMA operand modes the kernels rely on (K-major x K-major, K-major x MN-major, MN-major x MN-major
+     with M=64) reproduce a bf16-input / fp32-accumulate matmul to fp32 rounding;
+  2. the MLP kernels match a torch model of their own numerics (oracle.port.mlp_bf16_emulation: bf16 operands,
+     fp32 accumulation) tightly -- this is the "is the kernel right" test;
+  3. against the reference's fp32 arithmetic (oracle.port.mlp_forward) the outputs are within the 1e-2 the
+     north star grants the bf16 MLP.  Gradients of a ReLU network evaluated in 16-bit differ from the fp32 ones
+     mostly through activation-mask flips at pre-activations near zero (error ~ sqrt(fraction flipped)); torch's own
+     autocast shows the same (measured: bf16 autocast 5-7 %, fp16 autocast 1-2 % on this network), so the gradient
+     check against fp32 is calibrated against torch.autocast(bfloat16) evaluated on the same inputs."""
+import pytest
+import torch
+
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def bf(x):
+    return x.bfloat16().float()
+
+
+@pytest.mark.parametrize("mode,M,N,K", [(0, 128, 64, 32), (0, 128, 16, 64), (0, 128, 64, 48), (0, 128, 64, 64),
+                                        (1, 128, 64, 16), (1, 128, 48, 64), (1, 128, 32, 64), (1, 128, 64, 64),
+                                        (2, 64, 64, 128), (2, 64, 48, 128), (2, 64, 32, 128), (2, 64, 16, 128)])
+def test_umma_operand_modes(mode, M, N, K):
+    from human_body_reconstruction_b200 import ops
+    torch.manual_seed(mode * 1000 + N + K)
+    if mode == 0:
+        A, B = torch.randn(M, K), torch.randn(N, K)
+        ref = bf(A) @ bf(B).T
+    elif mode == 1:
+        A, B = torch.randn(M, K), torch.randn(K, N)
+        ref = bf(A) @ bf(B)
+    else:
+        A, B = torch.randn(K, 64), torch.randn(K, N)
+        ref = bf(A).T @ bf(B)
+    D = ops.debug_umma(mode, A.to(DEV), B.to(DEV), M, N, K)
+    assert rel(D, ref) < 1e-6
+
+
+def make(seed=5):
+    import human_body_reconstruction_b200 as h
+    p = port.mlp_init(seed=seed)
+    m = h.MLP_3D(num_sig=2, num_col=2, L=16, F=2, d_view=24, max_bound=torch.ones(3), min_bound=-torch.ones(3))
+    m.load_state_dict(p)
+    return p, m.to(DEV)
+
+
+@pytest.mark.parametrize("R,S", [(1, 1), (3, 100), (40, 24), (512, 128), (129, 7)])
+def test_mlp_tc_matches_numerics_model_and_reference(R, S):
+    torch.manual_seed(R * 1000 + S)
+    p, m = make()
+    feat = torch.randn(R * S, 32) * 0.5
+    dirs = port.dir_encode(torch.nn.functional.normalize(torch.randn(R, 3), dim=-1), 4)
+    drep = dirs[:, None, :].repeat(1, S, 1).reshape(R * S, -1)
+    dout = torch.randn(R * S, 4)
+    emu_out, emu_dfeat, emu_g, _ = port.mlp_bf16_emulation(p, feat, drep, dout)
+    pr = {k: v.clone().requires_grad_() for k, v in p.items()}
+    fr = feat.clone().requires_grad_()
+    ref = port.mlp_forward(pr, fr, drep)
+    ref.backward(dout)
+
+    f = feat.to(DEV).requires_grad_()
+    out = m.field(f, dirs.to(DEV), S, use_tc=True)
+    out.backward(dout.to(DEV))
+    # (2) kernel vs its numerics model
+    assert rel(out, emu_out) < 2e-4
+    assert rel(f.grad, emu_dfeat) < 5e-3
+    for k, q in m.named_parameters():
+        assert rel(q.grad, emu_g[k]) < 5e-3, k
+    # (3) kernel vs the reference's fp32 arithmetic
+    assert rel(out, ref) < 1e-2
+    if R * S >= 256:
+        pa = {k: v.clone().requires_grad_() for k, v in p.items()}
+        fa = feat.clone().requires_grad_()
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            oa = port.mlp_forward(pa, fa, drep)
+        oa.float().backward(dout)
+        budget = 2.0 * max(rel(fa.grad, fr.grad), 0.02)
+        assert rel(f.grad, fr.grad) < budget
+        for k, q in m.named_parameters():
+            assert rel(q.grad, pr[k].grad) < 2.0 * max(rel(pa[k].grad, pr[k].grad), 0.02), k
+
+
+def test_mlp_tc_under_autocast_is_selected_and_accumulates():
+    """Under torch.autocast the module picks the tensor-core path; ddirs and repeated backward calls accumulate."""
+    torch.manual_seed(1)
+    p, m = make()
+    R, S = 16, 32
+    feat = (torch.randn(R * S, 32) * 0.5).to(DEV).requires_grad_()
+    dirs = port.dir_encode(torch.nn.functional.normalize(torch.randn(R, 3), dim=-1), 4).to(DEV).requires_grad_()
+    from human_body_reconstruction_b200 import _lib
+    _lib.STATS.reset()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m.field(feat, dirs, S)
+    assert _lib.STATS.calls.get("hbr_mlp_fwd_tc", 0) == 1 and "hbr_mlp_fwd_f32" not in _lib.STATS.calls
+    dout = torch.randn(R * S, 4, device=DEV)
+    out.backward(dout, retain_graph=True)
+    g1 = {k: q.grad.clone() for k, q in m.named_parameters()}
+    dd1 = dirs.grad.clone()
+    out.backward(dout)
+    for k, q in m.named_parameters():
+        assert rel(q.grad, 2 * g1[k]) < 1e-5
+    assert rel(dirs.grad, 2 * dd1) < 1e-5
+    drep = dirs.detach().cpu()[:, None, :].repeat(1, S, 1).reshape(R * S, -1)
+    _, _, _, emu_dd = port.mlp_bf16_emulation(p, feat.detach().cpu(), drep, dout.cpu())
+    assert rel(dd1, emu_dd.reshape(R, S, -1).sum(1)) < 5e-3
+
+
+def test_vol_render_bf16_close_to_reference():
+    """Whole coarse+fine render under autocast: rendered colours within 1e-2 of the reference's fp32 outputs."""
+    from conftest import load_golden, mlp_params
+    from test_gpu_parity import build_renderer
+    g = load_golden("volrender.npz")
+    vr, enc, mlp = build_renderer(g)
+    S = 24
+    t = port.strat_t(g["near"], g["far"], S, g["coarse__u_t"]).to(DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        Cr, Cf, _ = vr.vol_render(mlp, g["rays_d"].to(DEV), g["rays_o"].to(DEV), num_samples=S, t=t,
+                                  dir_norm=g["dir_norm"].to(DEV), hierarchical=False)
+        loss = torch.nn.functional.mse_loss(Cr, g["gt"].to(DEV)) + torch.nn.functional.mse_loss(Cf, g["gt"].to(DEV))
+    assert rel(Cr, g["coarse__Cr"]) < 1e-2
+    assert abs(float(loss) - float(g["coarse__loss"])) < 1e-2 * float(g["coarse__loss"])
+    loss.backward()
+    grad = torch.stack([e.weight.grad for e in enc.Embedding_list])
+    assert torch.isfinite(grad).all() and rel(grad, g["coarse__dtables"]) < 0.25
