@@ -53,6 +53,17 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
+// exactly one lane of a converged warp gets true (lets ptxas keep the MMA operands on the uniform datapath)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMEM allocation (one full warp executes these) --------------------------------------------------------------
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot) {
@@ -81,6 +92,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* mbar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
   while (!mbar_try_wait(mbar, parity)) {
   }
+}
+// non-blocking probe (the MMA-issuing thread polls several barriers round-robin)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* mbar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(mbar)) : "memory");
 }
 
 // ---- TMEM -> registers: this thread's lane, N consecutive 32-bit columns ------------------------------------------
@@ -115,6 +139,19 @@ __device__ __forceinline__ uint32_t chunk_off(int r, int cg, int rows) {
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// max(x,0) fused into the conversion: low half <- lo, high half <- hi
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// dz * [h > 0] on packed bf16 pairs (h is a stored post-ReLU activation: h > 0 <=> pre-activation > 0)
+__device__ __forceinline__ uint32_t mask_pos_bf16x2(uint32_t dz, uint32_t h) {
+  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+  const __nv_bfloat162 m = __hgt2(*reinterpret_cast<const __nv_bfloat162*>(&h), zero);      // 1.0 / 0.0 per half
+  const __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&dz), m);
+  return *reinterpret_cast<const uint32_t*>(&r);
 }
 __device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
 
