@@ -2,22 +2,28 @@
 // This is the field evaluation of the training step (train_hash2.py:218-226 runs it under autocast); the fp32
 // CUDA-core version in mlp_simt.cu serves nerf2mesh and the 1e-5 parity tests.
 //
-// Structure (both kernels): one persistent CTA per SM = G "tile groups" of 128 threads + one MMA-issuing warp.
+// Structure (both kernels): one persistent CTA per SM = G "tile groups" of 128 threads + MMA-issuing warp(s).
 //   * A tile group owns one 128-point tile at a time (thread = point = TMEM lane) and walks the layer chain:
 //     it writes the next layer's bf16 A tile into shared memory, signals `full[g]` (mbarrier, 128 arrivals),
-//     waits on `done[g]`, pulls its accumulator row out of TMEM with tcgen05.ld and applies bias/activation.
-//   * Lane 0 of the MMA warp polls the G `full` barriers, issues the tcgen05.mma sequence of whichever group
-//     is ready (A = activation tile, B = weight tile, D = that group's 64 TMEM columns) and commits it to
-//     `done[g]`.  The chain of one tile is strictly serial, so throughput comes from G tiles in flight per SM:
-//     while one group waits for the tensor pipe the others run their epilogues.
-//   * Every MMA is issued by the same thread, so the weight-gradient accumulators that all tiles of a CTA share
-//     (backward) are updated in issue order.
-// Backward recomputes the forward activations in shared memory (nothing but the features is re-read from HBM),
-// then walks the layers in reverse: per layer one dgrad GEMM (dA = dZ W, B = the SAME weight tile read MN-major),
-// one weight-gradient GEMM (reduction over the 128 points, both operands read MN-major from tiles already in
-// smem) and one bias-gradient GEMM against a ones tile; the gradient accumulators stay resident in TMEM across
-// all tiles of the CTA and are flushed once with atomics.  dZ of a layer is written IN PLACE over the
-// activation tile whose consumer GEMMs have completed, so one group needs 88 KB and two groups fit an SM.
+//     waits on `done[g]`, pulls its accumulator row out of TMEM with tcgen05.ld and applies the activation.
+//   * An MMA warp waits on `full`, one elected lane issues the tcgen05.mma sequence of that layer in straight-line
+//     code (A = activation tile, B = weight tile, D = the group's 64 TMEM columns) and commits it to `done`.
+//     The chain of one tile is strictly serial (measured: ~130 cycles from commit to the waiter waking up, the rest
+//     is epilogue work and hand-off), so throughput comes from G tiles in flight per SM.
+//   * The bias rides on the tensor core too: the first MMA of every layer is ones[128x16] x biasB[Nx16]^T with
+//     biasB = (bf16(b), bf16(b - bf16(b)), 0...), i.e. the accumulator starts at b (to 2^-17 relative), which removes
+//     the bias loads/adds from the epilogues (the epilogue is tcgen05.ld -> cvt.relu.bf16x2 -> st.shared).
+// Forward: one MMA warp per tile group (independent accumulators).
+// Backward: recomputes the forward activations in shared memory (nothing but the features is re-read from HBM), then
+// walks the layers in reverse: per layer one dgrad GEMM (dA = dZ W, B = the SAME weight tile read MN-major) and one
+// weight-gradient GEMM (reduction over the 128 points, both operands read MN-major from tiles already in smem);
+// the gradient accumulators stay resident in TMEM across all tiles of the CTA and are flushed once with atomics.
+// Because all tiles of a CTA accumulate into the same TMEM columns, ONE warp issues every MMA of the CTA, visiting
+// the groups in a fixed order.  Bias gradients: a GEMM against a ones column (64-wide layers), a 1.0 planted in a
+// padding column of the colour-net input tile, or -- for the two 16-wide layers, whose gradient is accumulated
+// transposed with M = 128 -- a ones column group placed right behind the activation tile.  dZ of a layer is written
+// IN PLACE over the activation tile whose consumer GEMMs have completed.  ELU' and LeakyReLU' come from the saved
+// forward output (elu'(x) = x > 0 ? 1 : elu(x) + 1), so the last forward layer is not recomputed.
 // Layout conventions: tc_common.cuh.
 #include "mlp_layout.cuh"
 #include "tc_common.cuh"
@@ -39,10 +45,17 @@ struct WOfs {                         // byte offsets of the six bf16 weight til
   static constexpr int total = w5 + 16 * 64 * 2;
 };
 
+struct BOfs {                         // byte offsets of the six [JP x 16] bias tiles
+  __host__ __device__ static constexpr int ofs(int i) {
+    return i == 0 ? 0 : i == 1 ? 2048 : i == 2 ? 4096 : i == 3 ? 4608 : i == 4 ? 6656 : 8704;
+  }
+  static constexpr int total = 9216;
+};
+
 // fp32 (J,K) row-major weights -> bf16 canonical tile [JP rows x KP cols], zero padded; one 16-byte chunk per step
 template <int K0P, int KCP>
 __device__ __forceinline__ void stage_weights_bf16(const float* __restrict__ params, const MlpLayout& m, uint8_t* wsm,
-                                                   float* bias_sm) {
+                                                   uint8_t* bias_sm, uint8_t* ones16) {
   const int JP[6] = {64, 64, 16, 64, 64, 16};
   const int KP[6] = {K0P, 64, 64, KCP, 64, 64};
   const int wofs[6] = {WOfs<K0P, KCP>::w0, WOfs<K0P, KCP>::w1, WOfs<K0P, KCP>::w2, WOfs<K0P, KCP>::w3,
@@ -62,32 +75,62 @@ __device__ __forceinline__ void stage_weights_bf16(const float* __restrict__ par
       }
       store_chunk(w, j, cg, JP[i], v);
     }
-    for (int j = threadIdx.x; j < 64; j += blockDim.x) bias_sm[i * 64 + j] = j < J ? __ldg(params + m.b[i] + j) : 0.f;
+    // bias tile [JP x 16] (K-major B operand of the bias MMA): col 0 = bf16(b), col 1 = bf16(b - bf16(b))
+    uint8_t* bt = bias_sm + BOfs::ofs(i);
+    for (int e = threadIdx.x; e < JP[i] * 2; e += blockDim.x) {
+      const int cg = e / JP[i], j = e - cg * JP[i];
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (cg == 0 && j < J) {
+        const float b = __ldg(params + m.b[i] + j);
+        v[0] = bf16_round(b);
+        v[1] = b - v[0];
+      }
+      store_chunk(bt, j, cg, JP[i], v);
+    }
+  }
+  // ones16 [128 x 16] (A operand of the bias MMA): cols 0,1 = 1
+  for (int e = threadIdx.x; e < kTile * 2; e += blockDim.x) {
+    const int cg = e / kTile, rr = e - cg * kTile;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (cg == 0) v[0] = v[1] = 1.f;
+    store_chunk(ones16, rr, cg, kTile, v);
   }
 }
 
 // D[128 x N] (+)= A[128 x K] * W^T : A K-major activation tile, B K-major weight tile (forward)
-__device__ __forceinline__ void issue_fwd(uint32_t tmem_d, uint32_t a_tile, uint32_t w_tile, int JP, int KP) {
+__device__ __forceinline__ void issue_fwd(uint32_t tmem_d, uint32_t a_tile, uint32_t w_tile, int JP, int KP,
+                                          bool accumulate = false) {
   const uint32_t idesc = make_idesc(128, JP, false, false);
+#pragma unroll
   for (int kk = 0; kk < KP / 16; ++kk) {
     const uint64_t a = make_desc(a_tile + kk * 2 * kLBO128, kLBO128, 128);
     const uint64_t b = make_desc(w_tile + kk * 2 * JP * 16, JP * 16, 128);
-    mma_f16(tmem_d, a, b, idesc, kk > 0);
+    mma_f16(tmem_d, a, b, idesc, accumulate || kk > 0);
   }
+}
+// D[128 x JP] = b (broadcast over rows) + A W^T: the bias enters as ones16 x biasB^T
+__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_tile, uint32_t w_tile, uint32_t ones16,
+                                            uint32_t bias_tile, int JP, int KP) {
+  issue_fwd(tmem_d, ones16, bias_tile, JP, 16, false);
+  issue_fwd(tmem_d, a_tile, w_tile, JP, KP, true);
 }
 // D[128 x KP] = dZ[128 x JP] * W : A K-major dZ tile, B = weight tile [JP x KP] read MN-major (N = k, K = j)
 __device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t dz_tile, uint32_t w_tile, int JP, int KP) {
   const uint32_t idesc = make_idesc(128, KP, false, true);
+#pragma unroll
   for (int kk = 0; kk < JP / 16; ++kk) {
     const uint64_t a = make_desc(dz_tile + kk * 2 * kLBO128, kLBO128, 128);
     const uint64_t b = make_desc(w_tile + kk * 256, 128, JP * 16);
     mma_f16(tmem_d, a, b, idesc, kk > 0);
   }
 }
-// G[64 x N] += At^T[64 x 128] * Bt[128 x N]: both tiles [128 points x cols] read MN-major, reduction over points.
-// (weight gradient: At = dZ, Bt = activation; for the 16-wide layers the roles swap, giving the transposed gradient)
-__device__ __forceinline__ void issue_wgrad(uint32_t tmem_g, uint32_t a_tile, uint32_t b_tile, int N, bool accumulate) {
-  const uint32_t idesc = make_idesc(64, N, true, true);
+// G[M x N] += At^T[M x 128] * Bt[128 x N]: both tiles [128 points x cols] read MN-major, reduction over points.
+// (weight gradient: At = dZ, Bt = activation, M = 64; for the 16-wide layers the roles swap and M = 128 so that the
+//  ones column group behind the activation tile adds the bias-gradient row: transposed gradient)
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_g, uint32_t a_tile, uint32_t b_tile, int N, bool accumulate,
+                                            int M = 64) {
+  const uint32_t idesc = make_idesc(M, N, true, true);
+#pragma unroll
   for (int kk = 0; kk < kTile / 16; ++kk) {
     const uint64_t a = make_desc(a_tile + kk * 256, 128, kLBO128);
     const uint64_t b = make_desc(b_tile + kk * 256, 128, kLBO128);
@@ -195,20 +238,18 @@ __device__ __forceinline__ void load_features(const float* __restrict__ feat, lo
   }
 }
 
-// bias + ReLU on 64 accumulator columns -> bf16 activation tile (two 32-column halves to bound registers)
-__device__ __forceinline__ void relu_epilogue64(uint32_t taddr, const float* bias, int r, uint8_t* tile) {
+// ReLU on 64 accumulator columns (bias already inside) -> bf16 activation tile
+__device__ __forceinline__ void relu_epilogue64(uint32_t taddr, int r, uint8_t* tile) {
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     float v[32];
     tmem_ld<32>(taddr + half * 32, v);
 #pragma unroll
     for (int cg = 0; cg < 4; ++cg) {
-      const float4 b0 = *reinterpret_cast<const float4*>(bias + half * 32 + cg * 8);
-      const float4 b1 = *reinterpret_cast<const float4*>(bias + half * 32 + cg * 8 + 4);
       const float* p = v + cg * 8;
       uint4 o;
-      o.x = pack_bf16_relu(p[0] + b0.x, p[1] + b0.y); o.y = pack_bf16_relu(p[2] + b0.z, p[3] + b0.w);
-      o.z = pack_bf16_relu(p[4] + b1.x, p[5] + b1.y); o.w = pack_bf16_relu(p[6] + b1.z, p[7] + b1.w);
+      o.x = pack_bf16_relu(p[0], p[1]); o.y = pack_bf16_relu(p[2], p[3]);
+      o.z = pack_bf16_relu(p[4], p[5]); o.w = pack_bf16_relu(p[6], p[7]);
       *reinterpret_cast<uint4*>(tile + chunk_off(r, half * 4 + cg, kTile)) = o;
     }
   }
@@ -233,7 +274,8 @@ __device__ __forceinline__ void masked_dz_inplace64(uint32_t taddr, int r, uint8
   }
 }
 
-template <int KCP>
+// colour-net input tile: [15 features | direction encoding | (optionally a 1.0 at column 15+dv) | 0 ...]
+template <int KCP, bool PLANT_ONE>
 __device__ __forceinline__ void build_cin(const float* o16, const float* __restrict__ dirs, long long dir_row, int dv,
                                           bool valid, int r, uint8_t* cin) {
 #pragma unroll
@@ -244,14 +286,15 @@ __device__ __forceinline__ void build_cin(const float* o16, const float* __restr
       const int k = cg * 8 + i;
       float x = 0.f;
       if (k < kFeat) x = o16[1 + k];                                    // feat_vec = dens_vec[:,1:]  (test_hash.py:64)
-      else if (k < kFeat + dv && valid) x = __ldg(dirs + dir_row * dv + (k - kFeat));   // concat(viewdirs) (:66)
+      else if (k < kFeat + dv) x = valid ? __ldg(dirs + dir_row * dv + (k - kFeat)) : 0.f;   // concat(viewdirs) (:66)
+      else if (PLANT_ONE && k == kFeat + dv) x = 1.f;                   // meets a zero weight column; feeds the bias gradient
       v[i] = x;
     }
     store_chunk(cin, r, cg, kTile, v);
   }
 }
 
-// group -> MMA thread: "my A tile is written (and my TMEM reads are finished)";  MMA thread -> group: commit on done
+// group -> MMA warp: "my A tile is written (and my TMEM reads are finished)";  MMA warp -> group: commit on done
 #define HBR_SIGNAL()          \
   do {                        \
     fence_async_smem();       \
@@ -275,23 +318,25 @@ __device__ __forceinline__ long long tiles_of_slot(long long ntiles, long long s
 template <int K0P, int KCP, int G>
 struct FwdSmem {
   static constexpr int off_bias = WOfs<K0P, KCP>::total;
-  static constexpr int off_buf = off_bias + 6 * 64 * 4;
+  static constexpr int off_ones16 = off_bias + BOfs::total;
+  static constexpr int off_buf = off_ones16 + kTile * 16 * 2;
   static constexpr int buf_bytes = kTile * 64 * 2;
   static constexpr int off_bar = off_buf + G * buf_bytes;
   static constexpr int total = off_bar + 2 * G * 8 + 16;
 };
 
-template <int K0P, int KCP, int G>
-__global__ void __launch_bounds__(G * kTile + 32, 1)
+// TRACE: clock64 stamps of group 0 / its MMA warp in CTA 0 (debug entry point hbr_debug_mlp_trace; compiled out otherwise)
+template <int K0P, int KCP, int G, bool TRACE = false>
+__global__ void __launch_bounds__(G * (kTile + 32), 1)
 mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const float* __restrict__ dirs, long long dir_group,
-                  long long n, const float* __restrict__ params, int in0, int dv, float* __restrict__ out) {
+                  long long n, const float* __restrict__ params, int in0, int dv, float* __restrict__ out,
+                  long long* __restrict__ trace = nullptr) {
   using SM = FwdSmem<K0P, KCP, G>;
   using WO = WOfs<K0P, KCP>;
   constexpr int kCols = G * 64 <= 64 ? 64 : (G * 64 <= 128 ? 128 : (G * 64 <= 256 ? 256 : 512));
   extern __shared__ __align__(128) uint8_t sm[];
   const MlpLayout m = make_layout(in0, dv);
   uint8_t* wsm = sm;
-  float* bias = reinterpret_cast<float*>(sm + SM::off_bias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM::off_bar);      // full[0..G), done[0..G)
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2 * G);
   const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -301,7 +346,7 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     for (int g = 0; g < G; ++g) { mbar_init(bars + g, kTile); mbar_init(bars + G + g, 1); }
     fence_mbar_init();
   }
-  stage_weights_bf16<K0P, KCP>(params, m, wsm, bias);
+  stage_weights_bf16<K0P, KCP>(params, m, wsm, sm + SM::off_bias, sm + SM::off_ones16);
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -310,44 +355,38 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   const long long ntiles = (n + kTile - 1) / kTile;
   const long long nslots = (long long)gridDim.x * G;
 
-  if (warp == 4 * G) {
-    // ===== MMA issuer: the warp runs the loop converged (uniform control flow, operands on the uniform datapath),
-    //       one elected lane issues =====
+  if (warp >= 4 * G) {
+    // ===== MMA issuer of group g: converged warp, straight-line layer sequence, one elected lane issues =====
+    const int g = warp - 4 * G;
     const uint32_t tb = __shfl_sync(kFull, tbase, 0);
-    const uint32_t wa = smem_u32(wsm);
-    int left[G], layer[G];
-    uint32_t par[G];
-    int remaining = 0;
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      left[g] = 6 * (int)tiles_of_slot(ntiles, (long long)g * gridDim.x + blockIdx.x, nslots);
-      remaining += left[g];
-      layer[g] = 0;
-      par[g] = 0;
-    }
-    while (remaining > 0) {
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        if (left[g] > 0 && __all_sync(kFull, mbar_test_wait(bars + g, par[g]))) {
-          fence_after_sync();
-          if (elect_one()) {
-            const uint32_t d = tb + g * 64;
-            const uint32_t a = smem_u32(sm + SM::off_buf + g * SM::buf_bytes);
-            if (layer[g] == 0) issue_fwd(d, a, wa + WO::w0, 64, K0P);
-            else if (layer[g] == 1) issue_fwd(d, a, wa + WO::w1, 64, 64);
-            else if (layer[g] == 2) issue_fwd(d, a, wa + WO::w2, 16, 64);
-            else if (layer[g] == 3) issue_fwd(d, a, wa + WO::w3, 64, KCP);
-            else if (layer[g] == 4) issue_fwd(d, a, wa + WO::w4, 64, 64);
-            else issue_fwd(d, a, wa + WO::w5, 16, 64);
-            commit(bars + G + g);
-          }
-          __syncwarp();
-          layer[g] = layer[g] == 5 ? 0 : layer[g] + 1;
-          par[g] ^= 1;
-          --left[g];
-          --remaining;
-        }
-      }
+    const uint32_t wa = smem_u32(wsm), ba = smem_u32(sm + SM::off_bias), o16a = smem_u32(sm + SM::off_ones16);
+    const uint32_t d = tb + g * 64;
+    const uint32_t a = smem_u32(sm + SM::off_buf + g * SM::buf_bytes);
+    uint64_t* full = bars + g;
+    uint64_t* done = bars + G + g;
+    uint32_t par = 0;
+    int tmi = 0;
+    (void)tmi;
+#define HBR_MMA_STAGE(BODY)                                                                             \
+  do {                                                                                                  \
+    mbar_wait(full, par);                                                                               \
+    par ^= 1;                                                                                           \
+    if (TRACE && g == 0 && blockIdx.x == 0 && lane == 0 && tmi < 500) trace[1024 + tmi++] = clock64();  \
+    fence_after_sync();                                                                                 \
+    if (elect_one()) {                                                                                  \
+      BODY;                                                                                             \
+      commit(done);                                                                                     \
+    }                                                                                                   \
+    __syncwarp();                                                                                       \
+    if (TRACE && g == 0 && blockIdx.x == 0 && lane == 0 && tmi < 500) trace[1024 + tmi++] = clock64();  \
+  } while (0)
+    for (long long tile = (long long)g * gridDim.x + blockIdx.x; tile < ntiles; tile += nslots) {
+      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w0, o16a, ba + BOfs::ofs(0), 64, K0P));
+      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w1, o16a, ba + BOfs::ofs(1), 64, 64));
+      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w2, o16a, ba + BOfs::ofs(2), 16, 64));
+      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w3, o16a, ba + BOfs::ofs(3), 64, KCP));
+      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w4, o16a, ba + BOfs::ofs(4), 64, 64));
+      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w5, o16a, ba + BOfs::ofs(5), 16, 64));
     }
   } else {
     // ===== tile group =====
@@ -359,33 +398,38 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     const uint32_t taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + g * 64;
     uint32_t dphase = 0;
     const bool vec_ok = in0 == K0P && (feat_stride & 3) == 0 && ((uintptr_t)feat & 15) == 0;
+    int tgi = 0;
+    (void)tgi;
+#define TR()                                                                                  \
+  do {                                                                                        \
+    if (TRACE && blockIdx.x == 0 && threadIdx.x == 0 && tgi < 1000) trace[tgi++] = clock64(); \
+  } while (0)
     for (long long tile = (long long)g * gridDim.x + blockIdx.x; tile < ntiles; tile += nslots) {
       const long long gp = tile * kTile + r;
       const bool valid = gp < n;
+      TR();
       load_features<K0P>(feat, feat_stride, gp, n, in0, vec_ok, r, buf);
-      HBR_SIGNAL(); HBR_WAIT();
-      relu_epilogue64(taddr, bias + 0, r, buf);
-      HBR_SIGNAL(); HBR_WAIT();
-      relu_epilogue64(taddr, bias + 64, r, buf);
-      HBR_SIGNAL(); HBR_WAIT();
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
+      relu_epilogue64(taddr, r, buf);
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
+      relu_epilogue64(taddr, r, buf);
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
       float o16[16];
       tmem_ld<16>(taddr, o16);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) o16[k] += bias[128 + k];
       const float density = o16[0] > 0.f ? o16[0] : 0.01f * o16[0];     // LeakyReLU (test_hash.py:62)
-      build_cin<KCP>(o16, dirs, valid ? gp / dir_group : 0, dv, valid, r, buf);
-      HBR_SIGNAL(); HBR_WAIT();
-      relu_epilogue64(taddr, bias + 192, r, buf);
-      HBR_SIGNAL(); HBR_WAIT();
-      relu_epilogue64(taddr, bias + 256, r, buf);
-      HBR_SIGNAL(); HBR_WAIT();
+      build_cin<KCP, false>(o16, dirs, valid ? gp / dir_group : 0, dv, valid, r, buf);
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
+      relu_epilogue64(taddr, r, buf);
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
+      relu_epilogue64(taddr, r, buf);
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
       float c16[16];
       tmem_ld<16>(taddr, c16);
       if (valid) {
         float4 o;
-        o.x = elu1(c16[0] + bias[320]);                                 // ELU (test_hash.py:67)
-        o.y = elu1(c16[1] + bias[321]);
-        o.z = elu1(c16[2] + bias[322]);
+        o.x = elu1(c16[0]);                                             // ELU (test_hash.py:67)
+        o.y = elu1(c16[1]);
+        o.z = elu1(c16[2]);
         o.w = density;
         *reinterpret_cast<float4*>(out + gp * 4) = o;                   // (rgb, sigma), test_hash.py:69
       }
@@ -399,48 +443,62 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
 // ---------------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int kCg = kTile * 16;                                        // bytes of one 8-column group of a 128-row tile
+
 template <int K0P, int KCP, int G>
 struct BwdSmem {
+  // KCP == 48 (15 + d_view <= 40): column group 5 of the colour-net input tile is pure padding and doubles as the
+  // first half of the 16-wide dZ tile (its partner column group sits right behind the tile)
+  static constexpr bool kAliasDzs = KCP == 48;
   static constexpr int off_bias = WOfs<K0P, KCP>::total;
-  static constexpr int off_ones = off_bias + 6 * 64 * 4;               // [128 x 64] bf16 of 1.0
-  static constexpr int off_grp = off_ones + kTile * 64 * 2;
-  // per group
-  static constexpr int x0 = 0;
+  static constexpr int off_ones16 = off_bias + BOfs::total;
+  static constexpr int off_onesb = off_ones16 + kTile * 16 * 2;         // one column group of 1.0 (B operand, N = 8)
+  static constexpr int off_grp = off_onesb + kCg;
+  // per group; h2 and c2 are each followed by a ones column group and >= 14 KB of further tiles (M = 128 operand)
+  static constexpr int h2 = 0;
+  static constexpr int c2 = h2 + 9 * kCg;
+  static constexpr int x0 = c2 + 9 * kCg;
   static constexpr int h1 = x0 + kTile * K0P * 2;
-  static constexpr int h2 = h1 + kTile * 64 * 2;
-  static constexpr int cin = h2 + kTile * 64 * 2;
-  static constexpr int c1 = cin + kTile * KCP * 2;
-  static constexpr int c2 = c1 + kTile * 64 * 2;
-  static constexpr int dzs = c2 + kTile * 64 * 2;                      // [128 x 16] dZ of the two 16-wide layers
-  static constexpr int grp_bytes = dzs + kTile * 16 * 2;
+  static constexpr int c1 = h1 + 8 * kCg;
+  static constexpr int cin = c1 + 8 * kCg;
+  static constexpr int dzs = kAliasDzs ? cin + 5 * kCg : cin + kTile * KCP * 2;
+  static constexpr int grp_bytes = dzs + 2 * kCg;
   static constexpr int off_bar = off_grp + G * grp_bytes;
   static constexpr int total = off_bar + 2 * G * 8 + 16;
+  static_assert(total <= 232448, "shared memory budget exceeded");
 };
 
-// TMEM columns: [0, 128) two work accumulators; then the weight-gradient accumulators (64 lanes each):
-//   layers 0,1,3,4: G[j][k] (rows = output neuron, KP columns); layers 2,5 (16 outputs): transposed G^T[k][j], 16 columns
-// then the bias-gradient accumulators: 8 columns (layers 0,1,3,4), 16 columns (layers 2,5, every row equal).
+// TMEM columns: [0, 128) work accumulators of the (up to two) groups; then the gradient accumulators:
+//   layers 0,1,3,4 (M = 64): G[j][k], rows = output neuron, KP columns, followed by 8 bias-gradient columns
+//     (layer 3 with KCP == 48 has its bias gradient in column 15 + d_view instead);
+//   layers 2,5 (M = 128): transposed G^T[k][j], 16 columns, rows 0..63 = input index, row 64 = bias gradient.
 template <int K0P, int KCP>
 struct BwdTmem {
-  static constexpr int g0 = 128, g1 = g0 + K0P, g2 = g1 + 64, g3 = g2 + 16, g4 = g3 + KCP, g5 = g4 + 64;
-  static constexpr int b0 = g5 + 16, b1 = b0 + 8, b2 = b1 + 8, b3 = b2 + 16, b4 = b3 + 8, b5 = b4 + 8;
-  static constexpr int end = b5 + 16;
+  static constexpr bool kCinOne = KCP == 48;
+  static constexpr int g0 = 128, b0 = g0 + K0P;
+  static constexpr int g1 = b0 + 8, b1 = g1 + 64;
+  static constexpr int g2 = b1 + 8;
+  static constexpr int g3 = g2 + 16, b3 = g3 + KCP;
+  static constexpr int g4 = b3 + (kCinOne ? 0 : 8), b4 = g4 + 64;
+  static constexpr int g5 = b4 + 8;
+  static constexpr int end = g5 + 16;
   static_assert(end <= 512, "TMEM budget exceeded");
 };
 
 template <int K0P, int KCP, int G>
 __global__ void __launch_bounds__(G * kTile + 32, 1)
 mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const float* __restrict__ dirs, long long dir_group,
-                  long long n, const float* __restrict__ params, int in0, int dv, const float* __restrict__ dout,
-                  float* __restrict__ dfeat, long long dfeat_stride, float* __restrict__ ddirs, float* __restrict__ dparams) {
+                  long long n, const float* __restrict__ params, int in0, int dv, const float* __restrict__ out,
+                  const float* __restrict__ dout, float* __restrict__ dfeat, long long dfeat_stride,
+                  float* __restrict__ ddirs, float* __restrict__ dparams) {
   using SM = BwdSmem<K0P, KCP, G>;
   using WO = WOfs<K0P, KCP>;
   using TM = BwdTmem<K0P, KCP>;
+  constexpr bool kCinOne = TM::kCinOne;
+  static_assert(G >= 1 && G <= 2, "two work accumulators");
   extern __shared__ __align__(128) uint8_t sm[];
   const MlpLayout m = make_layout(in0, dv);
   uint8_t* wsm = sm;
-  float* bias = reinterpret_cast<float*>(sm + SM::off_bias);
-  uint8_t* ones = sm + SM::off_ones;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM::off_bar);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2 * G);
   const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -450,11 +508,23 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     for (int g = 0; g < G; ++g) { mbar_init(bars + g, kTile); mbar_init(bars + G + g, 1); }
     fence_mbar_init();
   }
-  stage_weights_bf16<K0P, KCP>(params, m, wsm, bias);
+  stage_weights_bf16<K0P, KCP>(params, m, wsm, sm + SM::off_bias, sm + SM::off_ones16);
   {
     const uint32_t one2 = pack_bf16(1.f, 1.f);
-    for (int e = threadIdx.x; e < kTile * 64 * 2 / 16; e += blockDim.x)
-      reinterpret_cast<uint4*>(ones)[e] = make_uint4(one2, one2, one2, one2);
+    const uint4 ones4 = make_uint4(one2, one2, one2, one2);
+    for (int e = threadIdx.x; e < kTile; e += blockDim.x) {
+      reinterpret_cast<uint4*>(sm + SM::off_onesb)[e] = ones4;
+      for (int g = 0; g < G; ++g) {
+        uint8_t* gb = sm + SM::off_grp + g * SM::grp_bytes;
+        reinterpret_cast<uint4*>(gb + SM::h2 + 8 * kCg)[e] = ones4;
+        reinterpret_cast<uint4*>(gb + SM::c2 + 8 * kCg)[e] = ones4;
+      }
+    }
+    // the M = 128 operands read 7 column groups past the ones group: keep that memory finite from the start
+    for (int e = threadIdx.x; e < G * SM::grp_bytes / 16; e += blockDim.x) {
+      const int g = e / (SM::grp_bytes / 16), o = (e - g * (SM::grp_bytes / 16)) * 16;
+      if (o >= SM::x0) *reinterpret_cast<uint4*>(sm + SM::off_grp + g * SM::grp_bytes + o) = make_uint4(0, 0, 0, 0);
+    }
   }
   fence_async_smem();
   fence_before_sync();
@@ -463,85 +533,87 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   const uint32_t tbase = *tslot;
   const long long ntiles = (n + kTile - 1) / kTile;
   const long long nslots = (long long)gridDim.x * G;
+  long long nt[G];
   long long cta_tiles = 0;
 #pragma unroll
-  for (int g = 0; g < G; ++g) cta_tiles += tiles_of_slot(ntiles, (long long)g * gridDim.x + blockIdx.x, nslots);
+  for (int g = 0; g < G; ++g) {
+    nt[g] = tiles_of_slot(ntiles, (long long)g * gridDim.x + blockIdx.x, nslots);
+    cta_tiles += nt[g];
+  }
 
   if (warp == 4 * G) {
-    // ===== MMA issuer (converged warp, one elected lane issues; see the forward kernel) =====
-    const uint32_t tb = __shfl_sync(kFull, tbase, 0);
-    const uint32_t wa = smem_u32(wsm), onesa = smem_u32(ones);
-    int left[G], stage[G];
+    // ===== the CTA's only MMA issuer: converged warp, fixed visiting order (stage-major, group-minor), straight-line
+    //       issue code; every gradient-accumulating MMA of the CTA comes from this one thread sequence =====
+    const uint32_t tb0 = __shfl_sync(kFull, tbase, 0);
+    const uint32_t sm0 = smem_u32(sm);
     uint32_t par[G];
-    int remaining = 0;
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      left[g] = 12 * (int)tiles_of_slot(ntiles, (long long)g * gridDim.x + blockIdx.x, nslots);
-      remaining += left[g];
-      stage[g] = 0;
-      par[g] = 0;
-    }
-    uint32_t inited = 0;                        // bit i: layer i's gradient accumulators hold a first contribution
-    while (remaining > 0) {
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        if (left[g] > 0 && __all_sync(kFull, mbar_test_wait(bars + g, par[g]))) {
-          fence_after_sync();
-          const int stg = stage[g];
-          if (elect_one()) {
-            const uint32_t d = tb + g * 64;
-            const uint32_t base = smem_u32(sm + SM::off_grp + g * SM::grp_bytes);
-            const uint32_t x0a = base + SM::x0, h1a = base + SM::h1, h2a = base + SM::h2, cina = base + SM::cin,
-                           c1a = base + SM::c1, c2a = base + SM::c2, dzsa = base + SM::dzs;
-            // ---- forward recompute ----
-            if (stg == 0) issue_fwd(d, x0a, wa + WO::w0, 64, K0P);
-            else if (stg == 1) issue_fwd(d, h1a, wa + WO::w1, 64, 64);
-            else if (stg == 2) issue_fwd(d, h2a, wa + WO::w2, 16, 64);
-            else if (stg == 3) issue_fwd(d, cina, wa + WO::w3, 64, KCP);
-            else if (stg == 4) issue_fwd(d, c1a, wa + WO::w4, 64, 64);
-            else if (stg == 5) issue_fwd(d, c2a, wa + WO::w5, 16, 64);
-            // ---- backward: dgrad into the work accumulator, weight/bias gradients into the resident ones ----
-            else if (stg == 6) {    // col_model.4: dZ = dzs (16 wide), input c2; transposed gradient [k][j]
-              const bool acc = (inited >> 5) & 1;
-              issue_dgrad(d, dzsa, wa + WO::w5, 16, 64);
-              issue_wgrad(tb + TM::g5, c2a, dzsa, 16, acc);
-              issue_wgrad(tb + TM::b5, onesa, dzsa, 16, acc);
-            } else if (stg == 7) {  // col_model.2: dZ in the c2 tile, input c1
-              const bool acc = (inited >> 4) & 1;
-              issue_dgrad(d, c2a, wa + WO::w4, 64, 64);
-              issue_wgrad(tb + TM::g4, c2a, c1a, 64, acc);
-              issue_wgrad(tb + TM::b4, c2a, onesa, 8, acc);
-            } else if (stg == 8) {  // col_model.0: dZ in the c1 tile, input cin
-              const bool acc = (inited >> 3) & 1;
-              issue_dgrad(d, c1a, wa + WO::w3, 64, KCP);
-              issue_wgrad(tb + TM::g3, c1a, cina, KCP, acc);
-              issue_wgrad(tb + TM::b3, c1a, onesa, 8, acc);
-            } else if (stg == 9) {  // sig_model.4: dZ = dzs (16 wide), input h2; transposed
-              const bool acc = (inited >> 2) & 1;
-              issue_dgrad(d, dzsa, wa + WO::w2, 16, 64);
-              issue_wgrad(tb + TM::g2, h2a, dzsa, 16, acc);
-              issue_wgrad(tb + TM::b2, onesa, dzsa, 16, acc);
-            } else if (stg == 10) { // sig_model.2: dZ in the h2 tile, input h1
-              const bool acc = (inited >> 1) & 1;
-              issue_dgrad(d, h2a, wa + WO::w1, 64, 64);
-              issue_wgrad(tb + TM::g1, h2a, h1a, 64, acc);
-              issue_wgrad(tb + TM::b1, h2a, onesa, 8, acc);
-            } else {                // sig_model.0: dZ in the h1 tile, input x0
-              const bool acc = inited & 1;
-              issue_dgrad(d, h1a, wa + WO::w0, 64, K0P);
-              issue_wgrad(tb + TM::g0, h1a, x0a, K0P, acc);
-              issue_wgrad(tb + TM::b0, h1a, onesa, 8, acc);
-            }
-            commit(bars + G + g);
-          }
-          __syncwarp();
-          if (stg >= 6) inited |= 1u << (11 - stg);
-          stage[g] = stg == 11 ? 0 : stg + 1;
-          par[g] ^= 1;
-          --left[g];
-          --remaining;
-        }
-      }
+    for (int g = 0; g < G; ++g) par[g] = 0;
+    bool first = true;                           // gradient accumulators not yet written
+    // The operand descriptors are rebuilt from two laundered base values in every stage: left to itself the compiler
+    // hoists all ~400 loop-invariant descriptors out of the tile loop and spills them.
+#define HBR_BWD_STAGE(BODY)                                                \
+  _Pragma("unroll") for (int g = 0; g < G; ++g) {                          \
+    if (k < nt[g]) {                                                       \
+      mbar_wait(bars + g, par[g]);                                         \
+      par[g] ^= 1;                                                         \
+      fence_after_sync();                                                  \
+      if (elect_one()) {                                                   \
+        uint32_t sb = sm0, tb = tb0;                                       \
+        asm volatile("" : "+r"(sb), "+r"(tb));                             \
+        const uint32_t wa = sb, ba = sb + SM::off_bias, o16a = sb + SM::off_ones16, onesb = sb + SM::off_onesb; \
+        const uint32_t d = tb + g * 64;                                    \
+        const uint32_t base = sb + SM::off_grp + g * SM::grp_bytes;        \
+        const uint32_t x0a = base + SM::x0, h1a = base + SM::h1, h2a = base + SM::h2, cina = base + SM::cin, \
+                       c1a = base + SM::c1, c2a = base + SM::c2, dzsa = base + SM::dzs; \
+        (void)wa; (void)ba; (void)o16a; (void)onesb;                       \
+        (void)x0a; (void)h1a; (void)h2a; (void)cina; (void)c1a; (void)c2a; (void)dzsa; \
+        const bool acc = !(first && g == 0);                               \
+        (void)acc;                                                         \
+        BODY;                                                              \
+        commit(bars + G + g);                                              \
+      }                                                                    \
+      __syncwarp();                                                        \
+    }                                                                      \
+  }
+    const long long kmax = nt[0];                // slot of group 0 never has fewer tiles than a later group's
+    for (long long k = 0; k < kmax; ++k) {
+      // ---- forward recompute (layers 0..4) ----
+      HBR_BWD_STAGE(issue_layer(d, x0a, wa + WO::w0, o16a, ba + BOfs::ofs(0), 64, K0P));
+      HBR_BWD_STAGE(issue_layer(d, h1a, wa + WO::w1, o16a, ba + BOfs::ofs(1), 64, 64));
+      HBR_BWD_STAGE(issue_layer(d, h2a, wa + WO::w2, o16a, ba + BOfs::ofs(2), 16, 64));
+      HBR_BWD_STAGE(issue_layer(d, cina, wa + WO::w3, o16a, ba + BOfs::ofs(3), 64, KCP));
+      HBR_BWD_STAGE(issue_layer(d, c1a, wa + WO::w4, o16a, ba + BOfs::ofs(4), 64, 64));
+      // ---- backward: dgrad into the work accumulator, weight/bias gradients into the resident accumulators ----
+      HBR_BWD_STAGE({   // col_model.4: dZ = dzs (16 wide), input c2 (+ ones group): transposed gradient, M = 128
+        issue_dgrad(d, dzsa, wa + WO::w5, 16, 64);
+        issue_wgrad(tb + TM::g5, c2a, dzsa, 16, acc, 128);
+      });
+      HBR_BWD_STAGE({   // col_model.2: dZ in the c2 tile, input c1
+        issue_dgrad(d, c2a, wa + WO::w4, 64, 64);
+        issue_wgrad(tb + TM::g4, c2a, c1a, 64, acc);
+        issue_wgrad(tb + TM::b4, c2a, onesb, 8, acc);
+      });
+      HBR_BWD_STAGE({   // col_model.0: dZ in the c1 tile, input cin (bias gradient through the planted 1.0 column)
+        issue_dgrad(d, c1a, wa + WO::w3, 64, KCP);
+        issue_wgrad(tb + TM::g3, c1a, cina, KCP, acc);
+        if (!kCinOne) issue_wgrad(tb + TM::b3, c1a, onesb, 8, acc);
+      });
+      HBR_BWD_STAGE({   // sig_model.4: dZ = dzs (16 wide), input h2 (+ ones group): transposed
+        issue_dgrad(d, dzsa, wa + WO::w2, 16, 64);
+        issue_wgrad(tb + TM::g2, h2a, dzsa, 16, acc, 128);
+      });
+      HBR_BWD_STAGE({   // sig_model.2: dZ in the h2 tile, input h1
+        issue_dgrad(d, h2a, wa + WO::w1, 64, 64);
+        issue_wgrad(tb + TM::g1, h2a, h1a, 64, acc);
+        issue_wgrad(tb + TM::b1, h2a, onesb, 8, acc);
+      });
+      HBR_BWD_STAGE({   // sig_model.0: dZ in the h1 tile, input x0
+        issue_dgrad(d, h1a, wa + WO::w0, 64, K0P);
+        issue_wgrad(tb + TM::g0, h1a, x0a, K0P, acc);
+        issue_wgrad(tb + TM::b0, h1a, onesb, 8, acc);
+      });
+      first = false;
     }
   } else {
     // ===== tile group =====
@@ -559,55 +631,48 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     for (long long tile = (long long)g * gridDim.x + blockIdx.x; tile < ntiles; tile += nslots) {
       const long long gp = tile * kTile + r;
       const bool valid = gp < n;
+      float4 fo = make_float4(0.f, 0.f, 0.f, 0.f), go = fo;           // saved forward output, upstream gradient
+      if (valid) {
+        fo = __ldg(reinterpret_cast<const float4*>(out + gp * 4));
+        go = __ldg(reinterpret_cast<const float4*>(dout + gp * 4));
+      }
       // ---- recompute the forward activations ----
       load_features<K0P>(feat, feat_stride, gp, n, in0, vec_ok, r, x0);
       HBR_SIGNAL(); HBR_WAIT();
-      relu_epilogue64(taddr, bias + 0, r, h1);
+      relu_epilogue64(taddr, r, h1);
       HBR_SIGNAL(); HBR_WAIT();
-      relu_epilogue64(taddr, bias + 64, r, h2);
+      relu_epilogue64(taddr, r, h2);
       HBR_SIGNAL(); HBR_WAIT();
-      float lrelu_slope;
       const long long dir_row = valid ? gp / dir_group : 0;
       {
         float o16[16];
         tmem_ld<16>(taddr, o16);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) o16[k] += bias[128 + k];
-        lrelu_slope = o16[0] > 0.f ? 1.f : 0.01f;
-        build_cin<KCP>(o16, dirs, dir_row, dv, valid, r, cin);
+        build_cin<KCP, kCinOne>(o16, dirs, dir_row, dv, valid, r, cin);
       }
       HBR_SIGNAL(); HBR_WAIT();
-      relu_epilogue64(taddr, bias + 192, r, c1);
+      relu_epilogue64(taddr, r, c1);
       HBR_SIGNAL(); HBR_WAIT();
-      relu_epilogue64(taddr, bias + 256, r, c2);
-      HBR_SIGNAL(); HBR_WAIT();
-      float g_density;
+      relu_epilogue64(taddr, r, c2);
       {
-        float c16[16], dz16[16];
-        tmem_ld<16>(taddr, c16);
-        float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) go = __ldg(reinterpret_cast<const float4*>(dout + gp * 4));
-        const float gg[3] = {go.x, go.y, go.z};
+        // d(rgb_pre) = g * ELU'(pre), with ELU'(pre) = pre > 0 ? 1 : exp(pre) = elu(pre) + 1 from the saved output
+        float dz16[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) dz16[c] = 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float pre = c16[c] + bias[320 + c];
-          dz16[c] = gg[c] * (pre > 0.f ? 1.f : expf(pre));               // ELU'
-        }
-        g_density = go.w * lrelu_slope;                                  // LeakyReLU'
+        dz16[0] = go.x * (fo.x > 0.f ? 1.f : fo.x + 1.f);
+        dz16[1] = go.y * (fo.y > 0.f ? 1.f : fo.y + 1.f);
+        dz16[2] = go.z * (fo.z > 0.f ? 1.f : fo.z + 1.f);
         store_chunk(dzs, r, 0, kTile, dz16);
         store_chunk(dzs, r, 1, kTile, dz16 + 8);
       }
-      HBR_SIGNAL(); HBR_WAIT();                  // stage 6 done: work = dA(c2)
+      HBR_SIGNAL(); HBR_WAIT();                  // col_model.4 backward done: work = dA(c2)
       masked_dz_inplace64(taddr, r, c2);
-      HBR_SIGNAL(); HBR_WAIT();                  // stage 7 done: work = dA(c1)
+      HBR_SIGNAL(); HBR_WAIT();                  // col_model.2 done: work = dA(c1)
       masked_dz_inplace64(taddr, r, c1);
-      HBR_SIGNAL(); HBR_WAIT();                  // stage 8 done: work[0,KCP) = d(cin)
+      HBR_SIGNAL(); HBR_WAIT();                  // col_model.0 done: work[0,KCP) = d(cin)
       {
         float dc[KCP], dz16[16];
         tmem_ld<KCP>(taddr, dc);
-        dz16[0] = g_density;
+        dz16[0] = go.w * (fo.w > 0.f ? 1.f : 0.01f);                    // LeakyReLU' from the saved density
 #pragma unroll
         for (int k = 0; k < kFeat; ++k) dz16[1 + k] = dc[k];
         store_chunk(dzs, r, 0, kTile, dz16);
@@ -629,11 +694,11 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
           }
         }
       }
-      HBR_SIGNAL(); HBR_WAIT();                  // stage 9 done: work = dA(h2)
+      HBR_SIGNAL(); HBR_WAIT();                  // sig_model.4 done: work = dA(h2)
       masked_dz_inplace64(taddr, r, h2);
-      HBR_SIGNAL(); HBR_WAIT();                  // stage 10 done: work = dA(h1)
+      HBR_SIGNAL(); HBR_WAIT();                  // sig_model.2 done: work = dA(h1)
       masked_dz_inplace64(taddr, r, h1);
-      HBR_SIGNAL(); HBR_WAIT();                  // stage 11 done: work[0,K0P) = d(feat)
+      HBR_SIGNAL(); HBR_WAIT();                  // sig_model.0 done: work[0,K0P) = d(feat)
       if (dfeat != nullptr) {
         float df[K0P];
         tmem_ld<K0P>(taddr, df);
@@ -655,34 +720,53 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   __syncthreads();
   fence_after_sync();
 
-  // ---- flush the gradient accumulators (M = 64 layout: row q lives in lane (q%16) + 32*(q/16)) ----
+  // ---- flush the gradient accumulators ----
   if (cta_tiles > 0 && dparams != nullptr && warp < 4) {
-    const int q = warp * 16 + lane;              // accumulator row, meaningful for lane < 16
     const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
-    const int gcol[6] = {TM::g0, TM::g1, TM::g2, TM::g3, TM::g4, TM::g5};
-    const int bcol[6] = {TM::b0, TM::b1, TM::b2, TM::b3, TM::b4, TM::b5};
+    // layers 0,1,3,4 -- M = 64 layout: accumulator row q (= output neuron) lives in lane (q % 16) + 32 * (q / 16)
+    {
+      const int q = warp * 16 + lane;            // meaningful for lane < 16
+      const int gcol[4] = {TM::g0, TM::g1, TM::g3, TM::g4};
+      const int bcol[4] = {TM::b0, TM::b1, TM::b3, TM::b4};
+      const int li[4] = {0, 1, 3, 4};
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const bool transposed = i == 2 || i == 5;
-      float gacc[64];
-      const int KP = i == 0 ? K0P : (i == 3 ? KCP : (transposed ? 16 : 64));
-      if (KP > 48) tmem_ld<64>(trow + gcol[i], gacc);
-      else if (KP > 32) tmem_ld<48>(trow + gcol[i], gacc);
-      else if (KP > 16) tmem_ld<32>(trow + gcol[i], gacc);
-      else tmem_ld<16>(trow + gcol[i], gacc);
-      float gbias[16];
-      tmem_ld<16>(trow + bcol[i], gbias);        // 8 or 16 valid columns; any excess belongs to the next accumulator
-      if (lane < 16) {
-        if (!transposed) {
-          if (q < m.J[i]) {
-            for (int k = 0; k < m.K[i]; ++k) atomicAdd(dparams + m.W[i] + q * m.K[i] + k, gacc[k]);
-            atomicAdd(dparams + m.b[i] + q, gbias[0]);
+      for (int t = 0; t < 4; ++t) {
+        const int i = li[t];
+        float gacc[64], gbias[16];
+        const int KP = i == 0 ? K0P : (i == 3 ? KCP : 64);
+        if (KP > 48) tmem_ld<64>(trow + gcol[t], gacc);
+        else if (KP > 32) tmem_ld<48>(trow + gcol[t], gacc);
+        else tmem_ld<32>(trow + gcol[t], gacc);
+        if (i == 3 && kCinOne) gbias[0] = 0.f;
+        else tmem_ld<16>(trow + bcol[t], gbias);    // 8 valid columns; the excess belongs to the next accumulator
+        if (lane < 16 && q < m.J[i]) {
+          float bsum = gbias[0];
+          for (int k = 0; k < KP; ++k) {
+            if (k < m.K[i]) atomicAdd(dparams + m.W[i] + q * m.K[i] + k, gacc[k]);
+            if (i == 3 && kCinOne && k == m.K[i]) bsum = gacc[k];
           }
-        } else {
-          // row q = input index k (K = 64), column = output neuron j
-          for (int j = 0; j < m.J[i]; ++j) atomicAdd(dparams + m.W[i] + j * m.K[i] + q, gacc[j]);
-          if (q == 0)
-            for (int j = 0; j < m.J[i]; ++j) atomicAdd(dparams + m.b[i] + j, gbias[j]);
+          atomicAdd(dparams + m.b[i] + q, bsum);
+        }
+      }
+    }
+    // layers 2,5 -- M = 128 layout: accumulator row = lane; rows 0..63 = input index k, row 64 = bias gradient
+    {
+      const int row = warp * 32 + lane;
+      const int gcol[2] = {TM::g2, TM::g5};
+      const int li[2] = {2, 5};
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int i = li[t];
+        float gacc[16];
+        tmem_ld<16>(trow + gcol[t], gacc);
+        if (row < 64) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < m.J[i]) atomicAdd(dparams + m.W[i] + j * 64 + row, gacc[j]);
+        } else if (row == 64) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < m.J[i]) atomicAdd(dparams + m.b[i] + j, gacc[j]);
         }
       }
     }
@@ -706,14 +790,20 @@ extern "C" int hbr_debug_umma(int mode, const float* A, const float* B, float* D
   return HBR_OK;
 }
 
+extern "C" int hbr_debug_mlp_trace(const float* feat, const float* dirs, int64_t dir_group, int64_t n, const float* params,
+                                   float* out, long long* trace, void* stream) {
+  constexpr int smem = FwdSmem<32, 48, 4>::total;
+  HBR_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<32, 48, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = (int)min64(ceil_div(ceil_div(n, kTile), 4), sm_count());
+  mlp_fwd_tc_kernel<32, 48, 4, true><<<grid, 4 * (kTile + 32), smem, as_stream(stream)>>>(feat, 32, dirs, dir_group, n,
+                                                                                         params, 32, 24, out, trace);
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
+
 // The reference's configuration (in0 = 32, d_view = 24) gets the widest pipelines (4 forward / 2 backward tile groups
 // per SM); other widths (in0 <= 64, 15 + d_view <= 64) run the same kernels with padded K and fewer groups.
-#define HBR_TC_LAUNCH(KERN, K0P_, KCP_, G_, SMEM_T, ...)                                                            \
-  do {                                                                                                              \
-    constexpr int smem = SMEM_T<K0P_, KCP_, G_>::total;                                                             \
-    HBR_CUDA(cudaFuncSetAttribute(KERN<K0P_, KCP_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
-    KERN<K0P_, KCP_, G_><<<grid, G_ * kTile + 32, smem, st>>>(__VA_ARGS__);                                         \
-  } while (0)
+static inline bool narrow_shape(const hbr_mlp_dims* d) { return d->in0 <= 32 && d->d_view + kFeat <= 40; }
 
 extern "C" int hbr_mlp_fwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                               const float* params, const hbr_mlp_dims* dims, float* out, void* stream) {
@@ -722,42 +812,49 @@ extern "C" int hbr_mlp_fwd_tc(const float* feat, int64_t feat_stride, const floa
   HBR_REQUIRE(feat && dirs && params && out, "NULL pointer");
   HBR_REQUIRE(feat_stride >= dims->in0 && dir_group >= 1, "bad stride / dir_group");
   HBR_REQUIRE((uintptr_t)out % 16 == 0, "out must be 16-byte aligned");
-  const int k0p = dims->in0 <= 32 ? 32 : 64, kcp = dims->d_view + kFeat <= 48 ? 48 : 64;
   cudaStream_t st = as_stream(stream);
   const int64_t ntiles = ceil_div(n, kTile);
   const int in0 = dims->in0, dv = dims->d_view;
-  if (k0p == 32 && kcp == 48) {
-    const int grid = (int)min64(ceil_div(ntiles, 4), sm_count());
-    HBR_TC_LAUNCH(mlp_fwd_tc_kernel, 32, 48, 4, FwdSmem, feat, feat_stride, dirs, dir_group, n, params, in0, dv, out);
+  const int grid = (int)min64(ceil_div(ntiles, 4), sm_count());
+  if (narrow_shape(dims)) {
+    constexpr int smem = FwdSmem<32, 48, 4>::total;
+    HBR_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<32, 48, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mlp_fwd_tc_kernel<32, 48, 4><<<grid, 4 * (kTile + 32), smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv,
+                                                                     out);
   } else {
-    const int grid = (int)min64(ceil_div(ntiles, 4), sm_count());
-    HBR_TC_LAUNCH(mlp_fwd_tc_kernel, 64, 64, 4, FwdSmem, feat, feat_stride, dirs, dir_group, n, params, in0, dv, out);
+    constexpr int smem = FwdSmem<64, 64, 4>::total;
+    HBR_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<64, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mlp_fwd_tc_kernel<64, 64, 4><<<grid, 4 * (kTile + 32), smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv,
+                                                                     out);
   }
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
 
 extern "C" int hbr_mlp_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
-                              const float* params, const hbr_mlp_dims* dims, const float* dout, float* dfeat,
-                              int64_t dfeat_stride, float* ddirs, float* dparams, void* stream) {
+                              const float* params, const hbr_mlp_dims* dims, const float* out, const float* dout,
+                              float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams, void* stream) {
   if (int rc = check_dims(dims)) return rc;
   if (n == 0) return HBR_OK;
-  HBR_REQUIRE(feat && dirs && params && dout, "NULL pointer");
+  HBR_REQUIRE(feat && dirs && params && out && dout, "NULL pointer");
   HBR_REQUIRE(feat_stride >= dims->in0 && dir_group >= 1, "bad stride / dir_group");
-  HBR_REQUIRE((uintptr_t)dout % 16 == 0, "dout must be 16-byte aligned");
+  HBR_REQUIRE((uintptr_t)dout % 16 == 0 && (uintptr_t)out % 16 == 0, "out / dout must be 16-byte aligned");
   HBR_REQUIRE(!dfeat || dfeat_stride >= dims->in0, "dfeat_stride too small");
-  const int k0p = dims->in0 <= 32 ? 32 : 64, kcp = dims->d_view + kFeat <= 48 ? 48 : 64;
   cudaStream_t st = as_stream(stream);
   const int64_t ntiles = ceil_div(n, kTile);
   const int in0 = dims->in0, dv = dims->d_view;
-  if (k0p == 32 && kcp == 48) {
+  if (narrow_shape(dims)) {
+    constexpr int smem = BwdSmem<32, 48, 2>::total;
     const int grid = (int)min64(ceil_div(ntiles, 2), sm_count());
-    HBR_TC_LAUNCH(mlp_bwd_tc_kernel, 32, 48, 2, BwdSmem, feat, feat_stride, dirs, dir_group, n, params, in0, dv, dout,
-                  dfeat, dfeat_stride, ddirs, dparams);
+    HBR_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<32, 48, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mlp_bwd_tc_kernel<32, 48, 2><<<grid, 2 * kTile + 32, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv,
+                                                                   out, dout, dfeat, dfeat_stride, ddirs, dparams);
   } else {
+    constexpr int smem = BwdSmem<64, 64, 1>::total;
     const int grid = (int)min64(ntiles, sm_count());
-    HBR_TC_LAUNCH(mlp_bwd_tc_kernel, 64, 64, 1, BwdSmem, feat, feat_stride, dirs, dir_group, n, params, in0, dv, dout,
-                  dfeat, dfeat_stride, ddirs, dparams);
+    HBR_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<64, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mlp_bwd_tc_kernel<64, 64, 1><<<grid, kTile + 32, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out,
+                                                               dout, dfeat, dfeat_stride, ddirs, dparams);
   }
   HBR_LAUNCH_CHECK();
   return HBR_OK;

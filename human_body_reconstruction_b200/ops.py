@@ -239,12 +239,13 @@ def mlp_fwd_tc(feat, dirs, dir_group, params, dims: MlpDims, keep_act: bool = Fa
     return out, None
 
 
-def mlp_bwd_tc(feat, dirs, dir_group, params, dims: MlpDims, dout, act, want_dfeat, want_ddirs, dparams):
+def mlp_bwd_tc(feat, dirs, dir_group, params, dims: MlpDims, out, dout, want_dfeat, want_ddirs, dparams):
+    """`out` is the forward output (N,4): the kernel takes ELU' / LeakyReLU' from it instead of recomputing the last layer."""
     n = feat.shape[0]
     dfeat = torch.empty((n, dims.in0), device=feat.device, dtype=torch.float32) if want_dfeat else None
     ddirs = torch.zeros_like(dirs) if want_ddirs else None
-    check(lib().hbr_mlp_bwd_tc(ptr(feat), feat.stride(0), ptr(dirs), dir_group, n, ptr(params), C.byref(dims), ptr(dout),
-                               ptr(dfeat), dims.in0, ptr(ddirs), ptr(dparams), stream()))
+    check(lib().hbr_mlp_bwd_tc(ptr(feat), feat.stride(0), ptr(dirs), dir_group, n, ptr(params), C.byref(dims), ptr(out),
+                               ptr(dout), ptr(dfeat), dims.in0, ptr(ddirs), ptr(dparams), stream()))
     return dfeat, ddirs
 
 

@@ -35,7 +35,7 @@ class _MlpFn(torch.autograd.Function):
         else:
             out, act = ops.mlp_fwd_f32(feat, dirs, dir_group, flat, dims, keep_act=train)
         ctx.mlp, ctx.dims, ctx.dir_group, ctx.use_tc = mlp, dims, dir_group, use_tc
-        ctx.save_for_backward(feat, dirs, act)
+        ctx.save_for_backward(feat, dirs, out if use_tc else act)     # the tensor-core backward reads the saved output
         return out
 
     @staticmethod
@@ -47,7 +47,8 @@ class _MlpFn(torch.autograd.Function):
         dout = dout.float().contiguous()
         want_dfeat, want_ddirs = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if ctx.use_tc:
-            dfeat, ddirs = ops.mlp_bwd_tc(feat, dirs, ctx.dir_group, flat, ctx.dims, dout, act, want_dfeat, want_ddirs, dflat)
+            dfeat, ddirs = ops.mlp_bwd_tc(feat, dirs, ctx.dir_group, flat, ctx.dims, act.detach(), dout, want_dfeat, want_ddirs,
+                                          dflat)
         else:
             dfeat, ddirs = ops.mlp_bwd_f32(feat, dirs, ctx.dir_group, flat, ctx.dims, dout, act, want_dfeat, want_ddirs, dflat)
         mlp._publish_grad(dflat)

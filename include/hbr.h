@@ -103,19 +103,24 @@ int hbr_mlp_bwd_f32(const float* feat, int64_t feat_stride, const float* dirs, i
                     float* dz, float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams, void* stream);
 
 /* ---- a7 on the tensor cores: bf16 operands, fp32 accumulation in TMEM (tcgen05) -----------------------
- * Same contract as the fp32 pair; this is what runs under autocast (train_hash2.py:218).  Nothing is kept
- * between the passes: the backward kernel recomputes the activations in shared memory from feat, and keeps
- * the weight-gradient accumulators in TMEM across all tiles of a persistent CTA.  dfeat / ddirs may be NULL;
- * dparams (flat fp32) and ddirs are ACCUMULATED into. */
+ * Same contract as the fp32 pair; this is what runs under autocast (train_hash2.py:218).  No activation is kept
+ * between the passes: the backward kernel recomputes them in shared memory from feat, takes ELU' / LeakyReLU'
+ * from `out` (the (n,4) result of the forward call), and keeps the weight-gradient accumulators in TMEM across
+ * all tiles of a persistent CTA.  dfeat / ddirs may be NULL; dparams (flat fp32) and ddirs are ACCUMULATED into. */
 int hbr_mlp_fwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                    const float* params, const hbr_mlp_dims* dims, float* out, void* stream);
 int hbr_mlp_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
-                   const float* params, const hbr_mlp_dims* dims, const float* dout, float* dfeat,
+                   const float* params, const hbr_mlp_dims* dims, const float* out, const float* dout, float* dfeat,
                    int64_t dfeat_stride, float* ddirs, float* dparams, void* stream);
 /* Self-test of the three UMMA operand modes the MLP kernels rely on (one 128-thread CTA, bf16 inputs
  * rounded from fp32, fp32 result): mode 0: D[128,N] = A[128,K] B[N,K]^T; mode 1: D[128,N] = A[128,K] Bt[K,N];
  * mode 2: D[64,N] = At[128,64]^T Bt[128,N]. */
 int hbr_debug_umma(int mode, const float* A, const float* B, float* D, int N, int K, void* stream);
+/* Latency probe of the forward kernel (in0 = 32, d_view = 24): trace[0..1000) = clock64 stamps of tile group 0 of CTA 0
+ * (tile start, then before-signal / after-signal / after-wait per layer), trace[1024..1524) = the MMA warp's
+ * (ready-seen, committed) pairs for that group.  trace holds 2048 int64. */
+int hbr_debug_mlp_trace(const float* feat, const float* dirs, int64_t dir_group, int64_t n, const float* params,
+                        float* out, long long* trace, void* stream);
 
 /* ---- a9: sample positions, vol_renderer.py:165 / helper.py:48 -------------------------------------
  * pts[r,s,:] = o[r,:] + d[r,:]*t  (separate multiply and add).  t is (S) shared (t_ray_stride = 0)

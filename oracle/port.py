@@ -390,7 +390,8 @@ def mlp_bf16_emulation(p: Dict[str, torch.Tensor], feat: torch.Tensor, dirs: tor
     fp32, the layer-3 vector (density + 15 features) and the outputs NOT rounded.  Returns out (N,4) and, with
     dout, (dfeat, grads dict).  Not a reference restatement -- a numerics model of our own kernel, used to test it
     tightly; the reference-facing tolerance (1e-2, BASELINE.json) is checked against mlp_forward."""
-    W = {k: _bf(v) if k.endswith("weight") else v for k, v in p.items()}
+    # the bias enters the accumulator through the tensor core as bf16(b) + bf16(b - bf16(b))
+    W = {k: _bf(v) if k.endswith("weight") else _bf(v) + _bf(v - _bf(v)) for k, v in p.items()}
     x0 = _bf(feat)
     h1p = x0 @ W["sig_model.0.weight"].T + W["sig_model.0.bias"]
     h1 = _bf(torch.relu(h1p))

@@ -1,6 +1,6 @@
 # usage: bash scripts/gpu_iter.sh "<pytest args>" "<bench args>"
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x $1 2>&1 | tail -25 > gpurun_out/pytest_gpu.log; cat gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -q -x $1 2>&1 | tail -25 > gpurun_out/pytest_gpu.log; cat gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline $2 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err
 python - <<'PY'
 import json
@@ -10,3 +10,4 @@ try:
     for k,v in d['kernels_ms'].items(): print(f"  {k:24s} {v['mean_ms']*1e3:8.1f} us x{v['launches_per_step']}")
 except Exception as e: print('no bench json', e)
 PY
+timeout 300 python scripts/dbg_trace.py > gpurun_out/trace.log 2>&1; head -12 gpurun_out/trace.log

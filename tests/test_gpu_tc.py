@@ -73,7 +73,9 @@ def test_mlp_tc_matches_numerics_model_and_reference(R, S):
     out = m.field(f, dirs.to(DEV), S, use_tc=True)
     out.backward(dout.to(DEV))
     # (2) kernel vs its numerics model
-    assert rel(out, emu_out) < 2e-4
+    # a last-bit difference in an fp32 accumulator flips the bf16 rounding of that activation (2^-9 relative for the
+    # element); a handful of flips per row is the expected residual between two correct evaluations
+    assert rel(out, emu_out) < 5e-4
     assert rel(f.grad, emu_dfeat) < 5e-3
     for k, q in m.named_parameters():
         assert rel(q.grad, emu_g[k]) < 5e-3, k
