@@ -264,34 +264,62 @@ def run_b200(args):
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
+
+    def timed_region(run_step):
+        """K steps, one CUDA-event pair per step on the launching stream, L2 flushed between steps."""
+        ev = []
+        for k in range(args.steps):
+            if flush is not None:
+                flush.zero_()                                              # evict L2 (outside the timed events)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run_step(k)
+            e1.record()
+            ev.append((e0, e1))
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in ev)
+
+    # (1) eager region: every C-ABI call bracketed by its own CUDA events -> per-kernel durations for the roofline
     _lib.STATS.reset()
     _lib.STATS.timing = True
-    ev = []
     t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        if flush is not None:
-            flush.zero_()                                                  # evict L2 (outside the timed events)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step(resident[k % len(resident)])
-        e1.record()
-        ev.append((e0, e1))
-    barrier()
+    eager_ms = timed_region(lambda k: step(resident[k % len(resident)]))
     wall = time.perf_counter() - t_wall0
     _lib.STATS.timing = False
     launches = _lib.STATS.launches
     kern = _lib.STATS.summary()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
 
-    # end to end: pinned host batch -> H2D -> step -> loss.item()
+    # (2) the same step captured once in a CUDA graph and replayed (one launch per step instead of ~35)
+    gs, graph_note = None, "eager"
+    if args.graph == "on" or (args.graph == "auto" and world == 1):
+        try:
+            from human_body_reconstruction_b200.graph import GraphedStep
+            gs = GraphedStep(vr, nerf, params, rays, args.samples, args.hierarchical, dev, autocast=amp).capture()
+            for k in range(3):
+                gs(*resident[k % len(resident)])
+            barrier()
+            graph_note = "cuda graph replay (vol_render + loss + backward captured once)"
+        except Exception as e:                                             # noqa: BLE001  (report, fall back to eager)
+            gs, graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {e})"
+            for p in params:
+                p.grad = None
+    if gs is not None:
+        dev_ms = timed_region(lambda k: gs(*resident[k % len(resident)]))
+    else:
+        dev_ms = eager_ms
+
+    # (3) end to end: pinned host batch -> H2D -> step -> loss.item()
     e2e_s = 0.0
     for k in range(args.steps):
         if flush is not None:
             flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        batch = tuple(t.to(dev, non_blocking=True) for t in host[k % len(host)])
-        loss = step(batch)
+        if gs is not None:
+            loss = gs(*host[k % len(host)])                               # non-blocking copies from pinned memory + replay
+        else:
+            batch = tuple(t.to(dev, non_blocking=True) for t in host[k % len(host)])
+            loss = step(batch)
         loss_val = loss.item()
         e2e_s += time.perf_counter() - t0
     barrier()
@@ -326,7 +354,9 @@ def run_b200(args):
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16 MLP / f32 encoder+compositor" if amp else "f32", "data": "synthetic",
         "config": {"workload": workload_name(args, rays), "rays_per_gpu": rays, "l2": "flushed between timed steps (512 MiB write)"
-                   if flush is not None else "warm", "parallelism": f"dp{world} (rays sharded, table+MLP grads all-reduced)"},
+                   if flush is not None else "warm", "parallelism": f"dp{world} (rays sharded, table+MLP grads all-reduced)",
+                   "launch": graph_note},
+        "eager_ms_per_step": eager_ms / args.steps,
         "e2e": {"value": total_rays / (e2e_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
@@ -336,7 +366,7 @@ def run_b200(args):
         "step_roofline": {"algorithmic_bytes_per_point": STEP_BYTES_PER_POINT, "achieved": step_achieved, "frac": step_achieved / peak,
                           "unit": "GB/s"},
         "kernels_ms": {k: {"launches_per_step": c / args.steps, "mean_ms": m} for k, (c, m) in sorted(kern.items())},
-        "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
+        "eager_wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
         "clocks": clk, "last_loss": loss_val,
     }
     if "hbr_hash_encode_fwd" in kern:
@@ -373,6 +403,8 @@ def main():
     ap.add_argument("--l2", default="flush", choices=["flush", "warm"])
     ap.add_argument("--cpu-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step from a CUDA graph (auto: single GPU only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

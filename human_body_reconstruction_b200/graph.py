@@ -1,0 +1,82 @@
+"""CUDA-graph capture of one training step of the hot path.
+
+A train_hash2.py step at 4096 rays is ~35 kernel launches of 2-250 us each; driven eagerly from Python the host
+needs ~1 ms to enqueue them, more than the GPU needs to run them.  `GraphedStep` captures
+
+    vol_render(...)  ->  loss_fn(Cr, Cf, gt)  ->  loss.backward()
+
+once (fixed ray count / sample count) and replays it: one `cudaGraphLaunch` per step.  Inputs are copied into
+static device buffers before each replay; the loss and the parameter gradients live in static buffers that every
+replay overwrites (the parameters' `.grad` tensors are allocated inside the graph's memory pool during capture, the
+documented whole-network-capture pattern of torch.cuda.graphs).  torch's CUDA generator is graph-safe, so the
+reference's RNG draws (strat_sampler, hierarchical_sampling) still advance on every replay.
+An optimiser may be stepped eagerly after the replay (its inputs, the `.grad` tensors, are static).
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, Optional
+
+import torch
+
+
+def default_loss(Cr, Cf, gt):
+    """train_hash2.py:221 with the MSE criterion of :177."""
+    return torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)
+
+
+class GraphedStep:
+    def __init__(self, renderer, model, params: Iterable[torch.nn.Parameter], n_rays: int, num_samples: int,
+                 hierarchical: bool, device, loss_fn: Callable = default_loss, autocast: bool = True, warmup: int = 3):
+        self.renderer, self.model = renderer, model
+        self.params = list(params)
+        self.num_samples, self.hierarchical = int(num_samples), bool(hierarchical)
+        self.loss_fn, self.autocast = loss_fn, autocast
+        dev = torch.device(device)
+        self.rays_o = torch.zeros((n_rays, 3), device=dev)
+        self.rays_d = torch.zeros((n_rays, 3), device=dev)
+        self.rays_d[:, 2] = 1.0
+        self.dir_norm = torch.ones((n_rays, 1), device=dev)
+        self.gt = torch.zeros((n_rays, 3), device=dev)
+        self.loss: Optional[torch.Tensor] = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._warmup = warmup
+
+    def _step(self):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
+            Cr, Cf, _ = self.renderer.vol_render(self.model, self.rays_d, self.rays_o, num_samples=self.num_samples,
+                                                 update_mask=False, dir_norm=self.dir_norm, hierarchical=self.hierarchical)
+            loss = self.loss_fn(Cr, Cf, self.gt)
+        loss.backward()
+        return loss
+
+    def load(self, rays_o, rays_d, dir_norm, gt, non_blocking: bool = True):
+        """Copy a batch (device or pinned-host tensors) into the static input buffers."""
+        self.rays_o.copy_(rays_o, non_blocking=non_blocking)
+        self.rays_d.copy_(rays_d, non_blocking=non_blocking)
+        self.dir_norm.copy_(dir_norm.reshape(-1, 1), non_blocking=non_blocking)
+        self.gt.copy_(gt, non_blocking=non_blocking)
+
+    def capture(self):
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(self._warmup):
+                for p in self.params:
+                    p.grad = None
+                self._step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for p in self.params:
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step()
+        return self
+
+    def __call__(self, rays_o=None, rays_d=None, dir_norm=None, gt=None) -> torch.Tensor:
+        if self.graph is None:
+            self.capture()
+        if rays_o is not None:
+            self.load(rays_o, rays_d, dir_norm, gt)
+        self.graph.replay()
+        return self.loss
