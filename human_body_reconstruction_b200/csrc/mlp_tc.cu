@@ -55,25 +55,38 @@ struct BOfs {                         // byte offsets of the six [JP x 16] bias 
 // fp32 (J,K) row-major weights -> bf16 canonical tile [JP rows x KP cols], zero padded; one 16-byte chunk per step
 template <int K0P, int KCP>
 __device__ __forceinline__ void stage_weights_bf16(const float* __restrict__ params, const MlpLayout& m, uint8_t* wsm,
-                                                   uint8_t* bias_sm, uint8_t* ones16) {
+                                                   uint8_t* bias_sm, uint8_t* ones16, float* bias_f32 = nullptr) {
   const int JP[6] = {64, 64, 16, 64, 64, 16};
   const int KP[6] = {K0P, 64, 64, KCP, 64, 64};
   const int wofs[6] = {WOfs<K0P, KCP>::w0, WOfs<K0P, KCP>::w1, WOfs<K0P, KCP>::w2, WOfs<K0P, KCP>::w3,
                        WOfs<K0P, KCP>::w4, WOfs<K0P, KCP>::w5};
+  // weight tiles: one flat loop over all 16-byte chunks of the six tiles so that every thread has several chunks'
+  // worth of global loads in flight (the whole image is staged in ~1 us instead of six dependent passes)
+  {
+    constexpr int kChunks = WOfs<K0P, KCP>::total / 16;
+    const int cbeg[7] = {0, wofs[1] / 16, wofs[2] / 16, wofs[3] / 16, wofs[4] / 16, wofs[5] / 16, kChunks};
+#pragma unroll 3
+    for (int c = threadIdx.x; c < kChunks; c += blockDim.x) {
+      int i = 0;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    const int J = m.J[i], K = m.K[i];
-    uint8_t* w = wsm + wofs[i];
-    const int ncg = KP[i] / 8;
-    for (int e = threadIdx.x; e < JP[i] * ncg; e += blockDim.x) {
-      const int cg = e / JP[i], j = e - cg * JP[i];          // consecutive threads -> consecutive rows: conflict-free STS.128
+      for (int t = 1; t < 6; ++t) i += c >= cbeg[t] ? 1 : 0;
+      const int J = m.J[i], K = m.K[i];
+      const int jp = (i == 2 || i == 5) ? 16 : 64;
+      const int e = c - cbeg[i];
+      const int cg = e / jp, j = e - cg * jp;                // consecutive threads -> consecutive rows: conflict-free STS.128
+      const float* src = params + m.W[i] + j * K + cg * 8;
       float v[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int k = cg * 8 + q;
-        v[q] = (j < J && k < K) ? __ldg(params + m.W[i] + j * K + k) : 0.f;
-      }
-      store_chunk(w, j, cg, JP[i], v);
+      for (int q = 0; q < 8; ++q) v[q] = (j < J && cg * 8 + q < K) ? __ldg(src + q) : 0.f;
+      store_chunk(wsm + wofs[i], j, cg, jp, v);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int J = m.J[i];
+    if (bias_f32 != nullptr) {               // plain fp32 biases for kernels that add them in the epilogue
+      for (int j = threadIdx.x; j < 64; j += blockDim.x) bias_f32[i * 64 + j] = j < J ? __ldg(params + m.b[i] + j) : 0.f;
+      continue;
     }
     // bias tile [JP x 16] (K-major B operand of the bias MMA): col 0 = bf16(b), col 1 = bf16(b - bf16(b))
     uint8_t* bt = bias_sm + BOfs::ofs(i);
@@ -88,6 +101,7 @@ __device__ __forceinline__ void stage_weights_bf16(const float* __restrict__ par
       store_chunk(bt, j, cg, JP[i], v);
     }
   }
+  if (bias_f32 != nullptr) return;
   // ones16 [128 x 16] (A operand of the bias MMA): cols 0,1 = 1
   for (int e = threadIdx.x; e < kTile * 2; e += blockDim.x) {
     const int cg = e / kTile, rr = e - cg * kTile;
@@ -97,43 +111,52 @@ __device__ __forceinline__ void stage_weights_bf16(const float* __restrict__ par
   }
 }
 
+// Shared-memory operand addresses are carried in 16-byte units (a4 = byte address >> 4) so that a descriptor is one
+// integer add on the low word (address + leading-byte-offset bits) next to a constant high word.
+__device__ __forceinline__ uint64_t desc64(uint32_t a4, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint32_t lo = a4 + ((lbo_bytes >> 4) << 16);
+  const uint32_t hi = (sbo_bytes >> 4) | (1u << 14);                   // bit 46: tcgen05 descriptor version
+  return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ uint32_t a4_of(const void* p) { return smem_u32(p) >> 4; }
+
 // D[128 x N] (+)= A[128 x K] * W^T : A K-major activation tile, B K-major weight tile (forward)
-__device__ __forceinline__ void issue_fwd(uint32_t tmem_d, uint32_t a_tile, uint32_t w_tile, int JP, int KP,
+__device__ __forceinline__ void issue_fwd(uint32_t tmem_d, uint32_t a4, uint32_t w4, int JP, int KP,
                                           bool accumulate = false) {
   const uint32_t idesc = make_idesc(128, JP, false, false);
 #pragma unroll
   for (int kk = 0; kk < KP / 16; ++kk) {
-    const uint64_t a = make_desc(a_tile + kk * 2 * kLBO128, kLBO128, 128);
-    const uint64_t b = make_desc(w_tile + kk * 2 * JP * 16, JP * 16, 128);
+    const uint64_t a = desc64(a4 + kk * (2 * kLBO128 / 16), kLBO128, 128);
+    const uint64_t b = desc64(w4 + kk * 2 * JP, JP * 16, 128);
     mma_f16(tmem_d, a, b, idesc, accumulate || kk > 0);
   }
 }
 // D[128 x JP] = b (broadcast over rows) + A W^T: the bias enters as ones16 x biasB^T
-__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_tile, uint32_t w_tile, uint32_t ones16,
-                                            uint32_t bias_tile, int JP, int KP) {
-  issue_fwd(tmem_d, ones16, bias_tile, JP, 16, false);
-  issue_fwd(tmem_d, a_tile, w_tile, JP, KP, true);
+__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a4, uint32_t w4, uint32_t ones16_4,
+                                            uint32_t bias4, int JP, int KP) {
+  issue_fwd(tmem_d, ones16_4, bias4, JP, 16, false);
+  issue_fwd(tmem_d, a4, w4, JP, KP, true);
 }
 // D[128 x KP] = dZ[128 x JP] * W : A K-major dZ tile, B = weight tile [JP x KP] read MN-major (N = k, K = j)
-__device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t dz_tile, uint32_t w_tile, int JP, int KP) {
+__device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t dz4, uint32_t w4, int JP, int KP) {
   const uint32_t idesc = make_idesc(128, KP, false, true);
 #pragma unroll
   for (int kk = 0; kk < JP / 16; ++kk) {
-    const uint64_t a = make_desc(dz_tile + kk * 2 * kLBO128, kLBO128, 128);
-    const uint64_t b = make_desc(w_tile + kk * 256, 128, JP * 16);
+    const uint64_t a = desc64(dz4 + kk * (2 * kLBO128 / 16), kLBO128, 128);
+    const uint64_t b = desc64(w4 + kk * 16, 128, JP * 16);
     mma_f16(tmem_d, a, b, idesc, kk > 0);
   }
 }
 // G[M x N] += At^T[M x 128] * Bt[128 x N]: both tiles [128 points x cols] read MN-major, reduction over points.
-// (weight gradient: At = dZ, Bt = activation, M = 64; for the 16-wide layers the roles swap and M = 128 so that the
-//  ones column group behind the activation tile adds the bias-gradient row: transposed gradient)
-__device__ __forceinline__ void issue_wgrad(uint32_t tmem_g, uint32_t a_tile, uint32_t b_tile, int N, bool accumulate,
+// (weight gradient: At = dZ, Bt = activation tile + its ones column group, M = 64; for the 16-wide layers the roles
+//  swap and M = 128 so that the ones column group behind the activation tile adds the bias-gradient row: transposed)
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_g, uint32_t a4, uint32_t b4, int N, bool accumulate,
                                             int M = 64) {
   const uint32_t idesc = make_idesc(M, N, true, true);
 #pragma unroll
   for (int kk = 0; kk < kTile / 16; ++kk) {
-    const uint64_t a = make_desc(a_tile + kk * 256, 128, kLBO128);
-    const uint64_t b = make_desc(b_tile + kk * 256, 128, kLBO128);
+    const uint64_t a = desc64(a4 + kk * 16, 128, kLBO128);
+    const uint64_t b = desc64(b4 + kk * 16, 128, kLBO128);
     mma_f16(tmem_g, a, b, idesc, accumulate || kk > 0);
   }
 }
@@ -173,7 +196,7 @@ __global__ void __launch_bounds__(128) umma_debug_kernel(int mode, const float* 
   fence_after_sync();
   const uint32_t tbase = tslot;
   if (tid == 0) {
-    const uint32_t at = smem_u32(a_t), bt = smem_u32(b_t);
+    const uint32_t at = a4_of(a_t), bt = a4_of(b_t);
     if (mode == 0) {
       issue_fwd(tbase, at, bt, N, K);
     } else if (mode == 1) {
@@ -206,25 +229,78 @@ __global__ void __launch_bounds__(128) umma_debug_kernel(int mode, const float* 
   if (warp == 0) tmem_dealloc<64>(tbase);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// tensor-pipe micro-benchmark (debug): `reps` tcgen05.mma of shape M x N x 16 issued back to back by one thread,
+// round-robin over `nacc` accumulators (nacc = 1: one dependent accumulation chain), then one commit.
+// cycles[0] = issue start -> completion observed, cycles[1] = issue start -> last MMA issued.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) umma_bench_kernel(int M, int N, int reps, int nacc, int mn_major,
+                                                          long long* __restrict__ cycles) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int e = tid; e < 65536 / 16; e += 128) reinterpret_cast<uint4*>(sm)[e] = make_uint4(0, 0, 0, 0);
+  if (warp == 0) tmem_alloc<512>(&tslot);
+  if (tid == 0) { mbar_init(&mbar, 1); fence_mbar_init(); }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = tslot;
+  if (warp == 0) {
+    long long t0 = 0, t1 = 0;
+    if (elect_one()) {
+      const uint32_t a4 = a4_of(sm), b4 = a4_of(sm + 32768);
+      const uint32_t idesc = make_idesc(M, N, mn_major != 0, mn_major != 0);
+      const uint64_t a = mn_major ? desc64(a4, 128, kLBO128) : desc64(a4, kLBO128, 128);
+      const uint64_t b = mn_major ? desc64(b4, 128, kLBO128) : desc64(b4, N * 16, 128);
+      t0 = clock64();
+      for (int i = 0; i < reps; ++i) mma_f16(tbase + (i % nacc) * N, a, b, idesc, i >= nacc);
+      t1 = clock64();
+      commit(&mbar);
+    }
+    __syncwarp();
+    mbar_wait(&mbar, 0);
+    const long long t2 = clock64();
+    t0 = __shfl_sync(kFull, t0, 0);   // elected lane is lane 0 in practice; good enough for a probe
+    t1 = __shfl_sync(kFull, t1, 0);
+    if (tid == 0) { cycles[0] = t2 - t0; cycles[1] = t1 - t0; }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tbase);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // tile-group side helpers (r = this thread's row in the tile, 0..127)
 // ---------------------------------------------------------------------------------------------------------------
+// One tile of features -> bf16 A tile.  Fast path (contiguous fp32 rows of exactly K0P floats): the tile is a contiguous
+// 128*K0P*4-byte block, read with lane-contiguous float4 loads (4 lines per warp instruction instead of 32) and
+// scattered into the canonical layout with 8-byte shared-memory stores.
 template <int K0P>
-__device__ __forceinline__ void load_features(const float* __restrict__ feat, long long stride, long long gp, long long n,
+__device__ __forceinline__ void load_features(const float* __restrict__ feat, long long stride, long long tile0, long long n,
                                               int in0, bool vec_ok, int r, uint8_t* x0) {
-  if (vec_ok) {                                   // in0 == K0P, 16-byte aligned rows
-    const float4* src = reinterpret_cast<const float4*>(feat + gp * stride);
-    float4 q[K0P / 4];
+  if (vec_ok) {                                   // in0 == stride == K0P, 16-byte aligned base
+    constexpr int kQ = K0P / 4;                   // float4 per row
+    const float4* src = reinterpret_cast<const float4*>(feat + tile0 * K0P);
+    float4 q[kQ];
 #pragma unroll
-    for (int i = 0; i < K0P / 4; ++i) q[i] = gp < n ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < kQ; ++it) {
+      const int idx = it * kTile + r;
+      q[it] = tile0 + idx / kQ < n ? __ldg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
-    for (int cg = 0; cg < K0P / 8; ++cg) {
-      uint4 o;
-      o.x = pack_bf16(q[2 * cg].x, q[2 * cg].y); o.y = pack_bf16(q[2 * cg].z, q[2 * cg].w);
-      o.z = pack_bf16(q[2 * cg + 1].x, q[2 * cg + 1].y); o.w = pack_bf16(q[2 * cg + 1].z, q[2 * cg + 1].w);
-      *reinterpret_cast<uint4*>(x0 + chunk_off(r, cg, kTile)) = o;
+    for (int it = 0; it < kQ; ++it) {
+      const int idx = it * kTile + r, row = idx / kQ, c4 = idx % kQ;
+      uint2 o;
+      o.x = pack_bf16(q[it].x, q[it].y);
+      o.y = pack_bf16(q[it].z, q[it].w);
+      *reinterpret_cast<uint2*>(x0 + chunk_off(row, c4 >> 1, kTile) + (c4 & 1) * 8) = o;
     }
   } else {
+    const long long gp = tile0 + r;
 #pragma unroll
     for (int cg = 0; cg < K0P / 8; ++cg) {
       float v[8];
@@ -255,26 +331,32 @@ __device__ __forceinline__ void relu_epilogue64(uint32_t taddr, int r, uint8_t* 
   }
 }
 
-// dA (64 accumulator columns) * [activation > 0] -> bf16 dZ written over the activation tile itself
-__device__ __forceinline__ void masked_dz_inplace64(uint32_t taddr, int r, uint8_t* tile) {
+// dA (64 accumulator columns) * [activation > 0] -> bf16 dZ written over the activation tile itself.  The values are
+// formed in registers first; `before_store()` (wait for the weight-gradient GEMM still reading the tile) runs right
+// before the in-place store.
+template <typename F>
+__device__ __forceinline__ void masked_dz_inplace64(uint32_t taddr, int r, uint8_t* tile, F before_store) {
+  uint4 o[8];
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     float v[32];
     tmem_ld<32>(taddr + half * 32, v);
 #pragma unroll
     for (int cg = 0; cg < 4; ++cg) {
-      uint4* q = reinterpret_cast<uint4*>(tile + chunk_off(r, half * 4 + cg, kTile));
-      const uint4 h = *q;
+      const uint4 h = *reinterpret_cast<const uint4*>(tile + chunk_off(r, half * 4 + cg, kTile));
       const float* p = v + cg * 8;
-      uint4 o;
-      o.x = mask_pos_bf16x2(pack_bf16(p[0], p[1]), h.x); o.y = mask_pos_bf16x2(pack_bf16(p[2], p[3]), h.y);
-      o.z = mask_pos_bf16x2(pack_bf16(p[4], p[5]), h.z); o.w = mask_pos_bf16x2(pack_bf16(p[6], p[7]), h.w);
-      *q = o;
+      uint4& q = o[half * 4 + cg];
+      q.x = mask_pos_bf16x2(pack_bf16(p[0], p[1]), h.x); q.y = mask_pos_bf16x2(pack_bf16(p[2], p[3]), h.y);
+      q.z = mask_pos_bf16x2(pack_bf16(p[4], p[5]), h.z); q.w = mask_pos_bf16x2(pack_bf16(p[6], p[7]), h.w);
     }
   }
+  before_store();
+#pragma unroll
+  for (int cg = 0; cg < 8; ++cg) *reinterpret_cast<uint4*>(tile + chunk_off(r, cg, kTile)) = o[cg];
 }
 
 // colour-net input tile: [15 features | direction encoding | (optionally a 1.0 at column 15+dv) | 0 ...]
+// (all rows of a ray read the same direction row: broadcast loads that hit L1 after the first touch)
 template <int KCP, bool PLANT_ONE>
 __device__ __forceinline__ void build_cin(const float* o16, const float* __restrict__ dirs, long long dir_row, int dv,
                                           bool valid, int r, uint8_t* cin) {
@@ -293,6 +375,9 @@ __device__ __forceinline__ void build_cin(const float* o16, const float* __restr
     store_chunk(cin, r, cg, kTile, v);
   }
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // group -> MMA warp: "my A tile is written (and my TMEM reads are finished)";  MMA warp -> group: commit on done
 #define HBR_SIGNAL()          \
@@ -359,9 +444,9 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     // ===== MMA issuer of group g: converged warp, straight-line layer sequence, one elected lane issues =====
     const int g = warp - 4 * G;
     const uint32_t tb = __shfl_sync(kFull, tbase, 0);
-    const uint32_t wa = smem_u32(wsm), ba = smem_u32(sm + SM::off_bias), o16a = smem_u32(sm + SM::off_ones16);
+    const uint32_t wa = a4_of(wsm), ba = a4_of(sm + SM::off_bias), o16a = a4_of(sm + SM::off_ones16);
     const uint32_t d = tb + g * 64;
-    const uint32_t a = smem_u32(sm + SM::off_buf + g * SM::buf_bytes);
+    const uint32_t a = a4_of(sm + SM::off_buf + g * SM::buf_bytes);
     uint64_t* full = bars + g;
     uint64_t* done = bars + G + g;
     uint32_t par = 0;
@@ -381,12 +466,12 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     if (TRACE && g == 0 && blockIdx.x == 0 && lane == 0 && tmi < 500) trace[1024 + tmi++] = clock64();  \
   } while (0)
     for (long long tile = (long long)g * gridDim.x + blockIdx.x; tile < ntiles; tile += nslots) {
-      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w0, o16a, ba + BOfs::ofs(0), 64, K0P));
-      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w1, o16a, ba + BOfs::ofs(1), 64, 64));
-      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w2, o16a, ba + BOfs::ofs(2), 16, 64));
-      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w3, o16a, ba + BOfs::ofs(3), 64, KCP));
-      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w4, o16a, ba + BOfs::ofs(4), 64, 64));
-      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w5, o16a, ba + BOfs::ofs(5), 16, 64));
+      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w0 / 16, o16a, ba + BOfs::ofs(0) / 16, 64, K0P));
+      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w1 / 16, o16a, ba + BOfs::ofs(1) / 16, 64, 64));
+      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w2 / 16, o16a, ba + BOfs::ofs(2) / 16, 16, 64));
+      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w3 / 16, o16a, ba + BOfs::ofs(3) / 16, 64, KCP));
+      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w4 / 16, o16a, ba + BOfs::ofs(4) / 16, 64, 64));
+      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w5 / 16, o16a, ba + BOfs::ofs(5) / 16, 16, 64));
     }
   } else {
     // ===== tile group =====
@@ -397,7 +482,7 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     uint64_t* done = bars + G + g;
     const uint32_t taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + g * 64;
     uint32_t dphase = 0;
-    const bool vec_ok = in0 == K0P && (feat_stride & 3) == 0 && ((uintptr_t)feat & 15) == 0;
+    const bool vec_ok = in0 == K0P && feat_stride == K0P && ((uintptr_t)feat & 15) == 0;
     int tgi = 0;
     (void)tgi;
 #define TR()                                                                                  \
@@ -407,8 +492,11 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     for (long long tile = (long long)g * gridDim.x + blockIdx.x; tile < ntiles; tile += nslots) {
       const long long gp = tile * kTile + r;
       const bool valid = gp < n;
+      const long long dir_row = valid ? gp / dir_group : 0;
+      if (valid && lane == 0) prefetch_l1(dirs + dir_row * dv);
       TR();
-      load_features<K0P>(feat, feat_stride, gp, n, in0, vec_ok, r, buf);
+      load_features<K0P>(feat, feat_stride, tile * kTile, n, in0, vec_ok, r, buf);
+      if ((tile + nslots) * kTile + r < n) prefetch_l2(feat + ((tile + nslots) * kTile + r) * feat_stride);
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
       relu_epilogue64(taddr, r, buf);
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
@@ -417,7 +505,7 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       float o16[16];
       tmem_ld<16>(taddr, o16);
       const float density = o16[0] > 0.f ? o16[0] : 0.01f * o16[0];     // LeakyReLU (test_hash.py:62)
-      build_cin<KCP, false>(o16, dirs, valid ? gp / dir_group : 0, dv, valid, r, buf);
+      build_cin<KCP, false>(o16, dirs, dir_row, dv, valid, r, buf);
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
       relu_epilogue64(taddr, r, buf);
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
@@ -445,52 +533,72 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kCg = kTile * 16;                                        // bytes of one 8-column group of a 128-row tile
 
+// bias + ReLU on 64 accumulator columns -> bf16 activation tile (the backward kernel adds the bias here: its two tile
+// groups leave the CUDA cores mostly idle, while every MMA saved shortens the issue-bound critical path)
+__device__ __forceinline__ void relu_bias_epilogue64(uint32_t taddr, const float* bias, int r, uint8_t* tile) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float v[32];
+    tmem_ld<32>(taddr + half * 32, v);
+#pragma unroll
+    for (int cg = 0; cg < 4; ++cg) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + half * 32 + cg * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias + half * 32 + cg * 8 + 4);
+      const float* p = v + cg * 8;
+      uint4 o;
+      o.x = pack_bf16_relu(p[0] + b0.x, p[1] + b0.y); o.y = pack_bf16_relu(p[2] + b0.z, p[3] + b0.w);
+      o.z = pack_bf16_relu(p[4] + b1.x, p[5] + b1.y); o.w = pack_bf16_relu(p[6] + b1.z, p[7] + b1.w);
+      *reinterpret_cast<uint4*>(tile + chunk_off(r, half * 4 + cg, kTile)) = o;
+    }
+  }
+}
+
 template <int K0P, int KCP, int G>
 struct BwdSmem {
   // KCP == 48 (15 + d_view <= 40): column group 5 of the colour-net input tile is pure padding and doubles as the
   // first half of the 16-wide dZ tile (its partner column group sits right behind the tile)
   static constexpr bool kAliasDzs = KCP == 48;
-  static constexpr int off_bias = WOfs<K0P, KCP>::total;
-  static constexpr int off_ones16 = off_bias + BOfs::total;
-  static constexpr int off_onesb = off_ones16 + kTile * 16 * 2;         // one column group of 1.0 (B operand, N = 8)
-  static constexpr int off_grp = off_onesb + kCg;
-  // per group; h2 and c2 are each followed by a ones column group and >= 14 KB of further tiles (M = 128 operand)
+  static constexpr int off_bias = WOfs<K0P, KCP>::total;                // 6 x 64 fp32
+  static constexpr int off_grp = off_bias + 6 * 64 * 4;
+  // per group: every activation tile is followed by a column group of 1.0 (bias gradient through the weight-gradient
+  // GEMM); h2 and c2 additionally by >= 7 further column groups of finite data (their M = 128 operand reads them)
   static constexpr int h2 = 0;
   static constexpr int c2 = h2 + 9 * kCg;
   static constexpr int x0 = c2 + 9 * kCg;
-  static constexpr int h1 = x0 + kTile * K0P * 2;
-  static constexpr int c1 = h1 + 8 * kCg;
-  static constexpr int cin = c1 + 8 * kCg;
+  static constexpr int h1 = x0 + kTile * K0P * 2 + kCg;
+  static constexpr int c1 = h1 + 9 * kCg;
+  static constexpr int cin = c1 + 9 * kCg;
   static constexpr int dzs = kAliasDzs ? cin + 5 * kCg : cin + kTile * KCP * 2;
   static constexpr int grp_bytes = dzs + 2 * kCg;
-  static constexpr int off_bar = off_grp + G * grp_bytes;
-  static constexpr int total = off_bar + 2 * G * 8 + 16;
+  static constexpr int off_bar = off_grp + G * grp_bytes;              // full[G], doneA[G], doneB[G], startB[G]
+  static constexpr int total = off_bar + 4 * G * 8 + 16;
   static_assert(total <= 232448, "shared memory budget exceeded");
 };
 
 // TMEM columns: [0, 128) work accumulators of the (up to two) groups; then the gradient accumulators:
-//   layers 0,1,3,4 (M = 64): G[j][k], rows = output neuron, KP columns, followed by 8 bias-gradient columns
-//     (layer 3 with KCP == 48 has its bias gradient in column 15 + d_view instead);
+//   layers 0,1,3,4 (M = 64): G[j][k], rows = output neuron; KP columns + 8 bias-gradient columns from the ones group
+//     (layer 3 with KCP == 48 has its bias gradient in column 15 + d_view: the 1.0 planted in the input tile);
 //   layers 2,5 (M = 128): transposed G^T[k][j], 16 columns, rows 0..63 = input index, row 64 = bias gradient.
 template <int K0P, int KCP>
 struct BwdTmem {
   static constexpr bool kCinOne = KCP == 48;
-  static constexpr int g0 = 128, b0 = g0 + K0P;
-  static constexpr int g1 = b0 + 8, b1 = g1 + 64;
-  static constexpr int g2 = b1 + 8;
-  static constexpr int g3 = g2 + 16, b3 = g3 + KCP;
-  static constexpr int g4 = b3 + (kCinOne ? 0 : 8), b4 = g4 + 64;
-  static constexpr int g5 = b4 + 8;
+  static constexpr int n0 = K0P + 8, n1 = 72, n3 = KCP + (kCinOne ? 0 : 8), n4 = 72;
+  static constexpr int g0 = 128;
+  static constexpr int g1 = g0 + n0;
+  static constexpr int g2 = g1 + n1;
+  static constexpr int g3 = g2 + 16;
+  static constexpr int g4 = g3 + n3;
+  static constexpr int g5 = g4 + n4;
   static constexpr int end = g5 + 16;
-  static_assert(end <= 512, "TMEM budget exceeded");
+  static_assert(end <= 512 && g4 + 80 <= 512, "TMEM budget exceeded");
 };
 
-template <int K0P, int KCP, int G>
-__global__ void __launch_bounds__(G * kTile + 32, 1)
+template <int K0P, int KCP, int G, bool TRACE = false>
+__global__ void __launch_bounds__(G * kTile + 64, 1)
 mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const float* __restrict__ dirs, long long dir_group,
                   long long n, const float* __restrict__ params, int in0, int dv, const float* __restrict__ out,
                   const float* __restrict__ dout, float* __restrict__ dfeat, long long dfeat_stride,
-                  float* __restrict__ ddirs, float* __restrict__ dparams) {
+                  float* __restrict__ ddirs, float* __restrict__ dparams, long long* __restrict__ trace = nullptr) {
   using SM = BwdSmem<K0P, KCP, G>;
   using WO = WOfs<K0P, KCP>;
   using TM = BwdTmem<K0P, KCP>;
@@ -499,31 +607,39 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   extern __shared__ __align__(128) uint8_t sm[];
   const MlpLayout m = make_layout(in0, dv);
   uint8_t* wsm = sm;
+  float* bias = reinterpret_cast<float*>(sm + SM::off_bias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM::off_bar);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2 * G);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4 * G);
   const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2000] = clock64();
 
   if (warp == 0) tmem_alloc<512>(tslot);
   if (threadIdx.x == 32) {
-    for (int g = 0; g < G; ++g) { mbar_init(bars + g, kTile); mbar_init(bars + G + g, 1); }
+    for (int g = 0; g < G; ++g) {
+      mbar_init(bars + g, kTile);
+      mbar_init(bars + G + g, 1);
+      mbar_init(bars + 2 * G + g, 1);
+      mbar_init(bars + 3 * G + g, 1);
+    }
     fence_mbar_init();
   }
-  stage_weights_bf16<K0P, KCP>(params, m, wsm, sm + SM::off_bias, sm + SM::off_ones16);
+  stage_weights_bf16<K0P, KCP>(params, m, wsm, nullptr, nullptr, bias);
   {
+    // zero the group regions (the M = 128 operands read column groups they do not own: keep them finite), then the ones
+    for (int e = threadIdx.x; e < G * SM::grp_bytes / 16; e += blockDim.x)
+      reinterpret_cast<uint4*>(sm + SM::off_grp)[e] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
     const uint32_t one2 = pack_bf16(1.f, 1.f);
     const uint4 ones4 = make_uint4(one2, one2, one2, one2);
     for (int e = threadIdx.x; e < kTile; e += blockDim.x) {
-      reinterpret_cast<uint4*>(sm + SM::off_onesb)[e] = ones4;
       for (int g = 0; g < G; ++g) {
         uint8_t* gb = sm + SM::off_grp + g * SM::grp_bytes;
         reinterpret_cast<uint4*>(gb + SM::h2 + 8 * kCg)[e] = ones4;
         reinterpret_cast<uint4*>(gb + SM::c2 + 8 * kCg)[e] = ones4;
+        reinterpret_cast<uint4*>(gb + SM::x0 + kTile * K0P * 2)[e] = ones4;
+        reinterpret_cast<uint4*>(gb + SM::h1 + 8 * kCg)[e] = ones4;
+        reinterpret_cast<uint4*>(gb + SM::c1 + 8 * kCg)[e] = ones4;
       }
-    }
-    // the M = 128 operands read 7 column groups past the ones group: keep that memory finite from the start
-    for (int e = threadIdx.x; e < G * SM::grp_bytes / 16; e += blockDim.x) {
-      const int g = e / (SM::grp_bytes / 16), o = (e - g * (SM::grp_bytes / 16)) * 16;
-      if (o >= SM::x0) *reinterpret_cast<uint4*>(sm + SM::off_grp + g * SM::grp_bytes + o) = make_uint4(0, 0, 0, 0);
     }
   }
   fence_async_smem();
@@ -531,6 +647,7 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   __syncthreads();
   fence_after_sync();
   const uint32_t tbase = *tslot;
+  if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2001] = clock64();
   const long long ntiles = (n + kTile - 1) / kTile;
   const long long nslots = (long long)gridDim.x * G;
   long long nt[G];
@@ -540,80 +657,83 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     nt[g] = tiles_of_slot(ntiles, (long long)g * gridDim.x + blockIdx.x, nslots);
     cta_tiles += nt[g];
   }
+  const long long kmax = nt[0];                  // the slot of group 0 never has fewer tiles than a later group's
 
-  if (warp == 4 * G) {
-    // ===== the CTA's only MMA issuer: converged warp, fixed visiting order (stage-major, group-minor), straight-line
-    //       issue code; every gradient-accumulating MMA of the CTA comes from this one thread sequence =====
+  if (warp >= 4 * G) {
+    // ===== two MMA-issuing warps, both converged, both visiting the groups in the same fixed order:
+    //   warp A: waits on full[g]; forward recompute + dgrad GEMMs (work accumulators), commits to doneA[g] and, on the
+    //           backward stages, to startB[g];
+    //   warp B: waits on startB[g] (the chain-critical dgrad of a stage is complete, so it never queues behind a weight
+    //           gradient in the in-order tensor pipe); every weight/bias-gradient GEMM of the CTA (the accumulators all
+    //           tiles share), commits to doneB[g].  startB advances only on backward stages and the group cannot pass
+    //           one without doneB, so B's phase tracking cannot fall behind.
+    // The operand descriptors are rebuilt from two laundered base values in every stage: left to itself the compiler
+    // hoists the loop-invariant descriptors out of the tile loop and spills them. =====
+    const bool is_b = warp == 4 * G + 1;
     const uint32_t tb0 = __shfl_sync(kFull, tbase, 0);
-    const uint32_t sm0 = smem_u32(sm);
+    const uint32_t sm0 = a4_of(sm);
     uint32_t par[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) par[g] = 0;
     bool first = true;                           // gradient accumulators not yet written
-    // The operand descriptors are rebuilt from two laundered base values in every stage: left to itself the compiler
-    // hoists all ~400 loop-invariant descriptors out of the tile loop and spills them.
-#define HBR_BWD_STAGE(BODY)                                                \
+    int tmi = 0;
+    (void)tmi;
+#define HBR_BWD_STAGE(BWD, BODY)                                         \
   _Pragma("unroll") for (int g = 0; g < G; ++g) {                          \
     if (k < nt[g]) {                                                       \
-      mbar_wait(bars + g, par[g]);                                         \
+      mbar_wait(bars + (is_b ? 3 * G : 0) + g, par[g]);                    \
       par[g] ^= 1;                                                         \
-      fence_after_sync();                                                  \
-      if (elect_one()) {                                                   \
-        uint32_t sb = sm0, tb = tb0;                                       \
-        asm volatile("" : "+r"(sb), "+r"(tb));                             \
-        const uint32_t wa = sb, ba = sb + SM::off_bias, o16a = sb + SM::off_ones16, onesb = sb + SM::off_onesb; \
-        const uint32_t d = tb + g * 64;                                    \
-        const uint32_t base = sb + SM::off_grp + g * SM::grp_bytes;        \
-        const uint32_t x0a = base + SM::x0, h1a = base + SM::h1, h2a = base + SM::h2, cina = base + SM::cin, \
-                       c1a = base + SM::c1, c2a = base + SM::c2, dzsa = base + SM::dzs; \
-        (void)wa; (void)ba; (void)o16a; (void)onesb;                       \
-        (void)x0a; (void)h1a; (void)h2a; (void)cina; (void)c1a; (void)c2a; (void)dzsa; \
-        const bool acc = !(first && g == 0);                               \
-        (void)acc;                                                         \
-        BODY;                                                              \
-        commit(bars + G + g);                                              \
+      {                                                                    \
+        if (TRACE && !is_b && g == 0 && blockIdx.x == 0 && lane == 0 && tmi < 500) trace[1024 + tmi++] = clock64(); \
+        fence_after_sync();                                                \
+        if (elect_one()) {                                                 \
+          uint32_t sb = sm0, tb = tb0;                                     \
+          asm volatile("" : "+r"(sb), "+r"(tb));                           \
+          const uint32_t wa = sb;                                          \
+          const uint32_t d = tb + g * 64;                                  \
+          const uint32_t base = sb + (SM::off_grp + g * SM::grp_bytes) / 16; \
+          const uint32_t x0a = base + SM::x0 / 16, h1a = base + SM::h1 / 16, h2a = base + SM::h2 / 16, \
+                         cina = base + SM::cin / 16, c1a = base + SM::c1 / 16, c2a = base + SM::c2 / 16, \
+                         dzsa = base + SM::dzs / 16;                       \
+          (void)wa; (void)d; (void)x0a; (void)h1a; (void)h2a; (void)cina; (void)c1a; (void)c2a; (void)dzsa; \
+          const bool acc = !(first && g == 0);                             \
+          (void)acc;                                                       \
+          BODY;                                                            \
+          commit(bars + (is_b ? 2 * G : G) + g);                           \
+          if (!is_b && (BWD)) commit(bars + 3 * G + g);                    \
+        }                                                                  \
+        __syncwarp();                                                      \
+        if (TRACE && !is_b && g == 0 && blockIdx.x == 0 && lane == 0 && tmi < 500) trace[1024 + tmi++] = clock64(); \
       }                                                                    \
-      __syncwarp();                                                        \
     }                                                                      \
   }
-    const long long kmax = nt[0];                // slot of group 0 never has fewer tiles than a later group's
-    for (long long k = 0; k < kmax; ++k) {
-      // ---- forward recompute (layers 0..4) ----
-      HBR_BWD_STAGE(issue_layer(d, x0a, wa + WO::w0, o16a, ba + BOfs::ofs(0), 64, K0P));
-      HBR_BWD_STAGE(issue_layer(d, h1a, wa + WO::w1, o16a, ba + BOfs::ofs(1), 64, 64));
-      HBR_BWD_STAGE(issue_layer(d, h2a, wa + WO::w2, o16a, ba + BOfs::ofs(2), 16, 64));
-      HBR_BWD_STAGE(issue_layer(d, cina, wa + WO::w3, o16a, ba + BOfs::ofs(3), 64, KCP));
-      HBR_BWD_STAGE(issue_layer(d, c1a, wa + WO::w4, o16a, ba + BOfs::ofs(4), 64, 64));
-      // ---- backward: dgrad into the work accumulator, weight/bias gradients into the resident accumulators ----
-      HBR_BWD_STAGE({   // col_model.4: dZ = dzs (16 wide), input c2 (+ ones group): transposed gradient, M = 128
-        issue_dgrad(d, dzsa, wa + WO::w5, 16, 64);
-        issue_wgrad(tb + TM::g5, c2a, dzsa, 16, acc, 128);
-      });
-      HBR_BWD_STAGE({   // col_model.2: dZ in the c2 tile, input c1
-        issue_dgrad(d, c2a, wa + WO::w4, 64, 64);
-        issue_wgrad(tb + TM::g4, c2a, c1a, 64, acc);
-        issue_wgrad(tb + TM::b4, c2a, onesb, 8, acc);
-      });
-      HBR_BWD_STAGE({   // col_model.0: dZ in the c1 tile, input cin (bias gradient through the planted 1.0 column)
-        issue_dgrad(d, c1a, wa + WO::w3, 64, KCP);
-        issue_wgrad(tb + TM::g3, c1a, cina, KCP, acc);
-        if (!kCinOne) issue_wgrad(tb + TM::b3, c1a, onesb, 8, acc);
-      });
-      HBR_BWD_STAGE({   // sig_model.4: dZ = dzs (16 wide), input h2 (+ ones group): transposed
-        issue_dgrad(d, dzsa, wa + WO::w2, 16, 64);
-        issue_wgrad(tb + TM::g2, h2a, dzsa, 16, acc, 128);
-      });
-      HBR_BWD_STAGE({   // sig_model.2: dZ in the h2 tile, input h1
-        issue_dgrad(d, h2a, wa + WO::w1, 64, 64);
-        issue_wgrad(tb + TM::g1, h2a, h1a, 64, acc);
-        issue_wgrad(tb + TM::b1, h2a, onesb, 8, acc);
-      });
-      HBR_BWD_STAGE({   // sig_model.0: dZ in the h1 tile, input x0
-        issue_dgrad(d, h1a, wa + WO::w0, 64, K0P);
-        issue_wgrad(tb + TM::g0, h1a, x0a, K0P, acc);
-        issue_wgrad(tb + TM::b0, h1a, onesb, 8, acc);
-      });
-      first = false;
+    if (!is_b) {
+      for (long long k = 0; k < kmax; ++k) {
+        // ---- forward recompute (layers 0..4; bias and activation in the epilogue) ----
+        HBR_BWD_STAGE(false, issue_fwd(d, x0a, wa + WO::w0 / 16, 64, K0P));
+        HBR_BWD_STAGE(false, issue_fwd(d, h1a, wa + WO::w1 / 16, 64, 64));
+        HBR_BWD_STAGE(false, issue_fwd(d, h2a, wa + WO::w2 / 16, 16, 64));
+        HBR_BWD_STAGE(false, issue_fwd(d, cina, wa + WO::w3 / 16, 64, KCP));
+        HBR_BWD_STAGE(false, issue_fwd(d, c1a, wa + WO::w4 / 16, 64, 64));
+        // ---- dgrad: dA = dZ W ----
+        HBR_BWD_STAGE(true, issue_dgrad(d, dzsa, wa + WO::w5 / 16, 16, 64));      // col_model.4
+        HBR_BWD_STAGE(true, issue_dgrad(d, c2a, wa + WO::w4 / 16, 64, 64));       // col_model.2 (dZ in the c2 tile)
+        HBR_BWD_STAGE(true, issue_dgrad(d, c1a, wa + WO::w3 / 16, 64, KCP));      // col_model.0 (dZ in the c1 tile)
+        HBR_BWD_STAGE(true, issue_dgrad(d, dzsa, wa + WO::w2 / 16, 16, 64));      // sig_model.4
+        HBR_BWD_STAGE(true, issue_dgrad(d, h2a, wa + WO::w1 / 16, 64, 64));       // sig_model.2 (dZ in the h2 tile)
+        HBR_BWD_STAGE(true, issue_dgrad(d, h1a, wa + WO::w0 / 16, 64, K0P));      // sig_model.0 (dZ in the h1 tile)
+      }
+    } else {
+      for (long long k = 0; k < kmax; ++k) {
+        // ---- weight + bias gradients: reduction over the tile's 128 points ----
+        HBR_BWD_STAGE(true, issue_wgrad(tb + TM::g5, c2a, dzsa, 16, acc, 128));   // transposed; input c2 | ones
+        HBR_BWD_STAGE(true, issue_wgrad(tb + TM::g4, c2a, c1a, TM::n4, acc));     // dZ = c2 tile, input c1 | ones
+        HBR_BWD_STAGE(true, issue_wgrad(tb + TM::g3, c1a, cina, TM::n3, acc));    // dZ = c1 tile, input cin (planted 1.0)
+        HBR_BWD_STAGE(true, issue_wgrad(tb + TM::g2, h2a, dzsa, 16, acc, 128));   // transposed; input h2 | ones
+        HBR_BWD_STAGE(true, issue_wgrad(tb + TM::g1, h2a, h1a, TM::n1, acc));     // dZ = h2 tile, input h1 | ones
+        HBR_BWD_STAGE(true, issue_wgrad(tb + TM::g0, h1a, x0a, TM::n0, acc));     // dZ = h1 tile, input x0 | ones
+        first = false;
+      }
     }
   } else {
     // ===== tile group =====
@@ -624,35 +744,55 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
             *c2 = gb + SM::c2, *dzs = gb + SM::dzs;
     uint64_t* full = bars + g;
     uint64_t* done = bars + G + g;
+    uint64_t* doneb = bars + 2 * G + g;
     const uint32_t taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + g * 64;
-    uint32_t dphase = 0;
-    const bool vec_ok = in0 == K0P && (feat_stride & 3) == 0 && ((uintptr_t)feat & 15) == 0;
-    const bool dvec_ok = dfeat != nullptr && in0 == K0P && (dfeat_stride & 3) == 0 && ((uintptr_t)dfeat & 15) == 0;
+    uint32_t dphase = 0, bphase = 0;
+    // weight-gradient GEMM of the stage has finished reading its tiles (they are about to be overwritten in place)
+#define HBR_WAIT_B()           \
+  do {                         \
+    mbar_wait(doneb, bphase);  \
+    bphase ^= 1;               \
+  } while (0)
+    const bool vec_ok = in0 == K0P && feat_stride == K0P && ((uintptr_t)feat & 15) == 0;
+    const bool dvec_ok = dfeat != nullptr && in0 == K0P && dfeat_stride == K0P && ((uintptr_t)dfeat & 15) == 0 && K0P <= 32;
+    int tgi = 0;
+    (void)tgi;
     for (long long tile = (long long)g * gridDim.x + blockIdx.x; tile < ntiles; tile += nslots) {
       const long long gp = tile * kTile + r;
       const bool valid = gp < n;
+      const long long dir_row = valid ? gp / dir_group : 0;
+      if (valid && lane == 0) prefetch_l1(dirs + dir_row * dv);
       float4 fo = make_float4(0.f, 0.f, 0.f, 0.f), go = fo;           // saved forward output, upstream gradient
       if (valid) {
         fo = __ldg(reinterpret_cast<const float4*>(out + gp * 4));
         go = __ldg(reinterpret_cast<const float4*>(dout + gp * 4));
       }
+      TR();
       // ---- recompute the forward activations ----
-      load_features<K0P>(feat, feat_stride, gp, n, in0, vec_ok, r, x0);
-      HBR_SIGNAL(); HBR_WAIT();
-      relu_epilogue64(taddr, r, h1);
-      HBR_SIGNAL(); HBR_WAIT();
-      relu_epilogue64(taddr, r, h2);
-      HBR_SIGNAL(); HBR_WAIT();
-      const long long dir_row = valid ? gp / dir_group : 0;
+      load_features<K0P>(feat, feat_stride, tile * kTile, n, in0, vec_ok, r, x0);
+      if ((tile + nslots) * kTile + r < n) {
+        prefetch_l2(feat + ((tile + nslots) * kTile + r) * feat_stride);
+        if ((r & 7) == 0) {
+          prefetch_l2(out + ((tile + nslots) * kTile + r) * 4);
+          prefetch_l2(dout + ((tile + nslots) * kTile + r) * 4);
+        }
+      }
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
+      relu_bias_epilogue64(taddr, bias + 0, r, h1);
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
+      relu_bias_epilogue64(taddr, bias + 64, r, h2);
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
       {
         float o16[16];
         tmem_ld<16>(taddr, o16);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) o16[k] += bias[128 + k];
         build_cin<KCP, kCinOne>(o16, dirs, dir_row, dv, valid, r, cin);
       }
-      HBR_SIGNAL(); HBR_WAIT();
-      relu_epilogue64(taddr, r, c1);
-      HBR_SIGNAL(); HBR_WAIT();
-      relu_epilogue64(taddr, r, c2);
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
+      relu_bias_epilogue64(taddr, bias + 192, r, c1);
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
+      relu_bias_epilogue64(taddr, bias + 256, r, c2);
       {
         // d(rgb_pre) = g * ELU'(pre), with ELU'(pre) = pre > 0 ? 1 : exp(pre) = elu(pre) + 1 from the saved output
         float dz16[16];
@@ -664,11 +804,12 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         store_chunk(dzs, r, 0, kTile, dz16);
         store_chunk(dzs, r, 1, kTile, dz16 + 8);
       }
-      HBR_SIGNAL(); HBR_WAIT();                  // col_model.4 backward done: work = dA(c2)
-      masked_dz_inplace64(taddr, r, c2);
-      HBR_SIGNAL(); HBR_WAIT();                  // col_model.2 done: work = dA(c1)
-      masked_dz_inplace64(taddr, r, c1);
-      HBR_SIGNAL(); HBR_WAIT();                  // col_model.0 done: work[0,KCP) = d(cin)
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // col_model.4 backward: work = dA(c2)
+      masked_dz_inplace64(taddr, r, c2, [&] { HBR_WAIT_B(); });
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // col_model.2: work = dA(c1)
+      masked_dz_inplace64(taddr, r, c1, [&] { HBR_WAIT_B(); });
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // col_model.0: work[0,KCP) = d(cin)
+      HBR_WAIT_B();
       {
         float dc[KCP], dz16[16];
         tmem_ld<KCP>(taddr, dc);
@@ -694,85 +835,107 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
           }
         }
       }
-      HBR_SIGNAL(); HBR_WAIT();                  // sig_model.4 done: work = dA(h2)
-      masked_dz_inplace64(taddr, r, h2);
-      HBR_SIGNAL(); HBR_WAIT();                  // sig_model.2 done: work = dA(h1)
-      masked_dz_inplace64(taddr, r, h1);
-      HBR_SIGNAL(); HBR_WAIT();                  // sig_model.0 done: work[0,K0P) = d(feat)
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // sig_model.4: work = dA(h2)
+      masked_dz_inplace64(taddr, r, h2, [&] { HBR_WAIT_B(); });
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // sig_model.2: work = dA(h1)
+      masked_dz_inplace64(taddr, r, h1, [&] { HBR_WAIT_B(); });
+      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // sig_model.0: work[0,K0P) = d(feat)
       if (dfeat != nullptr) {
         float df[K0P];
         tmem_ld<K0P>(taddr, df);
-        if (valid) {
-          if (dvec_ok) {
-            float4* dst = reinterpret_cast<float4*>(dfeat + gp * dfeat_stride);
+        if (dvec_ok) {
+          // rows -> the (dead) h2 tile as fp32 with an XOR swizzle on the 16-byte chunk index, then lane-contiguous
+          // float4 stores of the tile's contiguous 128*K0P*4-byte block of dfeat
+          constexpr int kQ = K0P / 4;
+          float4* stg = reinterpret_cast<float4*>(h2);
 #pragma unroll
-            for (int i = 0; i < K0P / 4; ++i) dst[i] = make_float4(df[4 * i], df[4 * i + 1], df[4 * i + 2], df[4 * i + 3]);
-          } else {
+          for (int c = 0; c < kQ; ++c)
+            stg[r * kQ + (c ^ (r & 7))] = make_float4(df[4 * c], df[4 * c + 1], df[4 * c + 2], df[4 * c + 3]);
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+          float4* dst = reinterpret_cast<float4*>(dfeat + tile * kTile * K0P);
 #pragma unroll
-            for (int k = 0; k < K0P; ++k)
-              if (k < in0) dfeat[gp * dfeat_stride + k] = df[k];
+          for (int it = 0; it < kQ; ++it) {
+            const int idx = it * kTile + r, row = idx / kQ, c = idx % kQ;
+            if (tile * kTile + row < n) dst[idx] = stg[row * kQ + (c ^ (row & 7))];
           }
+        } else if (valid) {
+#pragma unroll
+          for (int k = 0; k < K0P; ++k)
+            if (k < in0) dfeat[gp * dfeat_stride + k] = df[k];
         }
       }
+      HBR_WAIT_B();                              // x0 / h1 are rewritten by the next tile
     }
   }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2002] = clock64();
 
-  // ---- flush the gradient accumulators ----
-  if (cta_tiles > 0 && dparams != nullptr && warp < 4) {
-    const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
-    // layers 0,1,3,4 -- M = 64 layout: accumulator row q (= output neuron) lives in lane (q % 16) + 32 * (q / 16)
-    {
-      const int q = warp * 16 + lane;            // meaningful for lane < 16
-      const int gcol[4] = {TM::g0, TM::g1, TM::g3, TM::g4};
-      const int bcol[4] = {TM::b0, TM::b1, TM::b3, TM::b4};
-      const int li[4] = {0, 1, 3, 4};
+  // ---- flush the gradient accumulators: TMEM -> registers -> a flat fp32 image of the parameter gradient in shared
+  //      memory (the tile buffers are free now) -> coalesced atomics, every CTA starting at a different offset so the
+  //      148 CTAs do not march through the same addresses together ----
+  if (cta_tiles > 0 && dparams != nullptr) {
+    float* gflat = reinterpret_cast<float*>(sm + SM::off_grp);
+    static_assert(G * SM::grp_bytes >= 64 * (64 + 64 + 64 + 64) * 4 + 4096, "gradient image does not fit");
+    if (warp < 4) {
+      const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
+      // layers 0,1,3,4 -- M = 64 layout: accumulator row q (= output neuron) lives in lane (q % 16) + 32 * (q / 16)
+      {
+        const int q = warp * 16 + lane;          // meaningful for lane < 16
+        const int gcol[4] = {TM::g0, TM::g1, TM::g3, TM::g4};
+        const int ncol[4] = {TM::n0, TM::n1, TM::n3, TM::n4};
+        const int li[4] = {0, 1, 3, 4};
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int i = li[t];
-        float gacc[64], gbias[16];
-        const int KP = i == 0 ? K0P : (i == 3 ? KCP : 64);
-        if (KP > 48) tmem_ld<64>(trow + gcol[t], gacc);
-        else if (KP > 32) tmem_ld<48>(trow + gcol[t], gacc);
-        else tmem_ld<32>(trow + gcol[t], gacc);
-        if (i == 3 && kCinOne) gbias[0] = 0.f;
-        else tmem_ld<16>(trow + bcol[t], gbias);    // 8 valid columns; the excess belongs to the next accumulator
-        if (lane < 16 && q < m.J[i]) {
-          float bsum = gbias[0];
-          for (int k = 0; k < KP; ++k) {
-            if (k < m.K[i]) atomicAdd(dparams + m.W[i] + q * m.K[i] + k, gacc[k]);
-            if (i == 3 && kCinOne && k == m.K[i]) bsum = gacc[k];
+        for (int t = 0; t < 4; ++t) {
+          const int i = li[t];
+          float gacc[80];
+          if (ncol[t] > 64) tmem_ld<80>(trow + gcol[t], gacc);         // any excess belongs to the next accumulator
+          else if (ncol[t] > 48) tmem_ld<64>(trow + gcol[t], gacc);
+          else tmem_ld<48>(trow + gcol[t], gacc);
+          // bias gradient: first column of the ones group, or the planted 1.0 column of the colour-net input
+          const int bias_col = (i == 3 && kCinOne) ? m.K[i] : (i == 0 ? K0P : (i == 3 ? KCP : 64));
+          if (lane < 16 && q < m.J[i]) {
+#pragma unroll
+            for (int k = 0; k < ncol[t]; ++k) {
+              if (k < m.K[i]) gflat[m.W[i] + q * m.K[i] + k] = gacc[k];
+              if (k == bias_col) gflat[m.b[i] + q] = gacc[k];
+            }
           }
-          atomicAdd(dparams + m.b[i] + q, bsum);
+        }
+      }
+      // layers 2,5 -- M = 128 layout: accumulator row = lane; rows 0..63 = input index k, row 64 = bias gradient
+      {
+        const int row = warp * 32 + lane;
+        const int gcol[2] = {TM::g2, TM::g5};
+        const int li[2] = {2, 5};
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int i = li[t];
+          float gacc[16];
+          tmem_ld<16>(trow + gcol[t], gacc);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j < m.J[i]) {
+              if (row < 64) gflat[m.W[i] + j * 64 + row] = gacc[j];
+              else if (row == 64) gflat[m.b[i] + j] = gacc[j];
+            }
+          }
         }
       }
     }
-    // layers 2,5 -- M = 128 layout: accumulator row = lane; rows 0..63 = input index k, row 64 = bias gradient
-    {
-      const int row = warp * 32 + lane;
-      const int gcol[2] = {TM::g2, TM::g5};
-      const int li[2] = {2, 5};
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int i = li[t];
-        float gacc[16];
-        tmem_ld<16>(trow + gcol[t], gacc);
-        if (row < 64) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < m.J[i]) atomicAdd(dparams + m.W[i] + j * 64 + row, gacc[j]);
-        } else if (row == 64) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < m.J[i]) atomicAdd(dparams + m.b[i] + j, gacc[j]);
-        }
-      }
+    __syncthreads();
+    const int total = m.total;
+    const int rot = (int)(((long long)blockIdx.x * total) / gridDim.x);
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      int idx = e + rot;
+      if (idx >= total) idx -= total;
+      atomicAdd(dparams + idx, gflat[idx]);
     }
   }
   fence_before_sync();
   __syncthreads();
+  if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2003] = clock64();
   if (warp == 0) tmem_dealloc<512>(tbase);
 }
 
@@ -786,6 +949,27 @@ extern "C" int hbr_debug_umma(int mode, const float* A, const float* B, float* D
   HBR_REQUIRE(mode != 2 || K == 128, "mode 2 needs K=128");
   HBR_CUDA(cudaFuncSetAttribute(umma_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
   umma_debug_kernel<<<1, 128, 65536, as_stream(stream)>>>(mode, A, B, D, N, K);
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
+
+extern "C" int hbr_debug_umma_bench(int M, int N, int reps, int nacc, int mn_major, long long* cycles, void* stream) {
+  HBR_REQUIRE((M == 64 || M == 128) && N >= 8 && N <= 256 && N % 8 == 0 && nacc >= 1 && nacc * N <= 512 && reps >= 1,
+              "bad shape");
+  HBR_CUDA(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  umma_bench_kernel<<<1, 128, 65536, as_stream(stream)>>>(M, N, reps, nacc, mn_major, cycles);
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
+
+extern "C" int hbr_debug_mlp_trace_bwd(const float* feat, const float* dirs, int64_t dir_group, int64_t n,
+                                       const float* params, const float* out, const float* dout, float* dfeat,
+                                       float* dparams, long long* trace, void* stream) {
+  constexpr int smem = BwdSmem<32, 48, 2>::total;
+  HBR_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<32, 48, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = (int)min64(ceil_div(ceil_div(n, kTile), 2), sm_count());
+  mlp_bwd_tc_kernel<32, 48, 2, true><<<grid, 2 * kTile + 64, smem, as_stream(stream)>>>(
+      feat, 32, dirs, dir_group, n, params, 32, 24, out, dout, dfeat, 32, nullptr, dparams, trace);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -847,13 +1031,13 @@ extern "C" int hbr_mlp_bwd_tc(const float* feat, int64_t feat_stride, const floa
     constexpr int smem = BwdSmem<32, 48, 2>::total;
     const int grid = (int)min64(ceil_div(ntiles, 2), sm_count());
     HBR_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<32, 48, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    mlp_bwd_tc_kernel<32, 48, 2><<<grid, 2 * kTile + 32, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv,
+    mlp_bwd_tc_kernel<32, 48, 2><<<grid, 2 * kTile + 64, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv,
                                                                    out, dout, dfeat, dfeat_stride, ddirs, dparams);
   } else {
     constexpr int smem = BwdSmem<64, 64, 1>::total;
     const int grid = (int)min64(ntiles, sm_count());
     HBR_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<64, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    mlp_bwd_tc_kernel<64, 64, 1><<<grid, kTile + 32, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out,
+    mlp_bwd_tc_kernel<64, 64, 1><<<grid, kTile + 64, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out,
                                                                dout, dfeat, dfeat_stride, ddirs, dparams);
   }
   HBR_LAUNCH_CHECK();

@@ -116,11 +116,19 @@ int hbr_mlp_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, in
  * rounded from fp32, fp32 result): mode 0: D[128,N] = A[128,K] B[N,K]^T; mode 1: D[128,N] = A[128,K] Bt[K,N];
  * mode 2: D[64,N] = At[128,64]^T Bt[128,N]. */
 int hbr_debug_umma(int mode, const float* A, const float* B, float* D, int N, int K, void* stream);
+/* Tensor-pipe probe: `reps` tcgen05.mma (M x N x 16, bf16) issued back to back by one thread round-robin over `nacc`
+ * accumulators; cycles[0] = first issue -> completion observed, cycles[1] = first issue -> last issue (SM clocks). */
+int hbr_debug_umma_bench(int M, int N, int reps, int nacc, int mn_major, long long* cycles, void* stream);
 /* Latency probe of the forward kernel (in0 = 32, d_view = 24): trace[0..1000) = clock64 stamps of tile group 0 of CTA 0
  * (tile start, then before-signal / after-signal / after-wait per layer), trace[1024..1524) = the MMA warp's
  * (ready-seen, committed) pairs for that group.  trace holds 2048 int64. */
 int hbr_debug_mlp_trace(const float* feat, const float* dirs, int64_t dir_group, int64_t n, const float* params,
                         float* out, long long* trace, void* stream);
+/* Same probe for the backward kernel: per tile 1 + 3*11 stamps of tile group 0, (ready-seen, committed) pairs of the
+ * issuing warp for that group at trace[1024..]. */
+int hbr_debug_mlp_trace_bwd(const float* feat, const float* dirs, int64_t dir_group, int64_t n, const float* params,
+                            const float* out, const float* dout, float* dfeat, float* dparams, long long* trace,
+                            void* stream);
 
 /* ---- a9: sample positions, vol_renderer.py:165 / helper.py:48 -------------------------------------
  * pts[r,s,:] = o[r,:] + d[r,:]*t  (separate multiply and add).  t is (S) shared (t_ray_stride = 0)

@@ -11,3 +11,4 @@ try:
 except Exception as e: print('no bench json', e)
 PY
 timeout 300 python scripts/dbg_trace.py > gpurun_out/trace.log 2>&1; head -12 gpurun_out/trace.log
+timeout 300 python scripts/dbg_trace_bwd.py > gpurun_out/trace_bwd.log 2>&1; sed -n 13,26p gpurun_out/trace_bwd.log
