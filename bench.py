@@ -330,6 +330,7 @@ def run_b200(args):
         tdist.all_reduce(tms, op=tdist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(tms[0]), float(tms[1])
     if rank != 0:
+        _finish(world)
         return
     pts_per_ray = args.samples * (3 if args.hierarchical else 1)
     n_pts = rays * pts_per_ray
@@ -380,8 +381,17 @@ def run_b200(args):
                                 "sample": f"{args.cpu_rays} rays x {args.samples} samples per step (BASELINE config 1 shape, 200x200 views), "
                                           f"1 warm-up + 3 timed fwd+bwd steps of oracle/port.py (torch CPU, {os.cpu_count()} threads)"}
     print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def _finish(world):
+    """Multi-rank exit: everything is measured and printed; skip the process-group / CUDA-graph teardown (a graph that
+    captured NCCL collectives keeps the communicator busy at destruction and can hang the interpreter exit)."""
     if world > 1:
-        tdist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main():

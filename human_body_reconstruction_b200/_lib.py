@@ -99,7 +99,7 @@ SIGNATURES = {
     "hbr_mlp_param_count": ([_dims_p], _i64),
     "hbr_mlp_act_floats": ([], _i64),
     "hbr_hash_encode_fwd": ([_vp, _i32, _i64, _vp, _geom_p, _vp, _i64, _vp], C.c_int),
-    "hbr_hash_encode_bwd": ([_vp, _i32, _i64, _vp, _i64, _geom_p, _vp, _vp], C.c_int),
+    "hbr_hash_encode_bwd": ([_vp, _i32, _i64, _vp, _i64, _geom_p, _vp, _i32, _i32, _vp], C.c_int),
     "hbr_hash_indices": ([_vp, _i32, _i64, _geom_p, _vp, _vp, _vp], C.c_int),
     "hbr_dir_encode": ([_vp, _i32, _i64, _i32, _i32, _vp, _vp], C.c_int),
     "hbr_mlp_fwd_f32": ([_vp, _i64, _vp, _i64, _i64, _vp, _dims_p, _vp, _vp, _vp], C.c_int),

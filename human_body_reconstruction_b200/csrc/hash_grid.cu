@@ -55,7 +55,7 @@ __device__ __forceinline__ void load_point(const XT* __restrict__ x, long long g
 }
 
 // ---- forward ------------------------------------------------------------------------------------------
-template <int F, bool POW2, typename XT>
+template <int F, bool POW2, typename XT, bool PAIR = true>
 __global__ void __launch_bounds__(kHashThreads)
 hash_fwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__ table, float* __restrict__ y,
                 long long y_stride, const __grid_constant__ HashGeom g) {
@@ -80,8 +80,19 @@ hash_fwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__
     corner_indices<POW2>(ix, iy, iz, g.T, idx);
     const float* lvl = table + (size_t)l * g.T * F;
     float v[8][F];
+    if (F == 2 && POW2 && PAIR && !(ix & 1)) {
+      // even x: corners (x, x+1) hash to entries e and e^1 -- one aligned 16-byte slot, one LDG.128 for both
 #pragma unroll
-    for (int c = 0; c < 8; ++c) load_feat<F>(lvl, idx[c], v[c]);          // 8 independent gathers in flight
+      for (int c = 0; c < 8; c += 2) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(lvl) + (idx[c] >> 1));
+        const bool odd = idx[c] & 1;
+        v[c][0] = odd ? q.z : q.x;     v[c][F - 1] = odd ? q.w : q.y;
+        v[c + 1][0] = odd ? q.x : q.z; v[c + 1][F - 1] = odd ? q.y : q.w;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) load_feat<F>(lvl, idx[c], v[c]);        // 8 independent gathers in flight
+    }
     float w[8];
     corner_weights(fx, fy, fz, w);
     // sum over corners in index order, multiply and add rounded separately (hash_encoding.py:144)
@@ -107,7 +118,7 @@ hash_fwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__
 template <int F, bool POW2, typename XT>
 __global__ void __launch_bounds__(kHashThreads)
 hash_bwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__ dy, long long dy_stride,
-                float* __restrict__ dtable, const __grid_constant__ HashGeom g) {
+                float* __restrict__ dtable, const __grid_constant__ HashGeom g, int l_begin, int l_end) {
   extern __shared__ float tile[];
   const int C = g.L * F;
   const int pitch = C | 1;
@@ -115,7 +126,7 @@ hash_bwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__
   const long long base = (long long)blockIdx.x * kTilePts;
   for (int r = warp; r < kTilePts; r += kHashThreads / 32) {
     const long long gp = base + r;
-    for (int c = lane; c < C; c += 32) tile[r * pitch + c] = gp < n ? __ldg(dy + gp * dy_stride + c) : 0.f;
+    for (int c = l_begin * F + lane; c < l_end * F; c += 32) tile[r * pitch + c] = gp < n ? __ldg(dy + gp * dy_stride + c) : 0.f;
   }
   const int p = threadIdx.x & (kTilePts - 1);
   const int grp = threadIdx.x >> 7;
@@ -124,7 +135,7 @@ hash_bwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__
   load_point(x, base + p, n, pt);
   __syncthreads();
 
-  for (int l = grp; l < g.L; l += 2) {
+  for (int l = l_begin + grp; l < l_end; l += 2) {
     const float s = g.scale[l];
     long long ix, iy, iz;
     float fx, fy, fz;
@@ -167,8 +178,19 @@ hash_bwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__
       uint32_t idx[8];
       corner_indices<POW2>(ix, iy, iz, g.T, idx);
       float* lvl = dtable + (size_t)l * g.T * F;
+      if (F == 2 && POW2 && !(ix & 1)) {
+        // even x: corners (x, x+1) hash to entries e and e^1 -- one aligned 16-byte slot, one red.global.add.v4.f32
 #pragma unroll
-      for (int c = 0; c < 8; ++c) red_feat<F>(lvl, idx[c], val[c]);
+        for (int c = 0; c < 8; c += 2) {
+          const bool odd = idx[c] & 1;
+          const float4 q = odd ? make_float4(val[c + 1][0], val[c + 1][F - 1], val[c][0], val[c][F - 1])
+                               : make_float4(val[c][0], val[c][F - 1], val[c + 1][0], val[c + 1][F - 1]);
+          atomicAdd(reinterpret_cast<float4*>(lvl) + (idx[c] >> 1), q);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) red_feat<F>(lvl, idx[c], val[c]);
+      }
     }
   }
 }
@@ -219,11 +241,12 @@ static int launch_fwd(const void* x, int64_t n, const float* table, const HashGe
   return HBR_OK;
 }
 template <int F, bool POW2, typename XT>
-static int launch_bwd(const void* x, int64_t n, const float* dy, int64_t ds, const HashGeom& g, float* dt, cudaStream_t st) {
+static int launch_bwd(const void* x, int64_t n, const float* dy, int64_t ds, const HashGeom& g, float* dt, int l0, int l1,
+                      cudaStream_t st) {
   const size_t smem = (size_t)kTilePts * ((g.L * F) | 1) * sizeof(float);
   HBR_CUDA(cudaFuncSetAttribute(hash_bwd_kernel<F, POW2, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   hash_bwd_kernel<F, POW2, XT><<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(
-      static_cast<const XT*>(x), n, dy, ds, dt, g);
+      static_cast<const XT*>(x), n, dy, ds, dt, g, l0, l1);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -263,7 +286,8 @@ extern "C" int hbr_hash_encode_fwd(const void* x, int x_dtype, int64_t n, const 
 }
 
 extern "C" int hbr_hash_encode_bwd(const void* x, int x_dtype, int64_t n, const float* dy, int64_t dy_stride,
-                                   const hbr_hash_geom* geom, float* dtable, void* stream) {
+                                   const hbr_hash_geom* geom, float* dtable, int level_begin, int level_end,
+                                   void* stream) {
   if (int rc = check_geom(geom)) return rc;
   HBR_REQUIRE(x_dtype == HBR_F32 || x_dtype == HBR_F16, "x_dtype %d", x_dtype);
   HBR_REQUIRE(n >= 0 && n < (1LL << 40), "n=%lld", (long long)n);
@@ -271,8 +295,11 @@ extern "C" int hbr_hash_encode_bwd(const void* x, int x_dtype, int64_t n, const 
   HBR_REQUIRE(x && dy && dtable, "NULL pointer");
   HBR_REQUIRE(dy_stride >= geom->L * geom->F, "dy_stride %lld too small", (long long)dy_stride);
   HBR_REQUIRE((uintptr_t)dtable % 16 == 0, "dtable must be 16-byte aligned");
+  HBR_REQUIRE(level_begin >= 0 && level_begin <= level_end && level_end <= geom->L, "level range [%d,%d)", level_begin,
+              level_end);
+  if (level_begin == level_end) return HBR_OK;
   const HashGeom g = to_device_geom(*geom);
-  HBR_DISPATCH_HASH(launch_bwd, x, n, dy, dy_stride, g, dtable, as_stream(stream));
+  HBR_DISPATCH_HASH(launch_bwd, x, n, dy, dy_stride, g, dtable, level_begin, level_end, as_stream(stream));
 }
 
 extern "C" int hbr_hash_indices(const void* x, int x_dtype, int64_t n, const hbr_hash_geom* geom,

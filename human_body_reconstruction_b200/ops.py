@@ -60,13 +60,15 @@ def hash_encode_fwd(x: torch.Tensor, table: torch.Tensor, geom: HashGeom) -> tor
     return y
 
 
-def hash_encode_bwd(x: torch.Tensor, dy: torch.Tensor, geom: HashGeom, dtable: torch.Tensor) -> None:
-    """dtable (L,T,F) fp32 is accumulated into."""
+def hash_encode_bwd(x: torch.Tensor, dy: torch.Tensor, geom: HashGeom, dtable: torch.Tensor, level_begin: int = 0,
+                    level_end: Optional[int] = None) -> None:
+    """dtable (L,T,F) fp32 is accumulated into; only levels [level_begin, level_end) are processed."""
     require_cuda(x, dy, dtable)
     x = x.contiguous()
     dy = _f32c(dy)
+    level_end = geom.L if level_end is None else level_end
     check(lib().hbr_hash_encode_bwd(ptr(x), _xdtype(x), x.shape[0], ptr(dy), dy.stride(0), C.byref(geom), ptr(dtable),
-                                    stream()))
+                                    int(level_begin), int(level_end), stream()))
 
 
 def hash_indices(x: torch.Tensor, geom: HashGeom, want_w: bool = True):

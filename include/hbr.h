@@ -71,9 +71,10 @@ int hbr_hash_encode_fwd(const void* x, int x_dtype, int64_t n, const float* tabl
                         const hbr_hash_geom* geom_host, float* y, int64_t y_stride, void* stream);
 
 /* a5: autograd of the above (16 x embedding_dense_backward): dtable[l,h,:] += w * dy[:, lF:(l+1)F].
- * dtable (L,T,F) fp32 is ACCUMULATED into (caller zeroes it). */
+ * dtable (L,T,F) fp32 is ACCUMULATED into (caller zeroes it).  Only levels [level_begin, level_end) are processed,
+ * so a caller can split the pass into level chunks and overlap the all-reduce of a finished chunk (multi-GPU). */
 int hbr_hash_encode_bwd(const void* x, int x_dtype, int64_t n, const float* dy, int64_t dy_stride,
-                        const hbr_hash_geom* geom_host, float* dtable, void* stream);
+                        const hbr_hash_geom* geom_host, float* dtable, int level_begin, int level_end, void* stream);
 
 /* Parity probe: the hash indices hash_encoding.py:161-162 computes (hash_func, :41-55), and the
  * n-linear weights of :142-143.  idx: (L,n,8) int32, w: (L,n,8) fp32 (either may be NULL). */
