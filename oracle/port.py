@@ -354,14 +354,20 @@ def grid_query(p_mlp, tables, mu, sigma, scales, pts_f16: torch.Tensor, num_freq
     return torch.cat(outs, 0)
 
 
-def mc_crossing_edges(density: np.ndarray, iso: float) -> int:
+def mc_crossing_edges(density: np.ndarray, iso: float, i_begin: int = 0, i_end: Optional[int] = None) -> int:
     """Number of grid edges whose endpoints straddle the iso level with the inside test d < iso.
-    Equals the vertex count of any table-based marching cubes that welds one vertex per edge."""
+    Equals the vertex count of any table-based marching cubes that welds one vertex per edge.
+    With a slab [i_begin, i_end) of axis 0: only edges OWNED by the slab's grid points (an edge belongs to its lower
+    end point), the ownership rule of hbr_mc_count -- the slab counts of a partition add up to the whole grid's."""
     inside = density < iso
+    n0 = inside.shape[0]
+    i_end = n0 if i_end is None else i_end
+    own = inside[i_begin:i_end]
     n = 0
-    n += int(np.count_nonzero(inside[1:, :, :] != inside[:-1, :, :]))
-    n += int(np.count_nonzero(inside[:, 1:, :] != inside[:, :-1, :]))
-    n += int(np.count_nonzero(inside[:, :, 1:] != inside[:, :, :-1]))
+    up = inside[i_begin + 1:min(i_end + 1, n0)]                       # axis-0 edges: lower end point i in the slab
+    n += int(np.count_nonzero(up != own[:up.shape[0]]))
+    n += int(np.count_nonzero(own[:, 1:, :] != own[:, :-1, :]))
+    n += int(np.count_nonzero(own[:, :, 1:] != own[:, :, :-1]))
     return n
 
 

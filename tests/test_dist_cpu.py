@@ -1,0 +1,127 @@
+"""CPU tests (world_size 2, gloo) of the N > 1 host logic in human_body_reconstruction_b200/dist.py:
+ray sharding, the flat-gradient all-reduce launched from inside backward (DDP-style end-of-backward wait),
+slab sharding of the density grid and the all-gather of marching-cubes counts.  The kernels themselves need a GPU;
+here stand-in modules publish CPU gradients through the same `_grad_hooks` protocol HashEncoder / MLP_3D use."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as tdist
+import torch.multiprocessing as mp
+
+from human_body_reconstruction_b200 import dist as hdist
+from oracle import port
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class _FlatGradModule(torch.nn.Module):
+    """Stand-in for HashEncoder / MLP_3D: per-"level" parameters that are views of one flat buffer; the backward
+    publishes ONE flat gradient buffer through `_grad_hooks` (optionally in level chunks) and hands autograd views."""
+
+    def __init__(self, levels, width, chunks=1):
+        super().__init__()
+        g = torch.Generator().manual_seed(7)
+        self.flat = torch.randn(levels, width, generator=g)
+        self.levels = torch.nn.ParameterList([torch.nn.Parameter(self.flat[i]) for i in range(levels)])
+        self._grad_hooks = []
+        self.chunks = chunks
+
+    def forward(self, x):
+        mod = self
+
+        class Fn(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, x, *w):
+                ctx.save_for_backward(x)
+                return x @ mod.flat.detach().T                       # (N, levels)
+
+            @staticmethod
+            def backward(ctx, dy):
+                (x,) = ctx.saved_tensors
+                gflat = torch.zeros_like(mod.flat)
+                L = gflat.shape[0]
+                step = -(-L // mod.chunks)
+                for l0 in range(0, L, step):                         # level chunks, published as they complete
+                    l1 = min(L, l0 + step)
+                    gflat[l0:l1] = dy[:, l0:l1].T @ x
+                    for h in mod._grad_hooks:
+                        h(gflat[l0:l1])
+                return (None,) + tuple(gflat[i] for i in range(L))
+
+        return Fn.apply(x, *self.levels)
+
+
+def _worker(rank, world, port_no, tmp):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    r, w = hdist.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)                                             # identical parameters on every rank
+    n_rays, width, levels = 64, 5, 6
+    g = torch.Generator().manual_seed(3)
+    x_all = torch.randn(n_rays, width, generator=g)
+    gt_all = torch.randn(n_rays, levels, generator=g)
+
+    for chunks in (1, 3):
+        mod = _FlatGradModule(levels, width, chunks=chunks)
+        reducer = hdist.GradAllReduce(mod)
+        sl = hdist.shard_rays(n_rays, rank, world)
+        loss = torch.nn.functional.mse_loss(mod(x_all[sl]), gt_all[sl])   # mean over the LOCAL batch
+        loss.backward()
+        got = torch.stack([p.grad for p in mod.levels])
+        # single-process gradient of the concatenated batch
+        ref = _FlatGradModule(levels, width)
+        torch.nn.functional.mse_loss(ref(x_all), gt_all).backward()
+        want = torch.stack([p.grad for p in ref.levels])
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-6), (rank, chunks, (got - want).abs().max())
+        assert reducer.bytes_reduced == levels * width * 4
+        reducer.remove()
+        assert not mod._grad_hooks
+
+    # density-grid slabs: disjoint, ordered, covering; per-slab crossing-edge counts add up to the whole grid's
+    res = 11
+    i0, i1 = hdist.slab_range(res, rank, world)
+    rng = np.random.default_rng(5)
+    dens = rng.normal(30.0, 5.0, size=(res, res, res)).astype(np.float32)
+    whole = port.mc_crossing_edges(dens, 30.0)
+    mine = port.mc_crossing_edges(dens, 30.0, i_begin=i0, i_end=i1)
+    counts = hdist.allgather_counts([mine, i1 - i0])
+    assert len(counts) == world and counts[rank] == [mine, i1 - i0]
+    assert sum(c[0] for c in counts) == whole
+    assert sum(c[1] for c in counts) == res
+    if rank == 0:
+        with open(os.path.join(tmp, "ok"), "w") as f:
+            f.write("ok")
+    tdist.barrier()
+    tdist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_and_slabs(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / "ok").read_text() == "ok"
+
+
+@pytest.mark.parametrize("n,world", [(4096, 8), (10, 3), (7, 8), (1 << 20, 8)])
+def test_shard_rays_partition(n, world):
+    seen = []
+    for r in range(world):
+        s = hdist.shard_rays(n, r, world)
+        seen += list(range(n))[s]
+    assert seen == list(range(n))
+
+
+@pytest.mark.parametrize("res,world", [(512, 8), (256, 3), (5, 8), (11, 2)])
+def test_slab_range_partition(res, world):
+    edges = [hdist.slab_range(res, r, world) for r in range(world)]
+    assert edges[0][0] == 0 and edges[-1][1] == res
+    for (a0, a1), (b0, b1) in zip(edges, edges[1:]):
+        assert a1 == b0 and a0 <= a1
+    sizes = [b - a for a, b in edges]
+    assert max(sizes) - min(sizes) <= 1
