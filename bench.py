@@ -374,7 +374,7 @@ def run_b200(args):
         c, m = kern["hbr_hash_encode_fwd"]
         line["hash_encode_mpts_per_s"] = (n_pts / (c / args.steps)) / (m * 1e-3) / 1e6
     if reducer is not None:
-        line["allreduce_bytes_per_step"] = reducer.bytes_reduced // max(1, args.steps * 2 + args.warmup)
+        line["allreduce_bytes_per_step"] = 4 * sum(p.numel() for p in params)      # flat table + MLP gradients, fp32
     if world == 1 and not args.no_cpu_baseline:
         v, sec = cpu_step_rays_per_s(args, 3, 1, args.cpu_rays)
         line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",

@@ -55,18 +55,20 @@ struct BOfs {                         // byte offsets of the six [JP x 16] bias 
 // fp32 (J,K) row-major weights -> bf16 canonical tile [JP rows x KP cols], zero padded; one 16-byte chunk per step
 template <int K0P, int KCP>
 __device__ __forceinline__ void stage_weights_bf16(const float* __restrict__ params, const MlpLayout& m, uint8_t* wsm,
-                                                   uint8_t* bias_sm, uint8_t* ones16, float* bias_f32 = nullptr) {
+                                                   uint8_t* bias_sm, uint8_t* ones16, float* bias_f32 = nullptr,
+                                                   bool skip_weights = false, int tid = -1, int nthr = 0) {
+  if (tid < 0) { tid = threadIdx.x; nthr = blockDim.x; }
   const int JP[6] = {64, 64, 16, 64, 64, 16};
   const int KP[6] = {K0P, 64, 64, KCP, 64, 64};
   const int wofs[6] = {WOfs<K0P, KCP>::w0, WOfs<K0P, KCP>::w1, WOfs<K0P, KCP>::w2, WOfs<K0P, KCP>::w3,
                        WOfs<K0P, KCP>::w4, WOfs<K0P, KCP>::w5};
   // weight tiles: one flat loop over all 16-byte chunks of the six tiles so that every thread has several chunks'
   // worth of global loads in flight (the whole image is staged in ~1 us instead of six dependent passes)
-  {
+  if (!skip_weights) {
     constexpr int kChunks = WOfs<K0P, KCP>::total / 16;
     const int cbeg[7] = {0, wofs[1] / 16, wofs[2] / 16, wofs[3] / 16, wofs[4] / 16, wofs[5] / 16, kChunks};
 #pragma unroll 3
-    for (int c = threadIdx.x; c < kChunks; c += blockDim.x) {
+    for (int c = tid; c < kChunks; c += nthr) {
       int i = 0;
 #pragma unroll
       for (int t = 1; t < 6; ++t) i += c >= cbeg[t] ? 1 : 0;
@@ -84,13 +86,14 @@ __device__ __forceinline__ void stage_weights_bf16(const float* __restrict__ par
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     const int J = m.J[i];
+    if (bias_f32 == nullptr && bias_sm == nullptr) continue;          // weight tiles only
     if (bias_f32 != nullptr) {               // plain fp32 biases for kernels that add them in the epilogue
-      for (int j = threadIdx.x; j < 64; j += blockDim.x) bias_f32[i * 64 + j] = j < J ? __ldg(params + m.b[i] + j) : 0.f;
+      for (int j = tid; j < 64; j += nthr) bias_f32[i * 64 + j] = j < J ? __ldg(params + m.b[i] + j) : 0.f;
       continue;
     }
     // bias tile [JP x 16] (K-major B operand of the bias MMA): col 0 = bf16(b), col 1 = bf16(b - bf16(b))
     uint8_t* bt = bias_sm + BOfs::ofs(i);
-    for (int e = threadIdx.x; e < JP[i] * 2; e += blockDim.x) {
+    for (int e = tid; e < JP[i] * 2; e += nthr) {
       const int cg = e / JP[i], j = e - cg * JP[i];
       float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (cg == 0 && j < J) {
@@ -101,9 +104,9 @@ __device__ __forceinline__ void stage_weights_bf16(const float* __restrict__ par
       store_chunk(bt, j, cg, JP[i], v);
     }
   }
-  if (bias_f32 != nullptr) return;
+  if (bias_f32 != nullptr || ones16 == nullptr) return;
   // ones16 [128 x 16] (A operand of the bias MMA): cols 0,1 = 1
-  for (int e = threadIdx.x; e < kTile * 2; e += blockDim.x) {
+  for (int e = tid; e < kTile * 2; e += nthr) {
     const int cg = e / kTile, rr = e - cg * kTile;
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (cg == 0) v[0] = v[1] = 1.f;
@@ -398,6 +401,57 @@ __device__ __forceinline__ long long tiles_of_slot(long long ntiles, long long s
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// optional caller-provided scratch (hbr_mlp_tc_scratch_bytes): [bf16 weight tiles | bias tiles | ones16 | fp32 biases |
+// per-CTA gradient rows].  A small prep kernel builds the operand image once per call, the persistent CTAs then copy
+// it with 16-byte loads instead of each converting all 14 227 parameters; the backward CTAs write their gradient image
+// as one row each and a reduce kernel sums the rows (instead of 148-way contended atomics).
+// ---------------------------------------------------------------------------------------------------------------
+template <int K0P, int KCP>
+struct Scratch {
+  static constexpr int off_bias = WOfs<K0P, KCP>::total;
+  static constexpr int off_ones16 = off_bias + BOfs::total;
+  static constexpr int off_bias_f32 = off_ones16 + kTile * 16 * 2;
+  static constexpr int off_grad = (off_bias_f32 + 6 * 64 * 4 + 255) & ~255;
+  static constexpr int kMaxRows = 256;                                   // >= persistent grid size
+  static constexpr int kRowFloats = 18432;                               // >= parameter count (<= 17 875 at in0 = 64, d_view = 49)
+  static constexpr long long total = (long long)off_grad + (long long)kMaxRows * kRowFloats * 4;
+};
+
+constexpr int kPrepCtas = 11;                                           // 9 x 256 threads cover the <= 2304 weight chunks
+template <int K0P, int KCP>
+__global__ void __launch_bounds__(256) mlp_prep_kernel(const float* __restrict__ params, int in0, int dv, uint8_t* img) {
+  using SC = Scratch<K0P, KCP>;
+  const MlpLayout m = make_layout(in0, dv);
+  if (blockIdx.x < kPrepCtas - 2) {            // weight tiles: one 16-byte chunk per thread
+    constexpr int kChunks = WOfs<K0P, KCP>::total / 16;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < kChunks) stage_weights_bf16<K0P, KCP>(params, m, img, nullptr, nullptr, nullptr, false, c, 1 << 30);
+  } else if (blockIdx.x == kPrepCtas - 2) {    // bias tiles + ones16 (weights skipped)
+    stage_weights_bf16<K0P, KCP>(params, m, img, img + SC::off_bias, img + SC::off_ones16, nullptr, true);
+  } else {                                      // fp32 biases
+    stage_weights_bf16<K0P, KCP>(params, m, img, nullptr, nullptr, reinterpret_cast<float*>(img + SC::off_bias_f32), true);
+  }
+}
+
+__device__ __forceinline__ void copy_image(uint8_t* dst, const uint8_t* __restrict__ src, int bytes) {
+  for (int e = threadIdx.x; e < bytes / 16; e += blockDim.x)
+    reinterpret_cast<uint4*>(dst)[e] = __ldg(reinterpret_cast<const uint4*>(src) + e);
+}
+
+constexpr int kReduceSlices = 8;
+__global__ void __launch_bounds__(256) mlp_grad_reduce_kernel(const float* __restrict__ rows, int nrows, int row_floats,
+                                                               int total, float* __restrict__ dparams) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int per = (nrows + kReduceSlices - 1) / kReduceSlices;
+  const int r0 = blockIdx.y * per, r1 = min(nrows, r0 + per);
+  float acc = 0.f;
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) acc += __ldg(rows + (size_t)r * row_floats + e);
+  if (r1 > r0) atomicAdd(dparams + e, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------------
 template <int K0P, int KCP, int G>
@@ -415,7 +469,7 @@ template <int K0P, int KCP, int G, bool TRACE = false>
 __global__ void __launch_bounds__(G * (kTile + 32), 1)
 mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const float* __restrict__ dirs, long long dir_group,
                   long long n, const float* __restrict__ params, int in0, int dv, float* __restrict__ out,
-                  long long* __restrict__ trace = nullptr) {
+                  const uint8_t* __restrict__ image = nullptr, long long* __restrict__ trace = nullptr) {
   using SM = FwdSmem<K0P, KCP, G>;
   using WO = WOfs<K0P, KCP>;
   constexpr int kCols = G * 64 <= 64 ? 64 : (G * 64 <= 128 ? 128 : (G * 64 <= 256 ? 256 : 512));
@@ -431,7 +485,8 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     for (int g = 0; g < G; ++g) { mbar_init(bars + g, kTile); mbar_init(bars + G + g, 1); }
     fence_mbar_init();
   }
-  stage_weights_bf16<K0P, KCP>(params, m, wsm, sm + SM::off_bias, sm + SM::off_ones16);
+  if (image != nullptr) copy_image(sm, image, SM::off_buf);             // [weights | bias tiles | ones16], same layout
+  else stage_weights_bf16<K0P, KCP>(params, m, wsm, sm + SM::off_bias, sm + SM::off_ones16);
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -598,7 +653,8 @@ __global__ void __launch_bounds__(G * kTile + 64, 1)
 mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const float* __restrict__ dirs, long long dir_group,
                   long long n, const float* __restrict__ params, int in0, int dv, const float* __restrict__ out,
                   const float* __restrict__ dout, float* __restrict__ dfeat, long long dfeat_stride,
-                  float* __restrict__ ddirs, float* __restrict__ dparams, long long* __restrict__ trace = nullptr) {
+                  float* __restrict__ ddirs, float* __restrict__ dparams, const uint8_t* __restrict__ image = nullptr,
+                  float* __restrict__ grad_rows = nullptr, long long* __restrict__ trace = nullptr) {
   using SM = BwdSmem<K0P, KCP, G>;
   using WO = WOfs<K0P, KCP>;
   using TM = BwdTmem<K0P, KCP>;
@@ -623,7 +679,12 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     }
     fence_mbar_init();
   }
-  stage_weights_bf16<K0P, KCP>(params, m, wsm, nullptr, nullptr, bias);
+  if (image != nullptr) {
+    copy_image(wsm, image, WO::total);
+    copy_image(sm + SM::off_bias, image + Scratch<K0P, KCP>::off_bias_f32, 6 * 64 * 4);
+  } else {
+    stage_weights_bf16<K0P, KCP>(params, m, wsm, nullptr, nullptr, bias);
+  }
   {
     // zero the group regions (the M = 128 operands read column groups they do not own: keep them finite), then the ones
     for (int e = threadIdx.x; e < G * SM::grp_bytes / 16; e += blockDim.x)
@@ -926,12 +987,20 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     }
     __syncthreads();
     const int total = m.total;
-    const int rot = (int)(((long long)blockIdx.x * total) / gridDim.x);
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-      int idx = e + rot;
-      if (idx >= total) idx -= total;
-      atomicAdd(dparams + idx, gflat[idx]);
+    if (grad_rows != nullptr) {                  // one row per CTA, summed by mlp_grad_reduce_kernel
+      float* row = grad_rows + (size_t)blockIdx.x * Scratch<K0P, KCP>::kRowFloats;
+      for (int e = threadIdx.x; e < total; e += blockDim.x) row[e] = gflat[e];
+    } else {
+      const int rot = (int)(((long long)blockIdx.x * total) / gridDim.x);
+      for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        int idx = e + rot;
+        if (idx >= total) idx -= total;
+        atomicAdd(dparams + idx, gflat[idx]);
+      }
     }
+  } else if (grad_rows != nullptr && dparams != nullptr) {
+    float* row = grad_rows + (size_t)blockIdx.x * Scratch<K0P, KCP>::kRowFloats;
+    for (int e = threadIdx.x; e < m.total; e += blockDim.x) row[e] = 0.f;
   }
   fence_before_sync();
   __syncthreads();
@@ -969,7 +1038,7 @@ extern "C" int hbr_debug_mlp_trace_bwd(const float* feat, const float* dirs, int
   HBR_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<32, 48, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), 2), sm_count());
   mlp_bwd_tc_kernel<32, 48, 2, true><<<grid, 2 * kTile + 64, smem, as_stream(stream)>>>(
-      feat, 32, dirs, dir_group, n, params, 32, 24, out, dout, dfeat, 32, nullptr, dparams, trace);
+      feat, 32, dirs, dir_group, n, params, 32, 24, out, dout, dfeat, 32, nullptr, dparams, nullptr, nullptr, trace);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -980,7 +1049,7 @@ extern "C" int hbr_debug_mlp_trace(const float* feat, const float* dirs, int64_t
   HBR_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<32, 48, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), 4), sm_count());
   mlp_fwd_tc_kernel<32, 48, 4, true><<<grid, 4 * (kTile + 32), smem, as_stream(stream)>>>(feat, 32, dirs, dir_group, n,
-                                                                                         params, 32, 24, out, trace);
+                                                                                         params, 32, 24, out, nullptr, trace);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -989,57 +1058,76 @@ extern "C" int hbr_debug_mlp_trace(const float* feat, const float* dirs, int64_t
 // per SM); other widths (in0 <= 64, 15 + d_view <= 64) run the same kernels with padded K and fewer groups.
 static inline bool narrow_shape(const hbr_mlp_dims* d) { return d->in0 <= 32 && d->d_view + kFeat <= 40; }
 
-extern "C" int hbr_mlp_fwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
-                              const float* params, const hbr_mlp_dims* dims, float* out, void* stream) {
-  if (int rc = check_dims(dims)) return rc;
-  if (n == 0) return HBR_OK;
-  HBR_REQUIRE(feat && dirs && params && out, "NULL pointer");
-  HBR_REQUIRE(feat_stride >= dims->in0 && dir_group >= 1, "bad stride / dir_group");
-  HBR_REQUIRE((uintptr_t)out % 16 == 0, "out must be 16-byte aligned");
-  cudaStream_t st = as_stream(stream);
-  const int64_t ntiles = ceil_div(n, kTile);
-  const int in0 = dims->in0, dv = dims->d_view;
-  const int grid = (int)min64(ceil_div(ntiles, 4), sm_count());
-  if (narrow_shape(dims)) {
-    constexpr int smem = FwdSmem<32, 48, 4>::total;
-    HBR_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<32, 48, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    mlp_fwd_tc_kernel<32, 48, 4><<<grid, 4 * (kTile + 32), smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv,
-                                                                     out);
-  } else {
-    constexpr int smem = FwdSmem<64, 64, 4>::total;
-    HBR_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<64, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    mlp_fwd_tc_kernel<64, 64, 4><<<grid, 4 * (kTile + 32), smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv,
-                                                                     out);
+extern "C" int64_t hbr_mlp_tc_scratch_bytes(const hbr_mlp_dims* dims) {
+  if (check_dims(dims)) return 0;
+  return narrow_shape(dims) ? Scratch<32, 48>::total : Scratch<64, 64>::total;
+}
+
+template <int K0P, int KCP, int G>
+static int launch_fwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
+                         const float* params, int in0, int dv, float* out, uint8_t* scratch, cudaStream_t st) {
+  constexpr int smem = FwdSmem<K0P, KCP, G>::total;
+  const int grid = (int)min64(ceil_div(ceil_div(n, kTile), G), sm_count());
+  if (scratch != nullptr) mlp_prep_kernel<K0P, KCP><<<kPrepCtas - 1, 256, 0, st>>>(params, in0, dv, scratch);
+  HBR_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<K0P, KCP, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mlp_fwd_tc_kernel<K0P, KCP, G><<<grid, G * (kTile + 32), smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv,
+                                                                       out, scratch);
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
+
+template <int K0P, int KCP, int G>
+static int launch_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
+                         const float* params, int in0, int dv, const float* out, const float* dout, float* dfeat,
+                         int64_t dfeat_stride, float* ddirs, float* dparams, uint8_t* scratch, cudaStream_t st) {
+  using SC = Scratch<K0P, KCP>;
+  constexpr int smem = BwdSmem<K0P, KCP, G>::total;
+  const int grid = (int)min64(ceil_div(ceil_div(n, kTile), G), sm_count());
+  const bool rows = scratch != nullptr && dparams != nullptr && grid <= SC::kMaxRows;
+  if (scratch != nullptr) mlp_prep_kernel<K0P, KCP><<<kPrepCtas, 256, 0, st>>>(params, in0, dv, scratch);
+  HBR_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<K0P, KCP, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mlp_bwd_tc_kernel<K0P, KCP, G><<<grid, G * kTile + 64, smem, st>>>(
+      feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, dout, dfeat, dfeat_stride, ddirs, dparams, scratch,
+      rows ? reinterpret_cast<float*>(scratch + SC::off_grad) : nullptr);
+  if (rows) {
+    const int total = make_layout(in0, dv).total;
+    mlp_grad_reduce_kernel<<<dim3((total + 255) / 256, kReduceSlices), 256, 0, st>>>(reinterpret_cast<const float*>(scratch + SC::off_grad), grid,
+                                                                 SC::kRowFloats, total, dparams);
   }
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
 
+extern "C" int hbr_mlp_fwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
+                              const float* params, const hbr_mlp_dims* dims, float* out, void* scratch, void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (n == 0) return HBR_OK;
+  HBR_REQUIRE(feat && dirs && params && out, "NULL pointer");
+  HBR_REQUIRE(feat_stride >= dims->in0 && dir_group >= 1, "bad stride / dir_group");
+  HBR_REQUIRE((uintptr_t)out % 16 == 0 && (uintptr_t)scratch % 256 == 0, "out / scratch alignment");
+  cudaStream_t st = as_stream(stream);
+  uint8_t* sc = static_cast<uint8_t*>(scratch);
+  if (narrow_shape(dims))
+    return launch_fwd_tc<32, 48, 4>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out, sc, st);
+  return launch_fwd_tc<64, 64, 4>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out, sc, st);
+}
+
 extern "C" int hbr_mlp_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                               const float* params, const hbr_mlp_dims* dims, const float* out, const float* dout,
-                              float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams, void* stream) {
+                              float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams, void* scratch,
+                              void* stream) {
   if (int rc = check_dims(dims)) return rc;
   if (n == 0) return HBR_OK;
   HBR_REQUIRE(feat && dirs && params && out && dout, "NULL pointer");
   HBR_REQUIRE(feat_stride >= dims->in0 && dir_group >= 1, "bad stride / dir_group");
-  HBR_REQUIRE((uintptr_t)dout % 16 == 0 && (uintptr_t)out % 16 == 0, "out / dout must be 16-byte aligned");
+  HBR_REQUIRE((uintptr_t)dout % 16 == 0 && (uintptr_t)out % 16 == 0 && (uintptr_t)scratch % 256 == 0,
+              "out / dout / scratch alignment");
   HBR_REQUIRE(!dfeat || dfeat_stride >= dims->in0, "dfeat_stride too small");
   cudaStream_t st = as_stream(stream);
-  const int64_t ntiles = ceil_div(n, kTile);
-  const int in0 = dims->in0, dv = dims->d_view;
-  if (narrow_shape(dims)) {
-    constexpr int smem = BwdSmem<32, 48, 2>::total;
-    const int grid = (int)min64(ceil_div(ntiles, 2), sm_count());
-    HBR_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<32, 48, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    mlp_bwd_tc_kernel<32, 48, 2><<<grid, 2 * kTile + 64, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv,
-                                                                   out, dout, dfeat, dfeat_stride, ddirs, dparams);
-  } else {
-    constexpr int smem = BwdSmem<64, 64, 1>::total;
-    const int grid = (int)min64(ntiles, sm_count());
-    HBR_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<64, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    mlp_bwd_tc_kernel<64, 64, 1><<<grid, kTile + 64, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out,
-                                                               dout, dfeat, dfeat_stride, ddirs, dparams);
-  }
-  HBR_LAUNCH_CHECK();
-  return HBR_OK;
+  uint8_t* sc = static_cast<uint8_t*>(scratch);
+  if (narrow_shape(dims))
+    return launch_bwd_tc<32, 48, 2>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out, dout, dfeat,
+                                    dfeat_stride, ddirs, dparams, sc, st);
+  return launch_bwd_tc<64, 64, 1>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out, dout, dfeat,
+                                  dfeat_stride, ddirs, dparams, sc, st);
 }

@@ -5,8 +5,10 @@ reduced gradients.  The reference has no counterpart (it wraps only the MLP in n
 SURVEY section 8(e).
 
 Mechanics: `HashEncoder` / `MLP_3D` publish their flat gradient tensor (L,T,F) / (14227,) from inside their
-autograd backward; the hook below launches an asynchronous all-reduce on it right there (the MLP's reduce
-thus overlaps the hash-table backward that follows it) and registers an end-of-backward engine callback
+autograd backward -- the encoder in level chunks, each as soon as its scatter-add kernel has been enqueued;
+the hook below launches an asynchronous all-reduce on every published piece right there (NCCL's stream waits
+for the producing kernel, the compute stream runs on: the MLP's reduce overlaps the hash-table backward, a
+table chunk's reduce overlaps the next chunk's scatter-add) and registers an end-of-backward engine callback
 that makes the compute stream wait for the collectives.  MSE is a mean over the LOCAL batch, so the
 average over ranks equals the single-process gradient of the concatenated batch.
 """
@@ -56,9 +58,13 @@ class GradAllReduce:
     def _on_grad(self, flat: torch.Tensor):
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return
+        op = dist.ReduceOp.SUM
         if self.average:
-            flat.div_(dist.get_world_size(self.group))
-        self._pending.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            if dist.get_backend(self.group) == "nccl":
+                op = dist.ReduceOp.AVG                     # averaging inside the collective: no extra pass over the buffer
+            else:
+                flat.div_(dist.get_world_size(self.group))
+        self._pending.append(dist.all_reduce(flat, op=op, group=self.group, async_op=True))
         self.bytes_reduced += flat.numel() * flat.element_size()
         if not self._callback_queued:
             self._callback_queued = True

@@ -32,8 +32,14 @@ class _HashEncodeFn(torch.autograd.Function):
         enc = ctx.enc
         L, T, F = enc.L, enc.T, enc.F
         g = torch.zeros((L, T, F), device=dy.device, dtype=torch.float32)
-        ops.hash_encode_bwd(x, dy[:, : L * F], ctx.geom, g)
-        enc._publish_grad(g)
+        # With gradient hooks attached (multi-GPU) the pass runs in level chunks and every finished chunk is published
+        # at once: its all-reduce travels over NVLink while the next chunk's scatter-add still runs.
+        nch = max(1, min(L, enc._grad_chunks)) if enc._grad_hooks else 1
+        step = -(-L // nch)
+        for l0 in range(0, L, step):
+            l1 = min(L, l0 + step)
+            ops.hash_encode_bwd(x, dy[:, : L * F], ctx.geom, g, l0, l1)
+            enc._publish_grad(g[l0:l1])
         # no gradient w.r.t. x: the interpolation weights are detached in the reference (hash_encoding.py:160)
         return (None, None) + tuple(g[i] for i in range(L))
 
@@ -64,6 +70,7 @@ class HashEncoder(nn.Module):
         self._scales = [float((self.N_min * self.b ** i).to(torch.float32)) for i in range(self.L)]   # :153
         self._host_geom = None
         self._grad_hooks = []
+        self._grad_chunks = 4          # level chunks of the backward pass when gradient hooks are attached
         self._flat = None
         self._reflatten()
 

@@ -231,13 +231,26 @@ def mlp_bwd_f32(feat, dirs, dir_group, params, dims: MlpDims, dout, act, want_df
     return dfeat, ddirs
 
 
+_tc_scratch = {}
+
+
+def mlp_tc_scratch(dims: MlpDims, device) -> torch.Tensor:
+    """Per-device scratch of the tensor-core MLP kernels (operand image + per-CTA gradient rows), allocated once."""
+    key = (torch.device(device).index, dims.in0, dims.d_view)
+    buf = _tc_scratch.get(key)
+    if buf is None:
+        buf = torch.empty(int(lib().hbr_mlp_tc_scratch_bytes(C.byref(dims))), device=device, dtype=torch.uint8)
+        _tc_scratch[key] = buf
+    return buf
+
+
 def mlp_fwd_tc(feat, dirs, dir_group, params, dims: MlpDims, keep_act: bool = False):
     """bf16 tensor-core forward; keeps nothing (the backward recomputes), returns (out, None)."""
     require_cuda(feat, dirs, params)
     n = feat.shape[0]
     out = torch.empty((n, 4), device=feat.device, dtype=torch.float32)
     check(lib().hbr_mlp_fwd_tc(ptr(feat), feat.stride(0), ptr(dirs), dir_group, n, ptr(params), C.byref(dims), ptr(out),
-                               stream()))
+                               ptr(mlp_tc_scratch(dims, feat.device)), stream()))
     return out, None
 
 
@@ -247,7 +260,8 @@ def mlp_bwd_tc(feat, dirs, dir_group, params, dims: MlpDims, out, dout, want_dfe
     dfeat = torch.empty((n, dims.in0), device=feat.device, dtype=torch.float32) if want_dfeat else None
     ddirs = torch.zeros_like(dirs) if want_ddirs else None
     check(lib().hbr_mlp_bwd_tc(ptr(feat), feat.stride(0), ptr(dirs), dir_group, n, ptr(params), C.byref(dims), ptr(out),
-                               ptr(dout), ptr(dfeat), dims.in0, ptr(ddirs), ptr(dparams), stream()))
+                               ptr(dout), ptr(dfeat), dims.in0, ptr(ddirs), ptr(dparams),
+                               ptr(mlp_tc_scratch(dims, feat.device)), stream()))
     return dfeat, ddirs
 
 

@@ -108,11 +108,15 @@ int hbr_mlp_bwd_f32(const float* feat, int64_t feat_stride, const float* dirs, i
  * between the passes: the backward kernel recomputes them in shared memory from feat, takes ELU' / LeakyReLU'
  * from `out` (the (n,4) result of the forward call), and keeps the weight-gradient accumulators in TMEM across
  * all tiles of a persistent CTA.  dfeat / ddirs may be NULL; dparams (flat fp32) and ddirs are ACCUMULATED into. */
+/* scratch: optional device buffer of hbr_mlp_tc_scratch_bytes(dims) bytes, 256-byte aligned (NULL = none).  With it a
+ * small prep kernel builds the bf16 operand image once per call and the backward sums per-CTA gradient rows with a
+ * reduce kernel; without it every CTA converts the parameters itself and flushes its gradients with atomics. */
+int64_t hbr_mlp_tc_scratch_bytes(const hbr_mlp_dims* dims);
 int hbr_mlp_fwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
-                   const float* params, const hbr_mlp_dims* dims, float* out, void* stream);
+                   const float* params, const hbr_mlp_dims* dims, float* out, void* scratch, void* stream);
 int hbr_mlp_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                    const float* params, const hbr_mlp_dims* dims, const float* out, const float* dout, float* dfeat,
-                   int64_t dfeat_stride, float* ddirs, float* dparams, void* stream);
+                   int64_t dfeat_stride, float* ddirs, float* dparams, void* scratch, void* stream);
 /* Self-test of the three UMMA operand modes the MLP kernels rely on (one 128-thread CTA, bf16 inputs
  * rounded from fp32, fp32 result): mode 0: D[128,N] = A[128,K] B[N,K]^T; mode 1: D[128,N] = A[128,K] Bt[K,N];
  * mode 2: D[64,N] = At[128,64]^T Bt[128,N]. */
