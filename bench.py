@@ -35,9 +35,24 @@ sys.path.insert(0, ROOT)
 BYTES_PER_POINT = {
     "hbr_hash_encode_fwd": 1164, "hbr_hash_encode_bwd": 1164, "hbr_mlp_fwd_f32": 144, "hbr_mlp_bwd_f32": 272,
     "hbr_mlp_fwd_tc": 144, "hbr_mlp_bwd_tc": 272, "hbr_composite_fwd": 16, "hbr_composite_bwd": 32,
-    "hbr_field_fwd": 1040, "hbr_field_bwd": 1040,
+    "hbr_field_fwd_tc": 1164 + 144, "hbr_field_bwd_tc": 1164 + 272,
 }
+# algorithmic FLOP per point of MLP_3D: 27 904 forward, 2 x that for the backward GEMMs (dgrad + wgrad)
+FLOPS_PER_POINT = {"hbr_mlp_fwd_tc": 27904, "hbr_mlp_bwd_tc": 55808, "hbr_mlp_fwd_f32": 27904, "hbr_mlp_bwd_f32": 55808}
 STEP_BYTES_PER_POINT = 2792
+
+
+def kernel_roofline(name, pts_per_launch, mean_ms, peaks):
+    """Roofline entry of one C-ABI call: tensor-bound for the MLP GEMM chains, HBM-bound (effective bandwidth over the
+    algorithmic bytes, gathers counted whether or not they hit L2) for everything else."""
+    hbm, hbm_src, tf, tf_src = peaks
+    if name in FLOPS_PER_POINT:
+        ach = FLOPS_PER_POINT[name] * pts_per_launch / (mean_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf,
+                "peak_source": tf_src, "algorithmic_flop_per_point": FLOPS_PER_POINT[name], "mean_launch_ms": mean_ms}
+    ach = BYTES_PER_POINT.get(name, 0) * pts_per_launch / (mean_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+            "peak_source": hbm_src, "algorithmic_bytes_per_point": BYTES_PER_POINT.get(name), "mean_launch_ms": mean_ms}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -140,12 +155,14 @@ class ClockSampler:
 
 
 def measured_peaks():
+    """(HBM GB/s, source, bf16 TFLOP/s sustained -- the kernels are timed inside a long step --, source)."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return (float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)",
+                float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))), "measured sustained (MEASURED_PEAKS.json)")
+    return 6650.0, "fallback (B200_PROFILING.md)", 1400.0, "fallback sustained (B200_PROFILING.md)"
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -336,18 +353,24 @@ def run_b200(args):
     n_pts = rays * pts_per_ray
     total_rays = rays * world * args.steps
     value = total_rays / (dev_ms / 1e3)
-    peak, peak_src = measured_peaks()
+    peaks = measured_peaks()
+    peak = peaks[0]
     # dominant kernel
     tot = {k: c * m for k, (c, m) in kern.items()}
     dom = max(tot, key=tot.get)
-    calls_per_step = kern[dom][0] / args.steps
-    pts_per_launch = n_pts / calls_per_step
-    achieved = BYTES_PER_POINT.get(dom, 0) * pts_per_launch / (kern[dom][1] * 1e-3) / 1e9
-    traffic = None
+    traffic_tab = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get(dom)
+            traffic_tab = json.load(f)
+
+    def roof(name):
+        c, m = kern[name]
+        r = kernel_roofline(name, n_pts / (c / args.steps), m, peaks)
+        r["traffic"] = traffic_tab.get(name)       # dram bytes read+written per launch, one ncu --set full capture
+        return r
+
+    roofline = roof(dom)
     step_achieved = STEP_BYTES_PER_POINT * n_pts / (dev_ms / args.steps * 1e-3) / 1e9
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     line = {
@@ -361,9 +384,9 @@ def run_b200(args):
         "e2e": {"value": total_rays / (e2e_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_point": BYTES_PER_POINT.get(dom),
-                     "mean_launch_ms": kern[dom][1]},
+        "roofline": roofline,
+        "kernel_rooflines": {k: {kk: vv for kk, vv in roof(k).items() if kk in ("bound", "achieved", "unit", "frac", "traffic")}
+                             for k in sorted(kern) if k in BYTES_PER_POINT},
         "step_roofline": {"algorithmic_bytes_per_point": STEP_BYTES_PER_POINT, "achieved": step_achieved, "frac": step_achieved / peak,
                           "unit": "GB/s"},
         "kernels_ms": {k: {"launches_per_step": c / args.steps, "mean_ms": m} for k, (c, m) in sorted(kern.items())},

@@ -452,6 +452,141 @@ __global__ void __launch_bounds__(256) mlp_grad_reduce_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// fused hash-grid encoder (F = 2, L*F = 32, power-of-two T): the tile group gathers its own 128 x 32 feature tile
+// straight into the A operand (forward) and scatters d(features) straight out of the accumulator (backward); the fp32
+// feature / d(feature) tensors of the unfused path never exist.  Same arithmetic as hash_grid.cu (hash_encoding.py:146-170).
+// ---------------------------------------------------------------------------------------------------------------
+struct EncArgs {
+  const float* x;                // (n,3) fp32 sample positions
+  const float* table;            // (L,T,2) fp32                      (forward)
+  float* dtable;                 // (L,T,2) fp32, accumulated into    (backward)
+  __nv_bfloat16* feat16;         // (n,32) bf16 features: written by the forward, re-read by the backward recompute
+};
+
+// this thread's point -> 32 bf16 features into row r of the canonical A tile (+ its row of feat16)
+__device__ __forceinline__ void encode_row(const EncArgs& e, const HashGeom& g, long long gp, long long n, int r, uint8_t* x0) {
+  float pt[3] = {0.f, 0.f, 0.f};
+  if (gp < n) {
+    pt[0] = __ldg(e.x + gp * 3 + 0); pt[1] = __ldg(e.x + gp * 3 + 1); pt[2] = __ldg(e.x + gp * 3 + 2);
+  }
+  uint32_t packed[16];
+#pragma unroll 2
+  for (int l = 0; l < 16; ++l) {
+    const float s = g.scale[l];
+    long long ix, iy, iz;
+    float fx, fy, fz;
+    cell_of(pt[0], g.mu[0], g.sigma, s, ix, fx);
+    cell_of(pt[1], g.mu[1], g.sigma, s, iy, fy);
+    cell_of(pt[2], g.mu[2], g.sigma, s, iz, fz);
+    uint32_t idx[8];
+    corner_indices<true>(ix, iy, iz, g.T, idx);
+    const float* lvl = e.table + (size_t)l * g.T * 2;
+    float v[8][2];
+    if (!(ix & 1)) {             // even x: corners (x, x+1) share one aligned 16-byte slot
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(lvl) + (idx[c] >> 1));
+        const bool odd = idx[c] & 1;
+        v[c][0] = odd ? q.z : q.x;     v[c][1] = odd ? q.w : q.y;
+        v[c + 1][0] = odd ? q.x : q.z; v[c + 1][1] = odd ? q.y : q.w;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float2 q = __ldg(reinterpret_cast<const float2*>(lvl) + idx[c]);
+        v[c][0] = q.x; v[c][1] = q.y;
+      }
+    }
+    float w[8];
+    corner_weights(fx, fy, fz, w);
+    float a0 = __fmul_rn(v[0][0], w[0]), a1 = __fmul_rn(v[0][1], w[0]);
+#pragma unroll
+    for (int c = 1; c < 8; ++c) {
+      a0 = __fadd_rn(a0, __fmul_rn(v[c][0], w[c]));
+      a1 = __fadd_rn(a1, __fmul_rn(v[c][1], w[c]));
+    }
+    packed[l] = pack_bf16(a0, a1);
+  }
+#pragma unroll
+  for (int cg = 0; cg < 4; ++cg) {
+    const uint4 q = make_uint4(packed[4 * cg], packed[4 * cg + 1], packed[4 * cg + 2], packed[4 * cg + 3]);
+    *reinterpret_cast<uint4*>(x0 + chunk_off(r, cg, kTile)) = q;
+    if (gp < n) reinterpret_cast<uint4*>(e.feat16 + gp * 32)[cg] = q;
+  }
+}
+
+// backward recompute: this thread's saved bf16 feature row -> row r of the canonical A tile
+__device__ __forceinline__ void load_feat16_row(const EncArgs& e, long long gp, long long n, int r, uint8_t* x0) {
+#pragma unroll
+  for (int cg = 0; cg < 4; ++cg) {
+    const uint4 q = gp < n ? __ldg(reinterpret_cast<const uint4*>(e.feat16 + gp * 32) + cg) : make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(x0 + chunk_off(r, cg, kTile)) = q;
+  }
+}
+
+// d(features) of this thread's point (32 fp32 values in registers) -> scatter-add into the table gradient.  A warp is 32
+// consecutive points (consecutive samples of a ray): runs of lanes in the same cell are merged with shuffles and the
+// run head issues the reductions, paired into red.global.add.v4.f32 where the two corners share a 16-byte slot.
+__device__ __forceinline__ void scatter_row(const EncArgs& e, const HashGeom& g, const float pt[3], bool valid, int lane,
+                                            const float* df) {
+#pragma unroll 1
+  for (int l = 0; l < 16; ++l) {
+    const float s = g.scale[l];
+    long long ix, iy, iz;
+    float fx, fy, fz;
+    cell_of(pt[0], g.mu[0], g.sigma, s, ix, fx);
+    cell_of(pt[1], g.mu[1], g.sigma, s, iy, fy);
+    cell_of(pt[2], g.mu[2], g.sigma, s, iz, fz);
+    float w[8];
+    corner_weights(fx, fy, fz, w);
+    float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if (q == l) { g0 = df[2 * q]; g1 = df[2 * q + 1]; }
+    float val[8][2];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { val[c][0] = w[c] * g0; val[c][1] = w[c] * g1; }
+    const long long pix = __shfl_up_sync(kFull, ix, 1);
+    const long long piy = __shfl_up_sync(kFull, iy, 1);
+    const long long piz = __shfl_up_sync(kFull, iz, 1);
+    const int pvalid = __shfl_up_sync(kFull, (int)valid, 1);
+    const bool head = lane == 0 || !valid || !pvalid || pix != ix || piy != iy || piz != iz;
+    const unsigned heads = __ballot_sync(kFull, head);
+    if (heads != kFull) {
+      const unsigned above = lane == 31 ? 0u : (heads & (0xfffffffeu << lane));
+      const int end = above ? (__ffs(above) - 1) : 32;                    // first lane of the next run
+      const int maxrun = __reduce_max_sync(kFull, head ? end - lane : 0);
+      for (int d = 1; d < maxrun; d <<= 1) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int f = 0; f < 2; ++f) {
+            const float t = __shfl_down_sync(kFull, val[c][f], d);
+            if (lane + d < end) val[c][f] += t;
+          }
+      }
+    }
+    if (head && valid) {
+      uint32_t idx[8];
+      corner_indices<true>(ix, iy, iz, g.T, idx);
+      float* lvl = e.dtable + (size_t)l * g.T * 2;
+      if (!(ix & 1)) {
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+          const bool odd = idx[c] & 1;
+          const float4 q = odd ? make_float4(val[c + 1][0], val[c + 1][1], val[c][0], val[c][1])
+                               : make_float4(val[c][0], val[c][1], val[c + 1][0], val[c + 1][1]);
+          atomicAdd(reinterpret_cast<float4*>(lvl) + (idx[c] >> 1), q);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) atomicAdd(reinterpret_cast<float2*>(lvl) + idx[c], make_float2(val[c][0], val[c][1]));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------------
 template <int K0P, int KCP, int G>
@@ -465,11 +600,12 @@ struct FwdSmem {
 };
 
 // TRACE: clock64 stamps of group 0 / its MMA warp in CTA 0 (debug entry point hbr_debug_mlp_trace; compiled out otherwise)
-template <int K0P, int KCP, int G, bool TRACE = false>
+template <int K0P, int KCP, int G, bool TRACE = false, bool ENC = false>
 __global__ void __launch_bounds__(G * (kTile + 32), 1)
 mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const float* __restrict__ dirs, long long dir_group,
                   long long n, const float* __restrict__ params, int in0, int dv, float* __restrict__ out,
-                  const uint8_t* __restrict__ image = nullptr, long long* __restrict__ trace = nullptr) {
+                  const uint8_t* __restrict__ image, long long* __restrict__ trace, const EncArgs enc,
+                  const __grid_constant__ HashGeom geom) {
   using SM = FwdSmem<K0P, KCP, G>;
   using WO = WOfs<K0P, KCP>;
   constexpr int kCols = G * 64 <= 64 ? 64 : (G * 64 <= 128 ? 128 : (G * 64 <= 256 ? 256 : 512));
@@ -550,8 +686,12 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       const long long dir_row = valid ? gp / dir_group : 0;
       if (valid && lane == 0) prefetch_l1(dirs + dir_row * dv);
       TR();
-      load_features<K0P>(feat, feat_stride, tile * kTile, n, in0, vec_ok, r, buf);
-      if ((tile + nslots) * kTile + r < n) prefetch_l2(feat + ((tile + nslots) * kTile + r) * feat_stride);
+      if (ENC) {
+        encode_row(enc, geom, gp, n, r, buf);
+      } else {
+        load_features<K0P>(feat, feat_stride, tile * kTile, n, in0, vec_ok, r, buf);
+        if ((tile + nslots) * kTile + r < n) prefetch_l2(feat + ((tile + nslots) * kTile + r) * feat_stride);
+      }
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
       relu_epilogue64(taddr, r, buf);
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
@@ -648,13 +788,14 @@ struct BwdTmem {
   static_assert(end <= 512 && g4 + 80 <= 512, "TMEM budget exceeded");
 };
 
-template <int K0P, int KCP, int G, bool TRACE = false>
+template <int K0P, int KCP, int G, bool TRACE = false, bool ENC = false>
 __global__ void __launch_bounds__(G * kTile + 64, 1)
 mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const float* __restrict__ dirs, long long dir_group,
                   long long n, const float* __restrict__ params, int in0, int dv, const float* __restrict__ out,
                   const float* __restrict__ dout, float* __restrict__ dfeat, long long dfeat_stride,
-                  float* __restrict__ ddirs, float* __restrict__ dparams, const uint8_t* __restrict__ image = nullptr,
-                  float* __restrict__ grad_rows = nullptr, long long* __restrict__ trace = nullptr) {
+                  float* __restrict__ ddirs, float* __restrict__ dparams, const uint8_t* __restrict__ image,
+                  float* __restrict__ grad_rows, long long* __restrict__ trace, const EncArgs enc,
+                  const __grid_constant__ HashGeom geom) {
   using SM = BwdSmem<K0P, KCP, G>;
   using WO = WOfs<K0P, KCP>;
   using TM = BwdTmem<K0P, KCP>;
@@ -830,9 +971,16 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       }
       TR();
       // ---- recompute the forward activations ----
-      load_features<K0P>(feat, feat_stride, tile * kTile, n, in0, vec_ok, r, x0);
+      float pt[3] = {0.f, 0.f, 0.f};
+      if (ENC) {
+        if (valid) { pt[0] = __ldg(enc.x + gp * 3 + 0); pt[1] = __ldg(enc.x + gp * 3 + 1); pt[2] = __ldg(enc.x + gp * 3 + 2); }
+        load_feat16_row(enc, gp, n, r, x0);
+      } else {
+        load_features<K0P>(feat, feat_stride, tile * kTile, n, in0, vec_ok, r, x0);
+      }
       if ((tile + nslots) * kTile + r < n) {
-        prefetch_l2(feat + ((tile + nslots) * kTile + r) * feat_stride);
+        if (ENC) prefetch_l2(enc.feat16 + ((tile + nslots) * kTile + r) * 32);
+        else prefetch_l2(feat + ((tile + nslots) * kTile + r) * feat_stride);
         if ((r & 7) == 0) {
           prefetch_l2(out + ((tile + nslots) * kTile + r) * 4);
           prefetch_l2(dout + ((tile + nslots) * kTile + r) * 4);
@@ -901,7 +1049,11 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // sig_model.2: work = dA(h1)
       masked_dz_inplace64(taddr, r, h1, [&] { HBR_WAIT_B(); });
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // sig_model.0: work[0,K0P) = d(feat)
-      if (dfeat != nullptr) {
+      if (ENC) {
+        float df[K0P];
+        tmem_ld<K0P>(taddr, df);
+        scatter_row(enc, geom, pt, valid, lane, df);
+      } else if (dfeat != nullptr) {
         float df[K0P];
         tmem_ld<K0P>(taddr, df);
         if (dvec_ok) {
@@ -1038,7 +1190,8 @@ extern "C" int hbr_debug_mlp_trace_bwd(const float* feat, const float* dirs, int
   HBR_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<32, 48, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), 2), sm_count());
   mlp_bwd_tc_kernel<32, 48, 2, true><<<grid, 2 * kTile + 64, smem, as_stream(stream)>>>(
-      feat, 32, dirs, dir_group, n, params, 32, 24, out, dout, dfeat, 32, nullptr, dparams, nullptr, nullptr, trace);
+      feat, 32, dirs, dir_group, n, params, 32, 24, out, dout, dfeat, 32, nullptr, dparams, nullptr, nullptr, trace, EncArgs{},
+      HashGeom{});
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -1048,8 +1201,8 @@ extern "C" int hbr_debug_mlp_trace(const float* feat, const float* dirs, int64_t
   constexpr int smem = FwdSmem<32, 48, 4>::total;
   HBR_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<32, 48, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), 4), sm_count());
-  mlp_fwd_tc_kernel<32, 48, 4, true><<<grid, 4 * (kTile + 32), smem, as_stream(stream)>>>(feat, 32, dirs, dir_group, n,
-                                                                                         params, 32, 24, out, nullptr, trace);
+  mlp_fwd_tc_kernel<32, 48, 4, true><<<grid, 4 * (kTile + 32), smem, as_stream(stream)>>>(
+      feat, 32, dirs, dir_group, n, params, 32, 24, out, nullptr, trace, EncArgs{}, HashGeom{});
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -1063,36 +1216,40 @@ extern "C" int64_t hbr_mlp_tc_scratch_bytes(const hbr_mlp_dims* dims) {
   return narrow_shape(dims) ? Scratch<32, 48>::total : Scratch<64, 64>::total;
 }
 
-template <int K0P, int KCP, int G>
+template <int K0P, int KCP, int G, bool ENC>
 static int launch_fwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
-                         const float* params, int in0, int dv, float* out, uint8_t* scratch, cudaStream_t st) {
+                         const float* params, int in0, int dv, float* out, uint8_t* scratch, const EncArgs& enc,
+                         const HashGeom& geom, cudaStream_t st) {
   constexpr int smem = FwdSmem<K0P, KCP, G>::total;
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), G), sm_count());
   if (scratch != nullptr) mlp_prep_kernel<K0P, KCP><<<kPrepCtas - 1, 256, 0, st>>>(params, in0, dv, scratch);
-  HBR_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<K0P, KCP, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  mlp_fwd_tc_kernel<K0P, KCP, G><<<grid, G * (kTile + 32), smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv,
-                                                                       out, scratch);
+  auto kern = mlp_fwd_tc_kernel<K0P, KCP, G, false, ENC>;
+  HBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, G * (kTile + 32), smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, scratch, nullptr, enc,
+                                             geom);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
 
-template <int K0P, int KCP, int G>
+template <int K0P, int KCP, int G, bool ENC>
 static int launch_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                          const float* params, int in0, int dv, const float* out, const float* dout, float* dfeat,
-                         int64_t dfeat_stride, float* ddirs, float* dparams, uint8_t* scratch, cudaStream_t st) {
+                         int64_t dfeat_stride, float* ddirs, float* dparams, uint8_t* scratch, const EncArgs& enc,
+                         const HashGeom& geom, cudaStream_t st) {
   using SC = Scratch<K0P, KCP>;
   constexpr int smem = BwdSmem<K0P, KCP, G>::total;
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), G), sm_count());
   const bool rows = scratch != nullptr && dparams != nullptr && grid <= SC::kMaxRows;
   if (scratch != nullptr) mlp_prep_kernel<K0P, KCP><<<kPrepCtas, 256, 0, st>>>(params, in0, dv, scratch);
-  HBR_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<K0P, KCP, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  mlp_bwd_tc_kernel<K0P, KCP, G><<<grid, G * kTile + 64, smem, st>>>(
-      feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, dout, dfeat, dfeat_stride, ddirs, dparams, scratch,
-      rows ? reinterpret_cast<float*>(scratch + SC::off_grad) : nullptr);
+  auto kern = mlp_bwd_tc_kernel<K0P, KCP, G, false, ENC>;
+  HBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, G * kTile + 64, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, dout, dfeat,
+                                           dfeat_stride, ddirs, dparams, scratch,
+                                           rows ? reinterpret_cast<float*>(scratch + SC::off_grad) : nullptr, nullptr, enc, geom);
   if (rows) {
     const int total = make_layout(in0, dv).total;
-    mlp_grad_reduce_kernel<<<dim3((total + 255) / 256, kReduceSlices), 256, 0, st>>>(reinterpret_cast<const float*>(scratch + SC::off_grad), grid,
-                                                                 SC::kRowFloats, total, dparams);
+    mlp_grad_reduce_kernel<<<dim3((total + 255) / 256, kReduceSlices), 256, 0, st>>>(
+        reinterpret_cast<const float*>(scratch + SC::off_grad), grid, SC::kRowFloats, total, dparams);
   }
   HBR_LAUNCH_CHECK();
   return HBR_OK;
@@ -1108,8 +1265,10 @@ extern "C" int hbr_mlp_fwd_tc(const float* feat, int64_t feat_stride, const floa
   cudaStream_t st = as_stream(stream);
   uint8_t* sc = static_cast<uint8_t*>(scratch);
   if (narrow_shape(dims))
-    return launch_fwd_tc<32, 48, 4>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out, sc, st);
-  return launch_fwd_tc<64, 64, 4>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out, sc, st);
+    return launch_fwd_tc<32, 48, 4, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out, sc,
+                                           EncArgs{}, HashGeom{}, st);
+  return launch_fwd_tc<64, 64, 4, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out, sc,
+                                         EncArgs{}, HashGeom{}, st);
 }
 
 extern "C" int hbr_mlp_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
@@ -1126,8 +1285,49 @@ extern "C" int hbr_mlp_bwd_tc(const float* feat, int64_t feat_stride, const floa
   cudaStream_t st = as_stream(stream);
   uint8_t* sc = static_cast<uint8_t*>(scratch);
   if (narrow_shape(dims))
-    return launch_bwd_tc<32, 48, 2>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out, dout, dfeat,
-                                    dfeat_stride, ddirs, dparams, sc, st);
-  return launch_bwd_tc<64, 64, 1>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out, dout, dfeat,
-                                  dfeat_stride, ddirs, dparams, sc, st);
+    return launch_bwd_tc<32, 48, 2, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out, dout,
+                                           dfeat, dfeat_stride, ddirs, dparams, sc, EncArgs{}, HashGeom{}, st);
+  return launch_bwd_tc<64, 64, 1, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out, dout,
+                                         dfeat, dfeat_stride, ddirs, dparams, sc, EncArgs{}, HashGeom{}, st);
+}
+
+// ---- fused field evaluation: hash-grid encoder + MLP_3D in one kernel per direction ------------------------------
+static int check_field(const hbr_hash_geom* geom, const hbr_mlp_dims* dims) {
+  HBR_REQUIRE(geom != nullptr, "geom is NULL");
+  if (int rc = check_dims(dims)) return rc;
+  HBR_REQUIRE(geom->F == 2 && geom->L == 16 && geom->E == 0 && dims->in0 == 32 && is_pow2(geom->T) && geom->T >= 2 &&
+                  geom->T <= (1u << 30) && narrow_shape(dims),
+              "the fused field kernels cover F=2, L=16, E=0, power-of-two T, d_view <= 25 (use the separate kernels otherwise)");
+  return HBR_OK;
+}
+
+extern "C" int hbr_field_fwd_tc(const float* x, int64_t n, const float* table, const hbr_hash_geom* geom, const float* dirs,
+                                int64_t dir_group, const float* params, const hbr_mlp_dims* dims, float* out, void* feat16,
+                                void* scratch, void* stream) {
+  if (int rc = check_field(geom, dims)) return rc;
+  if (n == 0) return HBR_OK;
+  HBR_REQUIRE(x && table && dirs && params && out && feat16, "NULL pointer");
+  HBR_REQUIRE(dir_group >= 1, "dir_group");
+  HBR_REQUIRE((uintptr_t)out % 16 == 0 && (uintptr_t)table % 16 == 0 && (uintptr_t)feat16 % 16 == 0 &&
+                  (uintptr_t)scratch % 256 == 0, "alignment");
+  EncArgs e{};
+  e.x = x; e.table = table; e.feat16 = static_cast<__nv_bfloat16*>(feat16);
+  return launch_fwd_tc<32, 48, 4, true>(nullptr, 32, dirs, dir_group, n, params, 32, dims->d_view, out,
+                                        static_cast<uint8_t*>(scratch), e, to_device_geom(*geom), as_stream(stream));
+}
+
+extern "C" int hbr_field_bwd_tc(const float* x, int64_t n, const hbr_hash_geom* geom, const float* dirs, int64_t dir_group,
+                                const float* params, const hbr_mlp_dims* dims, const void* feat16, const float* out,
+                                const float* dout, float* dtable, float* ddirs, float* dparams, void* scratch, void* stream) {
+  if (int rc = check_field(geom, dims)) return rc;
+  if (n == 0) return HBR_OK;
+  HBR_REQUIRE(x && dirs && params && feat16 && out && dout && dtable, "NULL pointer");
+  HBR_REQUIRE(dir_group >= 1, "dir_group");
+  HBR_REQUIRE((uintptr_t)out % 16 == 0 && (uintptr_t)dout % 16 == 0 && (uintptr_t)dtable % 16 == 0 &&
+                  (uintptr_t)feat16 % 16 == 0 && (uintptr_t)scratch % 256 == 0, "alignment");
+  EncArgs e{};
+  e.x = x; e.dtable = dtable; e.feat16 = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(feat16));
+  return launch_bwd_tc<32, 48, 2, true>(nullptr, 32, dirs, dir_group, n, params, 32, dims->d_view, out, dout, nullptr, 32,
+                                        ddirs, dparams, static_cast<uint8_t*>(scratch), e, to_device_geom(*geom),
+                                        as_stream(stream));
 }

@@ -265,6 +265,27 @@ def mlp_bwd_tc(feat, dirs, dir_group, params, dims: MlpDims, out, dout, want_dfe
     return dfeat, ddirs
 
 
+def field_fwd_tc(x, table, geom: HashGeom, dirs, dir_group, params, dims: MlpDims):
+    """Fused hash-grid encoder + MLP_3D forward (bf16 tensor cores).  Returns (out (N,4) fp32, feat16 (N,32) bf16 = the
+    features that were fed to the tensor cores, kept for the backward recompute)."""
+    require_cuda(x, table, dirs, params)
+    n = x.shape[0]
+    out = torch.empty((n, 4), device=x.device, dtype=torch.float32)
+    feat16 = torch.empty((n, 32), device=x.device, dtype=torch.bfloat16)
+    check(lib().hbr_field_fwd_tc(ptr(x), n, ptr(table), C.byref(geom), ptr(dirs), dir_group, ptr(params), C.byref(dims),
+                                 ptr(out), ptr(feat16), ptr(mlp_tc_scratch(dims, x.device)), stream()))
+    return out, feat16
+
+
+def field_bwd_tc(x, geom: HashGeom, dirs, dir_group, params, dims: MlpDims, feat16, out, dout, dtable, want_ddirs, dparams):
+    """Fused MLP_3D backward + hash-grid scatter-add: dtable (L,T,2) and dparams are accumulated into."""
+    ddirs = torch.zeros_like(dirs) if want_ddirs else None
+    check(lib().hbr_field_bwd_tc(ptr(x), x.shape[0], C.byref(geom), ptr(dirs), dir_group, ptr(params), C.byref(dims),
+                                 ptr(feat16), ptr(out), ptr(dout), ptr(dtable), ptr(ddirs), ptr(dparams),
+                                 ptr(mlp_tc_scratch(dims, x.device)), stream()))
+    return ddirs
+
+
 def debug_umma(mode: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int) -> torch.Tensor:
     D = torch.empty((M, N), device=A.device, dtype=torch.float32)
     check(lib().hbr_debug_umma(mode, ptr(A.contiguous()), ptr(B.contiguous()), ptr(D), N, K, stream()))

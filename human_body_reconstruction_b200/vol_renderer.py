@@ -23,6 +23,34 @@ from .helper import calc_color, hierarchical_sampling, strat_sampler
 from .test_hash import MLP_3D
 
 
+class _FieldFn(torch.autograd.Function):
+    """Sample positions (N,3) -> (N,4) [rgb, sigma] through the FUSED encoder + MLP kernels (one kernel per direction):
+    HashEncoder.forward feeding MLP_3D.forward as vol_renderer.py:179,211 chains them, bf16 tensor-core arithmetic."""
+
+    @staticmethod
+    def forward(ctx, pts, dirs, dir_group, enc, mlp, *params):
+        geom, dims = enc._geom(), mlp._dims()
+        dirs = dirs.float().contiguous()
+        out, feat16 = ops.field_fwd_tc(pts, enc._flat_table(), geom, dirs, dir_group, mlp._flat_params(), dims)
+        ctx.enc, ctx.mlp, ctx.geom, ctx.dims, ctx.dir_group = enc, mlp, geom, dims, dir_group
+        ctx.save_for_backward(pts, dirs, feat16, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        pts, dirs, feat16, out = ctx.saved_tensors
+        enc, mlp = ctx.enc, ctx.mlp
+        L, T, F = enc.L, enc.T, enc.F
+        g = torch.zeros((L, T, F), device=dout.device, dtype=torch.float32)
+        flat = mlp._flat_params()
+        dflat = torch.zeros_like(flat)
+        ddirs = ops.field_bwd_tc(pts, ctx.geom, dirs, ctx.dir_group, flat, ctx.dims, feat16, out.detach(),
+                                 dout.float().contiguous(), g, ctx.needs_input_grad[1], dflat)
+        mlp._publish_grad(dflat)
+        enc._publish_grad(g)
+        return (None, ddirs, None, None, None) + tuple(g[i] for i in range(L)) + tuple(mlp._grad_views(dflat))
+
+
 def _unwrap(model):
     if isinstance(model, nn.DataParallel) and len(model.device_ids) <= 1:
         return model.module
@@ -54,6 +82,12 @@ class Volume_Renderer:
         self.var_model = var_model
         self._grid_state = (None, True)           # (bool_grid._version, all_true)
         self._host_norm = None
+        # Encoder + MLP fused into one kernel per direction (hbr_field_*_tc): no fp32 feature / d(feature) tensors in HBM
+        # (-235 B/point of traffic), same results.  Measured on B200 at 4096 x 128 points it is time-neutral against the
+        # separate kernels (the tile groups of the tensor-core kernel run at low occupancy, so their gather / scatter
+        # phases are latency-bound), and the separate path can overlap the table-gradient all-reduce per level chunk,
+        # so it is opt-in: True fuses whenever the configuration is covered, "auto" only without gradient hooks.
+        self.fuse_field = False
 
     # -- occupancy grid (vol_renderer.py:116-140) --------------------------------------------------------------
     def update_grid(self, points: torch.Tensor, alpha: torch.Tensor):
@@ -92,13 +126,29 @@ class Volume_Renderer:
               and isinstance(m, MLP_3D) and m._native and not m.use_sdf and not self.use_sdf)
         return m if ok else None
 
+    def _can_fuse(self, mlp) -> bool:
+        enc = self.Pos_encode
+        if self.fuse_field is False or not (torch.is_autocast_enabled() and ops.HAS_TC):
+            return False
+        ok = (enc.F == 2 and enc.L == 16 and enc.E == 0 and enc.T >= 2 and (enc.T & (enc.T - 1)) == 0
+              and mlp._in0 == 32 and mlp.d_view <= 25)
+        if self.fuse_field == "auto":
+            ok = ok and not enc._grad_hooks
+        return ok
+
     def _field_pass(self, mlp, rays_o, rays_d, t, dir_enc, dir_norm, mask_needed):
         """positions -> encoder -> MLP -> compositing for depths t ((S,) shared or (R,S) per ray)."""
         R, S = rays_o.shape[0], t.shape[-1]
         pts = ops.ray_points(rays_o, rays_d, t).view(-1, 3)
         mask = self.get_mask(pts) if mask_needed else None
-        feat = self.Pos_encode(pts)
-        out4 = mlp.field(feat, dir_enc, S)
+        if self._can_fuse(mlp):
+            enc = self.Pos_encode
+            if enc._flat_table().device != pts.device:
+                raise RuntimeError(f"encoder tables are on {enc._flat_table().device}, rays on {pts.device}")
+            out4 = _FieldFn.apply(pts, dir_enc, S, enc, mlp, *[e.weight for e in enc.Embedding_list], *mlp._ordered())
+        else:
+            feat = self.Pos_encode(pts)
+            out4 = mlp.field(feat, dir_enc, S)
         Cc, w = ops.CompositePacked.apply(out4, t, dir_norm, mask, R, S)
         return Cc, w
 

@@ -117,6 +117,18 @@ int hbr_mlp_fwd_tc(const float* feat, int64_t feat_stride, const float* dirs, in
 int hbr_mlp_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                    const float* params, const hbr_mlp_dims* dims, const float* out, const float* dout, float* dfeat,
                    int64_t dfeat_stride, float* ddirs, float* dparams, void* scratch, void* stream);
+/* ---- a2 + a7 fused (the training step's field evaluation under autocast): hash-grid encoder + MLP_3D in ONE kernel per
+ * direction -- HashEncoder.forward (hash_encoding.py:146-170) feeding MLP_3D.forward (test_hash.py:52-72) as
+ * vol_renderer.py:179,211 chains them.  Covers the reference's configuration family F = 2, L = 16, E = 0, power-of-two T,
+ * d_view <= 25; anything else uses the separate entry points.  x (n,3) fp32 sample positions.  The forward writes the
+ * bf16 features it fed to the tensor cores to feat16 (n,32) for the backward recompute; the backward scatter-adds
+ * d(features) into dtable (L,T,2) straight from the accumulator.  dparams / dtable / ddirs are ACCUMULATED into. */
+int hbr_field_fwd_tc(const float* x, int64_t n, const float* table, const hbr_hash_geom* geom_host, const float* dirs,
+                     int64_t dir_group, const float* params, const hbr_mlp_dims* dims, float* out, void* feat16,
+                     void* scratch, void* stream);
+int hbr_field_bwd_tc(const float* x, int64_t n, const hbr_hash_geom* geom_host, const float* dirs, int64_t dir_group,
+                     const float* params, const hbr_mlp_dims* dims, const void* feat16, const float* out,
+                     const float* dout, float* dtable, float* ddirs, float* dparams, void* scratch, void* stream);
 /* Self-test of the three UMMA operand modes the MLP kernels rely on (one 128-thread CTA, bf16 inputs
  * rounded from fp32, fp32 result): mode 0: D[128,N] = A[128,K] B[N,K]^T; mode 1: D[128,N] = A[128,K] Bt[K,N];
  * mode 2: D[64,N] = At[128,64]^T Bt[128,N]. */
