@@ -308,7 +308,7 @@ def run_b200(args):
 
     # (2) the same step captured once in a CUDA graph and replayed (one launch per step instead of ~35)
     gs, graph_note = None, "eager"
-    if args.graph == "on" or (args.graph == "auto" and world == 1):
+    if args.graph in ("on", "auto"):
         try:
             from human_body_reconstruction_b200.graph import GraphedStep
             gs = GraphedStep(vr, nerf, params, rays, args.samples, args.hierarchical, dev, autocast=amp).capture()
@@ -437,7 +437,7 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the step from a CUDA graph (auto: single GPU only)")
+                    help="replay the step from a CUDA graph (auto = on; falls back to eager if capture fails)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -70,7 +70,11 @@ class HashEncoder(nn.Module):
         self._scales = [float((self.N_min * self.b ** i).to(torch.float32)) for i in range(self.L)]   # :153
         self._host_geom = None
         self._grad_hooks = []
-        self._grad_chunks = 4          # level chunks of the backward pass when gradient hooks are attached
+        # level chunks of the backward pass when gradient hooks are attached (each chunk is published -- all-reduced --
+        # as soon as it is enqueued).  Measured on 2 x B200 at 4096 rays/GPU, overlapping the NCCL kernels with the
+        # scatter-add slows both (0.90 ms/step with 4 chunks against 0.79 ms with one all-reduce after the pass), so the
+        # default is one chunk; larger per-GPU batches may prefer more.
+        self._grad_chunks = 1
         self._flat = None
         self._reflatten()
 

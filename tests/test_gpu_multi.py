@@ -1,0 +1,83 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise): rays sharded over 2 ranks, gradients all-reduced
+inside backward by dist.GradAllReduce over NCCL == single-GPU gradients of the concatenated batch."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _build(dev):
+    import human_body_reconstruction_b200 as h
+    torch.manual_seed(0)
+    mu, maxb = torch.tensor([-4.27, -4.31, -3.95]), torch.tensor([4.28, 4.27, 2.37])
+    sigma = ((maxb - mu) ** 2).sum().sqrt()
+    enc = h.HashEncoder(N_min=16, N_max=2048.0, L=16, F=2, T=2 ** 14, dim=3, mu=mu.to(dev), sigma=sigma.to(dev))
+    with torch.no_grad():
+        for e in enc.Embedding_list:
+            e.weight.mul_(5e3)
+    mlp = h.MLP_3D(num_sig=2, num_col=2, L=16, F=2, d_view=24, max_bound=maxb, min_bound=mu)
+    enc, mlp = enc.to(dev), mlp.to(dev)
+    vr = h.Volume_Renderer(H=8, W=8, K=torch.eye(3), near=torch.tensor(2.0), far=torch.tensor(6.0), device=dev,
+                           Pos_encode=enc, Dir_encode=h.PositionalEncoder(3, 4), max_dim=64, sigma_val=sigma, mu=mu)
+    return enc, mlp, vr
+
+
+def _batch():
+    g = torch.Generator().manual_seed(11)
+    R = 256
+    ro = torch.tensor([[0.2, -0.1, 4.0]]).repeat(R, 1) + 0.05 * torch.randn(R, 3, generator=g)
+    rd = torch.nn.functional.normalize(-ro + 0.5 * torch.randn(R, 3, generator=g), dim=-1)
+    return ro, rd, 1 + 0.2 * torch.rand(R, 1, generator=g), torch.rand(R, 3, generator=g), torch.linspace(2.0, 6.0, 32)
+
+
+def _grads(enc, mlp, vr, ro, rd, dn, gt, t, dev):
+    Cr, Cf, _ = vr.vol_render(mlp, rd.to(dev), ro.to(dev), num_samples=32, t=t.to(dev), dir_norm=dn.to(dev), hierarchical=False)
+    (torch.nn.functional.mse_loss(Cr, gt.to(dev)) + torch.nn.functional.mse_loss(Cf, gt.to(dev))).backward()
+    torch.cuda.synchronize()
+    return (torch.stack([e.weight.grad for e in enc.Embedding_list]).cpu(),
+            torch.cat([p.grad.reshape(-1) for p in mlp.parameters()]).cpu())
+
+
+def _worker(rank, world, port_no, tmp):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port_no))
+    from human_body_reconstruction_b200 import dist as hdist
+    hdist.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    enc, mlp, vr = _build(dev)
+    hdist.GradAllReduce(enc, mlp)
+    ro, rd, dn, gt, t = _batch()
+    sl = hdist.shard_rays(ro.shape[0], rank, world)
+    for chunks in (1, 4):
+        enc._grad_chunks = chunks
+        for p in list(enc.parameters()) + list(mlp.parameters()):
+            p.grad = None
+        gt_tab, gt_mlp = _grads(enc, mlp, vr, ro[sl], rd[sl], dn[sl], gt[sl], t, dev)
+        torch.save((gt_tab, gt_mlp), os.path.join(tmp, f"g{rank}_{chunks}.pt"))
+    import torch.distributed as tdist
+    tdist.barrier()
+    tdist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_gradients_equal_single_gpu(tmp_path):
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    dev = torch.device("cuda", 0)
+    enc, mlp, vr = _build(dev)
+    want_tab, want_mlp = _grads(enc, mlp, vr, *_batch(), dev)
+    for chunks in (1, 4):
+        for rank in range(2):
+            tab, gm = torch.load(os.path.join(tmp_path, f"g{rank}_{chunks}.pt"))
+            assert float((tab - want_tab).norm() / want_tab.norm()) < 1e-5, (rank, chunks)
+            assert float((gm - want_mlp).norm() / want_mlp.norm()) < 1e-5, (rank, chunks)
