@@ -20,7 +20,11 @@ import torch
 
 
 def default_loss(Cr, Cf, gt):
-    """train_hash2.py:221 with the MSE criterion of :177."""
+    """train_hash2.py:221 with the MSE criterion of :177.  Without hierarchical sampling vol_render returns Cf = Cr (the
+    same tensor, vol_renderer.py:244): mse + mse of one tensor is exactly 2 * mse (x + x is exact in binary floating
+    point), which halves the loss kernels."""
+    if Cf is Cr:
+        return 2.0 * torch.nn.functional.mse_loss(Cr, gt)
     return torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)
 
 

@@ -136,6 +136,10 @@ int hbr_debug_umma(int mode, const float* A, const float* B, float* D, int N, in
 /* Tensor-pipe probe: `reps` tcgen05.mma (M x N x 16, bf16) issued back to back by one thread round-robin over `nacc`
  * accumulators; cycles[0] = first issue -> completion observed, cycles[1] = first issue -> last issue (SM clocks). */
 int hbr_debug_umma_bench(int M, int N, int reps, int nacc, int mn_major, long long* cycles, void* stream);
+/* Steady-state cost of the GEMM chains the MLP kernels issue: kind 0 forward layer (4 MMAs), 1 dgrad (4), 2 weight
+ * gradient M=64 N=72 (8), 3 transposed weight gradient M=128 N=16 (8); `reps` chains round-robin over `nacc`
+ * accumulators.  cycles[0] = total, cycles[1] = issue only (SM clocks). */
+int hbr_debug_umma_chain_bench(int kind, int reps, int nacc, long long* cycles, void* stream);
 /* Latency probe of the forward kernel (in0 = 32, d_view = 24): trace[0..1000) = clock64 stamps of tile group 0 of CTA 0
  * (tile start, then before-signal / after-signal / after-wait per layer), trace[1024..1524) = the MMA warp's
  * (ready-seen, committed) pairs for that group.  trace holds 2048 int64. */
