@@ -124,9 +124,28 @@ hash_bwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__
   const int pitch = C | 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long base = (long long)blockIdx.x * kTilePts;
-  for (int r = warp; r < kTilePts; r += kHashThreads / 32) {
-    const long long gp = base + r;
-    for (int c = l_begin * F + lane; c < l_end * F; c += 32) tile[r * pitch + c] = gp < n ? __ldg(dy + gp * dy_stride + c) : 0.f;
+  const int c0 = l_begin * F, c1 = l_end * F;
+  if (C == 32 && dy_stride == 32 && ((uintptr_t)dy & 15) == 0) {
+    // the tile is one contiguous 16 KB block of dy: four independent float4 loads per thread, all in flight before the
+    // first shared-memory store (a one-load-at-a-time loop here cost a quarter of the kernel in long-scoreboard stalls)
+    const float4* src = reinterpret_cast<const float4*>(dy + base * 32);
+    float4 q[kTilePts * 8 / kHashThreads];
+#pragma unroll
+    for (int it = 0; it < kTilePts * 8 / kHashThreads; ++it) {
+      const int idx = it * kHashThreads + threadIdx.x;          // float4 index in the tile: row = idx / 8
+      q[it] = base + idx / 8 < n ? __ldg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int it = 0; it < kTilePts * 8 / kHashThreads; ++it) {
+      const int idx = it * kHashThreads + threadIdx.x, r = idx >> 3, c = (idx & 7) * 4;
+      float* t = tile + r * pitch + c;                          // odd pitch: scalar stores, conflict-free
+      t[0] = q[it].x; t[1] = q[it].y; t[2] = q[it].z; t[3] = q[it].w;
+    }
+  } else {
+    for (int r = warp; r < kTilePts; r += kHashThreads / 32) {
+      const long long gp = base + r;
+      for (int c = c0 + lane; c < c1; c += 32) tile[r * pitch + c] = gp < n ? __ldg(dy + gp * dy_stride + c) : 0.f;
+    }
   }
   const int p = threadIdx.x & (kTilePts - 1);
   const int grp = threadIdx.x >> 7;

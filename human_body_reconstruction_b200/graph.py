@@ -36,11 +36,17 @@ class GraphedStep:
         self.num_samples, self.hierarchical = int(num_samples), bool(hierarchical)
         self.loss_fn, self.autocast = loss_fn, autocast
         dev = torch.device(device)
-        self.rays_o = torch.zeros((n_rays, 3), device=dev)
-        self.rays_d = torch.zeros((n_rays, 3), device=dev)
+        # one packed static buffer [rays_o (R,3) | rays_d (R,3) | dir_norm (R,1) | gt (R,3)]: a batch packed the same way
+        # (pack_batch) is loaded with ONE copy instead of four
+        self.n_rays = int(n_rays)
+        self.packed = torch.zeros(10 * n_rays, device=dev)
+        R = n_rays
+        self.rays_o = self.packed[0:3 * R].view(R, 3)
+        self.rays_d = self.packed[3 * R:6 * R].view(R, 3)
+        self.dir_norm = self.packed[6 * R:7 * R].view(R, 1)
+        self.gt = self.packed[7 * R:10 * R].view(R, 3)
         self.rays_d[:, 2] = 1.0
-        self.dir_norm = torch.ones((n_rays, 1), device=dev)
-        self.gt = torch.zeros((n_rays, 3), device=dev)
+        self.dir_norm.fill_(1.0)
         self.loss: Optional[torch.Tensor] = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._warmup = warmup
@@ -53,8 +59,18 @@ class GraphedStep:
         loss.backward()
         return loss
 
-    def load(self, rays_o, rays_d, dir_norm, gt, non_blocking: bool = True):
-        """Copy a batch (device or pinned-host tensors) into the static input buffers."""
+    @staticmethod
+    def pack_batch(rays_o, rays_d, dir_norm, gt, pin: bool = False) -> torch.Tensor:
+        """(rays_o, rays_d, dir_norm, gt) -> the flat (10 R,) layout of the static input buffer."""
+        flat = torch.cat([rays_o.reshape(-1), rays_d.reshape(-1), dir_norm.reshape(-1), gt.reshape(-1)]).float().contiguous()
+        return flat.pin_memory() if pin and not flat.is_cuda else flat
+
+    def load(self, rays_o, rays_d=None, dir_norm=None, gt=None, non_blocking: bool = True):
+        """Copy a batch (device or pinned-host tensors) into the static input buffers: either the four tensors or one
+        packed tensor from pack_batch()."""
+        if rays_d is None:
+            self.packed.copy_(rays_o, non_blocking=non_blocking)
+            return
         self.rays_o.copy_(rays_o, non_blocking=non_blocking)
         self.rays_d.copy_(rays_d, non_blocking=non_blocking)
         self.dir_norm.copy_(dir_norm.reshape(-1, 1), non_blocking=non_blocking)
