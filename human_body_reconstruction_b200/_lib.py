@@ -225,7 +225,9 @@ def ptr(t):
 
 
 def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """cudaStream_t of torch's current stream on the current device (raw getter: ~1 us instead of ~15 us for
+    torch.cuda.current_stream(), which every C-ABI call would otherwise pay)."""
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def require_cuda(*tensors):

@@ -55,7 +55,12 @@ __device__ __forceinline__ void load_point(const XT* __restrict__ x, long long g
 }
 
 // ---- forward ------------------------------------------------------------------------------------------
-template <int F, bool POW2, typename XT, bool PAIR = true>
+// PAIR: 0 = eight 8-byte gathers per level (default); 1 = (x, x+1) corner pairs of an even x share one aligned 16-byte
+// slot: one LDG.128 per pair, the odd-x second load predicated.  Measured at 524 288 points, T = 2^19, cold L2: PAIR 0
+// with 4 levels unrolled (32 gathers in flight per thread) 104 us, 2 levels 109 us, 8 levels 107 us; PAIR 1 124 us
+// (the 16-byte loads double the L1 traffic of the odd-x half) -- pairing only pays in the backward, where it halves
+// the number of reductions.
+template <int F, bool POW2, typename XT, int PAIR = 0, int UNR = 4>
 __global__ void __launch_bounds__(kHashThreads)
 hash_fwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__ table, float* __restrict__ y,
                 long long y_stride, const __grid_constant__ HashGeom g) {
@@ -68,7 +73,7 @@ hash_fwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__
   float pt[3];
   load_point(x, base + p, n, pt);
 
-#pragma unroll 2
+#pragma unroll UNR
   for (int l = grp; l < g.L; l += 2) {
     const float s = g.scale[l];
     long long ix, iy, iz;
@@ -80,14 +85,16 @@ hash_fwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__
     corner_indices<POW2>(ix, iy, iz, g.T, idx);
     const float* lvl = table + (size_t)l * g.T * F;
     float v[8][F];
-    if (F == 2 && POW2 && PAIR && !(ix & 1)) {
-      // even x: corners (x, x+1) hash to entries e and e^1 -- one aligned 16-byte slot, one LDG.128 for both
+    if (F == 2 && POW2 && PAIR == 1) {
+      const bool even = !(ix & 1);
 #pragma unroll
       for (int c = 0; c < 8; c += 2) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(lvl) + (idx[c] >> 1));
-        const bool odd = idx[c] & 1;
-        v[c][0] = odd ? q.z : q.x;     v[c][F - 1] = odd ? q.w : q.y;
-        v[c + 1][0] = odd ? q.x : q.z; v[c + 1][F - 1] = odd ? q.y : q.w;
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(lvl) + (idx[c] >> 1));
+        float4 q1 = q0;
+        if (!even) q1 = __ldg(reinterpret_cast<const float4*>(lvl) + (idx[c + 1] >> 1));
+        const bool o0 = idx[c] & 1, o1 = idx[c + 1] & 1;
+        v[c][0] = o0 ? q0.z : q0.x;     v[c][F - 1] = o0 ? q0.w : q0.y;
+        v[c + 1][0] = o1 ? q1.z : q1.x; v[c + 1][F - 1] = o1 ? q1.w : q1.y;
       }
     } else {
 #pragma unroll
@@ -253,9 +260,10 @@ static int check_geom(const hbr_hash_geom* g) {
 template <int F, bool POW2, typename XT>
 static int launch_fwd(const void* x, int64_t n, const float* table, const HashGeom& g, float* y, int64_t ys, cudaStream_t st) {
   const size_t smem = (size_t)kTilePts * ((g.L * F) | 1) * sizeof(float);
-  HBR_CUDA(cudaFuncSetAttribute(hash_fwd_kernel<F, POW2, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  hash_fwd_kernel<F, POW2, XT><<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(
-      static_cast<const XT*>(x), n, table, y, ys, g);
+  const unsigned grid = (unsigned)ceil_div(n, kTilePts);
+  auto k = hash_fwd_kernel<F, POW2, XT>;
+  HBR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid, kHashThreads, smem, st>>>(static_cast<const XT*>(x), n, table, y, ys, g);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }

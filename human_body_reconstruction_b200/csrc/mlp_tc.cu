@@ -1212,308 +1212,6 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   if (warp == 0) tmem_dealloc<512>(tbase);
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// backward, three tiles in flight (the reference's widths: K0P = 32, KCP = 48).
-// The serial chain of one tile leaves the tensor pipe idle most of the time with two tile groups; a third group needs
-// the per-tile shared memory cut from 98 KB to 54 KB.  The tile therefore runs in two phases that share three 18 KB
-// regions (R3, R1, R2; each 8 column groups + a column group of 1.0):
-//   colour phase:  F0 x0[R2.4-7] -> h1[R1] | F1 -> h2[R3] | F2 -> o16 -> cin[R3] | F3 -> c1[R2] | F4 -> c2[R1], dz5[R3.5-6]
-//                  B5 (c2|1, dz5) -> dz4 in R1 | B4 (dz4, c1|1) -> dz3 in R2 | B3 (dz3, cin) -> dz2 kept in registers
-//   sigma phase:   x0 reloaded [R2.4-7] | F0' -> h1[R1] | F1' -> h2[R3], dz2[R2.0-1]
-//                  B2 (h2|1, dz2) -> dz1 in R3 | B1 (dz1, h1|1) -> dz0 in R1 | B0 (dz0, x0|1) -> d(features)
-// i.e. h1/h2 are recomputed a second time (6 extra MMAs of 89) instead of being kept across the colour phase.
-// Issue structure as in mlp_bwd_tc_kernel: warp A = recompute + dgrad chains, warp B = all weight-gradient chains.
-// ---------------------------------------------------------------------------------------------------------------
-struct Bwd3Smem {
-  static constexpr int G = 3;
-  static constexpr int off_bias = WOfs<32, 48>::total;
-  static constexpr int off_grp = off_bias + 6 * 64 * 4;
-  static constexpr int r3 = 0, r1 = 9 * kCg, r2 = 18 * kCg;            // R3's M = 128 operand reads on into R1, R1's into R2
-  static constexpr int grp_bytes = 27 * kCg;
-  static constexpr int off_bar = off_grp + G * grp_bytes;               // full[3], doneA[3], doneB[3], startB[3]
-  static constexpr int total = off_bar + 4 * G * 8 + 16;
-  static_assert(total <= 232448, "shared memory budget exceeded");
-  static_assert(G * grp_bytes >= 73728, "gradient image does not fit");
-};
-
-template <bool TRACE = false>
-__global__ void __launch_bounds__(3 * kTile + 128, 1)
-mlp_bwd3_tc_kernel(const float* __restrict__ feat, long long feat_stride, const float* __restrict__ dirs, long long dir_group,
-                   long long n, const float* __restrict__ params, int in0, int dv, const float* __restrict__ out,
-                   const float* __restrict__ dout, float* __restrict__ dfeat, long long dfeat_stride,
-                   float* __restrict__ ddirs, float* __restrict__ dparams, const uint8_t* __restrict__ image,
-                   float* __restrict__ grad_rows, long long* __restrict__ trace) {
-  constexpr int K0P = 32, KCP = 48, G = 3;
-  using SM = Bwd3Smem;
-  using WO = WOfs<K0P, KCP>;
-  using TM = BwdTmem<K0P, KCP, 192>;
-  static_assert(TM::g0 >= G * 64, "work accumulators overlap the gradient accumulators");
-  extern __shared__ __align__(128) uint8_t sm[];
-  const MlpLayout m = make_layout(in0, dv);
-  uint8_t* wsm = sm;
-  float* bias = reinterpret_cast<float*>(sm + SM::off_bias);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM::off_bar);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4 * G);
-  const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2000] = clock64();
-
-  if (warp == 0) tmem_alloc<512>(tslot);
-  if (threadIdx.x == 32) {
-    for (int g = 0; g < G; ++g) {
-      mbar_init(bars + g, kTile);
-      mbar_init(bars + G + g, 1);
-      mbar_init(bars + 2 * G + g, 1);
-      mbar_init(bars + 3 * G + g, 1);
-    }
-    fence_mbar_init();
-  }
-  if (image != nullptr) {
-    copy_image(wsm, image, WO::total);
-    copy_image(sm + SM::off_bias, image + Scratch<K0P, KCP>::off_bias_f32, 6 * 64 * 4);
-  } else {
-    stage_weights_bf16<K0P, KCP>(params, m, wsm, nullptr, nullptr, bias);
-  }
-  {
-    for (int e = threadIdx.x; e < G * SM::grp_bytes / 16; e += blockDim.x)
-      reinterpret_cast<uint4*>(sm + SM::off_grp)[e] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    const uint32_t one2 = pack_bf16(1.f, 1.f);
-    const uint4 ones4 = make_uint4(one2, one2, one2, one2);
-    for (int e = threadIdx.x; e < kTile; e += blockDim.x) {
-      for (int g = 0; g < G; ++g) {
-        uint8_t* gb = sm + SM::off_grp + g * SM::grp_bytes;
-        reinterpret_cast<uint4*>(gb + SM::r1 + 8 * kCg)[e] = ones4;
-        reinterpret_cast<uint4*>(gb + SM::r2 + 8 * kCg)[e] = ones4;
-        reinterpret_cast<uint4*>(gb + SM::r3 + 8 * kCg)[e] = ones4;
-      }
-    }
-  }
-  fence_async_smem();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tbase = *tslot;
-  if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2001] = clock64();
-  const long long ntiles = (n + kTile - 1) / kTile;
-  const long long nslots = (long long)gridDim.x * G;
-  long long nt[G];
-  long long cta_tiles = 0;
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-    nt[g] = tiles_of_slot(ntiles, (long long)g * gridDim.x + blockIdx.x, nslots);
-    cta_tiles += nt[g];
-  }
-  const long long kmax = nt[0];
-
-  if (warp >= 4 * G) {
-    // warps 4G .. 4G+2: issuer A of one tile group each (recompute + dgrad chains into that group's work accumulator,
-    // independent of the other groups); warp 4G+3: issuer B, every weight-gradient chain of the CTA in a fixed group order.
-    const int wi = warp - 4 * G;
-    const bool is_b = wi == G;
-    const uint32_t tb0 = __shfl_sync(kFull, tbase, 0);
-    const uint32_t sm0 = a4_of(sm);
-    uint32_t par[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) par[g] = 0;
-    bool first = true;
-#define HBR_BWD3_ISSUE(g, BWD, BODY)                                       \
-  {                                                                        \
-    mbar_wait(bars + (is_b ? 3 * G : 0) + (g), par[g]);                    \
-    par[g] ^= 1;                                                           \
-    fence_after_sync();                                                    \
-    if (elect_one()) {                                                     \
-      uint32_t sb = sm0, tb = tb0;                                         \
-      asm volatile("" : "+r"(sb), "+r"(tb));                               \
-      const uint32_t wa = sb;                                              \
-      const uint32_t d = tb + (g) * 64;                                    \
-      const uint32_t base = sb + (SM::off_grp + (g) * SM::grp_bytes) / 16; \
-      const uint32_t R1 = base + SM::r1 / 16, R2 = base + SM::r2 / 16, R3 = base + SM::r3 / 16; \
-      const uint32_t X0 = R2 + 4 * kCg / 16, DZ5 = R3 + 5 * kCg / 16, DZ2 = R2; \
-      (void)wa; (void)d; (void)R1; (void)R2; (void)R3; (void)X0; (void)DZ5; (void)DZ2; \
-      const bool acc = !(first && (g) == 0);                               \
-      (void)acc;                                                           \
-      BODY;                                                                \
-      commit(bars + (is_b ? 2 * G : G) + (g));                             \
-      if (!is_b && (BWD)) commit(bars + 3 * G + (g));                      \
-    }                                                                      \
-    __syncwarp();                                                          \
-  }
-#define HBR_BWD3_STAGE_B(BODY)                                             \
-  _Pragma("unroll") for (int g = 0; g < G; ++g) {                          \
-    if (k < nt[g]) HBR_BWD3_ISSUE(g, true, BODY)                           \
-  }
-    if (!is_b) {
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        if (g == wi) {
-          for (long long k = 0; k < nt[g]; ++k) {
-            // ---- colour phase ----
-            HBR_BWD3_ISSUE(g, false, issue_fwd(d, X0, wa + WO::w0 / 16, 64, K0P));       // F0: x0 -> h1
-            HBR_BWD3_ISSUE(g, false, issue_fwd(d, R1, wa + WO::w1 / 16, 64, 64));        // F1: h1 -> h2
-            HBR_BWD3_ISSUE(g, false, issue_fwd(d, R3, wa + WO::w2 / 16, 16, 64));        // F2: h2 -> o16
-            HBR_BWD3_ISSUE(g, false, issue_fwd(d, R3, wa + WO::w3 / 16, 64, KCP));       // F3: cin -> c1
-            HBR_BWD3_ISSUE(g, false, issue_fwd(d, R2, wa + WO::w4 / 16, 64, 64));        // F4: c1 -> c2
-            HBR_BWD3_ISSUE(g, true, issue_dgrad(d, DZ5, wa + WO::w5 / 16, 16, 64));      // col_model.4
-            HBR_BWD3_ISSUE(g, true, issue_dgrad(d, R1, wa + WO::w4 / 16, 64, 64));       // col_model.2 (dZ in R1)
-            HBR_BWD3_ISSUE(g, true, issue_dgrad(d, R2, wa + WO::w3 / 16, 64, KCP));      // col_model.0 (dZ in R2)
-            // ---- sigma phase ----
-            HBR_BWD3_ISSUE(g, false, issue_fwd(d, X0, wa + WO::w0 / 16, 64, K0P));       // F0'
-            HBR_BWD3_ISSUE(g, false, issue_fwd(d, R1, wa + WO::w1 / 16, 64, 64));        // F1'
-            HBR_BWD3_ISSUE(g, true, issue_dgrad(d, DZ2, wa + WO::w2 / 16, 16, 64));      // sig_model.4
-            HBR_BWD3_ISSUE(g, true, issue_dgrad(d, R3, wa + WO::w1 / 16, 64, 64));       // sig_model.2 (dZ in R3)
-            HBR_BWD3_ISSUE(g, true, issue_dgrad(d, R1, wa + WO::w0 / 16, 64, K0P));      // sig_model.0 (dZ in R1)
-          }
-        }
-      }
-    } else {
-      for (long long k = 0; k < kmax; ++k) {
-        HBR_BWD3_STAGE_B(issue_wgrad(tb + TM::g5, R1, DZ5, 16, acc, 128));    // transposed; input c2 | ones
-        HBR_BWD3_STAGE_B(issue_wgrad(tb + TM::g4, R1, R2, TM::n4, acc));      // dZ = R1, input c1 | ones
-        HBR_BWD3_STAGE_B(issue_wgrad(tb + TM::g3, R2, R3, TM::n3, acc));      // dZ = R2, input cin (planted 1.0)
-        HBR_BWD3_STAGE_B(issue_wgrad(tb + TM::g2, R3, DZ2, 16, acc, 128));    // transposed; input h2 | ones
-        HBR_BWD3_STAGE_B(issue_wgrad(tb + TM::g1, R3, R1, TM::n1, acc));      // dZ = R3, input h1 | ones
-        HBR_BWD3_STAGE_B(issue_wgrad(tb + TM::g0, R1, X0, TM::n0, acc));      // dZ = R1, input x0 | ones
-        first = false;
-      }
-    }
-  } else {
-    // ===== tile group =====
-    const int g = warp >> 2;
-    const int r = threadIdx.x & (kTile - 1);
-    uint8_t* gb = sm + SM::off_grp + g * SM::grp_bytes;
-    uint8_t *R1 = gb + SM::r1, *R2 = gb + SM::r2, *R3 = gb + SM::r3;
-    uint8_t *X0 = R2 + 4 * kCg, *DZ5 = R3 + 5 * kCg, *DZ2 = R2;
-    uint64_t* full = bars + g;
-    uint64_t* done = bars + G + g;
-    uint64_t* doneb = bars + 2 * G + g;
-    const uint32_t taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + g * 64;
-    uint32_t dphase = 0, bphase = 0;
-    const bool vec_ok = in0 == K0P && feat_stride == K0P && ((uintptr_t)feat & 15) == 0;
-    const bool dvec_ok = dfeat != nullptr && in0 == K0P && dfeat_stride == K0P && ((uintptr_t)dfeat & 15) == 0;
-    for (long long tile = (long long)g * gridDim.x + blockIdx.x; tile < ntiles; tile += nslots) {
-      const long long gp = tile * kTile + r;
-      const bool valid = gp < n;
-      const long long dir_row = valid ? gp / dir_group : 0;
-      if (valid && lane == 0) prefetch_l1(dirs + dir_row * dv);
-      float4 fo = make_float4(0.f, 0.f, 0.f, 0.f), go = fo;           // saved forward output, upstream gradient
-      if (valid) {
-        fo = __ldg(reinterpret_cast<const float4*>(out + gp * 4));
-        go = __ldg(reinterpret_cast<const float4*>(dout + gp * 4));
-      }
-      // ---------------- colour phase ----------------
-      load_features<K0P>(feat, feat_stride, tile * kTile, n, in0, vec_ok, r, X0);
-      if ((tile + nslots) * kTile + r < n) {
-        prefetch_l2(feat + ((tile + nslots) * kTile + r) * feat_stride);
-        if ((r & 7) == 0) {
-          prefetch_l2(out + ((tile + nslots) * kTile + r) * 4);
-          prefetch_l2(dout + ((tile + nslots) * kTile + r) * 4);
-        }
-      }
-      HBR_SIGNAL(); HBR_WAIT();                                         // F0
-      relu_bias_epilogue64(taddr, bias + 0, r, R1);
-      HBR_SIGNAL(); HBR_WAIT();                                         // F1
-      relu_bias_epilogue64(taddr, bias + 64, r, R3);
-      HBR_SIGNAL(); HBR_WAIT();                                         // F2
-      {
-        float o16[16];
-        tmem_ld<16>(taddr, o16);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) o16[k] += bias[128 + k];
-        build_cin<KCP, true>(o16, dirs, dir_row, dv, valid, r, R3);     // over h2 (its GEMM has completed)
-      }
-      HBR_SIGNAL(); HBR_WAIT();                                         // F3
-      relu_bias_epilogue64(taddr, bias + 192, r, R2);                   // c1 (over x0)
-      HBR_SIGNAL(); HBR_WAIT();                                         // F4
-      relu_bias_epilogue64(taddr, bias + 256, r, R1);                   // c2 (over h1)
-      {
-        float dz16[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) dz16[c] = 0.f;
-        dz16[0] = go.x * (fo.x > 0.f ? 1.f : fo.x + 1.f);               // ELU' from the saved output
-        dz16[1] = go.y * (fo.y > 0.f ? 1.f : fo.y + 1.f);
-        dz16[2] = go.z * (fo.z > 0.f ? 1.f : fo.z + 1.f);
-        store_chunk(DZ5, r, 0, kTile, dz16);                            // cin's padding column group + the next one
-        store_chunk(DZ5, r, 1, kTile, dz16 + 8);
-      }
-      HBR_SIGNAL(); HBR_WAIT();                                         // B5: work = dA(c2)
-      masked_dz_inplace64(taddr, r, R1, [&] { HBR_WAIT_B(); });
-      HBR_SIGNAL(); HBR_WAIT();                                         // B4: work = dA(c1)
-      masked_dz_inplace64(taddr, r, R2, [&] { HBR_WAIT_B(); });
-      HBR_SIGNAL(); HBR_WAIT();                                         // B3: work[0,48) = d(cin)
-      uint32_t dz2p[8];
-      {
-        float dc[KCP];
-        tmem_ld<KCP>(taddr, dc);
-        dz2p[0] = pack_bf16(go.w * (fo.w > 0.f ? 1.f : 0.01f), dc[0]); // LeakyReLU' from the saved density
-#pragma unroll
-        for (int q = 1; q < 8; ++q) dz2p[q] = pack_bf16(dc[2 * q - 1], dc[2 * q]);
-        if (ddirs != nullptr) {
-          const long long row0 = __shfl_sync(kFull, dir_row, 0);
-          const bool uniform = __all_sync(kFull, dir_row == row0 && valid);
-#pragma unroll
-          for (int k = kFeat; k < KCP; ++k) {
-            if (k < kFeat + dv) {
-              if (uniform) {
-                const float sdc = warp_sum(dc[k]);
-                if (lane == 0) atomicAdd(ddirs + row0 * dv + (k - kFeat), sdc);
-              } else if (valid) {
-                atomicAdd(ddirs + dir_row * dv + (k - kFeat), dc[k]);
-              }
-            }
-          }
-        }
-      }
-      HBR_WAIT_B();                                                     // col_model.0 weight gradient done: R2, R3 free
-      // ---------------- sigma phase ----------------
-      load_features<K0P>(feat, feat_stride, tile * kTile, n, in0, vec_ok, r, X0);
-      HBR_SIGNAL(); HBR_WAIT();                                         // F0'
-      relu_bias_epilogue64(taddr, bias + 0, r, R1);
-      HBR_SIGNAL(); HBR_WAIT();                                         // F1'
-      relu_bias_epilogue64(taddr, bias + 64, r, R3);
-      *reinterpret_cast<uint4*>(DZ2 + chunk_off(r, 0, kTile)) = make_uint4(dz2p[0], dz2p[1], dz2p[2], dz2p[3]);
-      *reinterpret_cast<uint4*>(DZ2 + chunk_off(r, 1, kTile)) = make_uint4(dz2p[4], dz2p[5], dz2p[6], dz2p[7]);
-      HBR_SIGNAL(); HBR_WAIT();                                         // B2: work = dA(h2)
-      masked_dz_inplace64(taddr, r, R3, [&] { HBR_WAIT_B(); });
-      HBR_SIGNAL(); HBR_WAIT();                                         // B1: work = dA(h1)
-      masked_dz_inplace64(taddr, r, R1, [&] { HBR_WAIT_B(); });
-      HBR_SIGNAL(); HBR_WAIT();                                         // B0: work[0,32) = d(feat)
-      if (dfeat != nullptr) {
-        float df[K0P];
-        tmem_ld<K0P>(taddr, df);
-        if (dvec_ok) {
-          constexpr int kQ = K0P / 4;
-          float4* stg = reinterpret_cast<float4*>(R3);                  // dz1: both of its GEMMs have completed
-#pragma unroll
-          for (int c = 0; c < kQ; ++c)
-            stg[r * kQ + (c ^ (r & 7))] = make_float4(df[4 * c], df[4 * c + 1], df[4 * c + 2], df[4 * c + 3]);
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-          float4* dst = reinterpret_cast<float4*>(dfeat + tile * kTile * K0P);
-#pragma unroll
-          for (int it = 0; it < kQ; ++it) {
-            const int idx = it * kTile + r, row = idx / kQ, c = idx % kQ;
-            if (tile * kTile + row < n) dst[idx] = stg[row * kQ + (c ^ (row & 7))];
-          }
-        } else if (valid) {
-#pragma unroll
-          for (int k = 0; k < K0P; ++k)
-            if (k < in0) dfeat[gp * dfeat_stride + k] = df[k];
-        }
-      }
-      HBR_WAIT_B();                                                     // sig_model.0 weight gradient done (R1, R2 reused next)
-    }
-  }
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2002] = clock64();
-  flush_gradients<K0P, KCP, 192>(tbase, warp, lane, m, reinterpret_cast<float*>(sm + SM::off_grp), cta_tiles > 0, dparams,
-                                 grad_rows);
-  fence_before_sync();
-  __syncthreads();
-  if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2003] = clock64();
-  if (warp == 0) tmem_dealloc<512>(tbase);
-}
-
 }  // namespace hbr
 
 using namespace hbr;
@@ -1548,11 +1246,12 @@ extern "C" int hbr_debug_umma_chain_bench(int kind, int reps, int nacc, long lon
 extern "C" int hbr_debug_mlp_trace_bwd(const float* feat, const float* dirs, int64_t dir_group, int64_t n,
                                        const float* params, const float* out, const float* dout, float* dfeat,
                                        float* dparams, long long* trace, void* stream) {
-  constexpr int smem = Bwd3Smem::total;
-  HBR_CUDA(cudaFuncSetAttribute(mlp_bwd3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int grid = (int)min64(ceil_div(ceil_div(n, kTile), 3), sm_count());
-  mlp_bwd3_tc_kernel<true><<<grid, 3 * kTile + 128, smem, as_stream(stream)>>>(
-      feat, 32, dirs, dir_group, n, params, 32, 24, out, dout, dfeat, 32, nullptr, dparams, nullptr, nullptr, trace);
+  constexpr int smem = BwdSmem<32, 48, 2>::total;
+  HBR_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<32, 48, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = (int)min64(ceil_div(ceil_div(n, kTile), 2), sm_count());
+  mlp_bwd_tc_kernel<32, 48, 2, true><<<grid, 2 * kTile + 64, smem, as_stream(stream)>>>(
+      feat, 32, dirs, dir_group, n, params, 32, 24, out, dout, dfeat, 32, nullptr, dparams, nullptr, nullptr, trace, EncArgs{},
+      HashGeom{});
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -1645,25 +1344,9 @@ extern "C" int hbr_mlp_bwd_tc(const float* feat, int64_t feat_stride, const floa
   HBR_REQUIRE(!dfeat || dfeat_stride >= dims->in0, "dfeat_stride too small");
   cudaStream_t st = as_stream(stream);
   uint8_t* sc = static_cast<uint8_t*>(scratch);
-  if (narrow_shape(dims)) {
-    using SC = Scratch<32, 48>;
-    constexpr int smem = Bwd3Smem::total;
-    const int in0 = dims->in0, dv = dims->d_view;
-    const int grid = (int)min64(ceil_div(ceil_div(n, kTile), 3), sm_count());
-    const bool rows = sc != nullptr && dparams != nullptr && grid <= SC::kMaxRows;
-    if (sc != nullptr) mlp_prep_kernel<32, 48><<<kPrepCtas, 256, 0, st>>>(params, in0, dv, sc);
-    HBR_CUDA(cudaFuncSetAttribute(mlp_bwd3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    mlp_bwd3_tc_kernel<false><<<grid, 3 * kTile + 128, smem, st>>>(
-        feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, dout, dfeat, dfeat_stride, ddirs, dparams, sc,
-        rows ? reinterpret_cast<float*>(sc + SC::off_grad) : nullptr, nullptr);
-    if (rows) {
-      const int total = make_layout(in0, dv).total;
-      mlp_grad_reduce_kernel<<<dim3((total + 255) / 256, kReduceSlices), 256, 0, st>>>(
-          reinterpret_cast<const float*>(sc + SC::off_grad), grid, SC::kRowFloats, total, dparams);
-    }
-    HBR_LAUNCH_CHECK();
-    return HBR_OK;
-  }
+  if (narrow_shape(dims))
+    return launch_bwd_tc<32, 48, 2, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out, dout,
+                                           dfeat, dfeat_stride, ddirs, dparams, sc, EncArgs{}, HashGeom{}, st);
   return launch_bwd_tc<64, 64, 1, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out, dout,
                                          dfeat, dfeat_stride, ddirs, dparams, sc, EncArgs{}, HashGeom{}, st);
 }

@@ -10,6 +10,6 @@ $CMD > gpurun_out/${TAG}_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 echo "launch list rc=$?"
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"hash_fwd_kernel|hash_bwd_kernel|mlp_fwd_tc_kernel|mlp_bwd_tc_kernel|composite_fwd_kernel|composite_bwd_kernel" -s 18 -c 6 -f -o gpurun_out/${TAG}_prof $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"hash_fwd_kernel|hash_bwd_kernel|mlp_fwd_tc_kernel|mlp_bwd|composite_fwd_kernel|composite_bwd_kernel" -s 18 -c 6 -f -o gpurun_out/${TAG}_prof $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out | tail -8
