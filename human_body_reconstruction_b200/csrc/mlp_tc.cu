@@ -134,6 +134,15 @@ __device__ __forceinline__ void issue_fwd(uint32_t tmem_d, uint32_t a4, uint32_t
     mma_f16(tmem_d, a, b, idesc, accumulate || kk > 0);
   }
 }
+// same GEMM with the A operand in tensor memory: K packed two bf16 per column, 8 columns per K = 16 step
+__device__ __forceinline__ void issue_fwd_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t w4, int JP, int KP, bool accumulate) {
+  const uint32_t idesc = make_idesc(128, JP, false, false);
+#pragma unroll
+  for (int kk = 0; kk < KP / 16; ++kk) {
+    const uint64_t b = desc64(w4 + kk * 2 * JP, JP * 16, 128);
+    mma_f16_ts(tmem_d, tmem_a + kk * 8, b, idesc, accumulate || kk > 0);
+  }
+}
 // D[128 x JP] = b (broadcast over rows) + A W^T: the bias enters as ones16 x biasB^T
 __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a4, uint32_t w4, uint32_t ones16_4,
                                             uint32_t bias4, int JP, int KP) {
@@ -360,6 +369,21 @@ __device__ __forceinline__ void load_features(const float* __restrict__ feat, lo
       store_chunk(x0, r, cg, kTile, v);
     }
   }
+}
+
+// ReLU on 64 accumulator columns (bias already inside) -> bf16 activations packed into 32 TMEM columns (the next
+// layer's A operand): no shared-memory round trip, no proxy fence
+__device__ __forceinline__ void relu_epilogue64_tmem(uint32_t taddr_acc, uint32_t taddr_a) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float v[32];
+    tmem_ld<32>(taddr_acc + half * 32, v);
+    uint32_t p[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) p[q] = pack_bf16_relu(v[2 * q], v[2 * q + 1]);
+    tmem_st16(taddr_a + half * 16, p);
+  }
+  tmem_st_wait();
 }
 
 // ReLU on 64 accumulator columns (bias already inside) -> bf16 activation tile
@@ -639,21 +663,64 @@ struct FwdSmem {
   static constexpr int off_bias = WOfs<K0P, KCP>::total;
   static constexpr int off_ones16 = off_bias + BOfs::total;
   static constexpr int off_buf = off_ones16 + kTile * 16 * 2;
-  static constexpr int buf_bytes = kTile * 64 * 2;
-  static constexpr int off_bar = off_buf + G * buf_bytes;
+  static constexpr int buf_bytes = kTile * 64 * 2;                      // bf16 feature tile (layer 0's A operand)
+  static constexpr int off_stage = off_buf + G * buf_bytes;             // fp32 staging of the NEXT tile's features (cp.async)
+  static constexpr int stage_bytes = K0P == 32 ? kTile * K0P * 4 : 0;   // the wide variant loads features directly
+  static constexpr int off_bar = off_stage + G * stage_bytes;
   static constexpr int total = off_bar + 2 * G * 8 + 16;
+  static_assert(total <= 232448, "shared memory budget exceeded");
 };
+
+// 16-byte asynchronous global -> shared copy; valid == false zero-fills the destination
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Feature pipeline of the forward kernel (contiguous fp32 rows of K0P floats): every thread copies the float4 elements
+// idx = it*128 + r of a tile into the staging buffer with cp.async while the previous tile runs its layer chain, and at
+// the start of the tile converts exactly the elements it copied itself (no cross-thread hazard) into the bf16 A tile.
+template <int K0P>
+__device__ __forceinline__ void stage_features_async(const float* __restrict__ feat, long long tile0, long long n, int r,
+                                                     uint8_t* stage) {
+  constexpr int kQ = K0P / 4;
+  const float4* src = reinterpret_cast<const float4*>(feat + tile0 * K0P);
+#pragma unroll
+  for (int it = 0; it < kQ; ++it) {
+    const int idx = it * kTile + r;
+    const bool ok = tile0 + idx / kQ < n;
+    cp_async16(stage + idx * 16, ok ? (const void*)(src + idx) : (const void*)feat, ok);
+  }
+  cp_async_commit();
+}
+template <int K0P>
+__device__ __forceinline__ void convert_staged_features(const uint8_t* stage, int r, uint8_t* x0) {
+  constexpr int kQ = K0P / 4;
+#pragma unroll
+  for (int it = 0; it < kQ; ++it) {
+    const int idx = it * kTile + r, row = idx / kQ, c4 = idx % kQ;
+    const float4 q = *reinterpret_cast<const float4*>(stage + idx * 16);
+    uint2 o;
+    o.x = pack_bf16(q.x, q.y);
+    o.y = pack_bf16(q.z, q.w);
+    *reinterpret_cast<uint2*>(x0 + chunk_off(row, c4 >> 1, kTile) + (c4 & 1) * 8) = o;
+  }
+}
 
 // TRACE: clock64 stamps of group 0 / its MMA warp in CTA 0 (debug entry point hbr_debug_mlp_trace; compiled out otherwise)
 template <int K0P, int KCP, int G, bool TRACE = false, bool ENC = false>
-__global__ void __launch_bounds__(G * (kTile + 32), 1)
+__global__ void __launch_bounds__(G * kTile, 1)
 mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const float* __restrict__ dirs, long long dir_group,
                   long long n, const float* __restrict__ params, int in0, int dv, float* __restrict__ out,
                   const uint8_t* __restrict__ image, long long* __restrict__ trace, const EncArgs enc,
                   const __grid_constant__ HashGeom geom) {
   using SM = FwdSmem<K0P, KCP, G>;
   using WO = WOfs<K0P, KCP>;
-  constexpr int kCols = G * 64 <= 64 ? 64 : (G * 64 <= 128 ? 128 : (G * 64 <= 256 ? 256 : 512));
+  // TMEM per tile group: 64 accumulator columns + 32 columns holding the current layer input (bf16 pairs)
+  constexpr int kGrpCols = 96;
+  constexpr int kCols = G * kGrpCols <= 128 ? 128 : (G * kGrpCols <= 256 ? 256 : 512);
+  static_assert(G * kGrpCols <= 512, "TMEM budget exceeded");
   extern __shared__ __align__(128) uint8_t sm[];
   const MlpLayout m = make_layout(in0, dv);
   uint8_t* wsm = sm;
@@ -663,7 +730,7 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
 
   if (warp == 0) tmem_alloc<kCols>(tslot);
   if (threadIdx.x == 32) {
-    for (int g = 0; g < G; ++g) { mbar_init(bars + g, kTile); mbar_init(bars + G + g, 1); }
+    for (int g = 0; g < G; ++g) mbar_init(bars + G + g, 1);             // done[g]: the group's MMAs have completed
     fence_mbar_init();
   }
   if (image != nullptr) copy_image(sm, image, SM::off_buf);             // [weights | bias tiles | ones16], same layout
@@ -676,55 +743,60 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   const long long ntiles = (n + kTile - 1) / kTile;
   const long long nslots = (long long)gridDim.x * G;
 
-  if (warp >= 4 * G) {
-    // ===== MMA issuer of group g: converged warp, straight-line layer sequence, one elected lane issues =====
-    const int g = warp - 4 * G;
-    const uint32_t tb = __shfl_sync(kFull, tbase, 0);
-    const uint32_t wa = a4_of(wsm), ba = a4_of(sm + SM::off_bias), o16a = a4_of(sm + SM::off_ones16);
-    const uint32_t d = tb + g * 64;
-    const uint32_t a = a4_of(sm + SM::off_buf + g * SM::buf_bytes);
-    uint64_t* full = bars + g;
-    uint64_t* done = bars + G + g;
-    uint32_t par = 0;
-    int tmi = 0;
-    (void)tmi;
-#define HBR_MMA_STAGE(BODY)                                                                             \
-  do {                                                                                                  \
-    mbar_wait(full, par);                                                                               \
-    par ^= 1;                                                                                           \
-    if (TRACE && g == 0 && blockIdx.x == 0 && lane == 0 && tmi < 500) trace[1024 + tmi++] = clock64();  \
-    fence_after_sync();                                                                                 \
-    if (elect_one()) {                                                                                  \
-      BODY;                                                                                             \
-      commit(done);                                                                                     \
-    }                                                                                                   \
-    __syncwarp();                                                                                       \
-    if (TRACE && g == 0 && blockIdx.x == 0 && lane == 0 && tmi < 500) trace[1024 + tmi++] = clock64();  \
-  } while (0)
-    for (long long tile = (long long)g * gridDim.x + blockIdx.x; tile < ntiles; tile += nslots) {
-      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w0 / 16, o16a, ba + BOfs::ofs(0) / 16, 64, K0P));
-      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w1 / 16, o16a, ba + BOfs::ofs(1) / 16, 64, 64));
-      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w2 / 16, o16a, ba + BOfs::ofs(2) / 16, 16, 64));
-      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w3 / 16, o16a, ba + BOfs::ofs(3) / 16, 64, KCP));
-      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w4 / 16, o16a, ba + BOfs::ofs(4) / 16, 64, 64));
-      HBR_MMA_STAGE(issue_layer(d, a, wa + WO::w5 / 16, o16a, ba + BOfs::ofs(5) / 16, 16, 64));
-    }
-  } else {
-    // ===== tile group =====
+  {
+    // ===== tile group g (warps 4g .. 4g+3): 128 threads = the 128 points of a tile; the group's first warp also issues
+    // the group's MMAs (no separate issuer warps: 512 threads keep 128 registers each, and the hand-off is one named
+    // barrier instead of an mbarrier round trip through another warp) =====
     const int g = warp >> 2;
     const int r = threadIdx.x & (kTile - 1);
+    const bool issuer = (warp & 3) == 0;
     uint8_t* buf = sm + SM::off_buf + g * SM::buf_bytes;
-    uint64_t* full = bars + g;
     uint64_t* done = bars + G + g;
-    const uint32_t taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + g * 64;
+    const uint32_t tgrp = tbase + g * kGrpCols;                          // D: [tgrp, tgrp+64), A: [tgrp+64, tgrp+96)
+    const uint32_t taddr = tgrp + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t taddr_a = taddr + 64;
+    const uint32_t wa = a4_of(wsm), ba = a4_of(sm + SM::off_bias), o16a = a4_of(sm + SM::off_ones16), xa = a4_of(buf);
     uint32_t dphase = 0;
     const bool vec_ok = in0 == K0P && feat_stride == K0P && ((uintptr_t)feat & 15) == 0;
-    int tgi = 0;
-    (void)tgi;
+    int tgi = 0, tmi = 0;
+    (void)tgi; (void)tmi;
+    uint8_t* stage = sm + SM::off_stage + g * SM::stage_bytes;
+    const bool staged = !ENC && vec_ok && SM::stage_bytes > 0;
+    if (staged && (long long)g * gridDim.x + blockIdx.x < ntiles)
+      stage_features_async<K0P>(feat, ((long long)g * gridDim.x + blockIdx.x) * kTile, n, r, stage);
 #define TR()                                                                                  \
   do {                                                                                        \
     if (TRACE && blockIdx.x == 0 && threadIdx.x == 0 && tgi < 1000) trace[tgi++] = clock64(); \
   } while (0)
+    // operands written (SMEM: shared-memory tile, needs the generic->async proxy fence; otherwise tensor memory only):
+    // group barrier, the first warp's elected lane issues the layer's MMAs and commits, everybody waits for completion
+#define HBR_LAYER(SMEM, BODY)                                                                           \
+  do {                                                                                                  \
+    TR();                                                                                               \
+    if (SMEM) fence_async_smem();                                                                       \
+    fence_before_sync();                                                                                \
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");                                          \
+    TR();                                                                                               \
+    if (issuer) {                                                                                       \
+      if (TRACE && g == 0 && blockIdx.x == 0 && lane == 0 && tmi < 500) trace[1024 + tmi++] = clock64(); \
+      fence_after_sync();                                                                               \
+      if (elect_one()) {                                                                                \
+        BODY;                                                                                           \
+        commit(done);                                                                                   \
+      }                                                                                                 \
+      __syncwarp();                                                                                     \
+      if (TRACE && g == 0 && blockIdx.x == 0 && lane == 0 && tmi < 500) trace[1024 + tmi++] = clock64(); \
+    }                                                                                                   \
+    mbar_wait(done, dphase);                                                                            \
+    dphase ^= 1;                                                                                        \
+    fence_after_sync();                                                                                 \
+    TR();                                                                                               \
+  } while (0)
+#define HBR_TS_LAYER(I, W, JP, KP)                                      \
+  HBR_LAYER(false, {                                                    \
+    issue_fwd(tgrp, o16a, ba + BOfs::ofs(I) / 16, JP, 16, false);       \
+    issue_fwd_ts(tgrp, tgrp + 64, wa + WO::W / 16, JP, KP, true);       \
+  })
     for (long long tile = (long long)g * gridDim.x + blockIdx.x; tile < ntiles; tile += nslots) {
       const long long gp = tile * kTile + r;
       const bool valid = gp < n;
@@ -733,24 +805,50 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       TR();
       if (ENC) {
         encode_row(enc, geom, gp, n, r, buf);
+      } else if (staged) {
+        cp_async_wait_all();
+        TR();
+        convert_staged_features<K0P>(stage, r, buf);
+        TR();
+        if (tile + nslots < ntiles) stage_features_async<K0P>(feat, (tile + nslots) * kTile, n, r, stage);
       } else {
         load_features<K0P>(feat, feat_stride, tile * kTile, n, in0, vec_ok, r, buf);
-        if ((tile + nslots) * kTile + r < n) prefetch_l2(feat + ((tile + nslots) * kTile + r) * feat_stride);
       }
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
-      relu_epilogue64(taddr, r, buf);
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
-      relu_epilogue64(taddr, r, buf);
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
+      // layer 0 reads the feature tile from shared memory; the later layers read their input from tensor memory
+      HBR_LAYER(true, issue_layer(tgrp, xa, wa + WO::w0 / 16, o16a, ba + BOfs::ofs(0) / 16, 64, K0P));
+      relu_epilogue64_tmem(taddr, taddr_a);
+      HBR_TS_LAYER(1, w1, 64, 64);
+      relu_epilogue64_tmem(taddr, taddr_a);
+      HBR_TS_LAYER(2, w2, 16, 64);
       float o16[16];
       tmem_ld<16>(taddr, o16);
       const float density = o16[0] > 0.f ? o16[0] : 0.01f * o16[0];     // LeakyReLU (test_hash.py:62)
-      build_cin<KCP, false>(o16, dirs, dir_row, dv, valid, r, buf);
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
-      relu_epilogue64(taddr, r, buf);
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
-      relu_epilogue64(taddr, r, buf);
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
+      {
+        // colour-net input [15 features | direction encoding | 0...] packed straight into tensor memory
+        uint32_t p[KCP / 2];
+#pragma unroll
+        for (int q = 0; q < KCP / 2; ++q) {
+          float e[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int k = 2 * q + j;
+            float x = 0.f;
+            if (k < kFeat) x = o16[1 + k];                              // feat_vec = dens_vec[:,1:]  (test_hash.py:64)
+            else if (k < kFeat + dv) x = valid ? __ldg(dirs + dir_row * dv + (k - kFeat)) : 0.f;   // concat(viewdirs) (:66)
+            e[j] = x;
+          }
+          p[q] = pack_bf16(e[0], e[1]);
+        }
+        tmem_st16(taddr_a, p);
+        if (KCP == 48) tmem_st8(taddr_a + 16, p + 16);
+        else tmem_st16(taddr_a + 16, p + 16);
+        tmem_st_wait();
+      }
+      HBR_TS_LAYER(3, w3, 64, KCP);
+      relu_epilogue64_tmem(taddr, taddr_a);
+      HBR_TS_LAYER(4, w4, 64, 64);
+      relu_epilogue64_tmem(taddr, taddr_a);
+      HBR_TS_LAYER(5, w5, 16, 64);
       float c16[16];
       tmem_ld<16>(taddr, c16);
       if (valid) {
@@ -762,6 +860,8 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         *reinterpret_cast<float4*>(out + gp * 4) = o;                   // (rgb, sigma), test_hash.py:69
       }
     }
+#undef HBR_TS_LAYER
+#undef HBR_LAYER
   }
   fence_before_sync();
   __syncthreads();
@@ -1261,7 +1361,7 @@ extern "C" int hbr_debug_mlp_trace(const float* feat, const float* dirs, int64_t
   constexpr int smem = FwdSmem<32, 48, 4>::total;
   HBR_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<32, 48, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), 4), sm_count());
-  mlp_fwd_tc_kernel<32, 48, 4, true><<<grid, 4 * (kTile + 32), smem, as_stream(stream)>>>(
+  mlp_fwd_tc_kernel<32, 48, 4, true><<<grid, 4 * kTile, smem, as_stream(stream)>>>(
       feat, 32, dirs, dir_group, n, params, 32, 24, out, nullptr, trace, EncArgs{}, HashGeom{});
   HBR_LAUNCH_CHECK();
   return HBR_OK;
@@ -1285,7 +1385,7 @@ static int launch_fwd_tc(const float* feat, int64_t feat_stride, const float* di
   if (scratch != nullptr) mlp_prep_kernel<K0P, KCP><<<kPrepCtas - 1, 256, 0, st>>>(params, in0, dv, scratch);
   auto kern = mlp_fwd_tc_kernel<K0P, KCP, G, false, ENC>;
   HBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, G * (kTile + 32), smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, scratch, nullptr, enc,
+  kern<<<grid, G * kTile, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, scratch, nullptr, enc,
                                              geom);
   HBR_LAUNCH_CHECK();
   return HBR_OK;

@@ -17,16 +17,18 @@ for it in range(3):
     _lib.check(L.hbr_debug_mlp_trace(_lib.ptr(feat), _lib.ptr(dirs), 128, n, _lib.ptr(flat), _lib.ptr(out), _lib.ptr(trace), _lib.stream()))
     torch.cuda.synchronize()
 t = trace.cpu().tolist()
-g = t[:1000]; m = t[1024:1524]
-t0 = g[0]
-print("group 0 of CTA 0: per tile 19 stamps: start, then (pre-signal, post-signal, post-wait) x6")
-i = 0; tile = 0
-while i + 19 <= 1000 and g[i] != 0 and tile < 4:
-    s = g[i:i + 19]
-    print(f"tile {tile}: start@{s[0]-t0}")
+g = [x for x in t[:1000] if x]
+# stamps per tile: start, wait_all, convert, then per layer (pre-barrier, post-barrier, post-wait) x 6  = 21
+NS = 21
+names = ["L0", "L1", "L2", "L3", "L4", "L5"]
+m = t[1024:1524]
+for tile in range(min(4, len(g) // NS)):
+    s = g[tile * NS:(tile + 1) * NS]
+    nxt = g[(tile + 1) * NS] - s[0] if len(g) > (tile + 1) * NS else 0
+    print(f"tile {tile}: total {nxt}  | features: wait_all {s[1]-s[0]} convert {s[2]-s[1]}")
+    prev = s[2]
     for k in range(6):
-        a, b, c = s[1 + 3 * k], s[2 + 3 * k], s[3 + 3 * k]
-        prev = s[0] if k == 0 else s[3 * k]
+        a, b, c = s[3 + 3 * k], s[4 + 3 * k], s[5 + 3 * k]
         mm = m[(tile * 6 + k) * 2:(tile * 6 + k) * 2 + 2]
-        print(f"   L{k}: work {a-prev:5d}  signal {b-a:4d}  wait {c-b:5d}   | mma saw ready +{mm[0]-b:5d} after signal, issue+commit {mm[1]-mm[0]:4d}, done seen +{c-mm[1]:5d} after commit")
-    i += 19; tile += 1
+        print(f"   {names[k]}: work {a-prev:5d}  barrier {b-a:4d}  issue {mm[1]-mm[0]:4d}  mma+wake {c-mm[1]:5d}   (stage total {c-prev})")
+        prev = c
