@@ -407,7 +407,8 @@ __device__ __forceinline__ void relu_epilogue64(uint32_t taddr, int r, uint8_t* 
 // formed in registers first; `before_store()` (wait for the weight-gradient GEMM still reading the tile) runs right
 // before the in-place store.
 template <typename F>
-__device__ __forceinline__ void masked_dz_inplace64(uint32_t taddr, int r, uint8_t* tile, F before_store) {
+__device__ __forceinline__ void masked_dz_inplace64(uint32_t taddr, int r, uint8_t* tile, F before_store,
+                                                    uint32_t taddr_a = 0xffffffffu) {
   uint4 o[8];
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
@@ -422,9 +423,14 @@ __device__ __forceinline__ void masked_dz_inplace64(uint32_t taddr, int r, uint8
       q.z = mask_pos_bf16x2(pack_bf16(p[4], p[5]), h.z); q.w = mask_pos_bf16x2(pack_bf16(p[6], p[7]), h.w);
     }
   }
+  if (taddr_a != 0xffffffffu) {                  // also the dgrad GEMM's A operand, in tensor memory
+    tmem_st16(taddr_a, reinterpret_cast<const uint32_t*>(o));
+    tmem_st16(taddr_a + 16, reinterpret_cast<const uint32_t*>(o) + 16);
+  }
   before_store();
 #pragma unroll
   for (int cg = 0; cg < 8; ++cg) *reinterpret_cast<uint4*>(tile + chunk_off(r, cg, kTile)) = o[cg];
+  if (taddr_a != 0xffffffffu) tmem_st_wait();
 }
 
 // colour-net input tile: [15 features | direction encoding | (optionally a 1.0 at column 15+dv) | 0 ...]
@@ -875,21 +881,46 @@ constexpr int kCg = kTile * 16;                                        // bytes 
 
 // bias + ReLU on 64 accumulator columns -> bf16 activation tile (the backward kernel adds the bias here: its two tile
 // groups leave the CUDA cores mostly idle, while every MMA saved shortens the issue-bound critical path)
-__device__ __forceinline__ void relu_bias_epilogue64(uint32_t taddr, const float* bias, int r, uint8_t* tile) {
+__device__ __forceinline__ void relu_bias_epilogue64(uint32_t taddr, const float* bias, int r, uint8_t* tile,
+                                                     uint32_t taddr_a) {
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     float v[32];
     tmem_ld<32>(taddr + half * 32, v);
+    uint4 o[4];
 #pragma unroll
     for (int cg = 0; cg < 4; ++cg) {
       const float4 b0 = *reinterpret_cast<const float4*>(bias + half * 32 + cg * 8);
       const float4 b1 = *reinterpret_cast<const float4*>(bias + half * 32 + cg * 8 + 4);
       const float* p = v + cg * 8;
-      uint4 o;
-      o.x = pack_bf16_relu(p[0] + b0.x, p[1] + b0.y); o.y = pack_bf16_relu(p[2] + b0.z, p[3] + b0.w);
-      o.z = pack_bf16_relu(p[4] + b1.x, p[5] + b1.y); o.w = pack_bf16_relu(p[6] + b1.z, p[7] + b1.w);
-      *reinterpret_cast<uint4*>(tile + chunk_off(r, half * 4 + cg, kTile)) = o;
+      o[cg].x = pack_bf16_relu(p[0] + b0.x, p[1] + b0.y); o[cg].y = pack_bf16_relu(p[2] + b0.z, p[3] + b0.w);
+      o[cg].z = pack_bf16_relu(p[4] + b1.x, p[5] + b1.y); o[cg].w = pack_bf16_relu(p[6] + b1.z, p[7] + b1.w);
+      *reinterpret_cast<uint4*>(tile + chunk_off(r, half * 4 + cg, kTile)) = o[cg];     // weight-gradient operand
     }
+    if (taddr_a != 0xffffffffu) tmem_st16(taddr_a + half * 16, reinterpret_cast<const uint32_t*>(o));   // next layer's A operand
+  }
+  if (taddr_a != 0xffffffffu) tmem_st_wait();
+}
+
+// 16-wide dZ (the two 16-output layers): bf16 into the shared-memory tile (weight-gradient operand) and into tensor
+// memory (A operand of the dgrad GEMM)
+__device__ __forceinline__ void store_dz16_both(const float* dz16, int r, uint8_t* dzs, uint32_t taddr_a) {
+  uint32_t p[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) p[q] = pack_bf16(dz16[2 * q], dz16[2 * q + 1]);
+  *reinterpret_cast<uint4*>(dzs + chunk_off(r, 0, kTile)) = make_uint4(p[0], p[1], p[2], p[3]);
+  *reinterpret_cast<uint4*>(dzs + chunk_off(r, 1, kTile)) = make_uint4(p[4], p[5], p[6], p[7]);
+  tmem_st8(taddr_a, p);
+  tmem_st_wait();
+}
+
+// dgrad with the dZ operand in tensor memory: D[128 x KP] = dZ[128 x JP] * W, B = weight tile [JP x KP] read MN-major
+__device__ __forceinline__ void issue_dgrad_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t w4, int JP, int KP) {
+  const uint32_t idesc = make_idesc(128, KP, false, true);
+#pragma unroll
+  for (int kk = 0; kk < JP / 16; ++kk) {
+    const uint64_t b = desc64(w4 + kk * 16, 128, JP * 16);
+    mma_f16_ts(tmem_d, tmem_a + kk * 8, b, idesc, kk > 0);
   }
 }
 
@@ -1017,7 +1048,10 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
                   const __grid_constant__ HashGeom geom) {
   using SM = BwdSmem<K0P, KCP, G>;
   using WO = WOfs<K0P, KCP>;
-  using TM = BwdTmem<K0P, KCP>;
+  // TMEM per tile group: 64 work-accumulator columns + 32 columns holding the A operand (bf16 pairs) of the group's next
+  // forward / dgrad GEMM; the gradient accumulators start behind the groups
+  constexpr int kGrpCols = 96;
+  using TM = BwdTmem<K0P, KCP, 2 * kGrpCols>;
   constexpr bool kCinOne = TM::kCinOne;
   static_assert(G >= 1 && G <= 2, "two work accumulators");
   extern __shared__ __align__(128) uint8_t sm[];
@@ -1111,7 +1145,8 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
           uint32_t sb = sm0, tb = tb0;                                     \
           asm volatile("" : "+r"(sb), "+r"(tb));                           \
           const uint32_t wa = sb;                                          \
-          const uint32_t d = tb + g * 64;                                  \
+          const uint32_t d = tb + g * kGrpCols, ta = d + 64;               \
+          (void)ta;                                                        \
           const uint32_t base = sb + (SM::off_grp + g * SM::grp_bytes) / 16; \
           const uint32_t x0a = base + SM::x0 / 16, h1a = base + SM::h1 / 16, h2a = base + SM::h2 / 16, \
                          cina = base + SM::cin / 16, c1a = base + SM::c1 / 16, c2a = base + SM::c2 / 16, \
@@ -1132,17 +1167,18 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       for (long long k = 0; k < kmax; ++k) {
         // ---- forward recompute (layers 0..4; bias and activation in the epilogue) ----
         HBR_BWD_STAGE(false, issue_fwd(d, x0a, wa + WO::w0 / 16, 64, K0P));
-        HBR_BWD_STAGE(false, issue_fwd(d, h1a, wa + WO::w1 / 16, 64, 64));
-        HBR_BWD_STAGE(false, issue_fwd(d, h2a, wa + WO::w2 / 16, 16, 64));
-        HBR_BWD_STAGE(false, issue_fwd(d, cina, wa + WO::w3 / 16, 64, KCP));
-        HBR_BWD_STAGE(false, issue_fwd(d, c1a, wa + WO::w4 / 16, 64, 64));
+        // (layer 0 reads x0 from shared memory; every later A operand sits in tensor memory)
+        HBR_BWD_STAGE(false, issue_fwd_ts(d, ta, wa + WO::w1 / 16, 64, 64, false));
+        HBR_BWD_STAGE(false, issue_fwd_ts(d, ta, wa + WO::w2 / 16, 16, 64, false));
+        HBR_BWD_STAGE(false, issue_fwd_ts(d, ta, wa + WO::w3 / 16, 64, KCP, false));
+        HBR_BWD_STAGE(false, issue_fwd_ts(d, ta, wa + WO::w4 / 16, 64, 64, false));
         // ---- dgrad: dA = dZ W ----
-        HBR_BWD_STAGE(true, issue_dgrad(d, dzsa, wa + WO::w5 / 16, 16, 64));      // col_model.4
-        HBR_BWD_STAGE(true, issue_dgrad(d, c2a, wa + WO::w4 / 16, 64, 64));       // col_model.2 (dZ in the c2 tile)
-        HBR_BWD_STAGE(true, issue_dgrad(d, c1a, wa + WO::w3 / 16, 64, KCP));      // col_model.0 (dZ in the c1 tile)
-        HBR_BWD_STAGE(true, issue_dgrad(d, dzsa, wa + WO::w2 / 16, 16, 64));      // sig_model.4
-        HBR_BWD_STAGE(true, issue_dgrad(d, h2a, wa + WO::w1 / 16, 64, 64));       // sig_model.2 (dZ in the h2 tile)
-        HBR_BWD_STAGE(true, issue_dgrad(d, h1a, wa + WO::w0 / 16, 64, K0P));      // sig_model.0 (dZ in the h1 tile)
+        HBR_BWD_STAGE(true, issue_dgrad_ts(d, ta, wa + WO::w5 / 16, 16, 64));     // col_model.4
+        HBR_BWD_STAGE(true, issue_dgrad_ts(d, ta, wa + WO::w4 / 16, 64, 64));     // col_model.2
+        HBR_BWD_STAGE(true, issue_dgrad_ts(d, ta, wa + WO::w3 / 16, 64, KCP));    // col_model.0
+        HBR_BWD_STAGE(true, issue_dgrad_ts(d, ta, wa + WO::w2 / 16, 16, 64));     // sig_model.4
+        HBR_BWD_STAGE(true, issue_dgrad_ts(d, ta, wa + WO::w1 / 16, 64, 64));     // sig_model.2
+        HBR_BWD_STAGE(true, issue_dgrad_ts(d, ta, wa + WO::w0 / 16, 64, K0P));    // sig_model.0
       }
     } else {
       for (long long k = 0; k < kmax; ++k) {
@@ -1166,7 +1202,8 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     uint64_t* full = bars + g;
     uint64_t* done = bars + G + g;
     uint64_t* doneb = bars + 2 * G + g;
-    const uint32_t taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + g * 64;
+    const uint32_t taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + g * kGrpCols;
+    const uint32_t taddr_a = taddr + 64;
     uint32_t dphase = 0, bphase = 0;
     // weight-gradient GEMM of the stage has finished reading its tiles (they are about to be overwritten in place)
 #define HBR_WAIT_B()           \
@@ -1206,9 +1243,9 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         }
       }
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
-      relu_bias_epilogue64(taddr, bias + 0, r, h1);
+      relu_bias_epilogue64(taddr, bias + 0, r, h1, taddr_a);
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
-      relu_bias_epilogue64(taddr, bias + 64, r, h2);
+      relu_bias_epilogue64(taddr, bias + 64, r, h2, taddr_a);
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
       {
         float o16[16];
@@ -1216,11 +1253,22 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
 #pragma unroll
         for (int k = 0; k < 16; ++k) o16[k] += bias[128 + k];
         build_cin<KCP, kCinOne>(o16, dirs, dir_row, dv, valid, r, cin);
+        // the same row as the A operand of the colour net's first GEMM: copy this thread's chunks smem -> TMEM
+        uint32_t p[KCP / 2];
+#pragma unroll
+        for (int cg = 0; cg < KCP / 8; ++cg) {
+          const uint4 q = *reinterpret_cast<const uint4*>(cin + chunk_off(r, cg, kTile));
+          p[4 * cg] = q.x; p[4 * cg + 1] = q.y; p[4 * cg + 2] = q.z; p[4 * cg + 3] = q.w;
+        }
+        tmem_st16(taddr_a, p);
+        if (KCP == 48) tmem_st8(taddr_a + 16, p + 16);
+        else tmem_st16(taddr_a + 16, p + 16);
+        tmem_st_wait();
       }
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
-      relu_bias_epilogue64(taddr, bias + 192, r, c1);
+      relu_bias_epilogue64(taddr, bias + 192, r, c1, taddr_a);
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
-      relu_bias_epilogue64(taddr, bias + 256, r, c2);
+      relu_bias_epilogue64(taddr, bias + 256, r, c2, 0xffffffffu);
       {
         // d(rgb_pre) = g * ELU'(pre), with ELU'(pre) = pre > 0 ? 1 : exp(pre) = elu(pre) + 1 from the saved output
         float dz16[16];
@@ -1229,13 +1277,12 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         dz16[0] = go.x * (fo.x > 0.f ? 1.f : fo.x + 1.f);
         dz16[1] = go.y * (fo.y > 0.f ? 1.f : fo.y + 1.f);
         dz16[2] = go.z * (fo.z > 0.f ? 1.f : fo.z + 1.f);
-        store_chunk(dzs, r, 0, kTile, dz16);
-        store_chunk(dzs, r, 1, kTile, dz16 + 8);
+        store_dz16_both(dz16, r, dzs, taddr_a);
       }
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // col_model.4 backward: work = dA(c2)
-      masked_dz_inplace64(taddr, r, c2, [&] { HBR_WAIT_B(); });
+      masked_dz_inplace64(taddr, r, c2, [&] { HBR_WAIT_B(); }, taddr_a);
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // col_model.2: work = dA(c1)
-      masked_dz_inplace64(taddr, r, c1, [&] { HBR_WAIT_B(); });
+      masked_dz_inplace64(taddr, r, c1, [&] { HBR_WAIT_B(); }, taddr_a);
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // col_model.0: work[0,KCP) = d(cin)
       HBR_WAIT_B();
       {
@@ -1244,8 +1291,7 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         dz16[0] = go.w * (fo.w > 0.f ? 1.f : 0.01f);                    // LeakyReLU' from the saved density
 #pragma unroll
         for (int k = 0; k < kFeat; ++k) dz16[1 + k] = dc[k];
-        store_chunk(dzs, r, 0, kTile, dz16);
-        store_chunk(dzs, r, 1, kTile, dz16 + 8);
+        store_dz16_both(dz16, r, dzs, taddr_a);
         if (ddirs != nullptr) {
           // rows of one warp usually belong to one ray: reduce over the warp first, one atomic per column
           const long long row0 = __shfl_sync(kFull, dir_row, 0);
@@ -1264,9 +1310,9 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         }
       }
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // sig_model.4: work = dA(h2)
-      masked_dz_inplace64(taddr, r, h2, [&] { HBR_WAIT_B(); });
+      masked_dz_inplace64(taddr, r, h2, [&] { HBR_WAIT_B(); }, taddr_a);
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // sig_model.2: work = dA(h1)
-      masked_dz_inplace64(taddr, r, h1, [&] { HBR_WAIT_B(); });
+      masked_dz_inplace64(taddr, r, h1, [&] { HBR_WAIT_B(); }, taddr_a);
       TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // sig_model.0: work[0,K0P) = d(feat)
       if (ENC) {
         float df[K0P];
@@ -1304,7 +1350,7 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   fence_after_sync();
   if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2002] = clock64();
 
-  flush_gradients<K0P, KCP, 128>(tbase, warp, lane, m, reinterpret_cast<float*>(sm + SM::off_grp), cta_tiles > 0, dparams,
+  flush_gradients<K0P, KCP, 2 * kGrpCols>(tbase, warp, lane, m, reinterpret_cast<float*>(sm + SM::off_grp), cta_tiles > 0, dparams,
                             grad_rows);
   fence_before_sync();
   __syncthreads();
