@@ -109,6 +109,8 @@ SIGNATURES = {
     "hbr_mlp_bwd_tc": ([_vp, _i64, _vp, _i64, _i64, _vp, _dims_p, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp], C.c_int),
     "hbr_field_fwd_tc": ([_vp, _i64, _vp, _geom_p, _vp, _i64, _vp, _dims_p, _vp, _vp, _vp, _vp], C.c_int),
     "hbr_field_bwd_tc": ([_vp, _i64, _geom_p, _vp, _i64, _vp, _dims_p, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "hbr_adam_step": ([_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i32, _i64,
+                       C.c_double, _vp, _vp], C.c_int),
     "hbr_debug_umma": ([_i32, _vp, _vp, _vp, _i32, _i32, _vp], C.c_int),
     "hbr_debug_umma_bench": ([_i32, _i32, _i32, _i32, _i32, _vp, _vp], C.c_int),
     "hbr_debug_umma_chain_bench": ([_i32, _i32, _i32, _vp, _vp], C.c_int),
@@ -131,7 +133,7 @@ SIGNATURES = {
 # kernels launched by one call of each entry point (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
     "hbr_hash_encode_fwd": 1, "hbr_hash_encode_bwd": 1, "hbr_hash_indices": 1, "hbr_dir_encode": 1,
-    "hbr_mlp_fwd_f32": 1, "hbr_mlp_bwd_f32": 2, "hbr_mlp_fwd_tc": 2, "hbr_mlp_bwd_tc": 3, "hbr_field_fwd_tc": 2, "hbr_field_bwd_tc": 3, "hbr_debug_umma": 1, "hbr_debug_mlp_trace": 1, "hbr_debug_umma_chain_bench": 1, "hbr_debug_umma_bench": 1, "hbr_debug_mlp_trace_bwd": 1, "hbr_ray_points": 1, "hbr_occupancy_mask": 1,
+    "hbr_mlp_fwd_f32": 1, "hbr_mlp_bwd_f32": 2, "hbr_mlp_fwd_tc": 2, "hbr_mlp_bwd_tc": 3, "hbr_field_fwd_tc": 2, "hbr_field_bwd_tc": 3, "hbr_debug_umma": 1, "hbr_adam_step": 1, "hbr_debug_mlp_trace": 1, "hbr_debug_umma_chain_bench": 1, "hbr_debug_umma_bench": 1, "hbr_debug_mlp_trace_bwd": 1, "hbr_ray_points": 1, "hbr_occupancy_mask": 1,
     "hbr_composite_fwd": 1, "hbr_composite_bwd": 1, "hbr_hier_sample": 1, "hbr_grid_points": 1,
     "hbr_grid_density": 3, "hbr_mc_count": 1, "hbr_mc_emit": 2,
 }

@@ -212,6 +212,14 @@ int hbr_mc_emit(const float* density, int n0, int n1, int n2, float iso, int i_b
                 int32_t* edge_id, float* verts, int64_t max_verts, int32_t* faces, int64_t max_faces,
                 unsigned long long* cursors, void* stream);
 
+/* ---- 8f row 1: the optimiser step of train_hash2.py:141-142,227-228 (torch.optim.Adam / AdamW) as ONE pass --------
+ * param / grad / exp_avg / exp_avg_sq: n fp32 each (the flat table or MLP buffer).  step >= 1 is the 1-based step count.
+ * grad is multiplied by inv_scale (GradScaler unscale, 1.0 without AMP); with found_inf != NULL and *found_inf != 0 the
+ * step is skipped (GradScaler's inf check).  decoupled_weight_decay != 0 = AdamW. */
+int hbr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, int decoupled_weight_decay, int64_t step,
+                  double inv_scale, const float* found_inf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

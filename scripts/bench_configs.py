@@ -59,4 +59,28 @@ ms5, _ = ev_time(lambda: gs(), reps=5)
 pts = R * 768
 out["human_config_step"] = {"rays": R, "points_per_ray": 768, "T": 2 ** 22, "ms_per_step": ms5, "rays_per_s": R / ms5 * 1e3,
                             "step_algorithmic_GBps": 2792 * pts / ms5 / 1e6, "launch": "cuda graph replay, L2 warm"}
+# ---- 8f row 1: optimiser step over the 16 x 2^19 x 2 table + the MLP (train_hash2.py:141-142,227-228) ----
+del gs, enc, mlp, vr
+torch.cuda.empty_cache()
+enc, mlp = build(2 ** 19, 1e4)
+for p in list(enc.parameters()) + list(mlp.parameters()):
+    p.grad = torch.randn_like(p) * 1e-3
+# gradients as this package's backward delivers them: views of one flat buffer
+gflat = torch.randn(16, 2 ** 19, 2, device=dev) * 1e-3
+for i, e in enumerate(enc.Embedding_list):
+    e.weight.grad = gflat[i]
+def timed_opt(make):
+    o1, o2 = make()
+    def stepf():
+        o1.step(); o2.step()
+    return ev_time(stepf, reps=5)[0]
+n_par = sum(p.numel() for p in enc.parameters()) + sum(p.numel() for p in mlp.parameters())
+res = {}
+res["torch_adam_default_ms"] = timed_opt(lambda: (torch.optim.Adam(enc.Embedding_list.parameters(), lr=.05), torch.optim.AdamW(mlp.parameters(), lr=.005)))
+res["torch_adam_fused_ms"] = timed_opt(lambda: (torch.optim.Adam(enc.Embedding_list.parameters(), lr=.05, fused=True), torch.optim.AdamW(mlp.parameters(), lr=.005, fused=True)))
+res["hbr_fused_adam_ms"] = timed_opt(lambda: (h.optim.FusedAdam(enc.Embedding_list.parameters(), lr=.05), h.optim.FusedAdamW(mlp.parameters(), lr=.005)))
+res["params"] = n_par
+res["hbr_GBps"] = 28 * n_par / res["hbr_fused_adam_ms"] / 1e6
+res["roofline_frac"] = res["hbr_GBps"] / 6544.7
+out["optimizer_step"] = res
 print(json.dumps(out))
