@@ -1039,7 +1039,7 @@ __device__ __forceinline__ void flush_gradients(uint32_t tbase, int warp, int la
 }
 
 template <int K0P, int KCP, int G, bool TRACE = false, bool ENC = false>
-__global__ void __launch_bounds__(G * kTile + 64, 1)
+__global__ void __launch_bounds__(G * kTile + 32, 1)
 mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const float* __restrict__ dirs, long long dir_group,
                   long long n, const float* __restrict__ params, int in0, int dv, const float* __restrict__ out,
                   const float* __restrict__ dout, float* __restrict__ dfeat, long long dfeat_stride,
@@ -1065,8 +1065,7 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
 
   if (warp == 0) tmem_alloc<512>(tslot);
   if (threadIdx.x == 32) {
-    for (int g = 0; g < G; ++g) {
-      mbar_init(bars + g, kTile);
+    for (int g = 0; g < G; ++g) {                                       // done[g], doneB[g], startB[g] (slot 0 unused)
       mbar_init(bars + G + g, 1);
       mbar_init(bars + 2 * G + g, 1);
       mbar_init(bars + 3 * G + g, 1);
@@ -1115,82 +1114,49 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   const long long kmax = nt[0];                  // the slot of group 0 never has fewer tiles than a later group's
 
   if (warp >= 4 * G) {
-    // ===== two MMA-issuing warps, both converged, both visiting the groups in the same fixed order:
-    //   warp A: waits on full[g]; forward recompute + dgrad GEMMs (work accumulators), commits to doneA[g] and, on the
-    //           backward stages, to startB[g];
-    //   warp B: waits on startB[g] (the chain-critical dgrad of a stage is complete, so it never queues behind a weight
-    //           gradient in the in-order tensor pipe); every weight/bias-gradient GEMM of the CTA (the accumulators all
-    //           tiles share), commits to doneB[g].  startB advances only on backward stages and the group cannot pass
-    //           one without doneB, so B's phase tracking cannot fall behind.
+    // ===== weight-gradient issuer (one converged warp): every weight/bias-gradient GEMM of the CTA -- the accumulators
+    // all tiles share -- comes from this one thread sequence, visiting the groups in a fixed order.  It waits on
+    // startB[g], committed by the group right behind the stage's dgrad (so the chain-critical dgrad never queues behind a
+    // weight gradient in the in-order tensor pipe), and commits to doneB[g].  startB advances only on backward stages and
+    // a group cannot pass one without doneB, so the phase tracking cannot fall behind.
     // The operand descriptors are rebuilt from two laundered base values in every stage: left to itself the compiler
     // hoists the loop-invariant descriptors out of the tile loop and spills them. =====
-    const bool is_b = warp == 4 * G + 1;
     const uint32_t tb0 = __shfl_sync(kFull, tbase, 0);
     const uint32_t sm0 = a4_of(sm);
     uint32_t par[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) par[g] = 0;
     bool first = true;                           // gradient accumulators not yet written
-    int tmi = 0;
-    (void)tmi;
-#define HBR_BWD_STAGE(BWD, BODY)                                         \
+#define HBR_WGRAD_STAGE(BODY)                                              \
   _Pragma("unroll") for (int g = 0; g < G; ++g) {                          \
     if (k < nt[g]) {                                                       \
-      mbar_wait(bars + (is_b ? 3 * G : 0) + g, par[g]);                    \
+      mbar_wait(bars + 3 * G + g, par[g]);                                 \
       par[g] ^= 1;                                                         \
-      {                                                                    \
-        if (TRACE && !is_b && g == 0 && blockIdx.x == 0 && lane == 0 && tmi < 500) trace[1024 + tmi++] = clock64(); \
-        fence_after_sync();                                                \
-        if (elect_one()) {                                                 \
-          uint32_t sb = sm0, tb = tb0;                                     \
-          asm volatile("" : "+r"(sb), "+r"(tb));                           \
-          const uint32_t wa = sb;                                          \
-          const uint32_t d = tb + g * kGrpCols, ta = d + 64;               \
-          (void)ta;                                                        \
-          const uint32_t base = sb + (SM::off_grp + g * SM::grp_bytes) / 16; \
-          const uint32_t x0a = base + SM::x0 / 16, h1a = base + SM::h1 / 16, h2a = base + SM::h2 / 16, \
-                         cina = base + SM::cin / 16, c1a = base + SM::c1 / 16, c2a = base + SM::c2 / 16, \
-                         dzsa = base + SM::dzs / 16;                       \
-          (void)wa; (void)d; (void)x0a; (void)h1a; (void)h2a; (void)cina; (void)c1a; (void)c2a; (void)dzsa; \
-          const bool acc = !(first && g == 0);                             \
-          (void)acc;                                                       \
-          BODY;                                                            \
-          commit(bars + (is_b ? 2 * G : G) + g);                           \
-          if (!is_b && (BWD)) commit(bars + 3 * G + g);                    \
-        }                                                                  \
-        __syncwarp();                                                      \
-        if (TRACE && !is_b && g == 0 && blockIdx.x == 0 && lane == 0 && tmi < 500) trace[1024 + tmi++] = clock64(); \
+      fence_after_sync();                                                  \
+      if (elect_one()) {                                                   \
+        uint32_t sb = sm0, tb = tb0;                                       \
+        asm volatile("" : "+r"(sb), "+r"(tb));                             \
+        const uint32_t base = sb + (SM::off_grp + g * SM::grp_bytes) / 16; \
+        const uint32_t x0a = base + SM::x0 / 16, h1a = base + SM::h1 / 16, h2a = base + SM::h2 / 16, \
+                       cina = base + SM::cin / 16, c1a = base + SM::c1 / 16, c2a = base + SM::c2 / 16, \
+                       dzsa = base + SM::dzs / 16;                         \
+        (void)x0a; (void)h1a; (void)h2a; (void)cina; (void)c1a; (void)c2a; (void)dzsa; \
+        const bool acc = !(first && g == 0);                               \
+        BODY;                                                              \
+        commit(bars + 2 * G + g);                                          \
       }                                                                    \
+      __syncwarp();                                                        \
     }                                                                      \
   }
-    if (!is_b) {
-      for (long long k = 0; k < kmax; ++k) {
-        // ---- forward recompute (layers 0..4; bias and activation in the epilogue) ----
-        HBR_BWD_STAGE(false, issue_fwd(d, x0a, wa + WO::w0 / 16, 64, K0P));
-        // (layer 0 reads x0 from shared memory; every later A operand sits in tensor memory)
-        HBR_BWD_STAGE(false, issue_fwd_ts(d, ta, wa + WO::w1 / 16, 64, 64, false));
-        HBR_BWD_STAGE(false, issue_fwd_ts(d, ta, wa + WO::w2 / 16, 16, 64, false));
-        HBR_BWD_STAGE(false, issue_fwd_ts(d, ta, wa + WO::w3 / 16, 64, KCP, false));
-        HBR_BWD_STAGE(false, issue_fwd_ts(d, ta, wa + WO::w4 / 16, 64, 64, false));
-        // ---- dgrad: dA = dZ W ----
-        HBR_BWD_STAGE(true, issue_dgrad_ts(d, ta, wa + WO::w5 / 16, 16, 64));     // col_model.4
-        HBR_BWD_STAGE(true, issue_dgrad_ts(d, ta, wa + WO::w4 / 16, 64, 64));     // col_model.2
-        HBR_BWD_STAGE(true, issue_dgrad_ts(d, ta, wa + WO::w3 / 16, 64, KCP));    // col_model.0
-        HBR_BWD_STAGE(true, issue_dgrad_ts(d, ta, wa + WO::w2 / 16, 16, 64));     // sig_model.4
-        HBR_BWD_STAGE(true, issue_dgrad_ts(d, ta, wa + WO::w1 / 16, 64, 64));     // sig_model.2
-        HBR_BWD_STAGE(true, issue_dgrad_ts(d, ta, wa + WO::w0 / 16, 64, K0P));    // sig_model.0
-      }
-    } else {
-      for (long long k = 0; k < kmax; ++k) {
-        // ---- weight + bias gradients: reduction over the tile's 128 points ----
-        HBR_BWD_STAGE(true, issue_wgrad(tb + TM::g5, c2a, dzsa, 16, acc, 128));   // transposed; input c2 | ones
-        HBR_BWD_STAGE(true, issue_wgrad(tb + TM::g4, c2a, c1a, TM::n4, acc));     // dZ = c2 tile, input c1 | ones
-        HBR_BWD_STAGE(true, issue_wgrad(tb + TM::g3, c1a, cina, TM::n3, acc));    // dZ = c1 tile, input cin (planted 1.0)
-        HBR_BWD_STAGE(true, issue_wgrad(tb + TM::g2, h2a, dzsa, 16, acc, 128));   // transposed; input h2 | ones
-        HBR_BWD_STAGE(true, issue_wgrad(tb + TM::g1, h2a, h1a, TM::n1, acc));     // dZ = h2 tile, input h1 | ones
-        HBR_BWD_STAGE(true, issue_wgrad(tb + TM::g0, h1a, x0a, TM::n0, acc));     // dZ = h1 tile, input x0 | ones
-        first = false;
-      }
+    for (long long k = 0; k < kmax; ++k) {
+      // ---- weight + bias gradients: reduction over the tile's 128 points ----
+      HBR_WGRAD_STAGE(issue_wgrad(tb + TM::g5, c2a, dzsa, 16, acc, 128));   // transposed; input c2 | ones
+      HBR_WGRAD_STAGE(issue_wgrad(tb + TM::g4, c2a, c1a, TM::n4, acc));     // dZ = c2 tile, input c1 | ones
+      HBR_WGRAD_STAGE(issue_wgrad(tb + TM::g3, c1a, cina, TM::n3, acc));    // dZ = c1 tile, input cin (planted 1.0)
+      HBR_WGRAD_STAGE(issue_wgrad(tb + TM::g2, h2a, dzsa, 16, acc, 128));   // transposed; input h2 | ones
+      HBR_WGRAD_STAGE(issue_wgrad(tb + TM::g1, h2a, h1a, TM::n1, acc));     // dZ = h2 tile, input h1 | ones
+      HBR_WGRAD_STAGE(issue_wgrad(tb + TM::g0, h1a, x0a, TM::n0, acc));     // dZ = h1 tile, input x0 | ones
+      first = false;
     }
   } else {
     // ===== tile group =====
@@ -1199,12 +1165,35 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     uint8_t* gb = sm + SM::off_grp + g * SM::grp_bytes;
     uint8_t *x0 = gb + SM::x0, *h1 = gb + SM::h1, *h2 = gb + SM::h2, *cin = gb + SM::cin, *c1 = gb + SM::c1,
             *c2 = gb + SM::c2, *dzs = gb + SM::dzs;
-    uint64_t* full = bars + g;
+    // The group's first warp issues the group's own forward-recompute / dgrad GEMMs (independent work accumulator): the
+    // hand-off is one named barrier over the 128 threads instead of an mbarrier round trip through an issuer warp.
     uint64_t* done = bars + G + g;
     uint64_t* doneb = bars + 2 * G + g;
-    const uint32_t taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + g * kGrpCols;
+    uint64_t* startb = bars + 3 * G + g;
+    const bool issuer = (warp & 3) == 0;
+    const uint32_t tgrp = tbase + g * kGrpCols, tgrp_a = tgrp + 64;
+    const uint32_t taddr = tgrp + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t taddr_a = taddr + 64;
+    const uint32_t wa = a4_of(wsm), x0a = a4_of(x0);
     uint32_t dphase = 0, bphase = 0;
+#define HBR_BSTAGE(BWD, BODY)                                              \
+  do {                                                                     \
+    fence_async_smem();                                                    \
+    fence_before_sync();                                                   \
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");             \
+    if (issuer) {                                                          \
+      fence_after_sync();                                                  \
+      if (elect_one()) {                                                   \
+        BODY;                                                              \
+        commit(done);                                                      \
+        if (BWD) commit(startb);                                           \
+      }                                                                    \
+      __syncwarp();                                                        \
+    }                                                                      \
+    mbar_wait(done, dphase);                                               \
+    dphase ^= 1;                                                           \
+    fence_after_sync();                                                    \
+  } while (0)
     // weight-gradient GEMM of the stage has finished reading its tiles (they are about to be overwritten in place)
 #define HBR_WAIT_B()           \
   do {                         \
@@ -1225,7 +1214,6 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         fo = __ldg(reinterpret_cast<const float4*>(out + gp * 4));
         go = __ldg(reinterpret_cast<const float4*>(dout + gp * 4));
       }
-      TR();
       // ---- recompute the forward activations ----
       float pt[3] = {0.f, 0.f, 0.f};
       if (ENC) {
@@ -1242,11 +1230,11 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
           prefetch_l2(dout + ((tile + nslots) * kTile + r) * 4);
         }
       }
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
+      HBR_BSTAGE(false, issue_fwd(tgrp, x0a, wa + WO::w0 / 16, 64, K0P));                       // F0 (x0 from shared memory)
       relu_bias_epilogue64(taddr, bias + 0, r, h1, taddr_a);
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
+      HBR_BSTAGE(false, issue_fwd_ts(tgrp, tgrp_a, wa + WO::w1 / 16, 64, 64, false));           // F1
       relu_bias_epilogue64(taddr, bias + 64, r, h2, taddr_a);
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
+      HBR_BSTAGE(false, issue_fwd_ts(tgrp, tgrp_a, wa + WO::w2 / 16, 16, 64, false));           // F2
       {
         float o16[16];
         tmem_ld<16>(taddr, o16);
@@ -1265,9 +1253,9 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         else tmem_st16(taddr_a + 16, p + 16);
         tmem_st_wait();
       }
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
+      HBR_BSTAGE(false, issue_fwd_ts(tgrp, tgrp_a, wa + WO::w3 / 16, 64, KCP, false));          // F3
       relu_bias_epilogue64(taddr, bias + 192, r, c1, taddr_a);
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();
+      HBR_BSTAGE(false, issue_fwd_ts(tgrp, tgrp_a, wa + WO::w4 / 16, 64, 64, false));           // F4
       relu_bias_epilogue64(taddr, bias + 256, r, c2, 0xffffffffu);
       {
         // d(rgb_pre) = g * ELU'(pre), with ELU'(pre) = pre > 0 ? 1 : exp(pre) = elu(pre) + 1 from the saved output
@@ -1279,11 +1267,11 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         dz16[2] = go.z * (fo.z > 0.f ? 1.f : fo.z + 1.f);
         store_dz16_both(dz16, r, dzs, taddr_a);
       }
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // col_model.4 backward: work = dA(c2)
+      HBR_BSTAGE(true, issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w5 / 16, 16, 64));                 // col_model.4: work = dA(c2)
       masked_dz_inplace64(taddr, r, c2, [&] { HBR_WAIT_B(); }, taddr_a);
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // col_model.2: work = dA(c1)
+      HBR_BSTAGE(true, issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w4 / 16, 64, 64));                 // col_model.2: work = dA(c1)
       masked_dz_inplace64(taddr, r, c1, [&] { HBR_WAIT_B(); }, taddr_a);
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // col_model.0: work[0,KCP) = d(cin)
+      HBR_BSTAGE(true, issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w3 / 16, 64, KCP));                // col_model.0: work[0,KCP) = d(cin)
       HBR_WAIT_B();
       {
         float dc[KCP], dz16[16];
@@ -1309,11 +1297,11 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
           }
         }
       }
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // sig_model.4: work = dA(h2)
+      HBR_BSTAGE(true, issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w2 / 16, 16, 64));                 // sig_model.4: work = dA(h2)
       masked_dz_inplace64(taddr, r, h2, [&] { HBR_WAIT_B(); }, taddr_a);
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // sig_model.2: work = dA(h1)
+      HBR_BSTAGE(true, issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w1 / 16, 64, 64));                 // sig_model.2: work = dA(h1)
       masked_dz_inplace64(taddr, r, h1, [&] { HBR_WAIT_B(); }, taddr_a);
-      TR(); HBR_SIGNAL(); TR(); HBR_WAIT(); TR();   // sig_model.0: work[0,K0P) = d(feat)
+      HBR_BSTAGE(true, issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w0 / 16, 64, K0P));                // sig_model.0: work[0,K0P) = d(feat)
       if (ENC) {
         float df[K0P];
         tmem_ld<K0P>(taddr, df);
@@ -1395,7 +1383,7 @@ extern "C" int hbr_debug_mlp_trace_bwd(const float* feat, const float* dirs, int
   constexpr int smem = BwdSmem<32, 48, 2>::total;
   HBR_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<32, 48, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), 2), sm_count());
-  mlp_bwd_tc_kernel<32, 48, 2, true><<<grid, 2 * kTile + 64, smem, as_stream(stream)>>>(
+  mlp_bwd_tc_kernel<32, 48, 2, true><<<grid, 2 * kTile + 32, smem, as_stream(stream)>>>(
       feat, 32, dirs, dir_group, n, params, 32, 24, out, dout, dfeat, 32, nullptr, dparams, nullptr, nullptr, trace, EncArgs{},
       HashGeom{});
   HBR_LAUNCH_CHECK();
@@ -1449,7 +1437,7 @@ static int launch_bwd_tc(const float* feat, int64_t feat_stride, const float* di
   if (scratch != nullptr) mlp_prep_kernel<K0P, KCP><<<kPrepCtas, 256, 0, st>>>(params, in0, dv, scratch);
   auto kern = mlp_bwd_tc_kernel<K0P, KCP, G, false, ENC>;
   HBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, G * kTile + 64, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, dout, dfeat,
+  kern<<<grid, G * kTile + 32, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, dout, dfeat,
                                            dfeat_stride, ddirs, dparams, scratch,
                                            rows ? reinterpret_cast<float*>(scratch + SC::off_grad) : nullptr, nullptr, enc, geom);
   if (rows) {

@@ -34,16 +34,4 @@ for nm, fn in (("bwd", lambda: ops.mlp_bwd_tc(feat, dirs, 128, flat, dims, out, 
 t = trace.cpu().tolist()
 print("CTA0 clocks: setup", t[2001]-t[2000], "main loop", t[2002]-t[2001], "flush", t[2003]-t[2002])
 g = t[:1000]; m = t[1024:1524]
-names = ["F0", "F1", "F2", "F3", "F4", "B5", "B4", "B3", "B2", "B1", "B0"]
-t0 = g[0]
-NS = 1 + 3 * 11
-i = 0; tile = 0
-while i + NS <= 1000 and g[i] != 0 and tile < 3:
-    s = g[i:i + NS]
-    print(f"tile {tile}: start@{s[0]-t0}  (next tile start +{(g[i+NS]-s[0]) if g[i+NS] else 0})")
-    for k in range(11):
-        a, b, c = s[1 + 3 * k], s[2 + 3 * k], s[3 + 3 * k]
-        prev = s[0] if k == 0 else s[3 * k]
-        mm = m[(tile * 11 + k) * 2:(tile * 11 + k) * 2 + 2]
-        print(f"   {names[k]}: work {a-prev:5d}  signal {b-a:4d}  wait {c-b:5d}   | mma saw ready +{mm[0]-b:5d} after signal, issue+commit {mm[1]-mm[0]:4d}, done seen +{c-mm[1]:5d} after commit")
-    i += NS; tile += 1
+# (the per-stage stamps of earlier kernel versions are gone: the tile groups issue their own GEMMs now)
