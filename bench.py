@@ -252,6 +252,8 @@ def run_b200(args):
     near, far = torch.tensor(args.near), torch.tensor(args.far)
     vr = hbr.Volume_Renderer(H=H, W=W, K=K, near=near, far=far, device=dev, Pos_encode=enc, Dir_encode=pe, max_dim=2 ** 10,
                              sigma_val=sigma, mu=mn)
+    if args.fuse_field:
+        vr.fuse_field = True                                              # encoder + MLP in one kernel per direction
     reducer = hdist.GradAllReduce(enc, mlp) if world > 1 else None
     rays = args.rays                                                       # per GPU (weak scaling)
     host = [tuple(t.pin_memory() for t in b) for b in make_batches(c2w, K, H, W, rays, 4, 100 + rank)]
@@ -438,6 +440,7 @@ def main():
     ap.add_argument("--l2", default="flush", choices=["flush", "warm"])
     ap.add_argument("--cpu-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fuse-field", action="store_true", help="use the fused encoder+MLP kernels (hbr_field_*_tc)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step from a CUDA graph (auto = on; falls back to eager if capture fails)")
     args = ap.parse_args()
