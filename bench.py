@@ -254,7 +254,12 @@ def run_b200(args):
                              sigma_val=sigma, mu=mn)
     if args.fuse_field:
         vr.fuse_field = True                                              # encoder + MLP in one kernel per direction
-    reducer = hdist.GradAllReduce(enc, mlp) if world > 1 else None
+    reducer = None
+    if world > 1:
+        # the gradient exchange: "peer" = this package's one-kernel all-reduce over NVLink peer memory (csrc/comm.cu),
+        # "nccl" = torch.distributed all_reduce calls, "auto" = peer unless a rank cannot set it up
+        reducer = hdist.attach_grad_allreduce(enc, mlp, kind=args.allreduce, transport=args.peer_transport, ctas=args.peer_ctas,
+                                              overlap=args.peer_chunks > 0, chunks=max(1, args.peer_chunks))
     rays = args.rays                                                       # per GPU (weak scaling)
     host = [tuple(t.pin_memory() for t in b) for b in make_batches(c2w, K, H, W, rays, 4, 100 + rank)]
     resident = [tuple(t.to(dev) for t in b) for b in host]
@@ -402,6 +407,12 @@ def run_b200(args):
         line["hash_encode_mpts_per_s"] = (n_pts / (c / args.steps)) / (m * 1e-3) / 1e6
     if reducer is not None:
         line["allreduce_bytes_per_step"] = 4 * sum(p.numel() for p in params)      # flat table + MLP gradients, fp32
+        region = getattr(reducer, "region", None)
+        line["config"]["allreduce"] = "nccl" if region is None else (
+            f"one kernel over NVLink peer memory ({region.transport}{', NVLS multicast' if region.multicast_ptr else ''}"
+            f"{f', {args.peer_chunks} overlapped chunks' if args.peer_chunks else ''})")
+        if region is not None and region.timed_out():
+            line["error"] = "peer all-reduce barrier timed out"
     if world == 1 and not args.no_cpu_baseline:
         v, sec = cpu_step_rays_per_s(args, 3, 1, args.cpu_rays)
         line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
@@ -440,6 +451,11 @@ def main():
     ap.add_argument("--l2", default="flush", choices=["flush", "warm"])
     ap.add_argument("--cpu-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "peer", "nccl"], help="N>1 gradient exchange")
+    ap.add_argument("--peer-transport", default="auto", choices=["auto", "ipc", "symm"])
+    ap.add_argument("--peer-ctas", type=int, default=0)
+    ap.add_argument("--peer-chunks", type=int, default=0, help="> 0: all-reduce level chunks on a side stream while the "
+                    "remaining chunks' scatter-add runs")
     ap.add_argument("--fuse-field", action="store_true", help="use the fused encoder+MLP kernels (hbr_field_*_tc)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step from a CUDA graph (auto = on; falls back to eager if capture fails)")

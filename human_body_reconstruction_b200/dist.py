@@ -4,7 +4,10 @@ replicated, ONE flat gradient buffer per module all-reduced (averaged) over NCCL
 reduced gradients.  The reference has no counterpart (it wraps only the MLP in nn.DataParallel); this is
 SURVEY section 8(e).
 
-Mechanics: `HashEncoder` / `MLP_3D` publish their flat gradient tensor (L,T,F) / (14227,) from inside their
+Two exchanges are provided: `GradAllReduce` (NCCL calls, below) and `PeerGradAllReduce` (ONE kernel of this
+package over NVLink peer memory / NVLS multicast, csrc/comm.cu; the default of `attach_grad_allreduce`).
+
+Mechanics of the NCCL variant: `HashEncoder` / `MLP_3D` publish their flat gradient tensor (L,T,F) / (14227,) from inside their
 autograd backward -- the encoder in level chunks, each as soon as its scatter-add kernel has been enqueued;
 the hook below launches an asynchronous all-reduce on every published piece right there (NCCL's stream waits
 for the producing kernel, the compute stream runs on: the MLP's reduce overlaps the hash-table backward, a
@@ -75,6 +78,107 @@ class GradAllReduce:
             w.wait()                       # compute stream waits on the NCCL stream; no host sync for CUDA tensors
         self._pending.clear()
         self._callback_queued = False
+
+
+class PeerGradAllReduce:
+    """`PeerGradAllReduce(encoder, mlp)`: the same contract as GradAllReduce, but the exchange is ONE kernel over NVLink
+    peer memory (csrc/comm.cu) instead of NCCL calls.  The two modules' flat gradients become slices of one persistent
+    peer-mapped region [table (L,T,F) | MLP parameters]; the scatter-add of the hash-grid backward and the MLP
+    gradient reduction write straight into it, and an end-of-backward engine callback enqueues hbr_allreduce_peer on
+    the compute stream (no extra stream, no event round trip, capturable in the step's CUDA graph).  Every rank ends
+    with bit-identical averaged gradients.  `.grad` of the parameters aliases the region from step to step (use
+    zero_grad(set_to_none=True), torch's default)."""
+
+    def __init__(self, encoder, mlp, group=None, average: bool = True, transport: str = "ipc", ctas: int = 0,
+                 overlap: bool = False, chunks: int = 4):
+        """overlap=False: one all-reduce of the whole region behind the backward pass.  overlap=True: the table backward
+        runs in `chunks` level chunks and every published piece (the MLP gradient first, then each level chunk) is
+        all-reduced at once by a small grid (`ctas`, default 32) on a high-priority side stream while the next chunk's
+        scatter-add still runs on the compute stream."""
+        from .peer import PeerRegion
+        self.group, self.average, self.overlap = group, average, overlap
+        self.ctas = ctas if ctas > 0 else (32 if overlap else 0)
+        self.modules = [encoder, mlp]
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        n_tab = encoder.L * encoder.T * encoder.F
+        n_mlp = mlp._flat_params().numel()
+        off = -(-n_tab // 4) * 4
+        self.region = PeerRegion(off + n_mlp, group=group, transport=transport)
+        encoder._flat_table()
+        encoder._grad_buffer = self.region.tensor[:n_tab].view(encoder.L, encoder.T, encoder.F)
+        mlp._grad_buffer = self.region.tensor[off:off + n_mlp]
+        if overlap:
+            encoder._grad_chunks = chunks
+        self._side = torch.cuda.Stream(device=self.region.device, priority=-1) if overlap else None
+        self._base = self.region.tensor.data_ptr()
+        self._callback_queued = False
+        self._side_used = False
+        self.bytes_reduced = 0
+        for m in self.modules:
+            m._grad_hooks.append(self._on_grad)
+
+    def remove(self):
+        for m in self.modules:
+            if self._on_grad in m._grad_hooks:
+                m._grad_hooks.remove(self._on_grad)
+            m._grad_buffer = None
+
+    def _scale(self):
+        return 1.0 / self.world if self.average else 1.0
+
+    def _on_grad(self, flat: torch.Tensor):
+        if not self._callback_queued:
+            self._callback_queued = True
+            Variable._execution_engine.queue_callback(self._finish)
+        if self.overlap:
+            off = (flat.data_ptr() - self._base) // 4
+            n = -(-flat.numel() // 4) * 4
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)                       # the piece's producer kernel has been enqueued on `cur`
+            with torch.cuda.stream(self._side):
+                self.region.all_reduce(n=n, scale=self._scale(), ctas=self.ctas, offset=off)
+            self._side_used = True
+            self.bytes_reduced += n * 4
+
+    def _finish(self):
+        self._callback_queued = False
+        if self.overlap:
+            if self._side_used:
+                torch.cuda.current_stream().wait_stream(self._side)
+                self._side_used = False
+            return
+        self.region.all_reduce(scale=self._scale(), ctas=self.ctas)
+        self.bytes_reduced += self.region.n * 4
+
+
+def attach_grad_allreduce(encoder, mlp, group=None, kind: str = "auto", **peer_kw):
+    """The gradient exchange for `world` > 1: kind "peer" = PeerGradAllReduce, "nccl" = GradAllReduce, "auto" = peer
+    when every rank can set it up (CUDA ranks of one node), else NCCL.  Peer transport "auto": 2 ranks exchange through
+    plain peer loads/stores over CUDA-IPC mappings (measured 0.130 ms for 67 MB against 0.153 ms NCCL and 0.21 ms
+    multicast); more ranks reduce inside the NVSwitch through an NVLS multicast mapping when torch's symmetric memory
+    offers one (8 ranks: 0.184 ms against 0.240 ms peer loads/stores and 0.245 ms NCCL)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    if kind == "nccl" or not torch.cuda.is_available() or dist.get_backend(group) != "nccl":
+        return GradAllReduce(encoder, mlp, group=group)
+    world = dist.get_world_size(group)
+    kw = dict(peer_kw)
+    if kw.get("transport", "auto") == "auto":
+        kw["transport"] = "ipc" if world == 2 else "symm"
+    red, err = None, None
+    try:
+        red = PeerGradAllReduce(encoder, mlp, group=group, **kw)
+    except Exception as e:                                   # e.g. no peer access between the devices
+        err = e
+    ok = torch.tensor([1 if red is not None else 0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 1:
+        return red
+    if red is not None:
+        red.remove()
+    if kind == "peer":
+        raise RuntimeError(f"peer-memory all-reduce unavailable on at least one rank: {err!r}")
+    return GradAllReduce(encoder, mlp, group=group)
 
 
 def shard_rays(n_rays: int, rank: int, world: int) -> slice:

@@ -37,7 +37,7 @@ class _HashEncodeFn(torch.autograd.Function):
             ctx.g = None
             torch.cuda.current_stream().wait_event(ev)
         else:
-            g = torch.zeros((L, T, F), device=dy.device, dtype=torch.float32)
+            g = enc._new_grad(dy.device)
         # With gradient hooks attached (multi-GPU) the pass runs in level chunks and every finished chunk is published
         # at once: its all-reduce travels over NVLink while the next chunk's scatter-add still runs.
         nch = max(1, min(L, enc._grad_chunks)) if enc._grad_hooks else 1
@@ -82,6 +82,7 @@ class HashEncoder(nn.Module):
         # scatter-add slows both (0.90 ms/step with 4 chunks against 0.79 ms with one all-reduce after the pass), so the
         # default is one chunk; larger per-GPU batches may prefer more.
         self._grad_chunks = 1
+        self._grad_buffer = None
         self._flat = None
         self._reflatten()
 
@@ -140,10 +141,19 @@ class HashEncoder(nn.Module):
             side = self._side = torch.cuda.Stream(device=dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            g = torch.zeros((self.L, self.T, self.F), device=dev, dtype=torch.float32)
+            g = self._new_grad(dev)
             ev = side.record_event()
         g.record_stream(cur)
         return g, ev
+
+    def _new_grad(self, dev):
+        """Zero-filled (L,T,F) gradient buffer: fresh, or -- when dist.PeerGradAllReduce installed one -- the persistent
+        peer-mapped buffer the NVLink all-reduce kernel works on in place (then `.grad` of the level tables aliases it
+        from step to step: use optimizer.zero_grad(set_to_none=True), torch's default)."""
+        buf = self._grad_buffer
+        if buf is not None and buf.device == dev:
+            return buf.zero_()
+        return torch.zeros((self.L, self.T, self.F), device=dev, dtype=torch.float32)
 
     # -- gradient publication (dist.py hooks the flat gradient for the NCCL all-reduce) -------------------
     def _publish_grad(self, g: torch.Tensor):

@@ -43,7 +43,7 @@ class _MlpFn(torch.autograd.Function):
         feat, dirs, act = ctx.saved_tensors
         mlp = ctx.mlp
         flat = mlp._flat_params()
-        dflat = torch.zeros_like(flat)
+        dflat = mlp._grad_buffer.zero_() if mlp._grad_buffer is not None else torch.zeros_like(flat)
         dout = dout.float().contiguous()
         want_dfeat, want_ddirs = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if ctx.use_tc:
@@ -83,6 +83,7 @@ class MLP_3D(nn.Module):
         self._native = (num_sig == 2 and num_col == 2 and h_size == 64 and L * F + E <= 64 and 15 + d_view <= 64)
         self._in0 = L * F + E
         self._grad_hooks = []
+        self._grad_buffer = None     # persistent (peer-mapped) flat gradient buffer, see dist.PeerGradAllReduce
         self._flat = None
         if self._native:
             self._reflatten()

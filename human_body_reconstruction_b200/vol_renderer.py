@@ -41,9 +41,9 @@ class _FieldFn(torch.autograd.Function):
         pts, dirs, feat16, out = ctx.saved_tensors
         enc, mlp = ctx.enc, ctx.mlp
         L, T, F = enc.L, enc.T, enc.F
-        g = torch.zeros((L, T, F), device=dout.device, dtype=torch.float32)
+        g = enc._new_grad(dout.device)
         flat = mlp._flat_params()
-        dflat = torch.zeros_like(flat)
+        dflat = mlp._grad_buffer.zero_() if mlp._grad_buffer is not None else torch.zeros_like(flat)
         ddirs = ops.field_bwd_tc(pts, ctx.geom, dirs, ctx.dir_group, flat, ctx.dims, feat16, out.detach(),
                                  dout.float().contiguous(), g, ctx.needs_input_grad[1], dflat)
         mlp._publish_grad(dflat)

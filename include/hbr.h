@@ -220,6 +220,31 @@ int hbr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   double beta2, double eps, double weight_decay, int decoupled_weight_decay, int64_t step,
                   double inv_scale, const float* found_inf, void* stream);
 
+/* ---- 8e: the data-parallel step's gradient exchange over NVLink peer memory (csrc/comm.cu) -------------------------
+ * The reference has no multi-process path (train_hash2.py:134 wraps only the MLP in nn.DataParallel); this replaces the
+ * NCCL all-reduce dist.GradAllReduce would issue on the flat gradient buffer.
+ * hbr_peer_alloc: a zero-filled device allocation that other processes of this node can map (plain cudaMalloc, so a
+ * CUDA IPC handle addresses it exactly); hbr_peer_export / hbr_peer_import turn it into / open a 64-byte handle that the
+ * host side passes between ranks (e.g. torch.distributed.all_gather_object); hbr_peer_release unmaps an imported
+ * pointer, hbr_peer_free frees an owned one. */
+#define HBR_MAX_PEERS 8
+#define HBR_PEER_MAX_CTAS 128
+#define HBR_PEER_HANDLE_BYTES 64
+#define HBR_PEER_FLAG_BYTES (HBR_PEER_MAX_CTAS * HBR_MAX_PEERS * 4)
+int hbr_peer_alloc(void** ptr, int64_t bytes);
+int hbr_peer_free(void* ptr);
+int hbr_peer_export(void* ptr, unsigned char handle[HBR_PEER_HANDLE_BYTES]);
+int hbr_peer_import(const unsigned char handle[HBR_PEER_HANDLE_BYTES], void** ptr);
+int hbr_peer_release(void* ptr);
+/* In-place all-reduce of n fp32 (n % 4 == 0) over `world` ranks: every rank calls it with bufs[q] / flags[q] = ITS
+ * mapping of rank q's buffer and of rank q's HBR_PEER_FLAG_BYTES zero-initialised flag words (bufs[rank] is its own), on
+ * the stream that produced its buffer; result = scale * sum over ranks, bit-identical on every rank.  multicast: an NVLS
+ * multicast mapping of the same buffers (switch-side reduction) or NULL (plain peer loads/stores).  ctas <= 0 picks the
+ * default; the grid never exceeds the SM count (the flag barriers need co-resident CTAs) and must be the same on every
+ * rank.  status: optional device word set to 1 if a barrier timed out (10 s) -- the buffer is then undefined. */
+int hbr_allreduce_peer(void* const* bufs, void* const* flags, void* multicast, int rank, int world, int64_t n, float scale,
+                       int ctas, unsigned int* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,7 +70,11 @@ def _worker(rank, world, port_no, tmp):
 
     for chunks in (1, 3):
         mod = _FlatGradModule(levels, width, chunks=chunks)
-        reducer = hdist.GradAllReduce(mod)
+        if chunks == 1:
+            reducer = hdist.GradAllReduce(mod)
+        else:       # the front door picks the NCCL/gloo call path when the ranks are not CUDA ranks (no peer memory here)
+            reducer = hdist.attach_grad_allreduce(mod, _FlatGradModule(levels, width))
+            assert isinstance(reducer, hdist.GradAllReduce)
         sl = hdist.shard_rays(n_rays, rank, world)
         loss = torch.nn.functional.mse_loss(mod(x_all[sl]), gt_all[sl])   # mean over the LOCAL batch
         loss.backward()

@@ -48,7 +48,7 @@ def _grads(enc, mlp, vr, ro, rd, dn, gt, t, dev):
             torch.cat([p.grad.reshape(-1) for p in mlp.parameters()]).cpu())
 
 
-def _worker(rank, world, port_no, tmp):
+def _worker(rank, world, port_no, tmp, mode="nccl"):
     os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port_no))
     from human_body_reconstruction_b200 import dist as hdist
@@ -56,15 +56,17 @@ def _worker(rank, world, port_no, tmp):
     dev = torch.device("cuda", rank)
     torch.cuda.set_device(dev)
     enc, mlp, vr = _build(dev)
-    hdist.GradAllReduce(enc, mlp)
+    red = hdist.GradAllReduce(enc, mlp) if mode == "nccl" else hdist.PeerGradAllReduce(enc, mlp, transport=mode[5:])
     ro, rd, dn, gt, t = _batch()
     sl = hdist.shard_rays(ro.shape[0], rank, world)
-    for chunks in (1, 4):
+    for chunks in (1, 4) if mode == "nccl" else (1, 1):          # peer mode: two steps through the same persistent region
         enc._grad_chunks = chunks
         for p in list(enc.parameters()) + list(mlp.parameters()):
             p.grad = None
         gt_tab, gt_mlp = _grads(enc, mlp, vr, ro[sl], rd[sl], dn[sl], gt[sl], t, dev)
         torch.save((gt_tab, gt_mlp), os.path.join(tmp, f"g{rank}_{chunks}.pt"))
+    if mode != "nccl":
+        assert not red.region.timed_out()
     import torch.distributed as tdist
     tdist.barrier()
     tdist.destroy_process_group()
@@ -81,3 +83,20 @@ def test_sharded_gradients_equal_single_gpu(tmp_path):
             tab, gm = torch.load(os.path.join(tmp_path, f"g{rank}_{chunks}.pt"))
             assert float((tab - want_tab).norm() / want_tab.norm()) < 1e-5, (rank, chunks)
             assert float((gm - want_mlp).norm() / want_mlp.norm()) < 1e-5, (rank, chunks)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("transport", ["ipc", "symm"])
+def test_peer_memory_allreduce_equals_single_gpu(tmp_path, transport):
+    """dist.PeerGradAllReduce: gradients written into the peer-mapped region by the backward kernels, averaged by
+    hbr_allreduce_peer (one kernel over NVLink: peer loads/stores over CUDA-IPC mappings, or switch-side reduction
+    through torch symmetric memory's NVLS multicast mapping), == single-GPU gradients; both ranks bit-identical."""
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), "peer-" + transport), nprocs=2, join=True)
+    dev = torch.device("cuda", 0)
+    enc, mlp, vr = _build(dev)
+    want_tab, want_mlp = _grads(enc, mlp, vr, *_batch(), dev)
+    got = [torch.load(os.path.join(tmp_path, f"g{rank}_1.pt")) for rank in range(2)]
+    for tab, gm in got:
+        assert float((tab - want_tab).norm() / want_tab.norm()) < 1e-5
+        assert float((gm - want_mlp).norm() / want_mlp.norm()) < 1e-5
+    assert torch.equal(got[0][0], got[1][0]) and torch.equal(got[0][1], got[1][1])
