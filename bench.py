@@ -454,8 +454,8 @@ def main():
     ap.add_argument("--allreduce", default="auto", choices=["auto", "peer", "nccl"], help="N>1 gradient exchange")
     ap.add_argument("--peer-transport", default="auto", choices=["auto", "ipc", "symm"])
     ap.add_argument("--peer-ctas", type=int, default=0)
-    ap.add_argument("--peer-chunks", type=int, default=0, help="> 0: all-reduce level chunks on a side stream while the "
-                    "remaining chunks' scatter-add runs")
+    ap.add_argument("--peer-chunks", type=int, default=2, help="> 0: all-reduce level chunks on a side stream while the "
+                    "remaining chunks' scatter-add runs; 0: one all-reduce behind the backward pass")
     ap.add_argument("--fuse-field", action="store_true", help="use the fused encoder+MLP kernels (hbr_field_*_tc)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step from a CUDA graph (auto = on; falls back to eager if capture fails)")

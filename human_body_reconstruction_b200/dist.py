@@ -90,7 +90,7 @@ class PeerGradAllReduce:
     zero_grad(set_to_none=True), torch's default)."""
 
     def __init__(self, encoder, mlp, group=None, average: bool = True, transport: str = "ipc", ctas: int = 0,
-                 overlap: bool = False, chunks: int = 4):
+                 overlap: bool = False, chunks: int = 2):
         """overlap=False: one all-reduce of the whole region behind the backward pass.  overlap=True: the table backward
         runs in `chunks` level chunks and every published piece (the MLP gradient first, then each level chunk) is
         all-reduced at once by a small grid (`ctas`, default 32) on a high-priority side stream while the next chunk's
@@ -163,6 +163,8 @@ def attach_grad_allreduce(encoder, mlp, group=None, kind: str = "auto", **peer_k
         return GradAllReduce(encoder, mlp, group=group)
     world = dist.get_world_size(group)
     kw = dict(peer_kw)
+    kw.setdefault("overlap", True)        # measured best at 4 096 rays/GPU: 2 level chunks, 32 CTAs on the side stream
+    kw.setdefault("chunks", 2)            # (W=8: 0.656 ms/step against 0.712 behind the backward, 0.671 with 4 chunks)
     if kw.get("transport", "auto") == "auto":
         kw["transport"] = "ipc" if world == 2 else "symm"
     red, err = None, None
