@@ -348,6 +348,35 @@ def run_b200(args):
             loss = step(batch)
         loss_val = loss.item()
         e2e_s += time.perf_counter() - t0
+    # (4) 8f row 2: the batch comes from the device-resident views (no host batch, no H2D): ray ids drawn on the device
+    #     -> hbr_ray_gen -> static graph inputs -> replay -> loss.item()
+    sampler = None
+    if world == 1 and gs is not None and not args.no_device_sampler:
+        try:
+            yy, xx = torch.meshgrid(torch.arange(H, device=dev, dtype=torch.float32),
+                                    torch.arange(W, device=dev, dtype=torch.float32), indexing="ij")
+            img = torch.stack([0.5 + 0.5 * torch.sin(xx / 37.0), 0.5 + 0.5 * torch.cos(yy / 23.0), (xx + yy) / (H + W)], dim=-1)
+            img = (img * 255).round().to(torch.uint8).expand(args.views, H, W, 3).contiguous()   # 192 MB at 100 x 800 x 800
+            ds = hbr.DeviceRayDataset(img, c2w, K, device=dev, batch_size=rays)
+            gs2 = GraphedStep(vr, nerf, params, rays, args.samples, args.hierarchical, dev, autocast=amp, source=ds).capture()
+            for _ in range(3):
+                gs2()
+            torch.cuda.synchronize()
+            s_s = 0.0
+            for k in range(args.steps):
+                if flush is not None:
+                    flush.zero_()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                loss_s = gs2().item()
+                s_s += time.perf_counter() - t0
+            sampler = {"value": rays * args.steps / s_s, "unit": "rays/s", "ms_per_step": s_s * 1e3 / args.steps,
+                       "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4, "resident_view_bytes": img.numel() + c2w.numel() * 4,
+                       "note": "ray ids drawn on the device -> hbr_ray_gen from the resident views -> step, all captured in ONE "
+                               "cuda graph; timed: replay + loss.item()", "last_loss": loss_s}
+            del img, ds, gs2
+        except Exception as e:                                             # noqa: BLE001
+            sampler = {"error": f"{type(e).__name__}: {e}"}
     barrier()
     clk = clocks.stop()
 
@@ -405,6 +434,8 @@ def run_b200(args):
     if "hbr_hash_encode_fwd" in kern:
         c, m = kern["hbr_hash_encode_fwd"]
         line["hash_encode_mpts_per_s"] = (n_pts / (c / args.steps)) / (m * 1e-3) / 1e6
+    if sampler is not None:
+        line["device_sampler_e2e"] = sampler
     if reducer is not None:
         line["allreduce_bytes_per_step"] = 4 * sum(p.numel() for p in params)      # flat table + MLP gradients, fp32
         region = getattr(reducer, "region", None)
@@ -451,6 +482,7 @@ def main():
     ap.add_argument("--l2", default="flush", choices=["flush", "warm"])
     ap.add_argument("--cpu-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-device-sampler", action="store_true", help="skip the device-resident ray sampler leg (8f row 2)")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "peer", "nccl"], help="N>1 gradient exchange")
     ap.add_argument("--peer-transport", default="auto", choices=["auto", "ipc", "symm"])
     ap.add_argument("--peer-ctas", type=int, default=0)

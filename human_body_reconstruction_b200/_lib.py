@@ -30,7 +30,7 @@ NVCC_FLAGS = [
 HBR_MAX_LEVELS = 32
 HBR_MAX_PEERS, HBR_PEER_MAX_CTAS, HBR_PEER_HANDLE_BYTES = 8, 128, 64
 HBR_PEER_FLAG_BYTES = HBR_PEER_MAX_CTAS * HBR_MAX_PEERS * 4
-HBR_F32, HBR_F16 = 0, 1
+HBR_F32, HBR_F16, HBR_U8 = 0, 1, 2
 
 
 class HashGeom(C.Structure):
@@ -113,6 +113,9 @@ SIGNATURES = {
     "hbr_field_bwd_tc": ([_vp, _i64, _geom_p, _vp, _i64, _vp, _dims_p, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "hbr_adam_step": ([_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i32, _i64,
                        C.c_double, _vp, _vp], C.c_int),
+    "hbr_ray_gen": ([_vp, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
+                    C.c_int),
+    "hbr_ray_bbox": ([_vp, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp], C.c_int),
     "hbr_peer_alloc": ([C.POINTER(_vp), _i64], C.c_int),
     "hbr_peer_free": ([_vp], C.c_int),
     "hbr_peer_export": ([_vp, C.POINTER(C.c_ubyte)], C.c_int),
@@ -141,7 +144,7 @@ SIGNATURES = {
 # kernels launched by one call of each entry point (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
     "hbr_hash_encode_fwd": 1, "hbr_hash_encode_bwd": 1, "hbr_hash_indices": 1, "hbr_dir_encode": 1,
-    "hbr_mlp_fwd_f32": 1, "hbr_mlp_bwd_f32": 2, "hbr_mlp_fwd_tc": 2, "hbr_mlp_bwd_tc": 3, "hbr_field_fwd_tc": 2, "hbr_field_bwd_tc": 3, "hbr_debug_umma": 1, "hbr_adam_step": 1, "hbr_allreduce_peer": 1, "hbr_debug_mlp_trace": 1, "hbr_debug_umma_chain_bench": 1, "hbr_debug_umma_bench": 1, "hbr_debug_mlp_trace_bwd": 1, "hbr_ray_points": 1, "hbr_occupancy_mask": 1,
+    "hbr_mlp_fwd_f32": 1, "hbr_mlp_bwd_f32": 2, "hbr_mlp_fwd_tc": 2, "hbr_mlp_bwd_tc": 3, "hbr_field_fwd_tc": 2, "hbr_field_bwd_tc": 3, "hbr_debug_umma": 1, "hbr_adam_step": 1, "hbr_allreduce_peer": 1, "hbr_ray_gen": 1, "hbr_ray_bbox": 1, "hbr_debug_mlp_trace": 1, "hbr_debug_umma_chain_bench": 1, "hbr_debug_umma_bench": 1, "hbr_debug_mlp_trace_bwd": 1, "hbr_ray_points": 1, "hbr_occupancy_mask": 1,
     "hbr_composite_fwd": 1, "hbr_composite_bwd": 1, "hbr_hier_sample": 1, "hbr_grid_points": 1,
     "hbr_grid_density": 3, "hbr_mc_count": 1, "hbr_mc_emit": 2,
 }

@@ -30,8 +30,13 @@ def default_loss(Cr, Cf, gt):
 
 class GraphedStep:
     def __init__(self, renderer, model, params: Iterable[torch.nn.Parameter], n_rays: int, num_samples: int,
-                 hierarchical: bool, device, loss_fn: Callable = default_loss, autocast: bool = True, warmup: int = 3):
+                 hierarchical: bool, device, loss_fn: Callable = default_loss, autocast: bool = True, warmup: int = 3,
+                 source=None):
+        """source: optional rays.DeviceRayDataset.  Its sampler (ray ids from the graph-safe device generator ->
+        hbr_ray_gen) is then captured in front of the step, so a replay draws a fresh batch from the resident views by
+        itself: call the object with no arguments; nothing crosses PCIe but the graph launch."""
         self.renderer, self.model = renderer, model
+        self.source = source
         self.params = list(params)
         self.num_samples, self.hierarchical = int(num_samples), bool(hierarchical)
         self.loss_fn, self.autocast = loss_fn, autocast
@@ -52,10 +57,13 @@ class GraphedStep:
         self._warmup = warmup
 
     def _step(self):
+        rays_o, rays_d, dir_norm, gt = self.rays_o, self.rays_d, self.dir_norm, self.gt
+        if self.source is not None:
+            rays_o, rays_d, dir_norm, gt = self.source.sample(self.n_rays)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
-            Cr, Cf, _ = self.renderer.vol_render(self.model, self.rays_d, self.rays_o, num_samples=self.num_samples,
-                                                 update_mask=False, dir_norm=self.dir_norm, hierarchical=self.hierarchical)
-            loss = self.loss_fn(Cr, Cf, self.gt)
+            Cr, Cf, _ = self.renderer.vol_render(self.model, rays_d, rays_o, num_samples=self.num_samples,
+                                                 update_mask=False, dir_norm=dir_norm, hierarchical=self.hierarchical)
+            loss = self.loss_fn(Cr, Cf, gt)
         loss.backward()
         return loss
 

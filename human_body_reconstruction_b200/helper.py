@@ -80,6 +80,11 @@ def get_od(H, W, K, c2w: torch.Tensor, find_inv: Optional[bool] = False):
     """helper.py:176-208: per-pixel ray origins, unit directions and the direction norms (>= 1).
     K is the INTEGER intrinsics matrix of train_hash2.py:67-72 (focal / principal point truncated)."""
     device = c2w.device
+    if c2w.is_cuda and not find_inv and c2w.dim() == 3:
+        # one kernel instead of meshgrid + bmm + norm + div: rays of every pixel of every view, in the reference's order
+        B, hw = c2w.shape[0], int(H) * int(W)
+        o, d, n, _ = ops.ray_gen(c2w, int(H), int(W), K)
+        return o.view(B, hw, 3), d.view(B, hw, 3), n.view(B, hw, 1)
     i, j = torch.meshgrid(torch.arange(W, device=device), torch.arange(H, device=device), indexing="xy")
     i = ((i - K[0, 2]) / K[0, 0]).reshape(-1)
     j = ((j - K[1, 2]) / K[1, 1]).reshape(-1)
@@ -112,6 +117,13 @@ def find_bounding_box(data_loader, near, far, K, num_samples=64, exp=False, devi
         t = torch.from_numpy(np.asarray([near, far + 1.5])).to(device)
     min_bound = torch.ones(3, device=device) * 1e7
     max_bound = torch.ones(3, device=device) * (-1e7)
+    if torch.device(device).type == "cuda" and not exp:
+        # device path: one reduction kernel per loader batch, nothing materialised (hbr_ray_bbox)
+        bounds = None
+        for batch in data_loader:
+            _, c2w, _ = batch
+            bounds = ops.ray_bbox(c2w.to(device), int(H), int(W), K, float(t[0]), float(t[1]), bounds)
+        return bounds[3:].clone(), bounds[:3].clone()
     with torch.no_grad():
         for batch in data_loader:
             _, c2w, _ = batch

@@ -103,6 +103,59 @@ def ray_points(rays_o: torch.Tensor, rays_d: torch.Tensor, t: torch.Tensor) -> t
     return pts
 
 
+def _intrinsics(K) -> tuple:
+    """(fx, fy, cx, cy) as Python floats from the reference's 3x3 K (int64 at train_hash2.py:67-72, any dtype here)."""
+    K = torch.as_tensor(K).detach().cpu()
+    return float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+
+
+def ray_gen(c2w: torch.Tensor, H: int, W: int, K, ray_ids: Optional[torch.Tensor] = None, first: int = 0,
+            n_rays: Optional[int] = None, images: Optional[torch.Tensor] = None, check_ids: bool = False):
+    """helper.py:176-208 per requested ray (id = view*H*W + row*W + col).  c2w (V,4,4) fp32 CUDA; images (V,H,W,3)
+    fp32 or uint8.  Returns rays_o (n,3), rays_d (n,3), dir_norm (n,1), gt (n,3) or None."""
+    require_cuda(c2w, ray_ids, images)
+    c2w = c2w.float().contiguous()
+    V = c2w.shape[0]
+    if c2w.shape[1:] != (4, 4):
+        raise ValueError("c2w must be (V,4,4)")
+    if ray_ids is not None:
+        ray_ids = ray_ids.to(torch.int64).contiguous()
+        n_rays = ray_ids.numel()
+    elif n_rays is None:
+        n_rays = V * H * W - first
+    dtype = HBR_F32
+    if images is not None:
+        if tuple(images.shape) != (V, H, W, 3) or not images.is_contiguous():
+            raise ValueError("images must be contiguous (V,H,W,3)")
+        if images.dtype == torch.uint8:
+            dtype = _lib.HBR_U8
+        elif images.dtype != torch.float32:
+            raise TypeError("images must be float32 or uint8")
+    dev = c2w.device
+    o = torch.empty((n_rays, 3), device=dev)
+    d = torch.empty((n_rays, 3), device=dev)
+    nrm = torch.empty((n_rays, 1), device=dev)
+    gt = torch.empty((n_rays, 3), device=dev) if images is not None else None
+    bad = torch.zeros(1, dtype=torch.int32, device=dev) if check_ids else None
+    fx, fy, cx, cy = _intrinsics(K)
+    check(lib().hbr_ray_gen(ptr(c2w), V, int(H), int(W), fx, fy, cx, cy, ptr(ray_ids), int(first), int(n_rays), ptr(images), dtype,
+                            ptr(o), ptr(d), ptr(nrm), ptr(gt), ptr(bad), stream()))
+    if check_ids and int(bad.item()):
+        raise IndexError("ray id outside [0, V*H*W)")
+    return o, d, nrm, gt
+
+
+def ray_bbox(c2w: torch.Tensor, H: int, W: int, K, t0: float, t1: float, bounds: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """helper.py:109-141 over the views in c2w: updates / returns bounds = [min xyz, max xyz] (6 floats on the device)."""
+    require_cuda(c2w, bounds)
+    c2w = c2w.float().contiguous()
+    if bounds is None:
+        bounds = torch.tensor([1e7, 1e7, 1e7, -1e7, -1e7, -1e7], device=c2w.device)
+    fx, fy, cx, cy = _intrinsics(K)
+    check(lib().hbr_ray_bbox(ptr(c2w), c2w.shape[0], int(H), int(W), fx, fy, cx, cy, float(t0), float(t1), ptr(bounds), stream()))
+    return bounds
+
+
 def occupancy_mask(pts: torch.Tensor, grid: torch.Tensor, mu, sigma: float) -> torch.Tensor:
     require_cuda(pts, grid)
     pts = _f32c(pts)

@@ -33,7 +33,7 @@ typedef enum {
   HBR_ERR_UNSUPPORTED = -3
 } hbr_status;
 
-typedef enum { HBR_F32 = 0, HBR_F16 = 1 } hbr_dtype;
+typedef enum { HBR_F32 = 0, HBR_F16 = 1, HBR_U8 = 2 } hbr_dtype;
 
 /* Geometry of a HashEncoder instance: hash_encoding.py:6-39.
  * scale[l] = N_min * b**l is computed by the HOST with the reference's torch expression
@@ -219,6 +219,23 @@ int hbr_mc_emit(const float* density, int n0, int n1, int n2, float iso, int i_b
 int hbr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
                   double beta2, double eps, double weight_decay, int decoupled_weight_decay, int64_t step,
                   double inv_scale, const float* found_inf, void* stream);
+
+/* ---- 8f row 2: on-device ray generation, replacing the CPU TensorDataset + DataLoader of train_hash2.py:74-96,211-215 ----
+ * get_od (helper.py:176-208) evaluated per requested ray: ray id = view * H*W + row * W + col (the order of the
+ * reference's flattened (rays_o, rays_d, dir_norm, gt) dataset); ids from ray_ids (n_rays int64 on the device) or, with
+ * ray_ids == NULL, the consecutive range [first, first + n_rays).  c2w: (n_views,4,4) fp32 row-major on the device;
+ * fx, fy, cx, cy = K[0,0], K[1,1], K[0,2], K[1,2] converted to float (the reference's K is int64, train_hash2.py:67-72).
+ * images (optional, with gt): (n_views,H,W,3) fp32 in [0,1] or uint8 (then gt = u8 / 255 as torchvision's ToTensor).
+ * Outputs: rays_o (n,3), unit rays_d (n,3), dir_norm (n,1), gt (n,3).  bad_id (optional device int): set to 1 when an id
+ * falls outside [0, n_views*H*W) (that ray is written as zeros). */
+int hbr_ray_gen(const float* c2w, int64_t n_views, int H, int W, float fx, float fy, float cx, float cy,
+                const int64_t* ray_ids, int64_t first, int64_t n_rays, const void* images, int image_dtype, float* rays_o,
+                float* rays_d, float* dir_norm, float* gt, int* bad_id, void* stream);
+/* find_bounding_box (helper.py:109-141): bounds[0..2] = min, bounds[3..5] = max over every pixel of every view of
+ * o + d*t0 and o + d*t1 (t0 = near, t1 = far + 1.5 in the reference).  The caller initialises bounds to (+1e7 x3, -1e7 x3)
+ * like helper.py:121-122. */
+int hbr_ray_bbox(const float* c2w, int64_t n_views, int H, int W, float fx, float fy, float cx, float cy, float t0, float t1,
+                 float* bounds, void* stream);
 
 /* ---- 8e: the data-parallel step's gradient exchange over NVLink peer memory (csrc/comm.cu) -------------------------
  * The reference has no multi-process path (train_hash2.py:134 wraps only the MLP in nn.DataParallel); this replaces the
