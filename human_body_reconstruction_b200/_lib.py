@@ -126,7 +126,7 @@ SIGNATURES = {
     "hbr_debug_umma_bench": ([_i32, _i32, _i32, _i32, _i32, _vp, _vp], C.c_int),
     "hbr_debug_umma_chain_bench": ([_i32, _i32, _i32, _vp, _vp], C.c_int),
     "hbr_debug_mlp_trace": ([_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp], C.c_int),
-    "hbr_debug_mlp_trace_bwd": ([_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "hbr_debug_mlp_trace_bwd": ([_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "hbr_ray_points": ([_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp], C.c_int),
     "hbr_occupancy_mask": ([_vp, _i64, _vp, _i32, C.POINTER(C.c_float), _f32, _vp, _vp], C.c_int),
     "hbr_composite_fwd": ([_vp, _i64, _vp, _i64, _vp, _i64, _vp, _f32, _vp, _i64, _i64, _vp, _vp, _vp], C.c_int),

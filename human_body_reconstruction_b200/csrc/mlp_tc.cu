@@ -403,13 +403,10 @@ __device__ __forceinline__ void relu_epilogue64(uint32_t taddr, int r, uint8_t* 
   }
 }
 
-// dA (64 accumulator columns) * [activation > 0] -> bf16 dZ written over the activation tile itself.  The values are
-// formed in registers first; `before_store()` (wait for the weight-gradient GEMM still reading the tile) runs right
-// before the in-place store.
-template <typename F>
-__device__ __forceinline__ void masked_dz_inplace64(uint32_t taddr, int r, uint8_t* tile, F before_store,
-                                                    uint32_t taddr_a = 0xffffffffu) {
-  uint4 o[8];
+// dA (64 accumulator columns) * [activation > 0] -> bf16 dZ, in two steps for the backward chain: (1) dZ -> registers + tensor memory (the A operand of the next dgrad GEMM,
+// all the chain needs); (2) later, once the weight-gradient GEMM that still reads the activation tile has finished, the
+// in-place store of the dZ tile (the operand of the NEXT weight-gradient GEMM), off the critical chain.
+__device__ __forceinline__ void masked_dz_to_tmem64(uint32_t taddr, int r, const uint8_t* tile, uint32_t taddr_a, uint4* o) {
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     float v[32];
@@ -423,14 +420,13 @@ __device__ __forceinline__ void masked_dz_inplace64(uint32_t taddr, int r, uint8
       q.z = mask_pos_bf16x2(pack_bf16(p[4], p[5]), h.z); q.w = mask_pos_bf16x2(pack_bf16(p[6], p[7]), h.w);
     }
   }
-  if (taddr_a != 0xffffffffu) {                  // also the dgrad GEMM's A operand, in tensor memory
-    tmem_st16(taddr_a, reinterpret_cast<const uint32_t*>(o));
-    tmem_st16(taddr_a + 16, reinterpret_cast<const uint32_t*>(o) + 16);
-  }
-  before_store();
+  tmem_st16(taddr_a, reinterpret_cast<const uint32_t*>(o));
+  tmem_st16(taddr_a + 16, reinterpret_cast<const uint32_t*>(o) + 16);
+  tmem_st_wait();
+}
+__device__ __forceinline__ void store_tile64(int r, uint8_t* tile, const uint4* o) {
 #pragma unroll
   for (int cg = 0; cg < 8; ++cg) *reinterpret_cast<uint4*>(tile + chunk_off(r, cg, kTile)) = o[cg];
-  if (taddr_a != 0xffffffffu) tmem_st_wait();
 }
 
 // colour-net input tile: [15 features | direction encoding | (optionally a 1.0 at column 15+dv) | 0 ...]
@@ -508,9 +504,18 @@ __global__ void __launch_bounds__(256) mlp_prep_kernel(const float* __restrict__
   }
 }
 
-__device__ __forceinline__ void copy_image(uint8_t* dst, const uint8_t* __restrict__ src, int bytes) {
-  for (int e = threadIdx.x; e < bytes / 16; e += blockDim.x)
-    reinterpret_cast<uint4*>(dst)[e] = __ldg(reinterpret_cast<const uint4*>(src) + e);
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Operand image (built once per launch by mlp_prep_kernel) -> shared memory.  Every 16-byte chunk is its own cp.async, so
+// all of a thread's ~13 L2 reads are in flight together (a load/store loop pays the L2 latency once per iteration: measured
+// ~10 us of set-up per CTA).  The caller waits (cp_async_wait_all) before the CTA-wide barrier.
+__device__ __forceinline__ void copy_image_async(uint8_t* dst, const uint8_t* __restrict__ src, int bytes) {
+  for (int e = threadIdx.x; e < bytes / 16; e += blockDim.x) cp_async16(dst + e * 16, src + e * 16, true);
+  cp_async_commit();
 }
 
 constexpr int kReduceSlices = 8;
@@ -678,11 +683,6 @@ struct FwdSmem {
 };
 
 // 16-byte asynchronous global -> shared copy; valid == false zero-fills the destination
-__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // Feature pipeline of the forward kernel (contiguous fp32 rows of K0P floats): every thread copies the float4 elements
 // idx = it*128 + r of a tile into the staging buffer with cp.async while the previous tile runs its layer chain, and at
@@ -739,8 +739,12 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     for (int g = 0; g < G; ++g) mbar_init(bars + G + g, 1);             // done[g]: the group's MMAs have completed
     fence_mbar_init();
   }
-  if (image != nullptr) copy_image(sm, image, SM::off_buf);             // [weights | bias tiles | ones16], same layout
-  else stage_weights_bf16<K0P, KCP>(params, m, wsm, sm + SM::off_bias, sm + SM::off_ones16);
+  if (image != nullptr) {
+    copy_image_async(sm, image, SM::off_buf);                           // [weights | bias tiles | ones16], same layout
+    cp_async_wait_all();
+  } else {
+    stage_weights_bf16<K0P, KCP>(params, m, wsm, sm + SM::off_bias, sm + SM::off_ones16);
+  }
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -964,77 +968,85 @@ struct BwdTmem {
   static_assert(end <= 512 && g4 + 80 <= 512, "TMEM budget exceeded");
 };
 
-// ---- flush the gradient accumulators: TMEM -> registers -> a flat fp32 image of the parameter gradient in shared
-//      memory (the tile buffers are free by then; needs >= 72 KB) -> one row per CTA for the reduce kernel, or coalesced
-//      atomics with every CTA starting at a different offset.  Called by all threads of the CTA.
+// ---- flush the gradient accumulators: TMEM -> registers -> the CTA's row of the scratch (summed over CTAs by
+//      mlp_grad_reduce_kernel), or atomics into dparams when there is no scratch.  Straight from registers: accumulator
+//      row q (one lane) owns the K contiguous floats of dW[q][:], written as 16-byte stores.
+//      Written as ROLLED loops over 8-column TMEM loads on purpose: this code runs once per CTA, so its cost is its
+//      instruction fetch -- the fully unrolled version (~20 KB of SASS, cold in the instruction cache) measured ~31 k
+//      cycles per CTA, an earlier one staging through shared memory ~50 k (plus 16-way bank conflicts).
+//      The accumulators are split over the CTA's tile-group warps (a warp reads the TMEM lane quarter warp % 4).
 template <int K0P, int KCP, int WORK>
-__device__ __forceinline__ void flush_gradients(uint32_t tbase, int warp, int lane, const MlpLayout& m, float* gflat,
-                                                bool has_tiles, float* __restrict__ dparams, float* __restrict__ grad_rows) {
+__device__ __noinline__ void flush_gradients(uint32_t tbase, int warp, int lane, int ngroups, const MlpLayout& m,
+                                             bool has_tiles, float* __restrict__ dparams, float* __restrict__ grad_rows) {
   using TM = BwdTmem<K0P, KCP, WORK>;
   constexpr bool kCinOne = TM::kCinOne;
-  if (has_tiles && dparams != nullptr) {
-    if (warp < 4) {
-      const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
-      // layers 0,1,3,4 -- M = 64 layout: accumulator row q (= output neuron) lives in lane (q % 16) + 32 * (q / 16)
-      {
-        const int q = warp * 16 + lane;          // meaningful for lane < 16
-        const int gcol[4] = {TM::g0, TM::g1, TM::g3, TM::g4};
-        const int ncol[4] = {TM::n0, TM::n1, TM::n3, TM::n4};
-        const int li[4] = {0, 1, 3, 4};
+  if (dparams == nullptr) return;
+  float* row = grad_rows != nullptr ? grad_rows + (size_t)blockIdx.x * Scratch<K0P, KCP>::kRowFloats : nullptr;
+  if (!has_tiles) {
+    if (row != nullptr)
+      for (int e = threadIdx.x; e < m.total; e += blockDim.x) row[e] = 0.f;
+    return;
+  }
+  if (warp >= 4 * ngroups) return;
+  const int wg = warp >> 2, wq = warp & 3;
+  const uint32_t trow = tbase + ((uint32_t)(wq * 32) << 16);
+  auto put = [&](int idx, float v) {
+    if (row != nullptr) row[idx] = v;
+    else atomicAdd(dparams + idx, v);
+  };
+  // layers 0,1,3,4 -- M = 64 layout: accumulator row q (= output neuron) lives in lane (q % 16) + 32 * (q / 16)
+  const int q = wq * 16 + lane;                  // meaningful for lane < 16
+#pragma unroll 1
+  for (int t = 0; t < 4; ++t) {
+    if ((t % ngroups) != wg) continue;           // warp-uniform
+    const int i = t < 2 ? t : t + 1;
+    const int gcol = t == 0 ? TM::g0 : t == 1 ? TM::g1 : t == 2 ? TM::g3 : TM::g4;
+    const int ncol = t == 0 ? TM::n0 : t == 1 ? TM::n1 : t == 2 ? TM::n3 : TM::n4;      // multiples of 8
+    const int Ki = m.K[i], Ji = m.J[i], Wi = m.W[i], bi = m.b[i];
+    // bias gradient: first column of the ones group, or the planted 1.0 column of the colour-net input
+    const int bias_col = (i == 3 && kCinOne) ? Ki : (i == 0 ? K0P : (i == 3 ? KCP : 64));
+    const bool mine = lane < 16 && q < Ji;
+    const bool vec = row != nullptr && (Ki & 3) == 0 && (Wi & 3) == 0;
+    const int base = Wi + q * Ki;
+#pragma unroll 1
+    for (int c = 0; c < ncol; c += 8) {
+      float v[8];
+      tmem_ld8_wait(trow + gcol + c, v);         // executed by the whole warp (.sync.aligned)
+      if (mine) {
+        if (vec) {
+          if (c < Ki) *reinterpret_cast<float4*>(row + base + c) = make_float4(v[0], v[1], v[2], v[3]);
+          if (c + 4 < Ki) *reinterpret_cast<float4*>(row + base + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int i = li[t];
-          float gacc[80];
-          if (ncol[t] > 64) tmem_ld<80>(trow + gcol[t], gacc);         // any excess belongs to the next accumulator
-          else if (ncol[t] > 48) tmem_ld<64>(trow + gcol[t], gacc);
-          else tmem_ld<48>(trow + gcol[t], gacc);
-          // bias gradient: first column of the ones group, or the planted 1.0 column of the colour-net input
-          const int bias_col = (i == 3 && kCinOne) ? m.K[i] : (i == 0 ? K0P : (i == 3 ? KCP : 64));
-          if (lane < 16 && q < m.J[i]) {
-#pragma unroll
-            for (int k = 0; k < ncol[t]; ++k) {
-              if (k < m.K[i]) gflat[m.W[i] + q * m.K[i] + k] = gacc[k];
-              if (k == bias_col) gflat[m.b[i] + q] = gacc[k];
-            }
-          }
+          for (int j = 0; j < 8; ++j)
+            if (c + j < Ki) put(base + c + j, v[j]);
         }
-      }
-      // layers 2,5 -- M = 128 layout: accumulator row = lane; rows 0..63 = input index k, row 64 = bias gradient
-      {
-        const int row = warp * 32 + lane;
-        const int gcol[2] = {TM::g2, TM::g5};
-        const int li[2] = {2, 5};
+        if ((bias_col & ~7) == c) {
+          float bv = v[0];
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int i = li[t];
-          float gacc[16];
-          tmem_ld<16>(trow + gcol[t], gacc);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (j < m.J[i]) {
-              if (row < 64) gflat[m.W[i] + j * 64 + row] = gacc[j];
-              else if (row == 64) gflat[m.b[i] + j] = gacc[j];
-            }
-          }
+          for (int j = 1; j < 8; ++j)
+            if ((bias_col & 7) == j) bv = v[j];
+          put(bi + q, bv);
         }
       }
     }
-    __syncthreads();
-    const int total = m.total;
-    if (grad_rows != nullptr) {                  // one row per CTA, summed by mlp_grad_reduce_kernel
-      float* row = grad_rows + (size_t)blockIdx.x * Scratch<K0P, KCP>::kRowFloats;
-      for (int e = threadIdx.x; e < total; e += blockDim.x) row[e] = gflat[e];
-    } else {
-      const int rot = (int)(((long long)blockIdx.x * total) / gridDim.x);
-      for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        int idx = e + rot;
-        if (idx >= total) idx -= total;
-        atomicAdd(dparams + idx, gflat[idx]);
+  }
+  // layers 2,5 -- M = 128 layout: accumulator row = lane; rows 0..63 = input index k, row 64 = bias gradient
+  const int r = wq * 32 + lane;
+#pragma unroll 1
+  for (int t = 0; t < 2; ++t) {
+    if ((t % ngroups) != wg) continue;
+    const int i = t == 0 ? 2 : 5;
+    const int Ji = m.J[i], Wi = m.W[i], bi = m.b[i];
+    float gacc[16];
+    tmem_ld<16>(trow + (t == 0 ? TM::g2 : TM::g5), gacc);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < Ji) {
+        if (r < 64) put(Wi + j * 64 + r, gacc[j]);                       // lanes write consecutive floats: coalesced
+        else if (r == 64) put(bi + j, gacc[j]);
       }
     }
-  } else if (grad_rows != nullptr && dparams != nullptr) {
-    float* row = grad_rows + (size_t)blockIdx.x * Scratch<K0P, KCP>::kRowFloats;
-    for (int e = threadIdx.x; e < m.total; e += blockDim.x) row[e] = 0.f;
   }
 }
 
@@ -1073,8 +1085,8 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     fence_mbar_init();
   }
   if (image != nullptr) {
-    copy_image(wsm, image, WO::total);
-    copy_image(sm + SM::off_bias, image + Scratch<K0P, KCP>::off_bias_f32, 6 * 64 * 4);
+    copy_image_async(wsm, image, WO::total);                            // lands while the group regions are cleared below
+    copy_image_async(sm + SM::off_bias, image + Scratch<K0P, KCP>::off_bias_f32, 6 * 64 * 4);
   } else {
     stage_weights_bf16<K0P, KCP>(params, m, wsm, nullptr, nullptr, bias);
   }
@@ -1096,6 +1108,7 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       }
     }
   }
+  cp_async_wait_all();
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -1176,8 +1189,11 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     const uint32_t taddr_a = taddr + 64;
     const uint32_t wa = a4_of(wsm), x0a = a4_of(x0);
     uint32_t dphase = 0, bphase = 0;
-#define HBR_BSTAGE(BWD, BODY)                                              \
+#define HBR_BSTAGE(BWD, BODY) HBR_BSTAGE_T(BODY, {})
+    // forward-recompute stage; TRAIL runs between the issue and the wait (work the chain does not need)
+#define HBR_BSTAGE_T(BODY, TRAIL)                                          \
   do {                                                                     \
+    HBR_STAMP(0);                                                          \
     fence_async_smem();                                                    \
     fence_before_sync();                                                   \
     asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");             \
@@ -1186,13 +1202,50 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       if (elect_one()) {                                                   \
         BODY;                                                              \
         commit(done);                                                      \
-        if (BWD) commit(startb);                                           \
       }                                                                    \
       __syncwarp();                                                        \
     }                                                                      \
+    TRAIL;                                                                 \
     mbar_wait(done, dphase);                                               \
     dphase ^= 1;                                                           \
     fence_after_sync();                                                    \
+    HBR_STAMP(1);                                                          \
+  } while (0)
+    // Backward stage.  The A operand of its dgrad GEMM is already in tensor memory (written by the epilogue before), so
+    // the chain-critical dgrad is issued first; TRAIL is what the chain does not need -- wait for the previous
+    // weight-gradient GEMM, then the in-place store of the dZ tile this stage's weight-gradient GEMM reads -- and runs in
+    // the shadow of the dgrad; a plain arrive on startB then lets the weight-gradient warp issue behind the dgrad.
+    // (Waiting for the weight-gradient GEMM BEFORE issuing the next dgrad, as the first version did, put ~500 cycles of
+    // weight-gradient latency on every backward stage of the chain.)
+#define HBR_STAMP(j)                                                       \
+  do {                                                                     \
+    if (TRACE && blockIdx.x == 0 && threadIdx.x == 0 && tgi < 12) trace[tgi * 80 + stamp_i++] = clock64(); \
+  } while (0)
+#define HBR_BSTAGE_BWD(BODY, TRAIL)                                        \
+  do {                                                                     \
+    HBR_STAMP(0);                                                          \
+    fence_before_sync();                                                   \
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");             \
+    HBR_STAMP(1);                                                          \
+    if (issuer) {                                                          \
+      fence_after_sync();                                                  \
+      if (elect_one()) {                                                   \
+        BODY;                                                              \
+        commit(done);                                                      \
+      }                                                                    \
+      __syncwarp();                                                        \
+    }                                                                      \
+    HBR_STAMP(2);                                                          \
+    TRAIL;                                                                 \
+    HBR_STAMP(3);                                                          \
+    fence_async_smem();                                                    \
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");             \
+    if (r == 0) mbar_arrive(startb);                                       \
+    HBR_STAMP(4);                                                          \
+    mbar_wait(done, dphase);                                               \
+    dphase ^= 1;                                                           \
+    fence_after_sync();                                                    \
+    HBR_STAMP(5);                                                          \
   } while (0)
     // weight-gradient GEMM of the stage has finished reading its tiles (they are about to be overwritten in place)
 #define HBR_WAIT_B()           \
@@ -1204,7 +1257,10 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     const bool dvec_ok = dfeat != nullptr && in0 == K0P && dfeat_stride == K0P && ((uintptr_t)dfeat & 15) == 0 && K0P <= 32;
     int tgi = 0;
     (void)tgi;
-    for (long long tile = (long long)g * gridDim.x + blockIdx.x; tile < ntiles; tile += nslots) {
+    for (long long tile = (long long)g * gridDim.x + blockIdx.x; tile < ntiles; tile += nslots, ++tgi) {
+      int stamp_i = 0;
+      (void)stamp_i;
+      HBR_STAMP(0);                              // tile start
       const long long gp = tile * kTile + r;
       const bool valid = gp < n;
       const long long dir_row = valid ? gp / dir_group : 0;
@@ -1267,41 +1323,55 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         dz16[2] = go.z * (fo.z > 0.f ? 1.f : fo.z + 1.f);
         store_dz16_both(dz16, r, dzs, taddr_a);
       }
-      HBR_BSTAGE(true, issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w5 / 16, 16, 64));                 // col_model.4: work = dA(c2)
-      masked_dz_inplace64(taddr, r, c2, [&] { HBR_WAIT_B(); }, taddr_a);
-      HBR_BSTAGE(true, issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w4 / 16, 64, 64));                 // col_model.2: work = dA(c1)
-      masked_dz_inplace64(taddr, r, c1, [&] { HBR_WAIT_B(); }, taddr_a);
-      HBR_BSTAGE(true, issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w3 / 16, 64, KCP));                // col_model.0: work[0,KCP) = d(cin)
-      HBR_WAIT_B();
+      uint4 dzt[8];                              // the dZ tile formed by the last epilogue, stored to shared memory one stage later
+      HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w5 / 16, 16, 64), {});               // col_model.4: work = dA(c2)
+      masked_dz_to_tmem64(taddr, r, c2, taddr_a, dzt);
+      HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w4 / 16, 64, 64),                    // col_model.2: work = dA(c1)
+                     { HBR_WAIT_B(); store_tile64(r, c2, dzt); });
+      masked_dz_to_tmem64(taddr, r, c1, taddr_a, dzt);
+      HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w3 / 16, 64, KCP),                   // col_model.0: work[0,KCP) = d(cin)
+                     { HBR_WAIT_B(); store_tile64(r, c1, dzt); });
+      float dd[KCP - kFeat];                     // d(direction encoding), reduced into ddirs off the chain
+      uint32_t dzp[8];
       {
         float dc[KCP], dz16[16];
         tmem_ld<KCP>(taddr, dc);
         dz16[0] = go.w * (fo.w > 0.f ? 1.f : 0.01f);                    // LeakyReLU' from the saved density
 #pragma unroll
         for (int k = 0; k < kFeat; ++k) dz16[1 + k] = dc[k];
-        store_dz16_both(dz16, r, dzs, taddr_a);
+#pragma unroll
+        for (int k = kFeat; k < KCP; ++k) dd[k - kFeat] = dc[k];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dzp[q] = pack_bf16(dz16[2 * q], dz16[2 * q + 1]);
+        tmem_st8(taddr_a, dzp);
+        tmem_st_wait();
+      }
+      HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w2 / 16, 16, 64), {                  // sig_model.4: work = dA(h2)
+        HBR_WAIT_B();                            // the 16-wide dZ tile may alias the padding of the colour-net input tile
+        *reinterpret_cast<uint4*>(dzs + chunk_off(r, 0, kTile)) = make_uint4(dzp[0], dzp[1], dzp[2], dzp[3]);
+        *reinterpret_cast<uint4*>(dzs + chunk_off(r, 1, kTile)) = make_uint4(dzp[4], dzp[5], dzp[6], dzp[7]);
         if (ddirs != nullptr) {
           // rows of one warp usually belong to one ray: reduce over the warp first, one atomic per column
           const long long row0 = __shfl_sync(kFull, dir_row, 0);
           const bool uniform = __all_sync(kFull, dir_row == row0 && valid);
-#pragma unroll
-          for (int k = kFeat; k < KCP; ++k) {
+          _Pragma("unroll") for (int k = kFeat; k < KCP; ++k) {
             if (k < kFeat + dv) {
               if (uniform) {
-                const float s = warp_sum(dc[k]);
-                if (lane == 0) atomicAdd(ddirs + row0 * dv + (k - kFeat), s);
+                const float sdd = warp_sum(dd[k - kFeat]);
+                if (lane == 0) atomicAdd(ddirs + row0 * dv + (k - kFeat), sdd);
               } else if (valid) {
-                atomicAdd(ddirs + dir_row * dv + (k - kFeat), dc[k]);
+                atomicAdd(ddirs + dir_row * dv + (k - kFeat), dd[k - kFeat]);
               }
             }
           }
         }
-      }
-      HBR_BSTAGE(true, issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w2 / 16, 16, 64));                 // sig_model.4: work = dA(h2)
-      masked_dz_inplace64(taddr, r, h2, [&] { HBR_WAIT_B(); }, taddr_a);
-      HBR_BSTAGE(true, issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w1 / 16, 64, 64));                 // sig_model.2: work = dA(h1)
-      masked_dz_inplace64(taddr, r, h1, [&] { HBR_WAIT_B(); }, taddr_a);
-      HBR_BSTAGE(true, issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w0 / 16, 64, K0P));                // sig_model.0: work[0,K0P) = d(feat)
+      });
+      masked_dz_to_tmem64(taddr, r, h2, taddr_a, dzt);
+      HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w1 / 16, 64, 64),                    // sig_model.2: work = dA(h1)
+                     { HBR_WAIT_B(); store_tile64(r, h2, dzt); });
+      masked_dz_to_tmem64(taddr, r, h1, taddr_a, dzt);
+      HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w0 / 16, 64, K0P),                   // sig_model.0: work[0,K0P) = d(feat)
+                     { HBR_WAIT_B(); store_tile64(r, h1, dzt); });
       if (ENC) {
         float df[K0P];
         tmem_ld<K0P>(taddr, df);
@@ -1330,16 +1400,18 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
             if (k < in0) dfeat[gp * dfeat_stride + k] = df[k];
         }
       }
+      HBR_STAMP(0);                              // d(feat) written
       HBR_WAIT_B();                              // x0 / h1 are rewritten by the next tile
+      HBR_STAMP(0);                              // tile end
     }
+    if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2004] = clock64();
   }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2002] = clock64();
 
-  flush_gradients<K0P, KCP, 2 * kGrpCols>(tbase, warp, lane, m, reinterpret_cast<float*>(sm + SM::off_grp), cta_tiles > 0, dparams,
-                            grad_rows);
+  flush_gradients<K0P, KCP, 2 * kGrpCols>(tbase, warp, lane, G, m, cta_tiles > 0, dparams, grad_rows);
   fence_before_sync();
   __syncthreads();
   if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2003] = clock64();
@@ -1379,13 +1451,16 @@ extern "C" int hbr_debug_umma_chain_bench(int kind, int reps, int nacc, long lon
 
 extern "C" int hbr_debug_mlp_trace_bwd(const float* feat, const float* dirs, int64_t dir_group, int64_t n,
                                        const float* params, const float* out, const float* dout, float* dfeat,
-                                       float* dparams, long long* trace, void* stream) {
+                                       float* dparams, void* scratch, long long* trace, void* stream) {
+  using SC = Scratch<32, 48>;
   constexpr int smem = BwdSmem<32, 48, 2>::total;
   HBR_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel<32, 48, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), 2), sm_count());
+  uint8_t* sc = static_cast<uint8_t*>(scratch);                        // as hbr_mlp_bwd_tc: operand image + gradient rows
+  if (sc != nullptr) mlp_prep_kernel<32, 48><<<kPrepCtas, 256, 0, as_stream(stream)>>>(params, 32, 24, sc);
   mlp_bwd_tc_kernel<32, 48, 2, true><<<grid, 2 * kTile + 32, smem, as_stream(stream)>>>(
-      feat, 32, dirs, dir_group, n, params, 32, 24, out, dout, dfeat, 32, nullptr, dparams, nullptr, nullptr, trace, EncArgs{},
-      HashGeom{});
+      feat, 32, dirs, dir_group, n, params, 32, 24, out, dout, dfeat, 32, nullptr, dparams, sc,
+      sc != nullptr ? reinterpret_cast<float*>(sc + SC::off_grad) : nullptr, trace, EncArgs{}, HashGeom{});
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }

@@ -148,8 +148,8 @@ int hbr_debug_mlp_trace(const float* feat, const float* dirs, int64_t dir_group,
 /* Same probe for the backward kernel: per tile 1 + 3*11 stamps of tile group 0, (ready-seen, committed) pairs of the
  * issuing warp for that group at trace[1024..]. */
 int hbr_debug_mlp_trace_bwd(const float* feat, const float* dirs, int64_t dir_group, int64_t n, const float* params,
-                            const float* out, const float* dout, float* dfeat, float* dparams, long long* trace,
-                            void* stream);
+                            const float* out, const float* dout, float* dfeat, float* dparams, void* scratch,
+                            long long* trace, void* stream);
 
 /* ---- a9: sample positions, vol_renderer.py:165 / helper.py:48 -------------------------------------
  * pts[r,s,:] = o[r,:] + d[r,:]*t  (separate multiply and add).  t is (S) shared (t_ray_stride = 0)
