@@ -407,18 +407,15 @@ __device__ __forceinline__ void relu_epilogue64(uint32_t taddr, int r, uint8_t* 
 // all the chain needs); (2) later, once the weight-gradient GEMM that still reads the activation tile has finished, the
 // in-place store of the dZ tile (the operand of the NEXT weight-gradient GEMM), off the critical chain.
 __device__ __forceinline__ void masked_dz_to_tmem64(uint32_t taddr, int r, const uint8_t* tile, uint32_t taddr_a, uint4* o) {
+  float v[64];
+  tmem_ld<64>(taddr, v);                         // all four loads in flight, one wait
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    float v[32];
-    tmem_ld<32>(taddr + half * 32, v);
-#pragma unroll
-    for (int cg = 0; cg < 4; ++cg) {
-      const uint4 h = *reinterpret_cast<const uint4*>(tile + chunk_off(r, half * 4 + cg, kTile));
-      const float* p = v + cg * 8;
-      uint4& q = o[half * 4 + cg];
-      q.x = mask_pos_bf16x2(pack_bf16(p[0], p[1]), h.x); q.y = mask_pos_bf16x2(pack_bf16(p[2], p[3]), h.y);
-      q.z = mask_pos_bf16x2(pack_bf16(p[4], p[5]), h.z); q.w = mask_pos_bf16x2(pack_bf16(p[6], p[7]), h.w);
-    }
+  for (int cg = 0; cg < 8; ++cg) {
+    const uint4 h = *reinterpret_cast<const uint4*>(tile + chunk_off(r, cg, kTile));
+    const float* p = v + cg * 8;
+    uint4& q = o[cg];
+    q.x = mask_pos_bf16x2(pack_bf16(p[0], p[1]), h.x); q.y = mask_pos_bf16x2(pack_bf16(p[2], p[3]), h.y);
+    q.z = mask_pos_bf16x2(pack_bf16(p[4], p[5]), h.z); q.w = mask_pos_bf16x2(pack_bf16(p[6], p[7]), h.w);
   }
   tmem_st16(taddr_a, reinterpret_cast<const uint32_t*>(o));
   tmem_st16(taddr_a + 16, reinterpret_cast<const uint32_t*>(o) + 16);
@@ -883,27 +880,27 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kCg = kTile * 16;                                        // bytes of one 8-column group of a 128-row tile
 
-// bias + ReLU on 64 accumulator columns -> bf16 activation tile (the backward kernel adds the bias here: its two tile
-// groups leave the CUDA cores mostly idle, while every MMA saved shortens the issue-bound critical path)
-__device__ __forceinline__ void relu_bias_epilogue64(uint32_t taddr, const float* bias, int r, uint8_t* tile,
-                                                     uint32_t taddr_a) {
+// bias + ReLU on 64 accumulator columns -> bf16 activations in registers (o[8], one 16-byte chunk per column group) and,
+// with a valid taddr_a, in tensor memory as the next layer's A operand -- all the chain needs.  The caller stores o[] to
+// the activation tile in shared memory (the weight-gradient operand) behind the next GEMM's issue (store_tile64).
+// (The backward kernel adds the bias here: its two tile groups leave the CUDA cores mostly idle, while every MMA saved
+// shortens the issue-bound critical path.)
+__device__ __forceinline__ void relu_bias_to_tmem64(uint32_t taddr, const float* bias, uint32_t taddr_a, uint4* o) {
+  float v[64];
+  tmem_ld<64>(taddr, v);                         // all four loads in flight, one wait
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    float v[32];
-    tmem_ld<32>(taddr + half * 32, v);
-    uint4 o[4];
-#pragma unroll
-    for (int cg = 0; cg < 4; ++cg) {
-      const float4 b0 = *reinterpret_cast<const float4*>(bias + half * 32 + cg * 8);
-      const float4 b1 = *reinterpret_cast<const float4*>(bias + half * 32 + cg * 8 + 4);
-      const float* p = v + cg * 8;
-      o[cg].x = pack_bf16_relu(p[0] + b0.x, p[1] + b0.y); o[cg].y = pack_bf16_relu(p[2] + b0.z, p[3] + b0.w);
-      o[cg].z = pack_bf16_relu(p[4] + b1.x, p[5] + b1.y); o[cg].w = pack_bf16_relu(p[6] + b1.z, p[7] + b1.w);
-      *reinterpret_cast<uint4*>(tile + chunk_off(r, half * 4 + cg, kTile)) = o[cg];     // weight-gradient operand
-    }
-    if (taddr_a != 0xffffffffu) tmem_st16(taddr_a + half * 16, reinterpret_cast<const uint32_t*>(o));   // next layer's A operand
+  for (int cg = 0; cg < 8; ++cg) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + cg * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + cg * 8 + 4);
+    const float* p = v + cg * 8;
+    o[cg].x = pack_bf16_relu(p[0] + b0.x, p[1] + b0.y); o[cg].y = pack_bf16_relu(p[2] + b0.z, p[3] + b0.w);
+    o[cg].z = pack_bf16_relu(p[4] + b1.x, p[5] + b1.y); o[cg].w = pack_bf16_relu(p[6] + b1.z, p[7] + b1.w);
   }
-  if (taddr_a != 0xffffffffu) tmem_st_wait();
+  if (taddr_a != 0xffffffffu) {
+    tmem_st16(taddr_a, reinterpret_cast<const uint32_t*>(o));
+    tmem_st16(taddr_a + 16, reinterpret_cast<const uint32_t*>(o) + 16);
+    tmem_st_wait();
+  }
 }
 
 // 16-wide dZ (the two 16-output layers): bf16 into the shared-memory tile (weight-gradient operand) and into tensor
@@ -1257,6 +1254,12 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     const bool dvec_ok = dfeat != nullptr && in0 == K0P && dfeat_stride == K0P && ((uintptr_t)dfeat & 15) == 0 && K0P <= 32;
     int tgi = 0;
     (void)tgi;
+    // The next tile's fp32 feature rows travel into the (by then dead) c2 tile with cp.async during the last backward
+    // stages and are converted from shared memory at the start of the tile: a tile that begins by waiting for its own
+    // global loads spent ~2 300 cycles (15 % of its chain) there.  Contiguous K0P == 32 layout only (16 KB <= the tile).
+    constexpr bool kStage = K0P == 32 && !ENC;
+    const bool stage_ok = kStage && vec_ok;
+    bool staged = false;
     for (long long tile = (long long)g * gridDim.x + blockIdx.x; tile < ntiles; tile += nslots, ++tgi) {
       int stamp_i = 0;
       (void)stamp_i;
@@ -1275,22 +1278,28 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       if (ENC) {
         if (valid) { pt[0] = __ldg(enc.x + gp * 3 + 0); pt[1] = __ldg(enc.x + gp * 3 + 1); pt[2] = __ldg(enc.x + gp * 3 + 2); }
         load_feat16_row(enc, gp, n, r, x0);
+      } else if (staged) {
+        cp_async_wait_all();
+        convert_staged_features<K0P>(c2, r, x0);   // every thread converts exactly the elements it copied itself
       } else {
         load_features<K0P>(feat, feat_stride, tile * kTile, n, in0, vec_ok, r, x0);
       }
       if ((tile + nslots) * kTile + r < n) {
         if (ENC) prefetch_l2(enc.feat16 + ((tile + nslots) * kTile + r) * 32);
-        else prefetch_l2(feat + ((tile + nslots) * kTile + r) * feat_stride);
+        else if (!stage_ok) prefetch_l2(feat + ((tile + nslots) * kTile + r) * feat_stride);
         if ((r & 7) == 0) {
           prefetch_l2(out + ((tile + nslots) * kTile + r) * 4);
           prefetch_l2(dout + ((tile + nslots) * kTile + r) * 4);
         }
       }
+      uint4 dzt[8];                              // activation / dZ tile formed by the last epilogue, stored one stage later
       HBR_BSTAGE(false, issue_fwd(tgrp, x0a, wa + WO::w0 / 16, 64, K0P));                       // F0 (x0 from shared memory)
-      relu_bias_epilogue64(taddr, bias + 0, r, h1, taddr_a);
-      HBR_BSTAGE(false, issue_fwd_ts(tgrp, tgrp_a, wa + WO::w1 / 16, 64, 64, false));           // F1
-      relu_bias_epilogue64(taddr, bias + 64, r, h2, taddr_a);
-      HBR_BSTAGE(false, issue_fwd_ts(tgrp, tgrp_a, wa + WO::w2 / 16, 16, 64, false));           // F2
+      relu_bias_to_tmem64(taddr, bias + 0, taddr_a, dzt);
+      HBR_BSTAGE_T(issue_fwd_ts(tgrp, tgrp_a, wa + WO::w1 / 16, 64, 64, false),                 // F1
+                   { store_tile64(r, h1, dzt); });
+      relu_bias_to_tmem64(taddr, bias + 64, taddr_a, dzt);
+      HBR_BSTAGE_T(issue_fwd_ts(tgrp, tgrp_a, wa + WO::w2 / 16, 16, 64, false),                 // F2
+                   { store_tile64(r, h2, dzt); });
       {
         float o16[16];
         tmem_ld<16>(taddr, o16);
@@ -1310,9 +1319,10 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         tmem_st_wait();
       }
       HBR_BSTAGE(false, issue_fwd_ts(tgrp, tgrp_a, wa + WO::w3 / 16, 64, KCP, false));          // F3
-      relu_bias_epilogue64(taddr, bias + 192, r, c1, taddr_a);
-      HBR_BSTAGE(false, issue_fwd_ts(tgrp, tgrp_a, wa + WO::w4 / 16, 64, 64, false));           // F4
-      relu_bias_epilogue64(taddr, bias + 256, r, c2, 0xffffffffu);
+      relu_bias_to_tmem64(taddr, bias + 192, taddr_a, dzt);
+      HBR_BSTAGE_T(issue_fwd_ts(tgrp, tgrp_a, wa + WO::w4 / 16, 64, 64, false),                 // F4
+                   { store_tile64(r, c1, dzt); });
+      relu_bias_to_tmem64(taddr, bias + 256, 0xffffffffu, dzt);         // c2 feeds no forward GEMM here
       {
         // d(rgb_pre) = g * ELU'(pre), with ELU'(pre) = pre > 0 ? 1 : exp(pre) = elu(pre) + 1 from the saved output
         float dz16[16];
@@ -1323,14 +1333,18 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         dz16[2] = go.z * (fo.z > 0.f ? 1.f : fo.z + 1.f);
         store_dz16_both(dz16, r, dzs, taddr_a);
       }
-      uint4 dzt[8];                              // the dZ tile formed by the last epilogue, stored to shared memory one stage later
-      HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w5 / 16, 16, 64), {});               // col_model.4: work = dA(c2)
+      HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w5 / 16, 16, 64),                    // col_model.4: work = dA(c2)
+                     { store_tile64(r, c2, dzt); });   // the c2 activations, before this stage's weight-gradient GEMM starts
       masked_dz_to_tmem64(taddr, r, c2, taddr_a, dzt);
       HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w4 / 16, 64, 64),                    // col_model.2: work = dA(c1)
                      { HBR_WAIT_B(); store_tile64(r, c2, dzt); });
       masked_dz_to_tmem64(taddr, r, c1, taddr_a, dzt);
-      HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w3 / 16, 64, KCP),                   // col_model.0: work[0,KCP) = d(cin)
-                     { HBR_WAIT_B(); store_tile64(r, c1, dzt); });
+      staged = stage_ok && tile + nslots < ntiles;
+      HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w3 / 16, 64, KCP), {                 // col_model.0: work[0,KCP) = d(cin)
+        HBR_WAIT_B();                            // the weight-gradient GEMM reading c2 (dZ) and c1 has finished: c2 is dead
+        store_tile64(r, c1, dzt);
+        if (staged) stage_features_async<K0P>(feat, (tile + nslots) * kTile, n, r, c2);
+      });
       float dd[KCP - kFeat];                     // d(direction encoding), reduced into ddirs off the chain
       uint32_t dzp[8];
       {
@@ -1381,7 +1395,8 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         tmem_ld<K0P>(taddr, df);
         if (dvec_ok) {
           // rows -> the (dead) h2 tile as fp32 with an XOR swizzle on the 16-byte chunk index, then lane-contiguous
-          // float4 stores of the tile's contiguous 128*K0P*4-byte block of dfeat
+          // float4 stores of the tile's contiguous 128*K0P*4-byte block of dfeat (measured: eight 16-byte stores per
+          // thread straight from registers, 32 partial sectors per instruction, are ~400 cycles slower per tile)
           constexpr int kQ = K0P / 4;
           float4* stg = reinterpret_cast<float4*>(h2);
 #pragma unroll
