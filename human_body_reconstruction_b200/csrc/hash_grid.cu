@@ -58,8 +58,10 @@ __device__ __forceinline__ void load_point(const XT* __restrict__ x, long long g
 // PAIR: 0 = eight 8-byte gathers per level (default); 1 = (x, x+1) corner pairs of an even x share one aligned 16-byte
 // slot: one LDG.128 per pair, the odd-x second load predicated.  Measured at 524 288 points, T = 2^19, cold L2: PAIR 0
 // with 4 levels unrolled (32 gathers in flight per thread) 104 us, 2 levels 109 us, 8 levels 107 us; PAIR 1 124 us
-// (the 16-byte loads double the L1 traffic of the odd-x half) -- pairing only pays in the backward, where it halves
-// the number of reductions.
+// (the 16-byte loads double the L1 traffic of the odd-x half); a mixed variant (one 16-byte gather for lanes with an even
+// x, two 8-byte gathers for the others, i.e. 25 % fewer L1 wavefronts on the hashed levels) 112 us against 107 us in the
+// same step -- pairing only pays in the backward, where it halves the number of reductions.  ncu: the kernel runs at
+// 83 % of the L1TEX wavefront peak (l1tex__data_pipe_lsu_wavefronts), 49 % of L2 throughput, 9 % of HBM.
 template <int F, bool POW2, typename XT, int PAIR = 0, int UNR = 4>
 __global__ void __launch_bounds__(kHashThreads)
 hash_fwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__ table, float* __restrict__ y,
