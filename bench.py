@@ -123,13 +123,32 @@ def make_batches(c2w, K, H, W, n_rays, n_batches, seed):
 
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the measurement: an NVML polling thread (2 ms period -- the whole timed region
+    of the default run lasts well under a second, so nvidia-smi's 100-200 ms loop alone yields a handful of samples),
+    with the profiling recipe's `nvidia-smi --query-gpu=... -lms` loop as the fallback when NVML cannot be loaded."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    MASKS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.handle, self.samples, self.stop_flag, self.thread = None, None, [], False, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -137,11 +156,36 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n, h = self.nvml, self.handle
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.samples.append((n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM), int(reasons_fn(h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            if not self.samples:
+                return None
+            sm = sorted(c for c, _ in self.samples)
+            bits = 0
+            for _, r in self.samples:
+                bits |= r
+            try:
+                mx = self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)
+            except Exception:
+                mx = sm[-1]
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": [nm for nm, m in self.MASKS if bits & m],
+                    "samples": len(sm), "source": "nvml, 2 ms period, median over the measurement"}
         if self.proc is None:
             return None
         self.proc.terminate()
@@ -151,7 +195,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k] == "Active" for r in self.rows)]
         mx = max(int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit())
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def measured_peaks():

@@ -85,6 +85,11 @@ class GraphedStep:
         self.gt.copy_(gt, non_blocking=non_blocking)
 
     def capture(self):
+        # the parameters' AccumulateGrad nodes may predate the capture stream (eager steps before capture): harmless
+        # here (every step of the graph runs on the capture stream), so silence torch's per-backward warning about it
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
