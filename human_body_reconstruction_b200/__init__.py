@@ -12,8 +12,8 @@ from .encoder import PositionalEncoder
 from .hash_encoding import HashEncoder
 from .test_hash import MLP_3D
 from .vol_renderer import Volume_Renderer
-from . import dist, graph, helper, mesh, ops, optim, peer, rays  # noqa: F401
+from . import dist, formats, graph, helper, mesh, ops, optim, peer, rays  # noqa: F401
 from .rays import DeviceRayDataset
 
-__all__ = ["HashEncoder", "PositionalEncoder", "MLP_3D", "Volume_Renderer", "DeviceRayDataset", "dist", "graph", "helper", "mesh",
+__all__ = ["HashEncoder", "PositionalEncoder", "MLP_3D", "Volume_Renderer", "DeviceRayDataset", "dist", "formats", "graph", "helper", "mesh",
            "ops", "optim", "peer", "rays"]

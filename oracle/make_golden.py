@@ -233,6 +233,56 @@ def gold_rays(ref):
     npz("rays.npz", H=H, W=W, K=K, c2w=c2w, rays_o=o, rays_d=d, dir_norm=n, max_bound=mx, min_bound=mn)
 
 
+def gold_formats():
+    """dataset.py / dataset_new.py readers of the reference on two tiny scenes written here (tests/golden/scene_*), plus
+    the int64 K the trainer builds from them (train_hash2.py:67-72)."""
+    import importlib
+    import json
+    import cv2
+    rng = np.random.default_rng(4)
+    H, W, V = 5, 6, 2
+    kw = {}
+    for flavour in ("blender", "new"):
+        root = os.path.join(OUT, "scene_" + flavour)
+        os.makedirs(os.path.join(root, "train"), exist_ok=True)
+        frames = []
+        for v in range(V):
+            img = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+            name = f"r_{v}"
+            cv2.imwrite(os.path.join(root, "train", name + ".png"), img)          # cv2 writes BGR
+            m = np.eye(4)
+            m[:3, :4] = rng.normal(size=(3, 4))
+            fr = {"file_path": f"./train/{name}" + (".png" if flavour == "new" else ""), "transform_matrix": m.tolist()}
+            fr["sharpness" if flavour == "new" else "rotation"] = float(rng.uniform())
+            frames.append(fr)
+        meta = {"camera_angle_x": 0.6911112070083618, "frames": frames}
+        if flavour == "new":
+            meta.update(w=W, h=H, fl_x=7.9, fl_y=8.2, cx=3.4, cy=2.6)
+        jpath = os.path.join(root, "transforms_train.json")
+        with open(jpath, "w") as f:
+            json.dump(meta, f)
+        sys.path.insert(0, ref_loader.REF_DIR)
+        try:
+            mod = importlib.import_module("dataset_new" if flavour == "new" else "dataset")
+        finally:
+            sys.path.remove(ref_loader.REF_DIR)
+        ds = (mod.NeRF_DATA_NEW if flavour == "new" else mod.NeRF_DATA)(json_path=jpath)
+        items = [ds[i] for i in range(len(ds))]
+        K = torch.from_numpy(np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1]]))               # train_hash2.py:67-72
+        K[0, 0] = ds.focal1
+        K[1, 1] = ds.focal2
+        K[0, 2] = ds.cx
+        K[1, 2] = ds.cy
+        pre = flavour + "__"
+        kw.update({pre + "H": int(ds.H), pre + "W": int(ds.W), pre + "focal1": float(ds.focal1), pre + "focal2": float(ds.focal2),
+                   pre + "cx": float(ds.cx), pre + "cy": float(ds.cy), pre + "K": K,
+                   pre + "images": torch.stack([it[0] for it in items]), pre + "c2w": torch.stack([it[1] for it in items]),
+                   pre + "extra": np.array([it[2] for it in items], dtype=np.float64)})
+        for m in ("dataset", "dataset_new"):
+            sys.modules.pop(m, None)
+    npz("formats.npz", **kw)
+
+
 if __name__ == "__main__":
     ref = ref_loader.load()
     gold_hash(ref)
@@ -241,3 +291,4 @@ if __name__ == "__main__":
     gold_volrender(ref)
     gold_grid(ref)
     gold_rays(ref)
+    gold_formats()

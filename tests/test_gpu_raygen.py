@@ -120,3 +120,24 @@ def test_graphed_step_draws_its_own_batches():
     losses = [float(gs().item()) for _ in range(4)]
     assert all(np.isfinite(losses)) and len(set(losses)) > 1                   # a different batch every replay
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in params)
+
+
+def test_scene_on_disk_to_device_batches():
+    """formats.load_scene -> DeviceRayDataset: the batches equal the reference's data path (dataset.py reader ->
+    get_od with the truncated int64 K -> flattened TensorDataset rows, train_hash2.py:74-96) for the committed scene."""
+    import os
+    import human_body_reconstruction_b200 as h
+    from conftest import GOLDEN
+    g = load_golden("formats.npz")
+    images, c2w, K, meta = h.formats.load_scene(os.path.join(GOLDEN, "scene_blender", "transforms_train.json"))
+    H, W = int(meta["H"]), int(meta["W"])
+    ds = h.DeviceRayDataset(images, c2w, K, device=DEV, batch_size=16, shuffle=False)
+    o_all, d_all, n_all = port.get_od(H, W, K, c2w)
+    gts = g["blender__images"].permute(0, 2, 3, 1).reshape(-1, 3)                     # train_hash2.py:81-82
+    rows = [b for b in ds]
+    o = torch.cat([b[0] for b in rows]).cpu()
+    d = torch.cat([b[1] for b in rows]).cpu()
+    n = torch.cat([b[2] for b in rows]).cpu()
+    gt = torch.cat([b[3] for b in rows]).cpu()
+    assert torch.equal(o, o_all.reshape(-1, 3)) and torch.equal(gt, gts)
+    assert _close(d, d_all.reshape(-1, 3)) and _close(n, n_all.reshape(-1, 1))
