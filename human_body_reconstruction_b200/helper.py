@@ -65,15 +65,35 @@ def hierarchical_sampling(rays_o, rays_d, z_vals, weights, n_samples: int, tn, t
 
 def calc_color(t, rgb, sigma, dir_norm, use_sdf: bool = False, var_model=None, rays=None, model=None, encoder=None,
                device: str = "cuda"):
-    """helper.py:53-107, NeRF mode.  Returns (Cr (R,3), wts (R,S,1), None).  fp16 inputs (autocast) are promoted
+    """helper.py:53-107.  NeRF mode returns (Cr (R,3), wts (R,S,1), None); SDF mode (use_sdf) also the eikonal norms.  fp16 inputs (autocast) are promoted
     to fp32 like the reference's mixed-dtype arithmetic.  The -10 clamp (:76) is applied inside the kernel; the
     caller's sigma tensor is left untouched."""
-    if use_sdf:
-        raise NotImplementedError("SDF compositing (helper.py:80-89) is not implemented on the CUDA path yet")
     if not sigma.is_cuda:
         raise RuntimeError("calc_color needs CUDA tensors (there is no CPU fallback)")
+    if use_sdf:
+        return _calc_color_sdf(t, rgb, sigma, var_model, rays, model, encoder)
     Cr, w = ops.CompositeSplit.apply(rgb, sigma, t, dir_norm, None)
     return Cr, w[..., None], None
+
+
+def _calc_color_sdf(t, rgb, sigma, var_model, rays, model, encoder):
+    """helper.py:76-89,102-107, SDF mode: alpha_i = relu(1 - phi(s_{i+1}) / phi(s_i)) with phi = var_model (a sigmoid of
+    learnable sharpness), transmittance = exclusive cumprod(1 - alpha), plus the eikonal term |grad sdf| from central
+    differences at the sample positions.  Elementwise torch ops on the device around the path's kernels (the 6 extra
+    encoder + sigma-net passes of the normals run through hbr_hash_encode_* / hbr_mlp_*_f32); like the reference it
+    needs `rays` (so hierarchical=True, whose fine pass passes none, fails the same way: AttributeError on None.device)."""
+    sigma[sigma < -10] = -10                                             # :76 (in place, as the reference)
+    phi = var_model(sigma)
+    alpha = torch.zeros_like(sigma)
+    alpha[..., :-1] = 1 - phi[..., 1:] / phi[..., :-1]
+    alpha = torch.nn.functional.relu(alpha)
+    T = cumprod_exclusive(1 - alpha)
+    mlp = getattr(model, "module", model)                                # the reference reaches through nn.DataParallel (:87)
+    grads = mlp.finite_difference_normals_approximator(rays, encoder=encoder)
+    norm = eikonal_value(grads)
+    wts = T[:, :, None] * alpha[:, :, None]
+    Cr = torch.sum(T[:, :, None] * alpha[:, :, None] * rgb, dim=-2)
+    return Cr, wts, norm
 
 
 def get_od(H, W, K, c2w: torch.Tensor, find_inv: Optional[bool] = False):

@@ -146,28 +146,66 @@ class MLP_3D(nn.Module):
     def _check_native(self):
         if not self._native:
             raise NotImplementedError("native MLP_3D supports num_sig=2, num_col=2, h_size=64 (the reference's configuration)")
-        if self.use_sdf:
-            raise NotImplementedError("use_sdf=True (SDF mode, SURVEY 8f row 4) is not implemented on the CUDA path yet")
 
     # -- evaluation entry used by Volume_Renderer (one direction row per ray) ---------------------------------
-    def field(self, feat, dirs_enc, dir_group, use_tc=None):
+    def field(self, feat, dirs_enc, dir_group, use_tc=None, raw=False):
+        """(N,4) [rgb, density].  With use_sdf the density column is 2*sigmoid(pre-activation) - 1 (test_hash.py:59-60)
+        unless raw=True."""
         self._check_native()
         if use_tc is None:
             use_tc = torch.is_autocast_enabled()
         use_tc = bool(use_tc) and ops.HAS_TC
-        return _MlpFn.apply(feat, dirs_enc, int(dir_group), self, bool(use_tc), *self._ordered())
+        out = _MlpFn.apply(feat, dirs_enc, int(dir_group), self, bool(use_tc), *self._ordered())
+        if self.use_sdf and not raw:
+            out = torch.cat((out[:, :3], self._sdf_from_density(out[:, 3:4])), dim=-1)
+        return out
+
+    # -- SDF mode (test_hash.py:59-60,78-105; SURVEY 8f row 4) ------------------------------------------------
+    # Composed from the path's kernels plus elementwise torch ops on the device: the kernels end the density head with
+    # LeakyReLU(0.01), which is invertible, so the pre-activation the SDF head needs is recovered as d > 0 ? d : 100 d
+    # (1 ulp from the true pre-activation; autograd through kernel + inverse has slope exactly 1 or 0.01 * 100).
+    @staticmethod
+    def _sdf_from_density(density: torch.Tensor) -> torch.Tensor:
+        raw = torch.where(density > 0, density, density * 100.0)
+        return 2 * torch.sigmoid(raw) - 1                                # test_hash.py:60
+
+    def _density(self, x) -> torch.Tensor:
+        """LeakyReLU(dens_vec[:, 0:1]) of the sigma net for (N, L*F+E) features, with autograd when anything needs it."""
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            z = torch.zeros((x.shape[0], self.d_view), device=x.device)
+            return self.field(x, z, 1, use_tc=False, raw=True)[:, 3:4]
+        density, _ = ops.mlp_fwd_f32(x.float().contiguous(), None, 1, self._flat_params(), self._dims(), keep_act=False)
+        return density
+
+    def forward_sdf(self, x, encoder=None):
+        """test_hash.py:78-84: signed-distance-like value 2*sigmoid(.) - 1 in (-1, 1); fp32 kernels (the finite
+        differences below need more than bf16)."""
+        if encoder is not None:
+            x = encoder(x)
+        return self._sdf_from_density(self._density(x))
+
+    def finite_difference_normals_approximator(self, x, epsilon=0.0005, encoder=None):
+        """test_hash.py:86-105: central differences of forward_sdf along x, y, z at clamped positions (6 extra
+        encoder + sigma-net passes)."""
+        lo, hi = self.min_bound, self.max_bound
+        cols = []
+        for axis in range(3):
+            e = torch.zeros((1, 3), device=x.device)
+            e[0, axis] = epsilon
+            pos = self.forward_sdf((x + e).clamp(lo, hi), encoder)[:, :1]
+            neg = self.forward_sdf((x - e).clamp(lo, hi), encoder)[:, :1]
+            cols.append(0.5 * (pos - neg) / epsilon)
+        return torch.cat(cols, dim=-1)
 
     def forward(self, x, viewdirs=None, mask=None):
         self._check_native()
         if not x.is_cuda:
             raise RuntimeError("MLP_3D.forward needs CUDA tensors (there is no CPU fallback)")
         if viewdirs is None:
-            if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-                # the density-only branch (test_hash.py:73-77) is inference-only in the reference's callers
-                z = torch.zeros((x.shape[0], self.d_view), device=x.device)
-                density = self.field(x, z, 1, use_tc=False)[:, 3:4]
-            else:
-                density, _ = ops.mlp_fwd_f32(x, None, 1, self._flat_params(), self._dims(), keep_act=False)
+            # the density-only branch (test_hash.py:73-77) is inference-only in the reference's callers
+            density = self._density(x)
+            if self.use_sdf:
+                density = self._sdf_from_density(density)
             return density * mask if mask is not None else density
         out = self.field(x, viewdirs, 1)
         if mask is not None:

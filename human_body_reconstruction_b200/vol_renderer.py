@@ -191,7 +191,7 @@ class Volume_Renderer:
             raise ValueError("ERROR: No positional encoding")                               # :191-192
         num_samples = t.shape[-1]
 
-        def run(tt, masked):
+        def run(tt, masked, with_rays=True):
             pts = ops.ray_points(rays_o, rays_d, tt)
             R, S = pts.shape[0], pts.shape[1]
             flat = pts.reshape(-1, 3)
@@ -212,7 +212,8 @@ class Volume_Renderer:
                 mo = model(enc, dirs)
                 sigma, rgb = mo[..., 3:4], mo[..., 0:3]
             return calc_color(t=tt, rgb=rgb.reshape(R, S, -1), sigma=sigma.reshape(R, S), dir_norm=dir_norm,
-                              use_sdf=self.use_sdf, var_model=self.var_model, rays=flat, model=model, encoder=Pos_encode)
+                              use_sdf=self.use_sdf, var_model=self.var_model, rays=flat if with_rays else None, model=model,
+                              encoder=Pos_encode)
 
         if update_mask is True and self.reset_mask is True:
             self.bool_grid[...] = False
@@ -221,7 +222,7 @@ class Volume_Renderer:
         if hierarchical is True:
             _, t_fine = hierarchical_sampling(rays_o, rays_d, z_vals=t, weights=wts, n_samples=num_samples, tn=self.near,
                                               tf=self.far, _u=_u, _u_cand=_u_cand)
-            Cf, _, norm = run(t_fine, False)
+            Cf, _, norm = run(t_fine, False, with_rays=False)          # vol_renderer.py:242 passes no sample positions
         else:
             Cf = Cr
         return Cr, Cf, norm

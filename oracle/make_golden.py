@@ -233,6 +233,51 @@ def gold_rays(ref):
     npz("rays.npz", H=H, W=W, K=K, c2w=c2w, rays_o=o, rays_d=d, dir_norm=n, max_bound=mx, min_bound=mn)
 
 
+def gold_sdf(ref):
+    """SDF mode end to end (train_hash2.py:122-126,220-224 -> vol_renderer.py:165-223 -> helper.py:76-89 ->
+    test_hash.py:59-60,78-105): Volume_Renderer(use_sdf=True, var_model=VarModel()), hierarchical=False (the fine pass of
+    the reference passes no sample positions to calc_color and cannot run in SDF mode), loss = mse + mse + 0.1 * eikonal."""
+    L, T, R, S = 16, 1024, 12, 16
+    torch.manual_seed(21)
+    with ref_loader.quiet():
+        enc = ref.hash_encoding.HashEncoder(N_min=16, N_max=512.0, L=L, F=2, T=T, dim=3, mu=MU, sigma=SIGMA, device="cpu")
+        mlp = ref.test_hash.MLP_3D(num_sig=2, num_col=2, L=L, F=2, d_view=24, use_sdf=True, max_bound=ref.Bound(MAXB),
+                                   min_bound=ref.Bound(MU))
+        pe = ref.encoder.PositionalEncoder(3, 4)
+    pe.sinus_in = pe.sinus_in.cpu()
+    with torch.no_grad():
+        for e in enc.Embedding_list:
+            e.weight.mul_(5e3)
+    var = ref.helper.VarModel()
+    with torch.no_grad():
+        var.b.fill_(3.0)
+    model = torch.nn.DataParallel(mlp)                      # helper.py:87 reaches through .module
+    near, far = torch.tensor(2.0), torch.tensor(6.0)
+    vr = ref.vol_renderer.Volume_Renderer(H=8, W=8, K=torch.eye(3), near=near, far=far, device="cpu", Pos_encode=enc,
+                                          Dir_encode=pe, max_dim=64, sigma_val=SIGMA, mu=MU, use_sdf=True, var_model=var)
+    g = torch.Generator().manual_seed(5)
+    ro = torch.tensor([[0.5, -0.3, 4.0]]).repeat(R, 1) + 0.05 * torch.randn(R, 3, generator=g)
+    rd = torch.nn.functional.normalize(-ro + 0.6 * torch.randn(R, 3, generator=g), dim=-1)
+    dn = 1 + 0.2 * torch.rand(R, 1, generator=g)
+    gt = torch.rand(R, 3, generator=g)
+    t = torch.linspace(2.0, 6.0, S) + torch.rand(S, generator=g) * 4.0 / S
+    with ref_loader.quiet():
+        Cr, Cf, norm = vr.vol_render(model, rd, ro, num_samples=S, t=t, update_mask=False, dir_norm=dn, hierarchical=False)
+        sdf_probe = mlp.forward_sdf(ref_pts := (ro[:, None, :] + rd[:, None, :] * t[None, :, None]).reshape(-1, 3), encoder=enc)
+    loss = (torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)
+            + 0.1 * ref.helper.eikonal_loss(norm))           # train_hash2.py:221-224
+    loss.backward()
+    kw = dict(rays_o=ro, rays_d=rd, dir_norm=dn, gt=gt, t=t, mu=MU, sigma=SIGMA, min_bound=MU, max_bound=MAXB, b=torch.tensor(3.0),
+              tables=torch.stack([e.weight.detach().clone() for e in enc.Embedding_list]),
+              scales=torch.stack([(enc.N_min * enc.b ** i).float() for i in range(L)]),
+              Cr=Cr.detach(), norm=norm.detach(), sdf=sdf_probe.detach(), loss=loss.detach(), grad_b=var.b.grad.clone(),
+              dtables=torch.stack([e.weight.grad for e in enc.Embedding_list]))
+    kw.update({"mlp__" + k.replace(".", "__"): v.detach().clone() for k, v in mlp.state_dict().items()})
+    for k, v in mlp.named_parameters():
+        kw["grad__" + k.replace(".", "__")] = v.grad.clone()
+    npz("sdf.npz", **kw)
+
+
 def gold_formats():
     """dataset.py / dataset_new.py readers of the reference on two tiny scenes written here (tests/golden/scene_*), plus
     the int64 K the trainer builds from them (train_hash2.py:67-72)."""
@@ -291,4 +336,5 @@ if __name__ == "__main__":
     gold_volrender(ref)
     gold_grid(ref)
     gold_rays(ref)
+    gold_sdf(ref)
     gold_formats()

@@ -300,6 +300,66 @@ def vol_render(p_mlp, tables, mu, sigma, scales, rays_d, rays_o, t, dir_norm, nu
 
 
 # ------------------------------------------------------------------------------------------------
+# SDF mode (8f row 4): test_hash.py:59-60,78-105; helper.py:13-21,76-89,102-107,293-299
+# ------------------------------------------------------------------------------------------------
+def mlp_forward_sdf(p: Dict[str, torch.Tensor], feat: torch.Tensor, dirs: Optional[torch.Tensor]) -> torch.Tensor:
+    """MLP_3D.forward with use_sdf=True (test_hash.py:59-60): the density column is 2*sigmoid(dens_vec[:,0:1]) - 1
+    instead of LeakyReLU; dirs=None gives forward_sdf's value (test_hash.py:78-84)."""
+    h = Fnn.relu(Fnn.linear(feat, p["sig_model.0.weight"], p["sig_model.0.bias"]))
+    h = Fnn.relu(Fnn.linear(h, p["sig_model.2.weight"], p["sig_model.2.bias"]))
+    dens_vec = Fnn.linear(h, p["sig_model.4.weight"], p["sig_model.4.bias"])
+    sdf = 2 * torch.sigmoid(dens_vec[:, 0:1]) - 1
+    if dirs is None:
+        return sdf
+    c = torch.cat((dens_vec[:, 1:], dirs.to(dens_vec.dtype)), dim=-1)
+    c = Fnn.relu(Fnn.linear(c, p["col_model.0.weight"], p["col_model.0.bias"]))
+    c = Fnn.relu(Fnn.linear(c, p["col_model.2.weight"], p["col_model.2.bias"]))
+    rgb = Fnn.elu(Fnn.linear(c, p["col_model.4.weight"], p["col_model.4.bias"]))
+    return torch.cat((rgb, sdf), dim=-1)
+
+
+def fd_normals(p_mlp, tables, mu, sigma, scales, x, min_bound, max_bound, epsilon: float = 0.0005) -> torch.Tensor:
+    """MLP_3D.finite_difference_normals_approximator (test_hash.py:86-105): central differences of forward_sdf at
+    positions clamped to the bounding box."""
+    cols = []
+    for axis in range(3):
+        e = torch.zeros(1, 3)
+        e[0, axis] = epsilon
+        pos = mlp_forward_sdf(p_mlp, hash_encode((x + e).clamp(min_bound, max_bound), tables, mu, sigma, scales), None)
+        neg = mlp_forward_sdf(p_mlp, hash_encode((x - e).clamp(min_bound, max_bound), tables, mu, sigma, scales), None)
+        cols.append(0.5 * (pos - neg) / epsilon)
+    return torch.cat(cols, dim=-1)
+
+
+def composite_sdf(rgb: torch.Tensor, sdf: torch.Tensor, b) -> Tuple[torch.Tensor, torch.Tensor]:
+    """calc_color, SDF branch (helper.py:76-86,102-105) on a COPY of sdf (R,S): clamp at -10, phi = 1/(1+exp(-s*b))
+    (VarModel, helper.py:18-21), alpha_i = relu(1 - phi_{i+1}/phi_i) (last sample 0), T = exclusive cumprod(1-alpha).
+    Returns (Cr (R,3), wts (R,S,1))."""
+    s = sdf.clone()
+    s[s < -10] = -10
+    phi = 1 / (1 + torch.exp(-s * b))
+    alpha = torch.zeros_like(s)
+    alpha[..., :-1] = 1 - phi[..., 1:] / phi[..., :-1]
+    alpha = Fnn.relu(alpha)
+    T = torch.roll(torch.cumprod(1 - alpha, -1), 1, -1)
+    T[..., 0] = 1.0
+    wts = T[:, :, None] * alpha[:, :, None]
+    return torch.sum(T[:, :, None] * alpha[:, :, None] * rgb, dim=-2), wts
+
+
+def vol_render_sdf(p_mlp, tables, mu, sigma, scales, rays_d, rays_o, t, b, min_bound, max_bound, num_freq=4):
+    """Volume_Renderer.vol_render with use_sdf=True, hierarchical=False, all-True occupancy grid
+    (vol_renderer.py:165-223 -> helper.py:80-89).  Returns (Cr, wts, eikonal norms (R*S,))."""
+    R, S = rays_o.shape[0], t.shape[0]
+    pts = ray_points(rays_o, rays_d, t).reshape(-1, 3)
+    dirs = dir_encode(rays_d[:, None, :].repeat(1, S, 1).reshape(-1, 3), num_freq)
+    out = mlp_forward_sdf(p_mlp, hash_encode(pts, tables, mu, sigma, scales), dirs)
+    Cr, wts = composite_sdf(out[:, 0:3].reshape(R, S, 3), out[:, 3].reshape(R, S), b)
+    grads = fd_normals(p_mlp, tables, mu, sigma, scales, pts, min_bound, max_bound)
+    return Cr, wts, torch.sqrt(torch.sum(grads ** 2, dim=-1))
+
+
+# ------------------------------------------------------------------------------------------------
 # callers' setup either side of the path (rows "next": get_od, find_bounding_box)
 # ------------------------------------------------------------------------------------------------
 def get_od(H: int, W: int, K: torch.Tensor, c2w: torch.Tensor):

@@ -136,3 +136,28 @@ def test_mc_crossing_edges_small():
     ci = port.mc_case_index(d, 30.0)
     assert ci.shape == (6, 5, 4)
     assert ci[0, 0, 0] == sum(int(ins[v & 1, (v >> 1) & 1, (v >> 2) & 1]) << v for v in range(8))
+
+
+def test_sdf_mode_end_to_end():
+    """SDF mode (8f row 4): the oracle's restatement against the reference's vol_render(use_sdf=True) fixture -- colours,
+    eikonal norms, forward_sdf values, the loss of train_hash2.py:221-224 and its gradients w.r.t. the VarModel
+    sharpness, the hash tables and the MLP."""
+    g = load_golden("sdf.npz")
+    p = {k: v.clone().requires_grad_(True) for k, v in mlp_params(g, "mlp__").items()}
+    tables = g["tables"].clone().requires_grad_(True)
+    b = g["b"].clone().requires_grad_(True)
+    Cr, wts, norm = port.vol_render_sdf(p, tables, g["mu"], g["sigma"], g["scales"], g["rays_d"], g["rays_o"], g["t"], b,
+                                        g["min_bound"], g["max_bound"])
+    assert torch.allclose(Cr, g["Cr"], rtol=1e-5, atol=1e-8)
+    assert torch.allclose(norm, g["norm"], rtol=1e-4, atol=1e-6)
+    pts = port.ray_points(g["rays_o"], g["rays_d"], g["t"]).reshape(-1, 3)
+    sdf = port.mlp_forward_sdf(p, port.hash_encode(pts, tables, g["mu"], g["sigma"], g["scales"]), None)
+    assert torch.allclose(sdf, g["sdf"], rtol=1e-6, atol=1e-8)
+    loss = 2 * torch.nn.functional.mse_loss(Cr, g["gt"]) + 0.1 * torch.mean((norm - 1) ** 2)
+    assert torch.allclose(loss, g["loss"], rtol=1e-6)
+    loss.backward()
+    assert torch.allclose(b.grad, g["grad_b"], rtol=1e-4, atol=1e-9)
+    rel = lambda a, w: float((a - w).norm() / w.norm())
+    assert rel(tables.grad, g["dtables"]) < 1e-5
+    for k, v in p.items():
+        assert rel(v.grad, g["grad__" + k.replace(".", "__")]) < 1e-5, k
