@@ -971,6 +971,8 @@ struct BwdTmem {
 //      Written as ROLLED loops over 8-column TMEM loads on purpose: this code runs once per CTA, so its cost is its
 //      instruction fetch -- the fully unrolled version (~20 KB of SASS, cold in the instruction cache) measured ~31 k
 //      cycles per CTA, an earlier one staging through shared memory ~50 k (plus 16-way bank conflicts).
+//      (Also measured: the same rolled loop staging through a padded, conflict-free shared-memory image with
+//      lane-contiguous stores behind a named barrier: ~21 k cycles against ~16.5 k for the direct stores.)
 //      The accumulators are split over the CTA's tile-group warps (a warp reads the TMEM lane quarter warp % 4).
 template <int K0P, int KCP, int WORK>
 __device__ __noinline__ void flush_gradients(uint32_t tbase, int warp, int lane, int ngroups, const MlpLayout& m,
