@@ -71,11 +71,14 @@ def test_composite_weight_sum_and_closed_form_backward(seed, S):
     delta = torch.zeros_like(t)
     delta[:-1] = t[1:] - t[:-1]
     p = torch.clamp(sigma.detach(), min=-10) * (delta[None, :] * dn)
-    assert torch.allclose(w.sum(-1), 1 - torch.exp(-p.sum(-1)), atol=1e-9)                    # telescoping sum
+    # telescoping sum; negative densities make transmittance grow (values up to e^80), hence relative tolerances
+    assert torch.allclose(w.sum(-1), 1 - torch.exp(-p.sum(-1)), rtol=1e-9, atol=1e-9)
     gC = torch.randn(R, 3, generator=g, dtype=torch.float64)
     (C * gC).sum().backward()
     drgb, dsig = port.composite_bwd(t, rgb.detach(), sigma.detach(), dn, gC)
-    assert torch.allclose(drgb, rgb.grad, atol=1e-9) and torch.allclose(dsig, sigma.grad, atol=1e-8)
+    assert torch.allclose(drgb, rgb.grad, rtol=1e-9, atol=1e-9)
+    scale = float(sigma.grad.abs().max()) + 1.0
+    assert float((dsig - sigma.grad).abs().max()) < 1e-9 * scale
 
 
 @SET
