@@ -12,7 +12,7 @@ from hypothesis import given, settings, strategies as st
 
 from oracle import port
 
-SET = settings(max_examples=40, deadline=None)
+SET = settings(max_examples=60, deadline=None, derandomize=True, database=None)   # same examples on every run
 
 
 @SET
@@ -72,13 +72,15 @@ def test_composite_weight_sum_and_closed_form_backward(seed, S):
     delta[:-1] = t[1:] - t[:-1]
     p = torch.clamp(sigma.detach(), min=-10) * (delta[None, :] * dn)
     # telescoping sum; negative densities make transmittance grow (values up to e^80), hence relative tolerances
-    assert torch.allclose(w.sum(-1), 1 - torch.exp(-p.sum(-1)), rtol=1e-9, atol=1e-9)
+    # (the sum cancels: compare relative to the largest weight of the ray)
+    err = (w.sum(-1) - (1 - torch.exp(-p.sum(-1)))).abs()
+    assert bool((err <= 1e-9 * (w.detach().abs().max(dim=-1).values + 1)).all())
     gC = torch.randn(R, 3, generator=g, dtype=torch.float64)
     (C * gC).sum().backward()
     drgb, dsig = port.composite_bwd(t, rgb.detach(), sigma.detach(), dn, gC)
     assert torch.allclose(drgb, rgb.grad, rtol=1e-9, atol=1e-9)
-    scale = float(sigma.grad.abs().max()) + 1.0
-    assert float((dsig - sigma.grad).abs().max()) < 1e-9 * scale
+    scale = sigma.grad.abs().max(dim=-1, keepdim=True).values + 1.0      # per ray: suffix sums cancel as well
+    assert bool(((dsig - sigma.grad).abs() <= 1e-8 * scale).all())
 
 
 @SET
