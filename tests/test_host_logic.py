@@ -47,3 +47,26 @@ def test_default_loss_is_mse_plus_mse():
     mse = torch.nn.functional.mse_loss
     assert torch.equal(default_loss(Cr, Cf, gt), mse(Cr, gt) + mse(Cf, gt))      # train_hash2.py:221
     assert torch.equal(default_loss(Cr, Cr, gt), mse(Cr, gt) + mse(Cr, gt))      # x + x == 2 x exactly
+
+
+def test_same_seed_construction_reproduces_the_reference_parameters():
+    """Drop-in contract: same constructor arguments + same torch seed -> the same initial parameters as the
+    reference, i.e. the modules consume the RNG in the reference's order (hash_encoding.py:30-32: one nn.Embedding +
+    uniform_(-1e-4, 1e-4) per level; test_hash.py:27-50: sigma net then colour net).  The fixture grid.npz was built by
+    the reference with torch.manual_seed(14); HashEncoder(...), MLP_3D(...) in that order (oracle/make_golden.py: build)."""
+    import human_body_reconstruction_b200 as h
+    from conftest import load_golden, mlp_params
+    g = load_golden("grid.npz")
+    L, T, F = g["tables"].shape
+    torch.manual_seed(14)
+    enc = h.HashEncoder(N_min=16, N_max=2048.0, L=L, F=F, T=T, dim=3, mu=g["mu"], sigma=g["sigma"], device="cpu")
+    mlp = h.MLP_3D(num_sig=2, num_col=2, L=L, F=F, d_view=24, max_bound=g["max_bound"], min_bound=g["min_bound"])
+    tables = torch.stack([e.weight.detach() for e in enc.Embedding_list])
+    assert torch.equal(tables * 5e3, g["tables"])                             # the fixture scaled its tables by 5e3
+    assert [float(s) for s in g["scales"]] == enc.level_scales()
+    want = mlp_params(g, "mlp__")
+    sd = {k: v for k, v in mlp.state_dict().items()}
+    assert set(sd) == set(want)
+    for k in want:
+        assert torch.equal(sd[k].cpu(), want[k]), k
+    assert list(enc.state_dict().keys()) == [f"Embedding_list.{i}.weight" for i in range(L)]
