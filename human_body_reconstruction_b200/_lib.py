@@ -30,7 +30,8 @@ NVCC_FLAGS = [
 HBR_MAX_LEVELS = 32
 HBR_MAX_PEERS, HBR_PEER_MAX_CTAS, HBR_PEER_HANDLE_BYTES = 8, 128, 64
 HBR_PEER_FLAG_BYTES = HBR_PEER_MAX_CTAS * HBR_MAX_PEERS * 4
-HBR_F32, HBR_F16, HBR_U8 = 0, 1, 2
+HBR_F32, HBR_F16, HBR_U8, HBR_BF16 = 0, 1, 2, 3
+HBR_ABI_VERSION = 2
 
 
 class HashGeom(C.Structure):
@@ -42,16 +43,23 @@ class MlpDims(C.Structure):
     _fields_ = [("in0", C.c_int32), ("d_view", C.c_int32)]
 
 
+DEBUG_SO_PATH = os.path.join(_HERE, "libhbr_b200_debug.so")
+
+
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if os.path.isfile(os.path.join(CSRC, f))] + \
+        [os.path.join(INCLUDE, "hbr.h")]
 
 
 def _stale() -> bool:
     if not os.path.exists(SO_PATH):
         return True
     t = os.path.getmtime(SO_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "hbr.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -65,9 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        if (not force) and os.path.exists(obj) and os.path.getmtime(obj) > max(
-                os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC)) and \
-                os.path.getmtime(obj) > os.path.getmtime(os.path.join(INCLUDE, "hbr.h")):
+        if (not force) and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(d) for d in _deps()):
             continue
         cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -88,7 +94,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return SO_PATH
 
 
+def build_debug(force: bool = False) -> str:
+    """csrc/debug/*.cu (+ abi.cu for the error plumbing) -> libhbr_b200_debug.so: probes and self tests only."""
+    dbg = os.path.join(CSRC, "debug")
+    srcs = sorted(os.path.join(dbg, f) for f in os.listdir(dbg) if f.endswith(".cu")) + [os.path.join(CSRC, "abi.cu")]
+    deps = _deps() + [os.path.join(dbg, f) for f in os.listdir(dbg)]
+    if not force and os.path.exists(DEBUG_SO_PATH) and os.path.getmtime(DEBUG_SO_PATH) > max(os.path.getmtime(d) for d in deps):
+        return DEBUG_SO_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], "-I", INCLUDE, "-shared", "-o", DEBUG_SO_PATH, *srcs,
+           "-lcudart"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for the debug library:\n{r.stdout}")
+    return DEBUG_SO_PATH
+
+
 _lib = None
+_debug_lib = None
 _lock = threading.Lock()
 
 _i64, _i32, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
@@ -107,10 +130,11 @@ SIGNATURES = {
     "hbr_mlp_fwd_f32": ([_vp, _i64, _vp, _i64, _i64, _vp, _dims_p, _vp, _vp, _vp], C.c_int),
     "hbr_mlp_bwd_f32": ([_vp, _i64, _vp, _i64, _i64, _vp, _dims_p, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp], C.c_int),
     "hbr_mlp_tc_scratch_bytes": ([_dims_p], _i64),
-    "hbr_mlp_fwd_tc": ([_vp, _i64, _vp, _i64, _i64, _vp, _dims_p, _vp, _vp, _vp], C.c_int),
-    "hbr_mlp_bwd_tc": ([_vp, _i64, _vp, _i64, _i64, _vp, _dims_p, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp], C.c_int),
-    "hbr_field_fwd_tc": ([_vp, _i64, _vp, _geom_p, _vp, _i64, _vp, _dims_p, _vp, _vp, _vp, _vp], C.c_int),
-    "hbr_field_bwd_tc": ([_vp, _i64, _geom_p, _vp, _i64, _vp, _dims_p, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "hbr_mlp_fwd_tc": ([_vp, _i64, _vp, _i64, _i64, _vp, _dims_p, _i32, _vp, _vp, _vp], C.c_int),
+    "hbr_mlp_bwd_tc": ([_vp, _i64, _vp, _i64, _i64, _vp, _dims_p, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _f32, _vp, _vp], C.c_int),
+    "hbr_field_fwd_tc": ([_vp, _i64, _vp, _geom_p, _vp, _i64, _vp, _dims_p, _i32, _vp, _vp, _vp, _vp], C.c_int),
+    "hbr_field_bwd_tc": ([_vp, _i64, _geom_p, _vp, _i64, _vp, _dims_p, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp],
+                         C.c_int),
     "hbr_adam_step": ([_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i32, _i64,
                        C.c_double, _vp, _vp], C.c_int),
     "hbr_ray_gen": ([_vp, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -122,11 +146,6 @@ SIGNATURES = {
     "hbr_peer_import": ([C.POINTER(C.c_ubyte), C.POINTER(_vp)], C.c_int),
     "hbr_peer_release": ([_vp], C.c_int),
     "hbr_allreduce_peer": ([C.POINTER(_vp), C.POINTER(_vp), _vp, _i32, _i32, _i64, _f32, _i32, _vp, _vp], C.c_int),
-    "hbr_debug_umma": ([_i32, _vp, _vp, _vp, _i32, _i32, _vp], C.c_int),
-    "hbr_debug_umma_bench": ([_i32, _i32, _i32, _i32, _i32, _vp, _vp], C.c_int),
-    "hbr_debug_umma_chain_bench": ([_i32, _i32, _i32, _vp, _vp], C.c_int),
-    "hbr_debug_mlp_trace": ([_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp], C.c_int),
-    "hbr_debug_mlp_trace_bwd": ([_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "hbr_ray_points": ([_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp], C.c_int),
     "hbr_occupancy_mask": ([_vp, _i64, _vp, _i32, C.POINTER(C.c_float), _f32, _vp, _vp], C.c_int),
     "hbr_composite_fwd": ([_vp, _i64, _vp, _i64, _vp, _i64, _vp, _f32, _vp, _i64, _i64, _vp, _vp, _vp], C.c_int),
@@ -140,11 +159,20 @@ SIGNATURES = {
     "hbr_mc_emit": ([_vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp], C.c_int),
 }
 
+# probes / self tests: a separate library (csrc/debug/ -> libhbr_b200_debug.so), not part of the product ABI
+DEBUG_SIGNATURES = {
+    "hbr_debug_umma": ([_i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp], C.c_int),
+    "hbr_debug_umma_bench": ([_i32, _i32, _i32, _i32, _i32, _vp, _vp], C.c_int),
+    "hbr_debug_umma_chain_bench": ([_i32, _i32, _i32, _vp, _vp], C.c_int),
+    "hbr_debug_mlp_trace": ([_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp], C.c_int),
+    "hbr_debug_mlp_trace_bwd": ([_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], C.c_int),
+}
+
 
 # kernels launched by one call of each entry point (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
     "hbr_hash_encode_fwd": 1, "hbr_hash_encode_bwd": 1, "hbr_hash_indices": 1, "hbr_dir_encode": 1,
-    "hbr_mlp_fwd_f32": 1, "hbr_mlp_bwd_f32": 2, "hbr_mlp_fwd_tc": 2, "hbr_mlp_bwd_tc": 3, "hbr_field_fwd_tc": 2, "hbr_field_bwd_tc": 3, "hbr_debug_umma": 1, "hbr_adam_step": 1, "hbr_allreduce_peer": 1, "hbr_ray_gen": 1, "hbr_ray_bbox": 1, "hbr_debug_mlp_trace": 1, "hbr_debug_umma_chain_bench": 1, "hbr_debug_umma_bench": 1, "hbr_debug_mlp_trace_bwd": 1, "hbr_ray_points": 1, "hbr_occupancy_mask": 1,
+    "hbr_mlp_fwd_f32": 1, "hbr_mlp_bwd_f32": 2, "hbr_mlp_fwd_tc": 2, "hbr_mlp_bwd_tc": 3, "hbr_field_fwd_tc": 2, "hbr_field_bwd_tc": 3, "hbr_adam_step": 1, "hbr_allreduce_peer": 1, "hbr_ray_gen": 1, "hbr_ray_bbox": 1, "hbr_ray_points": 1, "hbr_occupancy_mask": 1,
     "hbr_composite_fwd": 1, "hbr_composite_bwd": 1, "hbr_hier_sample": 1, "hbr_grid_points": 1,
     "hbr_grid_density": 3, "hbr_mc_count": 1, "hbr_mc_emit": 2,
 }
@@ -220,11 +248,29 @@ def lib():
                 fn.argtypes = args
                 fn.restype = res
                 setattr(wrapped, name, _Counted(fn, name) if name in KERNELS_PER_CALL else fn)
-            if l.hbr_abi_version() != 1:
+            if l.hbr_abi_version() != HBR_ABI_VERSION:
                 raise RuntimeError("libhbr_b200.so ABI version mismatch")
             wrapped.cdll = l
             _lib = wrapped
     return _lib
+
+
+def debug_lib():
+    """The probe / self-test library (tests and scripts/dbg_*.py only)."""
+    global _debug_lib
+    with _lock:
+        if _debug_lib is None:
+            l = C.CDLL(build_debug())
+            wrapped = _Lib()
+            for name, (args, res) in DEBUG_SIGNATURES.items():
+                fn = getattr(l, name)
+                fn.argtypes = args
+                fn.restype = res
+                setattr(wrapped, name, fn)
+            l.hbr_last_error.restype = C.c_char_p
+            wrapped.cdll = l
+            _debug_lib = wrapped
+    return _debug_lib
 
 
 def check(rc: int):

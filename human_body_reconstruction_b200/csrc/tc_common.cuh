@@ -26,11 +26,64 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;                                    // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
 }
 
-// ---- instruction descriptor: kind::f16, bf16 x bf16 -> fp32 -------------------------------------------------------
+// ---- operand formats of kind::f16: bf16 (torch.autocast(bfloat16)) or fp16 (torch.autocast(float16), what the
+//      reference's trainer runs: train_hash2.py:218).  Everything format-specific -- conversions, the ReLU-mask
+//      product of the backward, the descriptor's A/B format field -- sits behind these two types.
+struct OpBf16 {
+  static constexpr uint32_t kFmt = 1;          // instruction-descriptor A/B format: 1 = bf16
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  // max(x,0) fused into the conversion: low half <- lo, high half <- hi
+  static __device__ __forceinline__ uint32_t pack_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+  }
+  // dz * [h > 0] on packed pairs (h is a stored post-ReLU activation: h > 0 <=> pre-activation > 0)
+  static __device__ __forceinline__ uint32_t mask_pos(uint32_t dz, uint32_t h) {
+    const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+    const __nv_bfloat162 m = __hgt2(*reinterpret_cast<const __nv_bfloat162*>(&h), zero);      // 1.0 / 0.0 per half
+    const __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&dz), m);
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ float round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+  static __device__ __forceinline__ uint16_t bits(float a) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(a);
+    return *reinterpret_cast<const uint16_t*>(&h);
+  }
+};
+struct OpF16 {
+  static constexpr uint32_t kFmt = 0;          // 0 = fp16
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ uint32_t pack_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+  }
+  static __device__ __forceinline__ uint32_t mask_pos(uint32_t dz, uint32_t h) {
+    const __half2 zero = __floats2half2_rn(0.f, 0.f);
+    const __half2 m = __hgt2(*reinterpret_cast<const __half2*>(&h), zero);
+    const __half2 r = __hmul2(*reinterpret_cast<const __half2*>(&dz), m);
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ float round(float a) { return __half2float(__float2half_rn(a)); }
+  static __device__ __forceinline__ uint16_t bits(float a) {
+    const __half h = __float2half_rn(a);
+    return *reinterpret_cast<const uint16_t*>(&h);
+  }
+};
+
+// ---- instruction descriptor: kind::f16, (bf16 | fp16) x same -> fp32 ------------------------------------------------
+template <class OP>
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major, bool b_mn_major) {
   return (1u << 4)                             // D format: f32
-         | (1u << 7)                           // A format: bf16
-         | (1u << 10)                          // B format: bf16
+         | (OP::kFmt << 7)                     // A format
+         | (OP::kFmt << 10)                    // B format
          | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16)
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -169,32 +222,22 @@ __device__ __forceinline__ uint32_t chunk_off(int r, int cg, int rows) {
   return (uint32_t)((r & 7) * 16 + (r >> 3) * 128 + cg * rows * 16);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-// max(x,0) fused into the conversion: low half <- lo, high half <- hi
-__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
-  uint32_t d;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-// dz * [h > 0] on packed bf16 pairs (h is a stored post-ReLU activation: h > 0 <=> pre-activation > 0)
-__device__ __forceinline__ uint32_t mask_pos_bf16x2(uint32_t dz, uint32_t h) {
-  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
-  const __nv_bfloat162 m = __hgt2(*reinterpret_cast<const __nv_bfloat162*>(&h), zero);      // 1.0 / 0.0 per half
-  const __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&dz), m);
-  return *reinterpret_cast<const uint32_t*>(&r);
-}
-__device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
-
 // store 8 consecutive columns (one chunk) of this thread's row
+template <class OP>
 __device__ __forceinline__ void store_chunk(uint8_t* tile, int r, int cg, int rows, const float* v8) {
   uint4 q;
-  q.x = pack_bf16(v8[0], v8[1]); q.y = pack_bf16(v8[2], v8[3]);
-  q.z = pack_bf16(v8[4], v8[5]); q.w = pack_bf16(v8[6], v8[7]);
+  q.x = OP::pack(v8[0], v8[1]); q.y = OP::pack(v8[2], v8[3]);
+  q.z = OP::pack(v8[4], v8[5]); q.w = OP::pack(v8[6], v8[7]);
   *reinterpret_cast<uint4*>(tile + chunk_off(r, cg, rows)) = q;
 }
+
+// arguments of the fused encoder + MLP variants (hbr_field_*_tc)
+struct EncArgs {
+  const float* x;                // (n,3) fp32 sample positions
+  const float* table;            // (L,T,2) fp32                      (forward)
+  float* dtable;                 // (L,T,2) fp32, accumulated into    (backward)
+  uint16_t* feat16;               // (n,32) bf16 features: written by the forward, re-read by the backward recompute
+};
 
 }  // namespace tc
 }  // namespace hbr

@@ -31,7 +31,7 @@ def default_loss(Cr, Cf, gt):
 class GraphedStep:
     def __init__(self, renderer, model, params: Iterable[torch.nn.Parameter], n_rays: int, num_samples: int,
                  hierarchical: bool, device, loss_fn: Callable = default_loss, autocast: bool = True, warmup: int = 3,
-                 source=None):
+                 source=None, autocast_dtype: torch.dtype = torch.bfloat16):
         """source: optional rays.DeviceRayDataset.  Its sampler (ray ids from the graph-safe device generator ->
         hbr_ray_gen) is then captured in front of the step, so a replay draws a fresh batch from the resident views by
         itself: call the object with no arguments; nothing crosses PCIe but the graph launch."""
@@ -39,7 +39,7 @@ class GraphedStep:
         self.source = source
         self.params = list(params)
         self.num_samples, self.hierarchical = int(num_samples), bool(hierarchical)
-        self.loss_fn, self.autocast = loss_fn, autocast
+        self.loss_fn, self.autocast, self.autocast_dtype = loss_fn, autocast, autocast_dtype
         dev = torch.device(device)
         # one packed static buffer [rays_o (R,3) | rays_d (R,3) | dir_norm (R,1) | gt (R,3)]: a batch packed the same way
         # (pack_batch) is loaded with ONE copy instead of four
@@ -60,7 +60,7 @@ class GraphedStep:
         rays_o, rays_d, dir_norm, gt = self.rays_o, self.rays_d, self.dir_norm, self.gt
         if self.source is not None:
             rays_o, rays_d, dir_norm, gt = self.source.sample(self.n_rays)
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
+        with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast):
             Cr, Cf, _ = self.renderer.vol_render(self.model, rays_d, rays_o, num_samples=self.num_samples,
                                                  update_mask=False, dir_norm=dir_norm, hierarchical=self.hierarchical)
             loss = self.loss_fn(Cr, Cf, gt)

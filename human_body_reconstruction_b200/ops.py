@@ -14,7 +14,7 @@ import torch
 from . import _lib
 HAS_TC = True    # csrc/mlp_tc.cu (tcgen05) is linked in
 
-from ._lib import HBR_F16, HBR_F32, HashGeom, MlpDims, check, lib, ptr, require_cuda, stream
+from ._lib import HBR_BF16, HBR_F16, HBR_F32, HashGeom, MlpDims, check, lib, ptr, require_cuda, stream
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -297,51 +297,77 @@ def mlp_tc_scratch(dims: MlpDims, device) -> torch.Tensor:
     return buf
 
 
-def mlp_fwd_tc(feat, dirs, dir_group, params, dims: MlpDims, keep_act: bool = False):
-    """bf16 tensor-core forward; keeps nothing (the backward recomputes), returns (out, None)."""
+def tc_operand(dtype=None) -> int:
+    """Tensor-core operand format of the MLP kernels for an autocast dtype: float16 -> HBR_F16 (the reference trainer's
+    precision, train_hash2.py:218), bfloat16 -> HBR_BF16.  None = the active CUDA autocast dtype (bf16 outside autocast)."""
+    if dtype is None:
+        dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else torch.bfloat16
+    if isinstance(dtype, int):
+        if dtype in (HBR_F16, HBR_BF16):
+            return dtype
+        raise ValueError(f"operand format {dtype}")
+    if dtype == torch.float16:
+        return HBR_F16
+    if dtype == torch.bfloat16:
+        return HBR_BF16
+    raise TypeError(f"the tensor-core MLP runs fp16 or bf16 operands, not {dtype}")
+
+
+def _operand_torch_dtype(operand: int):
+    return torch.float16 if operand == HBR_F16 else torch.bfloat16
+
+
+def mlp_fwd_tc(feat, dirs, dir_group, params, dims: MlpDims, keep_act: bool = False, operand: int = HBR_BF16):
+    """16-bit tensor-core forward; keeps nothing (the backward recomputes), returns (out, None)."""
     require_cuda(feat, dirs, params)
     n = feat.shape[0]
     out = torch.empty((n, 4), device=feat.device, dtype=torch.float32)
-    check(lib().hbr_mlp_fwd_tc(ptr(feat), feat.stride(0), ptr(dirs), dir_group, n, ptr(params), C.byref(dims), ptr(out),
-                               ptr(mlp_tc_scratch(dims, feat.device)), stream()))
+    check(lib().hbr_mlp_fwd_tc(ptr(feat), feat.stride(0), ptr(dirs), dir_group, n, ptr(params), C.byref(dims), operand,
+                               ptr(out), ptr(mlp_tc_scratch(dims, feat.device)), stream()))
     return out, None
 
 
-def mlp_bwd_tc(feat, dirs, dir_group, params, dims: MlpDims, out, dout, want_dfeat, want_ddirs, dparams):
+def mlp_bwd_tc(feat, dirs, dir_group, params, dims: MlpDims, out, dout, want_dfeat, want_ddirs, dparams,
+               operand: int = HBR_BF16, grad_scale: float = 1.0):
     """`out` is the forward output (N,4): the kernel takes ELU' / LeakyReLU' from it instead of recomputing the last layer."""
     n = feat.shape[0]
     dfeat = torch.empty((n, dims.in0), device=feat.device, dtype=torch.float32) if want_dfeat else None
     ddirs = torch.zeros_like(dirs) if want_ddirs else None
-    check(lib().hbr_mlp_bwd_tc(ptr(feat), feat.stride(0), ptr(dirs), dir_group, n, ptr(params), C.byref(dims), ptr(out),
-                               ptr(dout), ptr(dfeat), dims.in0, ptr(ddirs), ptr(dparams),
+    check(lib().hbr_mlp_bwd_tc(ptr(feat), feat.stride(0), ptr(dirs), dir_group, n, ptr(params), C.byref(dims), operand,
+                               ptr(out), ptr(dout), ptr(dfeat), dims.in0, ptr(ddirs), ptr(dparams), float(grad_scale),
                                ptr(mlp_tc_scratch(dims, feat.device)), stream()))
     return dfeat, ddirs
 
 
-def field_fwd_tc(x, table, geom: HashGeom, dirs, dir_group, params, dims: MlpDims):
-    """Fused hash-grid encoder + MLP_3D forward (bf16 tensor cores).  Returns (out (N,4) fp32, feat16 (N,32) bf16 = the
+def field_fwd_tc(x, table, geom: HashGeom, dirs, dir_group, params, dims: MlpDims, operand: int = HBR_BF16):
+    """Fused hash-grid encoder + MLP_3D forward (tensor cores).  Returns (out (N,4) fp32, feat16 (N,32) 16-bit = the
     features that were fed to the tensor cores, kept for the backward recompute)."""
     require_cuda(x, table, dirs, params)
     n = x.shape[0]
     out = torch.empty((n, 4), device=x.device, dtype=torch.float32)
-    feat16 = torch.empty((n, 32), device=x.device, dtype=torch.bfloat16)
+    feat16 = torch.empty((n, 32), device=x.device, dtype=_operand_torch_dtype(operand))
     check(lib().hbr_field_fwd_tc(ptr(x), n, ptr(table), C.byref(geom), ptr(dirs), dir_group, ptr(params), C.byref(dims),
-                                 ptr(out), ptr(feat16), ptr(mlp_tc_scratch(dims, x.device)), stream()))
+                                 operand, ptr(out), ptr(feat16), ptr(mlp_tc_scratch(dims, x.device)), stream()))
     return out, feat16
 
 
-def field_bwd_tc(x, geom: HashGeom, dirs, dir_group, params, dims: MlpDims, feat16, out, dout, dtable, want_ddirs, dparams):
+def field_bwd_tc(x, geom: HashGeom, dirs, dir_group, params, dims: MlpDims, feat16, out, dout, dtable, want_ddirs, dparams,
+                 operand: int = HBR_BF16, grad_scale: float = 1.0):
     """Fused MLP_3D backward + hash-grid scatter-add: dtable (L,T,2) and dparams are accumulated into."""
     ddirs = torch.zeros_like(dirs) if want_ddirs else None
     check(lib().hbr_field_bwd_tc(ptr(x), x.shape[0], C.byref(geom), ptr(dirs), dir_group, ptr(params), C.byref(dims),
-                                 ptr(feat16), ptr(out), ptr(dout), ptr(dtable), ptr(ddirs), ptr(dparams),
-                                 ptr(mlp_tc_scratch(dims, x.device)), stream()))
+                                 operand, ptr(feat16), ptr(out), ptr(dout), ptr(dtable), ptr(ddirs), ptr(dparams),
+                                 float(grad_scale), ptr(mlp_tc_scratch(dims, x.device)), stream()))
     return ddirs
 
 
-def debug_umma(mode: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int) -> torch.Tensor:
+def debug_umma(mode: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, operand: int = HBR_BF16) -> torch.Tensor:
+    """Self test of the UMMA operand modes (probe library, tests only)."""
     D = torch.empty((M, N), device=A.device, dtype=torch.float32)
-    check(lib().hbr_debug_umma(mode, ptr(A.contiguous()), ptr(B.contiguous()), ptr(D), N, K, stream()))
+    dl = _lib.debug_lib()
+    rc = dl.hbr_debug_umma(mode, operand, ptr(A.contiguous()), ptr(B.contiguous()), ptr(D), N, K, stream())
+    if rc != 0:
+        raise RuntimeError(f"libhbr_b200_debug: {dl.cdll.hbr_last_error().decode()} (status {rc})")
     return D
 
 

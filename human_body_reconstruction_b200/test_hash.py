@@ -31,7 +31,7 @@ class _MlpFn(torch.autograd.Function):
         feat = feat.float().contiguous()
         dirs = dirs.float().contiguous()
         if use_tc:
-            out, act = ops.mlp_fwd_tc(feat, dirs, dir_group, flat, dims, keep_act=train)
+            out, act = ops.mlp_fwd_tc(feat, dirs, dir_group, flat, dims, keep_act=train, operand=use_tc)
         else:
             out, act = ops.mlp_fwd_f32(feat, dirs, dir_group, flat, dims, keep_act=train)
         ctx.mlp, ctx.dims, ctx.dir_group, ctx.use_tc = mlp, dims, dir_group, use_tc
@@ -48,7 +48,7 @@ class _MlpFn(torch.autograd.Function):
         want_dfeat, want_ddirs = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if ctx.use_tc:
             dfeat, ddirs = ops.mlp_bwd_tc(feat, dirs, ctx.dir_group, flat, ctx.dims, act.detach(), dout, want_dfeat, want_ddirs,
-                                          dflat)
+                                          dflat, operand=ctx.use_tc, grad_scale=mlp.tc_grad_scale)
         else:
             dfeat, ddirs = ops.mlp_bwd_f32(feat, dirs, ctx.dir_group, flat, ctx.dims, dout, act, want_dfeat, want_ddirs, dflat)
         mlp._publish_grad(dflat)
@@ -82,6 +82,10 @@ class MLP_3D(nn.Module):
         self.use_sdf = use_sdf
         self._native = (num_sig == 2 and num_col == 2 and h_size == 64 and L * F + E <= 64 and 15 + d_view <= 64)
         self._in0 = L * F + E
+        # power-of-two factor the tensor-core backward applies to the upstream gradient before rounding it to the 16-bit
+        # operand format (and divides out of its results).  The reference's trainer scales the loss with GradScaler
+        # (train_hash2.py:156,226), which does the same job from outside; set this when running fp16 operands without one.
+        self.tc_grad_scale = 1.0
         self._grad_hooks = []
         self._grad_buffer = None     # persistent (peer-mapped) flat gradient buffer, see dist.PeerGradAllReduce
         self._flat = None
@@ -147,15 +151,22 @@ class MLP_3D(nn.Module):
         if not self._native:
             raise NotImplementedError("native MLP_3D supports num_sig=2, num_col=2, h_size=64 (the reference's configuration)")
 
+    @staticmethod
+    def _tc_operand(use_tc=None) -> int:
+        """0 = fp32 CUDA-core kernels; otherwise the tensor-core operand format (ops.HBR_F16 / HBR_BF16).  use_tc: None =
+        follow torch.autocast (its dtype picks the format), False, True (bf16 unless fp16 autocast is active) or a dtype."""
+        if use_tc is None:
+            use_tc = torch.is_autocast_enabled()
+        if use_tc is False or not ops.HAS_TC:
+            return 0
+        return ops.tc_operand(None if use_tc is True else use_tc)
+
     # -- evaluation entry used by Volume_Renderer (one direction row per ray) ---------------------------------
     def field(self, feat, dirs_enc, dir_group, use_tc=None, raw=False):
         """(N,4) [rgb, density].  With use_sdf the density column is 2*sigmoid(pre-activation) - 1 (test_hash.py:59-60)
         unless raw=True."""
         self._check_native()
-        if use_tc is None:
-            use_tc = torch.is_autocast_enabled()
-        use_tc = bool(use_tc) and ops.HAS_TC
-        out = _MlpFn.apply(feat, dirs_enc, int(dir_group), self, bool(use_tc), *self._ordered())
+        out = _MlpFn.apply(feat, dirs_enc, int(dir_group), self, self._tc_operand(use_tc), *self._ordered())
         if self.use_sdf and not raw:
             out = torch.cat((out[:, :3], self._sdf_from_density(out[:, 3:4])), dim=-1)
         return out

@@ -31,8 +31,9 @@ class _FieldFn(torch.autograd.Function):
     def forward(ctx, pts, dirs, dir_group, enc, mlp, *params):
         geom, dims = enc._geom(), mlp._dims()
         dirs = dirs.float().contiguous()
-        out, feat16 = ops.field_fwd_tc(pts, enc._flat_table(), geom, dirs, dir_group, mlp._flat_params(), dims)
-        ctx.enc, ctx.mlp, ctx.geom, ctx.dims, ctx.dir_group = enc, mlp, geom, dims, dir_group
+        operand = ops.tc_operand()
+        out, feat16 = ops.field_fwd_tc(pts, enc._flat_table(), geom, dirs, dir_group, mlp._flat_params(), dims, operand)
+        ctx.enc, ctx.mlp, ctx.geom, ctx.dims, ctx.dir_group, ctx.operand = enc, mlp, geom, dims, dir_group, operand
         ctx.save_for_backward(pts, dirs, feat16, out)
         return out
 
@@ -45,7 +46,8 @@ class _FieldFn(torch.autograd.Function):
         flat = mlp._flat_params()
         dflat = mlp._grad_buffer.zero_() if mlp._grad_buffer is not None else torch.zeros_like(flat)
         ddirs = ops.field_bwd_tc(pts, ctx.geom, dirs, ctx.dir_group, flat, ctx.dims, feat16, out.detach(),
-                                 dout.float().contiguous(), g, ctx.needs_input_grad[1], dflat)
+                                 dout.float().contiguous(), g, ctx.needs_input_grad[1], dflat, operand=ctx.operand,
+                                 grad_scale=mlp.tc_grad_scale)
         mlp._publish_grad(dflat)
         enc._publish_grad(g)
         return (None, ddirs, None, None, None) + tuple(g[i] for i in range(L)) + tuple(mlp._grad_views(dflat))

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define HBR_ABI_VERSION 1
+#define HBR_ABI_VERSION 2
 #define HBR_MAX_LEVELS 32
 
 typedef enum {
@@ -33,7 +33,7 @@ typedef enum {
   HBR_ERR_UNSUPPORTED = -3
 } hbr_status;
 
-typedef enum { HBR_F32 = 0, HBR_F16 = 1, HBR_U8 = 2 } hbr_dtype;
+typedef enum { HBR_F32 = 0, HBR_F16 = 1, HBR_U8 = 2, HBR_BF16 = 3 } hbr_dtype;
 
 /* Geometry of a HashEncoder instance: hash_encoding.py:6-39.
  * scale[l] = N_min * b**l is computed by the HOST with the reference's torch expression
@@ -103,54 +103,38 @@ int hbr_mlp_bwd_f32(const float* feat, int64_t feat_stride, const float* dirs, i
                     const float* params, const hbr_mlp_dims* dims, const float* dout, const float* act,
                     float* dz, float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams, void* stream);
 
-/* ---- a7 on the tensor cores: bf16 operands, fp32 accumulation in TMEM (tcgen05) -----------------------
- * Same contract as the fp32 pair; this is what runs under autocast (train_hash2.py:218).  No activation is kept
- * between the passes: the backward kernel recomputes them in shared memory from feat, takes ELU' / LeakyReLU'
- * from `out` (the (n,4) result of the forward call), and keeps the weight-gradient accumulators in TMEM across
- * all tiles of a persistent CTA.  dfeat / ddirs may be NULL; dparams (flat fp32) and ddirs are ACCUMULATED into. */
+/* ---- a7 on the tensor cores: 16-bit operands, fp32 accumulation in TMEM (tcgen05) ------------------------
+ * Same contract as the fp32 pair; this is what runs under autocast (train_hash2.py:218).  `operand` is the tensor-core
+ * operand format: HBR_F16 under torch.autocast(float16) -- the reference trainer's precision -- or HBR_BF16 under
+ * torch.autocast(bfloat16).  No activation is kept between the passes: the backward kernel recomputes them in shared
+ * memory from feat, takes ELU' / LeakyReLU' from `out` (the (n,4) result of the forward call), and keeps the
+ * weight-gradient accumulators in TMEM across all tiles of a persistent CTA.  dfeat / ddirs may be NULL; dparams (flat
+ * fp32) and ddirs are ACCUMULATED into.  grad_scale (> 0, a power of two; 1 = off) multiplies dout before it is rounded
+ * to the operand format and is divided out of every result: fp16's 5 exponent bits underflow on the gradients of a
+ * mean-reduced loss unless the caller scales (the reference's GradScaler, train_hash2.py:156,226) or passes it here. */
 /* scratch: optional device buffer of hbr_mlp_tc_scratch_bytes(dims) bytes, 256-byte aligned (NULL = none).  With it a
- * small prep kernel builds the bf16 operand image once per call and the backward sums per-CTA gradient rows with a
+ * small prep kernel builds the 16-bit operand image once per call and the backward sums per-CTA gradient rows with a
  * reduce kernel; without it every CTA converts the parameters itself and flushes its gradients with atomics. */
 int64_t hbr_mlp_tc_scratch_bytes(const hbr_mlp_dims* dims);
 int hbr_mlp_fwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
-                   const float* params, const hbr_mlp_dims* dims, float* out, void* scratch, void* stream);
+                   const float* params, const hbr_mlp_dims* dims, int operand, float* out, void* scratch, void* stream);
 int hbr_mlp_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
-                   const float* params, const hbr_mlp_dims* dims, const float* out, const float* dout, float* dfeat,
-                   int64_t dfeat_stride, float* ddirs, float* dparams, void* scratch, void* stream);
+                   const float* params, const hbr_mlp_dims* dims, int operand, const float* out, const float* dout,
+                   float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams, float grad_scale, void* scratch,
+                   void* stream);
 /* ---- a2 + a7 fused (the training step's field evaluation under autocast): hash-grid encoder + MLP_3D in ONE kernel per
  * direction -- HashEncoder.forward (hash_encoding.py:146-170) feeding MLP_3D.forward (test_hash.py:52-72) as
  * vol_renderer.py:179,211 chains them.  Covers the reference's configuration family F = 2, L = 16, E = 0, power-of-two T,
  * d_view <= 25; anything else uses the separate entry points.  x (n,3) fp32 sample positions.  The forward writes the
- * bf16 features it fed to the tensor cores to feat16 (n,32) for the backward recompute; the backward scatter-adds
+ * 16-bit features (operand format) it fed to the tensor cores to feat16 (n,32) for the backward recompute; the backward scatter-adds
  * d(features) into dtable (L,T,2) straight from the accumulator.  dparams / dtable / ddirs are ACCUMULATED into. */
 int hbr_field_fwd_tc(const float* x, int64_t n, const float* table, const hbr_hash_geom* geom_host, const float* dirs,
-                     int64_t dir_group, const float* params, const hbr_mlp_dims* dims, float* out, void* feat16,
-                     void* scratch, void* stream);
+                     int64_t dir_group, const float* params, const hbr_mlp_dims* dims, int operand, float* out,
+                     void* feat16, void* scratch, void* stream);
 int hbr_field_bwd_tc(const float* x, int64_t n, const hbr_hash_geom* geom_host, const float* dirs, int64_t dir_group,
-                     const float* params, const hbr_mlp_dims* dims, const void* feat16, const float* out,
-                     const float* dout, float* dtable, float* ddirs, float* dparams, void* scratch, void* stream);
-/* Self-test of the three UMMA operand modes the MLP kernels rely on (one 128-thread CTA, bf16 inputs
- * rounded from fp32, fp32 result): mode 0: D[128,N] = A[128,K] B[N,K]^T; mode 1: D[128,N] = A[128,K] Bt[K,N];
- * mode 2: D[64,N] = At[128,64]^T Bt[128,N]. */
-int hbr_debug_umma(int mode, const float* A, const float* B, float* D, int N, int K, void* stream);
-/* Tensor-pipe probe: `reps` tcgen05.mma (M x N x 16, bf16) issued back to back by one thread round-robin over `nacc`
- * accumulators; cycles[0] = first issue -> completion observed, cycles[1] = first issue -> last issue (SM clocks). */
-int hbr_debug_umma_bench(int M, int N, int reps, int nacc, int mn_major, long long* cycles, void* stream);
-/* Steady-state cost of the GEMM chains the MLP kernels issue: kind 0 forward layer (4 MMAs), 1 dgrad (4), 2 weight
- * gradient M=64 N=72 (8), 3 transposed weight gradient M=128 N=16 (8); `reps` chains round-robin over `nacc`
- * accumulators.  cycles[0] = total, cycles[1] = issue only (SM clocks). */
-int hbr_debug_umma_chain_bench(int kind, int reps, int nacc, long long* cycles, void* stream);
-/* Latency probe of the forward kernel (in0 = 32, d_view = 24): trace[0..1000) = clock64 stamps of tile group 0 of CTA 0
- * (tile start, then before-signal / after-signal / after-wait per layer), trace[1024..1524) = the MMA warp's
- * (ready-seen, committed) pairs for that group.  trace holds 2048 int64. */
-int hbr_debug_mlp_trace(const float* feat, const float* dirs, int64_t dir_group, int64_t n, const float* params,
-                        float* out, long long* trace, void* stream);
-/* Same probe for the backward kernel: per tile 1 + 3*11 stamps of tile group 0, (ready-seen, committed) pairs of the
- * issuing warp for that group at trace[1024..]. */
-int hbr_debug_mlp_trace_bwd(const float* feat, const float* dirs, int64_t dir_group, int64_t n, const float* params,
-                            const float* out, const float* dout, float* dfeat, float* dparams, void* scratch,
-                            long long* trace, void* stream);
-
+                     const float* params, const hbr_mlp_dims* dims, int operand, const void* feat16, const float* out,
+                     const float* dout, float* dtable, float* ddirs, float* dparams, float grad_scale, void* scratch,
+                     void* stream);
 /* ---- a9: sample positions, vol_renderer.py:165 / helper.py:48 -------------------------------------
  * pts[r,s,:] = o[r,:] + d[r,:]*t  (separate multiply and add).  t is (S) shared (t_ray_stride = 0)
  * or (R,S) per ray (t_ray_stride = S). */

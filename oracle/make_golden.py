@@ -95,6 +95,33 @@ def gold_mlp_dir(ref):
         dfeat=feat.grad, ddirs=dirs.grad, **kw)
 
 
+def gold_mlp_autocast(ref):
+    """The reference's own MLP_3D under torch.autocast (train_hash2.py:218 runs float16) against itself in fp32, on the
+    CPU: the reference's 16-bit gradients differ from its fp32 ones by percents (ReLU-mask flips at pre-activations
+    near zero), which is the yardstick the tensor-core kernels are held to (tests/test_gpu_precision.py)."""
+    _, mlp, pe = build(ref, 16, 64, 2048.0, 12, 1.0)
+    g = torch.Generator().manual_seed(15)
+    R, S = 8, 128
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    dirs = pe(d).reshape(R, -1)
+    feat = torch.randn(R * S, 32, generator=g) * 0.5
+    dout = torch.randn(R * S, 4, generator=g)
+    drep = dirs[:, None, :].repeat(1, S, 1).reshape(R * S, -1)          # vol_renderer.py:177-183
+    kw = {k.replace(".", "__"): v.detach().clone() for k, v in mlp.state_dict().items()}
+    for tag, dt in (("f32", None), ("f16", torch.float16), ("bf16", torch.bfloat16)):
+        f = feat.clone().requires_grad_()
+        for p_ in mlp.parameters():
+            p_.grad = None
+        with ref_loader.quiet(), torch.autocast("cpu", dtype=dt, enabled=dt is not None):
+            out = mlp(f, drep)
+        out.float().backward(dout)
+        kw[f"{tag}__out"] = out.detach().float()
+        kw[f"{tag}__dfeat"] = f.grad.clone()
+        for k, v in mlp.named_parameters():
+            kw[f"{tag}__grad__" + k.replace(".", "__")] = v.grad.clone()
+    npz("mlp_autocast.npz", feat=feat, dirs=dirs, dout=dout, S=S, **kw)
+
+
 def gold_composite(ref):
     g = torch.Generator().manual_seed(6)
     R, S = 48, 40
@@ -332,6 +359,7 @@ if __name__ == "__main__":
     ref = ref_loader.load()
     gold_hash(ref)
     gold_mlp_dir(ref)
+    gold_mlp_autocast(ref)
     gold_composite(ref)
     gold_volrender(ref)
     gold_grid(ref)

@@ -7,7 +7,7 @@ importers: tests/, __graft_entry__.smoke(), and bench.py's cpu_baseline / --impl
 Parity status: PINNED.  The reference ships no tests or golden vectors,
 so every function here is pinned against outputs of the reference itself, executed in the
 build container by oracle/make_golden.py (fixtures committed in tests/golden/*.npz) and, when
-the reference tree is present, live in tests/test_oracle_vs_reference.py.
+the reference tree is present, live in tests/test_oracle_golden.py.
 Exception: marching cubes (torchmcubes==0.1.0, Nerf.yml:198, source not vendored) -- only the
 table-independent invariant "welded vertex count == number of iso-crossing grid edges" is
 pinned; vertex order / face lists are parity-unpinned.
@@ -273,9 +273,12 @@ def occupancy_mask(points: torch.Tensor, bool_grid: torch.Tensor, mu, sigma_val)
 
 def vol_render(p_mlp, tables, mu, sigma, scales, rays_d, rays_o, t, dir_norm, num_freq=4,
                hierarchical=False, near=None, far=None, u_rs=None, u_s=None, bool_grid=None,
-               update_mask=False):
+               update_mask=False, t_fine=None):
     """Volume_Renderer.vol_render (vol_renderer.py:141-245), NeRF mode, with the strat depths `t`
-    and the hierarchical draws supplied.  Returns (Cr, Cf, aux) with aux = dict(w=..., t_fine=...)."""
+    and the hierarchical draws supplied.  Returns (Cr, Cf, aux) with aux = dict(w=..., t_fine=...).
+    t_fine: use these fine depths instead of resampling (the depths carry no gradient, helper.py:41-47: searchsorted /
+    gather / sort of detached values) -- lets a test evaluate the reference's fine pass and its gradients on the sampling
+    decisions of the implementation under test, whose coarse weights differ from the CPU's in the last bits."""
     R, S = rays_o.shape[0], t.shape[0]
     pts = ray_points(rays_o, rays_d, t).reshape(-1, 3)
     dirs = dir_encode(rays_d[:, None, :].repeat(1, S, 1).reshape(-1, 3), num_freq)
@@ -290,7 +293,8 @@ def vol_render(p_mlp, tables, mu, sigma, scales, rays_d, rays_o, t, dir_norm, nu
     aux = {"w": w}
     if not hierarchical:
         return Cr, Cr, aux
-    t_fine = hier_sample(w.detach(), t, near, far, u_rs, u_s)
+    if t_fine is None:
+        t_fine = hier_sample(w.detach(), t, near, far, u_rs, u_s)
     pts_f = ray_points(rays_o, rays_d, t_fine).reshape(-1, 3)
     dirs_f = dir_encode(rays_d[:, None, :].repeat(1, 2 * S, 1).reshape(-1, 3), num_freq)
     out_f = mlp_forward(p_mlp, hash_encode(pts_f, tables, mu, sigma, scales), dirs_f)
@@ -446,16 +450,17 @@ def mc_case_index(density: np.ndarray, iso: float) -> np.ndarray:
 # ------------------------------------------------------------------------------------------------
 # bf16 tensor-core numerics of MLP_3D, emulated in torch (checker for csrc/mlp_tc.cu)
 # ------------------------------------------------------------------------------------------------
-def _bf(x: torch.Tensor) -> torch.Tensor:
-    return x.to(torch.bfloat16).to(torch.float32)
+def mlp_tc_emulation(p: Dict[str, torch.Tensor], feat: torch.Tensor, dirs: torch.Tensor, dout: Optional[torch.Tensor] = None,
+                     fmt: torch.dtype = torch.bfloat16):
 
-
-def mlp_bf16_emulation(p: Dict[str, torch.Tensor], feat: torch.Tensor, dirs: torch.Tensor, dout: Optional[torch.Tensor] = None):
     """MLP_3D forward (and backward when dout is given) with the tensor-core kernel's rounding points:
-    weights, layer inputs and pre-activation gradients rounded to bf16, products/accumulation/bias/activations in
+    weights, layer inputs and pre-activation gradients rounded to the operand format `fmt` (bfloat16 or float16), products/accumulation/bias/activations in
     fp32, the layer-3 vector (density + 15 features) and the outputs NOT rounded.  Returns out (N,4) and, with
     dout, (dfeat, grads dict).  Not a reference restatement -- a numerics model of our own kernel, used to test it
     tightly; the reference-facing tolerance (1e-2, BASELINE.json) is checked against mlp_forward."""
+    def _bf(x: torch.Tensor) -> torch.Tensor:
+        return x.to(fmt).to(torch.float32)
+
     # the bias enters the accumulator through the tensor core as bf16(b) + bf16(b - bf16(b))
     W = {k: _bf(v) if k.endswith("weight") else _bf(v) + _bf(v - _bf(v)) for k, v in p.items()}
     x0 = _bf(feat)
@@ -490,3 +495,7 @@ def mlp_bf16_emulation(p: Dict[str, torch.Tensor], feat: torch.Tensor, dirs: tor
     g["sig_model.0.weight"], g["sig_model.0.bias"] = dz1.T @ x0, dz1.sum(0)
     dfeat = dz1 @ W["sig_model.0.weight"]
     return out, dfeat, g, dcin[:, 15:]
+
+
+def mlp_bf16_emulation(p, feat, dirs, dout=None):
+    return mlp_tc_emulation(p, feat, dirs, dout, torch.bfloat16)

@@ -11,7 +11,7 @@ feat = (torch.randn(n, 32) * 0.5).to(dev)
 dirs = torch.randn(n // 128, 24).to(dev)
 out = torch.empty(n, 4, device=dev)
 trace = torch.zeros(2048, dtype=torch.int64, device=dev)
-L = _lib.lib()
+L = _lib.debug_lib()
 for it in range(3):
     trace.zero_()
     _lib.check(L.hbr_debug_mlp_trace(_lib.ptr(feat), _lib.ptr(dirs), 128, n, _lib.ptr(flat), _lib.ptr(out), _lib.ptr(trace), _lib.stream()))

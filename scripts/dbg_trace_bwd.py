@@ -14,7 +14,7 @@ dout = torch.randn(n, 4, device=dev)
 dfeat = torch.empty(n, 32, device=dev)
 dparams = torch.zeros_like(flat)
 trace = torch.zeros(2048, dtype=torch.int64, device=dev)
-L = _lib.lib()
+L = _lib.debug_lib()
 from human_body_reconstruction_b200 import ops
 from human_body_reconstruction_b200._lib import MlpDims
 scratch = ops.mlp_tc_scratch(MlpDims(32, 24), dev)

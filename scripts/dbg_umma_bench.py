@@ -2,7 +2,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from human_body_reconstruction_b200 import _lib
-L = _lib.lib()
+L = _lib.debug_lib()
 cyc = torch.zeros(2, dtype=torch.int64, device="cuda")
 def run(M, N, reps, nacc, mn):
     best = None

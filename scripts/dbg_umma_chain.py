@@ -2,7 +2,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from human_body_reconstruction_b200 import _lib
-L = _lib.lib()
+L = _lib.debug_lib()
 cyc = torch.zeros(2, dtype=torch.int64, device="cuda")
 names = {0: "fwd 128x64x64 (4 MMA)", 1: "dgrad (4 MMA)", 2: "wgrad M64 N72 (8 MMA)", 3: "wgradT M128 N16 (8 MMA)"}
 nm = {0: 4, 1: 4, 2: 8, 3: 8}

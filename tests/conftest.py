@@ -1,3 +1,4 @@
+import contextlib
 import os
 import sys
 
@@ -41,3 +42,25 @@ def mlp_params(g, prefix=""):
 @pytest.fixture
 def golden():
     return load_golden
+
+
+@contextlib.contextmanager
+def capture_fine_sampling():
+    """Records what Volume_Renderer hands to / gets from hierarchical_sampling: rec["w"] (coarse weights before the in-place
+    clamp, (R,S)) and rec["t_fine"] ((R,2S))."""
+    from human_body_reconstruction_b200 import vol_renderer as vrm
+    rec = {}
+    orig = vrm.hierarchical_sampling
+
+    def wrapped(*a, **k):
+        w = k["weights"]
+        rec["w"] = (w.squeeze(-1) if w.dim() == 3 else w).detach().clone()
+        rays, tf = orig(*a, **k)
+        rec["t_fine"] = tf.detach().clone()
+        return rays, tf
+
+    vrm.hierarchical_sampling = wrapped
+    try:
+        yield rec
+    finally:
+        vrm.hierarchical_sampling = orig

@@ -22,7 +22,8 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(l, s), f"{s} declared in hbr.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(syms)
-    assert l.hbr_abi_version() == 1
+    assert l.hbr_abi_version() == 2
+    assert not any(s.startswith("hbr_debug") for s in syms), "probe entry points belong to the debug library"
 
 
 def test_param_count_and_errors_without_gpu():
@@ -41,3 +42,13 @@ def test_sass_is_sm100a_only():
     from human_body_reconstruction_b200 import _lib
     out = subprocess.run(["cuobjdump", "-lelf", _lib.build()], capture_output=True, text=True).stdout
     assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_debug_library_is_separate():
+    """The probes / self tests (csrc/debug) build into their own library; the product library exports none of them."""
+    from human_body_reconstruction_b200 import _lib
+    prod = ctypes.CDLL(_lib.build())
+    dbg = ctypes.CDLL(_lib.build_debug())
+    for name in _lib.DEBUG_SIGNATURES:
+        assert hasattr(dbg, name)
+        assert not hasattr(prod, name), f"{name} leaked into the product ABI"

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, mlp_params
+from conftest import capture_fine_sampling, load_golden, mlp_params
 from oracle import port
 
 pytestmark = pytest.mark.gpu
@@ -247,11 +247,10 @@ def test_hier_sample_golden():
                                               _u=g["u_rs"].to(DEV), _u_cand=g["u_s"].to(DEV))
     ref = port.hier_sample(wr, g["t"], g["near"], g["far"], g["u_rs"], g["u_s"])
     assert float(w[0, 0]) == 0.0
-    mism = (tf.cpu() != ref).any(dim=-1).float().mean()
-    assert mism <= 0.05, f"{mism} of rays differ"            # cdf ulp flips only
+    # identical weights in -> identical depths out, bit for bit (serial fp32 cdf == torch.cumsum on the CPU)
+    assert torch.equal(tf.cpu(), ref), f"{(tf.cpu() != ref).any(dim=-1).float().mean()} of rays differ"
     assert (tf[:, 1:] >= tf[:, :-1]).all()
-    same = (tf.cpu() == ref).all(dim=-1)
-    assert torch.allclose(rays.cpu()[same], port.ray_points(g["rays_o"], g["rays_d"], ref)[same], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(rays.cpu(), port.ray_points(g["rays_o"], g["rays_d"], ref), rtol=1e-6, atol=1e-6)
 
 
 def build_renderer(g, max_dim=64):
@@ -274,22 +273,40 @@ def test_vol_render_golden(tag, wrap):
     t = port.strat_t(g["near"], g["far"], S, g[f"{tag}__u_t"]).to(DEV)
     hier = tag == "hier"
     kw = dict(_u=g["hier__u_rs"].to(DEV), _u_cand=g["hier__u_s"].to(DEV)) if hier else {}
-    Cr, Cf, norm = vr.vol_render(model, g["rays_d"].to(DEV), g["rays_o"].to(DEV), num_samples=S, t=t, update_mask=False,
-                                 dir_norm=g["dir_norm"].to(DEV), hierarchical=hier, **kw)
+    with capture_fine_sampling() as rec:
+        Cr, Cf, norm = vr.vol_render(model, g["rays_d"].to(DEV), g["rays_o"].to(DEV), num_samples=S, t=t, update_mask=False,
+                                     dir_norm=g["dir_norm"].to(DEV), hierarchical=hier, **kw)
     assert norm is None
     assert torch.allclose(Cr.cpu(), g[f"{tag}__Cr"], rtol=1e-5, atol=1e-6)
-    bad = ~torch.isclose(Cf.cpu(), g[f"{tag}__Cf"], rtol=1e-5, atol=1e-6).all(dim=-1)
-    assert bad.float().mean() <= 0.05
-    if bad.any():
-        pytest.skip("a cdf ulp flip changed a fine sample; gradient comparison not meaningful")
     gt = g["gt"].to(DEV)
     loss = torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)
-    assert abs(float(loss) - float(g[f"{tag}__loss"])) < 1e-5 * float(g[f"{tag}__loss"])
     loss.backward()
     grad = torch.stack([e.weight.grad for e in enc.Embedding_list])
-    assert rel(grad, g[f"{tag}__dtables"]) < 1e-5
+    ref = {"Cf": g[f"{tag}__Cf"], "loss": g[f"{tag}__loss"], "dtables": g[f"{tag}__dtables"],
+           "mlp": {k: g[f"{tag}__grad__" + k.replace(".", "__")] for k, _ in mlp.named_parameters()}}
+    if hier:
+        # (1) the resampler on identical input: bit-identical to the oracle's (== the reference's) depths
+        near, far = g["near"], g["far"]
+        tf_same_in = port.hier_sample(rec["w"].cpu(), t.cpu(), near, far, g["hier__u_rs"], g["hier__u_s"])
+        assert torch.equal(rec["t_fine"].cpu(), tf_same_in)
+        # (2) against the reference's own run the coarse weights differ in the last bits (GPU expf / scan order), which may
+        # move a cdf boundary across a draw: measured 0 of 64 rays on this fixture (B200); if a ray does differ, the
+        # reference's fine pass is evaluated on OUR depths (they carry no gradient) so nothing is skipped
+        moved = ~torch.isclose(Cf.cpu(), ref["Cf"], rtol=1e-5, atol=1e-6).all(dim=-1)
+        assert moved.float().mean() <= 1 / 64
+        if moved.any():
+            tb = g["tables"].clone().requires_grad_()
+            pr = {k: v.clone().requires_grad_() for k, v in mlp_params(g, "mlp__").items()}
+            Cr_o, Cf_o, _ = port.vol_render(pr, tb, g["mu"], g["sigma"], g["scales"], g["rays_d"], g["rays_o"], t.cpu(), g["dir_norm"], 4, True, near, far,
+                                            g["hier__u_rs"], g["hier__u_s"], t_fine=rec["t_fine"].cpu())
+            lo = torch.nn.functional.mse_loss(Cr_o, g["gt"]) + torch.nn.functional.mse_loss(Cf_o, g["gt"])
+            lo.backward()
+            ref = {"Cf": Cf_o.detach(), "loss": lo.detach(), "dtables": tb.grad, "mlp": {k: v.grad for k, v in pr.items()}}
+    assert torch.allclose(Cf.cpu(), ref["Cf"], rtol=1e-5, atol=1e-6)
+    assert abs(float(loss.detach()) - float(ref["loss"])) < 1e-5 * float(ref["loss"])
+    assert rel(grad, ref["dtables"]) < 1e-5
     for k, p in mlp.named_parameters():
-        assert rel(p.grad, g[f"{tag}__grad__" + k.replace(".", "__")]) < 2e-5, k
+        assert rel(p.grad, ref["mlp"][k]) < 2e-5, k
 
 
 def test_vol_render_masked_and_generic_agree():

@@ -6,10 +6,11 @@ Three layers of evidence:
   2. the MLP kernels match a torch model of their own numerics (oracle.port.mlp_bf16_emulation: bf16 operands,
      fp32 accumulation) tightly -- this is the "is the kernel right" test;
   3. against the reference's fp32 arithmetic (oracle.port.mlp_forward) the outputs are within the 1e-2 the
-     north star grants the bf16 MLP.  Gradients of a ReLU network evaluated in 16-bit differ from the fp32 ones
-     mostly through activation-mask flips at pre-activations near zero (error ~ sqrt(fraction flipped)); torch's own
-     autocast shows the same (measured: bf16 autocast 5-7 %, fp16 autocast 1-2 % on this network), so the gradient
-     check against fp32 is calibrated against torch.autocast(bfloat16) evaluated on the same inputs."""
+     north star grants the 16-bit MLP.  Per-point gradients of a ReLU network evaluated in 16 bit differ from the fp32
+     ones mostly through activation-mask flips at pre-activations near zero; the reference's own autocast evaluation
+     shows the same (tests/golden/mlp_autocast.npz), and is the yardstick: tests/test_gpu_precision.py holds the stated
+     bounds, including 1e-2 on the gradients of the benchmarked step.
+Both operand formats are covered: bf16 (torch.autocast(bfloat16)) and fp16 (torch.autocast(float16), train_hash2.py:218)."""
 import pytest
 import torch
 
@@ -24,26 +25,27 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def bf(x):
-    return x.bfloat16().float()
+def bf(x, fmt=torch.bfloat16):
+    return x.to(fmt).float()
 
 
 @pytest.mark.parametrize("mode,M,N,K", [(0, 128, 64, 32), (0, 128, 16, 64), (0, 128, 64, 48), (0, 128, 64, 64),
                                         (1, 128, 64, 16), (1, 128, 48, 64), (1, 128, 32, 64), (1, 128, 64, 64),
                                         (2, 64, 64, 128), (2, 64, 48, 128), (2, 64, 32, 128), (2, 64, 16, 128)])
-def test_umma_operand_modes(mode, M, N, K):
+@pytest.mark.parametrize("fmt", [torch.bfloat16, torch.float16])
+def test_umma_operand_modes(mode, M, N, K, fmt):
     from human_body_reconstruction_b200 import ops
     torch.manual_seed(mode * 1000 + N + K)
     if mode == 0:
         A, B = torch.randn(M, K), torch.randn(N, K)
-        ref = bf(A) @ bf(B).T
+        ref = bf(A, fmt) @ bf(B, fmt).T
     elif mode == 1:
         A, B = torch.randn(M, K), torch.randn(K, N)
-        ref = bf(A) @ bf(B)
+        ref = bf(A, fmt) @ bf(B, fmt)
     else:
         A, B = torch.randn(K, 64), torch.randn(K, N)
-        ref = bf(A).T @ bf(B)
-    D = ops.debug_umma(mode, A.to(DEV), B.to(DEV), M, N, K)
+        ref = bf(A, fmt).T @ bf(B, fmt)
+    D = ops.debug_umma(mode, A.to(DEV), B.to(DEV), M, N, K, operand=ops.tc_operand(fmt))
     assert rel(D, ref) < 1e-6
 
 
@@ -56,44 +58,47 @@ def make(seed=5):
 
 
 @pytest.mark.parametrize("R,S", [(1, 1), (3, 100), (40, 24), (512, 128), (129, 7)])
-def test_mlp_tc_matches_numerics_model_and_reference(R, S):
+@pytest.mark.parametrize("fmt", [torch.bfloat16, torch.float16])
+def test_mlp_tc_matches_numerics_model_and_reference(R, S, fmt):
     torch.manual_seed(R * 1000 + S)
     p, m = make()
     feat = torch.randn(R * S, 32) * 0.5
     dirs = port.dir_encode(torch.nn.functional.normalize(torch.randn(R, 3), dim=-1), 4)
     drep = dirs[:, None, :].repeat(1, S, 1).reshape(R * S, -1)
     dout = torch.randn(R * S, 4)
-    emu_out, emu_dfeat, emu_g, _ = port.mlp_bf16_emulation(p, feat, drep, dout)
+    emu_out, emu_dfeat, emu_g, _ = port.mlp_tc_emulation(p, feat, drep, dout, fmt)
     pr = {k: v.clone().requires_grad_() for k, v in p.items()}
     fr = feat.clone().requires_grad_()
     ref = port.mlp_forward(pr, fr, drep)
     ref.backward(dout)
 
     f = feat.to(DEV).requires_grad_()
-    out = m.field(f, dirs.to(DEV), S, use_tc=True)
+    out = m.field(f, dirs.to(DEV), S, use_tc=fmt)
     out.backward(dout.to(DEV))
     # (2) kernel vs its numerics model
-    # a last-bit difference in an fp32 accumulator flips the bf16 rounding of that activation (2^-9 relative for the
-    # element); a handful of flips per row is the expected residual between two correct evaluations
+    # a last-bit difference in an fp32 accumulator flips the 16-bit rounding of that activation (2^-9 / 2^-12 relative for
+    # the element); a handful of flips per row is the expected residual between two correct evaluations
     assert rel(out, emu_out) < 5e-4
-    # ReLU-mask / bf16-rounding flips of single activations dominate the residual between two correct evaluations;
+    # ReLU-mask / rounding flips of single activations dominate the residual between two correct evaluations;
     # on a few hundred points one flip is already a percent of a bias gradient
     gtol = 1e-2 if R * S >= 4096 else 3e-2
     assert rel(f.grad, emu_dfeat) < gtol
     for k, q in m.named_parameters():
         assert rel(q.grad, emu_g[k]) < gtol, k
-    # (3) kernel vs the reference's fp32 arithmetic
+    # (3) kernel vs the reference's fp32 arithmetic: outputs within the north star's 1e-2
     assert rel(out, ref) < 1e-2
-    if R * S >= 256:
+    if R * S >= 65536:
+        # per-point gradients against fp32: the yardstick is what the reference's own torch expressions give under
+        # torch.autocast of the same dtype (oracle.port.mlp_forward == the reference's ops, pinned on the CPU by
+        # tests/test_oracle_golden.py::test_mlp_autocast_golden); tests/test_gpu_precision.py states the bounds
         pa = {k: v.clone().requires_grad_() for k, v in p.items()}
         fa = feat.clone().requires_grad_()
-        with torch.autocast("cpu", dtype=torch.bfloat16):
+        with torch.autocast("cpu", dtype=fmt):
             oa = port.mlp_forward(pa, fa, drep)
         oa.float().backward(dout)
-        budget = 2.0 * max(rel(fa.grad, fr.grad), 0.02)
-        assert rel(f.grad, fr.grad) < budget
+        assert rel(f.grad, fr.grad) <= 1.25 * rel(fa.grad, fr.grad) + 5e-3
         for k, q in m.named_parameters():
-            assert rel(q.grad, pr[k].grad) < 2.0 * max(rel(pa[k].grad, pr[k].grad), 0.02), k
+            assert rel(q.grad, pr[k].grad) <= 1.25 * rel(pa[k].grad, pr[k].grad) + 5e-3, k
 
 
 def test_mlp_tc_under_autocast_is_selected_and_accumulates():
@@ -117,27 +122,34 @@ def test_mlp_tc_under_autocast_is_selected_and_accumulates():
         assert rel(q.grad, 2 * g1[k]) < 1e-5
     assert rel(dirs.grad, 2 * dd1) < 1e-5
     drep = dirs.detach().cpu()[:, None, :].repeat(1, S, 1).reshape(R * S, -1)
-    _, _, _, emu_dd = port.mlp_bf16_emulation(p, feat.detach().cpu(), drep, dout.cpu())
+    _, _, _, emu_dd = port.mlp_tc_emulation(p, feat.detach().cpu(), drep, dout.cpu(), torch.bfloat16)
     assert rel(dd1, emu_dd.reshape(R, S, -1).sum(1)) < 5e-3
 
 
-def test_vol_render_bf16_close_to_reference():
-    """Whole coarse+fine render under autocast: rendered colours within 1e-2 of the reference's fp32 outputs."""
+@pytest.mark.parametrize("fmt,scale,gtol", [(torch.bfloat16, 1.0, 0.05), (torch.float16, 65536.0, 0.03)])
+def test_vol_render_16bit_close_to_reference(fmt, scale, gtol):
+    """Whole coarse render under autocast against the reference's fp32 fixture (64 rays x 24 samples): colours and loss
+    within 1e-2.  The table gradient of these 1 536 points is in the per-point regime (see tests/test_gpu_precision.py):
+    measured on B200 2.8 % (bf16) / 1.7 % (fp16, gradient scale 2^16); the bound is that with margin.  At the benchmarked size the same quantity is within 1e-2
+    (test_gpu_precision.py::test_training_step_gradients_at_c2_size_within_1e_2)."""
     from conftest import load_golden, mlp_params
     from test_gpu_parity import build_renderer
     g = load_golden("volrender.npz")
     vr, enc, mlp = build_renderer(g)
+    mlp.tc_grad_scale = scale
     S = 24
     t = port.strat_t(g["near"], g["far"], S, g["coarse__u_t"]).to(DEV)
-    with torch.autocast("cuda", dtype=torch.bfloat16):
+    with torch.autocast("cuda", dtype=fmt):
         Cr, Cf, _ = vr.vol_render(mlp, g["rays_d"].to(DEV), g["rays_o"].to(DEV), num_samples=S, t=t,
                                   dir_norm=g["dir_norm"].to(DEV), hierarchical=False)
         loss = torch.nn.functional.mse_loss(Cr, g["gt"].to(DEV)) + torch.nn.functional.mse_loss(Cf, g["gt"].to(DEV))
     assert rel(Cr, g["coarse__Cr"]) < 1e-2
-    assert abs(float(loss) - float(g["coarse__loss"])) < 1e-2 * float(g["coarse__loss"])
+    assert abs(float(loss.detach()) - float(g["coarse__loss"])) < 1e-2 * float(g["coarse__loss"])
     loss.backward()
     grad = torch.stack([e.weight.grad for e in enc.Embedding_list])
-    assert torch.isfinite(grad).all() and rel(grad, g["coarse__dtables"]) < 0.25
+    err = rel(grad, g["coarse__dtables"])
+    print(f"volrender fixture, {fmt}: table-gradient error {err:.4f}")
+    assert torch.isfinite(grad).all() and err < gtol
 
 
 @pytest.mark.parametrize("R,S,T", [(96, 128, 2 ** 19), (33, 40, 2 ** 14), (1, 7, 2 ** 10)])

@@ -161,3 +161,23 @@ def test_sdf_mode_end_to_end():
     assert rel(tables.grad, g["dtables"]) < 1e-5
     for k, v in p.items():
         assert rel(v.grad, g["grad__" + k.replace(".", "__")]) < 1e-5, k
+
+
+@pytest.mark.parametrize("tag,fmt", [("f32", None), ("f16", torch.float16), ("bf16", torch.bfloat16)])
+def test_mlp_autocast_golden(tag, fmt):
+    """oracle.port.mlp_forward is the reference's MLP_3D.forward op for op: under torch.autocast on the CPU it reproduces
+    the reference's own 16-bit outputs and gradients (tests/golden/mlp_autocast.npz, made by the unmodified reference),
+    so it can stand in for "the reference at 16 bit" at sizes no fixture holds."""
+    g = load_golden("mlp_autocast.npz")
+    p = {k: v.clone().requires_grad_() for k, v in mlp_params(g).items()}
+    S = int(g["S"])
+    f = g["feat"].clone().requires_grad_()
+    drep = g["dirs"][:, None, :].repeat(1, S, 1).reshape(-1, g["dirs"].shape[-1])
+    with torch.autocast("cpu", dtype=fmt or torch.bfloat16, enabled=fmt is not None):
+        out = port.mlp_forward(p, f, drep)
+    out.float().backward(g["dout"])
+    tol = dict(rtol=1e-6, atol=1e-7) if fmt is None else dict(rtol=0, atol=0)
+    assert torch.allclose(out.detach().float(), g[f"{tag}__out"], **tol)
+    assert torch.allclose(f.grad, g[f"{tag}__dfeat"], **tol)
+    for k, v in p.items():
+        assert torch.allclose(v.grad, g[f"{tag}__grad__" + k.replace(".", "__")], **tol), k
