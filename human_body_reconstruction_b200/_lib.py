@@ -157,6 +157,7 @@ SIGNATURES = {
                           _vp, _vp, _vp, _vp, _i64, _vp], C.c_int),
     "hbr_mc_count": ([_vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp], C.c_int),
     "hbr_mc_emit": ([_vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp], C.c_int),
+    "hbr_grid_interp": ([_vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp], C.c_int),
 }
 
 # probes / self tests: a separate library (csrc/debug/ -> libhbr_b200_debug.so), not part of the product ABI
@@ -174,7 +175,7 @@ KERNELS_PER_CALL = {
     "hbr_hash_encode_fwd": 1, "hbr_hash_encode_bwd": 1, "hbr_hash_indices": 1, "hbr_dir_encode": 1,
     "hbr_mlp_fwd_f32": 1, "hbr_mlp_bwd_f32": 2, "hbr_mlp_fwd_tc": 2, "hbr_mlp_bwd_tc": 3, "hbr_field_fwd_tc": 2, "hbr_field_bwd_tc": 3, "hbr_adam_step": 1, "hbr_allreduce_peer": 1, "hbr_ray_gen": 1, "hbr_ray_bbox": 1, "hbr_ray_points": 1, "hbr_occupancy_mask": 1,
     "hbr_composite_fwd": 1, "hbr_composite_bwd": 1, "hbr_hier_sample": 1, "hbr_grid_points": 1,
-    "hbr_grid_density": 3, "hbr_mc_count": 1, "hbr_mc_emit": 2,
+    "hbr_grid_density": 3, "hbr_mc_count": 1, "hbr_mc_emit": 2, "hbr_grid_interp": 1,
 }
 
 

@@ -13,7 +13,10 @@
 // the reduction happens in the NVSwitch (multimem.ld_reduce / multimem.st) and each direction carries S bytes.
 // The barriers are self-resetting CAS flags (put: 0 -> 1 on the peer, take: 1 -> 0 on my side), one word per
 // (CTA, sender): CTA b of every rank only talks to CTA b of the others, so the grid must be co-resident (<= SM count).
-// A barrier that does not complete within kBarrierTimeoutNs sets *status and the kernel carries on (never hangs a GPU).
+// A barrier that does not complete within kBarrierTimeoutNs sets *status (sticky; also checked on entry) and the kernel
+// returns WITHOUT touching the gradients: the failure is contained -- this rank keeps its own unreduced gradient -- and
+// the host side raises when it sees the word (peer.PeerRegion.raise_if_failed, called by dist.PeerGradAllReduce every
+// step), so no optimiser step runs on gradients the ranks disagree on.  The kernel never hangs a GPU.
 #include "common.cuh"
 #include <string.h>
 
@@ -54,15 +57,15 @@ __device__ __forceinline__ void mc_st(float* p, const float4& v) {  // one store
 }
 
 // All threads of CTA b on every rank have arrived (and their earlier writes are visible system-wide).
-__device__ __forceinline__ void peer_barrier(const PeerPtrs& p, int rank, int world, unsigned* status) {
+__device__ __forceinline__ bool peer_barrier(const PeerPtrs& p, int rank, int world, unsigned* status) {
   __syncthreads();
   const int q = threadIdx.x;
+  bool ok = true;
   if (q < world && q != rank) {
     __threadfence_system();
     unsigned* put = p.flag[q] + (size_t)blockIdx.x * kMaxPeers + rank;
     unsigned* take = p.flag[rank] + (size_t)blockIdx.x * kMaxPeers + q;
     const unsigned long long t0 = global_ns();
-    bool ok = true;
     while (atomicCAS_system(put, 0u, 1u) != 0u)
       if (global_ns() - t0 > kBarrierTimeoutNs) { ok = false; break; }
     while (ok && atomicCAS_system(take, 1u, 0u) != 1u)
@@ -70,7 +73,7 @@ __device__ __forceinline__ void peer_barrier(const PeerPtrs& p, int rank, int wo
     if (!ok && status != nullptr) atomicExch(status, 1u);
     __threadfence_system();
   }
-  __syncthreads();
+  return __syncthreads_and(ok) != 0;
 }
 
 __device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
@@ -79,7 +82,8 @@ __device__ __forceinline__ void mul4(float4& a, float s) { a.x *= s; a.y *= s; a
 template <int WORLD, bool MC>
 __global__ void __launch_bounds__(512)
 allreduce_peer_kernel(const PeerPtrs p, float* __restrict__ mc, int rank, long long n4, float scale, unsigned* status) {
-  peer_barrier(p, rank, WORLD, status);                           // every rank's scatter-add (previous kernel) is complete
+  if (status != nullptr && *reinterpret_cast<volatile unsigned*>(status) != 0u) return;   // an earlier exchange failed: the flags are not trustworthy
+  if (!peer_barrier(p, rank, WORLD, status)) return;              // every rank's scatter-add (previous kernel) is complete
   const long long per = (n4 + WORLD - 1) / WORLD;
   const long long lo = (long long)rank * per;
   const long long hi = lo + per < n4 ? lo + per : n4;

@@ -150,9 +150,45 @@ mc_faces_kernel(const float* __restrict__ d, int n0, int n1, int n2, float iso, 
   }
 }
 
+// torchmcubes.grid_interp (nerf2mesh.py:99): trilinear sample of vol (C, n0, n1, n2) at points given as (x, y, z) =
+// (index along axis 2, axis 1, axis 0) in grid-index units, clamped to the volume.  out (n, C).
+__global__ void __launch_bounds__(256)
+grid_interp_kernel(const float* __restrict__ vol, int C, int n0, int n1, int n2, const float* __restrict__ pts,
+                   long long n, float* __restrict__ out) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const float x = fminf(fmaxf(__ldg(pts + q * 3 + 0), 0.f), (float)(n2 - 1));
+  const float y = fminf(fmaxf(__ldg(pts + q * 3 + 1), 0.f), (float)(n1 - 1));
+  const float z = fminf(fmaxf(__ldg(pts + q * 3 + 2), 0.f), (float)(n0 - 1));
+  const int k0 = min((int)x, max(n2 - 2, 0)), j0 = min((int)y, max(n1 - 2, 0)), i0 = min((int)z, max(n0 - 2, 0));
+  const int k1 = min(k0 + 1, n2 - 1), j1 = min(j0 + 1, n1 - 1), i1 = min(i0 + 1, n0 - 1);
+  const float fx = x - (float)k0, fy = y - (float)j0, fz = z - (float)i0;
+  const long long plane = (long long)n1 * n2, volsz = (long long)n0 * plane;
+  for (int c = 0; c < C; ++c) {
+    const float* v = vol + (long long)c * volsz;
+    auto at = [&](int i, int j, int k) { return __ldg(v + (long long)i * plane + (long long)j * n2 + k); };
+    const float c00 = at(i0, j0, k0) * (1.f - fx) + at(i0, j0, k1) * fx;
+    const float c01 = at(i0, j1, k0) * (1.f - fx) + at(i0, j1, k1) * fx;
+    const float c10 = at(i1, j0, k0) * (1.f - fx) + at(i1, j0, k1) * fx;
+    const float c11 = at(i1, j1, k0) * (1.f - fx) + at(i1, j1, k1) * fx;
+    const float c0 = c00 * (1.f - fy) + c01 * fy, c1 = c10 * (1.f - fy) + c11 * fy;
+    out[q * C + c] = c0 * (1.f - fz) + c1 * fz;
+  }
+}
+
 }  // namespace hbr
 
 using namespace hbr;
+
+extern "C" int hbr_grid_interp(const float* vol, int C, int n0, int n1, int n2, const float* pts, int64_t n, float* out,
+                               void* stream) {
+  HBR_REQUIRE(C >= 1 && n0 >= 1 && n1 >= 1 && n2 >= 1 && n >= 0, "bad shape");
+  if (n == 0) return HBR_OK;
+  HBR_REQUIRE(vol && pts && out, "NULL pointer");
+  grid_interp_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(vol, C, n0, n1, n2, pts, n, out);
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
 
 extern "C" int hbr_grid_points(const double* min3, const double* max3, int res, int64_t p0, int64_t count,
                                void* pts_f16, void* stream) {

@@ -7,13 +7,13 @@ SURVEY section 8(e).
 Two exchanges are provided: `GradAllReduce` (NCCL calls, below) and `PeerGradAllReduce` (ONE kernel of this
 package over NVLink peer memory / NVLS multicast, csrc/comm.cu; the default of `attach_grad_allreduce`).
 
-Mechanics of the NCCL variant: `HashEncoder` / `MLP_3D` publish their flat gradient tensor (L,T,F) / (14227,) from inside their
-autograd backward -- the encoder in level chunks, each as soon as its scatter-add kernel has been enqueued;
-the hook below launches an asynchronous all-reduce on every published piece right there (NCCL's stream waits
-for the producing kernel, the compute stream runs on: the MLP's reduce overlaps the hash-table backward, a
-table chunk's reduce overlaps the next chunk's scatter-add) and registers an end-of-backward engine callback
-that makes the compute stream wait for the collectives.  MSE is a mean over the LOCAL batch, so the
-average over ranks equals the single-process gradient of the concatenated batch.
+Mechanics (class _GradExchange): `HashEncoder` / `MLP_3D` accumulate into ONE persistent flat gradient buffer each -- (L,T,F) /
+(14227,) -- that is zeroed once per backward pass however many autograd nodes feed it (a hierarchical render runs the field
+twice); the last backward node of a module publishes its buffer (the encoder in level chunks, each as soon as its
+scatter-add kernel has been enqueued) and the exchange of a published piece may start right there, overlapping what is
+left of the backward; an end-of-backward engine callback reduces the rest, makes the compute stream wait, and only then
+hands the buffers to `.grad`.  MSE is a mean over the LOCAL batch, so the average over ranks equals the single-process
+gradient of the concatenated batch.
 """
 from __future__ import annotations
 
@@ -40,115 +40,273 @@ def init_from_env(backend: str | None = None) -> tuple[int, int]:
     return rank, world
 
 
-class GradAllReduce:
-    """Attach to native modules: `GradAllReduce(encoder, mlp)`.  Detach with `.remove()`."""
+class _GradExchange:
+    """One backward pass = one SESSION.  The native modules (HashEncoder, MLP_3D) talk to the reducer installed in their
+    `_dp` attribute through four calls:
 
-    def __init__(self, *modules, group=None, average: bool = True):
-        self.group = group
-        self.average = average
+        note_forward(m)            in the autograd forward, when gradients will be wanted (counts the backward nodes to expect;
+                                   the first one of a step also starts zeroing the persistent buffers on a side stream)
+        buf, last = enter_backward(m)   in every backward node: the module's persistent flat gradient buffer -- zeroed ONCE
+                                   per session, so several passes through the same module (coarse + fine render,
+                                   vol_renderer.py:220,242) ACCUMULATE into it -- and whether this is the last node expected
+        publish(m, piece)          by the last node only, per finished piece (level chunk): may start that piece's exchange
+        (the node returns None for the parameter gradients)
+
+    and an autograd-engine end-of-backward callback reduces whatever was not published, makes the compute stream wait for
+    the exchange and only then hands the buffers to the parameters' `.grad` (assigned, or added if the caller keeps
+    gradients across backward calls).  Nothing is ever returned to AccumulateGrad while a collective may still write it, and
+    every buffer is reduced exactly once per backward however many autograd nodes fed it."""
+
+    def __init__(self, modules, group=None, average: bool = True):
+        self.group, self.average = group, average
         self.modules = list(modules)
-        self._pending: List = []
-        self._callback_queued = False
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._fwd = {id(m): 0 for m in self.modules}
+        self._pub = {id(m): [] for m in self.modules}        # published (offset, n) ranges of the module's buffer
+        self._touched = set()                                 # modules that ran a backward node in this session
+        self._active = False
+        self._prezero = None                                  # event of a zero-fill running on the side stream
+        self._zero_stream = None
         self.bytes_reduced = 0
+        self.sessions = 0
         for m in self.modules:
-            m._grad_hooks.append(self._on_grad)
+            if getattr(m, "_dp", None) is not None:
+                raise RuntimeError("module already has a gradient exchange attached")
+            m._dp = self
 
+    # -- to be provided -----------------------------------------------------------------------------------------
+    def _buffer(self, m) -> torch.Tensor:                     # persistent flat gradient buffer of module m
+        raise NotImplementedError
+
+    def _reduce(self, m, offset: int, n: int):                # start the exchange of floats [offset, offset+n) of m's buffer
+        raise NotImplementedError
+
+    def _reduce_all(self) -> bool:                            # optional: one exchange for everything; True if done
+        return False
+
+    def _join(self):                                          # compute stream waits for every exchange started
+        pass
+
+    def chunks(self, m) -> int:                               # pieces the last backward node of m should publish in
+        return 1
+
+    # -- module side ----------------------------------------------------------------------------------------------
     def remove(self):
         for m in self.modules:
-            if self._on_grad in m._grad_hooks:
-                m._grad_hooks.remove(self._on_grad)
+            if getattr(m, "_dp", None) is self:
+                m._dp = None
 
-    def _on_grad(self, flat: torch.Tensor):
-        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+    def _zero_buffers(self):
+        for m in self.modules:
+            self._buffer(m).zero_()
+
+    def _detach_aliases(self):
+        """A parameter whose .grad still IS the persistent buffer (the caller kept gradients: zero_grad(set_to_none=False)
+        or gradient accumulation) gets its own copy before the buffer is reused."""
+        for m in self.modules:
+            for p, v in m._dp_param_views(self._buffer(m)):
+                if p.grad is not None and p.grad.data_ptr() == v.data_ptr():
+                    p.grad = p.grad.clone()
+
+    def note_forward(self, m):
+        first = not self._active and self._prezero is None and not any(self._fwd.values())
+        self._fwd[id(m)] += 1
+        if first and self._buffer(m).is_cuda:
+            self._detach_aliases()
+            cur = torch.cuda.current_stream()
+            if self._zero_stream is None:
+                self._zero_stream = torch.cuda.Stream()
+            self._zero_stream.wait_stream(cur)                # everything that still reads last step's gradients is enqueued
+            with torch.cuda.stream(self._zero_stream):
+                self._zero_buffers()
+                self._prezero = self._zero_stream.record_event()
+
+    def _begin(self):
+        if self._active:
             return
+        self._active = True
+        self.sessions += 1
+        Variable._execution_engine.queue_callback(self._finish)
+        if self._prezero is not None:
+            torch.cuda.current_stream().wait_event(self._prezero)
+            self._prezero = None
+        else:
+            self._detach_aliases()
+            self._zero_buffers()
+
+    def enter_backward(self, m):
+        self._begin()
+        k = id(m)
+        self._touched.add(k)
+        self._fwd[k] = max(self._fwd[k] - 1, 0)
+        return self._buffer(m), self._fwd[k] == 0
+
+    def publish(self, m, piece: torch.Tensor):
+        buf = self._buffer(m)
+        off = (piece.data_ptr() - buf.data_ptr()) // buf.element_size()
+        n = piece.numel()
+        if self._start_on_publish():
+            self._reduce(m, off, n)
+            self._pub[id(m)].append((off, n))
+
+    def _start_on_publish(self) -> bool:
+        return True
+
+    def _gaps(self, m):
+        total = self._buffer(m).numel()
+        pos, out = 0, []
+        for off, n in sorted(self._pub[id(m)]):
+            if off > pos:
+                out.append((pos, off - pos))
+            pos = max(pos, off + n)
+        if pos < total:
+            out.append((pos, total - pos))
+        return out
+
+    def _finish(self):
+        try:
+            if self.world > 1:
+                nothing = not any(self._pub.values())
+                if not (nothing and self._reduce_all()):
+                    for m in self.modules:
+                        if id(m) not in self._touched:           # took no part in this backward (same on every rank)
+                            continue
+                        for off, n in self._gaps(m):
+                            self._reduce(m, off, n)
+                self._join()
+            for m in self.modules:
+                if id(m) not in self._touched:
+                    continue
+                for p, v in m._dp_param_views(self._buffer(m)):
+                    if not p.requires_grad:
+                        continue
+                    if p.grad is None:
+                        p.grad = v
+                    else:
+                        p.grad.add_(v)
+        finally:
+            self._active = False
+            self._touched = set()
+            for k in self._fwd:
+                self._fwd[k] = 0
+                self._pub[k] = []
+
+
+class GradAllReduce(_GradExchange):
+    """`GradAllReduce(encoder, mlp)`: the exchange as asynchronous torch.distributed all-reduces (NCCL; gloo on CPU ranks)
+    on persistent flat gradient buffers.  Detach with `.remove()`."""
+
+    def __init__(self, *modules, group=None, average: bool = True, chunks: int = 1):
+        super().__init__(modules, group=group, average=average)
+        self._bufs = {}
+        self._pending: List = []
+        self._chunks = int(chunks)
+
+    def chunks(self, m) -> int:
+        return max(1, int(getattr(m, "_grad_chunks", 0) or self._chunks))
+
+    def _buffer(self, m):
+        b = self._bufs.get(id(m))
+        t = m._dp_template()
+        if b is None or b.device != t.device or b.shape != t.shape:
+            b = self._bufs[id(m)] = torch.zeros_like(t)
+        return b
+
+    def _reduce(self, m, offset, n):
+        if not dist.is_initialized() or self.world == 1:
+            return
+        flat = self._buffer(m).view(-1)[offset:offset + n]
         op = dist.ReduceOp.SUM
         if self.average:
             if dist.get_backend(self.group) == "nccl":
-                op = dist.ReduceOp.AVG                     # averaging inside the collective: no extra pass over the buffer
+                op = dist.ReduceOp.AVG                        # averaging inside the collective: no extra pass over the buffer
             else:
-                flat.div_(dist.get_world_size(self.group))
+                flat.div_(self.world)
         self._pending.append(dist.all_reduce(flat, op=op, group=self.group, async_op=True))
-        self.bytes_reduced += flat.numel() * flat.element_size()
-        if not self._callback_queued:
-            self._callback_queued = True
-            Variable._execution_engine.queue_callback(self._finish)
+        self.bytes_reduced += n * flat.element_size()
 
-    def _finish(self):
+    def _join(self):
         for w in self._pending:
-            w.wait()                       # compute stream waits on the NCCL stream; no host sync for CUDA tensors
+            w.wait()                       # compute stream waits on the collective's stream; no host sync for CUDA tensors
         self._pending.clear()
-        self._callback_queued = False
 
 
-class PeerGradAllReduce:
-    """`PeerGradAllReduce(encoder, mlp)`: the same contract as GradAllReduce, but the exchange is ONE kernel over NVLink
-    peer memory (csrc/comm.cu) instead of NCCL calls.  The two modules' flat gradients become slices of one persistent
-    peer-mapped region [table (L,T,F) | MLP parameters]; the scatter-add of the hash-grid backward and the MLP
-    gradient reduction write straight into it, and an end-of-backward engine callback enqueues hbr_allreduce_peer on
-    the compute stream (no extra stream, no event round trip, capturable in the step's CUDA graph).  Every rank ends
-    with bit-identical averaged gradients.  `.grad` of the parameters aliases the region from step to step (use
-    zero_grad(set_to_none=True), torch's default)."""
+class PeerGradAllReduce(_GradExchange):
+    """`PeerGradAllReduce(encoder, mlp)`: the same contract, but the exchange is ONE kernel over NVLink peer memory
+    (csrc/comm.cu) instead of NCCL calls.  The two modules' gradient buffers are slices of one persistent peer-mapped region
+    [table (L,T,F) | MLP parameters]; the scatter-add of the hash-grid backward and the MLP gradient reduction write
+    straight into it, and hbr_allreduce_peer runs on the compute stream behind them (capturable in the step's CUDA
+    graph).  Every rank ends with bit-identical averaged gradients.  A failed exchange (flag-barrier timeout) raises at
+    the next step's end of backward instead of letting the optimiser run on."""
 
     def __init__(self, encoder, mlp, group=None, average: bool = True, transport: str = "ipc", ctas: int = 0,
                  overlap: bool = False, chunks: int = 2):
-        """overlap=False: one all-reduce of the whole region behind the backward pass.  overlap=True: the table backward
-        runs in `chunks` level chunks and every published piece (the MLP gradient first, then each level chunk) is
-        all-reduced at once by a small grid (`ctas`, default 32) on a high-priority side stream while the next chunk's
+        """overlap=False: one all-reduce of the whole region behind the backward pass.  overlap=True: the LAST table backward
+        of the pass runs in `chunks` level chunks and every published piece (the MLP gradient first, then each level chunk)
+        is all-reduced at once by a small grid (`ctas`, default 32) on a high-priority side stream while the next chunk's
         scatter-add still runs on the compute stream."""
         from .peer import PeerRegion
-        self.group, self.average, self.overlap = group, average, overlap
-        self.ctas = ctas if ctas > 0 else (32 if overlap else 0)
-        self.modules = [encoder, mlp]
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         n_tab = encoder.L * encoder.T * encoder.F
         n_mlp = mlp._flat_params().numel()
         off = -(-n_tab // 4) * 4
         self.region = PeerRegion(off + n_mlp, group=group, transport=transport)
+        self.overlap = overlap
+        self.ctas = ctas if ctas > 0 else (32 if overlap else 0)
+        self._nchunks = int(chunks)
+        self._enc, self._mlp = encoder, mlp
         encoder._flat_table()
-        encoder._grad_buffer = self.region.tensor[:n_tab].view(encoder.L, encoder.T, encoder.F)
-        mlp._grad_buffer = self.region.tensor[off:off + n_mlp]
-        if overlap:
-            encoder._grad_chunks = chunks
+        self._slices = {id(encoder): self.region.tensor[:n_tab].view(encoder.L, encoder.T, encoder.F),
+                        id(mlp): self.region.tensor[off:off + n_mlp]}
         self._side = torch.cuda.Stream(device=self.region.device, priority=-1) if overlap else None
         self._base = self.region.tensor.data_ptr()
-        self._callback_queued = False
         self._side_used = False
-        self.bytes_reduced = 0
-        for m in self.modules:
-            m._grad_hooks.append(self._on_grad)
+        super().__init__([encoder, mlp], group=group, average=average)
 
     def remove(self):
-        for m in self.modules:
-            if self._on_grad in m._grad_hooks:
-                m._grad_hooks.remove(self._on_grad)
-            m._grad_buffer = None
+        super().remove()
+
+    def chunks(self, m) -> int:
+        return self._nchunks if (self.overlap and m is self._enc) else 1
 
     def _scale(self):
         return 1.0 / self.world if self.average else 1.0
 
-    def _on_grad(self, flat: torch.Tensor):
-        if not self._callback_queued:
-            self._callback_queued = True
-            Variable._execution_engine.queue_callback(self._finish)
-        if self.overlap:
-            off = (flat.data_ptr() - self._base) // 4
-            n = -(-flat.numel() // 4) * 4
+    def _buffer(self, m):
+        return self._slices[id(m)]
+
+    def _zero_buffers(self):
+        self.region.tensor.zero_()                            # one memset over [table | MLP]
+
+    def _start_on_publish(self) -> bool:
+        return self.overlap
+
+    def _reduce(self, m, offset, n):
+        off = (self._buffer(m).data_ptr() - self._base) // 4 + offset
+        lo = off // 4 * 4                                     # whole float4s; the slack belongs to padding or a piece reduced
+        n4 = -(-(off + n - lo) // 4) * 4                      # in the same call sequence on every rank
+        if self._side is not None:
             cur = torch.cuda.current_stream()
             self._side.wait_stream(cur)                       # the piece's producer kernel has been enqueued on `cur`
             with torch.cuda.stream(self._side):
-                self.region.all_reduce(n=n, scale=self._scale(), ctas=self.ctas, offset=off)
+                self.region.all_reduce(n=n4, scale=self._scale(), ctas=self.ctas, offset=lo)
             self._side_used = True
-            self.bytes_reduced += n * 4
+        else:
+            self.region.all_reduce(n=n4, scale=self._scale(), ctas=self.ctas, offset=lo)
+        self.bytes_reduced += n4 * 4
 
-    def _finish(self):
-        self._callback_queued = False
-        if self.overlap:
-            if self._side_used:
-                torch.cuda.current_stream().wait_stream(self._side)
-                self._side_used = False
-            return
+    def _reduce_all(self) -> bool:
+        if self._side is not None:
+            return False
         self.region.all_reduce(scale=self._scale(), ctas=self.ctas)
         self.bytes_reduced += self.region.n * 4
+        return True
+
+    def _join(self):
+        if self._side_used:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_used = False
+        self.region.raise_if_failed()                         # the status word copied out at the end of the PREVIOUS step
+        self.region.poll_status()
 
 
 def attach_grad_allreduce(encoder, mlp, group=None, kind: str = "auto", **peer_kw):
@@ -160,7 +318,7 @@ def attach_grad_allreduce(encoder, mlp, group=None, kind: str = "auto", **peer_k
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return None
     if kind == "nccl" or not torch.cuda.is_available() or dist.get_backend(group) != "nccl":
-        return GradAllReduce(encoder, mlp, group=group)
+        return GradAllReduce(encoder, mlp, group=group, chunks=int(peer_kw.get("chunks", 1)) if kind == "nccl" else 1)
     world = dist.get_world_size(group)
     kw = dict(peer_kw)
     kw.setdefault("overlap", True)        # measured best at 4 096 rays/GPU: 2 level chunks, 32 CTAs on the side stream
@@ -181,6 +339,27 @@ def attach_grad_allreduce(encoder, mlp, group=None, kind: str = "auto", **peer_k
     if kind == "peer":
         raise RuntimeError(f"peer-memory all-reduce unavailable on at least one rank: {err!r}")
     return GradAllReduce(encoder, mlp, group=group)
+
+
+def broadcast_parameters(encoder, mlp, src: int = 0, group=None):
+    """Every rank takes rank `src`'s hash tables and MLP parameters (the unchanged trainer does not seed: each process
+    initialised its own).  Two broadcasts of the flat buffers."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        dist.broadcast(encoder._flat_table(), src=src, group=group)
+        dist.broadcast(mlp._flat_params(), src=src, group=group)
+
+
+def auto_attach(encoder, mlp, group=None):
+    """launch_rank.py's zero-edit route (HBR_AUTO_DP=1): called by Volume_Renderer at its first native vol_render of a
+    process that belongs to a process group -- broadcast rank 0's parameters, attach the gradient exchange (once)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    if getattr(encoder, "_dp", None) is not None:
+        return encoder._dp
+    broadcast_parameters(encoder, mlp, 0, group)
+    return attach_grad_allreduce(encoder, mlp, group=group)
 
 
 def shard_rays(n_rays: int, rank: int, world: int) -> slice:

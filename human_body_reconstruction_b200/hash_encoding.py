@@ -24,7 +24,12 @@ class _HashEncodeFn(torch.autograd.Function):
         ctx.enc = enc
         ctx.geom = geom
         ctx.save_for_backward(x)
-        ctx.g = enc._zeroed_grad_async() if any(ctx.needs_input_grad[2:]) else None
+        ctx.g = None
+        if any(ctx.needs_input_grad[2:]):
+            if enc._dp is not None:
+                enc._dp.note_forward(enc)
+            else:
+                ctx.g = enc._zeroed_grad_async()
         return y
 
     @staticmethod
@@ -32,20 +37,28 @@ class _HashEncodeFn(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         enc = ctx.enc
         L, T, F = enc.L, enc.T, enc.F
+        dp = enc._dp
+        if dp is not None:
+            # Data-parallel run (dist._GradExchange): accumulate into the persistent buffer of this backward pass.  The
+            # last table backward of the pass runs in level chunks and publishes each one as soon as its scatter-add is
+            # enqueued: that chunk's all-reduce travels over NVLink while the next chunk's scatter-add still runs.  The
+            # exchange hands the reduced buffer to .grad at the end of backward; nothing is returned to autograd here.
+            g, last = dp.enter_backward(enc)
+            nch = max(1, min(L, dp.chunks(enc))) if last else 1
+            step = -(-L // nch)
+            for l0 in range(0, L, step):
+                l1 = min(L, l0 + step)
+                ops.hash_encode_bwd(x, dy[:, : L * F], ctx.geom, g, l0, l1)
+                if last:
+                    dp.publish(enc, g[l0:l1])
+            return (None, None) + (None,) * L
         if ctx.g is not None:
             g, ev = ctx.g
             ctx.g = None
             torch.cuda.current_stream().wait_event(ev)
         else:
-            g = enc._new_grad(dy.device)
-        # With gradient hooks attached (multi-GPU) the pass runs in level chunks and every finished chunk is published
-        # at once: its all-reduce travels over NVLink while the next chunk's scatter-add still runs.
-        nch = max(1, min(L, enc._grad_chunks)) if enc._grad_hooks else 1
-        step = -(-L // nch)
-        for l0 in range(0, L, step):
-            l1 = min(L, l0 + step)
-            ops.hash_encode_bwd(x, dy[:, : L * F], ctx.geom, g, l0, l1)
-            enc._publish_grad(g[l0:l1])
+            g = torch.zeros((L, T, F), device=dy.device, dtype=torch.float32)
+        ops.hash_encode_bwd(x, dy[:, : L * F], ctx.geom, g, 0, L)
         # no gradient w.r.t. x: the interpolation weights are detached in the reference (hash_encoding.py:160)
         return (None, None) + tuple(g[i] for i in range(L))
 
@@ -75,14 +88,8 @@ class HashEncoder(nn.Module):
         self.Embedding_list = nn.ModuleList(tables)
         self._scales = [float((self.N_min * self.b ** i).to(torch.float32)) for i in range(self.L)]   # :153
         self._host_geom = None
-        self._grad_hooks = []
         self._side = None
-        # level chunks of the backward pass when gradient hooks are attached (each chunk is published -- all-reduced --
-        # as soon as it is enqueued).  Measured on 2 x B200 at 4096 rays/GPU, overlapping the NCCL kernels with the
-        # scatter-add slows both (0.90 ms/step with 4 chunks against 0.79 ms with one all-reduce after the pass), so the
-        # default is one chunk; larger per-GPU batches may prefer more.
-        self._grad_chunks = 1
-        self._grad_buffer = None
+        self._dp = None               # the data-parallel gradient exchange attached to this module (dist._GradExchange)
         self._flat = None
         self._reflatten()
 
@@ -141,24 +148,17 @@ class HashEncoder(nn.Module):
             side = self._side = torch.cuda.Stream(device=dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            g = self._new_grad(dev)
+            g = torch.zeros((self.L, self.T, self.F), device=dev, dtype=torch.float32)
             ev = side.record_event()
         g.record_stream(cur)
         return g, ev
 
-    def _new_grad(self, dev):
-        """Zero-filled (L,T,F) gradient buffer: fresh, or -- when dist.PeerGradAllReduce installed one -- the persistent
-        peer-mapped buffer the NVLink all-reduce kernel works on in place (then `.grad` of the level tables aliases it
-        from step to step: use optimizer.zero_grad(set_to_none=True), torch's default)."""
-        buf = self._grad_buffer
-        if buf is not None and buf.device == dev:
-            return buf.zero_()
-        return torch.zeros((self.L, self.T, self.F), device=dev, dtype=torch.float32)
+    # -- data-parallel gradient exchange (dist._GradExchange) ---------------------------------------------------
+    def _dp_template(self) -> torch.Tensor:
+        return self._flat_table()
 
-    # -- gradient publication (dist.py hooks the flat gradient for the NCCL all-reduce) -------------------
-    def _publish_grad(self, g: torch.Tensor):
-        for h in self._grad_hooks:
-            h(g)
+    def _dp_param_views(self, buf: torch.Tensor):
+        return [(e.weight, buf[i]) for i, e in enumerate(self.Embedding_list)]
 
     def level_scales(self):
         return list(self._scales)

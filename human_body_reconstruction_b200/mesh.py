@@ -65,3 +65,34 @@ def marching_cubes(density: torch.Tensor, iso: float):
     nv, nt = marching_cubes_counts(density, iso)
     verts, faces, _ = ops.mc_emit(density, iso, nv, nt)
     return verts, faces
+
+
+def _device_for(t: torch.Tensor) -> torch.device:
+    if t.is_cuda:
+        return t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("marching cubes / grid_interp run on a CUDA device (there is no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def marching_cubes_xyz(vol: torch.Tensor, iso: float):
+    """torchmcubes.marching_cubes as nerf2mesh.py:95-98 calls it: `vol` may live on the CPU (it does there) -- it is
+    uploaded, meshed on the GPU and the result returned on vol's device.  Vertices are (x, y, z) = (index along axis 2,
+    axis 1, axis 0), torchmcubes' order for a volume indexed [z, y, x]; faces (F,3) int32."""
+    dev = _device_for(vol)
+    d = vol.detach().to(dev, torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        verts, faces = marching_cubes(d, iso)
+        verts = verts.flip(-1).contiguous()
+    return verts.to(vol.device), faces.to(vol.device)
+
+
+def grid_interp(vol: torch.Tensor, points: torch.Tensor) -> torch.Tensor:
+    """torchmcubes.grid_interp (nerf2mesh.py:99): vol (C,Nz,Ny,Nx) or (Nz,Ny,Nx), points (V,3) as (x,y,z) -> (V,C)."""
+    dev = _device_for(vol if vol.is_cuda else points)
+    v = vol.detach().to(dev, torch.float32)
+    if v.dim() == 3:
+        v = v[None]
+    with torch.cuda.device(dev):
+        out = ops.grid_interp(v.contiguous(), points.detach().to(dev, torch.float32).contiguous())
+    return out.to(points.device)

@@ -419,3 +419,14 @@ def mc_emit(density: torch.Tensor, iso: float, n_verts: int, n_faces: int):
     check(lib().hbr_mc_emit(ptr(density), n0, n1, n2, float(iso), 0, n0, ptr(edge_id), ptr(verts), n_verts, ptr(faces),
                             n_faces, ptr(cursors), stream()))
     return verts[:n_verts], faces[:n_faces], cursors
+
+
+def grid_interp(vol: torch.Tensor, pts: torch.Tensor) -> torch.Tensor:
+    """vol (C,n0,n1,n2) fp32, pts (n,3) as (x,y,z) = (axis 2, axis 1, axis 0) index coordinates -> (n,C)."""
+    require_cuda(vol, pts)
+    vol, pts = _f32c(vol), _f32c(pts)
+    C_, n0, n1, n2 = vol.shape
+    n = pts.shape[0]
+    out = torch.empty((n, C_), device=vol.device, dtype=torch.float32)
+    check(lib().hbr_grid_interp(ptr(vol), C_, n0, n1, n2, ptr(pts), n, ptr(out), stream()))
+    return out

@@ -60,6 +60,7 @@ class PeerRegion:
         self._bufs = (C.c_void_p * W)(*[C.c_void_p(p) for p in self.ptrs])
         self._flags = (C.c_void_p * W)(*[C.c_void_p(p + self._flag_off) for p in self.ptrs])
         self._status_ptr = C.c_void_p(self.ptrs[self.rank] + self._status_off)
+        self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.calls = 0
 
     # -- transports ------------------------------------------------------------------------------------------
@@ -120,6 +121,18 @@ class PeerRegion:
         check(lib().hbr_allreduce_peer(bufs, self._flags, mc, self.rank, self.world, n, float(scale), int(ctas),
                                        self._status_ptr, _lib.stream()))
         self.calls += 1
+
+    def poll_status(self):
+        """Enqueue a 4-byte copy of the status word to pinned host memory on the current stream (capturable; no sync)."""
+        word = self._whole[self._status_off // 4: self._status_off // 4 + 1].view(torch.int32)
+        self._status_host.copy_(word, non_blocking=True)
+
+    def raise_if_failed(self):
+        """Raises if a status copy that has ALREADY landed shows a failed exchange (a flag barrier timed out on some earlier
+        all_reduce: this rank's gradients were left unreduced).  Never synchronises: detection lags by at most one step."""
+        if int(self._status_host[0]) != 0:
+            raise RuntimeError("peer-memory gradient all-reduce failed: a flag barrier timed out (a rank stalled or died); "
+                               "gradients of that step were NOT reduced -- stop and restart the ranks")
 
     def timed_out(self) -> bool:
         """True if a flag barrier of any all_reduce so far gave up (synchronises)."""

@@ -34,6 +34,8 @@ class _MlpFn(torch.autograd.Function):
             out, act = ops.mlp_fwd_tc(feat, dirs, dir_group, flat, dims, keep_act=train, operand=use_tc)
         else:
             out, act = ops.mlp_fwd_f32(feat, dirs, dir_group, flat, dims, keep_act=train)
+        if mlp._dp is not None and any(ctx.needs_input_grad[5:]):
+            mlp._dp.note_forward(mlp)
         ctx.mlp, ctx.dims, ctx.dir_group, ctx.use_tc = mlp, dims, dir_group, use_tc
         ctx.save_for_backward(feat, dirs, out if use_tc else act)     # the tensor-core backward reads the saved output
         return out
@@ -43,7 +45,11 @@ class _MlpFn(torch.autograd.Function):
         feat, dirs, act = ctx.saved_tensors
         mlp = ctx.mlp
         flat = mlp._flat_params()
-        dflat = mlp._grad_buffer.zero_() if mlp._grad_buffer is not None else torch.zeros_like(flat)
+        dp = mlp._dp if any(ctx.needs_input_grad[5:]) else None
+        if dp is not None:
+            dflat, last = dp.enter_backward(mlp)      # persistent buffer of this backward pass, accumulated into
+        else:
+            dflat, last = torch.zeros_like(flat), False
         dout = dout.float().contiguous()
         want_dfeat, want_ddirs = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if ctx.use_tc:
@@ -51,7 +57,10 @@ class _MlpFn(torch.autograd.Function):
                                           dflat, operand=ctx.use_tc, grad_scale=mlp.tc_grad_scale)
         else:
             dfeat, ddirs = ops.mlp_bwd_f32(feat, dirs, ctx.dir_group, flat, ctx.dims, dout, act, want_dfeat, want_ddirs, dflat)
-        mlp._publish_grad(dflat)
+        if dp is not None:
+            if last:
+                dp.publish(mlp, dflat)
+            return (dfeat, ddirs, None, None, None) + (None,) * len(mlp._ordered())
         return (dfeat, ddirs, None, None, None) + tuple(mlp._grad_views(dflat))
 
 
@@ -86,8 +95,7 @@ class MLP_3D(nn.Module):
         # operand format (and divides out of its results).  The reference's trainer scales the loss with GradScaler
         # (train_hash2.py:156,226), which does the same job from outside; set this when running fp16 operands without one.
         self.tc_grad_scale = 1.0
-        self._grad_hooks = []
-        self._grad_buffer = None     # persistent (peer-mapped) flat gradient buffer, see dist.PeerGradAllReduce
+        self._dp = None               # the data-parallel gradient exchange attached to this module (dist._GradExchange)
         self._flat = None
         if self._native:
             self._reflatten()
@@ -143,9 +151,11 @@ class MLP_3D(nn.Module):
     def _dims(self) -> MlpDims:
         return MlpDims(self._in0, self.d_view)
 
-    def _publish_grad(self, g):
-        for h in self._grad_hooks:
-            h(g)
+    def _dp_template(self) -> torch.Tensor:
+        return self._flat_params()
+
+    def _dp_param_views(self, buf: torch.Tensor):
+        return list(zip(self._ordered(), self._grad_views(buf)))
 
     def _check_native(self):
         if not self._native:

@@ -11,6 +11,7 @@ The legacy classic-NeRF MLP class (vol_renderer.py:12-86) is not part of the hot
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -34,6 +35,9 @@ class _FieldFn(torch.autograd.Function):
         operand = ops.tc_operand()
         out, feat16 = ops.field_fwd_tc(pts, enc._flat_table(), geom, dirs, dir_group, mlp._flat_params(), dims, operand)
         ctx.enc, ctx.mlp, ctx.geom, ctx.dims, ctx.dir_group, ctx.operand = enc, mlp, geom, dims, dir_group, operand
+        if enc._dp is not None:
+            enc._dp.note_forward(enc)
+            mlp._dp.note_forward(mlp)
         ctx.save_for_backward(pts, dirs, feat16, out)
         return out
 
@@ -42,14 +46,23 @@ class _FieldFn(torch.autograd.Function):
         pts, dirs, feat16, out = ctx.saved_tensors
         enc, mlp = ctx.enc, ctx.mlp
         L, T, F = enc.L, enc.T, enc.F
-        g = enc._new_grad(dout.device)
         flat = mlp._flat_params()
-        dflat = mlp._grad_buffer.zero_() if mlp._grad_buffer is not None else torch.zeros_like(flat)
+        dp = enc._dp
+        if dp is not None:
+            g, last_e = dp.enter_backward(enc)
+            dflat, last_m = mlp._dp.enter_backward(mlp)
+        else:
+            g = torch.zeros((L, T, F), device=dout.device, dtype=torch.float32)
+            dflat = torch.zeros_like(flat)
         ddirs = ops.field_bwd_tc(pts, ctx.geom, dirs, ctx.dir_group, flat, ctx.dims, feat16, out.detach(),
                                  dout.float().contiguous(), g, ctx.needs_input_grad[1], dflat, operand=ctx.operand,
                                  grad_scale=mlp.tc_grad_scale)
-        mlp._publish_grad(dflat)
-        enc._publish_grad(g)
+        if dp is not None:
+            if last_m:
+                mlp._dp.publish(mlp, dflat)
+            if last_e:
+                dp.publish(enc, g)
+            return (None, ddirs, None, None, None) + (None,) * (L + len(mlp._ordered()))
         return (None, ddirs, None, None, None) + tuple(g[i] for i in range(L)) + tuple(mlp._grad_views(dflat))
 
 
@@ -82,6 +95,7 @@ class Volume_Renderer:
         self.reset_mask = False
         self.use_sdf = use_sdf
         self.var_model = var_model
+        self._dp_checked = False
         self._grid_state = (None, True)           # (bool_grid._version, all_true)
         self._host_norm = None
         # Encoder + MLP fused into one kernel per direction (hbr_field_*_tc): no fp32 feature / d(feature) tensors in HBM
@@ -135,7 +149,7 @@ class Volume_Renderer:
         ok = (enc.F == 2 and enc.L == 16 and enc.E == 0 and enc.T >= 2 and (enc.T & (enc.T - 1)) == 0
               and mlp._in0 == 32 and mlp.d_view <= 25)
         if self.fuse_field == "auto":
-            ok = ok and not enc._grad_hooks
+            ok = ok and enc._dp is None
         return ok
 
     def _field_pass(self, mlp, rays_o, rays_d, t, dir_enc, dir_norm, mask_needed):
@@ -164,6 +178,11 @@ class Volume_Renderer:
         if t is None:
             t = strat_sampler(near, far, num_samples, device=rays_d.device)                 # RNG draw #1
         mlp = self._native(model)
+        if mlp is not None and not self._dp_checked:
+            self._dp_checked = True
+            if os.environ.get("HBR_AUTO_DP") == "1":            # launch_rank.py: zero-edit multi-GPU run of the trainer
+                from . import dist as _hdist
+                _hdist.auto_attach(self.Pos_encode, mlp)
         if mlp is None:
             return self._generic(model, rays_d, rays_o, t, update_mask, dir_norm, hierarchical, _u, _u_cand)
 

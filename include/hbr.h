@@ -196,6 +196,11 @@ int hbr_mc_emit(const float* density, int n0, int n1, int n2, float iso, int i_b
                 int32_t* edge_id, float* verts, int64_t max_verts, int32_t* faces, int64_t max_faces,
                 unsigned long long* cursors, void* stream);
 
+/* a14: torchmcubes.grid_interp (nerf2mesh.py:99): trilinear samples of vol (C, n0, n1, n2) fp32 at pts (n,3) given as
+ * (x, y, z) = (index along axis 2, axis 1, axis 0) in grid-index units (the order torchmcubes returns vertices in),
+ * clamped to the volume; out (n, C). */
+int hbr_grid_interp(const float* vol, int C, int n0, int n1, int n2, const float* pts, int64_t n, float* out, void* stream);
+
 /* ---- 8f row 1: the optimiser step of train_hash2.py:141-142,227-228 (torch.optim.Adam / AdamW) as ONE pass --------
  * param / grad / exp_avg / exp_avg_sq: n fp32 each (the flat table or MLP buffer).  step >= 1 is the 1-based step count.
  * grad is multiplied by inv_scale (GradScaler unscale, 1.0 without AMP); with found_inf != NULL and *found_inf != 0 the

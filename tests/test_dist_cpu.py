@@ -1,7 +1,8 @@
 """CPU tests (world_size 2, gloo) of the N > 1 host logic in human_body_reconstruction_b200/dist.py:
 ray sharding, the flat-gradient all-reduce launched from inside backward (DDP-style end-of-backward wait),
 slab sharding of the density grid and the all-gather of marching-cubes counts.  The kernels themselves need a GPU;
-here stand-in modules publish CPU gradients through the same `_grad_hooks` protocol HashEncoder / MLP_3D use."""
+here stand-in modules speak the same dist._GradExchange protocol HashEncoder / MLP_3D use, including several passes
+through one module inside one backward (hierarchical render) and gradient accumulation across backward calls."""
 import os
 import socket
 
@@ -22,16 +23,23 @@ def _free_port():
 
 
 class _FlatGradModule(torch.nn.Module):
-    """Stand-in for HashEncoder / MLP_3D: per-"level" parameters that are views of one flat buffer; the backward
-    publishes ONE flat gradient buffer through `_grad_hooks` (optionally in level chunks) and hands autograd views."""
+    """Stand-in for HashEncoder / MLP_3D: per-"level" parameters that are views of one flat buffer, speaking the modules'
+    side of the dist._GradExchange protocol (note_forward / enter_backward / publish, gradients never returned to
+    autograd while a reducer is attached)."""
 
     def __init__(self, levels, width, chunks=1):
         super().__init__()
         g = torch.Generator().manual_seed(7)
         self.flat = torch.randn(levels, width, generator=g)
         self.levels = torch.nn.ParameterList([torch.nn.Parameter(self.flat[i]) for i in range(levels)])
-        self._grad_hooks = []
-        self.chunks = chunks
+        self._dp = None
+        self._grad_chunks = chunks
+
+    def _dp_template(self):
+        return self.flat
+
+    def _dp_param_views(self, buf):
+        return [(p, buf[i]) for i, p in enumerate(self.levels)]
 
     def forward(self, x):
         mod = self
@@ -40,20 +48,26 @@ class _FlatGradModule(torch.nn.Module):
             @staticmethod
             def forward(ctx, x, *w):
                 ctx.save_for_backward(x)
+                if mod._dp is not None:
+                    mod._dp.note_forward(mod)
                 return x @ mod.flat.detach().T                       # (N, levels)
 
             @staticmethod
             def backward(ctx, dy):
                 (x,) = ctx.saved_tensors
-                gflat = torch.zeros_like(mod.flat)
-                L = gflat.shape[0]
-                step = -(-L // mod.chunks)
+                L = mod.flat.shape[0]
+                if mod._dp is None:
+                    gflat = dy.T @ x
+                    return (None,) + tuple(gflat[i] for i in range(L))
+                gflat, last = mod._dp.enter_backward(mod)
+                nch = mod._dp.chunks(mod) if last else 1
+                step = -(-L // nch)
                 for l0 in range(0, L, step):                         # level chunks, published as they complete
                     l1 = min(L, l0 + step)
-                    gflat[l0:l1] = dy[:, l0:l1].T @ x
-                    for h in mod._grad_hooks:
-                        h(gflat[l0:l1])
-                return (None,) + tuple(gflat[i] for i in range(L))
+                    gflat[l0:l1] += dy[:, l0:l1].T @ x
+                    if last:
+                        mod._dp.publish(mod, gflat[l0:l1])
+                return (None,) * (L + 1)
 
         return Fn.apply(x, *self.levels)
 
@@ -66,9 +80,18 @@ def _worker(rank, world, port_no, tmp):
     n_rays, width, levels = 64, 5, 6
     g = torch.Generator().manual_seed(3)
     x_all = torch.randn(n_rays, width, generator=g)
+    x2_all = torch.randn(n_rays, width, generator=g)
     gt_all = torch.randn(n_rays, levels, generator=g)
 
-    for chunks in (1, 3):
+    def loss_of(mod, sl, passes):
+        # passes == 2: the module is evaluated twice inside one loss, like the coarse + fine render of
+        # vol_renderer.py:220,242 -- two autograd nodes feeding the same flat gradient
+        loss = torch.nn.functional.mse_loss(mod(x_all[sl]), gt_all[sl])   # mean over the LOCAL batch
+        if passes == 2:
+            loss = loss + torch.nn.functional.mse_loss(mod(x2_all[sl]), gt_all[sl])
+        return loss
+
+    for chunks, passes in ((1, 1), (3, 1), (1, 2), (3, 2)):
         mod = _FlatGradModule(levels, width, chunks=chunks)
         if chunks == 1:
             reducer = hdist.GradAllReduce(mod)
@@ -76,17 +99,21 @@ def _worker(rank, world, port_no, tmp):
             reducer = hdist.attach_grad_allreduce(mod, _FlatGradModule(levels, width))
             assert isinstance(reducer, hdist.GradAllReduce)
         sl = hdist.shard_rays(n_rays, rank, world)
-        loss = torch.nn.functional.mse_loss(mod(x_all[sl]), gt_all[sl])   # mean over the LOCAL batch
-        loss.backward()
+        loss_of(mod, sl, passes).backward()
         got = torch.stack([p.grad for p in mod.levels])
         # single-process gradient of the concatenated batch
         ref = _FlatGradModule(levels, width)
-        torch.nn.functional.mse_loss(ref(x_all), gt_all).backward()
+        loss_of(ref, slice(None), passes).backward()
         want = torch.stack([p.grad for p in ref.levels])
-        assert torch.allclose(got, want, rtol=1e-5, atol=1e-6), (rank, chunks, (got - want).abs().max())
-        assert reducer.bytes_reduced == levels * width * 4
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-6), (rank, chunks, passes, (got - want).abs().max())
+        assert reducer.bytes_reduced == levels * width * 4, "every buffer is reduced exactly once per backward"
+        # a second backward WITHOUT clearing .grad accumulates (the persistent buffer is not handed out twice)
+        loss_of(mod, sl, passes).backward()
+        got2 = torch.stack([p.grad for p in mod.levels])
+        assert torch.allclose(got2, 2 * want, rtol=1e-5, atol=1e-6), (rank, chunks, passes)
+        assert reducer.sessions == 2
         reducer.remove()
-        assert not mod._grad_hooks
+        assert mod._dp is None
 
     # density-grid slabs: disjoint, ordered, covering; per-slab crossing-edge counts add up to the whole grid's
     res = 11

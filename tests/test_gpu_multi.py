@@ -1,5 +1,7 @@
 """Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise): rays sharded over 2 ranks, gradients all-reduced
-inside backward by dist.GradAllReduce over NCCL == single-GPU gradients of the concatenated batch."""
+inside backward by dist.GradAllReduce (NCCL) / dist.PeerGradAllReduce (one kernel over NVLink peer memory) == single-GPU
+gradients of the concatenated batch -- single pass and hierarchical (two field passes inside one backward),
+whole-buffer and chunk-overlapped exchanges."""
 import os
 import socket
 
@@ -37,11 +39,14 @@ def _batch():
     R = 256
     ro = torch.tensor([[0.2, -0.1, 4.0]]).repeat(R, 1) + 0.05 * torch.randn(R, 3, generator=g)
     rd = torch.nn.functional.normalize(-ro + 0.5 * torch.randn(R, 3, generator=g), dim=-1)
-    return ro, rd, 1 + 0.2 * torch.rand(R, 1, generator=g), torch.rand(R, 3, generator=g), torch.linspace(2.0, 6.0, 32)
+    return (ro, rd, 1 + 0.2 * torch.rand(R, 1, generator=g), torch.rand(R, 3, generator=g), torch.rand(R, 32, generator=g),
+            torch.linspace(2.0, 6.0, 32), torch.rand(32, generator=g))
 
 
-def _grads(enc, mlp, vr, ro, rd, dn, gt, t, dev):
-    Cr, Cf, _ = vr.vol_render(mlp, rd.to(dev), ro.to(dev), num_samples=32, t=t.to(dev), dir_norm=dn.to(dev), hierarchical=False)
+def _grads(enc, mlp, vr, ro, rd, dn, gt, u, t, u_cand, dev, hier=False):
+    """hier=True: coarse + fine render, i.e. TWO passes through the encoder and the MLP inside one backward."""
+    Cr, Cf, _ = vr.vol_render(mlp, rd.to(dev), ro.to(dev), num_samples=32, t=t.to(dev), dir_norm=dn.to(dev), hierarchical=hier,
+                              _u=u.to(dev), _u_cand=u_cand.to(dev))
     (torch.nn.functional.mse_loss(Cr, gt.to(dev)) + torch.nn.functional.mse_loss(Cf, gt.to(dev))).backward()
     torch.cuda.synchronize()
     return (torch.stack([e.weight.grad for e in enc.Embedding_list]).cpu(),
@@ -57,16 +62,22 @@ def _worker(rank, world, port_no, tmp, mode="nccl"):
     torch.cuda.set_device(dev)
     enc, mlp, vr = _build(dev)
     red = hdist.GradAllReduce(enc, mlp) if mode == "nccl" else hdist.PeerGradAllReduce(enc, mlp, transport=mode[5:])
-    ro, rd, dn, gt, t = _batch()
+    ro, rd, dn, gt, u, t, u_cand = _batch()
     sl = hdist.shard_rays(ro.shape[0], rank, world)
-    for chunks in (1, 4) if mode == "nccl" else (1, 1):          # peer mode: two steps through the same persistent region
+    # peer mode: several steps through the same persistent region; hier: two field passes inside one backward
+    for chunks, hier in ((1, False), (4, False), (1, True), (4, True)):
         enc._grad_chunks = chunks
+        if mode != "nccl":
+            red._nchunks, red.overlap = chunks, chunks > 1
+            if red.overlap and red._side is None:
+                red._side, red.ctas = torch.cuda.Stream(device=dev, priority=-1), 32
         for p in list(enc.parameters()) + list(mlp.parameters()):
             p.grad = None
-        gt_tab, gt_mlp = _grads(enc, mlp, vr, ro[sl], rd[sl], dn[sl], gt[sl], t, dev)
-        torch.save((gt_tab, gt_mlp), os.path.join(tmp, f"g{rank}_{chunks}.pt"))
+        gt_tab, gt_mlp = _grads(enc, mlp, vr, ro[sl], rd[sl], dn[sl], gt[sl], u[sl], t, u_cand, dev, hier)
+        torch.save((gt_tab, gt_mlp), os.path.join(tmp, f"g{rank}_{chunks}_{int(hier)}.pt"))
     if mode != "nccl":
         assert not red.region.timed_out()
+        red.region.raise_if_failed()
     import torch.distributed as tdist
     tdist.barrier()
     tdist.destroy_process_group()
@@ -77,12 +88,21 @@ def test_sharded_gradients_equal_single_gpu(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     dev = torch.device("cuda", 0)
     enc, mlp, vr = _build(dev)
-    want_tab, want_mlp = _grads(enc, mlp, vr, *_batch(), dev)
-    for chunks in (1, 4):
-        for rank in range(2):
-            tab, gm = torch.load(os.path.join(tmp_path, f"g{rank}_{chunks}.pt"))
-            assert float((tab - want_tab).norm() / want_tab.norm()) < 1e-5, (rank, chunks)
-            assert float((gm - want_mlp).norm() / want_mlp.norm()) < 1e-5, (rank, chunks)
+    _check(tmp_path, enc, mlp, vr, dev, bit_identical=False)
+
+
+def _check(tmp_path, enc, mlp, vr, dev, bit_identical):
+    for hier in (False, True):
+        for p in list(enc.parameters()) + list(mlp.parameters()):
+            p.grad = None
+        want_tab, want_mlp = _grads(enc, mlp, vr, *_batch(), dev, hier)
+        for chunks in (1, 4):
+            got = [torch.load(os.path.join(tmp_path, f"g{rank}_{chunks}_{int(hier)}.pt")) for rank in range(2)]
+            for rank, (tab, gm) in enumerate(got):
+                assert float((tab - want_tab).norm() / want_tab.norm()) < 1e-5, (rank, chunks, hier)
+                assert float((gm - want_mlp).norm() / want_mlp.norm()) < 1e-5, (rank, chunks, hier)
+            if bit_identical:
+                assert torch.equal(got[0][0], got[1][0]) and torch.equal(got[0][1], got[1][1]), (chunks, hier)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -94,9 +114,4 @@ def test_peer_memory_allreduce_equals_single_gpu(tmp_path, transport):
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), "peer-" + transport), nprocs=2, join=True)
     dev = torch.device("cuda", 0)
     enc, mlp, vr = _build(dev)
-    want_tab, want_mlp = _grads(enc, mlp, vr, *_batch(), dev)
-    got = [torch.load(os.path.join(tmp_path, f"g{rank}_1.pt")) for rank in range(2)]
-    for tab, gm in got:
-        assert float((tab - want_tab).norm() / want_tab.norm()) < 1e-5
-        assert float((gm - want_mlp).norm() / want_mlp.norm()) < 1e-5
-    assert torch.equal(got[0][0], got[1][0]) and torch.equal(got[0][1], got[1][1])
+    _check(tmp_path, enc, mlp, vr, dev, bit_identical=True)
