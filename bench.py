@@ -210,38 +210,97 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's algorithm on host cores
+# CPU arm: the reference ITSELF (unmodified modules from baseline/_ref or /root/reference, loaded by oracle/ref_loader.py
+# with environment shims only) on the box's host cores; oracle/port.py only when no reference tree can be found.
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_step_rays_per_s(args, steps, warmup, rays):
-    from oracle import port
-    torch.set_num_threads(os.cpu_count())
-    H = W = 200
-    c2w, K = make_cameras(100, 0), intrinsics(H, W)
+def _reference_modules():
+    from oracle import ref_loader
+    return (ref_loader.load(), ref_loader) if ref_loader.available() else (None, ref_loader)
+
+
+def reference_step(args, rays, device="cpu"):
+    """Builds the reference's own objects the way train_hash2.py:117-127 does and returns (step_fn, kind, note):
+    step_fn(k) runs vol_render + MSE(Cr)+MSE(Cf) + backward on batch k of the same synthetic scene as the B200 arm."""
+    ref, ref_loader = _reference_modules()
+    H = W = args.res
+    c2w, K = make_cameras(args.views, 0), intrinsics(H, W)
     mx, mn = scene_bbox(c2w, K, H, W, args.near, args.far)
     sigma = ((mx - mn) ** 2).sum().sqrt()
     L, F, T = 16, 2, 2 ** args.hash_size
-    g = torch.Generator().manual_seed(0)
-    tables = ((torch.rand(L, T, F, generator=g) * 2 - 1)).requires_grad_()
-    params = {k: v.requires_grad_() for k, v in port.mlp_init(seed=0).items()}
-    scales = port.level_scales(16, float(args.max_res), L)
-    batches = make_batches(c2w, K, H, W, rays, 2, 1)
+    batches = [tuple(t.to(device) for t in b) for b in make_batches(c2w, K, H, W, rays, 2, 100)]
     near, far = torch.tensor(args.near), torch.tensor(args.far)
+    torch.manual_seed(0)
+    if ref is None:
+        from oracle import port
+        g = torch.Generator().manual_seed(0)
+        tables = ((torch.rand(L, T, F, generator=g) * 2 - 1)).requires_grad_()
+        params = {k: v.requires_grad_() for k, v in port.mlp_init(seed=0).items()}
+        scales = port.level_scales(16, float(args.max_res), L)
+
+        def step(k):
+            o, d, n, gt = batches[k % len(batches)]
+            tt = port.strat_t(near, far, args.samples, torch.rand(args.samples))
+            u_rs = torch.rand(rays, args.samples) if args.hierarchical else None
+            u_s = torch.rand(args.samples) if args.hierarchical else None
+            Cr, Cf, _ = port.vol_render(params, tables, mn, sigma, scales, d, o, tt, n, 4, args.hierarchical, near, far, u_rs, u_s)
+            (torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)).backward()
+            tables.grad = None
+            for v in params.values():
+                v.grad = None
+        return step, "port", "oracle/port.py (torch-CPU restatement; no reference tree found on this box)"
+    with ref_loader.quiet():
+        enc = ref.hash_encoding.HashEncoder(N_min=16, N_max=float(args.max_res), L=L, F=F, T=T, dim=3, mu=mn.to(device),
+                                            sigma=sigma.to(device), device=device)
+        bound = (lambda t: t) if torch.cuda.is_available() else ref.Bound       # test_hash.py:25-26 calls .to('cuda')
+        mlp = ref.test_hash.MLP_3D(num_sig=2, num_col=2, L=L, F=F, d_view=24, max_bound=bound(mx), min_bound=bound(mn))
+        pe = ref.encoder.PositionalEncoder(3, 4)
+    pe.sinus_in = pe.sinus_in.to(device)
+    pe.device = device
+    with torch.no_grad():
+        for e in enc.Embedding_list:
+            e.weight.mul_(1e4)                                            # trained-like magnitudes, as in the B200 arm
+    enc, mlp = enc.to(device), mlp.to(device)
+    vr = ref.vol_renderer.Volume_Renderer(H=H, W=W, K=K, near=near, far=far, device=device, Pos_encode=enc, Dir_encode=pe,
+                                          max_dim=2 ** 10, sigma_val=sigma, mu=mn)
+    params = list(enc.parameters()) + list(mlp.parameters())
+    amp = device != "cpu"
+
+    def step(k):
+        o, d, n, gt = batches[k % len(batches)]
+        for p in params:
+            p.grad = None
+        with ref_loader.quiet():
+            with torch.autocast("cuda", dtype=torch.float16, enabled=amp):      # train_hash2.py:218 on the GPU; fp32 on the CPU
+                Cr, Cf, _ = vr.vol_render(mlp, d, o, num_samples=args.samples, update_mask=False, dir_norm=n,
+                                          hierarchical=args.hierarchical)
+                loss = torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)
+            (loss * (65536.0 if amp else 1.0)).backward()                       # GradScaler's initial scale (train_hash2.py:192,226)
+    from oracle import ref_loader as rl
+    return step, "reference", f"the unmodified reference modules from {rl.REF_DIR} (hash_encoding / encoder / test_hash / vol_renderer / helper)"
+
+
+def cpu_reference_rays_per_s(args, steps, warmup, rays, budget_s=None):
+    """Wall-clock rays/s of the reference's own CPU path, all host threads.  Returns (rays/s, s/step, kind, note, rays)."""
+    torch.set_num_threads(os.cpu_count())
+    if budget_s is not None:
+        # keep the whole run inside the budget: time one small step first and shrink the per-step sample if 4096-ray steps
+        # would not fit (the line then says so: cpu_baseline.sample / config.reference_rays_per_step)
+        probe, _, _ = reference_step(args, 256)
+        probe(0)
+        t0 = time.perf_counter()
+        probe(1)
+        per_ray = (time.perf_counter() - t0) / 256
+        while rays > 256 and per_ray * rays * (steps + warmup) > budget_s:
+            rays //= 2
+    step, kind, note = reference_step(args, rays)
     times = []
     for k in range(warmup + steps):
-        o, d, n, gt = batches[k % len(batches)]
         t0 = time.perf_counter()
-        tt = port.strat_t(near, far, args.samples, torch.rand(args.samples))
-        u_rs = torch.rand(rays, args.samples) if args.hierarchical else None
-        u_s = torch.rand(args.samples) if args.hierarchical else None
-        Cr, Cf, _ = port.vol_render(params, tables, mn, sigma, scales, d, o, tt, n, 4, args.hierarchical, near, far, u_rs, u_s)
-        loss = torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)
-        loss.backward()
-        tables.grad = None
-        for v in params.values():
-            v.grad = None
+        step(k)
         if k >= warmup:
             times.append(time.perf_counter() - t0)
-    return rays / (sum(times) / len(times)), sum(times) / len(times)
+    sec = sum(times) / len(times)
+    return rays / sec, sec, kind, note, rays
 
 
 def workload_name(args, rays):
@@ -251,19 +310,22 @@ def workload_name(args, rays):
 
 
 def run_reference(args):
+    """The reference arm: the reference's own implementation on the host cores, same scene / sizes / metric as the B200 arm.
+    Each step is args.rays rays (the B200 arm's per-GPU batch) unless that cannot finish in a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rays = args.cpu_rays
-    v, sec = cpu_step_rays_per_s(args, args.steps, max(args.warmup, 1), rays)
+    warm = max(args.warmup, 1)
+    v, sec, kind, note, rays = cpu_reference_rays_per_s(args, args.steps, warm, args.rays, budget_s=args.reference_budget_s)
     line = {
         "impl": "reference", "metric": "train_rays_per_sec", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args, args.rays)},
-        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{rays} rays x {args.samples} samples per step of the same synthetic scene (200x200 views), fwd+bwd, "
-                                   f"torch-CPU restatement of the reference (oracle/port.py)"},
+        "config": {"workload": workload_name(args, args.rays), "reference_rays_per_step": rays,
+                   "same_rays_per_step_as_b200_arm": rays == args.rays},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": kind,
+                         "sample": f"{rays} rays x {args.samples} samples per step of the same synthetic scene ({args.res}x{args.res} "
+                                   f"views, T=2^{args.hash_size}), fwd+bwd, {note}, torch CPU fp32, {os.cpu_count()} threads"},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -309,13 +371,16 @@ def run_b200(args):
     resident = [tuple(t.to(dev) for t in b) for b in host]
     params = list(enc.parameters()) + list(mlp.parameters())
     flush = torch.empty(512 * 1024 * 1024 // 4, device=dev) if args.l2 == "flush" else None
-    amp = args.precision == "bf16"
+    amp = args.precision in ("bf16", "f16")
+    amp_dtype = torch.float16 if args.precision == "f16" else torch.bfloat16
+    if args.precision == "f16":
+        mlp.tc_grad_scale = 65536.0                # fp16 operands: what GradScaler's initial scale does in train_hash2.py:192,226
 
     def step(batch):
         o, d, n, gt = batch
         for p in params:
             p.grad = None
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+        with torch.autocast("cuda", dtype=amp_dtype, enabled=amp):
             Cr, Cf, _ = vr.vol_render(nerf, d, o, num_samples=args.samples, update_mask=False, dir_norm=n,
                                       hierarchical=args.hierarchical)
             loss = torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)
@@ -362,7 +427,7 @@ def run_b200(args):
     if args.graph in ("on", "auto"):
         try:
             from human_body_reconstruction_b200.graph import GraphedStep
-            gs = GraphedStep(vr, nerf, params, rays, args.samples, args.hierarchical, dev, autocast=amp).capture()
+            gs = GraphedStep(vr, nerf, params, rays, args.samples, args.hierarchical, dev, autocast=amp, autocast_dtype=amp_dtype).capture()
             host_packed = [GraphedStep.pack_batch(*b, pin=True) for b in host]       # one H2D copy per step
             resident_packed = [p.to(dev) for p in host_packed]
             for k in range(3):
@@ -373,10 +438,11 @@ def run_b200(args):
             gs, graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {e})"
             for p in params:
                 p.grad = None
-    if gs is not None:
-        dev_ms = timed_region(lambda k: gs(resident_packed[k % len(resident_packed)]))
-    else:
-        dev_ms = eager_ms
+    # the headline region is repeated: median of `--repeats` regions of K steps each (every region is K steps, barrier +
+    # synchronize on both sides); the spread says how far one 10 ms region can be trusted
+    run = (lambda k: gs(resident_packed[k % len(resident_packed)])) if gs is not None else (lambda k: step(resident[k % len(resident)]))
+    region_ms = sorted(timed_region(run) for _ in range(max(1, args.repeats)))
+    dev_ms = region_ms[len(region_ms) // 2]
 
     # (3) end to end: pinned host batch -> H2D -> step -> loss.item()
     e2e_s = 0.0
@@ -402,7 +468,8 @@ def run_b200(args):
             img = torch.stack([0.5 + 0.5 * torch.sin(xx / 37.0), 0.5 + 0.5 * torch.cos(yy / 23.0), (xx + yy) / (H + W)], dim=-1)
             img = (img * 255).round().to(torch.uint8).expand(args.views, H, W, 3).contiguous()   # 192 MB at 100 x 800 x 800
             ds = hbr.DeviceRayDataset(img, c2w, K, device=dev, batch_size=rays)
-            gs2 = GraphedStep(vr, nerf, params, rays, args.samples, args.hierarchical, dev, autocast=amp, source=ds).capture()
+            gs2 = GraphedStep(vr, nerf, params, rays, args.samples, args.hierarchical, dev, autocast=amp, autocast_dtype=amp_dtype,
+                              source=ds).capture()
             for _ in range(3):
                 gs2()
             torch.cuda.synchronize()
@@ -424,10 +491,12 @@ def run_b200(args):
     barrier()
     clk = clocks.stop()
 
-    tms = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    tms = torch.tensor([dev_ms, e2e_s * 1e3, region_ms[0], region_ms[-1]], device=dev, dtype=torch.float64)
     if world > 1:
         tdist.all_reduce(tms, op=tdist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(tms[0]), float(tms[1])
+    dev_ms, e2e_ms, lo_ms, hi_ms = (float(v) for v in tms)
+    c3 = c3_leg(args, world, rank, dev, vr, nerf, enc, mlp, params, c2w, K, H, W, amp, amp_dtype, barrier) if args.c3 else None
+    grad_check = grad_check_leg(hdist, tdist, reducer, enc, mlp, params, step, resident, world, rank, args) if world > 1 else None
     if rank != 0:
         _finish(world)
         return
@@ -450,6 +519,7 @@ def run_b200(args):
         c, m = kern[name]
         r = kernel_roofline(name, n_pts / (c / args.steps), m, peaks)
         r["traffic"] = traffic_tab.get(name)       # dram bytes read+written per launch, one ncu --set full capture
+        r["traffic_source"] = "imported from profiles/traffic.json (an earlier ncu --set full capture of this command), not measured in this run"
         return r
 
     roofline = roof(dom)
@@ -458,10 +528,13 @@ def run_b200(args):
     line = {
         "metric": "train_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16 MLP / f32 encoder+compositor" if amp else "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": f"{args.precision} MLP operands (f32 accumulate) / f32 encoder+compositor" if amp else "f32",
+        "data": "synthetic",
         "config": {"workload": workload_name(args, rays), "rays_per_gpu": rays, "l2": "flushed between timed steps (512 MiB write)"
                    if flush is not None else "warm", "parallelism": f"dp{world} (rays sharded, table+MLP grads all-reduced)",
                    "launch": graph_note},
+        "timed_regions": {"repeats": len(region_ms), "ms_per_step_median": dev_ms / args.steps, "ms_per_step_min": lo_ms / args.steps,
+                          "ms_per_step_max": hi_ms / args.steps, "note": "each region = K steps between barrier+synchronize; value uses the median"},
         "eager_ms_per_step": eager_ms / args.steps,
         "e2e": {"value": total_rays / (e2e_ms / 1e3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps},
@@ -480,6 +553,10 @@ def run_b200(args):
         line["hash_encode_mpts_per_s"] = (n_pts / (c / args.steps)) / (m * 1e-3) / 1e6
     if sampler is not None:
         line["device_sampler_e2e"] = sampler
+    if c3 is not None:
+        line["c3"] = c3
+    if grad_check is not None:
+        line["grad_check"] = grad_check
     if reducer is not None:
         line["allreduce_bytes_per_step"] = 4 * sum(p.numel() for p in params)      # flat table + MLP gradients, fp32
         region = getattr(reducer, "region", None)
@@ -489,12 +566,121 @@ def run_b200(args):
         if region is not None and region.timed_out():
             line["error"] = "peer all-reduce barrier timed out"
     if world == 1 and not args.no_cpu_baseline:
-        v, sec = cpu_step_rays_per_s(args, 3, 1, args.cpu_rays)
-        line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"{args.cpu_rays} rays x {args.samples} samples per step (BASELINE config 1 shape, 200x200 views), "
-                                          f"1 warm-up + 3 timed fwd+bwd steps of oracle/port.py (torch CPU, {os.cpu_count()} threads)"}
+        v, sec, kind, note, cr = cpu_reference_rays_per_s(args, 3, 1, args.cpu_rays)
+        line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": kind,
+                                "sample": f"{cr} rays x {args.samples} samples per step of the same synthetic scene, 1 warm-up + 3 timed "
+                                          f"fwd+bwd steps of {note} (torch CPU fp32, {os.cpu_count()} threads)"}
+        if args.reference_eager_b200:
+            line["reference_eager_b200"] = reference_on_b200(args, rays)
     print(json.dumps(line), flush=True)
     _finish(world)
+
+
+def c3_leg(args, world, rank, dev, vr, nerf, enc, mlp, params, c2w, K, H, W, amp, amp_dtype, barrier):
+    """BASELINE configs[2]: 2^20 rays per step GLOBAL, sharded over the ranks (2^20 / N per GPU, table + MLP gradients
+    all-reduced); at N = 1 the single-GPU rate is taken on 2^17 rays (what one of 8 GPUs processes).  Eager launches (the
+    kernels run for milliseconds), 3 warm-up + 5 timed steps, CUDA events, max over ranks."""
+    import torch.distributed as tdist
+    rays = (1 << 20) // world if world > 1 else 1 << 17
+    try:
+        b = make_batches(c2w, K, H, W, rays, 1, 7 + rank)[0]
+        o, d, n, gt = (t.to(dev) for t in b)
+
+        def step():
+            for p in params:
+                p.grad = None
+            with torch.autocast("cuda", dtype=amp_dtype, enabled=amp):
+                Cr, Cf, _ = vr.vol_render(nerf, d, o, num_samples=args.samples, update_mask=False, dir_norm=n, hierarchical=False)
+                loss = 2.0 * torch.nn.functional.mse_loss(Cr, gt)
+            loss.backward()
+        for _ in range(3):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nstep = 5
+        e0.record()
+        for _ in range(nstep):
+            step()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / nstep], device=dev, dtype=torch.float64)
+        if world > 1:
+            tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
+        ms = float(ms)
+        del o, d, n, gt
+        for p in params:
+            p.grad = None
+        torch.cuda.empty_cache()
+        n_pts = rays * args.samples
+        return {"workload": f"configs[2]: {rays * world} rays/step global = {rays} rays x {args.samples} samples per GPU on {world} GPU(s), "
+                            f"T=2^{args.hash_size}, fwd+bwd" + (", gradients all-reduced" if world > 1 else " (single-GPU rate on 2^17 rays)"),
+                "rays_global": rays * world, "rays_per_gpu": rays, "ms_per_step": ms, "value": rays * world / (ms * 1e-3), "unit": "rays/s",
+                "steps": nstep, "warmup": 3, "launch": "eager",
+                "step_roofline_frac_per_gpu": STEP_BYTES_PER_POINT * n_pts / (ms * 1e-3) / 1e9 / measured_peaks()[0]}
+    except Exception as e:                                                 # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
+def grad_check_leg(hdist, tdist, reducer, enc, mlp, params, step, resident, world, rank, args):
+    """N > 1: the reduced gradients are (a) bit-identical on every rank and (b) equal to the average of the ranks' LOCAL
+    gradients, recomputed without the exchange on the same batches, on a sampled slice of every table level + the MLP."""
+    try:
+        L, T, F = enc.L, enc.T, enc.F
+        idx = torch.randint(0, T, (256,), generator=torch.Generator().manual_seed(5)).to(enc._flat_table().device)
+
+        def sample():
+            tab = torch.stack([e.weight.grad for e in enc.Embedding_list])            # (L,T,F)
+            return torch.cat([tab[:, idx, :].reshape(-1), torch.cat([p.grad.reshape(-1) for p in mlp.parameters()])]).clone()
+
+        def checksum():
+            tab = torch.stack([e.weight.grad for e in enc.Embedding_list])
+            bits = torch.cat([tab.reshape(-1), torch.cat([p.grad.reshape(-1) for p in mlp.parameters()])]).view(torch.int32)
+            return bits.to(torch.int64).sum().reshape(1)
+
+        step(resident[0])
+        reduced, cs = sample(), checksum()
+        all_cs = [torch.zeros_like(cs) for _ in range(world)]
+        tdist.all_gather(all_cs, cs)
+        identical = all(int(c) == int(all_cs[0]) for c in all_cs)
+        if reducer is not None:
+            reducer.remove()
+        step(resident[0])                                                  # the same batch, gradients left local
+        local = sample()
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        tdist.all_gather(gathered, local)
+        want = torch.stack(gathered).double().mean(0)
+        err = float((reduced.double() - want).norm() / (want.norm() + 1e-30))
+        for p in params:
+            p.grad = None
+        return {"ranks_bit_identical": bool(identical), "rel_err_vs_recomputed_mean_of_local_grads": err, "ok": bool(identical and err < 1e-4),
+                "sampled_entries": int(reduced.numel()), "note": "atomic accumulation order differs between the two backward passes: "
+                "the comparison is norm-wise (1e-4), the rank-to-rank comparison is bit-exact"}
+    except Exception as e:                                                 # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300], "ok": False}
+
+
+def reference_on_b200(args, rays):
+    """Second baseline: the SAME unmodified reference modules run eagerly on this B200 (fp16 autocast as
+    train_hash2.py:218), same scene and batch size.  Device-timed with CUDA events; a reported figure, not the target."""
+    try:
+        step, kind, note = reference_step(args, rays, device="cuda")
+        if kind != "reference":
+            return {"unavailable": "no reference tree on this box"}
+        for k in range(2):
+            step(k)
+        torch.cuda.synchronize()
+        n = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(n):
+            step(k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        return {"value": rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "steps": n,
+                "note": f"{note}, eager PyTorch on cuda:0, fp16 autocast, loss scaled by 65536, {rays} rays x {args.samples} samples"}
+    except Exception as e:                                                 # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def _finish(world):
@@ -522,9 +708,13 @@ def main():
     ap.add_argument("--near", type=float, default=2.0)
     ap.add_argument("--far", type=float, default=6.0)
     ap.add_argument("--hierarchical", action="store_true")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "f16", "f32"],
+                    help="MLP operand format: bf16 / f16 tensor-core kernels under autocast of that dtype, or the fp32 kernels")
     ap.add_argument("--l2", default="flush", choices=["flush", "warm"])
-    ap.add_argument("--cpu-rays", type=int, default=1024)
+    ap.add_argument("--cpu-rays", type=int, default=1024, help="rays per step of the cpu_baseline leg of the B200 arm (bounded sample)")
+    ap.add_argument("--reference-budget-s", type=float, default=300.0, help="--impl reference: shrink the per-step sample below "
+                    "--rays only if (steps + warmup) full steps would not fit this many seconds")
+    ap.add_argument("--reference-eager-b200", action="store_true", help="also time the unmodified reference modules eagerly on the GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-device-sampler", action="store_true", help="skip the device-resident ray sampler leg (8f row 2)")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "peer", "nccl"], help="N>1 gradient exchange")
@@ -533,6 +723,8 @@ def main():
     ap.add_argument("--peer-chunks", type=int, default=2, help="> 0: all-reduce level chunks on a side stream while the "
                     "remaining chunks' scatter-add runs; 0: one all-reduce behind the backward pass")
     ap.add_argument("--fuse-field", action="store_true", help="use the fused encoder+MLP kernels (hbr_field_*_tc)")
+    ap.add_argument("--repeats", type=int, default=5, help="timed regions of K steps each; value = their median")
+    ap.add_argument("--no-c3", dest="c3", action="store_false", help="skip the configs[2] leg (2^20 rays/step global; 2^17 at N=1)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step from a CUDA graph (auto = on; falls back to eager if capture fails)")
     args = ap.parse_args()
