@@ -75,7 +75,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         if (not force) and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(d) for d in _deps()):
             continue
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("HBR_EXTRA_NVCC", "").split(), "-I", INCLUDE, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:
@@ -130,8 +130,11 @@ SIGNATURES = {
     "hbr_mlp_fwd_f32": ([_vp, _i64, _vp, _i64, _i64, _vp, _dims_p, _vp, _vp, _vp], C.c_int),
     "hbr_mlp_bwd_f32": ([_vp, _i64, _vp, _i64, _i64, _vp, _dims_p, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp], C.c_int),
     "hbr_mlp_tc_scratch_bytes": ([_dims_p], _i64),
-    "hbr_mlp_fwd_tc": ([_vp, _i64, _vp, _i64, _i64, _vp, _dims_p, _i32, _vp, _vp, _vp], C.c_int),
-    "hbr_mlp_bwd_tc": ([_vp, _i64, _vp, _i64, _i64, _vp, _dims_p, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _f32, _vp, _vp], C.c_int),
+    "hbr_mlp_fwd_tc": ([_vp, _i32, _i64, _vp, _i64, _i64, _vp, _dims_p, _i32, _vp, _vp, _vp], C.c_int),
+    "hbr_mlp_bwd_tc": ([_vp, _i32, _i64, _vp, _i64, _i64, _vp, _dims_p, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _f32, _vp, _vp],
+                       C.c_int),
+    "hbr_hash_encode_fwd_rays": ([_vp, _vp, _vp, _i64, _i64, _i64, _vp, _geom_p, _vp, _i64, _i32, _vp], C.c_int),
+    "hbr_hash_encode_bwd_rays": ([_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _geom_p, _vp, _i32, _i32, _vp], C.c_int),
     "hbr_field_fwd_tc": ([_vp, _i64, _vp, _geom_p, _vp, _i64, _vp, _dims_p, _i32, _vp, _vp, _vp, _vp], C.c_int),
     "hbr_field_bwd_tc": ([_vp, _i64, _geom_p, _vp, _i64, _vp, _dims_p, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp],
                          C.c_int),
@@ -172,7 +175,7 @@ DEBUG_SIGNATURES = {
 
 # kernels launched by one call of each entry point (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
-    "hbr_hash_encode_fwd": 1, "hbr_hash_encode_bwd": 1, "hbr_hash_indices": 1, "hbr_dir_encode": 1,
+    "hbr_hash_encode_fwd": 1, "hbr_hash_encode_bwd": 1, "hbr_hash_encode_fwd_rays": 1, "hbr_hash_encode_bwd_rays": 1, "hbr_hash_indices": 1, "hbr_dir_encode": 1,
     "hbr_mlp_fwd_f32": 1, "hbr_mlp_bwd_f32": 2, "hbr_mlp_fwd_tc": 2, "hbr_mlp_bwd_tc": 3, "hbr_field_fwd_tc": 2, "hbr_field_bwd_tc": 3, "hbr_adam_step": 1, "hbr_allreduce_peer": 1, "hbr_ray_gen": 1, "hbr_ray_bbox": 1, "hbr_ray_points": 1, "hbr_occupancy_mask": 1,
     "hbr_composite_fwd": 1, "hbr_composite_bwd": 1, "hbr_hier_sample": 1, "hbr_grid_points": 1,
     "hbr_grid_density": 3, "hbr_mc_count": 1, "hbr_mc_emit": 2, "hbr_grid_interp": 1,

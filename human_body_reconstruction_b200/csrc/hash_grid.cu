@@ -11,8 +11,11 @@
 
 namespace hbr {
 
-constexpr int kTilePts = 128;
-constexpr int kHashThreads = 256;
+#ifndef HBR_HASH_TILE
+#define HBR_HASH_TILE 128
+#endif
+constexpr int kTilePts = HBR_HASH_TILE;          // points per CTA
+constexpr int kHashThreads = 2 * kTilePts;       // two threads per point (alternating levels)
 
 template <int F> struct FeatVec;
 template <> struct FeatVec<1> { using type = float; };
@@ -54,6 +57,29 @@ __device__ __forceinline__ void load_point(const XT* __restrict__ x, long long g
   }
 }
 
+// Sample positions formed in the kernel from the rays: point gp = (ray gp / S, sample gp % S), p = o + d * t with the
+// multiply and the add rounded separately -- bit-identical to hbr_ray_points (vol_renderer.py:165, helper.py:48) -- so
+// the (R*S,3) position tensor of the training step never exists.  t is (S) shared (t_stride = 0) or (R,S) per ray.
+struct RaySrc {
+  const float* o;
+  const float* d;
+  const float* t;
+  long long S, t_stride;
+};
+struct RayPts {};                                  // tag: positions come from a RaySrc
+__device__ __forceinline__ void load_point(const RaySrc& rs, long long gp, long long n, float p[3]) {
+  if (gp < n) {
+    const long long ray = gp / rs.S, smp = gp - ray * rs.S;
+    const float tt = __ldg(rs.t + ray * rs.t_stride + smp);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) p[a] = __fadd_rn(__ldg(rs.o + ray * 3 + a), __fmul_rn(__ldg(rs.d + ray * 3 + a), tt));
+  } else {
+    p[0] = p[1] = p[2] = 0.f;
+  }
+}
+template <typename XT> struct PointSrc { using type = const XT*; };
+template <> struct PointSrc<RayPts> { using type = RaySrc; };
+
 // ---- forward ------------------------------------------------------------------------------------------
 // PAIR: 0 = eight 8-byte gathers per level (default); 1 = (x, x+1) corner pairs of an even x share one aligned 16-byte
 // slot: one LDG.128 per pair, the odd-x second load predicated.  Measured at 524 288 points, T = 2^19, cold L2: PAIR 0
@@ -62,15 +88,18 @@ __device__ __forceinline__ void load_point(const XT* __restrict__ x, long long g
 // x, two 8-byte gathers for the others, i.e. 25 % fewer L1 wavefronts on the hashed levels) 112 us against 107 us in the
 // same step -- pairing only pays in the backward, where it halves the number of reductions.  ncu: the kernel runs at
 // 83 % of the L1TEX wavefront peak (l1tex__data_pipe_lsu_wavefronts), 49 % of L2 throughput, 9 % of HBM.
-template <int F, bool POW2, typename XT, int PAIR = 0, int UNR = 4>
+// YT: float (the module's output, hash_encoding.py:165) or a 16-bit operand format (uint16_t bits of bf16 / fp16, selected by
+// y_fmt): the rounding the MLP applies to its input under autocast, done here so the training step neither writes nor
+// re-reads fp32 features (64 B/point instead of 128, and the MLP kernels copy the rows straight into their operand tile).
+template <int F, bool POW2, typename XT, int PAIR = 0, int UNR = 4, typename YT = float>
 __global__ void __launch_bounds__(kHashThreads)
-hash_fwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__ table, float* __restrict__ y,
-                long long y_stride, const __grid_constant__ HashGeom g) {
+hash_fwd_kernel(const typename PointSrc<XT>::type x, long long n, const float* __restrict__ table, YT* __restrict__ y,
+                long long y_stride, const __grid_constant__ HashGeom g, int y_fmt) {
   extern __shared__ float tile[];                    // [kTilePts][pitch]
   const int C = g.L * F;
   const int pitch = C | 1;                           // odd pitch: conflict-free column writes
   const int p = threadIdx.x & (kTilePts - 1);
-  const int grp = threadIdx.x >> 7;
+  const int grp = threadIdx.x / kTilePts;
   const long long base = (long long)blockIdx.x * kTilePts;
   float pt[3];
   load_point(x, base + p, n, pt);
@@ -116,17 +145,38 @@ hash_fwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__
   __syncthreads();
   const int cols = C + g.E;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < kTilePts; r += kHashThreads / 32) {
-    const long long gp = base + r;
-    if (gp >= n) break;
-    for (int c = lane; c < cols; c += 32) y[gp * y_stride + c] = c < C ? tile[r * pitch + c] : 0.f;
+  if (sizeof(YT) == 2) {
+    // 16-bit rows: pairs of columns packed into one 32-bit store (cols is even for the 16-bit path: checked by the caller)
+    uint32_t* y32 = reinterpret_cast<uint32_t*>(y);
+    const int half = cols >> 1;
+    for (int e = threadIdx.x; e < kTilePts * half; e += kHashThreads) {
+      const int r = e / half, c = (e - r * half) * 2;
+      const long long gp = base + r;
+      if (gp >= n) break;
+      const float a = c < C ? tile[r * pitch + c] : 0.f, b = c + 1 < C ? tile[r * pitch + c + 1] : 0.f;
+      uint32_t v;
+      if (y_fmt == HBR_F16) {
+        const __half2 hh = __floats2half2_rn(a, b);
+        v = *reinterpret_cast<const uint32_t*>(&hh);
+      } else {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+        v = *reinterpret_cast<const uint32_t*>(&hh);
+      }
+      y32[(gp * y_stride + c) >> 1] = v;
+    }
+  } else {
+    for (int r = warp; r < kTilePts; r += kHashThreads / 32) {
+      const long long gp = base + r;
+      if (gp >= n) break;
+      for (int c = lane; c < cols; c += 32) y[gp * y_stride + c] = (YT)(c < C ? tile[r * pitch + c] : 0.f);
+    }
   }
 }
 
 // ---- backward -----------------------------------------------------------------------------------------
 template <int F, bool POW2, typename XT>
 __global__ void __launch_bounds__(kHashThreads)
-hash_bwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__ dy, long long dy_stride,
+hash_bwd_kernel(const typename PointSrc<XT>::type x, long long n, const float* __restrict__ dy, long long dy_stride,
                 float* __restrict__ dtable, const __grid_constant__ HashGeom g, int l_begin, int l_end) {
   extern __shared__ float tile[];
   const int C = g.L * F;
@@ -157,7 +207,7 @@ hash_bwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__
     }
   }
   const int p = threadIdx.x & (kTilePts - 1);
-  const int grp = threadIdx.x >> 7;
+  const int grp = threadIdx.x / kTilePts;
   const bool valid = base + p < n;
   float pt[3];
   load_point(x, base + p, n, pt);
@@ -206,7 +256,7 @@ hash_bwd_kernel(const XT* __restrict__ x, long long n, const float* __restrict__
       uint32_t idx[8];
       corner_indices<POW2>(ix, iy, iz, g.T, idx);
       float* lvl = dtable + (size_t)l * g.T * F;
-      if (F == 2 && POW2 && !(ix & 1)) {
+      if (F == 2 && POW2 && g.T >= 2 && !(ix & 1)) {       // T = 1 has no (e, e^1) slot pair
         // even x: corners (x, x+1) hash to entries e and e^1 -- one aligned 16-byte slot, one red.global.add.v4.f32
 #pragma unroll
         for (int c = 0; c < 8; c += 2) {
@@ -265,7 +315,7 @@ static int launch_fwd(const void* x, int64_t n, const float* table, const HashGe
   const unsigned grid = (unsigned)ceil_div(n, kTilePts);
   auto k = hash_fwd_kernel<F, POW2, XT>;
   HBR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<grid, kHashThreads, smem, st>>>(static_cast<const XT*>(x), n, table, y, ys, g);
+  k<<<grid, kHashThreads, smem, st>>>(static_cast<const XT*>(x), n, table, y, ys, g, HBR_F32);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -276,6 +326,27 @@ static int launch_bwd(const void* x, int64_t n, const float* dy, int64_t ds, con
   HBR_CUDA(cudaFuncSetAttribute(hash_bwd_kernel<F, POW2, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   hash_bwd_kernel<F, POW2, XT><<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(
       static_cast<const XT*>(x), n, dy, ds, dt, g, l0, l1);
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
+// the training step's variants: positions from the rays, features in fp32 or in the MLP's 16-bit operand format
+template <int F, bool POW2, typename YT>
+static int launch_fwd_rays(const RaySrc& rs, int64_t n, const float* table, const HashGeom& g, void* y, int64_t ys, int y_fmt,
+                           cudaStream_t st) {
+  const size_t smem = (size_t)kTilePts * ((g.L * F) | 1) * sizeof(float);
+  auto k = hash_fwd_kernel<F, POW2, RayPts, 0, 4, YT>;
+  HBR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(rs, n, table, static_cast<YT*>(y), ys, g, y_fmt);
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
+template <int F, bool POW2>
+static int launch_bwd_rays(const RaySrc& rs, int64_t n, const float* dy, int64_t ds, const HashGeom& g, float* dt, int l0,
+                           int l1, cudaStream_t st) {
+  const size_t smem = (size_t)kTilePts * ((g.L * F) | 1) * sizeof(float);
+  auto k = hash_bwd_kernel<F, POW2, RayPts>;
+  HBR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(rs, n, dy, ds, dt, g, l0, l1);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -350,4 +421,69 @@ extern "C" int hbr_hash_indices(const void* x, int x_dtype, int64_t n, const hbr
   }
   HBR_LAUNCH_CHECK();
   return HBR_OK;
+}
+
+static int check_rays(const float* o, const float* d, const float* t, int64_t t_rs, int64_t R, int64_t S) {
+  HBR_REQUIRE(R >= 0 && S >= 1 && R < (1LL << 40) / S, "R=%lld S=%lld", (long long)R, (long long)S);
+  HBR_REQUIRE(t_rs == 0 || t_rs >= S, "t_ray_stride %lld", (long long)t_rs);
+  HBR_REQUIRE(R == 0 || (o && d && t), "NULL ray pointer");
+  return HBR_OK;
+}
+
+extern "C" int hbr_hash_encode_fwd_rays(const float* rays_o, const float* rays_d, const float* t, int64_t t_ray_stride, int64_t R,
+                                        int64_t S, const float* table, const hbr_hash_geom* geom, void* y, int64_t y_stride,
+                                        int y_dtype, void* stream) {
+  if (int rc = check_geom(geom)) return rc;
+  if (int rc = check_rays(rays_o, rays_d, t, t_ray_stride, R, S)) return rc;
+  HBR_REQUIRE(y_dtype == HBR_F32 || y_dtype == HBR_F16 || y_dtype == HBR_BF16, "y_dtype %d", y_dtype);
+  const int64_t n = R * S;
+  if (n == 0) return HBR_OK;
+  HBR_REQUIRE(table && y, "NULL pointer");
+  const int cols = geom->L * geom->F + geom->E;
+  HBR_REQUIRE(y_stride >= cols, "y_stride %lld too small", (long long)y_stride);
+  HBR_REQUIRE((uintptr_t)table % 16 == 0, "table must be 16-byte aligned");
+  HBR_REQUIRE(y_dtype == HBR_F32 || (cols % 2 == 0 && y_stride % 2 == 0 && (uintptr_t)y % 4 == 0),
+              "16-bit features need an even column count / stride and a 4-byte aligned buffer");
+  const HashGeom g = to_device_geom(*geom);
+  const RaySrc rs{rays_o, rays_d, t, S, t_ray_stride};
+  cudaStream_t st = as_stream(stream);
+  const bool p2 = is_pow2(g.T);
+#define HBR_FWD_RAYS(F_)                                                                                              \
+  (y_dtype == HBR_F32 ? (p2 ? launch_fwd_rays<F_, true, float>(rs, n, table, g, y, y_stride, y_dtype, st)              \
+                            : launch_fwd_rays<F_, false, float>(rs, n, table, g, y, y_stride, y_dtype, st))            \
+                      : (p2 ? launch_fwd_rays<F_, true, uint16_t>(rs, n, table, g, y, y_stride, y_dtype, st)           \
+                            : launch_fwd_rays<F_, false, uint16_t>(rs, n, table, g, y, y_stride, y_dtype, st)))
+  switch (g.F) {
+    case 1: return HBR_FWD_RAYS(1);
+    case 2: return HBR_FWD_RAYS(2);
+    default: return HBR_FWD_RAYS(4);
+  }
+#undef HBR_FWD_RAYS
+}
+
+extern "C" int hbr_hash_encode_bwd_rays(const float* rays_o, const float* rays_d, const float* t, int64_t t_ray_stride, int64_t R,
+                                        int64_t S, const float* dy, int64_t dy_stride, const hbr_hash_geom* geom, float* dtable,
+                                        int level_begin, int level_end, void* stream) {
+  if (int rc = check_geom(geom)) return rc;
+  if (int rc = check_rays(rays_o, rays_d, t, t_ray_stride, R, S)) return rc;
+  const int64_t n = R * S;
+  if (n == 0) return HBR_OK;
+  HBR_REQUIRE(dy && dtable, "NULL pointer");
+  HBR_REQUIRE(dy_stride >= geom->L * geom->F, "dy_stride %lld too small", (long long)dy_stride);
+  HBR_REQUIRE((uintptr_t)dtable % 16 == 0, "dtable must be 16-byte aligned");
+  HBR_REQUIRE(level_begin >= 0 && level_begin <= level_end && level_end <= geom->L, "level range [%d,%d)", level_begin,
+              level_end);
+  if (level_begin == level_end) return HBR_OK;
+  const HashGeom g = to_device_geom(*geom);
+  const RaySrc rs{rays_o, rays_d, t, S, t_ray_stride};
+  cudaStream_t st = as_stream(stream);
+  const bool p2 = is_pow2(g.T);
+  switch (g.F) {
+    case 1: return p2 ? launch_bwd_rays<1, true>(rs, n, dy, dy_stride, g, dtable, level_begin, level_end, st)
+                      : launch_bwd_rays<1, false>(rs, n, dy, dy_stride, g, dtable, level_begin, level_end, st);
+    case 2: return p2 ? launch_bwd_rays<2, true>(rs, n, dy, dy_stride, g, dtable, level_begin, level_end, st)
+                      : launch_bwd_rays<2, false>(rs, n, dy, dy_stride, g, dtable, level_begin, level_end, st);
+    default: return p2 ? launch_bwd_rays<4, true>(rs, n, dy, dy_stride, g, dtable, level_begin, level_end, st)
+                       : launch_bwd_rays<4, false>(rs, n, dy, dy_stride, g, dtable, level_begin, level_end, st);
+  }
 }

@@ -33,32 +33,49 @@ extern "C" int64_t hbr_mlp_tc_scratch_bytes(const hbr_mlp_dims* dims) {
 }
 
 
-extern "C" int hbr_mlp_fwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
+// feat_dtype: HBR_F32, or the operand format itself (features already rounded by hbr_hash_encode_fwd_rays: contiguous rows)
+static int check_feat(const void* feat, int feat_dtype, int64_t feat_stride, const hbr_mlp_dims* d, int operand) {
+  HBR_REQUIRE(feat_dtype == HBR_F32 || feat_dtype == operand, "feat_dtype %d: HBR_F32 or the operand format %d", feat_dtype, operand);
+  if (feat_dtype != HBR_F32) {
+    const int kp = bf16::narrow_shape(d) ? 32 : 64;
+    HBR_REQUIRE(d->in0 == kp && feat_stride == kp && (uintptr_t)feat % 16 == 0,
+                "16-bit features need in0 == feat_stride == %d and a 16-byte aligned buffer", kp);
+  }
+  return HBR_OK;
+}
+
+extern "C" int hbr_mlp_fwd_tc(const void* feat_, int feat_dtype, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                               const float* params, const hbr_mlp_dims* dims, int operand, float* out, void* scratch,
                               void* stream) {
   if (int rc = check_dims(dims)) return rc;
   if (int rc = check_operand(operand, 1.f)) return rc;
   if (n == 0) return HBR_OK;
+  const float* feat = static_cast<const float*>(feat_);
   HBR_REQUIRE(feat && dirs && params && out, "NULL pointer");
+  if (int rc = check_feat(feat_, feat_dtype, feat_stride, dims, operand)) return rc;
+  const int f16 = feat_dtype != HBR_F32;
   HBR_REQUIRE(feat_stride >= dims->in0 && dir_group >= 1, "bad stride / dir_group");
   HBR_REQUIRE((uintptr_t)out % 16 == 0 && (uintptr_t)scratch % 256 == 0, "out / scratch alignment");
   cudaStream_t st = as_stream(stream);
   uint8_t* sc = static_cast<uint8_t*>(scratch);
   if (narrow_shape(dims))
     return HBR_BY_OPERAND(launch_fwd_tc<32, 48, 4, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view,
-                                                          out, sc, EncArgs{}, HashGeom{}, st));
+                                                          out, sc, EncArgs{}, HashGeom{}, f16, st));
   return HBR_BY_OPERAND(launch_fwd_tc<64, 64, 4, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out,
-                                                        sc, EncArgs{}, HashGeom{}, st));
+                                                        sc, EncArgs{}, HashGeom{}, f16, st));
 }
 
-extern "C" int hbr_mlp_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
+extern "C" int hbr_mlp_bwd_tc(const void* feat_, int feat_dtype, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                               const float* params, const hbr_mlp_dims* dims, int operand, const float* out,
                               const float* dout, float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams,
                               float grad_scale, void* scratch, void* stream) {
   if (int rc = check_dims(dims)) return rc;
   if (int rc = check_operand(operand, grad_scale)) return rc;
   if (n == 0) return HBR_OK;
+  const float* feat = static_cast<const float*>(feat_);
   HBR_REQUIRE(feat && dirs && params && out && dout, "NULL pointer");
+  if (int rc = check_feat(feat_, feat_dtype, feat_stride, dims, operand)) return rc;
+  const int f16 = feat_dtype != HBR_F32;
   HBR_REQUIRE(feat_stride >= dims->in0 && dir_group >= 1, "bad stride / dir_group");
   HBR_REQUIRE((uintptr_t)dout % 16 == 0 && (uintptr_t)out % 16 == 0 && (uintptr_t)scratch % 256 == 0,
               "out / dout / scratch alignment");
@@ -68,10 +85,10 @@ extern "C" int hbr_mlp_bwd_tc(const float* feat, int64_t feat_stride, const floa
   if (narrow_shape(dims))
     return HBR_BY_OPERAND(launch_bwd_tc<32, 48, 2, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view,
                                                           out, dout, dfeat, dfeat_stride, ddirs, dparams, sc, EncArgs{}, HashGeom{},
-                                                          grad_scale, st));
+                                                          grad_scale, f16, st));
   return HBR_BY_OPERAND(launch_bwd_tc<64, 64, 1, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out,
                                                         dout, dfeat, dfeat_stride, ddirs, dparams, sc, EncArgs{}, HashGeom{}, grad_scale,
-                                                        st));
+                                                        f16, st));
 }
 
 // ---- fused field evaluation: hash-grid encoder + MLP_3D in one kernel per direction ------------------------------
@@ -98,12 +115,12 @@ extern "C" int hbr_field_fwd_tc(const float* x, int64_t n, const float* table, c
     EncArgs e{};
     e.x = x; e.table = table; e.feat16 = static_cast<uint16_t*>(feat16);
     return f16::launch_fwd_tc<32, 48, 4, true>(nullptr, 32, dirs, dir_group, n, params, 32, dims->d_view, out,
-                                               static_cast<uint8_t*>(scratch), e, to_device_geom(*geom), as_stream(stream));
+                                               static_cast<uint8_t*>(scratch), e, to_device_geom(*geom), 0, as_stream(stream));
   }
   EncArgs e{};
   e.x = x; e.table = table; e.feat16 = static_cast<uint16_t*>(feat16);
   return bf16::launch_fwd_tc<32, 48, 4, true>(nullptr, 32, dirs, dir_group, n, params, 32, dims->d_view, out,
-                                              static_cast<uint8_t*>(scratch), e, to_device_geom(*geom), as_stream(stream));
+                                              static_cast<uint8_t*>(scratch), e, to_device_geom(*geom), 0, as_stream(stream));
 }
 
 extern "C" int hbr_field_bwd_tc(const float* x, int64_t n, const hbr_hash_geom* geom, const float* dirs, int64_t dir_group,
@@ -123,11 +140,11 @@ extern "C" int hbr_field_bwd_tc(const float* x, int64_t n, const hbr_hash_geom* 
     e.x = x; e.dtable = dtable; e.feat16 = f16p;
     return f16::launch_bwd_tc<32, 48, 2, true>(nullptr, 32, dirs, dir_group, n, params, 32, dims->d_view, out, dout, nullptr, 32,
                                                ddirs, dparams, static_cast<uint8_t*>(scratch), e, to_device_geom(*geom),
-                                               grad_scale, as_stream(stream));
+                                               grad_scale, 0, as_stream(stream));
   }
   EncArgs e{};
   e.x = x; e.dtable = dtable; e.feat16 = f16p;
   return bf16::launch_bwd_tc<32, 48, 2, true>(nullptr, 32, dirs, dir_group, n, params, 32, dims->d_view, out, dout, nullptr, 32,
                                               ddirs, dparams, static_cast<uint8_t*>(scratch), e, to_device_geom(*geom),
-                                              grad_scale, as_stream(stream));
+                                              grad_scale, 0, as_stream(stream));
 }

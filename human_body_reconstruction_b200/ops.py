@@ -71,6 +71,33 @@ def hash_encode_bwd(x: torch.Tensor, dy: torch.Tensor, geom: HashGeom, dtable: t
                                     int(level_begin), int(level_end), stream()))
 
 
+def _t_stride(t: torch.Tensor, S: int) -> int:
+    return 0 if t.dim() == 1 else S
+
+
+_TORCH_OF = {HBR_F32: torch.float32, HBR_F16: torch.float16, HBR_BF16: torch.bfloat16}
+
+
+def hash_encode_fwd_rays(rays_o, rays_d, t, table, geom: HashGeom, y_dtype: int = HBR_F32) -> torch.Tensor:
+    """Encoder forward with the sample positions o + d t formed in the kernel; y (R*S, L*F+E) in fp32 or already rounded to
+    the MLP's 16-bit operand format (y_dtype = HBR_F16 | HBR_BF16)."""
+    require_cuda(rays_o, rays_d, t, table)
+    R, S = rays_o.shape[0], t.shape[-1]
+    cols = geom.L * geom.F + geom.E
+    y = torch.empty((R * S, cols), device=table.device, dtype=_TORCH_OF[y_dtype])
+    check(lib().hbr_hash_encode_fwd_rays(ptr(rays_o), ptr(rays_d), ptr(t), _t_stride(t, S), R, S, ptr(table), C.byref(geom), ptr(y),
+                                         cols, y_dtype, stream()))
+    return y
+
+
+def hash_encode_bwd_rays(rays_o, rays_d, t, dy, geom: HashGeom, dtable, level_begin: int = 0, level_end: Optional[int] = None):
+    require_cuda(rays_o, rays_d, t, dy, dtable)
+    R, S = rays_o.shape[0], t.shape[-1]
+    level_end = geom.L if level_end is None else level_end
+    check(lib().hbr_hash_encode_bwd_rays(ptr(rays_o), ptr(rays_d), ptr(t), _t_stride(t, S), R, S, ptr(dy), dy.stride(0),
+                                         C.byref(geom), ptr(dtable), int(level_begin), int(level_end), stream()))
+
+
 def hash_indices(x: torch.Tensor, geom: HashGeom, want_w: bool = True):
     require_cuda(x)
     x = x.contiguous()
@@ -317,13 +344,22 @@ def _operand_torch_dtype(operand: int):
     return torch.float16 if operand == HBR_F16 else torch.bfloat16
 
 
+def _feat_dtype(feat: torch.Tensor, operand: int) -> int:
+    """HBR_F32, or the operand format when the features were produced in it already (hash_encode_fwd_rays)."""
+    if feat.dtype == torch.float32:
+        return HBR_F32
+    if feat.dtype == _operand_torch_dtype(operand):
+        return operand
+    raise TypeError(f"features are {feat.dtype}; the MLP kernels take float32 or their own operand format")
+
+
 def mlp_fwd_tc(feat, dirs, dir_group, params, dims: MlpDims, keep_act: bool = False, operand: int = HBR_BF16):
     """16-bit tensor-core forward; keeps nothing (the backward recomputes), returns (out, None)."""
     require_cuda(feat, dirs, params)
     n = feat.shape[0]
     out = torch.empty((n, 4), device=feat.device, dtype=torch.float32)
-    check(lib().hbr_mlp_fwd_tc(ptr(feat), feat.stride(0), ptr(dirs), dir_group, n, ptr(params), C.byref(dims), operand,
-                               ptr(out), ptr(mlp_tc_scratch(dims, feat.device)), stream()))
+    check(lib().hbr_mlp_fwd_tc(ptr(feat), _feat_dtype(feat, operand), feat.stride(0), ptr(dirs), dir_group, n, ptr(params),
+                               C.byref(dims), operand, ptr(out), ptr(mlp_tc_scratch(dims, feat.device)), stream()))
     return out, None
 
 
@@ -333,9 +369,9 @@ def mlp_bwd_tc(feat, dirs, dir_group, params, dims: MlpDims, out, dout, want_dfe
     n = feat.shape[0]
     dfeat = torch.empty((n, dims.in0), device=feat.device, dtype=torch.float32) if want_dfeat else None
     ddirs = torch.zeros_like(dirs) if want_ddirs else None
-    check(lib().hbr_mlp_bwd_tc(ptr(feat), feat.stride(0), ptr(dirs), dir_group, n, ptr(params), C.byref(dims), operand,
-                               ptr(out), ptr(dout), ptr(dfeat), dims.in0, ptr(ddirs), ptr(dparams), float(grad_scale),
-                               ptr(mlp_tc_scratch(dims, feat.device)), stream()))
+    check(lib().hbr_mlp_bwd_tc(ptr(feat), _feat_dtype(feat, operand), feat.stride(0), ptr(dirs), dir_group, n, ptr(params),
+                               C.byref(dims), operand, ptr(out), ptr(dout), ptr(dfeat), dims.in0, ptr(ddirs), ptr(dparams),
+                               float(grad_scale), ptr(mlp_tc_scratch(dims, feat.device)), stream()))
     return dfeat, ddirs
 
 

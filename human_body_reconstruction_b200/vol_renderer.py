@@ -66,6 +66,74 @@ class _FieldFn(torch.autograd.Function):
         return (None, ddirs, None, None, None) + tuple(g[i] for i in range(L)) + tuple(mlp._grad_views(dflat))
 
 
+class _FieldRaysFn(torch.autograd.Function):
+    """The autocast training path, one autograd node per field pass: (rays_o, rays_d, t) -> (R*S,4) [rgb, sigma].
+    Forward: hbr_hash_encode_fwd_rays (sample positions formed in the kernel, features written once, already in the MLP's
+    16-bit operand format -- the rounding MLP_3D's first Linear applies to its input under autocast, test_hash.py:53) ->
+    hbr_mlp_fwd_tc.  Backward: hbr_mlp_bwd_tc (recomputes from the saved 16-bit features) -> hbr_hash_encode_bwd_rays.
+    Against the module-by-module path (HashEncoder.forward -> MLP_3D.field) the (R*S,3) positions and the fp32 features are
+    never written or read, and the MLP kernels skip their conversion pass; the arithmetic is the same."""
+
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, t, dirs, enc, mlp, *params):
+        geom, dims = enc._geom(), mlp._dims()
+        operand = ops.tc_operand()
+        S = t.shape[-1]
+        feat16 = ops.hash_encode_fwd_rays(rays_o, rays_d, t, enc._flat_table(), geom, operand)
+        out, _ = ops.mlp_fwd_tc(feat16, dirs, S, mlp._flat_params(), dims, operand=operand)
+        ctx.enc, ctx.mlp, ctx.geom, ctx.dims, ctx.S, ctx.operand = enc, mlp, geom, dims, S, operand
+        ctx.save_for_backward(rays_o, rays_d, t, dirs, feat16, out)
+        ctx.want_tab = any(ctx.needs_input_grad[6:6 + enc.L])
+        ctx.want_mlp = any(ctx.needs_input_grad[6 + enc.L:])
+        ctx.g = None
+        if ctx.want_tab:
+            if enc._dp is not None:
+                enc._dp.note_forward(enc)
+            else:
+                ctx.g = enc._zeroed_grad_async()
+        if ctx.want_mlp and mlp._dp is not None:
+            mlp._dp.note_forward(mlp)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        rays_o, rays_d, t, dirs, feat16, out = ctx.saved_tensors
+        enc, mlp = ctx.enc, ctx.mlp
+        L, T, F = enc.L, enc.T, enc.F
+        flat = mlp._flat_params()
+        dpm = mlp._dp if ctx.want_mlp else None
+        if dpm is not None:
+            dflat, last_m = dpm.enter_backward(mlp)
+        else:
+            dflat, last_m = torch.zeros_like(flat), False
+        dfeat, ddirs = ops.mlp_bwd_tc(feat16, dirs, ctx.S, flat, ctx.dims, out.detach(), dout.float().contiguous(), ctx.want_tab,
+                                      ctx.needs_input_grad[3], dflat, operand=ctx.operand, grad_scale=mlp.tc_grad_scale)
+        if dpm is not None and last_m:
+            dpm.publish(mlp, dflat)
+        gm = (None,) * len(mlp._ordered()) if (dpm is not None or not ctx.want_mlp) else tuple(mlp._grad_views(dflat))
+        if not ctx.want_tab:
+            return (None, None, None, ddirs, None, None) + (None,) * L + gm
+        dpe = enc._dp
+        if dpe is not None:
+            g, last = dpe.enter_backward(enc)
+            nch = max(1, min(L, dpe.chunks(enc))) if last else 1
+            step = -(-L // nch)
+            for l0 in range(0, L, step):
+                l1 = min(L, l0 + step)
+                ops.hash_encode_bwd_rays(rays_o, rays_d, t, dfeat, ctx.geom, g, l0, l1)
+                if last:
+                    dpe.publish(enc, g[l0:l1])
+            return (None, None, None, ddirs, None, None) + (None,) * L + gm
+        if ctx.g is not None:
+            g, ev = ctx.g
+            ctx.g = None
+            torch.cuda.current_stream().wait_event(ev)
+        else:
+            g = torch.zeros((L, T, F), device=dout.device, dtype=torch.float32)
+        ops.hash_encode_bwd_rays(rays_o, rays_d, t, dfeat, ctx.geom, g, 0, L)
+        return (None, None, None, ddirs, None, None) + tuple(g[i] for i in range(L)) + gm
+
+
 def _unwrap(model):
     if isinstance(model, nn.DataParallel) and len(model.device_ids) <= 1:
         return model.module
@@ -104,6 +172,10 @@ class Volume_Renderer:
         # phases are latency-bound), and the separate path can overlap the table-gradient all-reduce per level chunk,
         # so it is opt-in: True fuses whenever the configuration is covered, "auto" only without gradient hooks.
         self.fuse_field = False
+        # Under autocast one autograd node drives the separate kernels (_FieldRaysFn): sample positions formed inside the
+        # hash-grid kernels, features handed to the MLP kernels in their 16-bit operand format.  False = module by module
+        # (HashEncoder.forward -> MLP_3D.field), the path every other caller of those modules takes.
+        self.chain_field = True
 
     # -- occupancy grid (vol_renderer.py:116-140) --------------------------------------------------------------
     def update_grid(self, points: torch.Tensor, alpha: torch.Tensor):
@@ -152,9 +224,25 @@ class Volume_Renderer:
             ok = ok and enc._dp is None
         return ok
 
+    def _can_chain(self, mlp) -> bool:
+        """_FieldRaysFn covers the autocast path whenever the encoder's width is the MLP kernels' operand width."""
+        enc = self.Pos_encode
+        if not (self.chain_field and torch.is_autocast_enabled() and ops.HAS_TC):
+            return False
+        width = enc.L * enc.F + enc.E
+        return width == mlp._in0 and (width % 2 == 0) and ((width == 32 and mlp.d_view <= 25) or width == 64)
+
     def _field_pass(self, mlp, rays_o, rays_d, t, dir_enc, dir_norm, mask_needed):
         """positions -> encoder -> MLP -> compositing for depths t ((S,) shared or (R,S) per ray)."""
         R, S = rays_o.shape[0], t.shape[-1]
+        if not self._can_fuse(mlp) and self._can_chain(mlp):
+            enc = self.Pos_encode
+            if enc._flat_table().device != rays_o.device:
+                raise RuntimeError(f"encoder tables are on {enc._flat_table().device}, rays on {rays_o.device}")
+            mask = self.get_mask(ops.ray_points(rays_o, rays_d, t).view(-1, 3)) if mask_needed else None
+            out4 = _FieldRaysFn.apply(rays_o, rays_d, t.float().contiguous(), dir_enc.float().contiguous(), enc, mlp,
+                                      *[e.weight for e in enc.Embedding_list], *mlp._ordered())
+            return ops.CompositePacked.apply(out4, t, dir_norm, mask, R, S)
         pts = ops.ray_points(rays_o, rays_d, t).view(-1, 3)
         mask = self.get_mask(pts) if mask_needed else None
         if self._can_fuse(mlp):

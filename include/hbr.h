@@ -76,6 +76,20 @@ int hbr_hash_encode_fwd(const void* x, int x_dtype, int64_t n, const float* tabl
 int hbr_hash_encode_bwd(const void* x, int x_dtype, int64_t n, const float* dy, int64_t dy_stride,
                         const hbr_hash_geom* geom_host, float* dtable, int level_begin, int level_end, void* stream);
 
+/* a2/a5/a9 for the training step: the same two kernels with the sample positions formed inside from the rays --
+ * point (r, s) = rays_o[r] + rays_d[r] * t[r * t_ray_stride + s], multiply and add rounded separately exactly like
+ * hbr_ray_points (vol_renderer.py:165, helper.py:48) -- so the (R*S,3) position tensor is never written or read.
+ * t is (S) shared (t_ray_stride = 0) or (R,S) per ray (t_ray_stride >= S).  The forward writes y (R*S, y_stride) as
+ * y_dtype = HBR_F32 or, for the autocast path (train_hash2.py:218), already rounded to the MLP's 16-bit operand
+ * format (HBR_F16 | HBR_BF16: y_stride even, y 4-byte aligned) -- the rounding the MLP's first Linear applies to its
+ * input under autocast -- which halves the feature traffic and lets hbr_mlp_*_tc skip its conversion pass. */
+int hbr_hash_encode_fwd_rays(const float* rays_o, const float* rays_d, const float* t, int64_t t_ray_stride, int64_t R,
+                             int64_t S, const float* table, const hbr_hash_geom* geom_host, void* y, int64_t y_stride,
+                             int y_dtype, void* stream);
+int hbr_hash_encode_bwd_rays(const float* rays_o, const float* rays_d, const float* t, int64_t t_ray_stride, int64_t R,
+                             int64_t S, const float* dy, int64_t dy_stride, const hbr_hash_geom* geom_host, float* dtable,
+                             int level_begin, int level_end, void* stream);
+
 /* Parity probe: the hash indices hash_encoding.py:161-162 computes (hash_func, :41-55), and the
  * n-linear weights of :142-143.  idx: (L,n,8) int32, w: (L,n,8) fp32 (either may be NULL). */
 int hbr_hash_indices(const void* x, int x_dtype, int64_t n, const hbr_hash_geom* geom_host,
@@ -116,9 +130,12 @@ int hbr_mlp_bwd_f32(const float* feat, int64_t feat_stride, const float* dirs, i
  * small prep kernel builds the 16-bit operand image once per call and the backward sums per-CTA gradient rows with a
  * reduce kernel; without it every CTA converts the parameters itself and flushes its gradients with atomics. */
 int64_t hbr_mlp_tc_scratch_bytes(const hbr_mlp_dims* dims);
-int hbr_mlp_fwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
+/* feat_dtype: HBR_F32 (n, feat_stride) fp32 features, or the operand format itself -- features already rounded to it by
+ * hbr_hash_encode_fwd_rays (contiguous rows of in0 16-bit values; in0 must be 32, or 64 for the wide shape): the kernels
+ * then copy the rows straight into their operand tile. */
+int hbr_mlp_fwd_tc(const void* feat, int feat_dtype, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                    const float* params, const hbr_mlp_dims* dims, int operand, float* out, void* scratch, void* stream);
-int hbr_mlp_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
+int hbr_mlp_bwd_tc(const void* feat, int feat_dtype, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                    const float* params, const hbr_mlp_dims* dims, int operand, const float* out, const float* dout,
                    float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams, float grad_scale, void* scratch,
                    void* stream);

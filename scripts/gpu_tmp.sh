@@ -1,4 +1,8 @@
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-( time timeout 1500 python -m pytest tests/test_gpu_multi.py tests/test_gpu_peer.py "tests/test_gpu_dropin_scripts.py::test_train_hash2_unmodified_on_two_gpus" -m gpu -q -x 2>&1 | tail -40 ) 2>&1 | tail -50
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench2.json 2> gpurun_out/bench2.err; echo "bench2 rc=$?"; tail -3 gpurun_out/bench2.err; cut -c1-400 gpurun_out/bench2.json
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 --hierarchical > gpurun_out/bench2h.json 2> gpurun_out/bench2h.err; echo "bench2h rc=$?"; tail -3 gpurun_out/bench2h.err; cut -c1-400 gpurun_out/bench2h.json
+for TILE in 128 64 32; do
+  export HBR_EXTRA_NVCC="-DHBR_HASH_TILE=$TILE"
+  touch human_body_reconstruction_b200/csrc/hash_grid.cu
+  python -c "from human_body_reconstruction_b200 import _lib; _lib.build()" > /dev/null 2>&1
+  python scripts/bench_hash.py 4096 2>&1 | tail -3
+  python scripts/bench_hash.py 131072 2>&1 | tail -3
+done

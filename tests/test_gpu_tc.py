@@ -217,3 +217,68 @@ def test_vol_render_fused_option_matches_default():
         res.append((Cr.detach(), torch.stack([e.weight.grad for e in enc.Embedding_list])))
     assert rel(res[1][0], res[0][0]) < 1e-5
     assert rel(res[1][1], res[0][1]) < 1e-4
+
+
+@pytest.mark.parametrize("fmt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("hier", [False, True])
+def test_chained_field_path_matches_module_path(fmt, hier):
+    """Volume_Renderer.chain_field (one autograd node: positions formed inside the hash kernels, 16-bit features handed to
+    the MLP kernels) against the module-by-module path (HashEncoder.forward -> MLP_3D.field): the MLP sees bit-identical
+    inputs, so colours are bit-identical and gradients agree to atomic-order noise."""
+    from conftest import load_golden
+    from test_gpu_parity import build_renderer
+    from human_body_reconstruction_b200 import _lib
+    g = load_golden("volrender.npz")
+    res = []
+    for chain in (False, True):
+        vr, enc, mlp = build_renderer(g)
+        vr.chain_field = chain
+        mlp.tc_grad_scale = 4096.0 if fmt == torch.float16 else 1.0
+        S = 24
+        t = port.strat_t(g["near"], g["far"], S, g["coarse__u_t"]).to(DEV)
+        _lib.STATS.reset()
+        with torch.autocast("cuda", dtype=fmt):
+            Cr, Cf, _ = vr.vol_render(mlp, g["rays_d"].to(DEV), g["rays_o"].to(DEV), num_samples=S, t=t,
+                                      dir_norm=g["dir_norm"].to(DEV), hierarchical=hier, _u=g["hier__u_rs"][:, :S].to(DEV),
+                                      _u_cand=g["hier__u_s"][:S].to(DEV))
+            loss = torch.nn.functional.mse_loss(Cr, g["gt"].to(DEV)) + torch.nn.functional.mse_loss(Cf, g["gt"].to(DEV))
+        loss.backward()
+        assert ("hbr_hash_encode_fwd_rays" in _lib.STATS.calls) == chain and ("hbr_hash_encode_bwd_rays" in _lib.STATS.calls) == chain
+        assert ("hbr_ray_points" in _lib.STATS.calls) == (not chain or hier)     # the chained path needs no position tensor
+        res.append((Cr.detach(), Cf.detach(), torch.stack([e.weight.grad for e in enc.Embedding_list]),
+                    {k: q.grad.clone() for k, q in mlp.named_parameters()}))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert rel(res[1][2], res[0][2]) < 1e-5
+    for k in res[0][3]:
+        assert rel(res[1][3][k], res[0][3][k]) < 1e-5, k
+
+
+def test_hash_encode_from_rays_matches_positions_path():
+    """hbr_hash_encode_fwd_rays / _bwd_rays == hbr_ray_points followed by hbr_hash_encode_fwd / _bwd, bit for bit in fp32;
+    the 16-bit outputs are the round-to-nearest of the fp32 ones."""
+    import human_body_reconstruction_b200 as h
+    from human_body_reconstruction_b200 import ops, _lib
+    torch.manual_seed(2)
+    mu, maxb = torch.tensor([-4.27, -4.31, -3.95]), torch.tensor([4.28, 4.27, 2.37])
+    sigma = ((maxb - mu) ** 2).sum().sqrt()
+    for T, R, S, per_ray in ((2 ** 14, 37, 40, False), (1000, 5, 128, True), (2 ** 12, 129, 7, True)):
+        enc = h.HashEncoder(N_min=16, N_max=2048.0, L=16, F=2, T=T, dim=3, mu=mu.to(DEV), sigma=sigma.to(DEV))
+        with torch.no_grad():
+            for e in enc.Embedding_list:
+                e.weight.mul_(5e3)
+        enc = enc.to(DEV)
+        ro = (torch.tensor([[0.2, -0.1, 4.0]]).repeat(R, 1) + 0.3 * torch.randn(R, 3)).to(DEV)
+        rd = torch.nn.functional.normalize(-ro.cpu() + 0.8 * torch.randn(R, 3), dim=-1).to(DEV)
+        t = (2 + 4 * torch.rand(R, S)).sort(-1).values.to(DEV) if per_ray else torch.linspace(2, 6, S, device=DEV)
+        geom, table = enc._geom(), enc._flat_table()
+        pts = ops.ray_points(ro, rd, t).view(-1, 3)
+        y = ops.hash_encode_fwd(pts, table, geom)
+        y_r = ops.hash_encode_fwd_rays(ro, rd, t, table, geom, _lib.HBR_F32)
+        assert torch.equal(y, y_r)
+        assert torch.equal(ops.hash_encode_fwd_rays(ro, rd, t, table, geom, _lib.HBR_BF16), y.bfloat16())
+        assert torch.equal(ops.hash_encode_fwd_rays(ro, rd, t, table, geom, _lib.HBR_F16), y.half())
+        dy = torch.randn_like(y)
+        g0, g1 = torch.zeros_like(table), torch.zeros_like(table)
+        ops.hash_encode_bwd(pts, dy, geom, g0)
+        ops.hash_encode_bwd_rays(ro, rd, t, dy, geom, g1)
+        assert rel(g1, g0) < 1e-6
