@@ -335,6 +335,7 @@ def run_reference(args):
 def run_b200(args):
     import human_body_reconstruction_b200 as hbr
     from human_body_reconstruction_b200 import _lib, dist as hdist
+    from human_body_reconstruction_b200.graph import default_loss
     import torch.distributed as tdist
 
     rank, world = hdist.init_from_env("nccl")
@@ -383,7 +384,7 @@ def run_b200(args):
         with torch.autocast("cuda", dtype=amp_dtype, enabled=amp):
             Cr, Cf, _ = vr.vol_render(nerf, d, o, num_samples=args.samples, update_mask=False, dir_norm=n,
                                       hierarchical=args.hierarchical)
-            loss = torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)
+            loss = default_loss(Cr, Cf, gt)                       # MSE(Cr) + MSE(Cf), train_hash2.py:221 (one fused kernel)
         loss.backward()
         return loss
 

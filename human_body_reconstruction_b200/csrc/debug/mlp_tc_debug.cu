@@ -58,7 +58,7 @@ extern "C" int hbr_debug_mlp_trace_bwd(const float* feat, const float* dirs, int
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), 2), sm_count());
   uint8_t* sc = static_cast<uint8_t*>(scratch);                        // as hbr_mlp_bwd_tc: operand image + gradient rows
   if (sc != nullptr) mlp_prep_kernel<32, 48><<<kPrepCtas, 256, 0, as_stream(stream)>>>(params, 32, 24, sc);
-  mlp_bwd_tc_kernel<32, 48, 2, true><<<grid, 2 * kGrpThreads + 32, smem, as_stream(stream)>>>(
+  mlp_bwd_tc_kernel<32, 48, 2, true><<<grid, 2 * kTile + 32, smem, as_stream(stream)>>>(
       feat, 32, dirs, dir_group, n, params, 32, 24, out, dout, dfeat, 32, nullptr, dparams, sc,
       sc != nullptr ? reinterpret_cast<float*>(sc + SC::off_grad) : nullptr, trace, EncArgs{}, HashGeom{}, 1.f, 0);
   HBR_LAUNCH_CHECK();

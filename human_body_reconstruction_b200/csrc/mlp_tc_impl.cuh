@@ -416,6 +416,50 @@ __device__ __forceinline__ void relu_epilogue64(uint32_t taddr, int r, uint8_t* 
   }
 }
 
+// dA (64 accumulator columns) * [activation > 0] -> bf16 dZ, in two steps for the backward chain: (1) dZ -> registers + tensor memory (the A operand of the next dgrad GEMM,
+// all the chain needs); (2) later, once the weight-gradient GEMM that still reads the activation tile has finished, the
+// in-place store of the dZ tile (the operand of the NEXT weight-gradient GEMM), off the critical chain.
+__device__ __forceinline__ void masked_dz_to_tmem64(uint32_t taddr, int r, const uint8_t* tile, uint32_t taddr_a, uint4* o) {
+  float v[64];
+  tmem_ld<64>(taddr, v);                         // all four loads in flight, one wait
+#pragma unroll
+  for (int cg = 0; cg < 8; ++cg) {
+    const uint4 h = *reinterpret_cast<const uint4*>(tile + chunk_off(r, cg, kTile));
+    const float* p = v + cg * 8;
+    uint4& q = o[cg];
+    q.x = OP::mask_pos(OP::pack(p[0], p[1]), h.x); q.y = OP::mask_pos(OP::pack(p[2], p[3]), h.y);
+    q.z = OP::mask_pos(OP::pack(p[4], p[5]), h.z); q.w = OP::mask_pos(OP::pack(p[6], p[7]), h.w);
+  }
+  tmem_st16(taddr_a, reinterpret_cast<const uint32_t*>(o));
+  tmem_st16(taddr_a + 16, reinterpret_cast<const uint32_t*>(o) + 16);
+  tmem_st_wait();
+}
+__device__ __forceinline__ void store_tile64(int r, uint8_t* tile, const uint4* o) {
+#pragma unroll
+  for (int cg = 0; cg < 8; ++cg) *reinterpret_cast<uint4*>(tile + chunk_off(r, cg, kTile)) = o[cg];
+}
+
+// colour-net input tile: [15 features | direction encoding | (optionally a 1.0 at column 15+dv) | 0 ...]
+// (all rows of a ray read the same direction row: broadcast loads that hit L1 after the first touch)
+template <int KCP, bool PLANT_ONE>
+__device__ __forceinline__ void build_cin(const float* o16, const float* __restrict__ dirs, long long dir_row, int dv,
+                                          bool valid, int r, uint8_t* cin) {
+#pragma unroll
+  for (int cg = 0; cg < KCP / 8; ++cg) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = cg * 8 + i;
+      float x = 0.f;
+      if (k < kFeat) x = o16[1 + k];                                    // feat_vec = dens_vec[:,1:]  (test_hash.py:64)
+      else if (k < kFeat + dv) x = valid ? __ldg(dirs + dir_row * dv + (k - kFeat)) : 0.f;   // concat(viewdirs) (:66)
+      else if (PLANT_ONE && k == kFeat + dv) x = 1.f;                   // meets a zero weight column; feeds the bias gradient
+      v[i] = x;
+    }
+    store_chunk<OP>(cin, r, cg, kTile, v);
+  }
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -555,25 +599,22 @@ __device__ __forceinline__ void encode_row(const EncArgs& e, const HashGeom& g, 
   }
 }
 
-// backward recompute: this thread's half (h) of the saved 16-bit feature row -> row r of the canonical A tile
-__device__ __forceinline__ void load_feat16_half(const EncArgs& e, long long gp, long long n, int r, int h, uint8_t* x0) {
+// backward recompute: this thread's saved bf16 feature row -> row r of the canonical A tile
+__device__ __forceinline__ void load_feat16_row(const EncArgs& e, long long gp, long long n, int r, uint8_t* x0) {
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    const int cg = 2 * h + c;
+  for (int cg = 0; cg < 4; ++cg) {
     const uint4 q = gp < n ? __ldg(reinterpret_cast<const uint4*>(e.feat16 + gp * 32) + cg) : make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(x0 + chunk_off(r, cg, kTile)) = q;
   }
 }
 
-// d(features) of levels [l_begin, l_begin + 8) of this thread's point (16 fp32 values in registers) -> scatter-add into the
-// table gradient.  A warp is 32 consecutive points (consecutive samples of a ray): runs of lanes in the same cell are merged
-// with shuffles and the run head issues the reductions, paired into red.global.add.v4.f32 where the two corners share a
-// 16-byte slot.
-__device__ __forceinline__ void scatter_levels(const EncArgs& e, const HashGeom& g, const float pt[3], bool valid, int lane,
-                                               const float* df, int l_begin, int nlev) {
+// d(features) of this thread's point (32 fp32 values in registers) -> scatter-add into the table gradient.  A warp is 32
+// consecutive points (consecutive samples of a ray): runs of lanes in the same cell are merged with shuffles and the
+// run head issues the reductions, paired into red.global.add.v4.f32 where the two corners share a 16-byte slot.
+__device__ __forceinline__ void scatter_row(const EncArgs& e, const HashGeom& g, const float pt[3], bool valid, int lane,
+                                            const float* df) {
 #pragma unroll 1
-  for (int li = 0; li < nlev; ++li) {
-    const int l = l_begin + li;
+  for (int l = 0; l < 16; ++l) {
     const float s = g.scale[l];
     long long ix, iy, iz;
     float fx, fy, fz;
@@ -584,8 +625,8 @@ __device__ __forceinline__ void scatter_levels(const EncArgs& e, const HashGeom&
     corner_weights(fx, fy, fz, w);
     float g0 = 0.f, g1 = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      if (q == li) { g0 = df[2 * q]; g1 = df[2 * q + 1]; }
+    for (int q = 0; q < 16; ++q)
+      if (q == l) { g0 = df[2 * q]; g1 = df[2 * q + 1]; }
     float val[8][2];
 #pragma unroll
     for (int c = 0; c < 8; ++c) { val[c][0] = w[c] * g0; val[c][1] = w[c] * g1; }
@@ -874,6 +915,29 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kCg = kTile * 16;                                        // bytes of one 8-column group of a 128-row tile
 
+// bias + ReLU on 64 accumulator columns -> bf16 activations in registers (o[8], one 16-byte chunk per column group) and,
+// with a valid taddr_a, in tensor memory as the next layer's A operand -- all the chain needs.  The caller stores o[] to
+// the activation tile in shared memory (the weight-gradient operand) behind the next GEMM's issue (store_tile64).
+// (The backward kernel adds the bias here: its two tile groups leave the CUDA cores mostly idle, while every MMA saved
+// shortens the issue-bound critical path.)
+__device__ __forceinline__ void relu_bias_to_tmem64(uint32_t taddr, const float* bias, uint32_t taddr_a, uint4* o) {
+  float v[64];
+  tmem_ld<64>(taddr, v);                         // all four loads in flight, one wait
+#pragma unroll
+  for (int cg = 0; cg < 8; ++cg) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + cg * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + cg * 8 + 4);
+    const float* p = v + cg * 8;
+    o[cg].x = OP::pack_relu(p[0] + b0.x, p[1] + b0.y); o[cg].y = OP::pack_relu(p[2] + b0.z, p[3] + b0.w);
+    o[cg].z = OP::pack_relu(p[4] + b1.x, p[5] + b1.y); o[cg].w = OP::pack_relu(p[6] + b1.z, p[7] + b1.w);
+  }
+  if (taddr_a != 0xffffffffu) {
+    tmem_st16(taddr_a, reinterpret_cast<const uint32_t*>(o));
+    tmem_st16(taddr_a + 16, reinterpret_cast<const uint32_t*>(o) + 16);
+    tmem_st_wait();
+  }
+}
+
 // 16-wide dZ (the two 16-output layers): bf16 into the shared-memory tile (weight-gradient operand) and into tensor
 // memory (A operand of the dgrad GEMM)
 __device__ __forceinline__ void store_dz16_both(const float* dz16, int r, uint8_t* dzs, uint32_t taddr_a) {
@@ -957,9 +1021,8 @@ __device__ __noinline__ void flush_gradients(uint32_t tbase, int warp, int lane,
       for (int e = threadIdx.x; e < m.total; e += blockDim.x) row[e] = 0.f;
     return;
   }
-  if (warp >= 8 * ngroups) return;
-  // a tile group is 8 warps = 4 TMEM lane quarters x 2: the six accumulators are dealt to the 2 * ngroups warp quartets
-  const int wq = warp & 3, unit = warp >> 2, units = 2 * ngroups;
+  if (warp >= 4 * ngroups) return;
+  const int wq = warp & 3, unit = warp >> 2, units = ngroups;     // the six accumulators are dealt to the groups' warp quartets
   const uint32_t trow = tbase + ((uint32_t)(wq * 32) << 16);
   auto put = [&](int idx, float v) {
     if (row != nullptr) row[idx] = v * ginv;
@@ -1021,54 +1084,8 @@ __device__ __noinline__ void flush_gradients(uint32_t tbase, int warp, int lane,
   }
 }
 
-// ---- half-row helpers of the backward kernel: a tile group is 256 threads, TWO per row: thread (r, h) owns TMEM lane r and
-//      the column half h of every 64-wide accumulator (columns [32 h, 32 h + 32)), so every epilogue chain is half as
-//      long as with one thread per row and twice as many warps hide the TMEM / shared-memory latency.
-// bias + ReLU on this thread's 32 accumulator columns -> activations in registers (o[4], one 16-byte chunk per column group)
-// and, with to_tmem, in tensor memory as the next layer's A operand -- all the chain needs.  The caller stores o[] to the
-// activation tile in shared memory (the weight-gradient operand) behind the next GEMM's issue (store_half).
-__device__ __forceinline__ void relu_bias_half(uint32_t taddr, const float* bias, int h, uint32_t taddr_a, bool to_tmem, uint4* o) {
-  float v[32];
-  tmem_ld<32>(taddr + 32 * h, v);                // both loads in flight, one wait
-  const float* b = bias + 32 * h;
-#pragma unroll
-  for (int cg = 0; cg < 4; ++cg) {
-    const float4 b0 = *reinterpret_cast<const float4*>(b + cg * 8);
-    const float4 b1 = *reinterpret_cast<const float4*>(b + cg * 8 + 4);
-    const float* p = v + cg * 8;
-    o[cg].x = OP::pack_relu(p[0] + b0.x, p[1] + b0.y); o[cg].y = OP::pack_relu(p[2] + b0.z, p[3] + b0.w);
-    o[cg].z = OP::pack_relu(p[4] + b1.x, p[5] + b1.y); o[cg].w = OP::pack_relu(p[6] + b1.z, p[7] + b1.w);
-  }
-  if (to_tmem) {
-    tmem_st16(taddr_a + 16 * h, reinterpret_cast<const uint32_t*>(o));
-    tmem_st_wait();
-  }
-}
-// dA (this thread's 32 accumulator columns) * [activation > 0] -> dZ in registers + tensor memory (the A operand of the
-// next dgrad GEMM); the in-place store of the dZ tile (operand of the NEXT weight-gradient GEMM) follows off the chain.
-__device__ __forceinline__ void masked_dz_half(uint32_t taddr, int r, int h, const uint8_t* tile, uint32_t taddr_a, uint4* o) {
-  float v[32];
-  tmem_ld<32>(taddr + 32 * h, v);
-#pragma unroll
-  for (int cg = 0; cg < 4; ++cg) {
-    const uint4 a = *reinterpret_cast<const uint4*>(tile + chunk_off(r, 4 * h + cg, kTile));
-    const float* p = v + cg * 8;
-    uint4& q = o[cg];
-    q.x = OP::mask_pos(OP::pack(p[0], p[1]), a.x); q.y = OP::mask_pos(OP::pack(p[2], p[3]), a.y);
-    q.z = OP::mask_pos(OP::pack(p[4], p[5]), a.z); q.w = OP::mask_pos(OP::pack(p[6], p[7]), a.w);
-  }
-  tmem_st16(taddr_a + 16 * h, reinterpret_cast<const uint32_t*>(o));
-  tmem_st_wait();
-}
-__device__ __forceinline__ void store_half(int r, int h, uint8_t* tile, const uint4* o) {
-#pragma unroll
-  for (int cg = 0; cg < 4; ++cg) *reinterpret_cast<uint4*>(tile + chunk_off(r, 4 * h + cg, kTile)) = o[cg];
-}
-
-constexpr int kGrpThreads = 2 * kTile;            // threads of a backward tile group
-
 template <int K0P, int KCP, int G, bool TRACE = false, bool ENC = false>
-__global__ void __launch_bounds__(G * kGrpThreads + 32, 1)
+__global__ void __launch_bounds__(G * kTile + 32, 1)
 mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const float* __restrict__ dirs, long long dir_group,
                   long long n, const float* __restrict__ params, int in0, int dv, const float* __restrict__ out,
                   const float* __restrict__ dout, float* __restrict__ dfeat, long long dfeat_stride,
@@ -1079,16 +1096,14 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   // gscale: power of two applied to the upstream gradient before it is rounded to the 16-bit operand format and divided
   // out of every result (fp16 has 5 exponent bits: unscaled gradients of a mean-reduced loss underflow; the reference
   // relies on GradScaler for the same reason, train_hash2.py:156,226).  1.0 = off.
+  const float ginv = 1.f / gscale;
   using SM = BwdSmem<K0P, KCP, G>;
   using WO = WOfs<K0P, KCP>;
-  // TMEM per tile group: 64 work-accumulator columns + 32 columns holding the A operand (16-bit pairs) of the group's next
+  // TMEM per tile group: 64 work-accumulator columns + 32 columns holding the A operand (bf16 pairs) of the group's next
   // forward / dgrad GEMM; the gradient accumulators start behind the groups
   constexpr int kGrpCols = 96;
   using TM = BwdTmem<K0P, KCP, 2 * kGrpCols>;
   constexpr bool kCinOne = TM::kCinOne;
-  // column split of the colour-net input / d(colour-net input) between the two threads of a row: thread h = 0 owns the
-  // columns that hold the 15 features (it also forms the 16-wide dZ of the density head), thread h = 1 the rest
-  constexpr int kCinSplit = KCP == 48 ? 16 : 32;
   static_assert(G >= 1 && G <= 2, "two work accumulators");
   extern __shared__ __align__(128) uint8_t sm[];
   const MlpLayout m = make_layout(in0, dv);
@@ -1150,7 +1165,7 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   }
   const long long kmax = nt[0];                  // the slot of group 0 never has fewer tiles than a later group's
 
-  if (warp >= 8 * G) {
+  if (warp >= 4 * G) {
     // ===== weight-gradient issuer (one converged warp): every weight/bias-gradient GEMM of the CTA -- the accumulators
     // all tiles share -- comes from this one thread sequence, visiting the groups in a fixed order.  It waits on
     // startB[g], committed by the group right behind the stage's dgrad (so the chain-critical dgrad never queues behind a
@@ -1196,26 +1211,23 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       first = false;
     }
   } else {
-    // ===== tile group: 8 warps = 128 rows x 2 column halves =====
-    const int g = warp >> 3;
-    const int wq = warp & 3, h = (warp >> 2) & 1;                       // TMEM lane quarter, column half
-    const int r = wq * 32 + lane;                                        // row of the tile == TMEM lane
-    const int gt = threadIdx.x - g * kGrpThreads;                        // thread index inside the group
+    // ===== tile group =====
+    const int g = warp >> 2;
+    const int r = threadIdx.x & (kTile - 1);
     uint8_t* gb = sm + SM::off_grp + g * SM::grp_bytes;
     uint8_t *x0 = gb + SM::x0, *h1 = gb + SM::h1, *h2 = gb + SM::h2, *cin = gb + SM::cin, *c1 = gb + SM::c1,
             *c2 = gb + SM::c2, *dzs = gb + SM::dzs;
     // The group's first warp issues the group's own forward-recompute / dgrad GEMMs (independent work accumulator): the
-    // hand-off is one named barrier over the group's 256 threads instead of an mbarrier round trip through an issuer warp.
+    // hand-off is one named barrier over the 128 threads instead of an mbarrier round trip through an issuer warp.
     uint64_t* done = bars + G + g;
     uint64_t* doneb = bars + 2 * G + g;
     uint64_t* startb = bars + 3 * G + g;
-    const bool issuer = (warp & 7) == 0;
+    const bool issuer = (warp & 3) == 0;
     const uint32_t tgrp = tbase + g * kGrpCols, tgrp_a = tgrp + 64;
-    const uint32_t taddr = tgrp + ((uint32_t)(wq * 32) << 16);
+    const uint32_t taddr = tgrp + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t taddr_a = taddr + 64;
     const uint32_t wa = a4_of(wsm), x0a = a4_of(x0);
     uint32_t dphase = 0, bphase = 0;
-#define HBR_GBAR() asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kGrpThreads) : "memory")
 #define HBR_BSTAGE(BWD, BODY) HBR_BSTAGE_T(BODY, {})
     // forward-recompute stage; TRAIL runs between the issue and the wait (work the chain does not need)
 #define HBR_BSTAGE_T(BODY, ...)                                            \
@@ -1223,7 +1235,7 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     HBR_STAMP(0);                                                          \
     fence_async_smem();                                                    \
     fence_before_sync();                                                   \
-    HBR_GBAR();                                                            \
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");             \
     if (issuer) {                                                          \
       fence_after_sync();                                                  \
       if (elect_one()) {                                                   \
@@ -1252,7 +1264,7 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   do {                                                                     \
     HBR_STAMP(0);                                                          \
     fence_before_sync();                                                   \
-    HBR_GBAR();                                                            \
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");             \
     HBR_STAMP(1);                                                          \
     if (issuer) {                                                          \
       fence_after_sync();                                                  \
@@ -1266,8 +1278,8 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     __VA_ARGS__;                                                           \
     HBR_STAMP(3);                                                          \
     fence_async_smem();                                                    \
-    HBR_GBAR();                                                            \
-    if (gt == 0) mbar_arrive(startb);                                      \
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");             \
+    if (r == 0) mbar_arrive(startb);                                       \
     HBR_STAMP(4);                                                          \
     mbar_wait(done, dphase);                                               \
     dphase ^= 1;                                                           \
@@ -1300,8 +1312,8 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       const bool valid = gp < n;
       const long long dir_row = valid ? gp / dir_group : 0;
       if (valid && lane == 0) prefetch_l1(dirs + dir_row * dv);
-      float4 fo = make_float4(0.f, 0.f, 0.f, 0.f), go = fo;           // saved forward output, upstream gradient (thread h = 0)
-      if (valid && h == 0) {
+      float4 fo = make_float4(0.f, 0.f, 0.f, 0.f), go = fo;           // saved forward output, upstream gradient
+      if (valid) {
         fo = __ldg(reinterpret_cast<const float4*>(out + gp * 4));
         go = __ldg(reinterpret_cast<const float4*>(dout + gp * 4));
         go.x *= gscale; go.y *= gscale; go.z *= gscale; go.w *= gscale;
@@ -1310,25 +1322,25 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       float pt[3] = {0.f, 0.f, 0.f};
       if (ENC) {
         if (valid) { pt[0] = __ldg(enc.x + gp * 3 + 0); pt[1] = __ldg(enc.x + gp * 3 + 1); pt[2] = __ldg(enc.x + gp * 3 + 2); }
-        load_feat16_half(enc, gp, n, r, h, x0);
+        load_feat16_row(enc, gp, n, r, x0);
       } else if (staged && f16in) {
-        // the rows were copied into the (dead) c2 tile in canonical layout already: move this thread's own chunks over
+        // the rows were copied into the (dead) c2 tile in canonical layout already: move this thread's own row over
         cp_async_wait_all();
 #pragma unroll
-        for (int c = 0; c < K0P / 16; ++c) {
-          const uint32_t o = chunk_off(r, h * (K0P / 16) + c, kTile);
+        for (int cg = 0; cg < K0P / 8; ++cg) {
+          const uint32_t o = chunk_off(r, cg, kTile);
           *reinterpret_cast<uint4*>(x0 + o) = *reinterpret_cast<const uint4*>(c2 + o);
         }
       } else if (f16in) {
-        copy_feat16_async<K0P, 2>(featq, tile * kTile, n, r, h, x0);
+        copy_feat16_async<K0P, 1>(featq, tile * kTile, n, r, 0, x0);
         cp_async_wait_all();
       } else if (staged) {
         cp_async_wait_all();
-        convert_staged_features<K0P, kGrpThreads>(c2, gt, x0);   // every thread converts exactly the elements it copied itself
+        convert_staged_features<K0P>(c2, r, x0);   // every thread converts exactly the elements it copied itself
       } else {
-        load_features<K0P, kGrpThreads>(feat, feat_stride, tile * kTile, n, in0, vec_ok, gt, r, h, x0);
+        load_features<K0P>(feat, feat_stride, tile * kTile, n, in0, vec_ok, r, r, 0, x0);
       }
-      if (h == 0 && (tile + nslots) * kTile + r < n) {
+      if ((tile + nslots) * kTile + r < n) {
         if (ENC) prefetch_l2(enc.feat16 + ((tile + nslots) * kTile + r) * 32);
         else if (!stage_ok && !f16in) prefetch_l2(feat + ((tile + nslots) * kTile + r) * feat_stride);
         if ((r & 7) == 0) {
@@ -1336,75 +1348,38 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
           prefetch_l2(dout + ((tile + nslots) * kTile + r) * 4);
         }
       }
-      uint4 dzt[4];                              // this thread's half of the activation / dZ row formed by the last epilogue
+      uint4 dzt[8];                              // activation / dZ tile formed by the last epilogue, stored one stage later
       HBR_BSTAGE(false, issue_fwd(tgrp, x0a, wa + WO::w0 / 16, 64, K0P));                       // F0 (x0 from shared memory)
-      relu_bias_half(taddr, bias + 0, h, taddr_a, true, dzt);
+      relu_bias_to_tmem64(taddr, bias + 0, taddr_a, dzt);
       HBR_BSTAGE_T(issue_fwd_ts(tgrp, tgrp_a, wa + WO::w1 / 16, 64, 64, false),                 // F1
-                   { store_half(r, h, h1, dzt); });
-      relu_bias_half(taddr, bias + 64, h, taddr_a, true, dzt);
+                   { store_tile64(r, h1, dzt); });
+      relu_bias_to_tmem64(taddr, bias + 64, taddr_a, dzt);
       HBR_BSTAGE_T(issue_fwd_ts(tgrp, tgrp_a, wa + WO::w2 / 16, 16, 64, false),                 // F2
-                   { store_half(r, h, h2, dzt); });
+                   { store_tile64(r, h2, dzt); });
       {
-        // colour-net input [15 features | direction encoding | (a planted 1.0) | 0 ...]: thread 0 of the row forms columns
-        // [0, kCinSplit) (it needs the density head's 16 outputs), thread 1 the rest (direction columns: broadcast loads
-        // that hit L1 after the first touch).  Both write their chunks to the shared-memory tile (weight-gradient operand)
-        // and to tensor memory (A operand of the colour net's first GEMM).
-        if (h == 0) {
-          float o16[16];
-          tmem_ld<16>(taddr, o16);
+        float o16[16];
+        tmem_ld<16>(taddr, o16);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) o16[k] += bias[128 + k];
-          uint32_t p[kCinSplit / 2];
+        for (int k = 0; k < 16; ++k) o16[k] += bias[128 + k];
+        build_cin<KCP, kCinOne>(o16, dirs, dir_row, dv, valid, r, cin);
+        // the same row as the A operand of the colour net's first GEMM: copy this thread's chunks smem -> TMEM
+        uint32_t p[KCP / 2];
 #pragma unroll
-          for (int q = 0; q < kCinSplit / 2; ++q) {
-            float e[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int k = 2 * q + j;                                   // compile-time column
-              float x = 0.f;
-              if (k < kFeat) x = o16[k < kFeat ? 1 + k : 0];             // feat_vec = dens_vec[:,1:]  (test_hash.py:64)
-              else if (k < kFeat + dv) x = valid ? __ldg(dirs + dir_row * dv + (k - kFeat)) : 0.f;   // concat(viewdirs) (:66)
-              else if (kCinOne && k == kFeat + dv) x = 1.f;             // meets a zero weight column; feeds the bias gradient
-              e[j] = x;
-            }
-            p[q] = OP::pack(e[0], e[1]);
-          }
-#pragma unroll
-          for (int cg = 0; cg < kCinSplit / 8; ++cg)
-            *reinterpret_cast<uint4*>(cin + chunk_off(r, cg, kTile)) = make_uint4(p[4 * cg], p[4 * cg + 1], p[4 * cg + 2], p[4 * cg + 3]);
-          if (kCinSplit == 16) tmem_st8(taddr_a, p);
-          else tmem_st16(taddr_a, p);
-        } else {
-          constexpr int kRest = KCP - kCinSplit;
-          uint32_t p[kRest / 2];
-#pragma unroll
-          for (int q = 0; q < kRest / 2; ++q) {
-            float e[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int k = kCinSplit + 2 * q + j;
-              float x = 0.f;
-              if (k < kFeat + dv) x = valid ? __ldg(dirs + dir_row * dv + (k - kFeat)) : 0.f;
-              else if (kCinOne && k == kFeat + dv) x = 1.f;
-              e[j] = x;
-            }
-            p[q] = OP::pack(e[0], e[1]);
-          }
-#pragma unroll
-          for (int cg = 0; cg < kRest / 8; ++cg)
-            *reinterpret_cast<uint4*>(cin + chunk_off(r, kCinSplit / 8 + cg, kTile)) =
-                make_uint4(p[4 * cg], p[4 * cg + 1], p[4 * cg + 2], p[4 * cg + 3]);
-          tmem_st16(taddr_a + kCinSplit / 2, p);
-          if (kRest == 32) {}                                            // 16 packed columns: one store
+        for (int cg = 0; cg < KCP / 8; ++cg) {
+          const uint4 q = *reinterpret_cast<const uint4*>(cin + chunk_off(r, cg, kTile));
+          p[4 * cg] = q.x; p[4 * cg + 1] = q.y; p[4 * cg + 2] = q.z; p[4 * cg + 3] = q.w;
         }
+        tmem_st16(taddr_a, p);
+        if (KCP == 48) tmem_st8(taddr_a + 16, p + 16);
+        else tmem_st16(taddr_a + 16, p + 16);
         tmem_st_wait();
       }
       HBR_BSTAGE(false, issue_fwd_ts(tgrp, tgrp_a, wa + WO::w3 / 16, 64, KCP, false));          // F3
-      relu_bias_half(taddr, bias + 192, h, taddr_a, true, dzt);
+      relu_bias_to_tmem64(taddr, bias + 192, taddr_a, dzt);
       HBR_BSTAGE_T(issue_fwd_ts(tgrp, tgrp_a, wa + WO::w4 / 16, 64, 64, false),                 // F4
-                   { store_half(r, h, c1, dzt); });
-      relu_bias_half(taddr, bias + 256, h, taddr_a, false, dzt);       // c2 feeds no forward GEMM here
-      if (h == 0) {
+                   { store_tile64(r, c1, dzt); });
+      relu_bias_to_tmem64(taddr, bias + 256, 0xffffffffu, dzt);         // c2 feeds no forward GEMM here
+      {
         // d(rgb_pre) = g * ELU'(pre), with ELU'(pre) = pre > 0 ? 1 : exp(pre) = elu(pre) + 1 from the saved output
         float dz16[16];
 #pragma unroll
@@ -1415,103 +1390,90 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         store_dz16_both(dz16, r, dzs, taddr_a);
       }
       HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w5 / 16, 16, 64),                    // col_model.4: work = dA(c2)
-                     { store_half(r, h, c2, dzt); });   // the c2 activations, before this stage's weight-gradient GEMM starts
-      masked_dz_half(taddr, r, h, c2, taddr_a, dzt);
+                     { store_tile64(r, c2, dzt); });   // the c2 activations, before this stage's weight-gradient GEMM starts
+      masked_dz_to_tmem64(taddr, r, c2, taddr_a, dzt);
       HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w4 / 16, 64, 64),                    // col_model.2: work = dA(c1)
-                     { HBR_WAIT_B(); store_half(r, h, c2, dzt); });
-      masked_dz_half(taddr, r, h, c1, taddr_a, dzt);
+                     { HBR_WAIT_B(); store_tile64(r, c2, dzt); });
+      masked_dz_to_tmem64(taddr, r, c1, taddr_a, dzt);
       staged = stage_ok && tile + nslots < ntiles;
       HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w3 / 16, 64, KCP), {                 // col_model.0: work[0,KCP) = d(cin)
         HBR_WAIT_B();                            // the weight-gradient GEMM reading c2 (dZ) and c1 has finished: c2 is dead
-        store_half(r, h, c1, dzt);
-        if (staged && f16in) copy_feat16_async<K0P, 2>(featq, (tile + nslots) * kTile, n, r, h, c2);
-        else if (staged) stage_features_async<K0P, kGrpThreads>(feat, (tile + nslots) * kTile, n, gt, c2);
+        store_tile64(r, c1, dzt);
+        if (staged && f16in) copy_feat16_async<K0P, 1>(featq, (tile + nslots) * kTile, n, r, 0, c2);
+        else if (staged) stage_features_async<K0P>(feat, (tile + nslots) * kTile, n, r, c2);
       });
-      // d(colour-net input): thread 0 takes columns [0, kCinSplit) -- the 15 feature gradients that, with the density
-      // gradient, form the 16-wide dZ of sig_model.4 -- thread 1 the remaining direction columns
-      constexpr int kDd = KCP - kCinSplit;       // >= columns either thread holds direction gradients for
-      float dd[kDd];                             // d(direction encoding), reduced into ddirs off the chain
+      float dd[KCP - kFeat];                     // d(direction encoding), reduced into ddirs off the chain
       uint32_t dzp[8];
-      const float ginv = 1.f / gscale;
-      if (h == 0) {
-        float dc[kCinSplit], dz16[16];
-        tmem_ld<kCinSplit>(taddr, dc);
+      {
+        float dc[KCP], dz16[16];
+        tmem_ld<KCP>(taddr, dc);
         dz16[0] = go.w * (fo.w > 0.f ? 1.f : 0.01f);                    // LeakyReLU' from the saved density
 #pragma unroll
         for (int k = 0; k < kFeat; ++k) dz16[1 + k] = dc[k];
 #pragma unroll
-        for (int k = kFeat; k < kCinSplit; ++k) dd[k - kFeat] = dc[k] * ginv;
+        for (int k = kFeat; k < KCP; ++k) dd[k - kFeat] = dc[k] * ginv;
 #pragma unroll
         for (int q = 0; q < 8; ++q) dzp[q] = OP::pack(dz16[2 * q], dz16[2 * q + 1]);
         tmem_st8(taddr_a, dzp);
         tmem_st_wait();
-      } else {
-        float dc[kDd];
-        tmem_ld<kDd>(taddr + kCinSplit, dc);
-#pragma unroll
-        for (int k = 0; k < kDd; ++k) dd[k] = dc[k] * ginv;
       }
       HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w2 / 16, 16, 64), {                  // sig_model.4: work = dA(h2)
         HBR_WAIT_B();                            // the 16-wide dZ tile may alias the padding of the colour-net input tile
-        if (h == 0) {
-          *reinterpret_cast<uint4*>(dzs + chunk_off(r, 0, kTile)) = make_uint4(dzp[0], dzp[1], dzp[2], dzp[3]);
-          *reinterpret_cast<uint4*>(dzs + chunk_off(r, 1, kTile)) = make_uint4(dzp[4], dzp[5], dzp[6], dzp[7]);
-        }
+        *reinterpret_cast<uint4*>(dzs + chunk_off(r, 0, kTile)) = make_uint4(dzp[0], dzp[1], dzp[2], dzp[3]);
+        *reinterpret_cast<uint4*>(dzs + chunk_off(r, 1, kTile)) = make_uint4(dzp[4], dzp[5], dzp[6], dzp[7]);
         if (ddirs != nullptr) {
-          // rows of one warp usually belong to one ray: reduce over the warp first, one atomic per column.
-          // dd[j] of thread h is column (h == 0 ? kFeat : kCinSplit) + j of the colour-net input
-          const int col0 = h == 0 ? kFeat : kCinSplit, ncol = h == 0 ? kCinSplit - kFeat : kDd;
+          // rows of one warp usually belong to one ray: reduce over the warp first, one atomic per column
           const long long row0 = __shfl_sync(kFull, dir_row, 0);
           const bool uniform = __all_sync(kFull, dir_row == row0 && valid);
-          _Pragma("unroll") for (int j = 0; j < kDd; ++j) {
-            const int k = col0 + j;
-            if (j < ncol && k < kFeat + dv) {
+          _Pragma("unroll") for (int k = kFeat; k < KCP; ++k) {
+            if (k < kFeat + dv) {
               if (uniform) {
-                const float sdd = warp_sum(dd[j]);
+                const float sdd = warp_sum(dd[k - kFeat]);
                 if (lane == 0) atomicAdd(ddirs + row0 * dv + (k - kFeat), sdd);
               } else if (valid) {
-                atomicAdd(ddirs + dir_row * dv + (k - kFeat), dd[j]);
+                atomicAdd(ddirs + dir_row * dv + (k - kFeat), dd[k - kFeat]);
               }
             }
           }
         }
       });
-      masked_dz_half(taddr, r, h, h2, taddr_a, dzt);
+      masked_dz_to_tmem64(taddr, r, h2, taddr_a, dzt);
       HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w1 / 16, 64, 64),                    // sig_model.2: work = dA(h1)
-                     { HBR_WAIT_B(); store_half(r, h, h2, dzt); });
-      masked_dz_half(taddr, r, h, h1, taddr_a, dzt);
+                     { HBR_WAIT_B(); store_tile64(r, h2, dzt); });
+      masked_dz_to_tmem64(taddr, r, h1, taddr_a, dzt);
       HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w0 / 16, 64, K0P),                   // sig_model.0: work[0,K0P) = d(feat)
-                     { HBR_WAIT_B(); store_half(r, h, h1, dzt); });
-      if (ENC || dfeat != nullptr) {
-        constexpr int kHalf = K0P / 2;           // this thread's d(feat) columns [h kHalf, (h + 1) kHalf)
-        float df[kHalf];
-        tmem_ld<kHalf>(taddr + h * kHalf, df);
+                     { HBR_WAIT_B(); store_tile64(r, h1, dzt); });
+      if (ENC) {
+        float df[K0P];
+        tmem_ld<K0P>(taddr, df);
 #pragma unroll
-        for (int k = 0; k < kHalf; ++k) df[k] *= ginv;
-        if (ENC) {
-          scatter_levels(enc, geom, pt, valid, lane, df, h * (kHalf / 2), kHalf / 2);
-        } else if (dvec_ok) {
+        for (int k = 0; k < K0P; ++k) df[k] *= ginv;
+        scatter_row(enc, geom, pt, valid, lane, df);
+      } else if (dfeat != nullptr) {
+        float df[K0P];
+        tmem_ld<K0P>(taddr, df);
+#pragma unroll
+        for (int k = 0; k < K0P; ++k) df[k] *= ginv;
+        if (dvec_ok) {
           // rows -> the (dead) h2 tile as fp32 with an XOR swizzle on the 16-byte chunk index, then lane-contiguous
-          // float4 stores of the tile's contiguous 128*K0P*4-byte block of dfeat (measured: 16-byte stores per thread
-          // straight from registers, 32 partial sectors per instruction, are ~400 cycles slower per tile)
+          // float4 stores of the tile's contiguous 128*K0P*4-byte block of dfeat (measured: eight 16-byte stores per
+          // thread straight from registers, 32 partial sectors per instruction, are ~400 cycles slower per tile)
           constexpr int kQ = K0P / 4;
           float4* stg = reinterpret_cast<float4*>(h2);
 #pragma unroll
-          for (int c = 0; c < kQ / 2; ++c) {
-            const int cc = h * (kQ / 2) + c;
-            stg[r * kQ + (cc ^ (r & 7))] = make_float4(df[4 * c], df[4 * c + 1], df[4 * c + 2], df[4 * c + 3]);
-          }
-          HBR_GBAR();
+          for (int c = 0; c < kQ; ++c)
+            stg[r * kQ + (c ^ (r & 7))] = make_float4(df[4 * c], df[4 * c + 1], df[4 * c + 2], df[4 * c + 3]);
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
           float4* dst = reinterpret_cast<float4*>(dfeat + tile * kTile * K0P);
 #pragma unroll
-          for (int it = 0; it < kTile * kQ / kGrpThreads; ++it) {
-            const int idx = it * kGrpThreads + gt, row = idx / kQ, c = idx % kQ;
+          for (int it = 0; it < kQ; ++it) {
+            const int idx = it * kTile + r, row = idx / kQ, c = idx % kQ;
             if (tile * kTile + row < n) dst[idx] = stg[row * kQ + (c ^ (row & 7))];
           }
         } else if (valid) {
 #pragma unroll
-          for (int k = 0; k < kHalf; ++k)
-            if (h * kHalf + k < in0) dfeat[gp * dfeat_stride + h * kHalf + k] = df[k];
+          for (int k = 0; k < K0P; ++k)
+            if (k < in0) dfeat[gp * dfeat_stride + k] = df[k];
         }
       }
       HBR_STAMP(0);                              // d(feat) written
@@ -1525,7 +1487,7 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   fence_after_sync();
   if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2002] = clock64();
 
-  flush_gradients<K0P, KCP, 2 * kGrpCols>(tbase, warp, lane, G, m, cta_tiles > 0, dparams, grad_rows, 1.f / gscale);
+  flush_gradients<K0P, KCP, 2 * kGrpCols>(tbase, warp, lane, G, m, cta_tiles > 0, dparams, grad_rows, ginv);
   fence_before_sync();
   __syncthreads();
   if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2003] = clock64();
@@ -1539,10 +1501,11 @@ static inline bool narrow_shape(const hbr_mlp_dims* d) { return d->in0 <= 32 && 
 template <int K0P, int KCP, int G, bool ENC>
 static int launch_fwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                          const float* params, int in0, int dv, float* out, uint8_t* scratch, const EncArgs& enc,
-                         const HashGeom& geom, int feat16, cudaStream_t st) {
+                         const HashGeom& geom, int feat16, int image_ready, cudaStream_t st) {
   constexpr int smem = FwdSmem<K0P, KCP, G>::total;
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), G), sm_count());
-  if (scratch != nullptr) mlp_prep_kernel<K0P, KCP><<<kPrepCtas - 1, 256, 0, st>>>(params, in0, dv, scratch);
+  // the full image (incl. the fp32 biases only the backward reads): the backward call of the step can then skip its prep
+  if (scratch != nullptr && !image_ready) mlp_prep_kernel<K0P, KCP><<<kPrepCtas, 256, 0, st>>>(params, in0, dv, scratch);
   auto kern = mlp_fwd_tc_kernel<K0P, KCP, G, false, ENC>;
   HBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, G * kTile, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, scratch, nullptr, enc,
@@ -1555,15 +1518,15 @@ template <int K0P, int KCP, int G, bool ENC>
 static int launch_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                          const float* params, int in0, int dv, const float* out, const float* dout, float* dfeat,
                          int64_t dfeat_stride, float* ddirs, float* dparams, uint8_t* scratch, const EncArgs& enc,
-                         const HashGeom& geom, float gscale, int feat16, cudaStream_t st) {
+                         const HashGeom& geom, float gscale, int feat16, int image_ready, cudaStream_t st) {
   using SC = Scratch<K0P, KCP>;
   constexpr int smem = BwdSmem<K0P, KCP, G>::total;
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), G), sm_count());
   const bool rows = scratch != nullptr && dparams != nullptr && grid <= SC::kMaxRows;
-  if (scratch != nullptr) mlp_prep_kernel<K0P, KCP><<<kPrepCtas, 256, 0, st>>>(params, in0, dv, scratch);
+  if (scratch != nullptr && !image_ready) mlp_prep_kernel<K0P, KCP><<<kPrepCtas, 256, 0, st>>>(params, in0, dv, scratch);
   auto kern = mlp_bwd_tc_kernel<K0P, KCP, G, false, ENC>;
   HBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, G * kGrpThreads + 32, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, dout, dfeat,
+  kern<<<grid, G * kTile + 32, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, dout, dfeat,
                                            dfeat_stride, ddirs, dparams, scratch,
                                            rows ? reinterpret_cast<float*>(scratch + SC::off_grad) : nullptr, nullptr, enc, geom, gscale, feat16);
   if (rows) {

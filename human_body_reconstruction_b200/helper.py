@@ -35,8 +35,28 @@ def strat_sampler(tn, tf, num_samples: int, exp: Optional[bool] = False, device:
         t = torch.linspace(torch.log(tn), torch.log(tf), num_samples, device=device)
         t = t + (torch.rand_like(t) * (torch.log(tf) - torch.log(tn)) / num_samples)
         return torch.exp(t)
-    t = torch.linspace(tn, tf, num_samples, device=device)
-    return t + (torch.rand_like(t) * (tf - tn) / num_samples)
+    t = _linspace(tn, tf, num_samples, device)
+    u = torch.rand_like(t)                                                # RNG draw #1
+    if t.is_cuda and t.dtype == torch.float32 and not torch.is_tensor(num_samples):
+        span = tf - tn                                                    # CPU 0-dim tensors in the reference's callers
+        if not (torch.is_tensor(span) and span.is_cuda):
+            return ops.strat_depths(t, u, float(span), float(num_samples))   # same three roundings, one kernel
+    return t + (u * (tf - tn) / num_samples)
+
+
+_LIN = {}
+
+
+def _linspace(tn, tf, num_samples, device):
+    """torch.linspace(tn, tf, num_samples) -- a constant of the run for the reference's callers (near / far are fixed CPU
+    scalars): computed once per (tn, tf, S, device) and reused, never written to."""
+    if (torch.is_tensor(tn) and tn.is_cuda) or (torch.is_tensor(tf) and tf.is_cuda):
+        return torch.linspace(tn, tf, num_samples, device=device)
+    key = (float(tn), float(tf), int(num_samples), str(torch.device(device)), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+    lin = _LIN.get(key)
+    if lin is None:
+        lin = _LIN[key] = torch.linspace(tn, tf, num_samples, device=device)
+    return lin
 
 
 def hierarchical_sampling(rays_o, rays_d, z_vals, weights, n_samples: int, tn, tf, perturb: bool = False,

@@ -283,6 +283,45 @@ def hier_sample(w: torch.Tensor, t: torch.Tensor, u: torch.Tensor, cand: torch.T
     return tf
 
 
+def strat_depths(lin: torch.Tensor, u: torch.Tensor, span: float, count: float) -> torch.Tensor:
+    """helper.py:231-232: lin + (u * span) / count, each operation rounded on its own (one kernel instead of three)."""
+    require_cuda(lin, u)
+    lin, u = _f32c(lin), _f32c(u)
+    t = torch.empty_like(lin)
+    check(lib().hbr_strat_depths(ptr(lin), ptr(u), float(span), float(count), lin.numel(), ptr(t), stream()))
+    return t
+
+
+class MsePair(torch.autograd.Function):
+    """nn.MSELoss()(a, gt) [+ nn.MSELoss()(b, gt)] (train_hash2.py:177,221) as one kernel per direction."""
+
+    @staticmethod
+    def forward(ctx, a, b, gt):
+        require_cuda(a, b, gt)
+        a, gt = _f32c(a), _f32c(gt)
+        b = _f32c(b) if b is not None else None
+        if a.shape != gt.shape or (b is not None and b.shape != gt.shape):
+            raise ValueError("MsePair: shapes differ")
+        loss = torch.zeros((), device=a.device, dtype=torch.float32)
+        check(lib().hbr_mse_pair_fwd(ptr(a), ptr(b), ptr(gt), a.numel(), ptr(loss), stream()))
+        ctx.save_for_backward(a, b, gt)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b, gt = ctx.saved_tensors
+        da = torch.empty_like(a)
+        db = torch.empty_like(b) if b is not None else None
+        gout = _f32c(gout)
+        check(lib().hbr_mse_pair_bwd(ptr(a), ptr(b), ptr(gt), a.numel(), ptr(gout), ptr(da), ptr(db), stream()))
+        return da, db, None
+
+
+def mse_pair(a: torch.Tensor, b: Optional[torch.Tensor], gt: torch.Tensor) -> torch.Tensor:
+    """mse(a, gt) + mse(b, gt) (b may be None)."""
+    return MsePair.apply(a, b, gt)
+
+
 # ------------------------------------------------------------------------------------------------------
 # MLP (fp32 CUDA-core path)
 # ------------------------------------------------------------------------------------------------------
@@ -312,6 +351,7 @@ def mlp_bwd_f32(feat, dirs, dir_group, params, dims: MlpDims, dout, act, want_df
 
 
 _tc_scratch = {}
+_tc_image = {}          # id(scratch buffer) -> (params data_ptr, params version, operand): what the operand image was built from
 
 
 def mlp_tc_scratch(dims: MlpDims, device) -> torch.Tensor:
@@ -358,8 +398,12 @@ def mlp_fwd_tc(feat, dirs, dir_group, params, dims: MlpDims, keep_act: bool = Fa
     require_cuda(feat, dirs, params)
     n = feat.shape[0]
     out = torch.empty((n, 4), device=feat.device, dtype=torch.float32)
+    scratch = mlp_tc_scratch(dims, feat.device)
+    # the forward always rebuilds the operand image (4 us) and records what it was built from; the backward of the same
+    # parameters (same storage, same version counter, same operand format) skips its prep kernel
     check(lib().hbr_mlp_fwd_tc(ptr(feat), _feat_dtype(feat, operand), feat.stride(0), ptr(dirs), dir_group, n, ptr(params),
-                               C.byref(dims), operand, ptr(out), ptr(mlp_tc_scratch(dims, feat.device)), stream()))
+                               C.byref(dims), operand, ptr(out), ptr(scratch), 0, stream()))
+    _tc_image[id(scratch)] = (params.data_ptr(), params._version, operand, torch.cuda.current_stream().cuda_stream)
     return out, None
 
 
@@ -369,9 +413,16 @@ def mlp_bwd_tc(feat, dirs, dir_group, params, dims: MlpDims, out, dout, want_dfe
     n = feat.shape[0]
     dfeat = torch.empty((n, dims.in0), device=feat.device, dtype=torch.float32) if want_dfeat else None
     ddirs = torch.zeros_like(dirs) if want_ddirs else None
+    scratch = mlp_tc_scratch(dims, feat.device)
+    key = (params.data_ptr(), params._version, operand, torch.cuda.current_stream().cuda_stream)
+    ready = 1 if _tc_image.get(id(scratch)) == key else 0
     check(lib().hbr_mlp_bwd_tc(ptr(feat), _feat_dtype(feat, operand), feat.stride(0), ptr(dirs), dir_group, n, ptr(params),
                                C.byref(dims), operand, ptr(out), ptr(dout), ptr(dfeat), dims.in0, ptr(ddirs), ptr(dparams),
-                               float(grad_scale), ptr(mlp_tc_scratch(dims, feat.device)), stream()))
+                               float(grad_scale), ptr(scratch), ready, stream()))
+    if ready:
+        _lib.STATS.launches -= 1              # no prep kernel in this call
+    else:
+        _tc_image[id(scratch)] = key
     return dfeat, ddirs
 
 

@@ -382,3 +382,37 @@ def test_no_cpu_fallback():
         enc(torch.zeros(4, 3))
     with pytest.raises(RuntimeError):
         h.helper.calc_color(torch.zeros(4), torch.zeros(2, 4, 3), torch.zeros(2, 4), 1.0)
+
+
+def test_strat_sampler_matches_reference_expression_bit_for_bit():
+    """helper.strat_sampler (cached linspace + one fused kernel) == the reference's torch expression (helper.py:231-232) on
+    the same RNG stream, bit for bit, and consumes the generator identically."""
+    h = hbr()
+    near, far = torch.tensor(2.0), torch.tensor(6.0)
+    for S in (1, 7, 64, 128, 256, 1000):
+        torch.manual_seed(11 + S)
+        t = h.helper.strat_sampler(near, far, S, device=DEV)
+        after = torch.rand(3, device=DEV)
+        torch.manual_seed(11 + S)
+        lin = torch.linspace(near, far, S, device=DEV)
+        ref = lin + (torch.rand_like(lin) * (far - near) / S)
+        assert torch.equal(t, ref) and torch.equal(after, torch.rand(3, device=DEV))
+    t2 = h.helper.strat_sampler(near, far, 128, device=DEV)
+    assert not torch.equal(t2, h.helper.strat_sampler(near, far, 128, device=DEV))     # the cached linspace is never written to
+
+
+@pytest.mark.parametrize("R,pair", [(1, True), (64, True), (4096, False), (4096, True), (100000, True)])
+def test_mse_pair_matches_torch(R, pair):
+    from human_body_reconstruction_b200 import ops
+    torch.manual_seed(R)
+    a, b, gt = (torch.rand(R, 3, device=DEV) for _ in range(3))
+    a.requires_grad_(); b.requires_grad_()
+    loss = ops.mse_pair(a, b if pair else None, gt)
+    (3.0 * loss).backward()
+    a2, b2 = a.detach().clone().requires_grad_(), b.detach().clone().requires_grad_()
+    ref = torch.nn.functional.mse_loss(a2, gt) + (torch.nn.functional.mse_loss(b2, gt) if pair else 0.0)
+    (3.0 * ref).backward()
+    assert abs(float(loss) - float(ref)) <= 1e-6 * float(ref)
+    assert torch.allclose(a.grad, a2.grad, rtol=1e-6, atol=1e-12)
+    if pair:
+        assert torch.allclose(b.grad, b2.grad, rtol=1e-6, atol=1e-12)
