@@ -68,8 +68,9 @@ extern "C" int hbr_mlp_fwd_tc(const void* feat_, int feat_dtype, int64_t feat_st
 extern "C" int hbr_mlp_bwd_tc(const void* feat_, int feat_dtype, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                               const float* params, const hbr_mlp_dims* dims, int operand, const float* out,
                               const float* dout, float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams,
-                              float grad_scale, void* scratch, int image_ready, void* stream) {
+                              float grad_scale, void* scratch, int image_ready, int defer_reduce, void* stream) {
   if (int rc = check_dims(dims)) return rc;
+  HBR_REQUIRE(!defer_reduce || (scratch != nullptr && dparams != nullptr), "defer_reduce needs scratch and dparams");
   if (int rc = check_operand(operand, grad_scale)) return rc;
   if (n == 0) return HBR_OK;
   const float* feat = static_cast<const float*>(feat_);
@@ -85,10 +86,30 @@ extern "C" int hbr_mlp_bwd_tc(const void* feat_, int feat_dtype, int64_t feat_st
   if (narrow_shape(dims))
     return HBR_BY_OPERAND(launch_bwd_tc<32, 48, 2, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view,
                                                           out, dout, dfeat, dfeat_stride, ddirs, dparams, sc, EncArgs{}, HashGeom{},
-                                                          grad_scale, f16, image_ready, st));
+                                                          grad_scale, f16, image_ready, defer_reduce, st));
   return HBR_BY_OPERAND(launch_bwd_tc<64, 64, 1, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out,
                                                         dout, dfeat, dfeat_stride, ddirs, dparams, sc, EncArgs{}, HashGeom{}, grad_scale,
-                                                        f16, image_ready, st));
+                                                        f16, image_ready, defer_reduce, st));
+}
+
+extern "C" int hbr_mlp_tc_prepare(const float* params, const hbr_mlp_dims* dims, int operand, void* scratch, void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (int rc = check_operand(operand, 1.f)) return rc;
+  HBR_REQUIRE(params && scratch && (uintptr_t)scratch % 256 == 0, "NULL / misaligned pointer");
+  uint8_t* sc = static_cast<uint8_t*>(scratch);
+  cudaStream_t st = as_stream(stream);
+  if (narrow_shape(dims)) return HBR_BY_OPERAND(prepare_tc<32, 48>(params, dims->in0, dims->d_view, sc, st));
+  return HBR_BY_OPERAND(prepare_tc<64, 64>(params, dims->in0, dims->d_view, sc, st));
+}
+
+extern "C" int hbr_mlp_tc_reduce_grads(const hbr_mlp_dims* dims, int64_t n, void* scratch, float* dparams, void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (n == 0) return HBR_OK;
+  HBR_REQUIRE(scratch && dparams, "NULL pointer");
+  uint8_t* sc = static_cast<uint8_t*>(scratch);
+  cudaStream_t st = as_stream(stream);
+  if (narrow_shape(dims)) return bf16::reduce_grads_tc<32, 48, 2>(n, dims->in0, dims->d_view, sc, dparams, st);
+  return bf16::reduce_grads_tc<64, 64, 1>(n, dims->in0, dims->d_view, sc, dparams, st);
 }
 
 // ---- fused field evaluation: hash-grid encoder + MLP_3D in one kernel per direction ------------------------------
@@ -140,11 +161,11 @@ extern "C" int hbr_field_bwd_tc(const float* x, int64_t n, const hbr_hash_geom* 
     e.x = x; e.dtable = dtable; e.feat16 = f16p;
     return f16::launch_bwd_tc<32, 48, 2, true>(nullptr, 32, dirs, dir_group, n, params, 32, dims->d_view, out, dout, nullptr, 32,
                                                ddirs, dparams, static_cast<uint8_t*>(scratch), e, to_device_geom(*geom),
-                                               grad_scale, 0, 0, as_stream(stream));
+                                               grad_scale, 0, 0, 0, as_stream(stream));
   }
   EncArgs e{};
   e.x = x; e.dtable = dtable; e.feat16 = f16p;
   return bf16::launch_bwd_tc<32, 48, 2, true>(nullptr, 32, dirs, dir_group, n, params, 32, dims->d_view, out, dout, nullptr, 32,
                                               ddirs, dparams, static_cast<uint8_t*>(scratch), e, to_device_geom(*geom),
-                                              grad_scale, 0, 0, as_stream(stream));
+                                              grad_scale, 0, 0, 0, as_stream(stream));
 }

@@ -1518,7 +1518,7 @@ template <int K0P, int KCP, int G, bool ENC>
 static int launch_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                          const float* params, int in0, int dv, const float* out, const float* dout, float* dfeat,
                          int64_t dfeat_stride, float* ddirs, float* dparams, uint8_t* scratch, const EncArgs& enc,
-                         const HashGeom& geom, float gscale, int feat16, int image_ready, cudaStream_t st) {
+                         const HashGeom& geom, float gscale, int feat16, int image_ready, int defer_reduce, cudaStream_t st) {
   using SC = Scratch<K0P, KCP>;
   constexpr int smem = BwdSmem<K0P, KCP, G>::total;
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), G), sm_count());
@@ -1529,11 +1529,30 @@ static int launch_bwd_tc(const float* feat, int64_t feat_stride, const float* di
   kern<<<grid, G * kTile + 32, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, dout, dfeat,
                                            dfeat_stride, ddirs, dparams, scratch,
                                            rows ? reinterpret_cast<float*>(scratch + SC::off_grad) : nullptr, nullptr, enc, geom, gscale, feat16);
-  if (rows) {
+  if (rows && !defer_reduce) {
     const int total = make_layout(in0, dv).total;
     mlp_grad_reduce_kernel<<<dim3((total + 255) / 256, kReduceSlices), 256, 0, st>>>(
         reinterpret_cast<const float*>(scratch + SC::off_grad), grid, SC::kRowFloats, total, dparams);
   }
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
+
+// grid size / row use of launch_bwd_tc for n points (the deferred reduce must see the same numbers)
+template <int K0P, int KCP, int G>
+static int reduce_grads_tc(int64_t n, int in0, int dv, uint8_t* scratch, float* dparams, cudaStream_t st) {
+  using SC = Scratch<K0P, KCP>;
+  const int grid = (int)min64(ceil_div(ceil_div(n, kTile), G), sm_count());
+  HBR_REQUIRE(grid <= SC::kMaxRows, "grid %d exceeds the gradient rows", grid);
+  const int total = make_layout(in0, dv).total;
+  mlp_grad_reduce_kernel<<<dim3((total + 255) / 256, kReduceSlices), 256, 0, st>>>(
+      reinterpret_cast<const float*>(scratch + SC::off_grad), grid, SC::kRowFloats, total, dparams);
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
+template <int K0P, int KCP>
+static int prepare_tc(const float* params, int in0, int dv, uint8_t* scratch, cudaStream_t st) {
+  mlp_prep_kernel<K0P, KCP><<<kPrepCtas, 256, 0, st>>>(params, in0, dv, scratch);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }

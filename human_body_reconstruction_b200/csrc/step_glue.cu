@@ -18,16 +18,18 @@ __global__ void strat_depths_kernel(const float* __restrict__ lin, const float* 
 __global__ void __launch_bounds__(256)
 mse_pair_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gt, long long n,
                     double inv_n, float* __restrict__ loss) {
-  double acc = 0.0;
+  // a thread sums at most a few dozen squares in fp32 (few-ulp error), everything above that in double
+  float facc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float g = __ldg(gt + i);
     const float da = __ldg(a + i) - g;
-    acc += (double)da * da;
+    facc = fmaf(da, da, facc);
     if (b != nullptr) {
       const float db = __ldg(b + i) - g;
-      acc += (double)db * db;
+      facc = fmaf(db, db, facc);
     }
   }
+  double acc = (double)facc;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
   __shared__ double part[8];
@@ -64,18 +66,19 @@ extern "C" int hbr_strat_depths(const float* lin, const float* u, float span, fl
   return HBR_OK;
 }
 
-extern "C" int hbr_mse_pair_fwd(const float* a, const float* b, const float* gt, int64_t n, float* loss, void* stream) {
+extern "C" int hbr_mse_pair_fwd(const float* a, const float* b, const float* gt, int64_t n, float scale, float* loss,
+                                void* stream) {
   HBR_REQUIRE(n >= 1 && a && gt && loss, "bad argument");
-  const int grid = (int)min64(ceil_div(n, 256 * 8), sm_count());
-  mse_pair_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(a, b, gt, n, 1.0 / (double)n, loss);
+  const int grid = (int)min64(ceil_div(n, 256 * 4), (long long)sm_count() * 4);
+  mse_pair_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(a, b, gt, n, (double)scale / (double)n, loss);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
 
-extern "C" int hbr_mse_pair_bwd(const float* a, const float* b, const float* gt, int64_t n, const float* gout, float* da,
-                                float* db, void* stream) {
+extern "C" int hbr_mse_pair_bwd(const float* a, const float* b, const float* gt, int64_t n, float scale, const float* gout,
+                                float* da, float* db, void* stream) {
   HBR_REQUIRE(n >= 1 && a && gt && gout && da && (b == nullptr || db != nullptr), "bad argument");
-  mse_pair_bwd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(a, b, gt, n, 2.f / (float)n, gout, da, db);
+  mse_pair_bwd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(a, b, gt, n, 2.f * scale / (float)n, gout, da, db);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }

@@ -26,7 +26,7 @@ def default_loss(Cr, Cf, gt):
     from . import ops
     if Cr.is_cuda and Cr.dtype == torch.float32 and gt.dtype == torch.float32 and Cr.shape == gt.shape:
         # one kernel per direction (ops.MsePair) instead of ~10 elementwise / reduce launches
-        return 2.0 * ops.mse_pair(Cr, None, gt) if Cf is Cr else ops.mse_pair(Cr, Cf, gt)
+        return ops.mse_pair(Cr, None, gt, 2.0) if Cf is Cr else ops.mse_pair(Cr, Cf, gt)
     if Cf is Cr:
         return 2.0 * torch.nn.functional.mse_loss(Cr, gt)
     return torch.nn.functional.mse_loss(Cr, gt) + torch.nn.functional.mse_loss(Cf, gt)

@@ -296,15 +296,16 @@ class MsePair(torch.autograd.Function):
     """nn.MSELoss()(a, gt) [+ nn.MSELoss()(b, gt)] (train_hash2.py:177,221) as one kernel per direction."""
 
     @staticmethod
-    def forward(ctx, a, b, gt):
+    def forward(ctx, a, b, gt, scale=1.0):
         require_cuda(a, b, gt)
         a, gt = _f32c(a), _f32c(gt)
         b = _f32c(b) if b is not None else None
         if a.shape != gt.shape or (b is not None and b.shape != gt.shape):
             raise ValueError("MsePair: shapes differ")
         loss = torch.zeros((), device=a.device, dtype=torch.float32)
-        check(lib().hbr_mse_pair_fwd(ptr(a), ptr(b), ptr(gt), a.numel(), ptr(loss), stream()))
+        check(lib().hbr_mse_pair_fwd(ptr(a), ptr(b), ptr(gt), a.numel(), float(scale), ptr(loss), stream()))
         ctx.save_for_backward(a, b, gt)
+        ctx.scale = float(scale)
         return loss
 
     @staticmethod
@@ -313,13 +314,13 @@ class MsePair(torch.autograd.Function):
         da = torch.empty_like(a)
         db = torch.empty_like(b) if b is not None else None
         gout = _f32c(gout)
-        check(lib().hbr_mse_pair_bwd(ptr(a), ptr(b), ptr(gt), a.numel(), ptr(gout), ptr(da), ptr(db), stream()))
-        return da, db, None
+        check(lib().hbr_mse_pair_bwd(ptr(a), ptr(b), ptr(gt), a.numel(), ctx.scale, ptr(gout), ptr(da), ptr(db), stream()))
+        return da, db, None, None
 
 
-def mse_pair(a: torch.Tensor, b: Optional[torch.Tensor], gt: torch.Tensor) -> torch.Tensor:
-    """mse(a, gt) + mse(b, gt) (b may be None)."""
-    return MsePair.apply(a, b, gt)
+def mse_pair(a: torch.Tensor, b: Optional[torch.Tensor], gt: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """scale * (mse(a, gt) + mse(b, gt)) (b may be None)."""
+    return MsePair.apply(a, b, gt, scale)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -393,36 +394,58 @@ def _feat_dtype(feat: torch.Tensor, operand: int) -> int:
     raise TypeError(f"features are {feat.dtype}; the MLP kernels take float32 or their own operand format")
 
 
-def mlp_fwd_tc(feat, dirs, dir_group, params, dims: MlpDims, keep_act: bool = False, operand: int = HBR_BF16):
+def _image_key(params, operand):
+    return (params.data_ptr(), params._version, operand)
+
+
+def mlp_tc_prepare(params, dims: MlpDims, operand: int):
+    """Build the operand image of `params` on the CURRENT stream (callers put it beside the hash-grid kernel on a side stream
+    and join before the MLP kernel); the following mlp_fwd_tc(image_ready=True) / mlp_bwd_tc calls reuse it."""
+    scratch = mlp_tc_scratch(dims, params.device)
+    check(lib().hbr_mlp_tc_prepare(ptr(params), C.byref(dims), operand, ptr(scratch), stream()))
+    _tc_image[id(scratch)] = _image_key(params, operand)
+
+
+def mlp_fwd_tc(feat, dirs, dir_group, params, dims: MlpDims, keep_act: bool = False, operand: int = HBR_BF16,
+               image_ready: bool = False):
     """16-bit tensor-core forward; keeps nothing (the backward recomputes), returns (out, None)."""
     require_cuda(feat, dirs, params)
     n = feat.shape[0]
     out = torch.empty((n, 4), device=feat.device, dtype=torch.float32)
     scratch = mlp_tc_scratch(dims, feat.device)
-    # the forward always rebuilds the operand image (4 us) and records what it was built from; the backward of the same
-    # parameters (same storage, same version counter, same operand format) skips its prep kernel
+    # unless the caller has just prepared it (mlp_tc_prepare), the forward rebuilds the operand image (4 us) and records
+    # what it was built from; the backward of the same parameters (same storage, same version counter, same operand
+    # format) skips its prep kernel
+    ready = 1 if (image_ready and _tc_image.get(id(scratch)) == _image_key(params, operand)) else 0
     check(lib().hbr_mlp_fwd_tc(ptr(feat), _feat_dtype(feat, operand), feat.stride(0), ptr(dirs), dir_group, n, ptr(params),
-                               C.byref(dims), operand, ptr(out), ptr(scratch), 0, stream()))
-    _tc_image[id(scratch)] = (params.data_ptr(), params._version, operand, torch.cuda.current_stream().cuda_stream)
+                               C.byref(dims), operand, ptr(out), ptr(scratch), ready, stream()))
+    if ready:
+        _lib.STATS.launches -= 1
+    _tc_image[id(scratch)] = _image_key(params, operand)
     return out, None
 
 
+def mlp_tc_reduce_grads(dims: MlpDims, n: int, dparams, device):
+    """Second half of mlp_bwd_tc(defer_reduce=True): per-CTA gradient rows -> dparams (accumulating), on the current stream."""
+    check(lib().hbr_mlp_tc_reduce_grads(C.byref(dims), int(n), ptr(mlp_tc_scratch(dims, device)), ptr(dparams), stream()))
+
+
 def mlp_bwd_tc(feat, dirs, dir_group, params, dims: MlpDims, out, dout, want_dfeat, want_ddirs, dparams,
-               operand: int = HBR_BF16, grad_scale: float = 1.0):
-    """`out` is the forward output (N,4): the kernel takes ELU' / LeakyReLU' from it instead of recomputing the last layer."""
+               operand: int = HBR_BF16, grad_scale: float = 1.0, defer_reduce: bool = False):
+    """`out` is the forward output (N,4): the kernel takes ELU' / LeakyReLU' from it instead of recomputing the last layer.
+    defer_reduce: leave the per-CTA gradient rows in the scratch; the caller runs mlp_tc_reduce_grads (on any stream that
+    waits for this one) before anything else uses the scratch or reads dparams."""
     n = feat.shape[0]
     dfeat = torch.empty((n, dims.in0), device=feat.device, dtype=torch.float32) if want_dfeat else None
     ddirs = torch.zeros_like(dirs) if want_ddirs else None
     scratch = mlp_tc_scratch(dims, feat.device)
-    key = (params.data_ptr(), params._version, operand, torch.cuda.current_stream().cuda_stream)
+    key = _image_key(params, operand)
     ready = 1 if _tc_image.get(id(scratch)) == key else 0
     check(lib().hbr_mlp_bwd_tc(ptr(feat), _feat_dtype(feat, operand), feat.stride(0), ptr(dirs), dir_group, n, ptr(params),
                                C.byref(dims), operand, ptr(out), ptr(dout), ptr(dfeat), dims.in0, ptr(ddirs), ptr(dparams),
-                               float(grad_scale), ptr(scratch), ready, stream()))
-    if ready:
-        _lib.STATS.launches -= 1              # no prep kernel in this call
-    else:
-        _tc_image[id(scratch)] = key
+                               float(grad_scale), ptr(scratch), ready, 1 if defer_reduce else 0, stream()))
+    _lib.STATS.launches -= ready + (1 if defer_reduce else 0)    # no prep kernel / no reduce kernel in this call
+    _tc_image[id(scratch)] = key
     return dfeat, ddirs
 
 

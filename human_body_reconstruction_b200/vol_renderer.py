@@ -79,8 +79,16 @@ class _FieldRaysFn(torch.autograd.Function):
         geom, dims = enc._geom(), mlp._dims()
         operand = ops.tc_operand()
         S = t.shape[-1]
+        # the MLP's operand image is built on a side stream, beside the hash-grid kernel (in a captured step: a parallel
+        # branch of the graph)
+        cur, side = torch.cuda.current_stream(), _side_stream(rays_o.device)
+        flat = mlp._flat_params()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            ops.mlp_tc_prepare(flat, dims, operand)
         feat16 = ops.hash_encode_fwd_rays(rays_o, rays_d, t, enc._flat_table(), geom, operand)
-        out, _ = ops.mlp_fwd_tc(feat16, dirs, S, mlp._flat_params(), dims, operand=operand)
+        cur.wait_stream(side)
+        out, _ = ops.mlp_fwd_tc(feat16, dirs, S, flat, dims, operand=operand, image_ready=True)
         ctx.enc, ctx.mlp, ctx.geom, ctx.dims, ctx.S, ctx.operand = enc, mlp, geom, dims, S, operand
         ctx.save_for_backward(rays_o, rays_d, t, dirs, feat16, out)
         ctx.want_tab = any(ctx.needs_input_grad[6:6 + enc.L])
@@ -106,12 +114,27 @@ class _FieldRaysFn(torch.autograd.Function):
             dflat, last_m = dpm.enter_backward(mlp)
         else:
             dflat, last_m = torch.zeros_like(flat), False
+        # the reduction of the MLP kernel's per-CTA gradient rows runs on a side stream, beside the hash-grid backward
+        defer = ctx.want_tab
         dfeat, ddirs = ops.mlp_bwd_tc(feat16, dirs, ctx.S, flat, ctx.dims, out.detach(), dout.float().contiguous(), ctx.want_tab,
-                                      ctx.needs_input_grad[3], dflat, operand=ctx.operand, grad_scale=mlp.tc_grad_scale)
-        if dpm is not None and last_m:
-            dpm.publish(mlp, dflat)
+                                      ctx.needs_input_grad[3], dflat, operand=ctx.operand, grad_scale=mlp.tc_grad_scale,
+                                      defer_reduce=defer)
+        cur, side = torch.cuda.current_stream(), _side_stream(dout.device)
+        if defer:
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                ops.mlp_tc_reduce_grads(ctx.dims, feat16.shape[0], dflat, dout.device)
+            dflat.record_stream(side)
+
+        def join_mlp():
+            if defer:
+                cur.wait_stream(side)
+            if dpm is not None and last_m:
+                dpm.publish(mlp, dflat)
+
         gm = (None,) * len(mlp._ordered()) if (dpm is not None or not ctx.want_mlp) else tuple(mlp._grad_views(dflat))
         if not ctx.want_tab:
+            join_mlp()
             return (None, None, None, ddirs, None, None) + (None,) * L + gm
         dpe = enc._dp
         if dpe is not None:
@@ -121,6 +144,8 @@ class _FieldRaysFn(torch.autograd.Function):
             for l0 in range(0, L, step):
                 l1 = min(L, l0 + step)
                 ops.hash_encode_bwd_rays(rays_o, rays_d, t, dfeat, ctx.geom, g, l0, l1)
+                if l0 == 0:
+                    join_mlp()                      # the MLP gradient is complete (and published) behind the first chunk
                 if last:
                     dpe.publish(enc, g[l0:l1])
             return (None, None, None, ddirs, None, None) + (None,) * L + gm
@@ -131,7 +156,21 @@ class _FieldRaysFn(torch.autograd.Function):
         else:
             g = torch.zeros((L, T, F), device=dout.device, dtype=torch.float32)
         ops.hash_encode_bwd_rays(rays_o, rays_d, t, dfeat, ctx.geom, g, 0, L)
+        join_mlp()
         return (None, None, None, ddirs, None, None) + tuple(g[i] for i in range(L)) + gm
+
+
+_SIDE = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    """One side stream per device for the small kernels that can run beside the hash-grid kernels."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    s = _SIDE.get(idx)
+    if s is None:
+        s = _SIDE[idx] = torch.cuda.Stream(device=idx)
+    return s
 
 
 def _unwrap(model):

@@ -130,6 +130,12 @@ int hbr_mlp_bwd_f32(const float* feat, int64_t feat_stride, const float* dirs, i
  * small prep kernel builds the 16-bit operand image once per call and the backward sums per-CTA gradient rows with a
  * reduce kernel; without it every CTA converts the parameters itself and flushes its gradients with atomics. */
 int64_t hbr_mlp_tc_scratch_bytes(const hbr_mlp_dims* dims);
+/* Builds the operand image of `params` in `scratch` (what hbr_mlp_fwd_tc / _bwd_tc do themselves unless image_ready): lets a
+ * caller run it on another stream, beside the hash-grid kernel of the step. */
+int hbr_mlp_tc_prepare(const float* params, const hbr_mlp_dims* dims, int operand, void* scratch, void* stream);
+/* Sums the per-CTA gradient rows a hbr_mlp_bwd_tc call with defer_reduce != 0 left in `scratch` into dparams (accumulating):
+ * the second half of that call, for callers that want it on another stream beside the hash-grid backward. */
+int hbr_mlp_tc_reduce_grads(const hbr_mlp_dims* dims, int64_t n, void* scratch, float* dparams, void* stream);
 /* image_ready != 0: the operand image in `scratch` was built by an earlier call for these very parameters and operand
  * format (the forward call of the same step): skip the prep kernel. */
 /* feat_dtype: HBR_F32 (n, feat_stride) fp32 features, or the operand format itself -- features already rounded to it by
@@ -141,7 +147,7 @@ int hbr_mlp_fwd_tc(const void* feat, int feat_dtype, int64_t feat_stride, const 
 int hbr_mlp_bwd_tc(const void* feat, int feat_dtype, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                    const float* params, const hbr_mlp_dims* dims, int operand, const float* out, const float* dout,
                    float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams, float grad_scale, void* scratch,
-                   int image_ready, void* stream);
+                   int image_ready, int defer_reduce, void* stream);
 /* ---- a2 + a7 fused (the training step's field evaluation under autocast): hash-grid encoder + MLP_3D in ONE kernel per
  * direction -- HashEncoder.forward (hash_encoding.py:146-170) feeding MLP_3D.forward (test_hash.py:52-72) as
  * vol_renderer.py:179,211 chains them.  Covers the reference's configuration family F = 2, L = 16, E = 0, power-of-two T,
@@ -160,12 +166,13 @@ int hbr_field_bwd_tc(const float* x, int64_t n, const hbr_hash_geom* geom_host, 
  * and u = torch.rand_like(lin) are produced by the caller (same RNG stream, Q9). */
 int hbr_strat_depths(const float* lin, const float* u, float span, float count, int64_t S, float* t, void* stream);
 
-/* The loss of train_hash2.py:177,221 -- nn.MSELoss (mean) of a against gt, plus that of b when b != NULL -- as one kernel
- * per direction.  loss (1 float) must be zero on entry and is accumulated into; gout is the scalar upstream gradient on
- * the device; da / db receive gout * 2 (x - gt) / n.  n = number of elements of each tensor. */
-int hbr_mse_pair_fwd(const float* a, const float* b, const float* gt, int64_t n, float* loss, void* stream);
-int hbr_mse_pair_bwd(const float* a, const float* b, const float* gt, int64_t n, const float* gout, float* da, float* db,
-                     void* stream);
+/* The loss of train_hash2.py:177,221 -- scale * (nn.MSELoss (mean) of a against gt, plus that of b when b != NULL) -- as one
+ * kernel per direction (scale = 2 with b == NULL serves the non-hierarchical step, where the trainer adds the same MSE
+ * twice).  loss (1 float) must be zero on entry and is accumulated into; gout is the scalar upstream gradient on the
+ * device; da / db receive gout * scale * 2 (x - gt) / n.  n = number of elements of each tensor. */
+int hbr_mse_pair_fwd(const float* a, const float* b, const float* gt, int64_t n, float scale, float* loss, void* stream);
+int hbr_mse_pair_bwd(const float* a, const float* b, const float* gt, int64_t n, float scale, const float* gout, float* da,
+                     float* db, void* stream);
 
 /* ---- a9: sample positions, vol_renderer.py:165 / helper.py:48 -------------------------------------
  * pts[r,s,:] = o[r,:] + d[r,:]*t  (separate multiply and add).  t is (S) shared (t_ray_stride = 0)
