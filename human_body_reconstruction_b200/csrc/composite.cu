@@ -72,15 +72,20 @@ struct SampleIn {
   bool keep;                 // sigma >= -10 (gradient passes)
 };
 
+// row: where sample gs lives in the rgb / sigma tensors (gs itself, or its compacted row; < 0 = skipped sample)
+__device__ __forceinline__ long long sample_row(const int32_t* __restrict__ rowmap, long long gs, int s, int S) {
+  return rowmap == nullptr ? gs : (s < S ? (long long)__ldg(rowmap + gs) : -1);
+}
+
 __device__ __forceinline__ SampleIn load_sample(const float* __restrict__ tr, const float* __restrict__ sigma,
                                                 long long sig_st, const uint8_t* __restrict__ mask, long long gs,
-                                                int s, int S, float dnr, bool& live) {
+                                                int s, int S, float dnr, bool& live, long long row) {
   SampleIn q;
-  live = s < S && (mask == nullptr || mask[gs]);
+  live = s < S && row >= 0 && (mask == nullptr || mask[gs]);
   float delta = 0.f;
   if (s + 1 < S) delta = __fsub_rn(__ldg(tr + s + 1), __ldg(tr + s));   // helper.py:67, last delta stays 0
   q.delta = __fmul_rn(delta, dnr);                                       // :71
-  const float raw = live ? __ldg(sigma + gs * sig_st) : 0.f;
+  const float raw = live ? __ldg(sigma + row * sig_st) : 0.f;
   q.keep = !(raw < -10.f);
   q.sig = q.keep ? raw : -10.f;                                          // :76
   q.p = s < S ? __fmul_rn(q.sig, q.delta) : 0.f;                         // :77
@@ -90,7 +95,13 @@ __device__ __forceinline__ SampleIn load_sample(const float* __restrict__ tr, co
 __global__ void __launch_bounds__(kRaysPerCta * 32)
 composite_fwd_kernel(const float* __restrict__ t, long long t_rs, const float* __restrict__ rgb, long long rgb_st,
                      const float* __restrict__ sigma, long long sig_st, const float* __restrict__ dn, float dn_scalar,
-                     const uint8_t* __restrict__ mask, long long R, int S, float* __restrict__ C, float* __restrict__ w_out) {
+                     const uint8_t* __restrict__ mask, const int32_t* __restrict__ rowmap, long long R, int S,
+                     float* __restrict__ C, float* __restrict__ w_out, float ert_tau) {
+  // ert_tau: early ray termination (opt-in; +inf = off, the reference's behaviour).  Once the optical depth accumulated
+  // over whole 32-sample chunks exceeds ert_tau the remaining chunks are skipped and get weight 0.  With the default
+  // threshold 104 the transmittance exp(-depth) of every skipped sample is EXACTLY 0 in fp32 (exp(-104) underflows), so
+  // the result is bit-identical as long as the depth does not fall back below the threshold -- always when sigma >= 0;
+  // MLP_3D's LeakyReLU density can be slightly negative, which is why this is not on by default.
   const int lane = threadIdx.x & 31;
   const long long ray = (long long)blockIdx.x * kRaysPerCta + (threadIdx.x >> 5);
   if (ray >= R) return;
@@ -101,7 +112,8 @@ composite_fwd_kernel(const float* __restrict__ t, long long t_rs, const float* _
     const int s = s0 + lane;
     const long long gs = ray * S + s;
     bool live;
-    const SampleIn q = load_sample(tr, sigma, sig_st, mask, gs, s, S, dnr, live);
+    const long long row = sample_row(rowmap, gs, s, S);
+    const SampleIn q = load_sample(tr, sigma, sig_st, mask, gs, s, S, dnr, live, row);
     const float incl = carry + warp_incl_scan(q.p, lane);               // cumsum(prod), helper.py:93
     float prev = __shfl_up_sync(kFull, incl, 1);
     if (lane == 0) prev = carry;
@@ -111,13 +123,18 @@ composite_fwd_kernel(const float* __restrict__ t, long long t_rs, const float* _
     if (s < S) {
       if (w_out) w_out[gs] = w;
       if (live) {
-        const float* c = rgb + gs * rgb_st;
+        const float* c = rgb + row * rgb_st;
         c0 += w * __ldg(c + 0);
         c1 += w * __ldg(c + 1);
         c2 += w * __ldg(c + 2);
       }
     }
     carry = __shfl_sync(kFull, incl, 31);
+    if (carry > ert_tau) {                                               // warp-uniform
+      if (w_out)
+        for (int s2 = s0 + 32 + lane; s2 < S; s2 += 32) w_out[ray * S + s2] = 0.f;
+      break;
+    }
   }
   c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
   if (lane == 0) { C[ray * 3 + 0] = c0; C[ray * 3 + 1] = c1; C[ray * 3 + 2] = c2; }
@@ -128,8 +145,9 @@ template <int NCH>
 __global__ void __launch_bounds__(kRaysPerCta * 32)
 composite_bwd_kernel(const float* __restrict__ t, long long t_rs, const float* __restrict__ rgb, long long rgb_st,
                      const float* __restrict__ sigma, long long sig_st, const float* __restrict__ dn, float dn_scalar,
-                     const uint8_t* __restrict__ mask, long long R, int S, const float* __restrict__ gC,
-                     float* __restrict__ drgb, long long drgb_st, float* __restrict__ dsig, long long dsig_st) {
+                     const uint8_t* __restrict__ mask, const int32_t* __restrict__ rowmap, long long R, int S,
+                     const float* __restrict__ gC, float* __restrict__ drgb, long long drgb_st, float* __restrict__ dsig,
+                     long long dsig_st, float ert_tau) {
   const int lane = threadIdx.x & 31;
   const long long ray = (long long)blockIdx.x * kRaysPerCta + (threadIdx.x >> 5);
   if (ray >= R) return;
@@ -140,14 +158,16 @@ composite_bwd_kernel(const float* __restrict__ t, long long t_rs, const float* _
 
   float Tk[NCH], ek[NCH], ck[NCH], dk[NCH];     // transmittance, exp(-p), g.rgb, delta*[keep]
   float carry = 0.f;
+  bool done = false;                             // early ray termination: the forward skipped the chunks from here on
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     const int s = i * 32 + lane;
     Tk[i] = 0.f; ek[i] = 1.f; ck[i] = 0.f; dk[i] = 0.f;
-    if (i * 32 < S) {
+    if (i * 32 < S && !done) {
       const long long gs = ray * S + s;
       bool live;
-      const SampleIn q = load_sample(tr, sigma, sig_st, mask, gs, s, S, dnr, live);
+      const long long row = sample_row(rowmap, gs, s, S);
+      const SampleIn q = load_sample(tr, sigma, sig_st, mask, gs, s, S, dnr, live, row);
       const float incl = carry + warp_incl_scan(q.p, lane);
       float prev = __shfl_up_sync(kFull, incl, 1);
       if (lane == 0) prev = carry;
@@ -156,11 +176,12 @@ composite_bwd_kernel(const float* __restrict__ t, long long t_rs, const float* _
         Tk[i] = s == 0 ? 1.f : expf(-prev);
         ek[i] = expf(-q.p);
         if (live) {
-          const float* c = rgb + gs * rgb_st;
+          const float* c = rgb + row * rgb_st;
           ck[i] = g0 * __ldg(c + 0) + g1 * __ldg(c + 1) + g2 * __ldg(c + 2);
           dk[i] = q.keep ? q.delta : 0.f;
         }
       }
+      done = carry > ert_tau;                    // warp-uniform; skipped chunks keep T = 0: zero weights, zero gradients
     }
   }
   float rcarry = 0.f;                            // sum of w*c over all later chunks
@@ -177,16 +198,19 @@ composite_bwd_kernel(const float* __restrict__ t, long long t_rs, const float* _
       const float suffix = rcarry + after;       // sum_{j>k} w_j c_j
       rcarry += __shfl_sync(kFull, rin, 0);
       if (s < S) {
-        const bool live = mask == nullptr || mask[gs];
+        const long long row = sample_row(rowmap, gs, s, S);
+        const bool live = row >= 0 && (mask == nullptr || mask[gs]);
         const float dp = Tk[i] * ek[i] * ck[i] - suffix;
         const float ds = live ? dk[i] * dp : 0.f;
         const float r0 = live ? w * g0 : 0.f, r1 = live ? w * g1 : 0.f, r2 = live ? w * g2 : 0.f;
-        if (packed) {
-          *reinterpret_cast<float4*>(drgb + gs * 4) = make_float4(r0, r1, r2, ds);
-        } else {
-          float* o = drgb + gs * drgb_st;
-          o[0] = r0; o[1] = r1; o[2] = r2;
-          dsig[gs * dsig_st] = ds;
+        if (row >= 0) {                          // skipped samples of a compacted list have no gradient row
+          if (packed) {
+            *reinterpret_cast<float4*>(drgb + row * 4) = make_float4(r0, r1, r2, ds);
+          } else {
+            float* o = drgb + row * drgb_st;
+            o[0] = r0; o[1] = r1; o[2] = r2;
+            dsig[row * dsig_st] = ds;
+          }
         }
       }
     }
@@ -302,31 +326,33 @@ static int check_composite(const float* t, int64_t t_rs, const float* rgb, const
 }
 
 extern "C" int hbr_composite_fwd(const float* t, int64_t t_rs, const float* rgb, int64_t rgb_st, const float* sigma,
-                                 int64_t sig_st, const float* dn, float dn_scalar, const uint8_t* mask, int64_t R,
-                                 int64_t S, float* C, float* w, void* stream) {
+                                 int64_t sig_st, const float* dn, float dn_scalar, const uint8_t* mask, const int32_t* rowmap,
+                                 int64_t R, int64_t S, float* C, float* w, float ert_tau, void* stream) {
   if (R == 0) return HBR_OK;
   if (int rc = check_composite(t, t_rs, rgb, sigma, R, S)) return rc;
   HBR_REQUIRE(C != nullptr, "C is NULL");
+  if (!(ert_tau > 0.f)) ert_tau = 3.0e38f;                           // <= 0 / NaN: off (no fp32 optical depth exceeds it)
   composite_fwd_kernel<<<(unsigned)ceil_div(R, kRaysPerCta), kRaysPerCta * 32, 0, as_stream(stream)>>>(
-      t, t_rs, rgb, rgb_st, sigma, sig_st, dn, dn_scalar, mask, R, (int)S, C, w);
+      t, t_rs, rgb, rgb_st, sigma, sig_st, dn, dn_scalar, mask, rowmap, R, (int)S, C, w, ert_tau);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
 
 extern "C" int hbr_composite_bwd(const float* t, int64_t t_rs, const float* rgb, int64_t rgb_st, const float* sigma,
-                                 int64_t sig_st, const float* dn, float dn_scalar, const uint8_t* mask, int64_t R,
-                                 int64_t S, const float* gC, float* drgb, int64_t drgb_st, float* dsig,
-                                 int64_t dsig_st, void* stream) {
+                                 int64_t sig_st, const float* dn, float dn_scalar, const uint8_t* mask, const int32_t* rowmap,
+                                 int64_t R, int64_t S, const float* gC, float* drgb, int64_t drgb_st, float* dsig,
+                                 int64_t dsig_st, float ert_tau, void* stream) {
   if (R == 0) return HBR_OK;
   if (int rc = check_composite(t, t_rs, rgb, sigma, R, S)) return rc;
   HBR_REQUIRE(gC && drgb && dsig, "NULL pointer");
+  if (!(ert_tau > 0.f)) ert_tau = 3.0e38f;
   if (drgb_st == 4 && dsig_st == 4 && dsig == drgb + 3)
     HBR_REQUIRE((uintptr_t)drgb % 16 == 0, "packed gradient buffer must be 16-byte aligned");
   const unsigned grid = (unsigned)ceil_div(R, kRaysPerCta);
   cudaStream_t st = as_stream(stream);
 #define HBR_CB(N)                                                                                               \
   composite_bwd_kernel<N><<<grid, kRaysPerCta * 32, 0, st>>>(t, t_rs, rgb, rgb_st, sigma, sig_st, dn, dn_scalar, \
-                                                             mask, R, (int)S, gC, drgb, drgb_st, dsig, dsig_st)
+                                                             mask, rowmap, R, (int)S, gC, drgb, drgb_st, dsig, dsig_st, ert_tau)
   if (S <= 128) HBR_CB(4);
   else if (S <= 256) HBR_CB(8);
   else if (S <= 512) HBR_CB(16);

@@ -60,7 +60,7 @@ extern "C" int hbr_debug_mlp_trace_bwd(const float* feat, const float* dirs, int
   if (sc != nullptr) mlp_prep_kernel<32, 48><<<kPrepCtas, 256, 0, as_stream(stream)>>>(params, 32, 24, sc);
   mlp_bwd_tc_kernel<32, 48, 2, true><<<grid, 2 * kTile + 32, smem, as_stream(stream)>>>(
       feat, 32, dirs, dir_group, n, params, 32, 24, out, dout, dfeat, 32, nullptr, dparams, sc,
-      sc != nullptr ? reinterpret_cast<float*>(sc + SC::off_grad) : nullptr, trace, EncArgs{}, HashGeom{}, 1.f, 0);
+      sc != nullptr ? reinterpret_cast<float*>(sc + SC::off_grad) : nullptr, trace, EncArgs{}, HashGeom{}, 1.f, 0, nullptr, nullptr);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -71,7 +71,7 @@ extern "C" int hbr_debug_mlp_trace(const float* feat, const float* dirs, int64_t
   HBR_CUDA(cudaFuncSetAttribute(mlp_fwd_tc_kernel<32, 48, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), 4), sm_count());
   mlp_fwd_tc_kernel<32, 48, 4, true><<<grid, 4 * kTile, smem, as_stream(stream)>>>(
-      feat, 32, dirs, dir_group, n, params, 32, 24, out, nullptr, trace, EncArgs{}, HashGeom{}, 0);
+      feat, 32, dirs, dir_group, n, params, 32, 24, out, nullptr, trace, EncArgs{}, HashGeom{}, 0, nullptr, nullptr);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }

@@ -94,8 +94,12 @@ template <> struct PointSrc<RayPts> { using type = RaySrc; };
 template <int F, bool POW2, typename XT, int PAIR = 0, int UNR = 4, typename YT = float>
 __global__ void __launch_bounds__(kHashThreads)
 hash_fwd_kernel(const typename PointSrc<XT>::type x, long long n, const float* __restrict__ table, YT* __restrict__ y,
-                long long y_stride, const __grid_constant__ HashGeom g, int y_fmt) {
+                long long y_stride, const __grid_constant__ HashGeom g, int y_fmt, const unsigned long long* __restrict__ n_dev) {
   extern __shared__ float tile[];                    // [kTilePts][pitch]
+  if (n_dev != nullptr) {                            // compacted sample lists: the live count lives on the device
+    n = min(n, (long long)__ldg(n_dev));
+    if ((long long)blockIdx.x * kTilePts >= n) return;
+  }
   const int C = g.L * F;
   const int pitch = C | 1;                           // odd pitch: conflict-free column writes
   const int p = threadIdx.x & (kTilePts - 1);
@@ -177,8 +181,13 @@ hash_fwd_kernel(const typename PointSrc<XT>::type x, long long n, const float* _
 template <int F, bool POW2, typename XT>
 __global__ void __launch_bounds__(kHashThreads)
 hash_bwd_kernel(const typename PointSrc<XT>::type x, long long n, const float* __restrict__ dy, long long dy_stride,
-                float* __restrict__ dtable, const __grid_constant__ HashGeom g, int l_begin, int l_end) {
+                float* __restrict__ dtable, const __grid_constant__ HashGeom g, int l_begin, int l_end,
+                const unsigned long long* __restrict__ n_dev) {
   extern __shared__ float tile[];
+  if (n_dev != nullptr) {
+    n = min(n, (long long)__ldg(n_dev));
+    if ((long long)blockIdx.x * kTilePts >= n) return;
+  }
   const int C = g.L * F;
   const int pitch = C | 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -315,7 +324,7 @@ static int launch_fwd(const void* x, int64_t n, const float* table, const HashGe
   const unsigned grid = (unsigned)ceil_div(n, kTilePts);
   auto k = hash_fwd_kernel<F, POW2, XT>;
   HBR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<grid, kHashThreads, smem, st>>>(static_cast<const XT*>(x), n, table, y, ys, g, HBR_F32);
+  k<<<grid, kHashThreads, smem, st>>>(static_cast<const XT*>(x), n, table, y, ys, g, HBR_F32, nullptr);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -325,7 +334,7 @@ static int launch_bwd(const void* x, int64_t n, const float* dy, int64_t ds, con
   const size_t smem = (size_t)kTilePts * ((g.L * F) | 1) * sizeof(float);
   HBR_CUDA(cudaFuncSetAttribute(hash_bwd_kernel<F, POW2, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   hash_bwd_kernel<F, POW2, XT><<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(
-      static_cast<const XT*>(x), n, dy, ds, dt, g, l0, l1);
+      static_cast<const XT*>(x), n, dy, ds, dt, g, l0, l1, nullptr);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -336,7 +345,7 @@ static int launch_fwd_rays(const RaySrc& rs, int64_t n, const float* table, cons
   const size_t smem = (size_t)kTilePts * ((g.L * F) | 1) * sizeof(float);
   auto k = hash_fwd_kernel<F, POW2, RayPts, 0, 4, YT>;
   HBR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(rs, n, table, static_cast<YT*>(y), ys, g, y_fmt);
+  k<<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(rs, n, table, static_cast<YT*>(y), ys, g, y_fmt, nullptr);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -346,7 +355,29 @@ static int launch_bwd_rays(const RaySrc& rs, int64_t n, const float* dy, int64_t
   const size_t smem = (size_t)kTilePts * ((g.L * F) | 1) * sizeof(float);
   auto k = hash_bwd_kernel<F, POW2, RayPts>;
   HBR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(rs, n, dy, ds, dt, g, l0, l1);
+  k<<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(rs, n, dy, ds, dt, g, l0, l1, nullptr);
+
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
+// compacted sample lists: explicit fp32 positions, at most n of them, the live count on the device
+template <int F, bool POW2, typename YT>
+static int launch_fwd_pts(const float* x, int64_t n, const unsigned long long* n_dev, const float* table, const HashGeom& g,
+                          void* y, int64_t ys, int y_fmt, cudaStream_t st) {
+  const size_t smem = (size_t)kTilePts * ((g.L * F) | 1) * sizeof(float);
+  auto k = hash_fwd_kernel<F, POW2, float, 0, 4, YT>;
+  HBR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(x, n, table, static_cast<YT*>(y), ys, g, y_fmt, n_dev);
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
+template <int F, bool POW2>
+static int launch_bwd_pts(const float* x, int64_t n, const unsigned long long* n_dev, const float* dy, int64_t ds,
+                          const HashGeom& g, float* dt, int l0, int l1, cudaStream_t st) {
+  const size_t smem = (size_t)kTilePts * ((g.L * F) | 1) * sizeof(float);
+  auto k = hash_bwd_kernel<F, POW2, float>;
+  HBR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(x, n, dy, ds, dt, g, l0, l1, n_dev);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -485,5 +516,56 @@ extern "C" int hbr_hash_encode_bwd_rays(const float* rays_o, const float* rays_d
                       : launch_bwd_rays<2, false>(rs, n, dy, dy_stride, g, dtable, level_begin, level_end, st);
     default: return p2 ? launch_bwd_rays<4, true>(rs, n, dy, dy_stride, g, dtable, level_begin, level_end, st)
                        : launch_bwd_rays<4, false>(rs, n, dy, dy_stride, g, dtable, level_begin, level_end, st);
+  }
+}
+
+extern "C" int hbr_hash_encode_fwd_pts(const float* x, int64_t n_max, const unsigned long long* n_dev, const float* table,
+                                       const hbr_hash_geom* geom, void* y, int64_t y_stride, int y_dtype, void* stream) {
+  if (int rc = check_geom(geom)) return rc;
+  HBR_REQUIRE(y_dtype == HBR_F32 || y_dtype == HBR_F16 || y_dtype == HBR_BF16, "y_dtype %d", y_dtype);
+  HBR_REQUIRE(n_max >= 0 && n_max < (1LL << 40), "n_max=%lld", (long long)n_max);
+  if (n_max == 0) return HBR_OK;
+  HBR_REQUIRE(x && table && y, "NULL pointer");
+  const int cols = geom->L * geom->F + geom->E;
+  HBR_REQUIRE(y_stride >= cols && (uintptr_t)table % 16 == 0, "y_stride / table alignment");
+  HBR_REQUIRE(y_dtype == HBR_F32 || (cols % 2 == 0 && y_stride % 2 == 0 && (uintptr_t)y % 4 == 0),
+              "16-bit features need an even column count / stride and a 4-byte aligned buffer");
+  const HashGeom g = to_device_geom(*geom);
+  cudaStream_t st = as_stream(stream);
+  const bool p2 = is_pow2(g.T);
+#define HBR_FWD_PTS(F_)                                                                                               \
+  (y_dtype == HBR_F32 ? (p2 ? launch_fwd_pts<F_, true, float>(x, n_max, n_dev, table, g, y, y_stride, y_dtype, st)     \
+                            : launch_fwd_pts<F_, false, float>(x, n_max, n_dev, table, g, y, y_stride, y_dtype, st))   \
+                      : (p2 ? launch_fwd_pts<F_, true, uint16_t>(x, n_max, n_dev, table, g, y, y_stride, y_dtype, st)  \
+                            : launch_fwd_pts<F_, false, uint16_t>(x, n_max, n_dev, table, g, y, y_stride, y_dtype, st)))
+  switch (g.F) {
+    case 1: return HBR_FWD_PTS(1);
+    case 2: return HBR_FWD_PTS(2);
+    default: return HBR_FWD_PTS(4);
+  }
+#undef HBR_FWD_PTS
+}
+
+extern "C" int hbr_hash_encode_bwd_pts(const float* x, int64_t n_max, const unsigned long long* n_dev, const float* dy,
+                                       int64_t dy_stride, const hbr_hash_geom* geom, float* dtable, int level_begin,
+                                       int level_end, void* stream) {
+  if (int rc = check_geom(geom)) return rc;
+  HBR_REQUIRE(n_max >= 0 && n_max < (1LL << 40), "n_max=%lld", (long long)n_max);
+  if (n_max == 0) return HBR_OK;
+  HBR_REQUIRE(x && dy && dtable, "NULL pointer");
+  HBR_REQUIRE(dy_stride >= geom->L * geom->F && (uintptr_t)dtable % 16 == 0, "dy_stride / dtable alignment");
+  HBR_REQUIRE(level_begin >= 0 && level_begin <= level_end && level_end <= geom->L, "level range [%d,%d)", level_begin,
+              level_end);
+  if (level_begin == level_end) return HBR_OK;
+  const HashGeom g = to_device_geom(*geom);
+  cudaStream_t st = as_stream(stream);
+  const bool p2 = is_pow2(g.T);
+  switch (g.F) {
+    case 1: return p2 ? launch_bwd_pts<1, true>(x, n_max, n_dev, dy, dy_stride, g, dtable, level_begin, level_end, st)
+                      : launch_bwd_pts<1, false>(x, n_max, n_dev, dy, dy_stride, g, dtable, level_begin, level_end, st);
+    case 2: return p2 ? launch_bwd_pts<2, true>(x, n_max, n_dev, dy, dy_stride, g, dtable, level_begin, level_end, st)
+                      : launch_bwd_pts<2, false>(x, n_max, n_dev, dy, dy_stride, g, dtable, level_begin, level_end, st);
+    default: return p2 ? launch_bwd_pts<4, true>(x, n_max, n_dev, dy, dy_stride, g, dtable, level_begin, level_end, st)
+                       : launch_bwd_pts<4, false>(x, n_max, n_dev, dy, dy_stride, g, dtable, level_begin, level_end, st);
   }
 }

@@ -46,7 +46,7 @@ static int check_feat(const void* feat, int feat_dtype, int64_t feat_stride, con
 
 extern "C" int hbr_mlp_fwd_tc(const void* feat_, int feat_dtype, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                               const float* params, const hbr_mlp_dims* dims, int operand, float* out, void* scratch,
-                              int image_ready, void* stream) {
+                              int image_ready, const unsigned long long* n_dev, const int32_t* dir_rows, void* stream) {
   if (int rc = check_dims(dims)) return rc;
   if (int rc = check_operand(operand, 1.f)) return rc;
   if (n == 0) return HBR_OK;
@@ -60,15 +60,16 @@ extern "C" int hbr_mlp_fwd_tc(const void* feat_, int feat_dtype, int64_t feat_st
   uint8_t* sc = static_cast<uint8_t*>(scratch);
   if (narrow_shape(dims))
     return HBR_BY_OPERAND(launch_fwd_tc<32, 48, 4, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view,
-                                                          out, sc, EncArgs{}, HashGeom{}, f16, image_ready, st));
+                                                          out, sc, EncArgs{}, HashGeom{}, f16, image_ready, n_dev, dir_rows, st));
   return HBR_BY_OPERAND(launch_fwd_tc<64, 64, 4, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out,
-                                                        sc, EncArgs{}, HashGeom{}, f16, image_ready, st));
+                                                        sc, EncArgs{}, HashGeom{}, f16, image_ready, n_dev, dir_rows, st));
 }
 
 extern "C" int hbr_mlp_bwd_tc(const void* feat_, int feat_dtype, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                               const float* params, const hbr_mlp_dims* dims, int operand, const float* out,
                               const float* dout, float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams,
-                              float grad_scale, void* scratch, int image_ready, int defer_reduce, void* stream) {
+                              float grad_scale, void* scratch, int image_ready, int defer_reduce,
+                              const unsigned long long* n_dev, const int32_t* dir_rows, void* stream) {
   if (int rc = check_dims(dims)) return rc;
   HBR_REQUIRE(!defer_reduce || (scratch != nullptr && dparams != nullptr), "defer_reduce needs scratch and dparams");
   if (int rc = check_operand(operand, grad_scale)) return rc;
@@ -86,10 +87,10 @@ extern "C" int hbr_mlp_bwd_tc(const void* feat_, int feat_dtype, int64_t feat_st
   if (narrow_shape(dims))
     return HBR_BY_OPERAND(launch_bwd_tc<32, 48, 2, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view,
                                                           out, dout, dfeat, dfeat_stride, ddirs, dparams, sc, EncArgs{}, HashGeom{},
-                                                          grad_scale, f16, image_ready, defer_reduce, st));
+                                                          grad_scale, f16, image_ready, defer_reduce, n_dev, dir_rows, st));
   return HBR_BY_OPERAND(launch_bwd_tc<64, 64, 1, false>(feat, feat_stride, dirs, dir_group, n, params, dims->in0, dims->d_view, out,
                                                         dout, dfeat, dfeat_stride, ddirs, dparams, sc, EncArgs{}, HashGeom{}, grad_scale,
-                                                        f16, image_ready, defer_reduce, st));
+                                                        f16, image_ready, defer_reduce, n_dev, dir_rows, st));
 }
 
 extern "C" int hbr_mlp_tc_prepare(const float* params, const hbr_mlp_dims* dims, int operand, void* scratch, void* stream) {
@@ -136,12 +137,12 @@ extern "C" int hbr_field_fwd_tc(const float* x, int64_t n, const float* table, c
     EncArgs e{};
     e.x = x; e.table = table; e.feat16 = static_cast<uint16_t*>(feat16);
     return f16::launch_fwd_tc<32, 48, 4, true>(nullptr, 32, dirs, dir_group, n, params, 32, dims->d_view, out,
-                                               static_cast<uint8_t*>(scratch), e, to_device_geom(*geom), 0, 0, as_stream(stream));
+                                               static_cast<uint8_t*>(scratch), e, to_device_geom(*geom), 0, 0, nullptr, nullptr, as_stream(stream));
   }
   EncArgs e{};
   e.x = x; e.table = table; e.feat16 = static_cast<uint16_t*>(feat16);
   return bf16::launch_fwd_tc<32, 48, 4, true>(nullptr, 32, dirs, dir_group, n, params, 32, dims->d_view, out,
-                                              static_cast<uint8_t*>(scratch), e, to_device_geom(*geom), 0, 0, as_stream(stream));
+                                              static_cast<uint8_t*>(scratch), e, to_device_geom(*geom), 0, 0, nullptr, nullptr, as_stream(stream));
 }
 
 extern "C" int hbr_field_bwd_tc(const float* x, int64_t n, const hbr_hash_geom* geom, const float* dirs, int64_t dir_group,
@@ -161,11 +162,11 @@ extern "C" int hbr_field_bwd_tc(const float* x, int64_t n, const hbr_hash_geom* 
     e.x = x; e.dtable = dtable; e.feat16 = f16p;
     return f16::launch_bwd_tc<32, 48, 2, true>(nullptr, 32, dirs, dir_group, n, params, 32, dims->d_view, out, dout, nullptr, 32,
                                                ddirs, dparams, static_cast<uint8_t*>(scratch), e, to_device_geom(*geom),
-                                               grad_scale, 0, 0, 0, as_stream(stream));
+                                               grad_scale, 0, 0, 0, nullptr, nullptr, as_stream(stream));
   }
   EncArgs e{};
   e.x = x; e.dtable = dtable; e.feat16 = f16p;
   return bf16::launch_bwd_tc<32, 48, 2, true>(nullptr, 32, dirs, dir_group, n, params, 32, dims->d_view, out, dout, nullptr, 32,
                                               ddirs, dparams, static_cast<uint8_t*>(scratch), e, to_device_geom(*geom),
-                                              grad_scale, 0, 0, 0, as_stream(stream));
+                                              grad_scale, 0, 0, 0, nullptr, nullptr, as_stream(stream));
 }

@@ -741,10 +741,14 @@ __device__ __forceinline__ void copy_feat16_async(const uint16_t* __restrict__ f
 template <int K0P, int KCP, int G, bool TRACE = false, bool ENC = false>
 __global__ void __launch_bounds__(G * kTile, 1)
 mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const float* __restrict__ dirs, long long dir_group,
-                  long long n, const float* __restrict__ params, int in0, int dv, float* __restrict__ out,
+                  long long n_arg, const float* __restrict__ params, int in0, int dv, float* __restrict__ out,
                   const uint8_t* __restrict__ image, long long* __restrict__ trace, const EncArgs enc,
-                  const __grid_constant__ HashGeom geom, int feat16) {
+                  const __grid_constant__ HashGeom geom, int feat16, const unsigned long long* __restrict__ n_dev,
+                  const int32_t* __restrict__ dir_rows) {
   // feat16 != 0: `feat` points at 16-bit features in the operand format (rows of K0P values, contiguous)
+  // n_dev / dir_rows: compacted sample lists: the live point count is read from the device, and point
+  // p takes the direction row dir_rows[p] (the ray it belongs to) instead of p / dir_group
+  const long long n = n_dev != nullptr ? min(n_arg, (long long)__ldg(n_dev)) : n_arg;
   using SM = FwdSmem<K0P, KCP, G>;
   using WO = WOfs<K0P, KCP>;
   // TMEM per tile group: 64 accumulator columns + 32 columns holding the current layer input (bf16 pairs)
@@ -838,7 +842,7 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     for (long long tile = (long long)g * gridDim.x + blockIdx.x; tile < ntiles; tile += nslots) {
       const long long gp = tile * kTile + r;
       const bool valid = gp < n;
-      const long long dir_row = valid ? gp / dir_group : 0;
+      const long long dir_row = valid ? (dir_rows != nullptr ? (long long)__ldg(dir_rows + gp) : gp / dir_group) : 0;
       if (valid && lane == 0) prefetch_l1(dirs + dir_row * dv);
       TR();
       if (ENC) {
@@ -1087,12 +1091,15 @@ __device__ __noinline__ void flush_gradients(uint32_t tbase, int warp, int lane,
 template <int K0P, int KCP, int G, bool TRACE = false, bool ENC = false>
 __global__ void __launch_bounds__(G * kTile + 32, 1)
 mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const float* __restrict__ dirs, long long dir_group,
-                  long long n, const float* __restrict__ params, int in0, int dv, const float* __restrict__ out,
+                  long long n_arg, const float* __restrict__ params, int in0, int dv, const float* __restrict__ out,
                   const float* __restrict__ dout, float* __restrict__ dfeat, long long dfeat_stride,
                   float* __restrict__ ddirs, float* __restrict__ dparams, const uint8_t* __restrict__ image,
                   float* __restrict__ grad_rows, long long* __restrict__ trace, const EncArgs enc,
-                  const __grid_constant__ HashGeom geom, float gscale, int feat16) {
+                  const __grid_constant__ HashGeom geom, float gscale, int feat16, const unsigned long long* __restrict__ n_dev,
+                  const int32_t* __restrict__ dir_rows) {
   // feat16 != 0: `feat` points at 16-bit features in the operand format (rows of K0P values, contiguous)
+  // n_dev / dir_rows: compacted sample lists, as in the forward kernel
+  const long long n = n_dev != nullptr ? min(n_arg, (long long)__ldg(n_dev)) : n_arg;
   // gscale: power of two applied to the upstream gradient before it is rounded to the 16-bit operand format and divided
   // out of every result (fp16 has 5 exponent bits: unscaled gradients of a mean-reduced loss underflow; the reference
   // relies on GradScaler for the same reason, train_hash2.py:156,226).  1.0 = off.
@@ -1310,7 +1317,7 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       HBR_STAMP(0);                              // tile start
       const long long gp = tile * kTile + r;
       const bool valid = gp < n;
-      const long long dir_row = valid ? gp / dir_group : 0;
+      const long long dir_row = valid ? (dir_rows != nullptr ? (long long)__ldg(dir_rows + gp) : gp / dir_group) : 0;
       if (valid && lane == 0) prefetch_l1(dirs + dir_row * dv);
       float4 fo = make_float4(0.f, 0.f, 0.f, 0.f), go = fo;           // saved forward output, upstream gradient
       if (valid) {
@@ -1501,7 +1508,8 @@ static inline bool narrow_shape(const hbr_mlp_dims* d) { return d->in0 <= 32 && 
 template <int K0P, int KCP, int G, bool ENC>
 static int launch_fwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                          const float* params, int in0, int dv, float* out, uint8_t* scratch, const EncArgs& enc,
-                         const HashGeom& geom, int feat16, int image_ready, cudaStream_t st) {
+                         const HashGeom& geom, int feat16, int image_ready, const unsigned long long* n_dev, const int32_t* dir_rows,
+                         cudaStream_t st) {
   constexpr int smem = FwdSmem<K0P, KCP, G>::total;
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), G), sm_count());
   // the full image (incl. the fp32 biases only the backward reads): the backward call of the step can then skip its prep
@@ -1509,7 +1517,7 @@ static int launch_fwd_tc(const float* feat, int64_t feat_stride, const float* di
   auto kern = mlp_fwd_tc_kernel<K0P, KCP, G, false, ENC>;
   HBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, G * kTile, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, scratch, nullptr, enc,
-                                             geom, feat16);
+                                             geom, feat16, n_dev, dir_rows);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -1518,7 +1526,8 @@ template <int K0P, int KCP, int G, bool ENC>
 static int launch_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                          const float* params, int in0, int dv, const float* out, const float* dout, float* dfeat,
                          int64_t dfeat_stride, float* ddirs, float* dparams, uint8_t* scratch, const EncArgs& enc,
-                         const HashGeom& geom, float gscale, int feat16, int image_ready, int defer_reduce, cudaStream_t st) {
+                         const HashGeom& geom, float gscale, int feat16, int image_ready, int defer_reduce,
+                         const unsigned long long* n_dev, const int32_t* dir_rows, cudaStream_t st) {
   using SC = Scratch<K0P, KCP>;
   constexpr int smem = BwdSmem<K0P, KCP, G>::total;
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), G), sm_count());
@@ -1528,7 +1537,7 @@ static int launch_bwd_tc(const float* feat, int64_t feat_stride, const float* di
   HBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, G * kTile + 32, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, dout, dfeat,
                                            dfeat_stride, ddirs, dparams, scratch,
-                                           rows ? reinterpret_cast<float*>(scratch + SC::off_grad) : nullptr, nullptr, enc, geom, gscale, feat16);
+                                           rows ? reinterpret_cast<float*>(scratch + SC::off_grad) : nullptr, nullptr, enc, geom, gscale, feat16, n_dev, dir_rows);
   if (rows && !defer_reduce) {
     const int total = make_layout(in0, dv).total;
     mlp_grad_reduce_kernel<<<dim3((total + 255) / 256, kReduceSlices), 256, 0, st>>>(

@@ -10,7 +10,9 @@ static device buffers before each replay; the loss and the parameter gradients l
 replay overwrites (the parameters' `.grad` tensors are allocated inside the graph's memory pool during capture, the
 documented whole-network-capture pattern of torch.cuda.graphs).  torch's CUDA generator is graph-safe, so the
 reference's RNG draws (strat_sampler, hierarchical_sampling) still advance on every replay.
-An optimiser may be stepped eagerly after the replay (its inputs, the `.grad` tensors, are static).
+An optimiser may be stepped eagerly after the replay (its inputs, the `.grad` tensors, are static), or -- with
+`optimizers=[optim.FusedAdam(..., capturable=True), ...]` -- inside the captured graph, so that one replay is a complete
+train_hash2.py iteration (:218-239) including both optimiser steps.
 """
 from __future__ import annotations
 
@@ -35,7 +37,7 @@ def default_loss(Cr, Cf, gt):
 class GraphedStep:
     def __init__(self, renderer, model, params: Iterable[torch.nn.Parameter], n_rays: int, num_samples: int,
                  hierarchical: bool, device, loss_fn: Callable = default_loss, autocast: bool = True, warmup: int = 3,
-                 source=None, autocast_dtype: torch.dtype = torch.bfloat16):
+                 source=None, autocast_dtype: torch.dtype = torch.bfloat16, optimizers: Iterable = ()):
         """source: optional rays.DeviceRayDataset.  Its sampler (ray ids from the graph-safe device generator ->
         hbr_ray_gen) is then captured in front of the step, so a replay draws a fresh batch from the resident views by
         itself: call the object with no arguments; nothing crosses PCIe but the graph launch."""
@@ -44,6 +46,13 @@ class GraphedStep:
         self.params = list(params)
         self.num_samples, self.hierarchical = int(num_samples), bool(hierarchical)
         self.loss_fn, self.autocast, self.autocast_dtype = loss_fn, autocast, autocast_dtype
+        # optimisers stepped INSIDE the captured graph (train_hash2.py:226-239 in one replay): optim.FusedAdam(capturable=True)
+        # keeps step count and learning rate on the device; note that the warm-up iterations of capture() are real steps
+        # on whatever the static input buffers hold: load() a real batch before capture()
+        self.optimizers = list(optimizers)
+        for o in self.optimizers:
+            if not getattr(o, "capturable", False):
+                raise ValueError("optimisers captured in the step's graph must be capturable (optim.FusedAdam(capturable=True))")
         dev = torch.device(device)
         # one packed static buffer [rays_o (R,3) | rays_d (R,3) | dir_norm (R,1) | gt (R,3)]: a batch packed the same way
         # (pack_batch) is loaded with ONE copy instead of four
@@ -69,6 +78,8 @@ class GraphedStep:
                                                  update_mask=False, dir_norm=dir_norm, hierarchical=self.hierarchical)
             loss = self.loss_fn(Cr, Cf, gt)
         loss.backward()
+        for o in self.optimizers:
+            o.step()
         return loss
 
     @staticmethod

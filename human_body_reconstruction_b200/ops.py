@@ -98,6 +98,48 @@ def hash_encode_bwd_rays(rays_o, rays_d, t, dy, geom: HashGeom, dtable, level_be
                                          C.byref(geom), ptr(dtable), int(level_begin), int(level_end), stream()))
 
 
+def occupancy_update(pts, alpha, grid, mu, sigma: float, flags2):
+    """Volume_Renderer.update_grid (vol_renderer.py:116-131) in place on `grid` ((G,G,G) bool)."""
+    require_cuda(pts, alpha, grid, flags2)
+    pts = _f32c(pts.reshape(-1, 3))
+    alpha = _f32c(alpha.reshape(-1))
+    mu3 = (C.c_float * 3)(*[float(v) for v in mu])
+    check(lib().hbr_occupancy_update(ptr(pts), pts.shape[0], ptr(alpha), 1, ptr(grid), grid.shape[0], mu3, float(sigma),
+                                     ptr(flags2), stream()))
+
+
+def compact_samples(rays_o, rays_d, t, grid, mu, sigma: float):
+    """Live samples of the rays under the occupancy grid: (pts_c (R*S,3), ray_c (R*S) int32, rowmap (R*S) int32,
+    count (1) uint64 on the device); only the first `count` rows of pts_c / ray_c are meaningful."""
+    require_cuda(rays_o, rays_d, t, grid)
+    R, S = rays_o.shape[0], t.shape[-1]
+    dev = rays_o.device
+    pts_c = torch.empty((R * S, 3), device=dev, dtype=torch.float32)
+    ray_c = torch.empty((R * S,), device=dev, dtype=torch.int32)
+    rowmap = torch.empty((R * S,), device=dev, dtype=torch.int32)
+    count = torch.zeros(1, device=dev, dtype=torch.int64)
+    mu3 = (C.c_float * 3)(*[float(v) for v in mu])
+    check(lib().hbr_compact_samples(ptr(rays_o), ptr(rays_d), ptr(t), _t_stride(t, S), R, S, ptr(grid), grid.shape[0], mu3,
+                                    float(sigma), ptr(pts_c), ptr(ray_c), ptr(rowmap), ptr(count), stream()))
+    return pts_c, ray_c, rowmap, count
+
+
+def hash_encode_fwd_pts(x, n_dev, table, geom: HashGeom, y_dtype: int = HBR_F32) -> torch.Tensor:
+    require_cuda(x, table)
+    n = x.shape[0]
+    cols = geom.L * geom.F + geom.E
+    y = torch.empty((n, cols), device=table.device, dtype=_TORCH_OF[y_dtype])
+    check(lib().hbr_hash_encode_fwd_pts(ptr(x), n, ptr(n_dev), ptr(table), C.byref(geom), ptr(y), cols, y_dtype, stream()))
+    return y
+
+
+def hash_encode_bwd_pts(x, n_dev, dy, geom: HashGeom, dtable, level_begin: int = 0, level_end: Optional[int] = None):
+    require_cuda(x, dy, dtable)
+    level_end = geom.L if level_end is None else level_end
+    check(lib().hbr_hash_encode_bwd_pts(ptr(x), x.shape[0], ptr(n_dev), ptr(dy), dy.stride(0), C.byref(geom), ptr(dtable),
+                                        int(level_begin), int(level_end), stream()))
+
+
 def hash_indices(x: torch.Tensor, geom: HashGeom, want_w: bool = True):
     require_cuda(x)
     x = x.contiguous()
@@ -207,31 +249,38 @@ def _dn_args(dir_norm, R, device):
     return None, float(dir_norm)
 
 
-def composite_fwd(t, rgb, rgb_stride, sigma, sigma_stride, dir_norm, mask, R, S, want_w=True):
+ERT_TAU = 104.0       # exp(-104) == 0 in fp32: the transmittance of every sample skipped by early ray termination is exactly 0
+
+
+def composite_fwd(t, rgb, rgb_stride, sigma, sigma_stride, dir_norm, mask, R, S, want_w=True, ert_tau=0.0, rowmap=None):
     dn, dns = _dn_args(dir_norm, R, t.device)
     Cc = torch.empty((R, 3), device=t.device, dtype=torch.float32)
     w = torch.empty((R, S), device=t.device, dtype=torch.float32) if want_w else None
     check(lib().hbr_composite_fwd(ptr(t), 0 if t.dim() == 1 else S, ptr(rgb), rgb_stride, ptr(sigma), sigma_stride,
-                                  ptr(dn), dns, ptr(mask), R, S, ptr(Cc), ptr(w), stream()))
+                                  ptr(dn), dns, ptr(mask), ptr(rowmap), R, S, ptr(Cc), ptr(w), float(ert_tau), stream()))
     return Cc, w
 
 
-def composite_bwd(t, rgb, rgb_stride, sigma, sigma_stride, dir_norm, mask, R, S, gC, drgb, drgb_stride, dsig, dsig_stride):
+def composite_bwd(t, rgb, rgb_stride, sigma, sigma_stride, dir_norm, mask, R, S, gC, drgb, drgb_stride, dsig, dsig_stride,
+                  ert_tau=0.0, rowmap=None):
     dn, dns = _dn_args(dir_norm, R, t.device)
     check(lib().hbr_composite_bwd(ptr(t), 0 if t.dim() == 1 else S, ptr(rgb), rgb_stride, ptr(sigma), sigma_stride,
-                                  ptr(dn), dns, ptr(mask), R, S, ptr(gC), ptr(drgb), drgb_stride, ptr(dsig), dsig_stride,
-                                  stream()))
+                                  ptr(dn), dns, ptr(mask), ptr(rowmap), R, S, ptr(gC), ptr(drgb), drgb_stride, ptr(dsig), dsig_stride,
+                                  float(ert_tau), stream()))
 
 
 class CompositePacked(torch.autograd.Function):
     """calc_color on the MLP's packed (R*S,4) [rgb,sigma] output -> (C (R,3), w (R,S)); w carries no gradient."""
 
     @staticmethod
-    def forward(ctx, out4, t, dir_norm, mask, R, S):
+    def forward(ctx, out4, t, dir_norm, mask, R, S, ert_tau=0.0, rowmap=None):
+        """rowmap (R*S) int32: out4 is a COMPACTED (n_live.., 4) list; sample i lives at row rowmap[i] (< 0: skipped)."""
         require_cuda(out4, t)
         out4 = _f32c(out4)
         t = _f32c(t)
-        Cc, w = composite_fwd(t, out4, 4, out4[:, 3:], 4, dir_norm, mask, R, S)
+        ctx.ert_tau = float(ert_tau)
+        Cc, w = composite_fwd(t, out4, 4, out4[:, 3:], 4, dir_norm, mask, R, S, ert_tau=ert_tau, rowmap=rowmap)
+        ctx.rowmap = rowmap
         ctx.save_for_backward(out4, t, dir_norm if torch.is_tensor(dir_norm) else None, mask)
         ctx.dn_scalar = None if torch.is_tensor(dir_norm) else dir_norm
         ctx.RS = (R, S)
@@ -244,8 +293,9 @@ class CompositePacked(torch.autograd.Function):
         dn = dn if dn is not None else ctx.dn_scalar
         R, S = ctx.RS
         d4 = torch.empty_like(out4)
-        composite_bwd(t, out4, 4, out4[:, 3:], 4, dn, mask, R, S, _f32c(gC), d4, 4, d4[:, 3:], 4)
-        return d4, None, None, None, None, None
+        composite_bwd(t, out4, 4, out4[:, 3:], 4, dn, mask, R, S, _f32c(gC), d4, 4, d4[:, 3:], 4, ert_tau=ctx.ert_tau,
+                      rowmap=ctx.rowmap)
+        return d4, None, None, None, None, None, None, None
 
 
 class CompositeSplit(torch.autograd.Function):
@@ -407,18 +457,19 @@ def mlp_tc_prepare(params, dims: MlpDims, operand: int):
 
 
 def mlp_fwd_tc(feat, dirs, dir_group, params, dims: MlpDims, keep_act: bool = False, operand: int = HBR_BF16,
-               image_ready: bool = False):
+               image_ready: bool = False, n_dev=None, dir_rows=None, n_max=None):
     """16-bit tensor-core forward; keeps nothing (the backward recomputes), returns (out, None)."""
     require_cuda(feat, dirs, params)
     n = feat.shape[0]
     out = torch.empty((n, 4), device=feat.device, dtype=torch.float32)
+    n = n if n_max is None else int(n_max)
     scratch = mlp_tc_scratch(dims, feat.device)
     # unless the caller has just prepared it (mlp_tc_prepare), the forward rebuilds the operand image (4 us) and records
     # what it was built from; the backward of the same parameters (same storage, same version counter, same operand
     # format) skips its prep kernel
     ready = 1 if (image_ready and _tc_image.get(id(scratch)) == _image_key(params, operand)) else 0
     check(lib().hbr_mlp_fwd_tc(ptr(feat), _feat_dtype(feat, operand), feat.stride(0), ptr(dirs), dir_group, n, ptr(params),
-                               C.byref(dims), operand, ptr(out), ptr(scratch), ready, stream()))
+                               C.byref(dims), operand, ptr(out), ptr(scratch), ready, ptr(n_dev), ptr(dir_rows), stream()))
     if ready:
         _lib.STATS.launches -= 1
     _tc_image[id(scratch)] = _image_key(params, operand)
@@ -431,7 +482,7 @@ def mlp_tc_reduce_grads(dims: MlpDims, n: int, dparams, device):
 
 
 def mlp_bwd_tc(feat, dirs, dir_group, params, dims: MlpDims, out, dout, want_dfeat, want_ddirs, dparams,
-               operand: int = HBR_BF16, grad_scale: float = 1.0, defer_reduce: bool = False):
+               operand: int = HBR_BF16, grad_scale: float = 1.0, defer_reduce: bool = False, n_dev=None, dir_rows=None):
     """`out` is the forward output (N,4): the kernel takes ELU' / LeakyReLU' from it instead of recomputing the last layer.
     defer_reduce: leave the per-CTA gradient rows in the scratch; the caller runs mlp_tc_reduce_grads (on any stream that
     waits for this one) before anything else uses the scratch or reads dparams."""
@@ -443,7 +494,8 @@ def mlp_bwd_tc(feat, dirs, dir_group, params, dims: MlpDims, out, dout, want_dfe
     ready = 1 if _tc_image.get(id(scratch)) == key else 0
     check(lib().hbr_mlp_bwd_tc(ptr(feat), _feat_dtype(feat, operand), feat.stride(0), ptr(dirs), dir_group, n, ptr(params),
                                C.byref(dims), operand, ptr(out), ptr(dout), ptr(dfeat), dims.in0, ptr(ddirs), ptr(dparams),
-                               float(grad_scale), ptr(scratch), ready, 1 if defer_reduce else 0, stream()))
+                               float(grad_scale), ptr(scratch), ready, 1 if defer_reduce else 0, ptr(n_dev), ptr(dir_rows),
+                               stream()))
     _lib.STATS.launches -= ready + (1 if defer_reduce else 0)    # no prep kernel / no reduce kernel in this call
     _tc_image[id(scratch)] = key
     return dfeat, ddirs

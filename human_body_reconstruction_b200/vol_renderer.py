@@ -160,6 +160,77 @@ class _FieldRaysFn(torch.autograd.Function):
         return (None, None, None, ddirs, None, None) + tuple(g[i] for i in range(L)) + gm
 
 
+class _FieldCompactFn(torch.autograd.Function):
+    """_FieldRaysFn with the occupancy grid as a live empty-space skipper: hbr_compact_samples keeps only
+    the samples that fall into occupied cells; the encoder, the MLP and their backward passes run on that compacted list
+    (live count on the device: no host synchronisation), and the compositor reads it back through the row map.  Skipped
+    samples contribute exactly what the reference's masked path gives them (sigma = rgb = 0, vol_renderer.py:211-216)."""
+
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, t, dirs, grid, mu, sigma, enc, mlp, *params):
+        geom, dims = enc._geom(), mlp._dims()
+        operand = ops.tc_operand()
+        pts_c, ray_c, rowmap, count = ops.compact_samples(rays_o, rays_d, t, grid, mu, sigma)
+        cur, side = torch.cuda.current_stream(), _side_stream(rays_o.device)
+        flat = mlp._flat_params()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            ops.mlp_tc_prepare(flat, dims, operand)
+        feat16 = ops.hash_encode_fwd_pts(pts_c, count, enc._flat_table(), geom, operand)
+        cur.wait_stream(side)
+        out, _ = ops.mlp_fwd_tc(feat16, dirs, 1, flat, dims, operand=operand, image_ready=True, n_dev=count, dir_rows=ray_c)
+        ctx.enc, ctx.mlp, ctx.geom, ctx.dims, ctx.operand = enc, mlp, geom, dims, operand
+        ctx.save_for_backward(pts_c, ray_c, count, dirs, feat16, out)
+        ctx.want_tab = any(ctx.needs_input_grad[9:9 + enc.L])
+        ctx.want_mlp = any(ctx.needs_input_grad[9 + enc.L:])
+        ctx.g = None
+        if ctx.want_tab:
+            if enc._dp is not None:
+                enc._dp.note_forward(enc)
+            else:
+                ctx.g = enc._zeroed_grad_async()
+        if ctx.want_mlp and mlp._dp is not None:
+            mlp._dp.note_forward(mlp)
+        ctx.mark_non_differentiable(rowmap, count)
+        return out, rowmap, count
+
+    @staticmethod
+    def backward(ctx, dout, _g_rowmap, _g_count):
+        pts_c, ray_c, count, dirs, feat16, out = ctx.saved_tensors
+        enc, mlp = ctx.enc, ctx.mlp
+        L, T, F = enc.L, enc.T, enc.F
+        flat = mlp._flat_params()
+        dpm = mlp._dp if ctx.want_mlp else None
+        if dpm is not None:
+            dflat, last_m = dpm.enter_backward(mlp)
+        else:
+            dflat, last_m = torch.zeros_like(flat), False
+        dfeat, ddirs = ops.mlp_bwd_tc(feat16, dirs, 1, flat, ctx.dims, out.detach(), dout.float().contiguous(), ctx.want_tab,
+                                      ctx.needs_input_grad[3], dflat, operand=ctx.operand, grad_scale=mlp.tc_grad_scale,
+                                      n_dev=count, dir_rows=ray_c)
+        if dpm is not None and last_m:
+            dpm.publish(mlp, dflat)
+        gm = (None,) * len(mlp._ordered()) if (dpm is not None or not ctx.want_mlp) else tuple(mlp._grad_views(dflat))
+        head = (None, None, None, ddirs, None, None, None, None, None)
+        if not ctx.want_tab:
+            return head + (None,) * L + gm
+        dpe = enc._dp
+        if dpe is not None:
+            g, last = dpe.enter_backward(enc)
+            ops.hash_encode_bwd_pts(pts_c, count, dfeat, ctx.geom, g, 0, L)
+            if last:
+                dpe.publish(enc, g)
+            return head + (None,) * L + gm
+        if ctx.g is not None:
+            g, ev = ctx.g
+            ctx.g = None
+            torch.cuda.current_stream().wait_event(ev)
+        else:
+            g = torch.zeros((L, T, F), device=dout.device, dtype=torch.float32)
+        ops.hash_encode_bwd_pts(pts_c, count, dfeat, ctx.geom, g, 0, L)
+        return head + tuple(g[i] for i in range(L)) + gm
+
+
 _SIDE = {}
 
 
@@ -203,6 +274,11 @@ class Volume_Renderer:
         self.use_sdf = use_sdf
         self.var_model = var_model
         self._dp_checked = False
+        self._grid_flags = None
+        # with an occupancy grid that is not all-True, True = skip the samples outside occupied cells
+        # altogether (compacted sample lists through encoder, MLP and compositor) instead of evaluating and zeroing them;
+        # same numbers, work proportional to the live samples.  Autocast / native modules only; off by default.
+        self.compact = False
         self._grid_state = (None, True)           # (bool_grid._version, all_true)
         self._host_norm = None
         # Encoder + MLP fused into one kernel per direction (hbr_field_*_tc): no fp32 feature / d(feature) tensors in HBM
@@ -215,9 +291,25 @@ class Volume_Renderer:
         # hash-grid kernels, features handed to the MLP kernels in their 16-bit operand format.  False = module by module
         # (HashEncoder.forward -> MLP_3D.field), the path every other caller of those modules takes.
         self.chain_field = True
+        # Early ray termination in the compositor (north star kernel 3): opt-in.  True skips the 32-sample chunks
+        # behind the point where the accumulated optical depth exceeds ops.ERT_TAU = 104, i.e. where the transmittance is
+        # exactly 0 in fp32; identical results whenever the depth does not fall back below it (always for sigma >= 0 -- the
+        # reference's LeakyReLU density can be slightly negative, hence off by default).
+        self.ert = False
 
     # -- occupancy grid (vol_renderer.py:116-140) --------------------------------------------------------------
     def update_grid(self, points: torch.Tensor, alpha: torch.Tensor):
+        """vol_renderer.py:116-131.  CUDA tensors go through hbr_occupancy_update (one pass, the "nothing was hit -> whole
+        grid True" fallback decided on the device, no synchronisation); the alpha <= 0 -> 0 clamp is applied to the
+        caller's tensor like the reference does."""
+        if points.is_cuda and self.bool_grid.is_cuda and self.mu.numel() in (1, 3):
+            alpha[alpha <= 0] = 0                                             # :121, in place on the caller's tensor
+            mu, sig = self._norm_host()
+            if self._grid_flags is None or self._grid_flags.device != self.bool_grid.device:
+                self._grid_flags = torch.zeros(2, dtype=torch.int32, device=self.bool_grid.device)
+            ops.occupancy_update(points, alpha, self.bool_grid, mu, sig, self._grid_flags)
+            self._grid_state = (None, True)                                   # contents changed behind torch's version counter
+            return
         points = (points - self.mu) / self.sigma_val
         points = (points * self.grid_size).long()
         alpha[alpha <= 0] = 0
@@ -235,6 +327,33 @@ class Volume_Renderer:
                 mu = mu * 3
             self._host_norm = (mu, float(self.sigma_val.detach().cpu()))
         return self._host_norm
+
+    @torch.no_grad()
+    def update_grid_from_field(self, model, threshold: float = 0.01, chunk: int = 1 << 21, reset: bool = True):
+        """Make the occupancy grid LIVE: evaluate the density of the current field at the centre of every grid cell
+        (cell (i,j,k) covers ((p - mu) / sigma * G) in [i, i+1) x ..., the arithmetic of get_mask) and mark the cells whose
+        density exceeds `threshold` (reset=True clears the grid first, like reset_mask at vol_renderer.py:201-203).  With
+        `self.compact = True` the training step then skips every sample outside the marked cells.  The reference never
+        refreshes its grid (update_grid is commented out of vol_render, :205) -- this is SURVEY 8f row 3."""
+        mlp = self._native(model)
+        if mlp is None:
+            raise TypeError("update_grid_from_field needs the native HashEncoder / MLP_3D")
+        G = self.grid_size
+        dev = self.bool_grid.device
+        mu, sig = self._norm_host()
+        if reset:
+            self.bool_grid[...] = False
+        idx = torch.arange(G, device=dev, dtype=torch.float32) + 0.5
+        mu_t = torch.tensor(mu, device=dev)
+        flat = self.bool_grid.view(-1)
+        for i0 in range(0, G, max(1, chunk // (G * G))):
+            i1 = min(G, i0 + max(1, chunk // (G * G)))
+            ii, jj, kk = torch.meshgrid(idx[i0:i1], idx, idx, indexing="ij")
+            p = torch.stack((ii, jj, kk), dim=-1).reshape(-1, 3) / G * sig + mu_t
+            dens = mlp(self.Pos_encode(p))                                       # density-only branch, fp32 kernels
+            flat[i0 * G * G:i1 * G * G] |= dens.reshape(-1) > threshold
+        self._grid_state = (None, True)
+        return float(self.bool_grid.float().mean())
 
     def get_mask(self, points: torch.Tensor) -> torch.Tensor:
         mu, sig = self._norm_host()
@@ -263,6 +382,9 @@ class Volume_Renderer:
             ok = ok and enc._dp is None
         return ok
 
+    def _ert_tau(self) -> float:
+        return ops.ERT_TAU if self.ert else 0.0
+
     def _can_chain(self, mlp) -> bool:
         """_FieldRaysFn covers the autocast path whenever the encoder's width is the MLP kernels' operand width."""
         enc = self.Pos_encode
@@ -278,10 +400,16 @@ class Volume_Renderer:
             enc = self.Pos_encode
             if enc._flat_table().device != rays_o.device:
                 raise RuntimeError(f"encoder tables are on {enc._flat_table().device}, rays on {rays_o.device}")
+            if mask_needed and self.compact and S <= 1024 and R * S < 2 ** 31:
+                mu, sig = self._norm_host()
+                out4, rowmap, _ = _FieldCompactFn.apply(rays_o, rays_d, t.float().contiguous(), dir_enc.float().contiguous(),
+                                                        self.bool_grid, mu, sig, enc, mlp,
+                                                        *[e.weight for e in enc.Embedding_list], *mlp._ordered())
+                return ops.CompositePacked.apply(out4, t, dir_norm, None, R, S, self._ert_tau(), rowmap)
             mask = self.get_mask(ops.ray_points(rays_o, rays_d, t).view(-1, 3)) if mask_needed else None
             out4 = _FieldRaysFn.apply(rays_o, rays_d, t.float().contiguous(), dir_enc.float().contiguous(), enc, mlp,
                                       *[e.weight for e in enc.Embedding_list], *mlp._ordered())
-            return ops.CompositePacked.apply(out4, t, dir_norm, mask, R, S)
+            return ops.CompositePacked.apply(out4, t, dir_norm, mask, R, S, self._ert_tau())
         pts = ops.ray_points(rays_o, rays_d, t).view(-1, 3)
         mask = self.get_mask(pts) if mask_needed else None
         if self._can_fuse(mlp):
@@ -292,7 +420,7 @@ class Volume_Renderer:
         else:
             feat = self.Pos_encode(pts)
             out4 = mlp.field(feat, dir_enc, S)
-        Cc, w = ops.CompositePacked.apply(out4, t, dir_norm, mask, R, S)
+        Cc, w = ops.CompositePacked.apply(out4, t, dir_norm, mask, R, S, self._ert_tau())
         return Cc, w
 
     def vol_render(self, model, rays_d: torch.Tensor, rays_o: torch.Tensor, num_samples=100,

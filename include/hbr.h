@@ -137,17 +137,19 @@ int hbr_mlp_tc_prepare(const float* params, const hbr_mlp_dims* dims, int operan
  * the second half of that call, for callers that want it on another stream beside the hash-grid backward. */
 int hbr_mlp_tc_reduce_grads(const hbr_mlp_dims* dims, int64_t n, void* scratch, float* dparams, void* stream);
 /* image_ready != 0: the operand image in `scratch` was built by an earlier call for these very parameters and operand
- * format (the forward call of the same step): skip the prep kernel. */
+ * format (the forward call of the same step): skip the prep kernel.
+ * n_dev / dir_rows (both may be NULL): compacted sample lists (hbr_compact_samples): at most n points, the live count is
+ * read from *n_dev on the device; point p uses direction row dir_rows[p] instead of p / dir_group. */
 /* feat_dtype: HBR_F32 (n, feat_stride) fp32 features, or the operand format itself -- features already rounded to it by
  * hbr_hash_encode_fwd_rays (contiguous rows of in0 16-bit values; in0 must be 32, or 64 for the wide shape): the kernels
  * then copy the rows straight into their operand tile. */
 int hbr_mlp_fwd_tc(const void* feat, int feat_dtype, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                    const float* params, const hbr_mlp_dims* dims, int operand, float* out, void* scratch, int image_ready,
-                   void* stream);
+                   const unsigned long long* n_dev, const int32_t* dir_rows, void* stream);
 int hbr_mlp_bwd_tc(const void* feat, int feat_dtype, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                    const float* params, const hbr_mlp_dims* dims, int operand, const float* out, const float* dout,
                    float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams, float grad_scale, void* scratch,
-                   int image_ready, int defer_reduce, void* stream);
+                   int image_ready, int defer_reduce, const unsigned long long* n_dev, const int32_t* dir_rows, void* stream);
 /* ---- a2 + a7 fused (the training step's field evaluation under autocast): hash-grid encoder + MLP_3D in ONE kernel per
  * direction -- HashEncoder.forward (hash_encoding.py:146-170) feeding MLP_3D.forward (test_hash.py:52-72) as
  * vol_renderer.py:179,211 chains them.  Covers the reference's configuration family F = 2, L = 16, E = 0, power-of-two T,
@@ -185,19 +187,46 @@ int hbr_ray_points(const float* rays_o, const float* rays_d, const float* t, int
 int hbr_occupancy_mask(const float* pts, int64_t n, const uint8_t* grid, int G, const float* mu3_host,
                        float sigma, uint8_t* mask, void* stream);
 
+/* ---- 8f row 3: the occupancy grid of vol_renderer.py:106-140 as a live empty-space skipper ---------------------------
+ * hbr_occupancy_update = Volume_Renderer.update_grid (vol_renderer.py:116-131): cells of grid (G^3 bytes) hit by a point
+ * with alpha > 0 are set; if no point hit anything the whole grid is set (the reference's fallback).  flags2: two zeroed
+ * 32-bit words of device scratch (left zeroed).
+ * hbr_compact_samples: sample positions from the rays (as hbr_ray_points), looked up in the grid (as hbr_occupancy_mask);
+ * only the live ones are written: pts_c (<= R*S, 3), ray_c (their ray), rowmap (R*S): sample -> compacted row or -1;
+ * *count (zero on entry) receives the number of live samples and is what the consumers read as n_dev.  Each ray's live
+ * samples are contiguous and in order; rays appear in arbitrary order. */
+int hbr_occupancy_update(const float* pts, int64_t n, const float* alpha, int64_t alpha_stride, uint8_t* grid, int G,
+                         const float* mu3_host, float sigma, unsigned int* flags2, void* stream);
+int hbr_compact_samples(const float* rays_o, const float* rays_d, const float* t, int64_t t_ray_stride, int64_t R, int64_t S,
+                        const uint8_t* grid, int G, const float* mu3_host, float sigma, float* pts_c, int32_t* ray_c,
+                        int32_t* rowmap, unsigned long long* count, void* stream);
+/* The encoder on a compacted list: x (<= n_max, 3) fp32, live count *n_dev (NULL = n_max); y as hbr_hash_encode_fwd_rays. */
+int hbr_hash_encode_fwd_pts(const float* x, int64_t n_max, const unsigned long long* n_dev, const float* table,
+                            const hbr_hash_geom* geom_host, void* y, int64_t y_stride, int y_dtype, void* stream);
+int hbr_hash_encode_bwd_pts(const float* x, int64_t n_max, const unsigned long long* n_dev, const float* dy, int64_t dy_stride,
+                            const hbr_hash_geom* geom_host, float* dtable, int level_begin, int level_end, void* stream);
+
 /* ---- a10: calc_color (NeRF mode), helper.py:53-107, and its backward ------------------
  * One warp per ray.  rgb/sigma are addressed as rgb[(r*S+s)*rgb_stride + c], sigma[(r*S+s)*sigma_stride]
  * so both the reference's separate (R,S,3)/(R,S) tensors (strides 3,1) and the MLP's packed (R*S,4)
  * output (rgb = out, sigma = out+3, strides 4,4) are accepted.  dir_norm: (R) or NULL (=> scalar).
  * mask: optional (R*S) bytes; masked-out samples contribute sigma = rgb = 0 (vol_renderer.py:213-216).
- * C (R,3), w (R,S). */
+ * rowmap: optional (R*S) int32 from hbr_compact_samples: sample i reads rgb / sigma (and its gradients are written) at
+ * row rowmap[i] of the compacted tensors; rowmap[i] < 0 = skipped sample (as masked out).
+ * C (R,3), w (R,S).
+ * ert_tau: early ray termination, opt-in (<= 0 = off, the reference's behaviour): once the optical depth accumulated over
+ * whole 32-sample chunks exceeds ert_tau, the rest of the ray is skipped (weight 0, gradient 0).  At ert_tau = 104 the
+ * skipped transmittances exp(-depth) are exactly 0 in fp32, so results are bit-identical whenever the depth stays above
+ * the threshold afterwards (always for sigma >= 0).  Pass the same value to the backward. */
 int hbr_composite_fwd(const float* t, int64_t t_ray_stride, const float* rgb, int64_t rgb_stride,
                       const float* sigma, int64_t sigma_stride, const float* dir_norm, float dir_norm_scalar,
-                      const uint8_t* mask, int64_t R, int64_t S, float* C, float* w, void* stream);
+                      const uint8_t* mask, const int32_t* rowmap, int64_t R, int64_t S, float* C, float* w, float ert_tau,
+                      void* stream);
 int hbr_composite_bwd(const float* t, int64_t t_ray_stride, const float* rgb, int64_t rgb_stride,
                       const float* sigma, int64_t sigma_stride, const float* dir_norm, float dir_norm_scalar,
-                      const uint8_t* mask, int64_t R, int64_t S, const float* gC,
-                      float* drgb, int64_t drgb_stride, float* dsigma, int64_t dsigma_stride, void* stream);
+                      const uint8_t* mask, const int32_t* rowmap, int64_t R, int64_t S, const float* gC,
+                      float* drgb, int64_t drgb_stride, float* dsigma, int64_t dsigma_stride, float ert_tau,
+                      void* stream);
 
 /* ---- a11: hierarchical_sampling, helper.py:23-51 --------------------------------------------------
  * w (R,S) coarse weights (negatives treated as 0; written back clamped when clamp_in_place != 0,
@@ -247,6 +276,16 @@ int hbr_grid_interp(const float* vol, int C, int n0, int n1, int n2, const float
 int hbr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
                   double beta2, double eps, double weight_decay, int decoupled_weight_decay, int64_t step,
                   double inv_scale, const float* found_inf, void* stream);
+/* The same step with every per-step scalar on the device (torch's "capturable" contract), so that the optimiser can be
+ * captured in the CUDA graph of the training step and a step GradScaler skips does not advance the bias correction:
+ * hbr_adam_tick: *step_dev += 1 unless *found_inf != 0 (once per optimiser step, before the updates);
+ * hbr_adam_step_dev: reads the step count and the learning rate from the device; grad is multiplied by
+ * inv_scale / *grad_scale_dev (grad_scale_dev may be NULL). */
+int hbr_adam_tick(long long* step_dev, const float* found_inf, void* stream);
+int hbr_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr_dev,
+                      double beta1, double beta2, double eps, double weight_decay, int decoupled_weight_decay,
+                      const long long* step_dev, double inv_scale, const float* grad_scale_dev, const float* found_inf,
+                      void* stream);
 
 /* ---- 8f row 2: on-device ray generation, replacing the CPU TensorDataset + DataLoader of train_hash2.py:74-96,211-215 ----
  * get_od (helper.py:176-208) evaluated per requested ray: ray id = view * H*W + row * W + col (the order of the

@@ -416,3 +416,106 @@ def test_mse_pair_matches_torch(R, pair):
     assert torch.allclose(a.grad, a2.grad, rtol=1e-6, atol=1e-12)
     if pair:
         assert torch.allclose(b.grad, b2.grad, rtol=1e-6, atol=1e-12)
+
+
+def test_early_ray_termination_is_opt_in_and_exact():
+    """ERT (north star kernel 3): off by default; switched on it changes nothing while no ray reaches optical depth
+    104, and where rays do terminate the skipped samples had transmittance exactly 0 anyway: colours, weights and gradients
+    are bit-identical for non-negative densities."""
+    from human_body_reconstruction_b200 import ops
+    torch.manual_seed(4)
+    R, S = 300, 256
+    t = torch.sort(2 + 4 * torch.rand(R, S), dim=-1).values.to(DEV)
+    gC = torch.randn(R, 3, device=DEV)
+    for dense in (False, True):
+        out4 = torch.rand(R * S, 4, device=DEV)
+        out4[:, 3] *= 4000.0 if dense else 3.0              # dense: the depth passes 104 within the first chunks of most rays
+        res = []
+        for tau in (0.0, ops.ERT_TAU):
+            o = out4.clone().requires_grad_()
+            C, w = ops.CompositePacked.apply(o, t, 1.0, None, R, S, tau)
+            C.backward(gC)
+            res.append((C.detach(), w.detach(), o.grad.clone()))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+        if dense:
+            assert float((res[1][1][:, 64:] == 0).float().mean()) == 1.0      # the tail really was behind the termination
+    h = hbr()
+    g = load_golden("volrender.npz")
+    vr, enc, mlp = build_renderer(g)
+    assert vr.ert is False
+
+
+@pytest.mark.parametrize("fmt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("occ", [0.0, 0.35, 1.0])
+def test_live_occupancy_grid_compacted_path(fmt, occ):
+    """with Volume_Renderer.compact the samples outside occupied cells are skipped through encoder, MLP and
+    compositor (compacted sample lists, live count on the device).  Same numbers as evaluating every sample and zeroing the
+    masked ones (the reference's data flow, vol_renderer.py:211-216): colours and weights bit-identical, gradients to
+    atomic-order noise; and within the 16-bit tolerance of the oracle's masked render."""
+    from human_body_reconstruction_b200 import _lib
+    g = load_golden("volrender.npz")
+    S = 24
+    t = port.strat_t(g["near"], g["far"], S, g["coarse__u_t"])
+    torch.manual_seed(7)
+    grid = torch.rand(16, 16, 16) < occ                     # max_dim=64 -> a 16^3 grid
+    res = []
+    for compact in (False, True):
+        vr, enc, mlp = build_renderer(g, max_dim=64)
+        vr.bool_grid[...] = grid.to(DEV)
+        vr.compact = compact
+        mlp.tc_grad_scale = 4096.0 if fmt == torch.float16 else 1.0
+        _lib.STATS.reset()
+        with torch.autocast("cuda", dtype=fmt):
+            Cr, Cf, _ = vr.vol_render(mlp, g["rays_d"].to(DEV), g["rays_o"].to(DEV), num_samples=S, t=t.to(DEV),
+                                      dir_norm=g["dir_norm"].to(DEV), hierarchical=False)
+            loss = torch.nn.functional.mse_loss(Cr, g["gt"].to(DEV))
+        loss.backward()
+        used = "hbr_compact_samples" in _lib.STATS.calls
+        assert used == (compact and occ < 1.0)               # an all-True grid never masks: nothing to compact
+        res.append((Cr.detach(), torch.stack([e.weight.grad for e in enc.Embedding_list]),
+                    {k: q.grad.clone() for k, q in mlp.named_parameters()}))
+    assert torch.equal(res[0][0], res[1][0])
+    if occ > 0:
+        assert rel(res[1][1], res[0][1]) < 1e-5
+        for k in res[0][2]:
+            assert rel(res[1][2][k], res[0][2][k]) < 1e-4, k
+    else:
+        assert float(res[1][1].abs().max()) == 0.0 and float(res[1][0].abs().max()) == 0.0
+    # the oracle's masked render (fp32): 16-bit MLP tolerance
+    Cr_ref, _, _ = port.vol_render(mlp_params(g, "mlp__"), g["tables"], g["mu"], g["sigma"], g["scales"], g["rays_d"], g["rays_o"], t,
+                                   g["dir_norm"], 4, False, bool_grid=grid)
+    assert float((res[1][0].cpu() - Cr_ref).norm()) <= 1e-2 * float(Cr_ref.norm()) + 1e-6
+
+
+def test_update_grid_kernel_matches_reference_semantics():
+    """Volume_Renderer.update_grid on CUDA tensors (hbr_occupancy_update) == the reference's torch expressions
+    (vol_renderer.py:116-131), including the "nothing hit -> whole grid True" fallback."""
+    h = hbr()
+    g = load_golden("volrender.npz")
+    vr, enc, mlp = build_renderer(g, max_dim=64)
+    G = vr.grid_size
+    torch.manual_seed(3)
+    pts = (g["mu"] + torch.rand(5000, 3) * g["sigma"] * 0.55).to(DEV)
+    for case in ("some", "none"):
+        alpha = (torch.randn(5000) if case == "some" else -torch.rand(5000)).to(DEV)
+        vr.bool_grid[...] = False
+        vr.update_grid(pts, alpha.clone())
+        # reference expressions
+        q = (((pts - vr.mu) / vr.sigma_val) * G).long()
+        a = alpha.clone()
+        a[a <= 0] = 0
+        tmp = torch.zeros((G, G, G), device=DEV, dtype=torch.int32)
+        tmp.index_put_((q[:, 0], q[:, 1], q[:, 2]), torch.ceil(a).int(), accumulate=True)
+        want = torch.zeros((G, G, G), device=DEV, dtype=torch.bool)
+        if int((tmp > 0).sum()) == 0:
+            want[...] = True
+        else:
+            want[tmp > 0] = True
+        assert torch.equal(vr.bool_grid, want), case
+    # the refresh from the field marks cells and reports the occupied fraction
+    with torch.no_grad():
+        for e in enc.Embedding_list:
+            e.weight.mul_(0.0)
+    frac = vr.update_grid_from_field(mlp, threshold=-1e9)
+    assert frac == 1.0
+    assert vr.update_grid_from_field(mlp, threshold=1e9) == 0.0
