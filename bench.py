@@ -32,10 +32,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # algorithmic bytes per sample point, L=16 F=2 fp32
+# (the _rays entry points are the same kernels fed from the rays; they are accounted with the survey's figures although
+#  they move less: no 12-byte position read, 64-byte 16-bit feature rows instead of 128 -- the contract fixes the numerator)
 BYTES_PER_POINT = {
-    "hbr_hash_encode_fwd": 1164, "hbr_hash_encode_bwd": 1164, "hbr_mlp_fwd_f32": 144, "hbr_mlp_bwd_f32": 272,
+    "hbr_hash_encode_fwd": 1164, "hbr_hash_encode_bwd": 1164, "hbr_hash_encode_fwd_rays": 1164, "hbr_hash_encode_bwd_rays": 1164,
+    "hbr_hash_encode_fwd_pts": 1164, "hbr_hash_encode_bwd_pts": 1164, "hbr_mlp_fwd_f32": 144, "hbr_mlp_bwd_f32": 272,
     "hbr_mlp_fwd_tc": 144, "hbr_mlp_bwd_tc": 272, "hbr_composite_fwd": 16, "hbr_composite_bwd": 32,
-    "hbr_field_fwd_tc": 1164 + 144, "hbr_field_bwd_tc": 1164 + 272,
+    "hbr_field_fwd_tc": 1164 + 144, "hbr_field_bwd_tc": 1164 + 272, "hbr_field_bwd_rays_tc": 1164 + 272,
 }
 # algorithmic FLOP per point of MLP_3D: 27 904 forward, 2 x that for the backward GEMMs (dgrad + wgrad)
 FLOPS_PER_POINT = {"hbr_mlp_fwd_tc": 27904, "hbr_mlp_bwd_tc": 55808, "hbr_mlp_fwd_f32": 27904, "hbr_mlp_bwd_f32": 55808}
@@ -361,6 +364,9 @@ def run_b200(args):
                              sigma_val=sigma, mu=mn)
     if args.fuse_field:
         vr.fuse_field = True                                              # encoder + MLP in one kernel per direction
+    if args.no_fuse_scatter:
+        from human_body_reconstruction_b200 import vol_renderer as _vrm
+        _vrm.FUSE_SCATTER = False                                         # MLP backward and hash-grid scatter-add as two kernels
     reducer = None
     if world > 1:
         # the gradient exchange: "peer" = this package's one-kernel all-reduce over NVLink peer memory (csrc/comm.cu),
@@ -496,8 +502,11 @@ def run_b200(args):
     if world > 1:
         tdist.all_reduce(tms, op=tdist.ReduceOp.MAX)
     dev_ms, e2e_ms, lo_ms, hi_ms = (float(v) for v in tms)
+    occ = occupancy_leg(args, dev, vr, nerf, params, rays, resident_packed if gs is not None else None, flush, amp, amp_dtype,
+                        mn, sigma) if (world == 1 and amp and gs is not None and not args.no_occupancy) else None
     c3 = c3_leg(args, world, rank, dev, vr, nerf, enc, mlp, params, c2w, K, H, W, amp, amp_dtype, barrier) if args.c3 else None
     grad_check = grad_check_leg(hdist, tdist, reducer, enc, mlp, params, step, resident, world, rank, args) if world > 1 else None
+    grid = grid_leg(args, hbr, hdist, world, rank, dev, mx, mn, sigma, barrier) if args.grid else None
     if rank != 0:
         _finish(world)
         return
@@ -554,10 +563,14 @@ def run_b200(args):
         line["hash_encode_mpts_per_s"] = (n_pts / (c / args.steps)) / (m * 1e-3) / 1e6
     if sampler is not None:
         line["device_sampler_e2e"] = sampler
+    if occ is not None:
+        line["occupancy_grid"] = occ
     if c3 is not None:
         line["c3"] = c3
     if grad_check is not None:
         line["grad_check"] = grad_check
+    if grid is not None:
+        line["grid"] = grid
     if reducer is not None:
         line["allreduce_bytes_per_step"] = 4 * sum(p.numel() for p in params)      # flat table + MLP gradients, fp32
         region = getattr(reducer, "region", None)
@@ -575,6 +588,55 @@ def run_b200(args):
             line["reference_eager_b200"] = reference_on_b200(args, rays)
     print(json.dumps(line), flush=True)
     _finish(world)
+
+
+def occupancy_leg(args, dev, vr, nerf, params, rays, resident_packed, flush, amp, amp_dtype, mn, sigma):
+    """the same step with the occupancy grid LIVE (Volume_Renderer.compact): a synthetic lego-sized
+    object -- the cells whose centre lies in the cube |x|,|y|,|z| <= 1 around the origin the cameras look at -- is marked
+    occupied, every sample outside it is skipped through encoder, MLP and compositor.  Graph replay, L2 flushed, CUDA events."""
+    try:
+        from human_body_reconstruction_b200.graph import GraphedStep
+        G = vr.grid_size
+        c = (torch.arange(G, device=dev, dtype=torch.float32) + 0.5) / G * float(sigma)
+        ax = [c + float(mn[k]) for k in range(3)]
+        inside = [(a.abs() <= 1.0) for a in ax]
+        grid = inside[0][:, None, None] & inside[1][None, :, None] & inside[2][None, None, :]
+        vr.bool_grid[...] = grid
+        vr.compact = True
+        from human_body_reconstruction_b200 import ops
+        o, d = resident_packed[0][:3 * rays].view(rays, 3), resident_packed[0][3 * rays:6 * rays].view(rays, 3)
+        t = torch.linspace(args.near, args.far, args.samples, device=dev)
+        mu_h, sig_h = vr._norm_host()
+        live = float(ops.compact_samples(o, d, t, vr.bool_grid, mu_h, sig_h)[3].item()) / (rays * args.samples)
+        gs = GraphedStep(vr, nerf, params, rays, args.samples, False, dev, autocast=amp, autocast_dtype=amp_dtype)
+        gs.load(resident_packed[0])
+        gs.capture()
+        for k in range(3):
+            gs(resident_packed[k % len(resident_packed)])
+        torch.cuda.synchronize()
+        ev = []
+        for k in range(args.steps):
+            if flush is not None:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gs(resident_packed[k % len(resident_packed)])
+            e1.record()
+            ev.append((e0, e1))
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+        vr.bool_grid[...] = True
+        vr.compact = False
+        for p in params:
+            p.grad = None
+        return {"value": rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "occupied_cells_frac": float(grid.float().mean()),
+                "live_samples_frac": live, "steps": args.steps,
+                "note": "synthetic occupancy: cube |x|,|y|,|z| <= 1 around the scene centre marked occupied in the "
+                        f"{G}^3 grid; samples outside are skipped (compacted lists); same rays, same step otherwise"}
+    except Exception as e:                                                 # noqa: BLE001
+        vr.bool_grid[...] = True
+        vr.compact = False
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def c3_leg(args, world, rank, dev, vr, nerf, enc, mlp, params, c2w, K, H, W, amp, amp_dtype, barrier):
@@ -597,14 +659,17 @@ def c3_leg(args, world, rank, dev, vr, nerf, enc, mlp, params, c2w, K, H, W, amp
         for _ in range(3):
             step()
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         nstep = 5
-        e0.record()
+        evs = []
         for _ in range(nstep):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             step()
-        e1.record()
+            e1.record()
+            evs.append((e0, e1))
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1) / nstep], device=dev, dtype=torch.float64)
+        per_step = [a.elapsed_time(b) for a, b in evs]
+        ms = torch.tensor([sum(per_step) / nstep], device=dev, dtype=torch.float64)
         if world > 1:
             tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
         ms = float(ms)
@@ -616,8 +681,76 @@ def c3_leg(args, world, rank, dev, vr, nerf, enc, mlp, params, c2w, K, H, W, amp
         return {"workload": f"configs[2]: {rays * world} rays/step global = {rays} rays x {args.samples} samples per GPU on {world} GPU(s), "
                             f"T=2^{args.hash_size}, fwd+bwd" + (", gradients all-reduced" if world > 1 else " (single-GPU rate on 2^17 rays)"),
                 "rays_global": rays * world, "rays_per_gpu": rays, "ms_per_step": ms, "value": rays * world / (ms * 1e-3), "unit": "rays/s",
-                "steps": nstep, "warmup": 3, "launch": "eager",
+                "steps": nstep, "warmup": 3, "launch": "eager", "ms_each_step_this_rank": per_step,
                 "step_roofline_frac_per_gpu": STEP_BYTES_PER_POINT * n_pts / (ms * 1e-3) / 1e9 / measured_peaks()[0]}
+    except Exception as e:                                                 # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
+def grid_leg(args, hbr, hdist, world, rank, dev, mx, mn, sigma, barrier):
+    """BASELINE configs[3]: the nerf2mesh density-grid query (nerf2mesh.py:27-40,69-87) at 512^3 over the scene bounds plus
+    marching cubes (:98), the grid sharded by slabs of its outermost axis over the ranks (each rank: its planes + one halo
+    plane, vertices owned by the lower end point of each crossing edge, counts all-gathered).  Field: a smooth synthetic
+    one (coarse hash levels only) so that the iso-surface looks like an object, not noise.  CUDA events, max over ranks."""
+    import torch.distributed as tdist
+    try:
+        res, L, F, T = args.grid_res, 16, 2, 2 ** args.hash_size
+        torch.manual_seed(1)
+        enc = hbr.HashEncoder(N_min=16, N_max=float(args.max_res), L=L, F=F, T=T, dim=3, mu=mn.to(dev), sigma=sigma.to(dev))
+        with torch.no_grad():
+            for l, e in enumerate(enc.Embedding_list):
+                e.weight.mul_(2e5 if l < 4 else 2e3)                     # smooth blobs: the coarse levels carry the shape
+        mlp = hbr.MLP_3D(num_sig=2, num_col=2, L=L, F=F, d_view=24, max_bound=mx, min_bound=mn)
+        enc, mlp = enc.to(dev), mlp.to(dev)
+        lo, hi = mn.double().tolist(), mx.double().tolist()
+        i0, i1 = hdist.slab_range(res, rank, world)
+        halo = min(res, i1 + 1)
+
+        def run():
+            dens = hbr.mesh.density_grid(enc, mlp, None, lo, hi, res, i_begin=i0, i_end=halo)       # (planes + halo, res, res)
+            return dens
+
+        dens = run()
+        iso = torch.tensor([float(dens.float().median())], device=dev)
+        if world > 1:
+            tdist.broadcast(iso, 0)
+        iso = float(iso)
+        barrier()
+        ts, tc = [], []
+        for _ in range(3):
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            dens = run()
+            e1.record()
+            counts = hbr.ops.mc_count(dens, iso, 0, i1 - i0)               # vertices / triangles owned by this slab
+            e2.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+            tc.append(e1.elapsed_time(e2))
+        mine = [int(v) for v in counts.tolist()]
+        allc = hdist.allgather_counts(mine)
+        ms = torch.tensor([min(ts), min(tc)], device=dev, dtype=torch.float64)
+        if world > 1:
+            tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
+        pts = res ** 3
+        peak = measured_peaks()[0]
+        roof_ms = 1034 * pts / world / (peak * 1e9) * 1e3
+        out = {"workload": f"configs[3]: {res}^3 density grid over the scene bounds (fp16 positions, fp32 field: encoder + density head) "
+                           f"+ marching-cubes count, {world} z-slab(s)", "density_ms": float(ms[0]), "mc_count_ms": float(ms[1]),
+               "points": pts, "Mpts_per_s": pts / float(ms[0]) / 1e3, "roofline_ms_per_gpu": roof_ms, "frac": roof_ms / float(ms[0]),
+               "algorithmic_bytes_per_point": 1034, "iso": iso, "vertices": sum(c[0] for c in allc), "triangles": sum(c[1] for c in allc),
+               "per_rank_counts": allc}
+        if world == 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            verts, faces = hbr.mesh.marching_cubes(dens, iso)
+            e1.record()
+            torch.cuda.synchronize()
+            out["mc_emit_ms"] = e0.elapsed_time(e1)
+            out["emitted"] = [int(verts.shape[0]), int(faces.shape[0])]
+        del dens
+        torch.cuda.empty_cache()
+        return out
     except Exception as e:                                                 # noqa: BLE001
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
@@ -724,6 +857,11 @@ def main():
     ap.add_argument("--peer-chunks", type=int, default=2, help="> 0: all-reduce level chunks on a side stream while the "
                     "remaining chunks' scatter-add runs; 0: one all-reduce behind the backward pass")
     ap.add_argument("--fuse-field", action="store_true", help="use the fused encoder+MLP kernels (hbr_field_*_tc)")
+    ap.add_argument("--no-fuse-scatter", action="store_true", help="A/B: run the MLP backward and the hash-grid scatter-add as "
+                    "two kernels (default on one GPU: hbr_field_bwd_rays_tc, the scatter-add on dedicated warps of the MLP kernel)")
+    ap.add_argument("--no-grid", dest="grid", action="store_false", help="skip the configs[3] leg (512^3 density grid + marching cubes)")
+    ap.add_argument("--grid-res", type=int, default=512)
+    ap.add_argument("--no-occupancy", action="store_true", help="skip the live-occupancy-grid leg (8f row 3)")
     ap.add_argument("--repeats", type=int, default=5, help="timed regions of K steps each; value = their median")
     ap.add_argument("--no-c3", dest="c3", action="store_false", help="skip the configs[2] leg (2^20 rays/step global; 2^17 at N=1)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],

@@ -981,8 +981,14 @@ struct BwdSmem {
   static constexpr int cin = c1 + 9 * kCg;
   static constexpr int dzs = kAliasDzs ? cin + 5 * kCg : cin + kTile * KCP * 2;
   static constexpr int grp_bytes = dzs + 2 * kCg;
-  static constexpr int off_bar = off_grp + G * grp_bytes;              // full[G], doneA[G], doneB[G], startB[G]
-  static constexpr int total = off_bar + 4 * G * 8 + 16;
+  // scatter variant with one tile group (SCAT = 11): two 16 KB slots for the d(feature) tiles on their way to the scatter
+  // warps (with two groups the slot is the group's own dead h2 region)
+  static constexpr int ring_slot = kTile * 32 * 4;
+  static constexpr int off_ring = off_grp + G * grp_bytes;
+  static constexpr int off_bar = off_ring + (G == 1 && K0P == 32 ? 2 * ring_slot : 0);   // full[G], doneA[G], doneB[G], startB[G], dfull[2], dempty[2]
+  // normalised sample positions of the scatter warps' current / next tile: [2][128 points][3] fp32
+  static constexpr int off_pos = off_bar + (4 * G + 4) * 8 + 16;
+  static constexpr int total = off_pos + 2 * kTile * 3 * 4;
   static_assert(total <= 232448, "shared memory budget exceeded");
 };
 
@@ -1015,14 +1021,15 @@ struct BwdTmem {
 //      The accumulators are split over the CTA's tile-group warps (a warp reads the TMEM lane quarter warp % 4).
 template <int K0P, int KCP, int WORK>
 __device__ __noinline__ void flush_gradients(uint32_t tbase, int warp, int lane, int ngroups, const MlpLayout& m,
-                                             bool has_tiles, float* __restrict__ dparams, float* __restrict__ grad_rows, float ginv) {
+                                             bool has_tiles, float* __restrict__ dparams, float* __restrict__ grad_rows, float ginv,
+                                             int nthreads) {
   using TM = BwdTmem<K0P, KCP, WORK>;
   constexpr bool kCinOne = TM::kCinOne;
   if (dparams == nullptr) return;
   float* row = grad_rows != nullptr ? grad_rows + (size_t)blockIdx.x * Scratch<K0P, KCP>::kRowFloats : nullptr;
   if (!has_tiles) {
     if (row != nullptr)
-      for (int e = threadIdx.x; e < m.total; e += blockDim.x) row[e] = 0.f;
+      for (int e = threadIdx.x; e < m.total; e += nthreads) row[e] = 0.f;      // called by the first `nthreads` threads
     return;
   }
   if (warp >= 4 * ngroups) return;
@@ -1088,8 +1095,31 @@ __device__ __noinline__ void flush_gradients(uint32_t tbase, int warp, int lane,
   }
 }
 
-template <int K0P, int KCP, int G, bool TRACE = false, bool ENC = false>
-__global__ void __launch_bounds__(G * kTile + 32, 1)
+// SCAT > 0 (= 7): the hash-grid scatter-add of the tile's d(features) (hash_grid.cu: hash_bwd_kernel) runs INSIDE this
+// kernel on SCAT dedicated warps: a tile group leaves its 128 x 32 fp32 d(feature) tile in shared memory (the dead h2
+// region, [level][point] float2), the scatter warps pull their values into registers, hand the buffer back and issue the
+// run-merged red.global.add while the groups walk the next tiles' layer chains.  The chain is latency-bound (tensor pipe
+// ~25 % busy, LSU idle), the scatter is bound by the red.global path: side by side on one SM they overlap instead of
+// adding up, and the (N,32) fp32 d(feature) tensor is neither written nor re-read.
+// Work split of the scatter warps: a tile is 64 units (32-point slice s, level l); warp w of 7 takes the units
+// u = w, w + 7, ... (u = 4 l + s) -- a unit is exactly what one warp of hash_bwd_kernel does for one level.
+// Registers: the register file is per SM sub-partition (4 warps of this CTA on each: 2 tile-group warps + 2 others), so
+// the CTA is 16 warps = 512 threads launched at 128 registers, and setmaxnreg moves them: warps 8..15 (7 scatter warps
+// + the weight-gradient issuer: setmaxnreg works on whole warpgroups) drop to kScatRegs, the tile groups rise to
+// kGroupRegs; per sub-partition 2 x 168 + 2 x 88 = 512 = what the launch allocated.
+constexpr int kGroupRegs = 168;
+// G = 2, SCAT = 7: 2 x 168 + 2 x 88 = 512 per sub-partition;  G = 1, SCAT = 11: 168 + 3 x 112 = 504
+__host__ __device__ constexpr int scat_regs(int G) { return G == 2 ? 88 : 112; }
+
+// (x - mu) / sigma is level-independent: the scatter warps keep it per slice and finish cell_of per level
+__device__ __forceinline__ void cell_of_norm(float u0, float scale, long long& cell, float& frac) {
+  const float u = __fmul_rn(u0, scale);
+  cell = __float2ll_rz(u);
+  frac = __fsub_rn(u, __ll2float_rn(cell));
+}
+
+template <int K0P, int KCP, int G, bool TRACE = false, bool ENC = false, int SCAT = 0>
+__global__ void __launch_bounds__(G * kTile + SCAT * 32 + 32, 1)
 mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const float* __restrict__ dirs, long long dir_group,
                   long long n_arg, const float* __restrict__ params, int in0, int dv, const float* __restrict__ out,
                   const float* __restrict__ dout, float* __restrict__ dfeat, long long dfeat_stride,
@@ -1117,8 +1147,11 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   uint8_t* wsm = sm;
   float* bias = reinterpret_cast<float*>(sm + SM::off_bias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM::off_bar);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4 * G);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4 * G + 4);
+  uint64_t* dfull = bars + 4 * G;                                        // [2] d(feature) slot written (128 arrivals)
+  uint64_t* dempty = bars + 4 * G + 2;                                   // [2] slot read by every scatter lane
   const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  constexpr int kIssuerWarp = 4 * G + SCAT;
   if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2000] = clock64();
 
   if (warp == 0) tmem_alloc<512>(tslot);
@@ -1127,6 +1160,10 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       mbar_init(bars + G + g, 1);
       mbar_init(bars + 2 * G + g, 1);
       mbar_init(bars + 3 * G + g, 1);
+    }
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(dfull + q, kTile);
+      mbar_init(dempty + q, SCAT > 0 ? SCAT * 32 : 1);
     }
     fence_mbar_init();
   }
@@ -1172,7 +1209,7 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   }
   const long long kmax = nt[0];                  // the slot of group 0 never has fewer tiles than a later group's
 
-  if (warp >= 4 * G) {
+  auto wgrad_issuer = [&]() {
     // ===== weight-gradient issuer (one converged warp): every weight/bias-gradient GEMM of the CTA -- the accumulators
     // all tiles share -- comes from this one thread sequence, visiting the groups in a fixed order.  It waits on
     // startB[g], committed by the group right behind the stage's dgrad (so the chain-critical dgrad never queues behind a
@@ -1217,8 +1254,160 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       HBR_WGRAD_STAGE(issue_wgrad(tb + TM::g0, h1a, x0a, TM::n0, acc));     // dZ = h1 tile, input x0 | ones
       first = false;
     }
+  };
+  if (SCAT > 0 && warp >= 4 * G) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(scat_regs(G)));
+    if (warp == kIssuerWarp) {
+      wgrad_issuer();
+    } else {
+      // ===== scatter warps: the hash-grid backward of every tile of this CTA (same arithmetic as hash_bwd_kernel) =====
+      // ROLLED loops on purpose: the tile groups' layer chain is ~115 KB of straight-line code; with the unit body unrolled
+      // (10 units x 2 groups = another ~90 KB) both instruction streams missed the instruction cache all the time
+      // (measured: 435 us for the kernel against 153 + 169 us for the two separate kernels).
+      const int sw = warp - 4 * G;                                        // 0 .. SCAT-1
+      constexpr int kUnits = 64;
+      uint32_t fpar = 0;                                                  // bit g: parity of dfull[g]
+      int pbuf = 0;
+#pragma unroll 1
+      for (long long kg = 0; kg < kmax * G; ++kg) {
+        const long long k = kg / G;
+        const int g = (int)(kg - k * G);
+        if (k >= (g == 0 ? nt[0] : nt[G - 1])) continue;
+        const long long tile = (long long)g * gridDim.x + blockIdx.x + k * nslots;
+        // normalised positions ((o + d t) - mu) / sigma of the tile's 128 points: warp w < 4 forms those of slice w and
+        // leaves them in shared memory for everybody (every warp forming all four slices itself cost ~3 k cycles per tile,
+        // on every warp at the same time: the scatter warps alone ran 250 us whether they were 7 or 11)
+        float* pos = reinterpret_cast<float*>(sm + SM::off_pos) + pbuf * (kTile * 3);
+        pbuf ^= 1;
+        if (sw < 4) {
+          const long long gp = tile * kTile + sw * 32 + lane;
+          float x3[3] = {0.f, 0.f, 0.f};
+          if (gp < n) {
+            long long ray, smp;
+            if (gp < (1LL << 31) && enc.S < (1LL << 31)) {
+              const unsigned q = (unsigned)gp / (unsigned)enc.S;
+              ray = q; smp = (long long)((unsigned)gp - q * (unsigned)enc.S);
+            } else {
+              ray = gp / enc.S; smp = gp - ray * enc.S;
+            }
+            const float tt = __ldg(enc.rt + ray * enc.t_stride + smp);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              const float x = __fadd_rn(__ldg(enc.ro + ray * 3 + a), __fmul_rn(__ldg(enc.rd + ray * 3 + a), tt));
+              x3[a] = __fdiv_rn(__fsub_rn(x, geom.mu[a]), geom.sigma);
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < 3; ++a) pos[(sw * 32 + lane) * 3 + a] = x3[a];
+        }
+        asm volatile("bar.sync 3, %0;" ::"n"(SCAT * 32) : "memory");
+        // slot of this tile: the group's h2 region (two groups), or the ring slot k & 1 (one group)
+        const int slot = G == 2 ? g : (int)(k & 1);
+        const float2* stg = reinterpret_cast<const float2*>(G == 2 ? sm + SM::off_grp + g * SM::grp_bytes + SM::h2
+                                                                   : sm + SM::off_ring + slot * SM::ring_slot);
+        mbar_wait(dfull + slot, (fpar >> slot) & 1u);
+        fpar ^= 1u << slot;
+        // two units per iteration (u and u + SCAT), written side by side: a unit is one long dependent chain (cells ->
+        // run test -> log-step shuffle merge -> reductions), and seven warps of such chains leave the SM's issue slots
+        // mostly empty (measured: 319 us for the kernel with the reductions compiled out) -- two independent chains per
+        // warp give the scheduler twice the work to pick from
+#pragma unroll 1
+        for (int ua = sw; ua < kUnits; ua += 2 * SCAT) {
+          int cx[2][3];
+          float val[2][8][2];
+          bool valid[2], head[2];
+          int end[2], lvl_of[2];
+          int maxrun = 0;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int u = ua + h * SCAT;
+            const bool live = u < kUnits;                                 // warp-uniform; the last pair of a warp may be half
+            const int uc = live ? u : ua;
+            const int l = uc >> 2, sl = uc & 3;
+            lvl_of[h] = l;
+            valid[h] = live && tile * kTile + sl * 32 + lane < n;
+            const float2 gy = stg[l * kTile + sl * 32 + lane];
+            float un[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) un[a] = pos[(sl * 32 + lane) * 3 + a];
+            const float s = geom.scale[l];
+            // cells as 32-bit integers: the power-of-two hash and the run test below only look at the low 32 bits of the
+            // reference's int64 cell, and trunc / frac agree with the int64 path whenever |u| < 2^31 (else: that path)
+            float fr[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              const float uu = __fmul_rn(un[a], s);
+              if (fabsf(uu) < 2147483648.f) {
+                cx[h][a] = __float2int_rz(uu);
+                fr[a] = __fsub_rn(uu, __int2float_rn(cx[h][a]));
+              } else {
+                const long long c64 = __float2ll_rz(uu);
+                cx[h][a] = (int)(uint32_t)(unsigned long long)c64;
+                fr[a] = __fsub_rn(uu, __ll2float_rn(c64));
+              }
+            }
+            float w[8];
+            corner_weights(fr[0], fr[1], fr[2], w);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { val[h][c][0] = w[c] * gy.x; val[h][c][1] = w[c] * gy.y; }
+            // runs of consecutive lanes in the same cell (a ray crosses a cell in one contiguous stretch)
+            const int pcx = __shfl_up_sync(kFull, cx[h][0], 1);
+            const int pcy = __shfl_up_sync(kFull, cx[h][1], 1);
+            const int pcz = __shfl_up_sync(kFull, cx[h][2], 1);
+            const int pvalid = __shfl_up_sync(kFull, (int)valid[h], 1);
+            head[h] = lane == 0 || !valid[h] || !pvalid || pcx != cx[h][0] || pcy != cx[h][1] || pcz != cx[h][2];
+            const unsigned heads = __ballot_sync(kFull, head[h]);
+            const unsigned above = lane == 31 ? 0u : (heads & (0xfffffffeu << lane));
+            end[h] = above ? (__ffs(above) - 1) : 32;                     // first lane of the next run
+            maxrun = max(maxrun, head[h] ? end[h] - lane : 0);
+          }
+          maxrun = __reduce_max_sync(kFull, maxrun);
+          for (int d = 1; d < maxrun; d <<= 1) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                  const float t = __shfl_down_sync(kFull, val[h][c][f], d);
+                  if (lane + d < end[h]) val[h][c][f] += t;
+                }
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (head[h] && valid[h]) {
+              uint32_t idx[8];
+              {
+                const uint32_t a0 = (uint32_t)cx[h][0], b0 = (uint32_t)cx[h][1] * kPrimeY, c0 = (uint32_t)cx[h][2] * kPrimeZ;
+                const uint32_t aa[2] = {a0, a0 + 1u}, bb[2] = {b0, b0 + kPrimeY}, cc[2] = {c0, c0 + kPrimeZ};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) idx[q] = (aa[q & 1] ^ bb[(q >> 1) & 1] ^ cc[(q >> 2) & 1]) & (geom.T - 1);
+              }
+              float* lvl = enc.dtable + (size_t)lvl_of[h] * geom.T * 2;
+              if (!(cx[h][0] & 1)) {   // even x: corners (x, x+1) share one aligned 16-byte slot, one red.global.add.v4.f32
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                  const bool odd = idx[c] & 1;
+                  const float4 q = odd ? make_float4(val[h][c + 1][0], val[h][c + 1][1], val[h][c][0], val[h][c][1])
+                                       : make_float4(val[h][c][0], val[h][c][1], val[h][c + 1][0], val[h][c + 1][1]);
+                  atomicAdd(reinterpret_cast<float4*>(lvl) + (idx[c] >> 1), q);
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                  atomicAdd(reinterpret_cast<float2*>(lvl) + idx[c], make_float2(val[h][c][0], val[h][c][1]));
+              }
+            }
+          }
+        }
+        mbar_arrive(dempty + slot);                                      // every unit's values have been read: the slot may be rewritten
+      }
+    }
+  } else if (SCAT == 0 && warp >= 4 * G) {
+    wgrad_issuer();
   } else {
     // ===== tile group =====
+    if (SCAT > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kGroupRegs));
     const int g = warp >> 2;
     const int r = threadIdx.x & (kTile - 1);
     uint8_t* gb = sm + SM::off_grp + g * SM::grp_bytes;
@@ -1234,7 +1423,8 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     const uint32_t taddr = tgrp + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t taddr_a = taddr + 64;
     const uint32_t wa = a4_of(wsm), x0a = a4_of(x0);
-    uint32_t dphase = 0, bphase = 0;
+    uint32_t dphase = 0, bphase = 0, ephase = 0;
+    (void)ephase;
 #define HBR_BSTAGE(BWD, BODY) HBR_BSTAGE_T(BODY, {})
     // forward-recompute stage; TRAIL runs between the issue and the wait (work the chain does not need)
 #define HBR_BSTAGE_T(BODY, ...)                                            \
@@ -1362,7 +1552,13 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
                    { store_tile64(r, h1, dzt); });
       relu_bias_to_tmem64(taddr, bias + 64, taddr_a, dzt);
       HBR_BSTAGE_T(issue_fwd_ts(tgrp, tgrp_a, wa + WO::w2 / 16, 16, 64, false),                 // F2
-                   { store_tile64(r, h2, dzt); });
+                   {
+                     if (SCAT > 0 && G == 2 && tgi > 0) {   // the scatter warps have taken the previous tile's d(features) out of h2
+                       mbar_wait(dempty + g, ephase & 1u);
+                       ephase ^= 1u;
+                     }
+                     store_tile64(r, h2, dzt);
+                   });
       {
         float o16[16];
         tmem_ld<16>(taddr, o16);
@@ -1450,7 +1646,21 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       masked_dz_to_tmem64(taddr, r, h1, taddr_a, dzt);
       HBR_BSTAGE_BWD(issue_dgrad_ts(tgrp, tgrp_a, wa + WO::w0 / 16, 64, K0P),                   // sig_model.0: work[0,K0P) = d(feat)
                      { HBR_WAIT_B(); store_tile64(r, h1, dzt); });
-      if (ENC) {
+      if (SCAT > 0) {
+        // d(features) of this row -> the (dead) h2 region as [level][point] float2 (conflict-free both ways), then the
+        // scatter warps take over: 128 arrivals (release) on dfull
+        float df[K0P];
+        tmem_ld<K0P>(taddr, df);
+        const int slot = G == 2 ? g : (tgi & 1);
+        if (G == 1 && tgi >= 2) {                  // ring slot: its previous tile (two tiles back) has been read
+          mbar_wait(dempty + slot, (ephase >> slot) & 1u);
+          ephase ^= 1u << slot;
+        }
+        float2* stg = reinterpret_cast<float2*>(G == 2 ? h2 : sm + SM::off_ring + slot * SM::ring_slot);
+#pragma unroll
+        for (int l = 0; l < K0P / 2; ++l) stg[l * kTile + r] = make_float2(df[2 * l] * ginv, df[2 * l + 1] * ginv);
+        mbar_arrive(dfull + slot);
+      } else if (ENC) {
         float df[K0P];
         tmem_ld<K0P>(taddr, df);
 #pragma unroll
@@ -1494,7 +1704,7 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   fence_after_sync();
   if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2002] = clock64();
 
-  flush_gradients<K0P, KCP, 2 * kGrpCols>(tbase, warp, lane, G, m, cta_tiles > 0, dparams, grad_rows, ginv);
+  if (warp < 4 * G) flush_gradients<K0P, KCP, 2 * kGrpCols>(tbase, warp, lane, G, m, cta_tiles > 0, dparams, grad_rows, ginv, 4 * G * 32);
   fence_before_sync();
   __syncthreads();
   if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2003] = clock64();
@@ -1522,7 +1732,7 @@ static int launch_fwd_tc(const float* feat, int64_t feat_stride, const float* di
   return HBR_OK;
 }
 
-template <int K0P, int KCP, int G, bool ENC>
+template <int K0P, int KCP, int G, bool ENC, int SCAT = 0>
 static int launch_bwd_tc(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                          const float* params, int in0, int dv, const float* out, const float* dout, float* dfeat,
                          int64_t dfeat_stride, float* ddirs, float* dparams, uint8_t* scratch, const EncArgs& enc,
@@ -1533,9 +1743,23 @@ static int launch_bwd_tc(const float* feat, int64_t feat_stride, const float* di
   const int grid = (int)min64(ceil_div(ceil_div(n, kTile), G), sm_count());
   const bool rows = scratch != nullptr && dparams != nullptr && grid <= SC::kMaxRows;
   if (scratch != nullptr && !image_ready) mlp_prep_kernel<K0P, KCP><<<kPrepCtas, 256, 0, st>>>(params, in0, dv, scratch);
-  auto kern = mlp_bwd_tc_kernel<K0P, KCP, G, false, ENC>;
+  auto kern = mlp_bwd_tc_kernel<K0P, KCP, G, false, ENC, SCAT>;
   HBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, G * kTile + 32, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, dout, dfeat,
+  if constexpr (SCAT > 0) {
+    // the setmaxnreg budget (see the kernel): 16 warps, 4 per SM sub-partition, launched at `regs` registers per thread;
+    // afterwards every sub-partition holds 2 tile-group warps + 2 scatter / issuer warps
+    static_assert((G == 2 && SCAT == 7) || (G == 1 && SCAT == 11), "register budget: 16 warps, 4 per sub-partition");
+    constexpr int kScatRegs = scat_regs(G);
+    static int regs = 0;
+    if (regs == 0) {
+      cudaFuncAttributes fa;
+      HBR_CUDA(cudaFuncGetAttributes(&fa, kern));
+      regs = fa.numRegs;
+    }
+    HBR_REQUIRE(regs >= kScatRegs && regs <= kGroupRegs && 4 * regs <= 512 && G * kGroupRegs + (4 - G) * kScatRegs <= 4 * regs,
+                "fused backward kernel compiled with %d registers per thread: the setmaxnreg budget does not hold", regs);
+  }
+  kern<<<grid, G * kTile + SCAT * 32 + 32, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, dout, dfeat,
                                            dfeat_stride, ddirs, dparams, scratch,
                                            rows ? reinterpret_cast<float*>(scratch + SC::off_grad) : nullptr, nullptr, enc, geom, gscale, feat16, n_dev, dir_rows);
   if (rows && !defer_reduce) {

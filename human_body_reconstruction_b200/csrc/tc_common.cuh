@@ -237,6 +237,11 @@ struct EncArgs {
   const float* table;            // (L,T,2) fp32                      (forward)
   float* dtable;                 // (L,T,2) fp32, accumulated into    (backward)
   uint16_t* feat16;               // (n,32) bf16 features: written by the forward, re-read by the backward recompute
+  // scatter warps of the backward kernel (SCAT): sample positions formed from the rays, p = o + d * t (vol_renderer.py:165)
+  const float* ro;               // (R,3)
+  const float* rd;               // (R,3)
+  const float* rt;               // (S) shared (t_stride = 0) or (R,S) per ray
+  long long S, t_stride;
 };
 
 }  // namespace tc

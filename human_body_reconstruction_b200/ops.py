@@ -523,6 +523,32 @@ def field_bwd_tc(x, geom: HashGeom, dirs, dir_group, params, dims: MlpDims, feat
     return ddirs
 
 
+def field_bwd_rays_tc(feat16, rays_o, rays_d, t, geom: HashGeom, dirs, params, dims: MlpDims, out, dout, dtable, want_ddirs,
+                      dparams, operand: int = HBR_BF16, grad_scale: float = 1.0, defer_reduce: bool = False):
+    """mlp_bwd_tc + hash_encode_bwd_rays in one kernel (scatter warps beside the tile groups): dtable (L,T,2) and dparams are
+    accumulated into; returns ddirs or None."""
+    require_cuda(feat16, rays_o, rays_d, t, dirs, params, out, dout, dtable)
+    R, S = rays_o.shape[0], t.shape[-1]
+    ddirs = torch.zeros_like(dirs) if want_ddirs else None
+    scratch = mlp_tc_scratch(dims, feat16.device)
+    key = _image_key(params, operand)
+    ready = 1 if _tc_image.get(id(scratch)) == key else 0
+    check(lib().hbr_field_bwd_rays_tc(ptr(feat16), ptr(rays_o), ptr(rays_d), ptr(t), _t_stride(t, S), R, S, C.byref(geom),
+                                      ptr(dirs), ptr(params), C.byref(dims), operand, ptr(out), ptr(dout), ptr(dtable),
+                                      ptr(ddirs), ptr(dparams), float(grad_scale), ptr(scratch), ready,
+                                      1 if defer_reduce else 0, stream()))
+    _lib.STATS.launches -= ready + (1 if defer_reduce else 0)
+    _tc_image[id(scratch)] = key
+    return ddirs
+
+
+def field_scatter_supported(geom: HashGeom, dims: MlpDims) -> bool:
+    """The configuration family hbr_field_bwd_rays_tc covers (the reference's: F = 2, L = 16, power-of-two T, d_view <= 25)."""
+    T = int(geom.T)
+    return (geom.F == 2 and geom.L == 16 and geom.E == 0 and T >= 2 and (T & (T - 1)) == 0 and dims.in0 == 32
+            and dims.d_view + 15 <= 40)
+
+
 def debug_umma(mode: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, operand: int = HBR_BF16) -> torch.Tensor:
     """Self test of the UMMA operand modes (probe library, tests only)."""
     D = torch.empty((M, N), device=A.device, dtype=torch.float32)

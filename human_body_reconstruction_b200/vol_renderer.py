@@ -114,6 +114,24 @@ class _FieldRaysFn(torch.autograd.Function):
             dflat, last_m = dpm.enter_backward(mlp)
         else:
             dflat, last_m = torch.zeros_like(flat), False
+        # single GPU, the reference's configuration family: ONE kernel -- the scatter-add into the table gradient runs on
+        # dedicated warps of the MLP backward kernel, tile by tile (hbr_field_bwd_rays_tc); the gradient exchange of the
+        # multi-GPU path publishes level chunks of the table gradient while the scatter-add is still running, so it keeps
+        # the two-kernel form below
+        # (measured: 0.467 against 0.477 ms per 4 096-ray step; at 131 072 rays the two kernels, each at full occupancy,
+        # are 1 % ahead, hence the size limit)
+        if (FUSE_SCATTER and ctx.want_tab and ctx.want_mlp and enc._dp is None and dpm is None
+                and feat16.shape[0] <= FUSE_SCATTER_MAX_POINTS and ops.field_scatter_supported(ctx.geom, ctx.dims)):
+            if ctx.g is not None:
+                g, ev = ctx.g
+                ctx.g = None
+                torch.cuda.current_stream().wait_event(ev)
+            else:
+                g = torch.zeros((L, T, F), device=dout.device, dtype=torch.float32)
+            ddirs = ops.field_bwd_rays_tc(feat16, rays_o, rays_d, t, ctx.geom, dirs, flat, ctx.dims, out.detach(),
+                                          dout.float().contiguous(), g, ctx.needs_input_grad[3], dflat, operand=ctx.operand,
+                                          grad_scale=mlp.tc_grad_scale, defer_reduce=False)
+            return (None, None, None, ddirs, None, None) + tuple(g[i] for i in range(L)) + tuple(mlp._grad_views(dflat))
         # the reduction of the MLP kernel's per-CTA gradient rows runs on a side stream, beside the hash-grid backward
         defer = ctx.want_tab
         dfeat, ddirs = ops.mlp_bwd_tc(feat16, dirs, ctx.S, flat, ctx.dims, out.detach(), dout.float().contiguous(), ctx.want_tab,
@@ -231,6 +249,11 @@ class _FieldCompactFn(torch.autograd.Function):
         return head + tuple(g[i] for i in range(L)) + gm
 
 
+# hbr_field_bwd_rays_tc (MLP backward + hash-grid scatter-add in one kernel) on the single-GPU autocast path; the
+# environment switch exists for A/B measurements (bench.py --no-fuse-scatter)
+FUSE_SCATTER = os.environ.get("HBR_FUSE_SCATTER", "1") != "0"
+FUSE_SCATTER_MAX_POINTS = 1 << 21
+
 _SIDE = {}
 
 
@@ -275,6 +298,9 @@ class Volume_Renderer:
         self.var_model = var_model
         self._dp_checked = False
         self._grid_flags = None
+        # vol_render feeds the kernels at most this many sample points at a time (ray chunks): per-point temporaries of a
+        # 2^20-ray step would otherwise be tens of GB.  2^26 points = 524 288 rays x 128 samples.
+        self.max_points = 1 << 26
         # with an occupancy grid that is not all-True, True = skip the samples outside occupied cells
         # altogether (compacted sample lists through encoder, MLP and compositor) instead of evaluating and zeroing them;
         # same numbers, work proportional to the live samples.  Autocast / native modules only; off by default.
@@ -451,14 +477,37 @@ class Volume_Renderer:
             mask_needed = False
         else:
             mask_needed = not self._grid_all_true()
+        R, S = rays_o.shape[0], t.shape[-1]
+        per = max(1, int(self.max_points) // (S * (3 if hierarchical is True else 1)))
+        if R > per:
+            # Large batches (BASELINE configs[2]: 2^20 rays/step) go through the kernels in ray chunks: the
+            # per-point temporaries (features, d(features), field outputs) exist for one chunk at a time.  The RNG draws of
+            # the hierarchical resampler are made ONCE for the whole batch, in the reference's order, and sliced.
+            if hierarchical is True and _u is None:
+                _u = torch.rand((R, S), device=rays_o.device)                                  # RNG draw #2 (helper.py:40)
+                _u_cand = torch.rand(S, device=rays_o.device)                                  # RNG draw #3 (helper.py:43)
+            dn_rows = torch.is_tensor(dir_norm) and dir_norm.numel() == R
+            Crs, Cfs = [], []
+            for r0 in range(0, R, per):
+                sl = slice(r0, min(R, r0 + per))
+                cr, cf = self._render_rays(mlp, rays_o[sl], rays_d[sl], t, dir_enc[sl], dir_norm[sl] if dn_rows else dir_norm,
+                                           mask_needed, hierarchical, _u[sl] if _u is not None else None, _u_cand)
+                Crs.append(cr)
+                Cfs.append(cf)
+            Cr = torch.cat(Crs)
+            return Cr, (Cr if hierarchical is not True else torch.cat(Cfs)), None
+        Cr, Cf = self._render_rays(mlp, rays_o, rays_d, t, dir_enc, dir_norm, mask_needed, hierarchical, _u, _u_cand)
+        return Cr, Cf, None
+
+    def _render_rays(self, mlp, rays_o, rays_d, t, dir_enc, dir_norm, mask_needed, hierarchical, _u, _u_cand):
         Cr, w = self._field_pass(mlp, rays_o, rays_d, t, dir_enc, dir_norm, mask_needed)
         if hierarchical is True:
-            _, t_fine = hierarchical_sampling(rays_o, rays_d, z_vals=t, weights=w, n_samples=t.shape[-1], tn=near, tf=far,
-                                              device=device, _u=_u, _u_cand=_u_cand)           # RNG draws #2, #3
+            _, t_fine = hierarchical_sampling(rays_o, rays_d, z_vals=t, weights=w, n_samples=t.shape[-1], tn=self.near,
+                                              tf=self.far, device="cuda", _u=_u, _u_cand=_u_cand)   # RNG draws #2, #3
             Cf, _ = self._field_pass(mlp, rays_o, rays_d, t_fine, dir_enc, dir_norm, False)    # the fine pass never masks (:237)
         else:
             Cf = Cr
-        return Cr, Cf, None
+        return Cr, Cf
 
     def _generic(self, model, rays_d, rays_o, t, update_mask, dir_norm, hierarchical, _u, _u_cand):
         """Reference data flow for foreign encoders / models (vol_renderer.py:165-245)."""

@@ -163,6 +163,19 @@ int hbr_field_bwd_tc(const float* x, int64_t n, const hbr_hash_geom* geom_host, 
                      const float* params, const hbr_mlp_dims* dims, int operand, const void* feat16, const float* out,
                      const float* dout, float* dtable, float* ddirs, float* dparams, float grad_scale, void* scratch,
                      void* stream);
+/* ---- a7 backward + a5 in one kernel (the training step's backward under autocast): what hbr_mlp_bwd_tc followed by
+ * hbr_hash_encode_bwd_rays computes -- the autograd of MLP_3D.forward (test_hash.py:52-72) chained into the autograd of
+ * HashEncoder.forward (hash_encoding.py:146-170; 16 x embedding_dense_backward) for the sample positions o + d t of
+ * vol_renderer.py:165 -- with the scatter-add running on dedicated warps of the MLP kernel, tile by tile, beside the layer
+ * chains of the following tiles: no fp32 d(feature) tensor, and the two phases overlap on every SM.  Same configuration
+ * family as hbr_field_*_tc.  feat16 (R*S,32): the 16-bit features hbr_hash_encode_fwd_rays wrote (operand format).
+ * t: (S) shared (t_ray_stride = 0) or (R,S).  dirs (R,d_view).  dtable (L,T,2) / dparams / ddirs are ACCUMULATED into.
+ * scratch / image_ready / defer_reduce as in hbr_mlp_bwd_tc. */
+int hbr_field_bwd_rays_tc(const void* feat16, const float* rays_o, const float* rays_d, const float* t, int64_t t_ray_stride,
+                          int64_t R, int64_t S, const hbr_hash_geom* geom_host, const float* dirs, const float* params,
+                          const hbr_mlp_dims* dims, int operand, const float* out, const float* dout, float* dtable,
+                          float* ddirs, float* dparams, float grad_scale, void* scratch, int image_ready, int defer_reduce,
+                          void* stream);
 /* ---- a8: strat_sampler, helper.py:231-232: t[s] = lin[s] + (u[s] * span) / count with span = tf - tn, count = num_samples,
  * each operation rounded on its own (bit-identical to the reference's three elementwise ops).  lin = torch.linspace(tn, tf, S)
  * and u = torch.rand_like(lin) are produced by the caller (same RNG stream, Q9). */

@@ -519,3 +519,23 @@ def test_update_grid_kernel_matches_reference_semantics():
     frac = vr.update_grid_from_field(mlp, threshold=-1e9)
     assert frac == 1.0
     assert vr.update_grid_from_field(mlp, threshold=1e9) == 0.0
+
+
+@pytest.mark.parametrize("hier", [False, True])
+def test_ray_chunking_changes_nothing(hier):
+    """Volume_Renderer.max_points: a batch rendered in ray chunks == the same batch in one piece -- colours
+    bit-identical (same RNG draws, sliced), gradients to accumulation-order noise."""
+    g = load_golden("volrender.npz")
+    S = 24
+    res = []
+    for max_points in (1 << 26, 24 * 7 * (3 if hier else 1)):         # one piece / chunks of 7 rays
+        vr, enc, mlp = build_renderer(g)
+        vr.max_points = max_points
+        torch.manual_seed(5)
+        Cr, Cf, _ = vr.vol_render(mlp, g["rays_d"].to(DEV), g["rays_o"].to(DEV), num_samples=S, dir_norm=g["dir_norm"].to(DEV),
+                                  hierarchical=hier)
+        (torch.nn.functional.mse_loss(Cr, g["gt"].to(DEV)) + torch.nn.functional.mse_loss(Cf, g["gt"].to(DEV))).backward()
+        res.append((Cr.detach(), Cf.detach(), torch.stack([e.weight.grad for e in enc.Embedding_list]),
+                    torch.cat([q.grad.reshape(-1) for q in mlp.parameters()])))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert rel(res[1][2], res[0][2]) < 1e-5 and rel(res[1][3], res[0][3]) < 1e-5
