@@ -213,8 +213,9 @@ extern "C" int hbr_grid_points(const double* min3, const double* max3, int res, 
 extern "C" int hbr_grid_density(const double* min3, const double* max3, int res, int64_t p0, int64_t count,
                                 const float* table, const hbr_hash_geom* geom, const float* params,
                                 const hbr_mlp_dims* dims, const float* dir_enc, float* out, void* pts_scratch,
-                                float* feat_scratch, int64_t chunk, void* stream) {
+                                float* feat_scratch, int64_t chunk, int field_mode, void* stream) {
   HBR_REQUIRE(geom && dims && chunk >= 1, "bad argument");
+  HBR_REQUIRE(field_mode == 0 || field_mode == 1, "field_mode %d", field_mode);
   HBR_REQUIRE(dims->in0 == geom->L * geom->F + geom->E, "MLP input width %d != encoder width %d", dims->in0,
               geom->L * geom->F + geom->E);
   const int ow = dir_enc ? 4 : 1;
@@ -222,6 +223,10 @@ extern "C" int hbr_grid_density(const double* min3, const double* max3, int res,
     const int64_t c = count - s < chunk ? count - s : chunk;
     if (int rc = hbr_grid_points(min3, max3, res, p0 + s, c, pts_scratch, stream)) return rc;
     if (int rc = hbr_hash_encode_fwd(pts_scratch, HBR_F16, c, table, geom, feat_scratch, dims->in0, stream)) return rc;
+    if (!dir_enc && field_mode == 0 && dims->in0 == 32) {
+      if (int rc = hbr_mlp_density_tf32x3(feat_scratch, c, params, dims, out + s, stream)) return rc;
+      continue;
+    }
     // one direction row for all points: dir_group >= c maps every point to row 0 (nerf2mesh.py:69-70)
     if (int rc = hbr_mlp_fwd_f32(feat_scratch, dims->in0, dir_enc, c, c, params, dims, out + s * ow, nullptr, stream))
       return rc;

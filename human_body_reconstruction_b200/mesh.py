@@ -31,7 +31,7 @@ def view_dir_encoding(dir_encoder: PositionalEncoder, device) -> torch.Tensor:
 
 
 def density_grid(encoder: HashEncoder, nerf, dir_encoder: Optional[PositionalEncoder], min_bound, max_bound, res: int,
-                 i_begin: int = 0, i_end: Optional[int] = None, chunk: int = 1 << 20) -> torch.Tensor:
+                 i_begin: int = 0, i_end: Optional[int] = None, chunk: int = 1 << 19, cuda_core_mlp: bool = False) -> torch.Tensor:
     """Field values on planes [i_begin, i_end) of the res^3 grid.
 
     With a dir_encoder: (planes, res, res, 4) = [rgb, density], the layout nerf2mesh.py:86-87 saves to
@@ -49,7 +49,7 @@ def density_grid(encoder: HashEncoder, nerf, dir_encoder: Optional[PositionalEnc
     denc = view_dir_encoding(dir_encoder, table.device) if dir_encoder is not None else None
     with torch.no_grad():
         out = ops.grid_density([float(v) for v in min_bound], [float(v) for v in max_bound], res, p0, count, table,
-                               encoder._geom(), mlp._flat_params(), mlp._dims(), denc, chunk=chunk)
+                               encoder._geom(), mlp._flat_params(), mlp._dims(), denc, chunk=chunk, cuda_core_mlp=cuda_core_mlp)
     return out.view((i_end - i_begin, res, res, 4) if denc is not None else (i_end - i_begin, res, res))
 
 

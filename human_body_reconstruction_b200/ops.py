@@ -571,7 +571,18 @@ def grid_points(min_bound, max_bound, res: int, p0: int, count: int, device) -> 
     return pts
 
 
-def grid_density(min_bound, max_bound, res, p0, count, table, geom, params, dims, dir_enc, chunk=1 << 20):
+def mlp_density_tf32x3(feat, params, dims: MlpDims):
+    """Density head of MLP_3D on (n,32) fp32 features, tensor cores with split-TF32 operands (fp32-level accuracy)."""
+    require_cuda(feat, params)
+    feat = _f32c(feat)
+    out = torch.empty((feat.shape[0],), device=feat.device, dtype=torch.float32)
+    check(lib().hbr_mlp_density_tf32x3(ptr(feat), feat.shape[0], ptr(params), C.byref(dims), ptr(out), stream()))
+    return out
+
+
+def grid_density(min_bound, max_bound, res, p0, count, table, geom, params, dims, dir_enc, chunk=1 << 19, cuda_core_mlp=False):
+    """chunk: points per pass (default 2^19: the chunk's 64 MB of fp32 features stay in L2 between the encoder and the MLP).
+    cuda_core_mlp: force the fp32 CUDA-core MLP (default: the density-only query runs the split-TF32 tensor-core head)."""
     require_cuda(table, params)
     mn = (C.c_double * 3)(*[float(v) for v in min_bound])
     mx = (C.c_double * 3)(*[float(v) for v in max_bound])
@@ -581,7 +592,7 @@ def grid_density(min_bound, max_bound, res, p0, count, table, geom, params, dims
     pts = torch.empty((chunk, 3), device=dev, dtype=torch.float16)
     feat = torch.empty((chunk, dims.in0), device=dev, dtype=torch.float32)
     check(lib().hbr_grid_density(mn, mx, res, p0, count, ptr(table), C.byref(geom), ptr(params), C.byref(dims),
-                                 ptr(dir_enc), ptr(out), ptr(pts), ptr(feat), chunk, stream()))
+                                 ptr(dir_enc), ptr(out), ptr(pts), ptr(feat), chunk, 1 if cuda_core_mlp else 0, stream()))
     return out
 
 

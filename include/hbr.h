@@ -259,10 +259,19 @@ int hbr_grid_points(const double* min3_host, const double* max3_host, int res, i
  * out: count rows of 4 floats [rgb, density]; with dir_enc == NULL, count floats (density only).
  * pts_scratch: (chunk,3) halfs, feat_scratch: (chunk, L*F+E) floats.  z-slab / multi-GPU sharding = one
  * [p0, p0+count) range per rank. */
+/* field_mode: 0 = automatic -- the density-only query of the reference's shape (dir_enc == NULL, in0 == 32) runs its MLP on
+ * the tensor cores at fp32-level accuracy (hbr_mlp_density_tf32x3), everything else on the fp32 CUDA-core kernel;
+ * 1 = fp32 CUDA-core kernel always. */
 int hbr_grid_density(const double* min3_host, const double* max3_host, int res, int64_t p0, int64_t count,
                      const float* table, const hbr_hash_geom* geom_host, const float* params,
                      const hbr_mlp_dims* dims, const float* dir_enc, float* out, void* pts_scratch,
-                     float* feat_scratch, int64_t chunk, void* stream);
+                     float* feat_scratch, int64_t chunk, int field_mode, void* stream);
+/* Density head of MLP_3D (test_hash.py:52-62: sig_model on the (n,32) fp32 features, output 0, LeakyReLU) for n points,
+ * as nerf2mesh.py:80-82 evaluates it (no autocast: fp32), on the tensor cores: every fp32 operand split into two TF32
+ * parts, three tcgen05.mma.kind::tf32 terms per product, fp32 accumulation -- within 1e-5 of the fp32 CUDA-core kernel.
+ * feat: contiguous rows of 32 floats, 16-byte aligned.  out: n floats. */
+int hbr_mlp_density_tf32x3(const float* feat, int64_t n, const float* params, const hbr_mlp_dims* dims, float* out,
+                           void* stream);
 
 /* ---- a14: marching cubes at iso over density (n0,n1,n2) fp32, inside test d < iso -------------------
  * Cells i in [i_begin, i_end) along axis 0 (slab ownership for multi-GPU).  counts[0] = vertices

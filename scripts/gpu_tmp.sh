@@ -1,12 +1,8 @@
 cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -8 > gpurun_out/pytest_gpu.log; cat gpurun_out/pytest_gpu.log
-for extra in "" "--no-fuse-scatter"; do
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-grid --no-occupancy --no-device-sampler $extra > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench $extra rc=$?"; tail -3 gpurun_out/bench.err
+timeout 300 python -m pytest tests/test_gpu_grid.py tests/test_gpu_parity.py -m gpu -q -x -s -k "density or grid" 2>&1 | tail -25
+timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-c3 --no-occupancy --no-device-sampler > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err
 python - <<'PY'
 import json
-try:
-    d=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
-    print('value', d['value'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'], 'c3', d['c3']['value'], d['c3']['ms_per_step'])
-except Exception as e: print("no json", e)
+d=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
+print(d.get('grid'))
 PY
-done
