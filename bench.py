@@ -368,11 +368,14 @@ def run_b200(args):
         from human_body_reconstruction_b200 import vol_renderer as _vrm
         _vrm.FUSE_SCATTER = False                                         # MLP backward and hash-grid scatter-add as two kernels
     reducer = None
+    # "--peer-chunks 2" = two equal level ranges; "--peer-chunks 4,8,12,14" = inner level boundaries (cheap coarse levels first)
+    pc = [int(v) for v in str(args.peer_chunks).split(",") if v != ""]
+    peer_chunks = pc if len(pc) > 1 else (pc[0] if pc else 0)
     if world > 1:
         # the gradient exchange: "peer" = this package's one-kernel all-reduce over NVLink peer memory (csrc/comm.cu),
         # "nccl" = torch.distributed all_reduce calls, "auto" = peer unless a rank cannot set it up
         reducer = hdist.attach_grad_allreduce(enc, mlp, kind=args.allreduce, transport=args.peer_transport, ctas=args.peer_ctas,
-                                              overlap=args.peer_chunks > 0, chunks=max(1, args.peer_chunks))
+                                              overlap=peer_chunks != 0, chunks=peer_chunks if peer_chunks else 1)
     rays = args.rays                                                       # per GPU (weak scaling)
     host = [tuple(t.pin_memory() for t in b) for b in make_batches(c2w, K, H, W, rays, 4, 100 + rank)]
     resident = [tuple(t.to(dev) for t in b) for b in host]
@@ -576,7 +579,7 @@ def run_b200(args):
         region = getattr(reducer, "region", None)
         line["config"]["allreduce"] = "nccl" if region is None else (
             f"one kernel over NVLink peer memory ({region.transport}{', NVLS multicast' if region.multicast_ptr else ''}"
-            f"{f', {args.peer_chunks} overlapped chunks' if args.peer_chunks else ''})")
+            f"{f', overlapped level chunks {args.peer_chunks}' if peer_chunks else ''})")
         if region is not None and region.timed_out():
             line["error"] = "peer all-reduce barrier timed out"
     if world == 1 and not args.no_cpu_baseline:
@@ -771,6 +774,9 @@ def grad_check_leg(hdist, tdist, reducer, enc, mlp, params, step, resident, worl
             bits = torch.cat([tab.reshape(-1), torch.cat([p.grad.reshape(-1) for p in mlp.parameters()])]).view(torch.int32)
             return bits.to(torch.int64).sum().reshape(1)
 
+        # the step draws its stratified depths from torch's generator (helper.strat_sampler): both passes start from the
+        # same generator state so that they see the same samples
+        torch.manual_seed(4242 + rank)
         step(resident[0])
         reduced, cs = sample(), checksum()
         all_cs = [torch.zeros_like(cs) for _ in range(world)]
@@ -778,6 +784,7 @@ def grad_check_leg(hdist, tdist, reducer, enc, mlp, params, step, resident, worl
         identical = all(int(c) == int(all_cs[0]) for c in all_cs)
         if reducer is not None:
             reducer.remove()
+        torch.manual_seed(4242 + rank)
         step(resident[0])                                                  # the same batch, gradients left local
         local = sample()
         gathered = [torch.zeros_like(local) for _ in range(world)]
@@ -854,7 +861,7 @@ def main():
     ap.add_argument("--allreduce", default="auto", choices=["auto", "peer", "nccl"], help="N>1 gradient exchange")
     ap.add_argument("--peer-transport", default="auto", choices=["auto", "ipc", "symm"])
     ap.add_argument("--peer-ctas", type=int, default=0)
-    ap.add_argument("--peer-chunks", type=int, default=2, help="> 0: all-reduce level chunks on a side stream while the "
+    ap.add_argument("--peer-chunks", type=str, default="2", help="> 0: all-reduce level chunks on a side stream while the "
                     "remaining chunks' scatter-add runs; 0: one all-reduce behind the backward pass")
     ap.add_argument("--fuse-field", action="store_true", help="use the fused encoder+MLP kernels (hbr_field_*_tc)")
     ap.add_argument("--no-fuse-scatter", action="store_true", help="A/B: run the MLP backward and the hash-grid scatter-add as "

@@ -201,7 +201,8 @@ hash_bwd_kernel(const typename PointSrc<XT>::type x, long long n, const float* _
 #pragma unroll
     for (int it = 0; it < kTilePts * 8 / kHashThreads; ++it) {
       const int idx = it * kHashThreads + threadIdx.x;          // float4 index in the tile: row = idx / 8
-      q[it] = base + idx / 8 < n ? __ldg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int c = (idx & 7) * 4;                              // a level chunk reads only its own columns of dy
+      q[it] = (base + idx / 8 < n && c + 4 > c0 && c < c1) ? __ldg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int it = 0; it < kTilePts * 8 / kHashThreads; ++it) {

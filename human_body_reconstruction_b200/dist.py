@@ -87,6 +87,19 @@ class _GradExchange:
     def _join(self):                                          # compute stream waits for every exchange started
         pass
 
+    def level_chunks(self, m, L: int):
+        """[(l0, l1), ...]: the level ranges the last table backward of a pass runs and publishes in.  `chunks` may be a
+        count (equal level ranges) or a list of inner level boundaries, e.g. [4, 8, 12, 14] -> [0,4) [4,8) [8,12) [12,14)
+        [14,16): all levels carry the same bytes, but the scatter-add of a coarse level costs a fraction of a fine one's,
+        so early cheap chunks put bytes on the wire while most of the scatter-add is still to come."""
+        c = self.chunks(m)
+        if isinstance(c, (list, tuple)):
+            b = [0] + sorted(int(v) for v in c if 0 < int(v) < L) + [L]
+            return [(b[i], b[i + 1]) for i in range(len(b) - 1) if b[i + 1] > b[i]]
+        n = max(1, min(L, int(c)))
+        step = -(-L // n)
+        return [(l0, min(L, l0 + step)) for l0 in range(0, L, step)]
+
     def chunks(self, m) -> int:                               # pieces the last backward node of m should publish in
         return 1
 
@@ -252,7 +265,7 @@ class PeerGradAllReduce(_GradExchange):
         self.region = PeerRegion(off + n_mlp, group=group, transport=transport)
         self.overlap = overlap
         self.ctas = ctas if ctas > 0 else (32 if overlap else 0)
-        self._nchunks = int(chunks)
+        self._nchunks = [int(v) for v in chunks] if isinstance(chunks, (list, tuple)) else int(chunks)
         self._enc, self._mlp = encoder, mlp
         encoder._flat_table()
         self._slices = {id(encoder): self.region.tensor[:n_tab].view(encoder.L, encoder.T, encoder.F),

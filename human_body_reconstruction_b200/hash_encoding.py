@@ -44,10 +44,7 @@ class _HashEncodeFn(torch.autograd.Function):
             # enqueued: that chunk's all-reduce travels over NVLink while the next chunk's scatter-add still runs.  The
             # exchange hands the reduced buffer to .grad at the end of backward; nothing is returned to autograd here.
             g, last = dp.enter_backward(enc)
-            nch = max(1, min(L, dp.chunks(enc))) if last else 1
-            step = -(-L // nch)
-            for l0 in range(0, L, step):
-                l1 = min(L, l0 + step)
+            for l0, l1 in (dp.level_chunks(enc, L) if last else [(0, L)]):
                 ops.hash_encode_bwd(x, dy[:, : L * F], ctx.geom, g, l0, l1)
                 if last:
                     dp.publish(enc, g[l0:l1])

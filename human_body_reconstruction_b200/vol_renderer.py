@@ -157,10 +157,7 @@ class _FieldRaysFn(torch.autograd.Function):
         dpe = enc._dp
         if dpe is not None:
             g, last = dpe.enter_backward(enc)
-            nch = max(1, min(L, dpe.chunks(enc))) if last else 1
-            step = -(-L // nch)
-            for l0 in range(0, L, step):
-                l1 = min(L, l0 + step)
+            for l0, l1 in (dpe.level_chunks(enc, L) if last else [(0, L)]):
                 ops.hash_encode_bwd_rays(rays_o, rays_d, t, dfeat, ctx.geom, g, l0, l1)
                 if l0 == 0:
                     join_mlp()                      # the MLP gradient is complete (and published) behind the first chunk

@@ -156,3 +156,24 @@ def test_slab_range_partition(res, world):
         assert a1 == b0 and a0 <= a1
     sizes = [b - a for a, b in edges]
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_level_chunks_boundaries():
+    """dist._GradExchange.level_chunks: a count gives equal level ranges, a list gives inner boundaries; both cover [0, L)."""
+    from human_body_reconstruction_b200.dist import _GradExchange
+
+    class Fake(_GradExchange):
+        def __init__(self, c):
+            self._c = c
+
+        def chunks(self, m):
+            return self._c
+
+    assert Fake(1).level_chunks(None, 16) == [(0, 16)]
+    assert Fake(2).level_chunks(None, 16) == [(0, 8), (8, 16)]
+    assert Fake(3).level_chunks(None, 16) == [(0, 6), (6, 12), (12, 16)]
+    assert Fake([4, 8, 12, 14]).level_chunks(None, 16) == [(0, 4), (4, 8), (8, 12), (12, 14), (14, 16)]
+    assert Fake([12, 4, 0, 16, 99]).level_chunks(None, 16) == [(0, 4), (4, 12), (12, 16)]
+    for c in (1, 2, 5, 16, 40, [3], [1, 2, 3]):
+        ch = Fake(c).level_chunks(None, 16)
+        assert ch[0][0] == 0 and ch[-1][1] == 16 and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
