@@ -14,6 +14,8 @@ hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
 names = {"hash_fwd_kernel": "hbr_hash_encode_fwd", "hash_bwd_kernel": "hbr_hash_encode_bwd", "mlp_fwd_tc_kernel": "hbr_mlp_fwd_tc",
          "mlp_bwd_tc_kernel": "hbr_mlp_bwd_tc", "composite_fwd_kernel": "hbr_composite_fwd", "composite_bwd_kernel": "hbr_composite_bwd"}
+# the fused backward (scatter warps inside mlp_bwd_tc_kernel<.., SCAT = 11>) is the same kernel template: both keys get its traffic
+ALIAS = {"hbr_mlp_bwd_tc": ["hbr_field_bwd_rays_tc"], "hbr_hash_encode_fwd": ["hbr_hash_encode_fwd_rays"]}
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 out = {"_source": f"profiles/{tag}_ncu_full_summary.md (ncu --set full, one launch each, bench.py --steps 3 --warmup 3 --graph off, 524288 points)"}
 for r in rows[2:]:
@@ -21,6 +23,10 @@ for r in rows[2:]:
         if s in r[idx["Kernel Name"]]:
             out[n] = int(round(sum(float(r[idx[m]].replace(",", "")) * scale[units[idx[m]]]
                                    for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))))
+for k, al in ALIAS.items():
+    for a in al:
+        if k in out:
+            out[a] = out[k]
 json.dump(out, open("profiles/traffic.json", "w"), indent=1)
 lines = [l for l in open(f"gpurun_out/{tag}_launches.csv").read().splitlines() if l.startswith('"')]
 rd = csv.reader(lines)
