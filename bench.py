@@ -714,10 +714,9 @@ def grid_leg(args, hbr, hdist, world, rank, dev, mx, mn, sigma, barrier):
             return dens
 
         dens = run()
-        iso = torch.tensor([float(dens.float().median())], device=dev)
-        if world > 1:
-            tdist.broadcast(iso, 0)
-        iso = float(iso)
+        # iso level: the median of the field on a coarse 64^3 grid over the same bounds -- every rank (and every N) computes
+        # the same value, so the vertex / triangle totals are comparable across 1, 2, 4 and 8 GPUs
+        iso = float(hbr.mesh.density_grid(enc, mlp, None, lo, hi, 64).float().median())
         barrier()
         ts, tc = [], []
         for _ in range(3):

@@ -44,7 +44,7 @@ class _HashEncodeFn(torch.autograd.Function):
             # enqueued: that chunk's all-reduce travels over NVLink while the next chunk's scatter-add still runs.  The
             # exchange hands the reduced buffer to .grad at the end of backward; nothing is returned to autograd here.
             g, last = dp.enter_backward(enc)
-            for l0, l1 in (dp.level_chunks(enc, L) if last else [(0, L)]):
+            for l0, l1 in (dp.level_chunks(enc, L, x.shape[0]) if last else [(0, L)]):
                 ops.hash_encode_bwd(x, dy[:, : L * F], ctx.geom, g, l0, l1)
                 if last:
                     dp.publish(enc, g[l0:l1])

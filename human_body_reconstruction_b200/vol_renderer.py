@@ -157,7 +157,7 @@ class _FieldRaysFn(torch.autograd.Function):
         dpe = enc._dp
         if dpe is not None:
             g, last = dpe.enter_backward(enc)
-            for l0, l1 in (dpe.level_chunks(enc, L) if last else [(0, L)]):
+            for l0, l1 in (dpe.level_chunks(enc, L, feat16.shape[0]) if last else [(0, L)]):
                 ops.hash_encode_bwd_rays(rays_o, rays_d, t, dfeat, ctx.geom, g, l0, l1)
                 if l0 == 0:
                     join_mlp()                      # the MLP gradient is complete (and published) behind the first chunk
