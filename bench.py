@@ -367,15 +367,21 @@ def run_b200(args):
     if args.no_fuse_scatter:
         from human_body_reconstruction_b200 import vol_renderer as _vrm
         _vrm.FUSE_SCATTER = False                                         # MLP backward and hash-grid scatter-add as two kernels
+    if args.peer_scatter == "tile":
+        from human_body_reconstruction_b200 import vol_renderer as _vrm
+        _vrm.STREAM_LEVEL_MAJOR = False
     reducer = None
     # "--peer-chunks 2" = two equal level ranges; "--peer-chunks 4,8,12,14" = inner level boundaries (cheap coarse levels first)
-    pc = [int(v) for v in str(args.peer_chunks).split(",") if v != ""]
+    streamed = args.peer_exchange == "stream"
+    pcs = str(args.peer_chunks) if args.peer_chunks != "auto" else ("8" if streamed else "2")
+    pc = [int(v) for v in pcs.split(",") if v != ""]
     peer_chunks = pc if len(pc) > 1 else (pc[0] if pc else 0)
     if world > 1:
         # the gradient exchange: "peer" = this package's one-kernel all-reduce over NVLink peer memory (csrc/comm.cu),
         # "nccl" = torch.distributed all_reduce calls, "auto" = peer unless a rank cannot set it up
         reducer = hdist.attach_grad_allreduce(enc, mlp, kind=args.allreduce, transport=args.peer_transport, ctas=args.peer_ctas,
-                                              overlap=peer_chunks != 0, chunks=peer_chunks if peer_chunks else 1)
+                                              overlap=peer_chunks != 0, chunks=peer_chunks if peer_chunks else 1,
+                                              streamed=streamed)
     rays = args.rays                                                       # per GPU (weak scaling)
     host = [tuple(t.pin_memory() for t in b) for b in make_batches(c2w, K, H, W, rays, 4, 100 + rank)]
     resident = [tuple(t.to(dev) for t in b) for b in host]
@@ -579,7 +585,8 @@ def run_b200(args):
         region = getattr(reducer, "region", None)
         line["config"]["allreduce"] = "nccl" if region is None else (
             f"one kernel over NVLink peer memory ({region.transport}{', NVLS multicast' if region.multicast_ptr else ''}"
-            f"{f', overlapped level chunks {args.peer_chunks}' if peer_chunks else ''})")
+            f"{f', overlapped level chunks {pcs}' if peer_chunks else ''}"
+            f"{', streamed: one scatter-add launch + one exchange launch side by side' if getattr(reducer, 'streamed', False) else ''})")
         if region is not None and region.timed_out():
             line["error"] = "peer all-reduce barrier timed out"
     if world == 1 and not args.no_cpu_baseline:
@@ -860,8 +867,13 @@ def main():
     ap.add_argument("--allreduce", default="auto", choices=["auto", "peer", "nccl"], help="N>1 gradient exchange")
     ap.add_argument("--peer-transport", default="auto", choices=["auto", "ipc", "symm"])
     ap.add_argument("--peer-ctas", type=int, default=0)
-    ap.add_argument("--peer-chunks", type=str, default="2", help="> 0: all-reduce level chunks on a side stream while the "
-                    "remaining chunks' scatter-add runs; 0: one all-reduce behind the backward pass")
+    ap.add_argument("--peer-chunks", type=str, default="auto", help="> 0: all-reduce level chunks on a side stream while the "
+                    "remaining chunks' scatter-add runs; 0: one all-reduce behind the backward pass; a list = inner level "
+                    "boundaries; auto = 8 (streamed) / 2 (one launch per chunk)")
+    ap.add_argument("--peer-scatter", default="lm", choices=["lm", "tile"], help="producer of the streamed exchange: the "
+                    "level-major scatter-add (co-resident grid, levels in order) or the tile-major kernel launched chunk-major")
+    ap.add_argument("--peer-exchange", default="stream", choices=["stream", "launch"], help="stream: ONE scatter-add launch "
+                    "finishing the level chunks in order + ONE exchange launch beside it; launch: a launch pair per chunk")
     ap.add_argument("--fuse-field", action="store_true", help="use the fused encoder+MLP kernels (hbr_field_*_tc)")
     ap.add_argument("--no-fuse-scatter", action="store_true", help="A/B: run the MLP backward and the hash-grid scatter-add as "
                     "two kernels (default on one GPU: hbr_field_bwd_rays_tc, the scatter-add on dedicated warps of the MLP kernel)")

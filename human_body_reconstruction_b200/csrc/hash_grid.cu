@@ -8,6 +8,7 @@
 // equal cells with shuffles before issuing one red.global.add.v2.f32 per distinct entry.
 // Rows of y / dy cross shared memory so global traffic is full 128-byte lines.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace hbr {
 
@@ -35,14 +36,27 @@ __device__ __forceinline__ void load_feat(const float* __restrict__ base, uint32
   }
 }
 
+// Explicit red.global (no return value).  atomicAdd() with an unused result is lowered to RED as well -- unless the kernel
+// contains a memory fence: the streamed variants below (a gpu-scope fence before the completion count) then got ATOMG for
+// every gradient update, whose returned values the LSU has to track: measured 257 us against 183 us for the same reductions.
+__device__ __forceinline__ void red_add_f32(float* p, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 template <int F>
 __device__ __forceinline__ void red_feat(float* base, uint32_t idx, const float v[F]) {
   if (F == 1) {
-    atomicAdd(base + idx, v[0]);
+    red_add_f32(base + idx, v[0]);
   } else if (F == 2) {
-    atomicAdd(reinterpret_cast<float2*>(base) + idx, make_float2(v[0], v[1]));      // red.global.add.v2.f32
+    red_add_v2(base + 2 * (size_t)idx, v[0], v[1]);
   } else {
-    atomicAdd(reinterpret_cast<float4*>(base) + idx, make_float4(v[0], v[1], v[2], v[3]));
+    red_add_v4(base + 4 * (size_t)idx, v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -178,20 +192,41 @@ hash_fwd_kernel(const typename PointSrc<XT>::type x, long long n, const float* _
 }
 
 // ---- backward -----------------------------------------------------------------------------------------
-template <int F, bool POW2, typename XT>
+// STREAM (multi-GPU gradient exchange, comm.cu: allreduce_stream_kernel): ONE launch walks the level chunks
+// [bounds[c], bounds[c+1]) in chunk-major CTA order -- CTA b serves chunk b / tiles, tile b % tiles, and CTAs are
+// dispatched in index order, so chunk c of the table gradient is complete long before the launch ends -- and every CTA
+// counts itself into done[c] (all its reductions ordered before the count by a gpu-scope fence).  The all-reduce kernel
+// running beside this one on another stream watches the counters and puts chunk c on the wire while the later chunks
+// are still being accumulated.  Against one launch per chunk there are no launch gaps or per-chunk tails.
+struct ChunkPlan {
+  int nchunks;
+  int bounds[HBR_MAX_LEVELS + 1];
+  unsigned* done;                                  // [nchunks] counters, zeroed by the caller before the launch
+  unsigned tiles;
+  int order[HBR_MAX_LEVELS];                       // level-major kernel: the levels in visiting order (bounds index this list)
+};
+
+template <int F, bool POW2, typename XT, bool STREAM = false>
 __global__ void __launch_bounds__(kHashThreads)
 hash_bwd_kernel(const typename PointSrc<XT>::type x, long long n, const float* __restrict__ dy, long long dy_stride,
                 float* __restrict__ dtable, const __grid_constant__ HashGeom g, int l_begin, int l_end,
-                const unsigned long long* __restrict__ n_dev) {
+                const unsigned long long* __restrict__ n_dev, const __grid_constant__ ChunkPlan plan) {
   extern __shared__ float tile[];
   if (n_dev != nullptr) {
     n = min(n, (long long)__ldg(n_dev));
     if ((long long)blockIdx.x * kTilePts >= n) return;
   }
+  unsigned bidx = blockIdx.x, chunk = 0;
+  if (STREAM) {
+    chunk = blockIdx.x / plan.tiles;
+    bidx = blockIdx.x - chunk * plan.tiles;
+    l_begin = plan.bounds[chunk];
+    l_end = plan.bounds[chunk + 1];
+  }
   const int C = g.L * F;
   const int pitch = C | 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long base = (long long)blockIdx.x * kTilePts;
+  const long long base = (long long)bidx * kTilePts;
   const int c0 = l_begin * F, c1 = l_end * F;
   if (C == 32 && dy_stride == 32 && ((uintptr_t)dy & 15) == 0) {
     // the tile is one contiguous 16 KB block of dy: four independent float4 loads per thread, all in flight before the
@@ -273,11 +308,133 @@ hash_bwd_kernel(const typename PointSrc<XT>::type x, long long n, const float* _
           const bool odd = idx[c] & 1;
           const float4 q = odd ? make_float4(val[c + 1][0], val[c + 1][F - 1], val[c][0], val[c][F - 1])
                                : make_float4(val[c][0], val[c][F - 1], val[c + 1][0], val[c + 1][F - 1]);
-          atomicAdd(reinterpret_cast<float4*>(lvl) + (idx[c] >> 1), q);
+          red_add_v4(lvl + 4 * (size_t)(idx[c] >> 1), q.x, q.y, q.z, q.w);
         }
       } else {
 #pragma unroll
         for (int c = 0; c < 8; ++c) red_feat<F>(lvl, idx[c], val[c]);
+      }
+    }
+  }
+  if (STREAM) {
+    __syncthreads();                                // every thread's reductions have been issued ...
+    if (threadIdx.x == 0) {
+      __threadfence();                              // ... and are ordered (gpu scope) before the count
+      atomicAdd(plan.done + chunk, 1u);
+    }
+  }
+}
+
+// ---- backward, level-major traversal (the multi-GPU training step) --------------------------------------------
+// dy arrives level-major, (L, n, F) -- hbr_mlp_bwd_tc writes it so on request -- and the grid is small enough to be
+// co-resident: CTA b owns kLmPts consecutive points (thread t: points b*kLmPts + j*256 + t, j < kLmPer; their normalised
+// positions stay in registers) and walks the LEVELS in order, all CTAs roughly in lockstep.  So the table gradient is
+// finished level by level: after the last level of chunk c every CTA counts itself into done[c] (its reductions ordered
+// before the count by a gpu-scope fence taken by one thread, while the other warps go on with the next chunk), and the
+// all-reduce kernel beside it (comm.cu: allreduce_stream_kernel) puts chunk c on the wire while the finer levels -- where
+// most of the reductions are -- are still being accumulated.  Same arithmetic, run merging and (x, x+1) pairing as
+// hash_bwd_kernel; no shared memory (the per-level dy reads are coalesced 8-byte loads), positions formed once.
+constexpr int kLmThreads = 256;
+constexpr int kLmPer = 4;                           // points per thread
+constexpr int kLmPts = kLmThreads * kLmPer;         // points per CTA
+
+template <int F, bool POW2, typename XT>
+__global__ void __launch_bounds__(kLmThreads, 4)
+hash_bwd_lm_kernel(const typename PointSrc<XT>::type x, long long n, const float* __restrict__ dy, float* __restrict__ dtable,
+                   const __grid_constant__ HashGeom g, const __grid_constant__ ChunkPlan plan) {
+  using FV = typename FeatVec<F>::type;
+  const int lane = threadIdx.x & 31;
+  const long long base = (long long)blockIdx.x * kLmPts + threadIdx.x;
+  float un[kLmPer][3];
+  bool valid[kLmPer];
+#pragma unroll
+  for (int j = 0; j < kLmPer; ++j) {
+    const long long gp = base + j * kLmThreads;
+    valid[j] = gp < n;
+    float pt[3];
+    load_point(x, gp, n, pt);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) un[j][a] = __fdiv_rn(__fsub_rn(pt[a], g.mu[a]), g.sigma);   // level-independent part of cell_of
+  }
+  for (int c = 0; c < plan.nchunks; ++c) {
+    const int b0 = plan.bounds[c], b1 = plan.bounds[c + 1];
+#pragma unroll 1
+    for (int i = b0; i < b1; ++i) {
+      // odd warps walk the chunk's levels backwards: a chunk that pairs coarse levels (shuffle-merge work on the SM) with
+      // fine ones (reductions, L2-bound) keeps both kinds of work in flight at any time
+      const int l = plan.order[((threadIdx.x >> 5) & 1) ? b1 - 1 - (i - b0) : i];
+      const float s = g.scale[l];
+      const FV* dyl = reinterpret_cast<const FV*>(dy) + (size_t)l * n;
+      float* lvl = dtable + (size_t)l * g.T * F;
+      FV gyv[kLmPer];
+#pragma unroll
+      for (int j = 0; j < kLmPer; ++j) {            // all loads of the level in flight before the first use
+        const long long gp = base + j * kLmThreads;
+        gyv[j] = valid[j] ? __ldg(dyl + gp) : FV{};
+      }
+#pragma unroll
+      for (int j = 0; j < kLmPer; ++j) {
+        const float* gy = reinterpret_cast<const float*>(&gyv[j]);
+        const bool vj = valid[j];
+        long long ix, iy, iz;
+        float fx, fy, fz;
+        {
+          const float ux = __fmul_rn(un[j][0], s), uy = __fmul_rn(un[j][1], s), uz = __fmul_rn(un[j][2], s);
+          ix = __float2ll_rz(ux); fx = __fsub_rn(ux, __ll2float_rn(ix));
+          iy = __float2ll_rz(uy); fy = __fsub_rn(uy, __ll2float_rn(iy));
+          iz = __float2ll_rz(uz); fz = __fsub_rn(uz, __ll2float_rn(iz));
+        }
+        float w[8];
+        corner_weights(fx, fy, fz, w);
+        float val[8][F];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+          for (int f = 0; f < F; ++f) val[q][f] = w[q] * gy[f];
+        // runs of consecutive lanes in the same cell (a ray crosses a cell in one contiguous stretch)
+        const long long pix = __shfl_up_sync(kFull, ix, 1);
+        const long long piy = __shfl_up_sync(kFull, iy, 1);
+        const long long piz = __shfl_up_sync(kFull, iz, 1);
+        const int pvalid = __shfl_up_sync(kFull, (int)vj, 1);
+        const bool head = lane == 0 || !vj || !pvalid || pix != ix || piy != iy || piz != iz;
+        const unsigned heads = __ballot_sync(kFull, head);
+        if (heads != kFull) {
+          const unsigned above = lane == 31 ? 0u : (heads & (0xfffffffeu << lane));
+          const int end = above ? (__ffs(above) - 1) : 32;
+          const int maxrun = __reduce_max_sync(kFull, head ? end - lane : 0);
+          for (int d = 1; d < maxrun; d <<= 1) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+#pragma unroll
+              for (int f = 0; f < F; ++f) {
+                const float tt = __shfl_down_sync(kFull, val[q][f], d);
+                if (lane + d < end) val[q][f] += tt;
+              }
+          }
+        }
+        if (head && vj) {
+          uint32_t idx[8];
+          corner_indices<POW2>(ix, iy, iz, g.T, idx);
+          if (F == 2 && POW2 && g.T >= 2 && !(ix & 1)) {
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) {
+              const bool odd = idx[q] & 1;
+              const float4 v4 = odd ? make_float4(val[q + 1][0], val[q + 1][F - 1], val[q][0], val[q][F - 1])
+                                    : make_float4(val[q][0], val[q][F - 1], val[q + 1][0], val[q + 1][F - 1]);
+              red_add_v4(lvl + 4 * (size_t)(idx[q] >> 1), v4.x, v4.y, v4.z, v4.w);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) red_feat<F>(lvl, idx[q], val[q]);
+          }
+        }
+      }
+    }
+    if (plan.done != nullptr) {
+      __syncthreads();                              // every thread's reductions of this chunk have been issued ...
+      if (threadIdx.x == 0) {
+        __threadfence();                            // ... and are ordered (gpu scope) before the count
+        atomicAdd(plan.done + c, 1u);
       }
     }
   }
@@ -335,7 +492,7 @@ static int launch_bwd(const void* x, int64_t n, const float* dy, int64_t ds, con
   const size_t smem = (size_t)kTilePts * ((g.L * F) | 1) * sizeof(float);
   HBR_CUDA(cudaFuncSetAttribute(hash_bwd_kernel<F, POW2, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   hash_bwd_kernel<F, POW2, XT><<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(
-      static_cast<const XT*>(x), n, dy, ds, dt, g, l0, l1, nullptr);
+      static_cast<const XT*>(x), n, dy, ds, dt, g, l0, l1, nullptr, ChunkPlan{});
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -356,7 +513,7 @@ static int launch_bwd_rays(const RaySrc& rs, int64_t n, const float* dy, int64_t
   const size_t smem = (size_t)kTilePts * ((g.L * F) | 1) * sizeof(float);
   auto k = hash_bwd_kernel<F, POW2, RayPts>;
   HBR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(rs, n, dy, ds, dt, g, l0, l1, nullptr);
+  k<<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(rs, n, dy, ds, dt, g, l0, l1, nullptr, ChunkPlan{});
 
   HBR_LAUNCH_CHECK();
   return HBR_OK;
@@ -378,7 +535,44 @@ static int launch_bwd_pts(const float* x, int64_t n, const unsigned long long* n
   const size_t smem = (size_t)kTilePts * ((g.L * F) | 1) * sizeof(float);
   auto k = hash_bwd_kernel<F, POW2, float>;
   HBR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(x, n, dy, ds, dt, g, l0, l1, n_dev);
+  k<<<(unsigned)ceil_div(n, kTilePts), kHashThreads, smem, st>>>(x, n, dy, ds, dt, g, l0, l1, n_dev, ChunkPlan{});
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
+
+// one launch over all level chunks in chunk-major CTA order, counting finished CTAs per chunk (ChunkPlan above)
+template <int F, bool POW2, typename XT>
+static int launch_bwd_stream(const typename PointSrc<XT>::type src, int64_t n, const float* dy, int64_t ds, const HashGeom& g,
+                             float* dt, ChunkPlan plan, cudaStream_t st) {
+  const size_t smem = (size_t)kTilePts * ((g.L * F) | 1) * sizeof(float);
+  auto k = hash_bwd_kernel<F, POW2, XT, true>;
+  HBR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t tiles = ceil_div(n, kTilePts);
+  HBR_REQUIRE(tiles * plan.nchunks < (1LL << 31), "too many CTAs: %lld tiles x %d chunks", (long long)tiles, plan.nchunks);
+  plan.tiles = (unsigned)tiles;
+  k<<<(unsigned)(tiles * plan.nchunks), kHashThreads, smem, st>>>(src, n, dy, ds, dt, g, 0, 0, nullptr, plan);
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
+static int make_plan(const hbr_hash_geom* geom, const int* bounds, int nchunks, unsigned* done, ChunkPlan& plan) {
+  HBR_REQUIRE(bounds != nullptr && done != nullptr, "NULL level_bounds / done");
+  HBR_REQUIRE(nchunks >= 1 && nchunks <= geom->L, "nchunks=%d out of range [1,%d]", nchunks, geom->L);
+  HBR_REQUIRE(bounds[0] == 0 && bounds[nchunks] == geom->L, "level_bounds must run from 0 to L");
+  for (int c = 0; c < nchunks; ++c) HBR_REQUIRE(bounds[c] < bounds[c + 1], "level_bounds must increase");
+  plan = ChunkPlan{};
+  plan.nchunks = nchunks;
+  for (int c = 0; c <= nchunks; ++c) plan.bounds[c] = bounds[c];
+  for (int l = 0; l < geom->L; ++l) plan.order[l] = l;
+  plan.done = done;
+  return HBR_OK;
+}
+
+template <int F, bool POW2, typename XT>
+static int launch_bwd_lm(const typename PointSrc<XT>::type src, int64_t n, const float* dy, const HashGeom& g, float* dt,
+                         const ChunkPlan& plan, cudaStream_t st) {
+  const int64_t ctas = ceil_div(n, kLmPts);
+  HBR_REQUIRE(ctas < (1LL << 31), "too many points: %lld", (long long)n);
+  hash_bwd_lm_kernel<F, POW2, XT><<<(unsigned)ctas, kLmThreads, 0, st>>>(src, n, dy, dt, g, plan);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }
@@ -568,5 +762,129 @@ extern "C" int hbr_hash_encode_bwd_pts(const float* x, int64_t n_max, const unsi
                       : launch_bwd_pts<2, false>(x, n_max, n_dev, dy, dy_stride, g, dtable, level_begin, level_end, st);
     default: return p2 ? launch_bwd_pts<4, true>(x, n_max, n_dev, dy, dy_stride, g, dtable, level_begin, level_end, st)
                        : launch_bwd_pts<4, false>(x, n_max, n_dev, dy, dy_stride, g, dtable, level_begin, level_end, st);
+  }
+}
+
+extern "C" int64_t hbr_hash_bwd_stream_tiles(int64_t n) { return ceil_div(n, kTilePts); }
+extern "C" int64_t hbr_hash_bwd_lm_ctas(int64_t n) { return ceil_div(n, kLmPts); }
+
+static int make_lm_plan(const hbr_hash_geom* geom, const int* bounds, int nchunks, unsigned* done, ChunkPlan& plan) {
+  if (bounds == nullptr) {                          // one chunk over all levels, no counters
+    HBR_REQUIRE(done == nullptr, "done without level_bounds");
+    plan = ChunkPlan{};
+    plan.nchunks = 1;
+    plan.bounds[0] = 0;
+    plan.bounds[1] = geom->L;
+    for (int l = 0; l < geom->L; ++l) plan.order[l] = l;
+    if (getenv("HBR_LM_PAIR")) {                    // experiment: pairs (c, L-1-c) as chunks
+      plan.nchunks = geom->L / 2;
+      for (int c = 0; c < geom->L / 2; ++c) { plan.bounds[c] = 2 * c; plan.order[2 * c] = c; plan.order[2 * c + 1] = geom->L - 1 - c; }
+      plan.bounds[geom->L / 2] = geom->L;
+    }
+    return HBR_OK;
+  }
+  return make_plan(geom, bounds, nchunks, done, plan);
+}
+
+extern "C" int hbr_hash_encode_bwd_lm(const void* x, int x_dtype, int64_t n, const float* dy_lm, const hbr_hash_geom* geom,
+                                      float* dtable, const int* level_bounds, int nchunks, unsigned int* done, void* stream) {
+  if (int rc = check_geom(geom)) return rc;
+  HBR_REQUIRE(x_dtype == HBR_F32 || x_dtype == HBR_F16, "x_dtype %d", x_dtype);
+  HBR_REQUIRE(n > 0 && n < (1LL << 38), "n=%lld", (long long)n);
+  HBR_REQUIRE(x && dy_lm && dtable, "NULL pointer");
+  HBR_REQUIRE((uintptr_t)dtable % 16 == 0 && (uintptr_t)dy_lm % (4 * geom->F) == 0 && geom->E == 0, "alignment / E != 0");
+  ChunkPlan plan;
+  if (int rc = make_lm_plan(geom, level_bounds, nchunks, done, plan)) return rc;
+  const HashGeom g = to_device_geom(*geom);
+  cudaStream_t st = as_stream(stream);
+  const bool p2 = is_pow2(g.T), h = x_dtype == HBR_F16;
+#define HBR_BWD_LM(F_)                                                                                            \
+  (p2 ? (h ? launch_bwd_lm<F_, true, __half>((const __half*)x, n, dy_lm, g, dtable, plan, st)                      \
+           : launch_bwd_lm<F_, true, float>((const float*)x, n, dy_lm, g, dtable, plan, st))                       \
+      : (h ? launch_bwd_lm<F_, false, __half>((const __half*)x, n, dy_lm, g, dtable, plan, st)                     \
+           : launch_bwd_lm<F_, false, float>((const float*)x, n, dy_lm, g, dtable, plan, st)))
+  switch (g.F) {
+    case 1: return HBR_BWD_LM(1);
+    case 2: return HBR_BWD_LM(2);
+    default: return HBR_BWD_LM(4);
+  }
+#undef HBR_BWD_LM
+}
+
+extern "C" int hbr_hash_encode_bwd_rays_lm(const float* rays_o, const float* rays_d, const float* t, int64_t t_ray_stride,
+                                           int64_t R, int64_t S, const float* dy_lm, const hbr_hash_geom* geom, float* dtable,
+                                           const int* level_bounds, int nchunks, unsigned int* done, void* stream) {
+  if (int rc = check_geom(geom)) return rc;
+  if (int rc = check_rays(rays_o, rays_d, t, t_ray_stride, R, S)) return rc;
+  const int64_t n = R * S;
+  HBR_REQUIRE(n > 0 && n < (1LL << 38), "n=%lld", (long long)n);
+  HBR_REQUIRE(dy_lm && dtable, "NULL pointer");
+  HBR_REQUIRE((uintptr_t)dtable % 16 == 0 && (uintptr_t)dy_lm % (4 * geom->F) == 0 && geom->E == 0, "alignment / E != 0");
+  ChunkPlan plan;
+  if (int rc = make_lm_plan(geom, level_bounds, nchunks, done, plan)) return rc;
+  const HashGeom g = to_device_geom(*geom);
+  const RaySrc rs{rays_o, rays_d, t, S, t_ray_stride};
+  cudaStream_t st = as_stream(stream);
+  const bool p2 = is_pow2(g.T);
+  switch (g.F) {
+    case 1: return p2 ? launch_bwd_lm<1, true, RayPts>(rs, n, dy_lm, g, dtable, plan, st)
+                      : launch_bwd_lm<1, false, RayPts>(rs, n, dy_lm, g, dtable, plan, st);
+    case 2: return p2 ? launch_bwd_lm<2, true, RayPts>(rs, n, dy_lm, g, dtable, plan, st)
+                      : launch_bwd_lm<2, false, RayPts>(rs, n, dy_lm, g, dtable, plan, st);
+    default: return p2 ? launch_bwd_lm<4, true, RayPts>(rs, n, dy_lm, g, dtable, plan, st)
+                       : launch_bwd_lm<4, false, RayPts>(rs, n, dy_lm, g, dtable, plan, st);
+  }
+}
+
+
+extern "C" int hbr_hash_encode_bwd_stream(const void* x, int x_dtype, int64_t n, const float* dy, int64_t dy_stride,
+                                          const hbr_hash_geom* geom, float* dtable, const int* level_bounds, int nchunks,
+                                          unsigned int* done, void* stream) {
+  if (int rc = check_geom(geom)) return rc;
+  HBR_REQUIRE(x_dtype == HBR_F32 || x_dtype == HBR_F16, "x_dtype %d", x_dtype);
+  HBR_REQUIRE(n > 0 && n < (1LL << 38), "n=%lld", (long long)n);     // n = 0 would leave the counters at zero: not allowed
+  HBR_REQUIRE(x && dy && dtable, "NULL pointer");
+  HBR_REQUIRE(dy_stride >= geom->L * geom->F && (uintptr_t)dtable % 16 == 0, "dy_stride / dtable alignment");
+  ChunkPlan plan;
+  if (int rc = make_plan(geom, level_bounds, nchunks, done, plan)) return rc;
+  const HashGeom g = to_device_geom(*geom);
+  cudaStream_t st = as_stream(stream);
+  const bool p2 = is_pow2(g.T), h = x_dtype == HBR_F16;
+#define HBR_BWD_STREAM(F_)                                                                                                       \
+  (p2 ? (h ? launch_bwd_stream<F_, true, __half>((const __half*)x, n, dy, dy_stride, g, dtable, plan, st)                         \
+           : launch_bwd_stream<F_, true, float>((const float*)x, n, dy, dy_stride, g, dtable, plan, st))                          \
+      : (h ? launch_bwd_stream<F_, false, __half>((const __half*)x, n, dy, dy_stride, g, dtable, plan, st)                        \
+           : launch_bwd_stream<F_, false, float>((const float*)x, n, dy, dy_stride, g, dtable, plan, st)))
+  switch (g.F) {
+    case 1: return HBR_BWD_STREAM(1);
+    case 2: return HBR_BWD_STREAM(2);
+    default: return HBR_BWD_STREAM(4);
+  }
+#undef HBR_BWD_STREAM
+}
+
+extern "C" int hbr_hash_encode_bwd_rays_stream(const float* rays_o, const float* rays_d, const float* t, int64_t t_ray_stride,
+                                               int64_t R, int64_t S, const float* dy, int64_t dy_stride,
+                                               const hbr_hash_geom* geom, float* dtable, const int* level_bounds, int nchunks,
+                                               unsigned int* done, void* stream) {
+  if (int rc = check_geom(geom)) return rc;
+  if (int rc = check_rays(rays_o, rays_d, t, t_ray_stride, R, S)) return rc;
+  const int64_t n = R * S;
+  HBR_REQUIRE(n > 0 && n < (1LL << 38), "n=%lld", (long long)n);
+  HBR_REQUIRE(dy && dtable, "NULL pointer");
+  HBR_REQUIRE(dy_stride >= geom->L * geom->F && (uintptr_t)dtable % 16 == 0, "dy_stride / dtable alignment");
+  ChunkPlan plan;
+  if (int rc = make_plan(geom, level_bounds, nchunks, done, plan)) return rc;
+  const HashGeom g = to_device_geom(*geom);
+  const RaySrc rs{rays_o, rays_d, t, S, t_ray_stride};
+  cudaStream_t st = as_stream(stream);
+  const bool p2 = is_pow2(g.T);
+  switch (g.F) {
+    case 1: return p2 ? launch_bwd_stream<1, true, RayPts>(rs, n, dy, dy_stride, g, dtable, plan, st)
+                      : launch_bwd_stream<1, false, RayPts>(rs, n, dy, dy_stride, g, dtable, plan, st);
+    case 2: return p2 ? launch_bwd_stream<2, true, RayPts>(rs, n, dy, dy_stride, g, dtable, plan, st)
+                      : launch_bwd_stream<2, false, RayPts>(rs, n, dy, dy_stride, g, dtable, plan, st);
+    default: return p2 ? launch_bwd_stream<4, true, RayPts>(rs, n, dy, dy_stride, g, dtable, plan, st)
+                       : launch_bwd_stream<4, false, RayPts>(rs, n, dy, dy_stride, g, dtable, plan, st);
   }
 }

@@ -81,7 +81,11 @@ extern "C" int hbr_mlp_bwd_tc(const void* feat_, int feat_dtype, int64_t feat_st
   HBR_REQUIRE(feat_stride >= dims->in0 && dir_group >= 1, "bad stride / dir_group");
   HBR_REQUIRE((uintptr_t)dout % 16 == 0 && (uintptr_t)out % 16 == 0 && (uintptr_t)scratch % 256 == 0,
               "out / dout / scratch alignment");
-  HBR_REQUIRE(!dfeat || dfeat_stride >= dims->in0, "dfeat_stride too small");
+  if (dfeat && dfeat_stride == HBR_DFEAT_LEVEL_MAJOR)
+    HBR_REQUIRE(narrow_shape(dims) && dims->in0 == 32 && n % 2 == 0 && (uintptr_t)dfeat % 16 == 0 && n_dev == nullptr,
+                "level-major dfeat: in0 = 32, even n, 16-byte aligned buffer, no compacted list");
+  else
+    HBR_REQUIRE(!dfeat || dfeat_stride >= dims->in0, "dfeat_stride too small");
   cudaStream_t st = as_stream(stream);
   uint8_t* sc = static_cast<uint8_t*>(scratch);
   if (narrow_shape(dims))

@@ -31,6 +31,11 @@
 #error "define HBR_OP (tc::OpBf16 | tc::OpF16) and HBR_OPNS before including mlp_tc_impl.cuh"
 #endif
 
+// fused backward (one tile group + scatter warps): d(feature) tiles in flight between the tile group and the scatter warps
+#ifndef HBR_RING_SLOTS
+#define HBR_RING_SLOTS 2
+#endif
+
 namespace hbr {
 namespace HBR_OPNS {
 using namespace tc;
@@ -984,10 +989,11 @@ struct BwdSmem {
   // scatter variant with one tile group (SCAT = 11): two 16 KB slots for the d(feature) tiles on their way to the scatter
   // warps (with two groups the slot is the group's own dead h2 region)
   static constexpr int ring_slot = kTile * 32 * 4;
+  static constexpr int ring_slots = HBR_RING_SLOTS;                     // one group: d(feature) tiles in flight towards the scatter warps
   static constexpr int off_ring = off_grp + G * grp_bytes;
-  static constexpr int off_bar = off_ring + (G == 1 && K0P == 32 ? 2 * ring_slot : 0);   // full[G], doneA[G], doneB[G], startB[G], dfull[2], dempty[2]
+  static constexpr int off_bar = off_ring + (G == 1 && K0P == 32 ? ring_slots * ring_slot : 0);   // full[G], doneA[G], doneB[G], startB[G], dfull[slots], dempty[slots]
   // normalised sample positions of the scatter warps' current / next tile: [2][128 points][3] fp32
-  static constexpr int off_pos = off_bar + (4 * G + 4) * 8 + 16;
+  static constexpr int off_pos = off_bar + (4 * G + 2 * ring_slots) * 8 + 16;
   static constexpr int total = off_pos + 2 * kTile * 3 * 4;
   static_assert(total <= 232448, "shared memory budget exceeded");
 };
@@ -1147,9 +1153,10 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   uint8_t* wsm = sm;
   float* bias = reinterpret_cast<float*>(sm + SM::off_bias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM::off_bar);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4 * G + 4);
-  uint64_t* dfull = bars + 4 * G;                                        // [2] d(feature) slot written (128 arrivals)
-  uint64_t* dempty = bars + 4 * G + 2;                                   // [2] slot read by every scatter lane
+  constexpr int kSlots = SM::ring_slots;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4 * G + 2 * kSlots);
+  uint64_t* dfull = bars + 4 * G;                                        // [kSlots] d(feature) slot written (128 arrivals)
+  uint64_t* dempty = bars + 4 * G + kSlots;                              // [kSlots] slot read by every scatter lane
   const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   constexpr int kIssuerWarp = 4 * G + SCAT;
   if (TRACE && blockIdx.x == 0 && threadIdx.x == 0) trace[2000] = clock64();
@@ -1161,7 +1168,7 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       mbar_init(bars + 2 * G + g, 1);
       mbar_init(bars + 3 * G + g, 1);
     }
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < kSlots; ++q) {
       mbar_init(dfull + q, kTile);
       mbar_init(dempty + q, SCAT > 0 ? SCAT * 32 : 1);
     }
@@ -1302,7 +1309,7 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         }
         asm volatile("bar.sync 3, %0;" ::"n"(SCAT * 32) : "memory");
         // slot of this tile: the group's h2 region (two groups), or the ring slot k & 1 (one group)
-        const int slot = G == 2 ? g : (int)(k & 1);
+        const int slot = G == 2 ? g : (int)(k % kSlots);
         const float2* stg = reinterpret_cast<const float2*>(G == 2 ? sm + SM::off_grp + g * SM::grp_bytes + SM::h2
                                                                    : sm + SM::off_ring + slot * SM::ring_slot);
         mbar_wait(dfull + slot, (fpar >> slot) & 1u);
@@ -1491,6 +1498,9 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   } while (0)
     const bool vec_ok = in0 == K0P && feat_stride == K0P && ((uintptr_t)feat & 15) == 0;
     const bool dvec_ok = dfeat != nullptr && in0 == K0P && dfeat_stride == K0P && ((uintptr_t)dfeat & 15) == 0 && K0P <= 32;
+    // dfeat_stride == HBR_DFEAT_LEVEL_MAJOR: d(features) leave as (K0P/2 levels, n, 2) -- what the level-major scatter-add
+    // (hash_grid.cu: hash_bwd_lm_kernel) reads with coalesced 8-byte loads, level by level (checked by the entry point)
+    const bool dlm = dfeat != nullptr && dfeat_stride == HBR_DFEAT_LEVEL_MAJOR && K0P <= 32;
     int tgi = 0;
     (void)tgi;
     // The next tile's fp32 feature rows travel into the (by then dead) c2 tile with cp.async during the last backward
@@ -1651,8 +1661,8 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         // scatter warps take over: 128 arrivals (release) on dfull
         float df[K0P];
         tmem_ld<K0P>(taddr, df);
-        const int slot = G == 2 ? g : (tgi & 1);
-        if (G == 1 && tgi >= 2) {                  // ring slot: its previous tile (two tiles back) has been read
+        const int slot = G == 2 ? g : (tgi % kSlots);
+        if (G == 1 && tgi >= kSlots) {             // ring slot: its previous tile (kSlots tiles back) has been read
           mbar_wait(dempty + slot, (ephase >> slot) & 1u);
           ephase ^= 1u << slot;
         }
@@ -1671,7 +1681,21 @@ mlp_bwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         tmem_ld<K0P>(taddr, df);
 #pragma unroll
         for (int k = 0; k < K0P; ++k) df[k] *= ginv;
-        if (dvec_ok) {
+        if (dlm) {
+          // rows -> the (dead) h2 tile as [level][point] float2 (conflict-free), then the tile's 1 KB run of every level
+          // goes out with lane-contiguous 16-byte stores
+          float2* stg = reinterpret_cast<float2*>(h2);
+#pragma unroll
+          for (int l = 0; l < K0P / 2; ++l) stg[l * kTile + r] = make_float2(df[2 * l], df[2 * l + 1]);
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+          const float4* s4 = reinterpret_cast<const float4*>(h2);
+#pragma unroll
+          for (int it = 0; it < K0P / 4; ++it) {
+            const int idx = it * kTile + r, l = idx >> 6, j = idx & 63;            // 64 float4 = 128 points per level
+            if (tile * kTile + 2 * j < n)                                          // n is even: a pair is valid or not
+              reinterpret_cast<float4*>(dfeat + ((size_t)l * n + tile * kTile) * 2)[j] = s4[idx];
+          }
+        } else if (dvec_ok) {
           // rows -> the (dead) h2 tile as fp32 with an XOR swizzle on the 16-byte chunk index, then lane-contiguous
           // float4 stores of the tile's contiguous 128*K0P*4-byte block of dfeat (measured: eight 16-byte stores per
           // thread straight from registers, 32 partial sectors per instruction, are ~400 cycles slower per tile)

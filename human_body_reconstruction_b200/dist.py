@@ -109,6 +109,11 @@ class _GradExchange:
     def chunks(self, m) -> int:                               # pieces the last backward node of m should publish in
         return 1
 
+    def stream_plan(self, m, L: int, n_points: int = 0):
+        """Level chunks for a STREAMED exchange of the last table backward (one producer launch + one exchange launch running
+        side by side, PeerGradAllReduce(streamed=True)), or None: the caller then runs level_chunks() launch by launch."""
+        return None
+
     # -- module side ----------------------------------------------------------------------------------------------
     def remove(self):
         for m in self.modules:
@@ -259,11 +264,14 @@ class PeerGradAllReduce(_GradExchange):
     the next step's end of backward instead of letting the optimiser run on."""
 
     def __init__(self, encoder, mlp, group=None, average: bool = True, transport: str = "ipc", ctas: int = 0,
-                 overlap: bool = False, chunks: int = 2):
+                 overlap: bool = False, chunks: int = 2, streamed: bool = False):
         """overlap=False: one all-reduce of the whole region behind the backward pass.  overlap=True: the LAST table backward
         of the pass runs in `chunks` level chunks and every published piece (the MLP gradient first, then each level chunk)
         is all-reduced at once by a small grid (`ctas`, default 32) on a high-priority side stream while the next chunk's
-        scatter-add still runs on the compute stream."""
+        scatter-add still runs on the compute stream.  streamed=True (with overlap): the chunks are not separate launches --
+        ONE scatter-add launch finishes them in order and counts finished CTAs per chunk (hbr_hash_encode_bwd*_stream), ONE
+        exchange launch beside it (hbr_allreduce_peer_stream) sends each chunk as soon as its count is complete on every
+        rank: no launch gaps, no per-chunk tails, and the flag barriers of a chunk hide behind the next chunk's scatter-add."""
         from .peer import PeerRegion
         n_tab = encoder.L * encoder.T * encoder.F
         n_mlp = mlp._flat_params().numel()
@@ -279,6 +287,8 @@ class PeerGradAllReduce(_GradExchange):
         self._side = torch.cuda.Stream(device=self.region.device, priority=-1) if overlap else None
         self._base = self.region.tensor.data_ptr()
         self._side_used = False
+        self.streamed = bool(streamed and overlap)
+        self._done = torch.zeros(64, dtype=torch.int32, device=self.region.device)   # finished CTAs per level chunk
         super().__init__([encoder, mlp], group=group, average=average)
 
     def remove(self):
@@ -295,9 +305,46 @@ class PeerGradAllReduce(_GradExchange):
 
     def _zero_buffers(self):
         self.region.tensor.zero_()                            # one memset over [table | MLP]
+        if self.streamed:
+            self._done.zero_()
 
     def _start_on_publish(self) -> bool:
         return self.overlap
+
+    def stream_plan(self, m, L: int, n_points: int = 0):
+        if not self.streamed or m is not self._enc or n_points > self.CHUNK_MAX_POINTS or n_points <= 0:
+            return None
+        ch = self.level_chunks(m, L, n_points)
+        return ch if len(ch) > 1 else None
+
+    @property
+    def done(self) -> torch.Tensor:
+        return self._done
+
+    def exchange_streamed(self, chunks, need: int, after=(), include_mlp: bool = False):
+        """Called by the last table backward right AFTER it has enqueued the producer (ops.hash_encode_bwd*_lm or *_stream with
+        `chunks` and self.done) on the compute stream; `need` = the count a chunk's done word reaches when the chunk is
+        complete (ops.hash_bwd_lm_ctas / hash_bwd_stream_tiles).  Enqueues the exchange of [MLP gradient (include_mlp: it is
+        complete once the events in `after` have fired) | level chunks] on the side stream, which waits for `after` only --
+        not for the scatter-add it runs beside."""
+        enc, mlp = self._enc, self._mlp
+        per_level = enc.T * enc.F
+        tiles = int(need)
+        pieces = []
+        if include_mlp:
+            off = (self._slices[id(mlp)].data_ptr() - self._base) // 4
+            pieces.append((off, self.region.n - off, 0, 0))
+            self._pub[id(mlp)].append((0, self._slices[id(mlp)].numel()))
+        for c, (l0, l1) in enumerate(chunks):
+            pieces.append((l0 * per_level, (l1 - l0) * per_level, tiles, c))
+        self._pub[id(enc)].append((0, enc.L * per_level))
+        for ev in after:
+            if ev is not None:
+                self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            self.region.all_reduce_stream(pieces, self._done, scale=self._scale(), ctas=self.ctas)
+        self._side_used = True
+        self.bytes_reduced += 4 * sum(p[1] for p in pieces)
 
     def _reduce(self, m, offset, n):
         off = (self._buffer(m).data_ptr() - self._base) // 4 + offset
@@ -340,8 +387,12 @@ def attach_grad_allreduce(encoder, mlp, group=None, kind: str = "auto", **peer_k
         return GradAllReduce(encoder, mlp, group=group, chunks=int(peer_kw.get("chunks", 1)) if kind == "nccl" else 1)
     world = dist.get_world_size(group)
     kw = dict(peer_kw)
-    kw.setdefault("overlap", True)        # measured best at 4 096 rays/GPU: 2 level chunks, 32 CTAs on the side stream
-    kw.setdefault("chunks", 2)            # (W=8: 0.656 ms/step against 0.712 behind the backward, 0.671 with 4 chunks)
+    kw.setdefault("overlap", True)        # launch-per-chunk form, measured best at 4 096 rays/GPU: 2 level chunks, 32 CTAs on
+    kw.setdefault("chunks", 2)            # the side stream (W=8: 0.656 ms/step against 0.712 behind the backward, 0.671 with 4)
+    if kw.get("streamed", None) is None:
+        kw["streamed"] = True             # one scatter-add launch + one exchange launch side by side (8 level chunks)
+        if "chunks" not in peer_kw:
+            kw["chunks"] = 8
     if kw.get("transport", "auto") == "auto":
         kw["transport"] = "ipc" if world == 2 else "symm"
     red, err = None, None

@@ -44,6 +44,14 @@ class _HashEncodeFn(torch.autograd.Function):
             # enqueued: that chunk's all-reduce travels over NVLink while the next chunk's scatter-add still runs.  The
             # exchange hands the reduced buffer to .grad at the end of backward; nothing is returned to autograd here.
             g, last = dp.enter_backward(enc)
+            plan = dp.stream_plan(enc, L, x.shape[0]) if last else None
+            if plan is not None:
+                # streamed exchange (dist.PeerGradAllReduce(streamed=True)): one scatter-add launch finishing the level
+                # chunks in order, one exchange launch beside it on the reducer's side stream
+                ev_pre = torch.cuda.current_stream().record_event()
+                ops.hash_encode_bwd_stream(x, dy[:, : L * F], ctx.geom, g, plan, dp.done)
+                dp.exchange_streamed(plan, ops.hash_bwd_stream_tiles(x.shape[0]), after=(ev_pre,))
+                return (None, None) + (None,) * L
             for l0, l1 in (dp.level_chunks(enc, L, x.shape[0]) if last else [(0, L)]):
                 ops.hash_encode_bwd(x, dy[:, : L * F], ctx.geom, g, l0, l1)
                 if last:

@@ -98,6 +98,65 @@ def hash_encode_bwd_rays(rays_o, rays_d, t, dy, geom: HashGeom, dtable, level_be
                                          C.byref(geom), ptr(dtable), int(level_begin), int(level_end), stream()))
 
 
+def _bounds(chunks, L):
+    b = [int(chunks[0][0])] + [int(c[1]) for c in chunks]
+    if (b[0] != 0 or b[-1] != L or any(b[i] >= b[i + 1] for i in range(len(b) - 1))
+            or any(int(chunks[i][0]) != int(chunks[i - 1][1]) for i in range(1, len(chunks)))):
+        raise ValueError(f"level chunks {chunks} do not partition [0, {L})")
+    return (C.c_int * len(b))(*b), len(b) - 1
+
+
+def hash_bwd_stream_tiles(n_points: int) -> int:
+    """CTAs per level chunk of the streamed scatter-add = the count a chunk's `done` word reaches when it is complete."""
+    return int(lib().hbr_hash_bwd_stream_tiles(int(n_points)))
+
+
+def hash_encode_bwd_stream(x, dy, geom: HashGeom, dtable, chunks, done):
+    """hash_encode_bwd over all levels in ONE launch that finishes the level chunks [(l0, l1), ...] in order and counts
+    finished CTAs per chunk into `done` (int32 device tensor, zeroed by the caller): the producer side of the streamed
+    gradient exchange (peer.PeerRegion.all_reduce_stream)."""
+    require_cuda(x, dy, dtable, done)
+    x = x.contiguous()
+    dy = _f32c(dy)
+    b, nch = _bounds(chunks, geom.L)
+    check(lib().hbr_hash_encode_bwd_stream(ptr(x), _xdtype(x), x.shape[0], ptr(dy), dy.stride(0), C.byref(geom), ptr(dtable),
+                                           b, nch, ptr(done), stream()))
+
+
+def hash_encode_bwd_rays_stream(rays_o, rays_d, t, dy, geom: HashGeom, dtable, chunks, done):
+    require_cuda(rays_o, rays_d, t, dy, dtable, done)
+    R, S = rays_o.shape[0], t.shape[-1]
+    b, nch = _bounds(chunks, geom.L)
+    check(lib().hbr_hash_encode_bwd_rays_stream(ptr(rays_o), ptr(rays_d), ptr(t), _t_stride(t, S), R, S, ptr(dy), dy.stride(0),
+                                                C.byref(geom), ptr(dtable), b, nch, ptr(done), stream()))
+
+
+def hash_bwd_lm_ctas(n_points: int) -> int:
+    """CTAs of the level-major scatter-add = the count a chunk's `done` word reaches when the chunk is complete."""
+    return int(lib().hbr_hash_bwd_lm_ctas(int(n_points)))
+
+
+def hash_encode_bwd_lm(x, dy_lm, geom: HashGeom, dtable, chunks=None, done=None):
+    """Scatter-add from LEVEL-MAJOR d(features) dy_lm (L, N, F) (mlp_bwd_tc(..., level_major=True)): a co-resident grid
+    walks the levels in order, so the table gradient is finished level by level; with chunks = [(l0, l1), ...] and `done`
+    (int32 device tensor, zeroed by the caller) every CTA counts itself into done[c] when it has finished chunk c."""
+    require_cuda(x, dy_lm, dtable)
+    x = x.contiguous()
+    assert dy_lm.is_contiguous() and dy_lm.dtype == torch.float32 and dy_lm.shape == (geom.L, x.shape[0], geom.F)
+    b, nch = _bounds(chunks, geom.L) if chunks is not None else (None, 0)
+    check(lib().hbr_hash_encode_bwd_lm(ptr(x), _xdtype(x), x.shape[0], ptr(dy_lm), C.byref(geom), ptr(dtable), b, nch,
+                                       ptr(done), stream()))
+
+
+def hash_encode_bwd_rays_lm(rays_o, rays_d, t, dy_lm, geom: HashGeom, dtable, chunks=None, done=None):
+    require_cuda(rays_o, rays_d, t, dy_lm, dtable)
+    R, S = rays_o.shape[0], t.shape[-1]
+    assert dy_lm.is_contiguous() and dy_lm.dtype == torch.float32 and dy_lm.shape == (geom.L, R * S, geom.F)
+    b, nch = _bounds(chunks, geom.L) if chunks is not None else (None, 0)
+    check(lib().hbr_hash_encode_bwd_rays_lm(ptr(rays_o), ptr(rays_d), ptr(t), _t_stride(t, S), R, S, ptr(dy_lm), C.byref(geom),
+                                            ptr(dtable), b, nch, ptr(done), stream()))
+
+
 def occupancy_update(pts, alpha, grid, mu, sigma: float, flags2):
     """Volume_Renderer.update_grid (vol_renderer.py:116-131) in place on `grid` ((G,G,G) bool)."""
     require_cuda(pts, alpha, grid, flags2)
@@ -482,23 +541,36 @@ def mlp_tc_reduce_grads(dims: MlpDims, n: int, dparams, device):
 
 
 def mlp_bwd_tc(feat, dirs, dir_group, params, dims: MlpDims, out, dout, want_dfeat, want_ddirs, dparams,
-               operand: int = HBR_BF16, grad_scale: float = 1.0, defer_reduce: bool = False, n_dev=None, dir_rows=None):
+               operand: int = HBR_BF16, grad_scale: float = 1.0, defer_reduce: bool = False, n_dev=None, dir_rows=None,
+               level_major: bool = False):
     """`out` is the forward output (N,4): the kernel takes ELU' / LeakyReLU' from it instead of recomputing the last layer.
     defer_reduce: leave the per-CTA gradient rows in the scratch; the caller runs mlp_tc_reduce_grads (on any stream that
-    waits for this one) before anything else uses the scratch or reads dparams."""
+    waits for this one) before anything else uses the scratch or reads dparams.
+    level_major: dfeat comes back as (in0/2, N, 2) -- level-major, for hash_encode_bwd*_lm (see mlp_level_major_ok)."""
     n = feat.shape[0]
-    dfeat = torch.empty((n, dims.in0), device=feat.device, dtype=torch.float32) if want_dfeat else None
+    if level_major and want_dfeat:
+        dfeat = torch.empty((dims.in0 // 2, n, 2), device=feat.device, dtype=torch.float32)
+    else:
+        level_major = False
+        dfeat = torch.empty((n, dims.in0), device=feat.device, dtype=torch.float32) if want_dfeat else None
     ddirs = torch.zeros_like(dirs) if want_ddirs else None
     scratch = mlp_tc_scratch(dims, feat.device)
     key = _image_key(params, operand)
     ready = 1 if _tc_image.get(id(scratch)) == key else 0
     check(lib().hbr_mlp_bwd_tc(ptr(feat), _feat_dtype(feat, operand), feat.stride(0), ptr(dirs), dir_group, n, ptr(params),
-                               C.byref(dims), operand, ptr(out), ptr(dout), ptr(dfeat), dims.in0, ptr(ddirs), ptr(dparams),
+                               C.byref(dims), operand, ptr(out), ptr(dout), ptr(dfeat),
+                               _lib.HBR_DFEAT_LEVEL_MAJOR if level_major else dims.in0, ptr(ddirs), ptr(dparams),
                                float(grad_scale), ptr(scratch), ready, 1 if defer_reduce else 0, ptr(n_dev), ptr(dir_rows),
                                stream()))
     _lib.STATS.launches -= ready + (1 if defer_reduce else 0)    # no prep kernel / no reduce kernel in this call
     _tc_image[id(scratch)] = key
     return dfeat, ddirs
+
+
+def mlp_level_major_ok(geom: HashGeom, dims: MlpDims, n_points: int) -> bool:
+    """The reference's configuration family (F = 2, L = 16, E = 0 -> in0 = 32) with an even point count: the MLP backward
+    can write d(features) level-major for hash_encode_bwd*_lm."""
+    return geom.F == 2 and geom.L == 16 and geom.E == 0 and dims.in0 == 32 and n_points % 2 == 0 and n_points > 0
 
 
 def field_fwd_tc(x, table, geom: HashGeom, dirs, dir_group, params, dims: MlpDims, operand: int = HBR_BF16):

@@ -122,6 +122,25 @@ class PeerRegion:
                                        self._status_ptr, _lib.stream()))
         self.calls += 1
 
+    def all_reduce_stream(self, pieces, done: Optional[torch.Tensor], scale: float = 1.0, ctas: int = 0):
+        """The exchange as ONE launch over `pieces` = [(offset, n, need, done_index), ...] (floats, multiples of 4): piece i
+        travels as soon as done[done_index] has reached `need` on this rank (need = 0: complete by stream order) and every
+        other rank reports the same -- hbr_allreduce_peer_stream.  Enqueue it on a side stream AFTER the producer kernel
+        (ops.hash_encode_bwd*_stream) has been enqueued on the compute stream: the two run side by side."""
+        k = len(pieces)
+        for off, n, _need, _idx in pieces:
+            if off % 4 or n % 4 or off < 0 or n <= 0 or off + n > self.n:
+                raise ValueError("pieces must be multiples of 4 floats inside the region")
+        offs = (C.c_int64 * k)(*[int(p[0]) for p in pieces])
+        ns = (C.c_int64 * k)(*[int(p[1]) for p in pieces])
+        need = (C.c_uint * k)(*[int(p[2]) for p in pieces])
+        idx = (C.c_int * k)(*[int(p[3]) for p in pieces])
+        mc = C.c_void_p(self.multicast_ptr) if self.multicast_ptr else None
+        dptr = C.c_void_p(done.data_ptr()) if done is not None else None
+        check(lib().hbr_allreduce_peer_stream(self._bufs, self._flags, mc, self.rank, self.world, k, offs, ns, need, idx, dptr,
+                                              float(scale), int(ctas), self._status_ptr, _lib.stream()))
+        self.calls += 1
+
     def poll_status(self):
         """Enqueue a 4-byte copy of the status word to pinned host memory on the current stream (capturable; no sync)."""
         word = self._whole[self._status_off // 4: self._status_off // 4 + 1].view(torch.int32)

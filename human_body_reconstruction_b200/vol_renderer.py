@@ -134,9 +134,19 @@ class _FieldRaysFn(torch.autograd.Function):
             return (None, None, None, ddirs, None, None) + tuple(g[i] for i in range(L)) + tuple(mlp._grad_views(dflat))
         # the reduction of the MLP kernel's per-CTA gradient rows runs on a side stream, beside the hash-grid backward
         defer = ctx.want_tab
+        n_pts = feat16.shape[0]
+        dpe = enc._dp if ctx.want_tab else None
+        plan, lm = None, False
+        if dpe is not None:
+            g, last = dpe.enter_backward(enc)
+            # streamed exchange (dist.PeerGradAllReduce(streamed=True)): the last table backward of the pass finishes the
+            # table gradient level chunk by level chunk while the all-reduce kernel beside it sends the finished chunks; the
+            # MLP kernel then writes d(features) level-major for the level-major scatter-add
+            plan = dpe.stream_plan(enc, L, n_pts) if last else None
+            lm = plan is not None and STREAM_LEVEL_MAJOR and ops.mlp_level_major_ok(ctx.geom, ctx.dims, n_pts)
         dfeat, ddirs = ops.mlp_bwd_tc(feat16, dirs, ctx.S, flat, ctx.dims, out.detach(), dout.float().contiguous(), ctx.want_tab,
                                       ctx.needs_input_grad[3], dflat, operand=ctx.operand, grad_scale=mlp.tc_grad_scale,
-                                      defer_reduce=defer)
+                                      defer_reduce=defer, level_major=lm)
         cur, side = torch.cuda.current_stream(), _side_stream(dout.device)
         if defer:
             side.wait_stream(cur)
@@ -154,9 +164,25 @@ class _FieldRaysFn(torch.autograd.Function):
         if not ctx.want_tab:
             join_mlp()
             return (None, None, None, ddirs, None, None) + (None,) * L + gm
-        dpe = enc._dp
         if dpe is not None:
-            g, last = dpe.enter_backward(enc)
+            if plan is not None:
+                # ONE scatter-add launch that finishes the level chunks in order, ONE exchange launch on the reducer's side
+                # stream beside it (it waits for the MLP kernels only, not for the scatter-add)
+                ev_pre = cur.record_event()
+                if lm:
+                    ops.hash_encode_bwd_rays_lm(rays_o, rays_d, t, dfeat, ctx.geom, g, plan, dpe.done)
+                    need = ops.hash_bwd_lm_ctas(n_pts)
+                else:
+                    ops.hash_encode_bwd_rays_stream(rays_o, rays_d, t, dfeat, ctx.geom, g, plan, dpe.done)
+                    need = ops.hash_bwd_stream_tiles(n_pts)
+                with_mlp = dpm is dpe and last_m
+                ev_mlp = side.record_event() if (defer and with_mlp) else None
+                dpe.exchange_streamed(plan, need, after=(ev_pre, ev_mlp), include_mlp=with_mlp)
+                if defer:
+                    cur.wait_stream(side)
+                if dpm is not None and last_m and not with_mlp:
+                    dpm.publish(mlp, dflat)
+                return (None, None, None, ddirs, None, None) + (None,) * L + gm
             for l0, l1 in (dpe.level_chunks(enc, L, feat16.shape[0]) if last else [(0, L)]):
                 ops.hash_encode_bwd_rays(rays_o, rays_d, t, dfeat, ctx.geom, g, l0, l1)
                 if l0 == 0:
@@ -250,6 +276,9 @@ class _FieldCompactFn(torch.autograd.Function):
 # environment switch exists for A/B measurements (bench.py --no-fuse-scatter)
 FUSE_SCATTER = os.environ.get("HBR_FUSE_SCATTER", "1") != "0"
 FUSE_SCATTER_MAX_POINTS = 1 << 21
+# streamed gradient exchange (multi-GPU): producer = the level-major scatter-add (co-resident grid walking the levels in
+# order, hbr_hash_encode_bwd_rays_lm) or the tile-major kernel launched chunk-major (hbr_hash_encode_bwd_rays_stream)
+STREAM_LEVEL_MAJOR = os.environ.get("HBR_STREAM_LEVEL_MAJOR", "1") != "0"
 
 _SIDE = {}
 

@@ -90,6 +90,31 @@ int hbr_hash_encode_bwd_rays(const float* rays_o, const float* rays_d, const flo
                              int64_t S, const float* dy, int64_t dy_stride, const hbr_hash_geom* geom_host, float* dtable,
                              int level_begin, int level_end, void* stream);
 
+/* a5 for the multi-GPU training step: the whole scatter-add in ONE launch that walks `nchunks` level chunks
+ * [level_bounds[c], level_bounds[c+1]) (level_bounds[0] = 0, level_bounds[nchunks] = L) in chunk-major CTA order and
+ * counts every finished CTA into done[c] (nchunks device words the caller zeroes beforehand; chunk c of dtable is
+ * complete when done[c] == ceil(n / 128), the value hbr_hash_bwd_stream_tiles returns).  hbr_allreduce_peer_stream,
+ * running beside it on another stream, exchanges chunk c over NVLink while the later chunks are still accumulated. */
+int64_t hbr_hash_bwd_stream_tiles(int64_t n);
+int hbr_hash_encode_bwd_stream(const void* x, int x_dtype, int64_t n, const float* dy, int64_t dy_stride,
+                               const hbr_hash_geom* geom_host, float* dtable, const int* level_bounds, int nchunks,
+                               unsigned int* done, void* stream);
+int hbr_hash_encode_bwd_rays_stream(const float* rays_o, const float* rays_d, const float* t, int64_t t_ray_stride, int64_t R,
+                                    int64_t S, const float* dy, int64_t dy_stride, const hbr_hash_geom* geom_host,
+                                    float* dtable, const int* level_bounds, int nchunks, unsigned int* done, void* stream);
+
+/* a5, level-major traversal: dy_lm is (L, n, F) -- hbr_mlp_bwd_tc writes d(features) so with dfeat_stride =
+ * HBR_DFEAT_LEVEL_MAJOR -- and a co-resident grid (hbr_hash_bwd_lm_ctas(n) CTAs, 1024 points each, positions kept in
+ * registers) walks the levels in order, all CTAs roughly in lockstep, so the table gradient is finished level by level.
+ * level_bounds / nchunks / done as for hbr_hash_encode_bwd_stream (chunk c complete when done[c] == hbr_hash_bwd_lm_ctas(n));
+ * all three NULL / 0: no counters.  Same arithmetic, run merging and pairing as hbr_hash_encode_bwd; E must be 0. */
+int64_t hbr_hash_bwd_lm_ctas(int64_t n);
+int hbr_hash_encode_bwd_lm(const void* x, int x_dtype, int64_t n, const float* dy_lm, const hbr_hash_geom* geom_host,
+                           float* dtable, const int* level_bounds, int nchunks, unsigned int* done, void* stream);
+int hbr_hash_encode_bwd_rays_lm(const float* rays_o, const float* rays_d, const float* t, int64_t t_ray_stride, int64_t R,
+                                int64_t S, const float* dy_lm, const hbr_hash_geom* geom_host, float* dtable,
+                                const int* level_bounds, int nchunks, unsigned int* done, void* stream);
+
 /* Parity probe: the hash indices hash_encoding.py:161-162 computes (hash_func, :41-55), and the
  * n-linear weights of :142-143.  idx: (L,n,8) int32, w: (L,n,8) fp32 (either may be NULL). */
 int hbr_hash_indices(const void* x, int x_dtype, int64_t n, const hbr_hash_geom* geom_host,
@@ -146,6 +171,9 @@ int hbr_mlp_tc_reduce_grads(const hbr_mlp_dims* dims, int64_t n, void* scratch, 
 int hbr_mlp_fwd_tc(const void* feat, int feat_dtype, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                    const float* params, const hbr_mlp_dims* dims, int operand, float* out, void* scratch, int image_ready,
                    const unsigned long long* n_dev, const int32_t* dir_rows, void* stream);
+/* dfeat_stride == HBR_DFEAT_LEVEL_MAJOR: dfeat is written as (in0/2 levels, n, 2) instead of (n, in0) -- the layout
+ * hbr_hash_encode_bwd*_lm reads level by level with coalesced loads (in0 = 32, even n, 16-byte aligned, n_dev NULL). */
+#define HBR_DFEAT_LEVEL_MAJOR (-1)
 int hbr_mlp_bwd_tc(const void* feat, int feat_dtype, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                    const float* params, const hbr_mlp_dims* dims, int operand, const float* out, const float* dout,
                    float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams, float grad_scale, void* scratch,
@@ -350,6 +378,16 @@ int hbr_peer_release(void* ptr);
  * rank.  status: optional device word set to 1 if a barrier timed out (10 s) -- the buffer is then undefined. */
 int hbr_allreduce_peer(void* const* bufs, void* const* flags, void* multicast, int rank, int world, int64_t n, float scale,
                        int ctas, unsigned int* status, void* stream);
+
+/* The same exchange as ONE launch over a list of pieces [piece_off[i], piece_off[i] + piece_n[i]) of the region (floats,
+ * multiples of 4; at most HBR_MAX_LEVELS + 2 pieces), meant to run on a side stream BESIDE the kernel that produces them:
+ * piece i is exchanged as soon as the local counter done[piece_done_idx[i]] has reached piece_need[i] (0 = complete when
+ * the kernel starts) and the other ranks report the same.  Enqueue it AFTER the producer (hbr_hash_encode_bwd*_stream) so
+ * that a device that serialises the two launches still terminates.  Same result, status and grid rules as above. */
+int hbr_allreduce_peer_stream(void* const* bufs, void* const* flags, void* multicast, int rank, int world, int npieces,
+                              const int64_t* piece_off, const int64_t* piece_n, const unsigned int* piece_need,
+                              const int* piece_done_idx, const unsigned int* done, float scale, int ctas,
+                              unsigned int* status, void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,3 +46,25 @@ for name, fn in (("fwd f32 ", lambda: ops.hash_encode_fwd_rays(o, d, t, table, g
                  ("fwd bf16", lambda: ops.hash_encode_fwd_rays(o, d, t, table, geom, _lib.HBR_BF16)),
                  ("bwd     ", lambda: ops.hash_encode_bwd_rays(o, d, t, dy, geom, g))):
     print(f"tile={os.environ.get('HBR_EXTRA_NVCC', 'default'):24s} rays={rays} {name}: flushed {timeit(fn, True):7.1f} us   warm {timeit(fn, False):7.1f} us", flush=True)
+
+# streamed scatter-add (multi-GPU producer): one launch finishing k level chunks in order + per-chunk CTA counts
+done = torch.zeros(64, dtype=torch.int32, device=dev)
+for k in (1, 2, 4, 8, 16):
+    step = 16 // k
+    chunks = [(l0, l0 + step) for l0 in range(0, 16, step)]
+    if k == 1:
+        continue
+    fn = lambda: (done.zero_(), ops.hash_encode_bwd_rays_stream(o, d, t, dy, geom, g, chunks, done))
+    print(f"bwd streamed, {k:2d} chunks: flushed {timeit(fn, True):7.1f} us   warm {timeit(fn, False):7.1f} us", flush=True)
+    launches = lambda: [ops.hash_encode_bwd_rays(o, d, t, dy, geom, g, l0, l1) for l0, l1 in chunks]
+    print(f"bwd {k:2d} launches       : flushed {timeit(launches, True):7.1f} us   warm {timeit(launches, False):7.1f} us", flush=True)
+
+# level-major scatter-add (co-resident grid walking the levels in order; d(features) as (L, N, F))
+dy_lm = dy.view(rays * S, 16, 2).permute(1, 0, 2).contiguous()
+fn = lambda: ops.hash_encode_bwd_rays_lm(o, d, t, dy_lm, geom, g)
+print(f"bwd level-major, no counters: flushed {timeit(fn, True):7.1f} us   warm {timeit(fn, False):7.1f} us", flush=True)
+for k in (2, 4, 8, 16):
+    step = 16 // k
+    chunks = [(l0, l0 + step) for l0 in range(0, 16, step)]
+    fn = lambda: (done.zero_(), ops.hash_encode_bwd_rays_lm(o, d, t, dy_lm, geom, g, chunks, done))
+    print(f"bwd level-major, {k:2d} chunks + counters: flushed {timeit(fn, True):7.1f} us   warm {timeit(fn, False):7.1f} us", flush=True)

@@ -43,11 +43,14 @@ def _batch():
             torch.linspace(2.0, 6.0, 32), torch.rand(32, generator=g))
 
 
-def _grads(enc, mlp, vr, ro, rd, dn, gt, u, t, u_cand, dev, hier=False):
-    """hier=True: coarse + fine render, i.e. TWO passes through the encoder and the MLP inside one backward."""
-    Cr, Cf, _ = vr.vol_render(mlp, rd.to(dev), ro.to(dev), num_samples=32, t=t.to(dev), dir_norm=dn.to(dev), hierarchical=hier,
-                              _u=u.to(dev), _u_cand=u_cand.to(dev))
-    (torch.nn.functional.mse_loss(Cr, gt.to(dev)) + torch.nn.functional.mse_loss(Cf, gt.to(dev))).backward()
+def _grads(enc, mlp, vr, ro, rd, dn, gt, u, t, u_cand, dev, hier=False, amp=False):
+    """hier=True: coarse + fine render, i.e. TWO passes through the encoder and the MLP inside one backward.
+    amp=True: the autocast training path (tensor-core MLP kernels, positions formed from the rays in the hash kernels)."""
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+        Cr, Cf, _ = vr.vol_render(mlp, rd.to(dev), ro.to(dev), num_samples=32, t=t.to(dev), dir_norm=dn.to(dev),
+                                  hierarchical=hier, _u=u.to(dev), _u_cand=u_cand.to(dev))
+        loss = torch.nn.functional.mse_loss(Cr, gt.to(dev)) + torch.nn.functional.mse_loss(Cf, gt.to(dev))
+    loss.backward()
     torch.cuda.synchronize()
     return (torch.stack([e.weight.grad for e in enc.Embedding_list]).cpu(),
             torch.cat([p.grad.reshape(-1) for p in mlp.parameters()]).cpu())
@@ -65,16 +68,23 @@ def _worker(rank, world, port_no, tmp, mode="nccl"):
     ro, rd, dn, gt, u, t, u_cand = _batch()
     sl = hdist.shard_rays(ro.shape[0], rank, world)
     # peer mode: several steps through the same persistent region; hier: two field passes inside one backward
-    for chunks, hier in ((1, False), (4, False), (1, True), (4, True)):
-        enc._grad_chunks = chunks
+    # "4s" / "8s": the streamed exchange (one scatter-add launch finishing 4 / 8 level chunks in order + one exchange launch
+    # beside it); amp: the autocast training path (_FieldRaysFn), whose MLP gradient travels in the same exchange launch
+    cases = [(1, False, False), (4, False, False), (1, True, False), (4, True, False)]
+    if mode != "nccl":
+        cases += [("4s", False, False), ("8s", True, False), ("8s", False, True), ("4s", True, True), (1, False, True)]
+    for chunks, hier, amp in cases:
+        streamed = isinstance(chunks, str)
+        nch = int(chunks[:-1]) if streamed else chunks
+        enc._grad_chunks = nch
         if mode != "nccl":
-            red._nchunks, red.overlap = chunks, chunks > 1
+            red._nchunks, red.overlap, red.streamed = nch, nch > 1, streamed
             if red.overlap and red._side is None:
                 red._side, red.ctas = torch.cuda.Stream(device=dev, priority=-1), 32
         for p in list(enc.parameters()) + list(mlp.parameters()):
             p.grad = None
-        gt_tab, gt_mlp = _grads(enc, mlp, vr, ro[sl], rd[sl], dn[sl], gt[sl], u[sl], t, u_cand, dev, hier)
-        torch.save((gt_tab, gt_mlp), os.path.join(tmp, f"g{rank}_{chunks}_{int(hier)}.pt"))
+        gt_tab, gt_mlp = _grads(enc, mlp, vr, ro[sl], rd[sl], dn[sl], gt[sl], u[sl], t, u_cand, dev, hier, amp)
+        torch.save((gt_tab, gt_mlp), os.path.join(tmp, f"g{rank}_{chunks}_{int(hier)}_{int(amp)}.pt"))
     if mode != "nccl":
         assert not red.region.timed_out()
         red.region.raise_if_failed()
@@ -92,17 +102,27 @@ def test_sharded_gradients_equal_single_gpu(tmp_path):
 
 
 def _check(tmp_path, enc, mlp, vr, dev, bit_identical):
-    for hier in (False, True):
-        for p in list(enc.parameters()) + list(mlp.parameters()):
-            p.grad = None
-        want_tab, want_mlp = _grads(enc, mlp, vr, *_batch(), dev, hier)
-        for chunks in (1, 4):
-            got = [torch.load(os.path.join(tmp_path, f"g{rank}_{chunks}_{int(hier)}.pt")) for rank in range(2)]
-            for rank, (tab, gm) in enumerate(got):
-                assert float((tab - want_tab).norm() / want_tab.norm()) < 1e-5, (rank, chunks, hier)
-                assert float((gm - want_mlp).norm() / want_mlp.norm()) < 1e-5, (rank, chunks, hier)
-            if bit_identical:
-                assert torch.equal(got[0][0], got[1][0]) and torch.equal(got[0][1], got[1][1]), (chunks, hier)
+    seen = 0
+    for amp in (False, True):
+        for hier in (False, True):
+            for p in list(enc.parameters()) + list(mlp.parameters()):
+                p.grad = None
+            want_tab, want_mlp = _grads(enc, mlp, vr, *_batch(), dev, hier, amp)
+            # fp32: 1e-5 (the path's bar); autocast: the same 16-bit arithmetic per point on both sides, but the tiles (and
+            # with them the fp32 summation order of the weight gradients inside the tensor cores) differ: 1e-4
+            tol = 1e-4 if amp else 1e-5
+            for chunks in (1, 4, "4s", "8s"):
+                files = [os.path.join(tmp_path, f"g{rank}_{chunks}_{int(hier)}_{int(amp)}.pt") for rank in range(2)]
+                if not all(os.path.exists(f) for f in files):
+                    continue
+                seen += 1
+                got = [torch.load(f) for f in files]
+                for rank, (tab, gm) in enumerate(got):
+                    assert float((tab - want_tab).norm() / want_tab.norm()) < tol, (rank, chunks, hier, amp)
+                    assert float((gm - want_mlp).norm() / want_mlp.norm()) < tol, (rank, chunks, hier, amp)
+                if bit_identical:
+                    assert torch.equal(got[0][0], got[1][0]) and torch.equal(got[0][1], got[1][1]), (chunks, hier, amp)
+    assert seen >= 4
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")

@@ -328,3 +328,59 @@ def test_field_bwd_rays_matches_two_kernels(R, S, T, per_ray, fmt):
     # accumulation contract: a second call adds on top
     ops.field_bwd_rays_tc(feat16, ro, rd, t, geom, dirs, flat, dims, out, dout, g1, False, dp1, operand=operand, grad_scale=scale)
     assert rel(g1, 2 * g0) < 1e-6 and rel(dp1, 2 * dp0) < 1e-6
+
+
+@pytest.mark.parametrize("R,S,T,per_ray", [(1, 2, 2 ** 10, False), (3, 100, 2 ** 14, True), (130, 7, 2 ** 12, True),
+                                           (700, 128, 2 ** 19, False), (4096, 32, 2 ** 19, True)])
+@pytest.mark.parametrize("fmt", [torch.bfloat16, torch.float16])
+def test_level_major_backward_pair_matches_row_major(R, S, T, per_ray, fmt):
+    """The multi-GPU form of the step's backward: hbr_mlp_bwd_tc writing d(features) LEVEL-MAJOR (16, N, 2)
+    (dfeat_stride = HBR_DFEAT_LEVEL_MAJOR) followed by the level-major scatter-add hbr_hash_encode_bwd_rays_lm, against the
+    row-major pair.  The level-major tensor is the exact transpose of the row-major one (same values, bit for bit), the MLP
+    gradients do not depend on the layout, and the table gradient agrees to atomic-order noise -- with and without level
+    chunks / completion counters, and through the explicit-positions entry point.  Covers partial tiles and partial CTAs
+    of the 1024-point level-major grid."""
+    import human_body_reconstruction_b200 as h
+    from human_body_reconstruction_b200 import ops, _lib
+    torch.manual_seed(R * 5 + S)
+    operand = _lib.HBR_BF16 if fmt == torch.bfloat16 else _lib.HBR_F16
+    scale = 1.0 if fmt == torch.bfloat16 else 1024.0
+    mu, maxb = torch.tensor([-4.27, -4.31, -3.95]), torch.tensor([4.28, 4.27, 2.37])
+    sigma = ((maxb - mu) ** 2).sum().sqrt()
+    enc = h.HashEncoder(N_min=16, N_max=2048.0, L=16, F=2, T=T, dim=3, mu=mu.to(DEV), sigma=sigma.to(DEV))
+    with torch.no_grad():
+        for e in enc.Embedding_list:
+            e.weight.mul_(5e3)
+    enc = enc.to(DEV)
+    p, m = make()
+    flat, dims, geom, table = m._flat_params(), m._dims(), enc._geom(), enc._flat_table()
+    N = R * S
+    assert ops.mlp_level_major_ok(geom, dims, N)
+    ro = (torch.tensor([[0.2, -0.1, 4.0]]).repeat(R, 1) + 0.3 * torch.randn(R, 3)).to(DEV)
+    rd = torch.nn.functional.normalize(-ro.cpu() + 0.8 * torch.randn(R, 3), dim=-1).to(DEV)
+    t = (2 + 4 * torch.rand(R, S)).sort(-1).values.to(DEV) if per_ray else torch.linspace(2, 6, S, device=DEV)
+    dirs = port.dir_encode(torch.nn.functional.normalize(torch.randn(R, 3), dim=-1), 4).to(DEV)
+    feat16 = ops.hash_encode_fwd_rays(ro, rd, t, table, geom, operand)
+    out, _ = ops.mlp_fwd_tc(feat16, dirs, S, flat, dims, operand=operand)
+    dout = torch.randn(N, 4, device=DEV) / N
+    dp0, dp1 = torch.zeros_like(flat), torch.zeros_like(flat)
+    dfeat, dd0 = ops.mlp_bwd_tc(feat16, dirs, S, flat, dims, out, dout, True, True, dp0, operand=operand, grad_scale=scale)
+    dfeat_lm, dd1 = ops.mlp_bwd_tc(feat16, dirs, S, flat, dims, out, dout, True, True, dp1, operand=operand, grad_scale=scale,
+                                   level_major=True)
+    assert dfeat_lm.shape == (16, N, 2)
+    assert torch.equal(dfeat_lm, dfeat.view(N, 16, 2).permute(1, 0, 2).contiguous())
+    assert rel(dp1, dp0) < 1e-6 and rel(dd1, dd0) < 1e-6          # (accumulated with atomics: order noise only)
+    g0, g1, g2, g3 = (torch.zeros_like(table) for _ in range(4))
+    ops.hash_encode_bwd_rays(ro, rd, t, dfeat, geom, g0)
+    ops.hash_encode_bwd_rays_lm(ro, rd, t, dfeat_lm, geom, g1)
+    chunks = [(0, 3), (3, 4), (4, 10), (10, 16)]
+    done = torch.zeros(8, dtype=torch.int32, device=DEV)
+    ops.hash_encode_bwd_rays_lm(ro, rd, t, dfeat_lm, geom, g2, chunks, done)
+    tt = t if per_ray else t[None, :].expand(R, S)
+    pts = (ro[:, None, :] + rd[:, None, :] * tt[:, :, None]).reshape(-1, 3).contiguous()
+    ops.hash_encode_bwd_lm(pts, dfeat_lm, geom, g3, chunks[:2] + [(4, 16)], done[4:])
+    torch.cuda.synchronize()
+    assert g0.abs().sum() > 0
+    assert rel(g1, g0) < 1e-6 and rel(g2, g0) < 1e-6 and rel(g3, g0) < 1e-6
+    ctas = ops.hash_bwd_lm_ctas(N)
+    assert ctas == -(-N // 1024) and done.tolist() == [ctas] * 4 + [ctas] * 3 + [0]
