@@ -367,13 +367,12 @@ def run_b200(args):
     if args.no_fuse_scatter:
         from human_body_reconstruction_b200 import vol_renderer as _vrm
         _vrm.FUSE_SCATTER = False                                         # MLP backward and hash-grid scatter-add as two kernels
-    if args.peer_scatter == "tile":
-        from human_body_reconstruction_b200 import vol_renderer as _vrm
-        _vrm.STREAM_LEVEL_MAJOR = False
+    from human_body_reconstruction_b200 import vol_renderer as _vrm
+    _vrm.STREAM_LEVEL_MAJOR = args.peer_scatter == "lm"
     reducer = None
     # "--peer-chunks 2" = two equal level ranges; "--peer-chunks 4,8,12,14" = inner level boundaries (cheap coarse levels first)
     streamed = args.peer_exchange == "stream"
-    pcs = str(args.peer_chunks) if args.peer_chunks != "auto" else ("8" if streamed else "2")
+    pcs = str(args.peer_chunks) if args.peer_chunks != "auto" else ("4" if streamed else "2")
     pc = [int(v) for v in pcs.split(",") if v != ""]
     peer_chunks = pc if len(pc) > 1 else (pc[0] if pc else 0)
     if world > 1:
@@ -869,8 +868,8 @@ def main():
     ap.add_argument("--peer-ctas", type=int, default=0)
     ap.add_argument("--peer-chunks", type=str, default="auto", help="> 0: all-reduce level chunks on a side stream while the "
                     "remaining chunks' scatter-add runs; 0: one all-reduce behind the backward pass; a list = inner level "
-                    "boundaries; auto = 8 (streamed) / 2 (one launch per chunk)")
-    ap.add_argument("--peer-scatter", default="lm", choices=["lm", "tile"], help="producer of the streamed exchange: the "
+                    "boundaries; auto = 4 (streamed) / 2 (one launch per chunk)")
+    ap.add_argument("--peer-scatter", default="tile", choices=["lm", "tile"], help="producer of the streamed exchange: the "
                     "level-major scatter-add (co-resident grid, levels in order) or the tile-major kernel launched chunk-major")
     ap.add_argument("--peer-exchange", default="stream", choices=["stream", "launch"], help="stream: ONE scatter-add launch "
                     "finishing the level chunks in order + ONE exchange launch beside it; launch: a launch pair per chunk")

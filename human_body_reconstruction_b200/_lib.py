@@ -67,10 +67,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -shared -> libhbr_b200.so (cross-compiles without a GPU)."""
     if not force and not _stale():
         return SO_PATH
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objs, procs = [], []
     bdir = os.path.join(_HERE, "build")
     os.makedirs(bdir, exist_ok=True)
+    # several ranks of one node may find the library stale at the same moment (torchrun): one of them builds, the others
+    # wait on the lock and then find it fresh; the finished library is moved into place atomically, so a process that
+    # loads it concurrently sees either the old or the new file, never a half-written one
+    import fcntl
+    with open(os.path.join(bdir, ".lock"), "w") as lockf:
+        fcntl.flock(lockf, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return SO_PATH
+            return _build_locked(bdir, force, verbose)
+        finally:
+            fcntl.flock(lockf, fcntl.LOCK_UN)
+
+
+def _build_locked(bdir: str, force: bool, verbose: bool) -> str:
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs, procs = [], []
     for src in sources():
         obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
@@ -88,10 +103,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", SO_PATH, *objs, "-lcudart"]
+    tmp_so = os.path.join(bdir, f"libhbr_b200.{os.getpid()}.so.tmp")
+    cmd = [nvcc, "-shared", "-o", tmp_so, *objs, "-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp_so, SO_PATH)
     return SO_PATH
 
 

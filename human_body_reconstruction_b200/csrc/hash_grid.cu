@@ -334,12 +334,18 @@ hash_bwd_kernel(const typename PointSrc<XT>::type x, long long n, const float* _
 // all-reduce kernel beside it (comm.cu: allreduce_stream_kernel) puts chunk c on the wire while the finer levels -- where
 // most of the reductions are -- are still being accumulated.  Same arithmetic, run merging and (x, x+1) pairing as
 // hash_bwd_kernel; no shared memory (the per-level dy reads are coalesced 8-byte loads), positions formed once.
+#ifndef HBR_LM_PER
+#define HBR_LM_PER 4
+#endif
+#ifndef HBR_LM_MINB
+#define HBR_LM_MINB 4
+#endif
 constexpr int kLmThreads = 256;
-constexpr int kLmPer = 4;                           // points per thread
+constexpr int kLmPer = HBR_LM_PER;                  // points per thread
 constexpr int kLmPts = kLmThreads * kLmPer;         // points per CTA
 
 template <int F, bool POW2, typename XT>
-__global__ void __launch_bounds__(kLmThreads, 4)
+__global__ void __launch_bounds__(kLmThreads, HBR_LM_MINB)
 hash_bwd_lm_kernel(const typename PointSrc<XT>::type x, long long n, const float* __restrict__ dy, float* __restrict__ dtable,
                    const __grid_constant__ HashGeom g, const __grid_constant__ ChunkPlan plan) {
   using FV = typename FeatVec<F>::type;

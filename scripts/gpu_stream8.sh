@@ -19,13 +19,9 @@ PY
 done <<'CFG'
 --peer-exchange launch
 --peer-exchange stream --peer-scatter lm
---peer-exchange stream --peer-scatter lm --peer-chunks 16
---peer-exchange stream --peer-scatter lm --peer-chunks 4
 --peer-exchange stream --peer-scatter lm --peer-ctas 64
---peer-exchange stream --peer-scatter lm --peer-ctas 16
---peer-exchange stream --peer-scatter tile --peer-chunks 4
---peer-exchange stream --peer-scatter tile --peer-chunks 10,13,15
 --peer-exchange stream --peer-scatter tile --peer-chunks 8,12,14,15
+--peer-exchange stream --peer-scatter tile --peer-chunks 10,13,15
+--peer-exchange stream --peer-scatter tile --peer-chunks 4
 --peer-exchange stream --peer-scatter tile --peer-chunks 8,12,14,15 --peer-ctas 64
---peer-chunks 0
 CFG

@@ -83,6 +83,10 @@ def _worker(rank, world, port_no, tmp, mode="nccl"):
                 red._side, red.ctas = torch.cuda.Stream(device=dev, priority=-1), 32
         for p in list(enc.parameters()) + list(mlp.parameters()):
             p.grad = None
+        # the streamed autocast cases cover both producers: "8s" the level-major scatter-add (fed by level-major d(features)
+        # from the MLP backward), "4s" the tile-major kernel launched chunk-major
+        from human_body_reconstruction_b200 import vol_renderer as vrm
+        vrm.STREAM_LEVEL_MAJOR = chunks == "8s"
         gt_tab, gt_mlp = _grads(enc, mlp, vr, ro[sl], rd[sl], dn[sl], gt[sl], u[sl], t, u_cand, dev, hier, amp)
         torch.save((gt_tab, gt_mlp), os.path.join(tmp, f"g{rank}_{chunks}_{int(hier)}_{int(amp)}.pt"))
     if mode != "nccl":
