@@ -38,7 +38,7 @@ BYTES_PER_POINT = {
     "hbr_hash_encode_fwd": 1164, "hbr_hash_encode_bwd": 1164, "hbr_hash_encode_fwd_rays": 1164, "hbr_hash_encode_bwd_rays": 1164,
     "hbr_hash_encode_fwd_pts": 1164, "hbr_hash_encode_bwd_pts": 1164, "hbr_mlp_fwd_f32": 144, "hbr_mlp_bwd_f32": 272,
     "hbr_mlp_fwd_tc": 144, "hbr_mlp_bwd_tc": 272, "hbr_composite_fwd": 16, "hbr_composite_bwd": 32,
-    "hbr_field_fwd_tc": 1164 + 144, "hbr_field_bwd_tc": 1164 + 272, "hbr_field_bwd_rays_tc": 1164 + 272,
+    "hbr_field_fwd_tc": 1164 + 144, "hbr_field_fwd_rays_tc": 1164 + 144, "hbr_field_bwd_tc": 1164 + 272, "hbr_field_bwd_rays_tc": 1164 + 272,
 }
 # algorithmic FLOP per point of MLP_3D: 27 904 forward, 2 x that for the backward GEMMs (dgrad + wgrad)
 FLOPS_PER_POINT = {"hbr_mlp_fwd_tc": 27904, "hbr_mlp_bwd_tc": 55808, "hbr_mlp_fwd_f32": 27904, "hbr_mlp_bwd_f32": 55808}
@@ -364,6 +364,9 @@ def run_b200(args):
                              sigma_val=sigma, mu=mn)
     if args.fuse_field:
         vr.fuse_field = True                                              # encoder + MLP in one kernel per direction
+    if args.fuse_gather:
+        from human_body_reconstruction_b200 import vol_renderer as _vrm
+        _vrm.FUSE_GATHER = True                                           # hash-grid gather + MLP forward in one kernel (A/B)
     if args.no_fuse_scatter:
         from human_body_reconstruction_b200 import vol_renderer as _vrm
         _vrm.FUSE_SCATTER = False                                         # MLP backward and hash-grid scatter-add as two kernels
@@ -874,6 +877,8 @@ def main():
     ap.add_argument("--peer-exchange", default="stream", choices=["stream", "launch"], help="stream: ONE scatter-add launch "
                     "finishing the level chunks in order + ONE exchange launch beside it; launch: a launch pair per chunk")
     ap.add_argument("--fuse-field", action="store_true", help="use the fused encoder+MLP kernels (hbr_field_*_tc)")
+    ap.add_argument("--fuse-gather", action="store_true", help="A/B: hbr_field_fwd_rays_tc, the hash-grid gather on dedicated "
+                    "warps of the MLP forward kernel (measured slower than the two kernels: 152 vs 140 us)")
     ap.add_argument("--no-fuse-scatter", action="store_true", help="A/B: run the MLP backward and the hash-grid scatter-add as "
                     "two kernels (default on one GPU: hbr_field_bwd_rays_tc, the scatter-add on dedicated warps of the MLP kernel)")
     ap.add_argument("--no-grid", dest="grid", action="store_false", help="skip the configs[3] leg (512^3 density grid + marching cubes)")

@@ -83,7 +83,15 @@ struct RaySrc {
 struct RayPts {};                                  // tag: positions come from a RaySrc
 __device__ __forceinline__ void load_point(const RaySrc& rs, long long gp, long long n, float p[3]) {
   if (gp < n) {
-    const long long ray = gp / rs.S, smp = gp - ray * rs.S;
+    long long ray, smp;
+    if (n <= 0xffffffffLL) {                      // 32-bit division (the 64-bit one is a ~100-instruction subroutine)
+      const unsigned q = (unsigned)gp / (unsigned)rs.S;
+      ray = q;
+      smp = (long long)((unsigned)gp - q * (unsigned)rs.S);
+    } else {
+      ray = gp / rs.S;
+      smp = gp - ray * rs.S;
+    }
     const float tt = __ldg(rs.t + ray * rs.t_stride + smp);
 #pragma unroll
     for (int a = 0; a < 3; ++a) p[a] = __fadd_rn(__ldg(rs.o + ray * 3 + a), __fmul_rn(__ldg(rs.d + ray * 3 + a), tt));

@@ -175,6 +175,36 @@ extern "C" int hbr_field_bwd_tc(const float* x, int64_t n, const hbr_hash_geom* 
                                               grad_scale, 0, 0, 0, nullptr, nullptr, as_stream(stream));
 }
 
+// Forward of the training step's field evaluation in ONE kernel: the hash-grid gather (hbr_hash_encode_fwd_rays) on dedicated
+// warps of the tensor-core MLP kernel (mlp_fwd_tc_kernel<GATH>), feeding its tile groups tile by tile through shared
+// memory.  out (R*S,4) = [rgb, sigma]; feat16 (R*S,32): the 16-bit features for the backward recompute.  image_ready != 0:
+// the operand image in `scratch` was built for these parameters and format (hbr_mlp_tc_prepare); otherwise the kernel
+// converts the parameters itself.
+#ifndef HBR_FWD_GATHER_WARPS
+#define HBR_FWD_GATHER_WARPS 8
+#endif
+extern "C" int hbr_field_fwd_rays_tc(const float* rays_o, const float* rays_d, const float* t, int64_t t_ray_stride, int64_t R,
+                                     int64_t S, const float* table, const hbr_hash_geom* geom, const float* dirs,
+                                     const float* params, const hbr_mlp_dims* dims, int operand, float* out, void* feat16,
+                                     void* scratch, int image_ready, void* stream) {
+  if (int rc = check_field(geom, dims)) return rc;
+  if (int rc = check_operand(operand, 1.f)) return rc;
+  HBR_REQUIRE(R >= 0 && S >= 1 && R < (1LL << 40) / S, "R=%lld S=%lld", (long long)R, (long long)S);
+  HBR_REQUIRE(t_ray_stride == 0 || t_ray_stride >= S, "t_ray_stride %lld", (long long)t_ray_stride);
+  HBR_REQUIRE(!image_ready || scratch != nullptr, "image_ready without scratch");
+  const int64_t n = R * S;
+  if (n == 0) return HBR_OK;
+  HBR_REQUIRE(rays_o && rays_d && t && table && dirs && params && out && feat16, "NULL pointer");
+  HBR_REQUIRE((uintptr_t)out % 16 == 0 && (uintptr_t)table % 16 == 0 && (uintptr_t)feat16 % 16 == 0 &&
+                  (uintptr_t)scratch % 256 == 0, "alignment");
+  EncArgs e{};
+  e.table = table; e.feat16 = static_cast<uint16_t*>(feat16);
+  e.ro = rays_o; e.rd = rays_d; e.rt = t; e.S = S; e.t_stride = t_ray_stride;
+  const uint8_t* image = image_ready ? static_cast<const uint8_t*>(scratch) : nullptr;
+  return HBR_BY_OPERAND(launch_fwd_gather_tc<HBR_FWD_GATHER_WARPS>(dirs, S, n, params, dims->d_view, out, image, e,
+                                                                     to_device_geom(*geom), as_stream(stream)));
+}
+
 // MLP backward with the hash-grid scatter-add on dedicated warps of the same kernel (mlp_bwd_tc_kernel<SCAT = 7>): what
 // hbr_mlp_bwd_tc followed by hbr_hash_encode_bwd_rays computes (same arithmetic, same run merging), without the fp32
 // d(feature) tensor and with the two phases overlapped on every SM.  feat16: the (R*S,32) 16-bit features

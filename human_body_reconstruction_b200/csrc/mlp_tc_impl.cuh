@@ -687,9 +687,88 @@ struct FwdSmem {
   static constexpr int off_stage = off_buf + G * buf_bytes;             // fp32 staging of the NEXT tile's features (cp.async)
   static constexpr int stage_bytes = K0P == 32 ? kTile * K0P * 4 : 0;   // the wide variant loads features directly
   static constexpr int off_bar = off_stage + G * stage_bytes;
-  static constexpr int total = off_bar + 2 * G * 8 + 16;
+  // full[G], done[G], tslot (16 bytes), then the gather variant's xfull[G][2], xempty[G][2]
+  static constexpr int off_xbar = off_bar + 2 * G * 8 + 16;
+  static constexpr int total = off_xbar + 4 * G * 8;
   static_assert(total <= 232448, "shared memory budget exceeded");
 };
+
+// (x - mu) / sigma is level-independent: the scatter warps keep it per slice and finish cell_of per level
+__device__ __forceinline__ void cell_of_norm(float u0, float scale, long long& cell, float& frac) {
+  const float u = __fmul_rn(u0, scale);
+  cell = __float2ll_rz(u);
+  frac = __fsub_rn(u, __ll2float_rn(cell));
+}
+
+// ---- gather warps of the fused forward (GATH > 0): one (32-point slice, 4-level group) unit -----------------------------
+// Lane = point: 4 levels x 8 corner gathers = 32 independent 8-byte loads in flight, interpolated exactly like
+// hash_fwd_kernel (hash_grid.cu; products and sums rounded separately, hash_encoding.py:144), rounded to the operand
+// format in pairs and stored as ONE 16-byte chunk of the canonical A tile (row r, column group lg) -- and as the same
+// 16 bytes of the point's feat16 row for the backward recompute.
+template <int NLV>   // levels per unit: 4 (one 16-byte chunk, 32 loads in flight) or 2 (half a chunk, 16 loads in flight)
+__device__ __forceinline__ void gather_unit(const EncArgs& e, const HashGeom& g, long long n, long long tile, int slice, int lg,
+                                            int lane, uint8_t* x0) {
+  const int r = slice * 32 + lane;
+  const long long gp = tile * kTile + r;
+  float un[3] = {0.f, 0.f, 0.f};
+  if (gp < n) {
+    long long ray, smp;
+    if (n <= 0xffffffffLL) {
+      const unsigned q = (unsigned)gp / (unsigned)e.S;
+      ray = q;
+      smp = (long long)((unsigned)gp - q * (unsigned)e.S);
+    } else {
+      ray = gp / e.S;
+      smp = gp - ray * e.S;
+    }
+    const float tt = __ldg(e.rt + ray * e.t_stride + smp);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float x = __fadd_rn(__ldg(e.ro + ray * 3 + a), __fmul_rn(__ldg(e.rd + ray * 3 + a), tt));   // vol_renderer.py:165
+      un[a] = __fdiv_rn(__fsub_rn(x, g.mu[a]), g.sigma);
+    }
+  }
+  float2 v[NLV][8];
+  float fr[NLV][3];
+#pragma unroll
+  for (int q = 0; q < NLV; ++q) {
+    const int l = lg * NLV + q;
+    const float s = g.scale[l];
+    long long ix, iy, iz;
+    float fx, fy, fz;
+    cell_of_norm(un[0], s, ix, fx);
+    cell_of_norm(un[1], s, iy, fy);
+    cell_of_norm(un[2], s, iz, fz);
+    uint32_t idx[8];
+    corner_indices<true>(ix, iy, iz, g.T, idx);
+    const float2* lvl = reinterpret_cast<const float2*>(e.table) + (size_t)l * g.T;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[q][c] = __ldg(lvl + idx[c]);
+    fr[q][0] = fx; fr[q][1] = fy; fr[q][2] = fz;
+  }
+  uint32_t packed[NLV];
+#pragma unroll
+  for (int q = 0; q < NLV; ++q) {
+    float w[8];
+    corner_weights(fr[q][0], fr[q][1], fr[q][2], w);
+    float a0 = __fmul_rn(v[q][0].x, w[0]), a1 = __fmul_rn(v[q][0].y, w[0]);
+#pragma unroll
+    for (int c = 1; c < 8; ++c) {
+      a0 = __fadd_rn(a0, __fmul_rn(v[q][c].x, w[c]));
+      a1 = __fadd_rn(a1, __fmul_rn(v[q][c].y, w[c]));
+    }
+    packed[q] = OP::pack(a0, a1);
+  }
+  if constexpr (NLV == 4) {
+    const uint4 out4 = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    *reinterpret_cast<uint4*>(x0 + chunk_off(r, lg, kTile)) = out4;
+    if (gp < n) reinterpret_cast<uint4*>(e.feat16 + gp * 32)[lg] = out4;
+  } else {
+    const uint2 out2 = make_uint2(packed[0], packed[1]);
+    *reinterpret_cast<uint2*>(x0 + chunk_off(r, lg >> 1, kTile) + (lg & 1) * 8) = out2;
+    if (gp < n) reinterpret_cast<uint2*>(e.feat16 + gp * 32)[lg] = out2;
+  }
+}
 
 // 16-byte asynchronous global -> shared copy; valid == false zero-fills the destination
 
@@ -743,8 +822,16 @@ __device__ __forceinline__ void copy_feat16_async(const uint16_t* __restrict__ f
 }
 
 // TRACE: clock64 stamps of group 0 / its MMA warp in CTA 0 (debug entry point hbr_debug_mlp_trace; compiled out otherwise)
-template <int K0P, int KCP, int G, bool TRACE = false, bool ENC = false>
-__global__ void __launch_bounds__(G * kTile, 1)
+// GATH > 0 (= hbr_field_fwd_rays_tc, the training step's forward on one GPU): the hash-grid gather runs INSIDE this kernel
+// on GATH dedicated warps beside G = 2 tile groups.  A tile's 16 units (32-point slice x 4-level group, gather_unit) are
+// dealt to the gather warps, which fill the group's feature tile -- two 8 KB buffers per group, xfull / xempty mbarriers --
+// one tile ahead of the layer chain; the chain (latency-bound, tensor pipe ~40 %, no LSU traffic beyond layer 0's
+// operand) hides behind the gather (bound by the L1TEX wavefront rate of the scattered 8-byte loads).  The sample
+// positions come from the rays, the fp32 feature tensor never exists, the 16-bit features are written once for the
+// backward recompute, and the weights are staged by the tile groups while the gather warps are already at work (no prep
+// kernel in front).  Same arithmetic as hbr_hash_encode_fwd_rays + hbr_mlp_fwd_tc.
+template <int K0P, int KCP, int G, bool TRACE = false, bool ENC = false, int GATH = 0>
+__global__ void __launch_bounds__(G * kTile + GATH * 32, 1)
 mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const float* __restrict__ dirs, long long dir_group,
                   long long n_arg, const float* __restrict__ params, int in0, int dv, float* __restrict__ out,
                   const uint8_t* __restrict__ image, long long* __restrict__ trace, const EncArgs enc,
@@ -767,18 +854,29 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2 * G);
   const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
+  uint64_t* xfull = reinterpret_cast<uint64_t*>(sm + SM::off_xbar);     // [G][2] feature buffer written by the gather warps
+  uint64_t* xempty = xfull + 2 * G;                                     // [G][2] layer 0 has consumed the buffer
+  constexpr int kXBuf = kTile * K0P * 2;                                // one feature buffer (the group's buf holds two)
+  static_assert(GATH == 0 || (K0P == 32 && !ENC && 2 * kXBuf <= SM::buf_bytes), "gather variant: 32 features, two buffers");
   if (warp == 0) tmem_alloc<kCols>(tslot);
   if (threadIdx.x == 32) {
     for (int g = 0; g < G; ++g) mbar_init(bars + G + g, 1);             // done[g]: the group's MMAs have completed
+    if (GATH > 0)
+      for (int q = 0; q < 2 * G; ++q) {
+        mbar_init(xfull + q, GATH * 32);
+        mbar_init(xempty + q, 1);
+      }
     fence_mbar_init();
   }
-  if (image != nullptr) {
-    copy_image_async(sm, image, SM::off_buf);                           // [weights | bias tiles | ones16], same layout
-    cp_async_wait_all();
-  } else {
-    stage_weights_bf16<K0P, KCP>(params, m, wsm, sm + SM::off_bias, sm + SM::off_ones16);
+  if (GATH == 0) {
+    if (image != nullptr) {
+      copy_image_async(sm, image, SM::off_buf);                         // [weights | bias tiles | ones16], same layout
+      cp_async_wait_all();
+    } else {
+      stage_weights_bf16<K0P, KCP>(params, m, wsm, sm + SM::off_bias, sm + SM::off_ones16);
+    }
+    fence_async_smem();
   }
-  fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -786,7 +884,51 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
   const long long ntiles = (n + kTile - 1) / kTile;
   const long long nslots = (long long)gridDim.x * G;
 
-  {
+  // GATH <= 8: 16 units of 4 levels per tile; more gather warps: 32 units of 2 levels, and the registers are rebalanced
+  // with setmaxnreg (launch at 80: the tile groups rise to 128, the gather warps drop to 56)
+  constexpr int kNlv = GATH > 8 ? 2 : 4;
+  constexpr int kUnits = 64 / kNlv;
+  if (GATH > 0 && warp >= 4 * G) {
+    // ===== gather warps =====
+    if (GATH > 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(56));
+    const int gw = warp - 4 * G;
+    uint32_t epar = 0;                                                   // bit (2 g + slot): parity of xempty[g][slot]
+#pragma unroll 1
+    for (long long k = 0;; ++k) {
+      bool any = false;
+#pragma unroll 1
+      for (int g = 0; g < G; ++g) {
+        const long long tile = (long long)g * gridDim.x + blockIdx.x + k * nslots;
+        if (tile >= ntiles) continue;
+        any = true;
+        const int slot = (int)(k & 1), q = 2 * g + slot;
+        if (k >= 2) {                                                    // the buffer's previous tile has been consumed
+          mbar_wait(xempty + q, (epar >> q) & 1u);
+          epar ^= 1u << q;
+        }
+        uint8_t* x0 = sm + SM::off_buf + g * SM::buf_bytes + slot * kXBuf;
+#pragma unroll 1
+        for (int u = gw; u < kUnits; u += GATH) gather_unit<kNlv>(enc, geom, n, tile, u & 3, u >> 2, lane, x0);
+        fence_async_smem();                                              // generic-proxy stores -> visible to the tensor core
+        mbar_arrive(xfull + q);
+      }
+      if (!any) break;
+    }
+  } else {
+    if (GATH > 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(128));
+    if (GATH > 0) {
+      // the tile groups stage the weights themselves (threads 0 .. G*128-1) while the gather warps already work
+      if (image != nullptr) {
+        for (int e = threadIdx.x; e < SM::off_buf / 16; e += G * kTile) cp_async16(sm + e * 16, image + e * 16, true);
+        cp_async_commit();
+        cp_async_wait_all();
+      } else {
+        stage_weights_bf16<K0P, KCP>(params, m, wsm, sm + SM::off_bias, sm + SM::off_ones16, nullptr, false, threadIdx.x,
+                                     G * kTile);
+      }
+      fence_async_smem();
+      asm volatile("bar.sync 7, %0;" ::"n"(G * kTile) : "memory");
+    }
     // ===== tile group g (warps 4g .. 4g+3): 128 threads = the 128 points of a tile; the group's first warp also issues
     // the group's MMAs (no separate issuer warps: 512 threads keep 128 registers each, and the hand-off is one named
     // barrier instead of an mbarrier round trip through another warp) =====
@@ -803,10 +945,13 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
     const bool vec_ok = in0 == K0P && feat_stride == K0P && ((uintptr_t)feat & 15) == 0;
     int tgi = 0, tmi = 0;
     (void)tgi; (void)tmi;
+    int tgk = 0;                                 // gather variant: tiles done by this group; xpar: parity of xfull[g][slot]
+    uint32_t xpar = 0;
+    (void)tgk; (void)xpar;
     uint8_t* stage = sm + SM::off_stage + g * SM::stage_bytes;
-    const bool f16in = !ENC && feat16 != 0;
+    const bool f16in = !ENC && GATH == 0 && feat16 != 0;
     const uint16_t* featq = reinterpret_cast<const uint16_t*>(feat);
-    const bool staged = !ENC && !f16in && vec_ok && SM::stage_bytes > 0;
+    const bool staged = !ENC && GATH == 0 && !f16in && vec_ok && SM::stage_bytes > 0;
     if (staged && (long long)g * gridDim.x + blockIdx.x < ntiles)
       stage_features_async<K0P>(feat, ((long long)g * gridDim.x + blockIdx.x) * kTile, n, r, stage);
     if (f16in && (long long)g * gridDim.x + blockIdx.x < ntiles)
@@ -850,7 +995,13 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
       const long long dir_row = valid ? (dir_rows != nullptr ? (long long)__ldg(dir_rows + gp) : gp / dir_group) : 0;
       if (valid && lane == 0) prefetch_l1(dirs + dir_row * dv);
       TR();
-      if (ENC) {
+      uint32_t xofs = 0;                         // gather variant: which of the group's two feature buffers holds this tile
+      if (GATH > 0) {
+        const int slot = tgk & 1;
+        mbar_wait(xfull + 2 * g + slot, (xpar >> slot) & 1u);
+        xpar ^= 1u << slot;
+        xofs = slot * (kXBuf / 16);
+      } else if (ENC) {
         encode_row(enc, geom, gp, n, r, buf);
       } else if (f16in) {
         cp_async_wait_all();                     // this tile's rows: copied while the previous tile ran layers 1..5
@@ -864,8 +1015,12 @@ mlp_fwd_tc_kernel(const float* __restrict__ feat, long long feat_stride, const f
         load_features<K0P>(feat, feat_stride, tile * kTile, n, in0, vec_ok, r, r, 0, buf);
       }
       // layer 0 reads the feature tile from shared memory; the later layers read their input from tensor memory
-      HBR_LAYER(true, issue_layer(tgrp, xa, wa + WO::w0 / 16, o16a, ba + BOfs::ofs(0) / 16, 64, K0P));
+      HBR_LAYER(true, issue_layer(tgrp, xa + xofs, wa + WO::w0 / 16, o16a, ba + BOfs::ofs(0) / 16, 64, K0P));
       // layer 0 has consumed the tile: the next tile's rows travel into it during the rest of this chain
+      if (GATH > 0) {
+        if (r == 0) mbar_arrive(xempty + 2 * g + (tgk & 1));             // hand the buffer back to the gather warps
+        ++tgk;
+      }
       if (f16in && tile + nslots < ntiles) copy_feat16_async<K0P, 1>(featq, (tile + nslots) * kTile, n, r, 0, buf);
       relu_epilogue64_tmem(taddr, taddr_a);
       HBR_TS_LAYER(1, w1, 64, 64);
@@ -1117,12 +1272,6 @@ constexpr int kGroupRegs = 168;
 // G = 2, SCAT = 7: 2 x 168 + 2 x 88 = 512 per sub-partition;  G = 1, SCAT = 11: 168 + 3 x 112 = 504
 __host__ __device__ constexpr int scat_regs(int G) { return G == 2 ? 88 : 112; }
 
-// (x - mu) / sigma is level-independent: the scatter warps keep it per slice and finish cell_of per level
-__device__ __forceinline__ void cell_of_norm(float u0, float scale, long long& cell, float& frac) {
-  const float u = __fmul_rn(u0, scale);
-  cell = __float2ll_rz(u);
-  frac = __fsub_rn(u, __ll2float_rn(cell));
-}
 
 template <int K0P, int KCP, int G, bool TRACE = false, bool ENC = false, int SCAT = 0>
 __global__ void __launch_bounds__(G * kTile + SCAT * 32 + 32, 1)
@@ -1752,6 +1901,23 @@ static int launch_fwd_tc(const float* feat, int64_t feat_stride, const float* di
   HBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, G * kTile, smem, st>>>(feat, feat_stride, dirs, dir_group, n, params, in0, dv, out, scratch, nullptr, enc,
                                              geom, feat16, n_dev, dir_rows);
+  HBR_LAUNCH_CHECK();
+  return HBR_OK;
+}
+
+// forward with the hash-grid gather on dedicated warps (mlp_fwd_tc_kernel<GATH>): 2 tile groups + GATH gather warps per SM.
+// image != 0: the operand image in `scratch` is current (copied by the tile groups); otherwise they convert the fp32
+// parameters themselves while the gather warps work -- no prep kernel in front of this one either way.
+template <int GATH>
+static int launch_fwd_gather_tc(const float* dirs, int64_t dir_group, int64_t n, const float* params, int dv, float* out,
+                                const uint8_t* image, const EncArgs& enc, const HashGeom& geom, cudaStream_t st) {
+  constexpr int G = 2;
+  constexpr int smem = FwdSmem<32, 48, G>::total;
+  const int grid = (int)min64(ceil_div(ceil_div(n, kTile), G), sm_count());
+  auto kern = mlp_fwd_tc_kernel<32, 48, G, false, false, GATH>;
+  HBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, G * kTile + GATH * 32, smem, st>>>(nullptr, 32, dirs, dir_group, n, params, 32, dv, out, image, nullptr, enc, geom,
+                                                  1, nullptr, nullptr);
   HBR_LAUNCH_CHECK();
   return HBR_OK;
 }

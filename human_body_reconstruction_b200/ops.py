@@ -585,6 +585,24 @@ def field_fwd_tc(x, table, geom: HashGeom, dirs, dir_group, params, dims: MlpDim
     return out, feat16
 
 
+def field_fwd_rays_tc(rays_o, rays_d, t, table, geom: HashGeom, dirs, params, dims: MlpDims, operand: int = HBR_BF16):
+    """hash_encode_fwd_rays + mlp_fwd_tc in ONE kernel (gather warps beside the tile groups, hbr_field_fwd_rays_tc).  Returns
+    (out (R*S,4) fp32, feat16 (R*S,32) in the operand format).  Uses the operand image in the scratch when it is current;
+    otherwise the kernel converts the parameters itself (it never writes the image: the caller builds it for the backward,
+    e.g. on a side stream, with mlp_tc_prepare)."""
+    require_cuda(rays_o, rays_d, t, table, dirs, params)
+    R, S = rays_o.shape[0], t.shape[-1]
+    n = R * S
+    out = torch.empty((n, 4), device=table.device, dtype=torch.float32)
+    feat16 = torch.empty((n, 32), device=table.device, dtype=_operand_torch_dtype(operand))
+    scratch = mlp_tc_scratch(dims, table.device)
+    ready = 1 if _tc_image.get(id(scratch)) == _image_key(params, operand) else 0
+    check(lib().hbr_field_fwd_rays_tc(ptr(rays_o), ptr(rays_d), ptr(t), _t_stride(t, S), R, S, ptr(table), C.byref(geom),
+                                      ptr(dirs), ptr(params), C.byref(dims), operand, ptr(out), ptr(feat16), ptr(scratch), ready,
+                                      stream()))
+    return out, feat16
+
+
 def field_bwd_tc(x, geom: HashGeom, dirs, dir_group, params, dims: MlpDims, feat16, out, dout, dtable, want_ddirs, dparams,
                  operand: int = HBR_BF16, grad_scale: float = 1.0):
     """Fused MLP_3D backward + hash-grid scatter-add: dtable (L,T,2) and dparams are accumulated into."""

@@ -84,11 +84,20 @@ class _FieldRaysFn(torch.autograd.Function):
         cur, side = torch.cuda.current_stream(), _side_stream(rays_o.device)
         flat = mlp._flat_params()
         side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            ops.mlp_tc_prepare(flat, dims, operand)
-        feat16 = ops.hash_encode_fwd_rays(rays_o, rays_d, t, enc._flat_table(), geom, operand)
-        cur.wait_stream(side)
-        out, _ = ops.mlp_fwd_tc(feat16, dirs, S, flat, dims, operand=operand, image_ready=True)
+        if FUSE_GATHER and rays_o.shape[0] * S <= FUSE_GATHER_MAX_POINTS and ops.field_scatter_supported(geom, dims):
+            # ONE kernel: the gather runs on dedicated warps of the MLP kernel and feeds its tile groups tile by tile
+            # (hbr_field_fwd_rays_tc); it converts the parameters itself, so the operand image -- still wanted by the
+            # backward -- is built beside it instead of in front of it
+            out, feat16 = ops.field_fwd_rays_tc(rays_o, rays_d, t, enc._flat_table(), geom, dirs, flat, dims, operand)
+            with torch.cuda.stream(side):
+                ops.mlp_tc_prepare(flat, dims, operand)
+            cur.wait_stream(side)
+        else:
+            with torch.cuda.stream(side):
+                ops.mlp_tc_prepare(flat, dims, operand)
+            feat16 = ops.hash_encode_fwd_rays(rays_o, rays_d, t, enc._flat_table(), geom, operand)
+            cur.wait_stream(side)
+            out, _ = ops.mlp_fwd_tc(feat16, dirs, S, flat, dims, operand=operand, image_ready=True)
         ctx.enc, ctx.mlp, ctx.geom, ctx.dims, ctx.S, ctx.operand = enc, mlp, geom, dims, S, operand
         ctx.save_for_backward(rays_o, rays_d, t, dirs, feat16, out)
         ctx.want_tab = any(ctx.needs_input_grad[6:6 + enc.L])
@@ -276,6 +285,12 @@ class _FieldCompactFn(torch.autograd.Function):
 # environment switch exists for A/B measurements (bench.py --no-fuse-scatter)
 FUSE_SCATTER = os.environ.get("HBR_FUSE_SCATTER", "1") != "0"
 FUSE_SCATTER_MAX_POINTS = 1 << 21
+# hbr_field_fwd_rays_tc (hash-grid gather + MLP forward in one kernel) on the autocast path: opt-in.  Measured at 4 096 rays x
+# 128 samples: 152 us with 8 gather warps beside two tile groups, 162 us with 16 (setmaxnreg 128 / 56), against 108 + 32 us
+# for the two kernels -- bit-identical results; the layer chain of only two tile groups, sharing the issue slots with the
+# gather's address arithmetic, becomes the bottleneck (bench.py --fuse-gather)
+FUSE_GATHER = os.environ.get("HBR_FUSE_GATHER", "0") != "0"
+FUSE_GATHER_MAX_POINTS = 1 << 21
 # streamed gradient exchange (multi-GPU): producer = the level-major scatter-add (co-resident grid walking the levels in
 # order, hbr_hash_encode_bwd_rays_lm) or the tile-major kernel launched chunk-major (hbr_hash_encode_bwd_rays_stream)
 # (measured on 8 GPUs, 4 096 rays each: tile-major in 4 equal level chunks 0.594 ms per step, level-major in 8 chunks 0.685 --

@@ -191,6 +191,14 @@ int hbr_field_bwd_tc(const float* x, int64_t n, const hbr_hash_geom* geom_host, 
                      const float* params, const hbr_mlp_dims* dims, int operand, const void* feat16, const float* out,
                      const float* dout, float* dtable, float* ddirs, float* dparams, float grad_scale, void* scratch,
                      void* stream);
+/* a2 + a7 + a9 for the training step's forward in ONE kernel: what hbr_hash_encode_fwd_rays followed by hbr_mlp_fwd_tc
+ * computes (same arithmetic), with the gather on dedicated warps of the tensor-core kernel feeding its tile groups through
+ * shared memory -- no fp32 features, the layer chain hidden behind the gather.  Same configuration family as
+ * hbr_field_fwd_tc.  out (R*S,4) = [rgb, sigma]; feat16 (R*S,32) 16-bit features (operand format) for the backward. */
+int hbr_field_fwd_rays_tc(const float* rays_o, const float* rays_d, const float* t, int64_t t_ray_stride, int64_t R, int64_t S,
+                          const float* table, const hbr_hash_geom* geom_host, const float* dirs, const float* params,
+                          const hbr_mlp_dims* dims, int operand, float* out, void* feat16, void* scratch, int image_ready,
+                          void* stream);
 /* ---- a7 backward + a5 in one kernel (the training step's backward under autocast): what hbr_mlp_bwd_tc followed by
  * hbr_hash_encode_bwd_rays computes -- the autograd of MLP_3D.forward (test_hash.py:52-72) chained into the autograd of
  * HashEncoder.forward (hash_encoding.py:146-170; 16 x embedding_dense_backward) for the sample positions o + d t of

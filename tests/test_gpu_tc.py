@@ -384,3 +384,43 @@ def test_level_major_backward_pair_matches_row_major(R, S, T, per_ray, fmt):
     assert rel(g1, g0) < 1e-6 and rel(g2, g0) < 1e-6 and rel(g3, g0) < 1e-6
     ctas = ops.hash_bwd_lm_ctas(N)
     assert ctas == -(-N // 1024) and done.tolist() == [ctas] * 4 + [ctas] * 3 + [0]
+
+
+@pytest.mark.parametrize("R,S,T,per_ray", [(1, 1, 2 ** 10, False), (3, 100, 2 ** 14, True), (129, 7, 2 ** 12, True),
+                                           (700, 128, 2 ** 19, False), (4096, 32, 2 ** 19, True)])
+@pytest.mark.parametrize("fmt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("image", [False, True])
+def test_field_fwd_rays_matches_two_kernels(R, S, T, per_ray, fmt, image):
+    """hbr_field_fwd_rays_tc (the hash-grid gather on dedicated warps of the MLP forward kernel, feeding its tile groups
+    through shared memory) against hbr_hash_encode_fwd_rays followed by hbr_mlp_fwd_tc: the same arithmetic on the same
+    operands, so the 16-bit features AND the (rgb, sigma) outputs are bit-identical -- whether the kernel converts the
+    parameters itself or copies the prepared operand image.  Covers a single partial tile, several tiles per tile group
+    (700 * 128 / 128 = 700 tiles > 296 slots), per-ray depths, and a ragged last tile."""
+    import human_body_reconstruction_b200 as h
+    from human_body_reconstruction_b200 import ops, _lib
+    torch.manual_seed(R * 3 + S)
+    operand = _lib.HBR_BF16 if fmt == torch.bfloat16 else _lib.HBR_F16
+    mu, maxb = torch.tensor([-4.27, -4.31, -3.95]), torch.tensor([4.28, 4.27, 2.37])
+    sigma = ((maxb - mu) ** 2).sum().sqrt()
+    enc = h.HashEncoder(N_min=16, N_max=2048.0, L=16, F=2, T=T, dim=3, mu=mu.to(DEV), sigma=sigma.to(DEV))
+    with torch.no_grad():
+        for e in enc.Embedding_list:
+            e.weight.mul_(5e3)
+    enc = enc.to(DEV)
+    p, m = make()
+    flat, dims, geom, table = m._flat_params(), m._dims(), enc._geom(), enc._flat_table()
+    assert ops.field_scatter_supported(geom, dims)
+    ro = (torch.tensor([[0.2, -0.1, 4.0]]).repeat(R, 1) + 0.3 * torch.randn(R, 3)).to(DEV)
+    rd = torch.nn.functional.normalize(-ro.cpu() + 0.8 * torch.randn(R, 3), dim=-1).to(DEV)
+    t = (2 + 4 * torch.rand(R, S)).sort(-1).values.to(DEV) if per_ray else torch.linspace(2, 6, S, device=DEV)
+    dirs = port.dir_encode(torch.nn.functional.normalize(torch.randn(R, 3), dim=-1), 4).to(DEV)
+    feat16 = ops.hash_encode_fwd_rays(ro, rd, t, table, geom, operand)
+    out, _ = ops.mlp_fwd_tc(feat16, dirs, S, flat, dims, operand=operand)
+    if image:
+        ops.mlp_tc_prepare(flat, dims, operand)                 # the fused kernel copies the image
+    else:
+        ops._tc_image.clear()                                   # ... or converts the fp32 parameters itself
+    out1, feat1 = ops.field_fwd_rays_tc(ro, rd, t, table, geom, dirs, flat, dims, operand)
+    torch.cuda.synchronize()
+    assert feat1.dtype == feat16.dtype and torch.equal(feat1.view(torch.int16), feat16.view(torch.int16))
+    assert torch.isfinite(out1).all() and torch.equal(out1, out)
