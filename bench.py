@@ -374,7 +374,8 @@ def run_b200(args):
     _vrm.STREAM_LEVEL_MAJOR = args.peer_scatter == "lm"
     reducer = None
     # "--peer-chunks 2" = two equal level ranges; "--peer-chunks 4,8,12,14" = inner level boundaries (cheap coarse levels first)
-    streamed = args.peer_exchange == "stream"
+    # auto: streamed above 2 ranks (NVLS multicast); at 2 ranks (peer loads/stores) a launch pair per chunk measured faster
+    streamed = args.peer_exchange == "stream" or (args.peer_exchange == "auto" and world > 2)
     pcs = str(args.peer_chunks) if args.peer_chunks != "auto" else ("4" if streamed else "2")
     pc = [int(v) for v in pcs.split(",") if v != ""]
     peer_chunks = pc if len(pc) > 1 else (pc[0] if pc else 0)
@@ -874,7 +875,7 @@ def main():
                     "boundaries; auto = 4 (streamed) / 2 (one launch per chunk)")
     ap.add_argument("--peer-scatter", default="tile", choices=["lm", "tile"], help="producer of the streamed exchange: the "
                     "level-major scatter-add (co-resident grid, levels in order) or the tile-major kernel launched chunk-major")
-    ap.add_argument("--peer-exchange", default="stream", choices=["stream", "launch"], help="stream: ONE scatter-add launch "
+    ap.add_argument("--peer-exchange", default="auto", choices=["auto", "stream", "launch"], help="stream: ONE scatter-add launch "
                     "finishing the level chunks in order + ONE exchange launch beside it; launch: a launch pair per chunk")
     ap.add_argument("--fuse-field", action="store_true", help="use the fused encoder+MLP kernels (hbr_field_*_tc)")
     ap.add_argument("--fuse-gather", action="store_true", help="A/B: hbr_field_fwd_rays_tc, the hash-grid gather on dedicated "

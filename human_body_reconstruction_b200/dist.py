@@ -390,9 +390,13 @@ def attach_grad_allreduce(encoder, mlp, group=None, kind: str = "auto", **peer_k
     kw.setdefault("overlap", True)        # launch-per-chunk form, measured best at 4 096 rays/GPU: 2 level chunks, 32 CTAs on
     kw.setdefault("chunks", 2)            # the side stream (W=8: 0.656 ms/step against 0.712 behind the backward, 0.671 with 4)
     if kw.get("streamed", None) is None:
-        kw["streamed"] = True             # one scatter-add launch + one exchange launch side by side, 4 equal level chunks
-        if "chunks" not in peer_kw:       # (W=8, 4 096 rays/GPU: 0.594 ms/step; [8,12,14,15] 0.634; a launch pair per chunk 0.639)
-            kw["chunks"] = 4
+        # W >= 3 (NVLS multicast): one scatter-add launch + one exchange launch side by side, 4 equal level chunks
+        # (W=8, 4 096 rays/GPU: 0.591 ms/step; 3 chunks 0.596; [6,10,13] 0.598; [6,9,12,14] 0.606; a launch pair per chunk 0.639).
+        # W = 2 (peer loads/stores, which take SMs and L2 bandwidth from the scatter-add they run beside): a launch pair
+        # per chunk, 2 chunks: 0.639 ms/step against 0.688 streamed
+        kw["streamed"] = world > 2
+        if "chunks" not in peer_kw:
+            kw["chunks"] = 4 if world > 2 else 2
     if kw.get("transport", "auto") == "auto":
         kw["transport"] = "ipc" if world == 2 else "symm"
     red, err = None, None
