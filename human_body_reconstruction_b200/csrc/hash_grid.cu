@@ -8,7 +8,6 @@
 // equal cells with shuffles before issuing one red.global.add.v2.f32 per distinct entry.
 // Rows of y / dy cross shared memory so global traffic is full 128-byte lines.
 #include "common.cuh"
-#include <stdlib.h>
 
 namespace hbr {
 
@@ -374,8 +373,8 @@ hash_bwd_lm_kernel(const typename PointSrc<XT>::type x, long long n, const float
     const int b0 = plan.bounds[c], b1 = plan.bounds[c + 1];
 #pragma unroll 1
     for (int i = b0; i < b1; ++i) {
-      // odd warps walk the chunk's levels backwards: a chunk that pairs coarse levels (shuffle-merge work on the SM) with
-      // fine ones (reductions, L2-bound) keeps both kinds of work in flight at any time
+      // odd warps walk the chunk's levels backwards, so that cheap (coarse: shuffle merges) and expensive (fine: one
+      // reduction per corner) levels are in flight together; chunks pairing level c with L-1-c were measured too: no gain
       const int l = plan.order[((threadIdx.x >> 5) & 1) ? b1 - 1 - (i - b0) : i];
       const float s = g.scale[l];
       const FV* dyl = reinterpret_cast<const FV*>(dy) + (size_t)l * n;
@@ -790,11 +789,6 @@ static int make_lm_plan(const hbr_hash_geom* geom, const int* bounds, int nchunk
     plan.bounds[0] = 0;
     plan.bounds[1] = geom->L;
     for (int l = 0; l < geom->L; ++l) plan.order[l] = l;
-    if (getenv("HBR_LM_PAIR")) {                    // experiment: pairs (c, L-1-c) as chunks
-      plan.nchunks = geom->L / 2;
-      for (int c = 0; c < geom->L / 2; ++c) { plan.bounds[c] = 2 * c; plan.order[2 * c] = c; plan.order[2 * c + 1] = geom->L - 1 - c; }
-      plan.bounds[geom->L / 2] = geom->L;
-    }
     return HBR_OK;
   }
   return make_plan(geom, bounds, nchunks, done, plan);

@@ -177,3 +177,37 @@ def test_level_chunks_boundaries():
     for c in (1, 2, 5, 16, 40, [3], [1, 2, 3]):
         ch = Fake(c).level_chunks(None, 16)
         assert ch[0][0] == 0 and ch[-1][1] == 16 and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+
+
+def test_stream_plan_and_level_bounds_host_logic():
+    """Host side of the streamed exchange: the base exchange never streams; PeerGradAllReduce.stream_plan streams only the
+    encoder's last table backward, only when `streamed`, only below CHUNK_MAX_POINTS and only with more than one chunk;
+    ops._bounds turns a chunk list into the C ABI's level_bounds and rejects lists that do not partition the levels."""
+    from human_body_reconstruction_b200 import ops
+    from human_body_reconstruction_b200.dist import PeerGradAllReduce, _GradExchange
+
+    class Base(_GradExchange):
+        def __init__(self):
+            pass
+
+    assert Base().stream_plan(object(), 16, 1000) is None
+
+    enc, other = object(), object()
+
+    class Fake(PeerGradAllReduce):
+        def __init__(self, streamed, chunks):
+            self.streamed, self.overlap, self._nchunks, self._enc = streamed, True, chunks, enc
+
+    assert Fake(True, 4).stream_plan(enc, 16, 524288) == [(0, 4), (4, 8), (8, 12), (12, 16)]
+    assert Fake(True, [6, 10, 13]).stream_plan(enc, 16, 524288) == [(0, 6), (6, 10), (10, 13), (13, 16)]
+    assert Fake(False, 4).stream_plan(enc, 16, 524288) is None                        # launch pair per chunk
+    assert Fake(True, 4).stream_plan(other, 16, 524288) is None                       # not the encoder
+    assert Fake(True, 4).stream_plan(enc, 16, Fake.CHUNK_MAX_POINTS + 1) is None      # long steps are not chunked
+    assert Fake(True, 1).stream_plan(enc, 16, 524288) is None                         # a single chunk: nothing to stream
+    assert Fake(True, 4).stream_plan(enc, 16, 0) is None
+
+    b, n = ops._bounds([(0, 4), (4, 8), (8, 16)], 16)
+    assert n == 3 and list(b) == [0, 4, 8, 16]
+    for bad in ([(0, 4), (5, 16)], [(0, 4), (4, 12)], [(1, 16)], [(0, 8), (8, 8), (8, 16)], [(0, 8), (4, 16)]):
+        with pytest.raises(ValueError):
+            ops._bounds(bad, 16)
