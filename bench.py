@@ -519,6 +519,7 @@ def run_b200(args):
     c3 = c3_leg(args, world, rank, dev, vr, nerf, enc, mlp, params, c2w, K, H, W, amp, amp_dtype, barrier) if args.c3 else None
     grad_check = grad_check_leg(hdist, tdist, reducer, enc, mlp, params, step, resident, world, rank, args) if world > 1 else None
     grid = grid_leg(args, hbr, hdist, world, rank, dev, mx, mn, sigma, barrier) if args.grid else None
+    c5 = c5_leg(args, hbr, dev, pe, mn, mx, sigma, near, far, flush, amp_dtype) if (world == 1 and amp and args.c5) else None
     if rank != 0:
         _finish(world)
         return
@@ -583,6 +584,8 @@ def run_b200(args):
         line["grad_check"] = grad_check
     if grid is not None:
         line["grid"] = grid
+    if c5 is not None:
+        line["c5"] = c5
     if reducer is not None:
         line["allreduce_bytes_per_step"] = 4 * sum(p.numel() for p in params)      # flat table + MLP gradients, fp32
         region = getattr(reducer, "region", None)
@@ -697,6 +700,61 @@ def c3_leg(args, world, rank, dev, vr, nerf, enc, mlp, params, c2w, K, H, W, amp
                 "steps": nstep, "warmup": 3, "launch": "eager", "ms_each_step_this_rank": per_step,
                 "step_roofline_frac_per_gpu": STEP_BYTES_PER_POINT * n_pts / (ms * 1e-3) / 1e9 / measured_peaks()[0]}
     except Exception as e:                                                 # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
+def c5_leg(args, hbr, dev, pe, mn, mx, sigma, near, far, flush, amp_dtype):
+    """BASELINE configs[4], the human-reconstruction shape: T = 2^22 tables (512 MiB + 512 MiB of gradient), 256 samples per
+    ray with hierarchical resampling (coarse 256 + fine 512 = 768 field evaluations per ray, both passes in the loss,
+    train_hash2.py:221), 4096 rays of a 1080 x 1920 frame.  Graph replay, L2 flushed between steps, CUDA events; the step
+    roofline is the same 2792 B per evaluated point."""
+    try:
+        from human_body_reconstruction_b200.graph import GraphedStep
+        R, S, T = 4096, 256, 2 ** 22
+        torch.manual_seed(5)
+        enc = hbr.HashEncoder(N_min=16, N_max=args.max_res, L=16, F=2, T=T, dim=3, mu=mn.to(dev), sigma=sigma.to(dev))
+        with torch.no_grad():
+            for e in enc.Embedding_list:
+                e.weight.mul_(1e4)
+        mlp = hbr.MLP_3D(num_sig=2, num_col=2, L=16, F=2, d_view=24, max_bound=mx, min_bound=mn)
+        enc, mlp = enc.to(dev), mlp.to(dev)
+        vr = hbr.Volume_Renderer(H=1080, W=1920, K=torch.eye(3), near=near, far=far, device=dev, Pos_encode=enc, Dir_encode=pe,
+                                 max_dim=1024, sigma_val=sigma, mu=mn)
+        g = torch.Generator().manual_seed(11)
+        ro = (torch.tensor([[0.2, -0.1, 4.0]]).repeat(R, 1) + 0.05 * torch.randn(R, 3, generator=g)).to(dev)
+        rd = torch.nn.functional.normalize(-ro.cpu() + 0.5 * torch.randn(R, 3, generator=g), dim=-1).to(dev)
+        dn = (1 + 0.2 * torch.rand(R, 1, generator=g)).to(dev)
+        gt = torch.rand(R, 3, generator=g).to(dev)
+        params = list(enc.parameters()) + list(mlp.parameters())
+        gs = GraphedStep(vr, mlp, params, R, S, True, dev, autocast=True, autocast_dtype=amp_dtype).capture()
+        gs.load(ro, rd, dn, gt)
+        for _ in range(3):
+            gs()
+        torch.cuda.synchronize()
+        nstep, ev = 10, []
+        for _ in range(nstep):
+            if flush is not None:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gs()
+            e1.record()
+            ev.append((e0, e1))
+        torch.cuda.synchronize()
+        per = sorted(a.elapsed_time(b) for a, b in ev)
+        ms = per[len(per) // 2]
+        loss = float(gs.loss) if hasattr(gs, "loss") and torch.is_tensor(gs.loss) else None
+        del gs, enc, mlp, vr, params
+        torch.cuda.empty_cache()
+        n_pts = R * 3 * S
+        return {"workload": f"configs[4]: {R} rays x {S} samples/ray hierarchical (coarse {S} + fine {2 * S} evaluations per ray), "
+                            f"L=16 F=2 T=2^22, fwd+bwd of both passes, synthetic 1080x1920 frame",
+                "ms_per_step": ms, "ms_min": per[0], "ms_max": per[-1], "value": R / (ms * 1e-3), "unit": "rays/s", "steps": nstep,
+                "warmup": 3, "launch": "cuda graph replay", "l2": "flushed between timed steps" if flush is not None else "warm",
+                "points_per_step": n_pts, "last_loss": loss,
+                "step_roofline_frac": STEP_BYTES_PER_POINT * n_pts / (ms * 1e-3) / 1e9 / measured_peaks()[0]}
+    except Exception as e:                                                 # noqa: BLE001
+        torch.cuda.empty_cache()
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
@@ -886,6 +944,7 @@ def main():
     ap.add_argument("--grid-res", type=int, default=512)
     ap.add_argument("--no-occupancy", action="store_true", help="skip the live-occupancy-grid leg (8f row 3)")
     ap.add_argument("--repeats", type=int, default=5, help="timed regions of K steps each; value = their median")
+    ap.add_argument("--no-c5", dest="c5", action="store_false", help="skip the configs[4] leg (T=2^22, 256 samples/ray hierarchical; N=1 only)")
     ap.add_argument("--no-c3", dest="c3", action="store_false", help="skip the configs[2] leg (2^20 rays/step global; 2^17 at N=1)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step from a CUDA graph (auto = on; falls back to eager if capture fails)")

@@ -16,6 +16,10 @@ from . import ops
 from .test_hash import MLP_3D  # noqa: F401  (helper.py:10 re-exports it through `from helper import *`)
 
 
+# SDF mode on the dedicated kernels of csrc/sdf.cu (False: the composed tensor expressions, kept as the A/B for the tests)
+SDF_KERNELS = True
+
+
 class VarModel(nn.Module):
     """helper.py:13-21 (SDF mode's learnable sharpness)."""
 
@@ -99,16 +103,27 @@ def calc_color(t, rgb, sigma, dir_norm, use_sdf: bool = False, var_model=None, r
 def _calc_color_sdf(t, rgb, sigma, var_model, rays, model, encoder):
     """helper.py:76-89,102-107, SDF mode: alpha_i = relu(1 - phi(s_{i+1}) / phi(s_i)) with phi = var_model (a sigmoid of
     learnable sharpness), transmittance = exclusive cumprod(1 - alpha), plus the eikonal term |grad sdf| from central
-    differences at the sample positions.  Elementwise torch ops on the device around the path's kernels (the 6 extra
-    encoder + sigma-net passes of the normals run through hbr_hash_encode_* / hbr_mlp_*_f32); like the reference it
-    needs `rays` (so hierarchical=True, whose fine pass passes none, fails the same way: AttributeError on None.device)."""
+    differences at the sample positions.  With the reference's own VarModel and the native MLP_3D / HashEncoder this is
+    three launches each way -- hbr_composite_sdf_fwd/bwd (the -10 clamp of :76 applied inside, the caller's tensor left
+    untouched like the NeRF branch) and the 6-point stencil of MLP_3D.eikonal_norms around ONE encoder + density-head
+    pass; any other var_model / model / encoder takes the reference's tensor expressions on the device.  Like the reference
+    it needs `rays` (so hierarchical=True, whose fine pass passes none, fails the same way: AttributeError on None.device)."""
+    mlp = getattr(model, "module", model)                                # the reference reaches through nn.DataParallel (:87)
+    if SDF_KERNELS and type(var_model) is VarModel and sigma.dim() == 2 and sigma.shape[1] <= 1024:
+        Cr, w = ops.CompositeSdf.apply(rgb, sigma, var_model.b, False)
+        if rays is None:
+            rays.device                                                  # test_hash.py:90 on None: the reference's failure
+        if isinstance(mlp, MLP_3D) and mlp._native and hasattr(encoder, "_flat_table"):
+            norm = mlp.eikonal_norms(rays, encoder=encoder)
+        else:
+            norm = eikonal_value(mlp.finite_difference_normals_approximator(rays, encoder=encoder))
+        return Cr, w[..., None], norm
     sigma[sigma < -10] = -10                                             # :76 (in place, as the reference)
     phi = var_model(sigma)
     alpha = torch.zeros_like(sigma)
     alpha[..., :-1] = 1 - phi[..., 1:] / phi[..., :-1]
     alpha = torch.nn.functional.relu(alpha)
     T = cumprod_exclusive(1 - alpha)
-    mlp = getattr(model, "module", model)                                # the reference reaches through nn.DataParallel (:87)
     grads = mlp.finite_difference_normals_approximator(rays, encoder=encoder)
     norm = eikonal_value(grads)
     wts = T[:, :, None] * alpha[:, :, None]

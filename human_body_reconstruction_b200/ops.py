@@ -382,6 +382,136 @@ class CompositeSplit(torch.autograd.Function):
         return drgb, dsig, None, None, None
 
 
+# ------------------------------------------------------------------------------------------------------
+# SDF mode: csrc/sdf.cu
+# ------------------------------------------------------------------------------------------------------
+def _sample_stride(x: torch.Tensor, width: int) -> Optional[int]:
+    """Element stride between consecutive samples of an (R,S[,width]) tensor whose samples are uniformly strided (a
+    contiguous tensor, or a column view of the MLP's packed (R*S,4) output); None if it has to be copied."""
+    R, S = x.shape[0], x.shape[1]
+    if x.dim() == 3 and (x.shape[2] != width or (width > 1 and x.stride(2) != 1)):
+        return None
+    st = x.stride(1) if S > 1 else (x.stride(0) if R > 1 else max(width, 1))
+    if R > 1 and x.stride(0) != S * st:
+        return None
+    return int(st) if st >= width else None
+
+
+def _sdf_views(rgb, sdf):
+    if rgb.dtype != torch.float32 or _sample_stride(rgb, 3) is None:
+        rgb = rgb.float().contiguous()
+    if sdf.dtype != torch.float32 or _sample_stride(sdf, 1) is None:
+        sdf = sdf.float().contiguous()
+    return rgb, _sample_stride(rgb, 3), sdf, _sample_stride(sdf, 1)
+
+
+def _composite_sdf_fwd(rgb, rgb_st, sdf, sdf_st, from_density, b32, R, S):
+    Cc = torch.empty((R, 3), device=sdf.device, dtype=torch.float32)
+    w = torch.empty((R, S), device=sdf.device, dtype=torch.float32)
+    check(lib().hbr_composite_sdf_fwd(ptr(rgb), rgb_st, ptr(sdf), sdf_st, from_density, ptr(b32), R, S, ptr(Cc), ptr(w), stream()))
+    return Cc, w
+
+
+def _composite_sdf_bwd(rgb, rgb_st, sdf, sdf_st, from_density, b32, R, S, gC, gw):
+    """-> (d4 (R*S,4) packed [d rgb, d sdf] (one 16-byte store per sample), dL/db as a 0-dim tensor)."""
+    dev = b32.device
+    d4 = torch.empty((R * S, 4), device=dev, dtype=torch.float32)
+    db_ray = torch.empty((R,), device=dev, dtype=torch.float32)
+    gC = _f32c(gC) if gC is not None else torch.zeros((R, 3), device=dev)
+    gw = _f32c(gw.reshape(R, S)) if gw is not None else None
+    check(lib().hbr_composite_sdf_bwd(ptr(rgb), rgb_st, ptr(sdf), sdf_st, from_density, ptr(b32), R, S, ptr(gC), ptr(gw),
+                                      ptr(d4), 4, ptr(d4[:, 3:]), 4, ptr(db_ray), stream()))
+    return d4, db_ray.sum()
+
+
+class CompositeSdf(torch.autograd.Function):
+    """calc_color's SDF branch (helper.py:76-86,102-105) on rgb (R,S,3) / sdf (R,S) with VarModel's sharpness b (0-dim
+    parameter) -> (C (R,3), w (R,S)).  from_density: `sdf` holds the density head's LeakyReLU output and the SDF value
+    2*sigmoid(pre-activation) - 1 (test_hash.py:59-60) is formed inside the kernel."""
+
+    @staticmethod
+    def forward(ctx, rgb, sdf, b, from_density=False):
+        require_cuda(rgb, sdf, b)
+        R, S = sdf.shape
+        rgb, rgb_st, sdf, sdf_st = _sdf_views(rgb, sdf)
+        b32 = b.detach().reshape(1).float().contiguous()
+        Cc, w = _composite_sdf_fwd(rgb, rgb_st, sdf, sdf_st, int(bool(from_density)), b32, R, S)
+        ctx.save_for_backward(rgb, sdf, b32)
+        ctx.meta = (rgb_st, sdf_st, int(bool(from_density)), b.shape, b.dtype)
+        ctx.set_materialize_grads(False)          # an unused weight output costs no zero-filled (R,S) gradient
+        return Cc, w
+
+    @staticmethod
+    def backward(ctx, gC, gw):
+        rgb, sdf, b32 = ctx.saved_tensors
+        rgb_st, sdf_st, from_density, b_shape, b_dtype = ctx.meta
+        R, S = sdf.shape
+        d4, db = _composite_sdf_bwd(rgb, rgb_st, sdf, sdf_st, from_density, b32, R, S, gC, gw)
+        d4 = d4.view(R, S, 4)
+        return d4[..., :3], d4[..., 3], db.reshape(b_shape).to(b_dtype), None
+
+
+class CompositeSdfPacked(torch.autograd.Function):
+    """The same on the MLP's packed (R*S,4) [rgb, density-or-sdf] output: no column views, the gradient goes back as one
+    (R*S,4) tensor (Volume_Renderer's native SDF route)."""
+
+    @staticmethod
+    def forward(ctx, out4, b, R, S, from_density=True):
+        require_cuda(out4, b)
+        out4 = _f32c(out4)
+        b32 = b.detach().reshape(1).float().contiguous()
+        Cc, w = _composite_sdf_fwd(out4, 4, out4[:, 3:], 4, int(bool(from_density)), b32, R, S)
+        ctx.save_for_backward(out4, b32)
+        ctx.meta = (R, S, int(bool(from_density)), b.shape, b.dtype)
+        ctx.set_materialize_grads(False)
+        return Cc, w
+
+    @staticmethod
+    def backward(ctx, gC, gw):
+        out4, b32 = ctx.saved_tensors
+        R, S, from_density, b_shape, b_dtype = ctx.meta
+        d4, db = _composite_sdf_bwd(out4, 4, out4[:, 3:], 4, from_density, b32, R, S, gC, gw)
+        return d4, db.reshape(b_shape).to(b_dtype), None, None, None
+
+
+def sdf_stencil_points(x: torch.Tensor, eps: float, lo, hi) -> torch.Tensor:
+    """x (n,3) -> (6,n,3): clamp(x +- eps e_axis, lo, hi) for axis = x, y, z (test_hash.py:91-102), slabs [+x, -x, +y, ...]."""
+    require_cuda(x)
+    x = _f32c(x)
+    n = x.shape[0]
+    pts = torch.empty((6, n, 3), device=x.device, dtype=torch.float32)
+    lo3, hi3 = (C.c_float * 3)(*lo), (C.c_float * 3)(*hi)
+    check(lib().hbr_sdf_stencil_points(ptr(x), n, float(eps), lo3, hi3, ptr(pts), stream()))
+    return pts
+
+
+class SdfEikonal(torch.autograd.Function):
+    """dens6 (6,n): LeakyReLU density-head output at the stencil points -> (norm (n), grads (n,3)): the central differences
+    of 2*sigmoid(pre-activation) - 1 and their Euclidean norm (test_hash.py:104, helper.py:293-297).  Only the norm carries
+    a gradient."""
+
+    @staticmethod
+    def forward(ctx, dens6, eps):
+        require_cuda(dens6)
+        dens6 = _f32c(dens6)
+        n = dens6.shape[1]
+        norm = torch.empty((n,), device=dens6.device, dtype=torch.float32)
+        grads = torch.empty((n, 3), device=dens6.device, dtype=torch.float32)
+        check(lib().hbr_sdf_eikonal_fwd(ptr(dens6), n, float(eps), ptr(norm), ptr(grads), stream()))
+        ctx.save_for_backward(dens6)
+        ctx.eps = float(eps)
+        ctx.mark_non_differentiable(grads)
+        return norm, grads
+
+    @staticmethod
+    def backward(ctx, gnorm, _ggrads):
+        (dens6,) = ctx.saved_tensors
+        n = dens6.shape[1]
+        dd = torch.empty_like(dens6)
+        check(lib().hbr_sdf_eikonal_bwd(ptr(dens6), n, ctx.eps, ptr(_f32c(gnorm)), ptr(dd), stream()))
+        return dd, None
+
+
 def hier_sample(w: torch.Tensor, t: torch.Tensor, u: torch.Tensor, cand: torch.Tensor, clamp_in_place=False) -> torch.Tensor:
     require_cuda(w, t, u, cand)
     R, S = w.shape

@@ -218,6 +218,34 @@ class MLP_3D(nn.Module):
             cols.append(0.5 * (pos - neg) / epsilon)
         return torch.cat(cols, dim=-1)
 
+    def _bounds_host(self):
+        """(min_bound, max_bound) as host floats for the stencil kernel's clamp; one read-back per change of the tensors."""
+        key = (self.min_bound.data_ptr(), self.min_bound._version, self.max_bound.data_ptr(), self.max_bound._version)
+        if getattr(self, "_bounds_key", None) != key:
+            lo = self.min_bound.detach().float().reshape(-1).cpu().tolist()
+            hi = self.max_bound.detach().float().reshape(-1).cpu().tolist()
+            self._bounds_val = (lo * 3 if len(lo) == 1 else lo, hi * 3 if len(hi) == 1 else hi)
+            self._bounds_key = key
+        return self._bounds_val
+
+    def eikonal_norms(self, x, epsilon=0.0005, encoder=None, with_grads=False):
+        """eikonal_value(finite_difference_normals_approximator(x)) (helper.py:87-89) as a 6-point stencil: one kernel forms
+        the six clamped positions, ONE encoder pass and ONE density-head pass (fp32 kernels) evaluate them, one kernel turns
+        the six values into 2*sigmoid - 1, the central differences and their norm -- instead of six encoder + sigma-net
+        passes and ~30 elementwise launches; the backward is the mirror image (gradients reach the tables and the MLP
+        through the same autograd nodes as any other encoder / field call)."""
+        self._check_native()
+        if not x.is_cuda:
+            raise RuntimeError("MLP_3D.eikonal_norms needs CUDA tensors (there is no CPU fallback)")
+        if encoder is None:
+            raise ValueError("eikonal_norms takes sample POSITIONS and needs the encoder")
+        n = x.shape[0]
+        lo, hi = self._bounds_host()
+        pts = ops.sdf_stencil_points(x.detach().reshape(n, 3), float(epsilon), lo, hi)
+        dens = self._density(encoder(pts.view(6 * n, 3)))
+        norm, grads = ops.SdfEikonal.apply(dens.reshape(6, n), float(epsilon))
+        return (norm, grads) if with_grads else norm
+
     def forward(self, x, viewdirs=None, mask=None):
         self._check_native()
         if not x.is_cuda:

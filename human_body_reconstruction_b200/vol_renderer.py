@@ -365,6 +365,11 @@ class Volume_Renderer:
         # exactly 0 in fp32; identical results whenever the depth does not fall back below it (always for sigma >= 0 -- the
         # reference's LeakyReLU density can be slightly negative, hence off by default).
         self.ert = False
+        # SDF mode (use_sdf) with the native modules and the reference's VarModel: the field runs as in NeRF mode and the
+        # SDF compositing / eikonal stencil kernels of csrc/sdf.cu take its packed output (False: the reference's data flow,
+        # _generic, whose calc_color still uses those kernels).  hierarchical=True stays on _generic: it fails there exactly
+        # like the reference does (vol_renderer.py:242 passes no sample positions).
+        self.sdf_native = True
 
     # -- occupancy grid (vol_renderer.py:116-140) --------------------------------------------------------------
     def update_grid(self, points: torch.Tensor, alpha: torch.Tensor):
@@ -501,6 +506,10 @@ class Volume_Renderer:
         device = "cuda"
         if t is None:
             t = strat_sampler(near, far, num_samples, device=rays_d.device)                 # RNG draw #1
+        if self.use_sdf and self.sdf_native and hierarchical is not True and update_mask is not True:
+            sdf_mlp = self._native_sdf(model)
+            if sdf_mlp is not None and self._grid_all_true():
+                return self._render_sdf(sdf_mlp, rays_o, rays_d, t)
         mlp = self._native(model)
         if mlp is not None and not self._dp_checked:
             self._dp_checked = True
@@ -541,6 +550,34 @@ class Volume_Renderer:
             return Cr, (Cr if hierarchical is not True else torch.cat(Cfs)), None
         Cr, Cf = self._render_rays(mlp, rays_o, rays_d, t, dir_enc, dir_norm, mask_needed, hierarchical, _u, _u_cand)
         return Cr, Cf, None
+
+    # -- SDF mode on the native modules (vol_renderer.py:165-223 with use_sdf -> helper.py:76-89) -----
+    def _native_sdf(self, model):
+        from .helper import VarModel
+        m = _unwrap(model)
+        ok = (isinstance(self.Pos_encode, HashEncoder) and isinstance(self.Dir_encode, PositionalEncoder)
+              and isinstance(m, MLP_3D) and m._native and type(self.var_model) is VarModel)
+        return m if ok else None
+
+    def _render_sdf(self, mlp, rays_o, rays_d, t):
+        """One coarse pass in SDF mode: the field as in NeRF mode (directions encoded once per ray, packed (N,4) output with
+        the density head's LeakyReLU value in column 3), then hbr_composite_sdf_* forms 2*sigmoid - 1 and composites in one
+        kernel each way, and the eikonal norms come from the 6-point stencil (MLP_3D.eikonal_norms).  dir_norm plays no
+        part (helper.py:71 computes del_t, the SDF branch never reads it).  Returns (Cr, Cr, norm) like the reference."""
+        rays_o = rays_o.float().contiguous()
+        rays_d = rays_d.float().contiguous()
+        dir_enc = self.Dir_encode(rays_d)
+        R, S = rays_o.shape[0], t.shape[-1]
+        enc = self.Pos_encode
+        pts = ops.ray_points(rays_o, rays_d, t).view(-1, 3)
+        if self._can_chain(mlp):
+            out4 = _FieldRaysFn.apply(rays_o, rays_d, t.float().contiguous(), dir_enc.float().contiguous(), enc, mlp,
+                                      *[e.weight for e in enc.Embedding_list], *mlp._ordered())
+        else:
+            out4 = mlp.field(enc(pts), dir_enc, S, raw=True)
+        Cr, _ = ops.CompositeSdfPacked.apply(out4, self.var_model.b, R, S, bool(mlp.use_sdf))
+        norm = mlp.eikonal_norms(pts, encoder=enc)
+        return Cr, Cr, norm
 
     def _render_rays(self, mlp, rays_o, rays_d, t, dir_enc, dir_norm, mask_needed, hierarchical, _u, _u_cand):
         Cr, w = self._field_pass(mlp, rays_o, rays_d, t, dir_enc, dir_norm, mask_needed)

@@ -284,6 +284,31 @@ int hbr_composite_bwd(const float* t, int64_t t_ray_stride, const float* rgb, in
 int hbr_hier_sample(float* w, const float* t, const float* u, const float* cand, int64_t R, int64_t S,
                     int clamp_in_place, float* t_fine, void* stream);
 
+/* ---- 8f row 4: SDF mode (--use_sdf) -----------------------------------------------------------------
+ * hbr_composite_sdf_fwd/bwd = the SDF branch of calc_color (helper.py:76-86,102-105): phi = VarModel (helper.py:18-21,
+ * b = its sharpness parameter, ONE float on the device), alpha_i = relu(1 - phi(s_{i+1}) / phi(s_i)) (last sample 0),
+ * T = exclusive cumprod(1 - alpha), C = sum T alpha rgb.  One warp per ray; rgb / sdf addressed like hbr_composite_fwd
+ * ((r*S+s)*stride).  from_density != 0: the sdf column holds the density head's LeakyReLU output d and the SDF value
+ * 2*sigmoid(d > 0 ? d : 100 d) - 1 (test_hash.py:59-60 on the recovered pre-activation) is formed in the kernel, the
+ * gradient handed back is then with respect to d.  The -10 clamp of helper.py:76 is applied in the kernel (gradient 0).
+ * bwd: gw (R,S) optional gradient of the weights; db_ray (R): per-ray partial sums of dL/db (the caller adds them up). */
+int hbr_composite_sdf_fwd(const float* rgb, int64_t rgb_stride, const float* sdf, int64_t sdf_stride, int from_density,
+                          const float* b, int64_t R, int64_t S, float* C, float* w, void* stream);
+int hbr_composite_sdf_bwd(const float* rgb, int64_t rgb_stride, const float* sdf, int64_t sdf_stride, int from_density,
+                          const float* b, int64_t R, int64_t S, const float* gC, const float* gw, float* drgb,
+                          int64_t drgb_stride, float* dsdf, int64_t dsdf_stride, float* db_ray, void* stream);
+/* The eikonal term, MLP_3D.finite_difference_normals_approximator + eikonal_value (test_hash.py:86-105, helper.py:293-297),
+ * as a 6-point stencil around ONE encoder + density-head pass instead of six:
+ * hbr_sdf_stencil_points: x (n,3) -> pts (6,n,3), slab 2*axis = clamp(x + eps e_axis, lo, hi), slab 2*axis+1 = clamp(x - eps
+ * e_axis, lo, hi) (lo / hi = MLP_3D.min_bound / max_bound, host floats);
+ * hbr_sdf_eikonal_fwd: dens6 (6,n) = LeakyReLU density-head output at those points -> norm (n) = |0.5 (s+ - s-) / eps| with
+ * s = 2 sigmoid(pre-activation) - 1; grads (n,3) optional (the central differences themselves);
+ * hbr_sdf_eikonal_bwd: gnorm (n) -> ddens6 (6,n). */
+int hbr_sdf_stencil_points(const float* x, int64_t n, float eps, const float* lo3_host, const float* hi3_host, float* pts,
+                           void* stream);
+int hbr_sdf_eikonal_fwd(const float* dens6, int64_t n, float eps, float* norm, float* grads, void* stream);
+int hbr_sdf_eikonal_bwd(const float* dens6, int64_t n, float eps, const float* gnorm, float* ddens6, void* stream);
+
 /* ---- a13: nerf2mesh.py:27-40,69-86 density grid -----------------------------------------------------
  * Grid point p = (i*res + j)*res + k  <->  (x[j], y[i], z[k]) with x,y,z = np.linspace(min,max,res)
  * evaluated in float64 (numpy 1.23 semantics, Nerf.yml:119) and rounded to fp16 (nerf2mesh.py:31-40).

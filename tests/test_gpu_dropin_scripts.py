@@ -151,6 +151,29 @@ def test_nerf2mesh_runs_unmodified_on_the_dropins(trained):
 
 
 @needs_ref
+def test_train_hash2_use_sdf_runs_unmodified_on_the_sdf_kernels(tmp_path):
+    """`train_hash2.py --use_sdf`, unmodified: VarModel + Volume_Renderer(use_sdf=True) as the script
+    builds them (train_hash2.py:122-126; its MLP_3D keeps use_sdf=False, so the density column itself is composited as the
+    SDF), the eikonal term in the loss (:223-224), three optimisers stepped through the GradScaler (:226-237).  Every step
+    must go through the dedicated kernels of csrc/sdf.cu: one SDF compositing launch each way, one stencil, one eikonal
+    launch each way -- and none through the NeRF-mode compositor."""
+    work = str(tmp_path)
+    scene = os.path.join(work, "scene")
+    shutil.copytree(os.path.join(GOLDEN, "scene_new"), scene)
+    shutil.copy(os.path.join(scene, "transforms_train.json"), os.path.join(scene, "transforms_tmp.json"))
+    os.makedirs(os.path.join(work, "results"))
+    rep, out = run_script("train_hash2.py", ["--data_path", scene + "/", "--num_epochs", "2", "--num_batch", "16", "--num_samples", "16",
+                                             "--hash_size", "12", "--use_sdf", "--model_name", "s"], work,
+                          os.path.join(work, "sdf_report.json"))
+    assert rep["modules"]["helper"].startswith(os.path.join(ROOT, "dropin") + os.sep)
+    calls, steps = rep["calls"], 2 * 4
+    for name in ("hbr_composite_sdf_fwd", "hbr_composite_sdf_bwd", "hbr_sdf_stencil_points", "hbr_sdf_eikonal_fwd", "hbr_sdf_eikonal_bwd"):
+        assert calls.get(name, 0) == steps, (name, calls)
+    assert calls.get("hbr_composite_fwd", 0) == 0 and calls.get("hbr_mlp_fwd_tc", 0) == steps       # the field itself: fp16 autocast
+    assert "DATASET_LENGTH: 4" in out
+
+
+@needs_ref
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_train_hash2_unmodified_on_two_gpus(tmp_path):
     """torchrun + launch_rank.py: the unmodified trainer, one process per GPU; the drop-in renderer broadcasts rank 0's
