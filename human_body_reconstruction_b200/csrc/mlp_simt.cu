@@ -171,29 +171,40 @@ template <int IN0P, int KCP>
 __global__ void __launch_bounds__(kMlpThreads)
 mlp_bwd_point_kernel(long long n, const float* __restrict__ params, int in0, int dv, long long dir_group,
                      const float* __restrict__ dout, const float* __restrict__ act, float* __restrict__ dz,
-                     float* __restrict__ dfeat, long long dfeat_stride, float* __restrict__ ddirs) {
+                     float* __restrict__ dfeat, long long dfeat_stride, float* __restrict__ ddirs, int dens_only) {
+  // dens_only: the backward of the density-only forward (dirs == NULL there): dout is (n) -- the gradient of the
+  // LeakyReLU density --, the colour net is not walked and the 15 feature outputs of the density head carry no gradient
+  // (SDF mode's eikonal stencil, test_hash.py:78-84: six such evaluations per sample).
   extern __shared__ __align__(16) float smem[];
   const MlpLayout m = make_layout(in0, dv);
   const SmemW s = make_smem_layout(m, IN0P, KCP);
   float* ws = smem;
   float* col = smem + s.total + threadIdx.x;
-  stage_weights(params, m, s, ws, 0, 5);
+  stage_weights(params, m, s, ws, 0, dens_only ? 2 : 5);
   __syncthreads();
 
   for (long long gp = (long long)blockIdx.x * kMlpThreads + threadIdx.x; gp < n; gp += (long long)gridDim.x * kMlpThreads) {
+    float d[kH];
+    float dsig16[kSigOut];
+    float go_w;
+    if (dens_only) {
+      go_w = __ldg(dout + gp);
+#pragma unroll
+      for (int k = 1; k < kSigOut; ++k) dsig16[k] = 0.f;
+    } else {
     const float4 go = *reinterpret_cast<const float4*>(dout + gp * 4);
+    go_w = go.w;
     // colour head: ELU'
     {
       const float g[3] = {go.x, go.y, go.z};
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float pre = act[(size_t)(kRowRgb + c) * n + gp];
-        const float d = g[c] * (pre > 0.f ? 1.f : expf(pre));
-        col[c * kMlpThreads] = d;
-        dz[(size_t)(kRowRgb + c) * n + gp] = d;
+        const float dpre = g[c] * (pre > 0.f ? 1.f : expf(pre));
+        col[c * kMlpThreads] = dpre;
+        dz[(size_t)(kRowRgb + c) * n + gp] = dpre;
       }
     }
-    float d[kH];
     dense_bwd<kH>(ws + s.W[5], 3, col, d);
 #pragma unroll
     for (int k = 0; k < kH; ++k) {
@@ -208,7 +219,6 @@ mlp_bwd_point_kernel(long long n, const float* __restrict__ params, int in0, int
       col[k * kMlpThreads] = v;
       dz[(size_t)(kRowC1 + k) * n + gp] = v;
     }
-    float dsig16[kSigOut];
     {
       float dc[KCP];
       dense_bwd<KCP>(ws + s.W[3], kH, col, dc);
@@ -221,7 +231,8 @@ mlp_bwd_point_kernel(long long n, const float* __restrict__ params, int in0, int
           if (k < kFeat + dv) atomicAdd(dd + (k - kFeat), dc[k]);
       }
     }
-    dsig16[0] = go.w * (act[(size_t)kRowO16 * n + gp] > 0.f ? 1.f : 0.01f);   // LeakyReLU'
+    }   // !dens_only
+    dsig16[0] = go_w * (act[(size_t)kRowO16 * n + gp] > 0.f ? 1.f : 0.01f);   // LeakyReLU'
 #pragma unroll
     for (int k = 0; k < kSigOut; ++k) {
       col[k * kMlpThreads] = dsig16[k];
@@ -375,8 +386,10 @@ extern "C" int hbr_mlp_bwd_f32(const float* feat, int64_t feat_stride, const flo
                                float* dz, float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams, void* stream) {
   if (int rc = check_dims(dims)) return rc;
   if (n == 0) return HBR_OK;
-  HBR_REQUIRE(feat && dirs && params && dout && act && dz, "NULL pointer (the backward needs the colour branch)");
-  HBR_REQUIRE((uintptr_t)dout % 16 == 0, "dout must be 16-byte aligned");
+  HBR_REQUIRE(feat && params && dout && act && dz, "NULL pointer");
+  const int dens_only = dirs == nullptr;             // backward of the density-only forward: dout is (n), no colour net
+  HBR_REQUIRE(dens_only || (uintptr_t)dout % 16 == 0, "dout must be 16-byte aligned");
+  HBR_REQUIRE(!dens_only || !ddirs, "ddirs requested without dirs");
   HBR_REQUIRE(!dfeat || dfeat_stride >= dims->in0, "dfeat_stride too small");
   const int in0p = dims->in0 <= 32 ? 32 : 64, kcp = dims->d_view + kFeat <= 40 ? 40 : 64;
   const size_t smem = simt_smem_bytes(dims, in0p, kcp);
@@ -386,12 +399,12 @@ extern "C" int hbr_mlp_bwd_f32(const float* feat, int64_t feat_stride, const flo
   if (int rc = set_smem(K, smem)) return rc;             \
   K<<<grid, kMlpThreads, smem, st>>>(__VA_ARGS__)
   HBR_MLP_DISPATCH(mlp_bwd_point_kernel, n, params, dims->in0, dims->d_view, dir_group, dout, act, dz, dfeat,
-                   dfeat_stride, ddirs);
+                   dfeat_stride, ddirs, dens_only);
 #undef HBR_MLP_GO
   HBR_LAUNCH_CHECK();
   if (dparams) {
     const long long chunk = 2048;
-    const dim3 g((unsigned)ceil_div(n, chunk), 6);
+    const dim3 g((unsigned)ceil_div(n, chunk), dens_only ? 3 : 6);   // density only: the three layers of the density head
     mlp_wgrad_kernel<<<g, 256, 0, st>>>(feat, feat_stride, dirs, dir_group, n, dims->in0, dims->d_view, act, dz,
                                         dparams, chunk);
     HBR_LAUNCH_CHECK();

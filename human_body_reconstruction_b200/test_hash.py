@@ -64,6 +64,42 @@ class _MlpFn(torch.autograd.Function):
         return (dfeat, ddirs, None, None, None) + tuple(mlp._grad_views(dflat))
 
 
+class _DensityFn(torch.autograd.Function):
+    """feat (N,in0) -> (N,1) LeakyReLU density, the density-only branch (test_hash.py:73-77) WITH a backward: fp32 kernels,
+    only the density head is evaluated and differentiated (hbr_mlp_fwd_f32 / hbr_mlp_bwd_f32 with dirs == NULL).  Serves
+    SDF mode's eikonal stencil, where six of these per sample are the bulk of the step."""
+
+    @staticmethod
+    def forward(ctx, feat, mlp, *params):
+        flat = mlp._flat_params()
+        dims = mlp._dims()
+        train = any(ctx.needs_input_grad)
+        feat = feat.float().contiguous()
+        out, act = ops.mlp_fwd_f32(feat, None, 1, flat, dims, keep_act=train)
+        if mlp._dp is not None and any(ctx.needs_input_grad[2:]):
+            mlp._dp.note_forward(mlp)
+        ctx.mlp, ctx.dims = mlp, dims
+        ctx.save_for_backward(feat, act)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        feat, act = ctx.saved_tensors
+        mlp = ctx.mlp
+        flat = mlp._flat_params()
+        dp = mlp._dp if any(ctx.needs_input_grad[2:]) else None
+        if dp is not None:
+            dflat, last = dp.enter_backward(mlp)
+        else:
+            dflat, last = torch.zeros_like(flat), False
+        dfeat, _ = ops.mlp_bwd_f32(feat, None, 1, flat, ctx.dims, dout.float().contiguous(), act, ctx.needs_input_grad[0], False, dflat)
+        if dp is not None:
+            if last:
+                dp.publish(mlp, dflat)
+            return (dfeat, None) + (None,) * len(mlp._ordered())
+        return (dfeat, None) + tuple(mlp._grad_views(dflat))
+
+
 class MLP_3D(nn.Module):
     def __init__(self, num_sig=3, num_col=2, h_size=64, d_view=3, L=16, F=2, E=0, use_sdf=False, max_bound=1.0,
                  min_bound=-1.0):
@@ -95,6 +131,12 @@ class MLP_3D(nn.Module):
         # operand format (and divides out of its results).  The reference's trainer scales the loss with GradScaler
         # (train_hash2.py:156,226), which does the same job from outside; set this when running fp16 operands without one.
         self.tc_grad_scale = 1.0
+        # SDF mode: forward_sdf / the eikonal stencil always run the fp32 kernels (central differences with eps = 5e-4
+        # amplify the density head's rounding 1000x).  The reference evaluates them inside torch.autocast like everything
+        # else (train_hash2.py:218 -> helper.py:87), i.e. with fp16 matrix products; True follows it: under autocast the
+        # training-time stencil pass runs on the 16-bit tensor-core kernels (measured 4096 x 128 samples x 6 stencil points:
+        # profiles/r02f_sdf_measurements.json).  Off by default.
+        self.sdf_follows_autocast = False
         self._dp = None               # the data-parallel gradient exchange attached to this module (dist._GradExchange)
         self._flat = None
         if self._native:
@@ -193,8 +235,11 @@ class MLP_3D(nn.Module):
     def _density(self, x) -> torch.Tensor:
         """LeakyReLU(dens_vec[:, 0:1]) of the sigma net for (N, L*F+E) features, with autograd when anything needs it."""
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            z = torch.zeros((x.shape[0], self.d_view), device=x.device)
-            return self.field(x, z, 1, use_tc=False, raw=True)[:, 3:4]
+            if self.sdf_follows_autocast and self._tc_operand(None):
+                z = torch.zeros((x.shape[0], self.d_view), device=x.device)
+                return self.field(x, z, 1, use_tc=None, raw=True)[:, 3:4]       # 16-bit tensor-core kernels (whole field)
+            self._check_native()
+            return _DensityFn.apply(x, self, *self._ordered())
         density, _ = ops.mlp_fwd_f32(x.float().contiguous(), None, 1, self._flat_params(), self._dims(), keep_act=False)
         return density
 

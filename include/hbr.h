@@ -137,7 +137,10 @@ int hbr_mlp_fwd_f32(const float* feat, int64_t feat_stride, const float* dirs, i
 
 /* dout (n,4).  dparams (flat, same layout as params) is ACCUMULATED into.  dfeat (n,in0) and
  * ddirs (n/dir_group, d_view; accumulated with atomics, caller zeroes; may be NULL) are written.
- * act is the buffer hbr_mlp_fwd_f32 filled; dz is scratch of the same size. */
+ * act is the buffer hbr_mlp_fwd_f32 filled; dz is scratch of the same size.
+ * dirs == NULL: the backward of the density-only forward -- dout is (n), the gradient of the density; only the three layers
+ * of the density head are walked and only their parameter gradients accumulated (ddirs must be NULL).  This is the sigma-net
+ * pass of SDF mode's eikonal stencil (test_hash.py:78-105: six density-only evaluations per sample). */
 int hbr_mlp_bwd_f32(const float* feat, int64_t feat_stride, const float* dirs, int64_t dir_group, int64_t n,
                     const float* params, const hbr_mlp_dims* dims, const float* dout, const float* act,
                     float* dz, float* dfeat, int64_t dfeat_stride, float* ddirs, float* dparams, void* stream);

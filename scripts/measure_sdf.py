@@ -97,5 +97,16 @@ for route in T.ROUTES:
     launches = h._lib.STATS.launches
     out["step_" + route] = {"fp32": timed(False), "fp16_autocast": timed(True), "hbr_launches_per_step": launches}
 h.helper.SDF_KERNELS = True
+vr.sdf_native = True
+mlp.sdf_follows_autocast = True
+out["step_native_stencil_follows_autocast"] = {"fp16_autocast": timed(True)}
+mlp.sdf_follows_autocast = False
+# where the time goes (native route, fp32 stencil): per C-ABI entry point, CUDA events around every call
+h._lib.STATS.reset()
+h._lib.STATS.timing = True
+step(True)
+torch.cuda.synchronize()
+h._lib.STATS.timing = False
+out["native_fp16_step_kernels_ms"] = {k: {"calls": c, "mean_ms": m} for k, (c, m) in sorted(h._lib.STATS.summary().items())}
 out["workload"] = f"{R} rays x {S} samples, L=16 F=2 T=2^19, use_sdf, fwd+bwd incl. the eikonal term, eager (host-driven), L2 warm"
 print(json.dumps(out))

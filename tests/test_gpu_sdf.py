@@ -238,3 +238,31 @@ def test_native_sdf_route_under_autocast_runs_the_tensor_core_field():
             Cr16, _, norm16 = vr.vol_render(*args, **kw)
     assert _rel(Cr16, Cr) < 5e-2, _rel(Cr16, Cr)
     assert torch.equal(norm16, norm)
+
+
+def test_density_only_backward_equals_the_density_column_of_the_full_field():
+    """hbr_mlp_bwd_f32 with dirs == NULL (the sigma-net pass of the eikonal stencil): d(features) bit-identical to the full
+    field's backward fed a gradient on the density column only (the per-point chain is the same arithmetic), density-head
+    parameter gradients equal up to the order of the atomic accumulation, colour-net gradients exactly zero."""
+    import human_body_reconstruction_b200 as h
+    from human_body_reconstruction_b200.test_hash import _DensityFn
+    torch.manual_seed(3)
+    mlp = h.MLP_3D(num_sig=2, num_col=2, L=16, F=2, d_view=24).to(DEV)
+    n = 5000
+    feat = torch.randn(n, 32, device=DEV)
+    gd = torch.randn(n, 1, device=DEV)
+    f1 = feat.clone().requires_grad_()
+    d1 = _DensityFn.apply(f1, mlp, *mlp._ordered())
+    d1.backward(gd)
+    g1 = {k: v.grad.clone() for k, v in mlp.named_parameters()}
+    for p in mlp.parameters():
+        p.grad = None
+    f2 = feat.clone().requires_grad_()
+    d2 = mlp.field(f2, torch.zeros(n, 24, device=DEV), 1, use_tc=False, raw=True)[:, 3:4]
+    d2.backward(gd)
+    assert torch.equal(d1, d2) and torch.equal(f1.grad, f2.grad)
+    for k, v in mlp.named_parameters():
+        if k.startswith("sig_model"):
+            assert _rel(g1[k], v.grad) < 1e-5, k
+        else:
+            assert float(g1[k].abs().max()) == 0.0 and float(v.grad.abs().max()) == 0.0, k

@@ -70,3 +70,33 @@ def test_same_seed_construction_reproduces_the_reference_parameters():
     for k in want:
         assert torch.equal(sd[k].cpu(), want[k]), k
     assert list(enc.state_dict().keys()) == [f"Embedding_list.{i}.weight" for i in range(L)]
+
+
+def test_sdf_compositor_accepts_column_views_of_the_packed_field_output_without_copies():
+    """ops._sample_stride: the SDF compositor addresses rgb / sdf as base + (r*S+s)*stride, so the (R,S,3) / (R,S) column
+    views of the MLP's packed (R*S,4) output (what vol_renderer.py:213-216 hands calc_color) go in as they are (stride 4),
+    contiguous tensors with strides 3 / 1, anything else is copied."""
+    from human_body_reconstruction_b200.ops import _sample_stride, _sdf_views
+    R, S = 5, 7
+    mo = torch.randn(R * S, 4)
+    rgb, sdf = mo[..., 0:3].reshape(R, S, -1), mo[..., 3:4].reshape(R, S)
+    assert _sample_stride(rgb, 3) == 4 and _sample_stride(sdf, 1) == 4
+    r2, rs, s2, ss = _sdf_views(rgb, sdf)
+    assert r2.data_ptr() == mo.data_ptr() and s2.data_ptr() == mo.data_ptr() + 12 and (rs, ss) == (4, 4)
+    assert _sample_stride(torch.randn(R, S, 3), 3) == 3 and _sample_stride(torch.randn(R, S), 1) == 1
+    assert _sample_stride(torch.randn(S, R, 3).transpose(0, 1), 3) is None and _sample_stride(torch.randn(S, R).t(), 1) is None
+    r3, rs3, s3, ss3 = _sdf_views(torch.randn(S, R, 3).transpose(0, 1).half(), torch.randn(S, R).t())
+    assert r3.is_contiguous() and r3.dtype == torch.float32 and s3.is_contiguous() and (rs3, ss3) == (3, 1)
+    for shape in ((1, 1), (1, S), (R, 1)):                                 # degenerate shapes keep a usable stride
+        assert _sample_stride(torch.randn(*shape, 3), 3) == 3 and _sample_stride(torch.randn(*shape), 1) == 1
+
+
+def test_mlp_bounds_for_the_eikonal_stencil_follow_the_tensors():
+    """MLP_3D._bounds_host: min_bound / max_bound (test_hash.py:25-26) as three host floats each for the stencil kernel's
+    clamp; scalars broadcast; re-read when the tensors change."""
+    import human_body_reconstruction_b200 as h
+    m = h.MLP_3D(num_sig=2, num_col=2, L=16, F=2, d_view=24, max_bound=torch.tensor([1., 2., 3.]), min_bound=torch.tensor([-1., -2., -3.]))
+    assert m._bounds_host() == ([-1.0, -2.0, -3.0], [1.0, 2.0, 3.0])
+    m.max_bound[1] = 5.0
+    assert m._bounds_host()[1] == [1.0, 5.0, 3.0]
+    assert h.MLP_3D(num_sig=2, num_col=2, L=16, F=2, d_view=24)._bounds_host() == ([-1.0] * 3, [1.0] * 3)

@@ -23,6 +23,15 @@ def test_modules_raise_without_cuda():
         mlp(torch.rand(4, 32), torch.rand(4, 24))
     with pytest.raises(RuntimeError, match="CUDA"):
         h.helper.calc_color(torch.linspace(2, 6, 4), torch.rand(2, 4, 3), torch.rand(2, 4), torch.ones(2, 1))
+    with pytest.raises(RuntimeError, match="CUDA"):                      # SDF mode (8f row 4): compositor, stencil, eikonal
+        h.helper.calc_color(torch.linspace(2, 6, 4), torch.rand(2, 4, 3), torch.rand(2, 4), torch.ones(2, 1), use_sdf=True,
+                            var_model=h.helper.VarModel(), rays=torch.rand(8, 3), model=mlp, encoder=enc)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mlp.eikonal_norms(torch.rand(4, 3), encoder=enc)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        h.ops.CompositeSdf.apply(torch.rand(2, 4, 3), torch.rand(2, 4), torch.tensor(0.5), False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        h.ops.sdf_stencil_points(torch.rand(4, 3), 5e-4, [-1.0] * 3, [1.0] * 3)
     vr = h.Volume_Renderer(H=4, W=4, K=torch.eye(3), near=torch.tensor(2.0), far=torch.tensor(6.0), device="cpu", Pos_encode=enc,
                            Dir_encode=h.PositionalEncoder(3, 4), max_dim=16, sigma_val=torch.tensor(1.0), mu=torch.zeros(3))
     with pytest.raises(RuntimeError, match="CUDA"):
