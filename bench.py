@@ -658,7 +658,7 @@ def occupancy_leg(args, dev, vr, nerf, params, rays, resident_packed, flush, amp
 def c3_leg(args, world, rank, dev, vr, nerf, enc, mlp, params, c2w, K, H, W, amp, amp_dtype, barrier):
     """BASELINE configs[2]: 2^20 rays per step GLOBAL, sharded over the ranks (2^20 / N per GPU, table + MLP gradients
     all-reduced); at N = 1 the single-GPU rate is taken on 2^17 rays (what one of 8 GPUs processes).  Eager launches (the
-    kernels run for milliseconds), 3 warm-up + 5 timed steps, CUDA events, max over ranks."""
+    kernels run for milliseconds), 3 warm-up + 5 timed steps, CUDA events per step; reported: the median step, max over ranks."""
     import torch.distributed as tdist
     rays = (1 << 20) // world if world > 1 else 1 << 17
     try:
@@ -685,10 +685,13 @@ def c3_leg(args, world, rank, dev, vr, nerf, enc, mlp, params, c2w, K, H, W, amp
             evs.append((e0, e1))
         barrier()
         per_step = [a.elapsed_time(b) for a, b in evs]
-        ms = torch.tensor([sum(per_step) / nstep], device=dev, dtype=torch.float64)
+        # median step of this rank, max over ranks: the eager step allocates ~10 GB of per-point temporaries and a single step
+        # now and then pays a cudaMalloc of a fresh allocator segment (seen: one 76 ms step among four of 11.5 ms); the mean
+        # and every step's time are reported beside it
+        ms = torch.tensor([sorted(per_step)[nstep // 2], sum(per_step) / nstep], device=dev, dtype=torch.float64)
         if world > 1:
             tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
-        ms = float(ms)
+        ms, ms_mean = float(ms[0]), float(ms[1])
         del o, d, n, gt
         for p in params:
             p.grad = None
@@ -697,7 +700,8 @@ def c3_leg(args, world, rank, dev, vr, nerf, enc, mlp, params, c2w, K, H, W, amp
         return {"workload": f"configs[2]: {rays * world} rays/step global = {rays} rays x {args.samples} samples per GPU on {world} GPU(s), "
                             f"T=2^{args.hash_size}, fwd+bwd" + (", gradients all-reduced" if world > 1 else " (single-GPU rate on 2^17 rays)"),
                 "rays_global": rays * world, "rays_per_gpu": rays, "ms_per_step": ms, "value": rays * world / (ms * 1e-3), "unit": "rays/s",
-                "steps": nstep, "warmup": 3, "launch": "eager", "ms_each_step_this_rank": per_step,
+                "steps": nstep, "warmup": 3, "launch": "eager", "ms_per_step_is": "median step, max over ranks", "ms_per_step_mean": ms_mean,
+                "ms_each_step_this_rank": per_step,
                 "step_roofline_frac_per_gpu": STEP_BYTES_PER_POINT * n_pts / (ms * 1e-3) / 1e9 / measured_peaks()[0]}
     except Exception as e:                                                 # noqa: BLE001
         return {"error": f"{type(e).__name__}: {e}"[:300]}
