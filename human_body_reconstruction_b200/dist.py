@@ -425,11 +425,36 @@ def broadcast_parameters(encoder, mlp, src: int = 0, group=None):
         dist.broadcast(mlp._flat_params(), src=src, group=group)
 
 
-def auto_attach(encoder, mlp, group=None):
+def attach_small_params(params, group=None, src: int = 0):
+    """Parameters that live outside the two flat gradient buffers -- SDF mode's VarModel.b (helper.py:13-21), one float --:
+    every rank takes rank `src`'s value now, and a post-accumulate hook averages the gradient over the ranks inside
+    loss.backward() (one tiny all-reduce per parameter; the table and MLP gradients keep their own exchange).  Idempotent."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return []
+    done = []
+    for p in params:
+        if getattr(p, "_hbr_dp_hook", None) is not None:
+            continue
+        with torch.no_grad():
+            dist.broadcast(p.data, src=src, group=group)
+
+        def hook(q, group=group):
+            if q.grad is not None:
+                dist.all_reduce(q.grad, op=dist.ReduceOp.SUM, group=group)
+                q.grad.div_(dist.get_world_size(group))
+
+        p._hbr_dp_hook = p.register_post_accumulate_grad_hook(hook)
+        done.append(p)
+    return done
+
+
+def auto_attach(encoder, mlp, group=None, extra=()):
     """launch_rank.py's zero-edit route (HBR_AUTO_DP=1): called by Volume_Renderer at its first native vol_render of a
-    process that belongs to a process group -- broadcast rank 0's parameters, attach the gradient exchange (once)."""
+    process that belongs to a process group -- broadcast rank 0's parameters, attach the gradient exchange (once).
+    extra: further small parameters of the step (SDF mode's VarModel), see attach_small_params."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return None
+    attach_small_params(extra, group)
     if getattr(encoder, "_dp", None) is not None:
         return encoder._dp
     broadcast_parameters(encoder, mlp, 0, group)

@@ -509,13 +509,11 @@ class Volume_Renderer:
         if self.use_sdf and self.sdf_native and hierarchical is not True and update_mask is not True:
             sdf_mlp = self._native_sdf(model)
             if sdf_mlp is not None and self._grid_all_true():
+                self._auto_dp(sdf_mlp)
                 return self._render_sdf(sdf_mlp, rays_o, rays_d, t)
         mlp = self._native(model)
-        if mlp is not None and not self._dp_checked:
-            self._dp_checked = True
-            if os.environ.get("HBR_AUTO_DP") == "1":            # launch_rank.py: zero-edit multi-GPU run of the trainer
-                from . import dist as _hdist
-                _hdist.auto_attach(self.Pos_encode, mlp)
+        if mlp is not None:
+            self._auto_dp(mlp)
         if mlp is None:
             return self._generic(model, rays_d, rays_o, t, update_mask, dir_norm, hierarchical, _u, _u_cand)
 
@@ -550,6 +548,18 @@ class Volume_Renderer:
             return Cr, (Cr if hierarchical is not True else torch.cat(Cfs)), None
         Cr, Cf = self._render_rays(mlp, rays_o, rays_d, t, dir_enc, dir_norm, mask_needed, hierarchical, _u, _u_cand)
         return Cr, Cf, None
+
+    def _auto_dp(self, mlp):
+        """launch_rank.py's zero-edit multi-GPU run of the trainer (HBR_AUTO_DP=1): at the first native render of a process
+        that belongs to a process group, take rank 0's parameters and attach the gradient exchange (dist.auto_attach);
+        SDF mode's VarModel parameter joins through a small all-reduce of its own."""
+        if self._dp_checked:
+            return
+        self._dp_checked = True
+        if os.environ.get("HBR_AUTO_DP") == "1":
+            from . import dist as _hdist
+            extra = list(self.var_model.parameters()) if (self.use_sdf and isinstance(self.var_model, nn.Module)) else ()
+            _hdist.auto_attach(self.Pos_encode, mlp, extra=extra)
 
     # -- SDF mode on the native modules (SURVEY 8f row 4; vol_renderer.py:165-223 with use_sdf -> helper.py:76-89) -----
     def _native_sdf(self, model):

@@ -211,3 +211,37 @@ def test_stream_plan_and_level_bounds_host_logic():
     for bad in ([(0, 4), (5, 16)], [(0, 4), (4, 12)], [(1, 16)], [(0, 8), (8, 8), (8, 16)], [(0, 8), (4, 16)]):
         with pytest.raises(ValueError):
             ops._bounds(bad, 16)
+
+
+def _small_param_worker(rank, world, port_no, tmp):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    from human_body_reconstruction_b200.helper import VarModel
+    var = VarModel()
+    with torch.no_grad():
+        var.b.fill_(0.5 + rank)                                        # every process initialised its own
+    assert hdist.attach_small_params(var.parameters()) == [var.b]
+    assert hdist.attach_small_params(var.parameters()) == []           # idempotent: one hook per parameter
+    b0 = float(var.b)
+    x = torch.linspace(-1, 1, 8) * (rank + 1)
+    for _ in range(2):                                                 # two backward passes: the hook fires on each
+        var.b.grad = None
+        var(x).sum().backward()
+    torch.save((b0, var.b.grad.clone()), os.path.join(tmp, f"b{rank}.pt"))
+    tdist.barrier()
+    tdist.destroy_process_group()
+
+
+def test_small_params_broadcast_and_gradient_average(tmp_path):
+    """dist.attach_small_params (SDF mode's VarModel.b under launch_rank.py): rank 0's value everywhere, gradient = mean
+    over the ranks' local gradients, identical on both ranks."""
+    mp.spawn(_small_param_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    (b0, g0), (b1, g1) = (torch.load(os.path.join(tmp_path, f"b{r}.pt")) for r in range(2))
+    assert b0 == 0.5 and b1 == 0.5
+    b = torch.tensor(0.5, requires_grad=True)
+    want = 0
+    for r in range(2):
+        x = torch.linspace(-1, 1, 8) * (r + 1)
+        (g,) = torch.autograd.grad((1 / (1 + torch.exp(-x * b))).sum(), b)
+        want = want + g / 2
+    assert torch.equal(g0, g1) and torch.allclose(g0, want, rtol=1e-6)

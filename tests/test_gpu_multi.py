@@ -139,3 +139,79 @@ def test_peer_memory_allreduce_equals_single_gpu(tmp_path, transport):
     dev = torch.device("cuda", 0)
     enc, mlp, vr = _build(dev)
     _check(tmp_path, enc, mlp, vr, dev, bit_identical=True)
+
+
+# ---- SDF mode sharded over 2 ranks ---------------------------------------------------------------------
+def _build_sdf(dev):
+    import human_body_reconstruction_b200 as h
+    enc, mlp, _ = _build(dev)
+    var = h.helper.VarModel().to(dev)
+    mu, maxb = torch.tensor([-4.27, -4.31, -3.95]), torch.tensor([4.28, 4.27, 2.37])
+    sigma = ((maxb - mu) ** 2).sum().sqrt()
+    vr = h.Volume_Renderer(H=8, W=8, K=torch.eye(3), near=torch.tensor(2.0), far=torch.tensor(6.0), device=dev, Pos_encode=enc,
+                           Dir_encode=h.PositionalEncoder(3, 4), max_dim=64, sigma_val=sigma, mu=mu, use_sdf=True, var_model=var)
+    return enc, mlp, var, vr
+
+
+def _sdf_grads(enc, mlp, var, vr, ro, rd, gt, t, dev, amp):
+    """One SDF training step as train_hash2.py:218-226 forms it: two field passes inside one backward (the render and the
+    eikonal stencil), three parameter sets (tables, MLP, VarModel.b)."""
+    import human_body_reconstruction_b200 as h
+    for p in list(enc.parameters()) + list(mlp.parameters()) + list(var.parameters()):
+        p.grad = None
+    with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+        Cr, Cf, norm = vr.vol_render(mlp, rd.to(dev), ro.to(dev), num_samples=32, t=t.to(dev), update_mask=False, dir_norm=1.0,
+                                     hierarchical=False)
+        loss = (torch.nn.functional.mse_loss(Cr, gt.to(dev)) + torch.nn.functional.mse_loss(Cf, gt.to(dev))
+                + 0.1 * h.helper.eikonal_loss(norm))
+    loss.backward()
+    torch.cuda.synchronize()
+    return (torch.stack([e.weight.grad for e in enc.Embedding_list]).cpu(),
+            torch.cat([p.grad.reshape(-1) for p in mlp.parameters()]).cpu(), var.b.grad.detach().cpu().clone())
+
+
+def _sdf_worker(rank, world, port_no, tmp, kind):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port_no))
+    from human_body_reconstruction_b200 import dist as hdist
+    hdist.init_from_env("nccl")
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    enc, mlp, var, vr = _build_sdf(dev)
+    red = hdist.attach_grad_allreduce(enc, mlp, kind=kind)             # "auto": the production default at 2 ranks
+    hdist.attach_small_params(var.parameters())
+    ro, rd, dn, gt, u, t, u_cand = _batch()
+    sl = hdist.shard_rays(ro.shape[0], rank, world)
+    for amp in (False, True):
+        for step in range(2):                                          # twice through the same persistent buffers
+            got = _sdf_grads(enc, mlp, var, vr, ro[sl], rd[sl], gt[sl], t, dev, amp)
+        torch.save(got, os.path.join(tmp, f"sdf{rank}_{int(amp)}.pt"))
+    region = getattr(red, "region", None)
+    if region is not None:
+        region.raise_if_failed()
+    import torch.distributed as tdist
+    tdist.barrier()
+    tdist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("kind", ["auto", "nccl"])
+def test_sdf_mode_sharded_gradients_equal_single_gpu(tmp_path, kind):
+    """SDF mode over 2 ranks: the table / MLP gradients of BOTH field passes (render + eikonal stencil: _FieldRaysFn or
+    HashEncoder/_MlpFn, then HashEncoder/_DensityFn) go through one exchange per backward, VarModel.b through
+    dist.attach_small_params; == single-GPU gradients of the whole batch, identical on both ranks.  Tolerance 2e-3: the
+    stencil's +-1/(2 eps) coefficients land on the same table entries with opposite signs, which amplifies the fp32
+    summation-order noise of the atomics (the single-GPU fixture test carries the same bound)."""
+    mp.spawn(_sdf_worker, args=(2, _free_port(), str(tmp_path), kind), nprocs=2, join=True)
+    dev = torch.device("cuda", 0)
+    enc, mlp, var, vr = _build_sdf(dev)
+    ro, rd, dn, gt, u, t, u_cand = _batch()
+    for amp in (False, True):
+        want = _sdf_grads(enc, mlp, var, vr, ro, rd, gt, t, dev, amp)
+        got = [torch.load(os.path.join(tmp_path, f"sdf{rank}_{int(amp)}.pt")) for rank in range(2)]
+        for rank in range(2):
+            for name, a, b in zip(("tables", "mlp", "b"), got[rank], want):
+                err = float((a - b).norm() / b.norm())
+                assert err < 2e-3, (kind, amp, rank, name, err)
+        for a, b in zip(got[0], got[1]):
+            assert torch.equal(a, b), (kind, amp)
