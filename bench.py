@@ -15,6 +15,10 @@ value   : rays/s with the ray batch already resident in HBM, timed with CUDA eve
 e2e     : same step driven from pinned HOST buffers: H2D of (rays_o, rays_d, dir_norm, gt) and a D2H read of the
           loss inside the timed region, wall clock.
 roofline: the dominant kernel's algorithmic bytes / its mean CUDA-event duration inside the timed steps.
+legs    : further sub-records of the same line, each skippable: c3 (configs[2]: 2^20 rays/step over the ranks, 2^17 at N=1;
+          --no-c3), grid (configs[3]: 512^3 density grid + marching cubes, slabs over the ranks; --no-grid), c5 (configs[4]:
+          T=2^22, 256 samples/ray hierarchical, N=1 only; --no-c5), occupancy_grid (--no-occupancy), device_sampler_e2e
+          (--no-device-sampler), grad_check (N>1), cpu_baseline (N=1; --no-cpu-baseline).
 """
 import argparse
 import json

@@ -284,9 +284,10 @@ class MLP_3D(nn.Module):
             raise RuntimeError("MLP_3D.eikonal_norms needs CUDA tensors (there is no CPU fallback)")
         if encoder is None:
             raise ValueError("eikonal_norms takes sample POSITIONS and needs the encoder")
+        x = x.detach().reshape(-1, 3)
         n = x.shape[0]
         lo, hi = self._bounds_host()
-        pts = ops.sdf_stencil_points(x.detach().reshape(n, 3), float(epsilon), lo, hi)
+        pts = ops.sdf_stencil_points(x, float(epsilon), lo, hi)
         dens = self._density(encoder(pts.view(6 * n, 3)))
         norm, grads = ops.SdfEikonal.apply(dens.reshape(6, n), float(epsilon))
         return (norm, grads) if with_grads else norm
