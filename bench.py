@@ -511,6 +511,35 @@ def run_b200(args):
             del img, ds, gs2
         except Exception as e:                                             # noqa: BLE001
             sampler = {"error": f"{type(e).__name__}: {e}"}
+    # (5) per-kernel durations INSIDE the replayed graph: a further capture of the same step with an external CUDA event
+    #     (an event-record node of the graph) on either side of every C-ABI call.  The eager region (1) brackets the calls
+    #     with events too, but there the host needs ~1.1 ms to enqueue what the GPU runs in ~0.47 ms, so an interval also
+    #     holds the wait for the launch to arrive; inside the graph it is the kernel (plus a node boundary).
+    kern_graph, kern_graph_note = None, None
+    if gs is not None and args.graph_kernel_times:
+        try:
+            _lib.STATS.reset()
+            _lib.STATS.timing = True
+            gst = GraphedStep(vr, nerf, params, rays, args.samples, args.hierarchical, dev, autocast=amp, autocast_dtype=amp_dtype).capture()
+            _lib.STATS.timing = False
+            for k in range(3):
+                gst(resident_packed[k % len(resident_packed)])
+            torch.cuda.synchronize()
+            acc = {}
+            for k in range(args.steps):
+                if flush is not None:
+                    flush.zero_()
+                gst(resident_packed[k % len(resident_packed)])
+                torch.cuda.synchronize()
+                for name, ts in _lib.STATS.graph_times().items():
+                    c, tot = acc.get(name, (0, 0.0))
+                    acc[name] = (c + len(ts), tot + sum(ts))
+            kern_graph = {k: (c, tot / c) for k, (c, tot) in acc.items() if c}
+            del gst
+        except Exception as e:                                             # noqa: BLE001  (keep the eager figures)
+            kern_graph, kern_graph_note = None, f"{type(e).__name__}: {e}"[:200]
+        finally:
+            _lib.STATS.timing = False
     barrier()
     clk = clocks.stop()
 
@@ -533,7 +562,13 @@ def run_b200(args):
     value = total_rays / (dev_ms / 1e3)
     peaks = measured_peaks()
     peak = peaks[0]
-    # dominant kernel
+    # dominant kernel; durations from inside the replayed graph when that measurement succeeded, else from the eager region
+    kern_eager = kern
+    timing_src = "cuda events around every C-ABI call in the eager region (host-driven launches)"
+    if kern_graph and all(k in kern_graph for k in kern if k in BYTES_PER_POINT or k in FLOPS_PER_POINT):
+        kern = dict(kern_eager)
+        kern.update(kern_graph)
+        timing_src = "external cuda events recorded inside the replayed cuda graph, on either side of every C-ABI call"
     tot = {k: c * m for k, (c, m) in kern.items()}
     dom = max(tot, key=tot.get)
     traffic_tab = {}
@@ -547,6 +582,7 @@ def run_b200(args):
         r = kernel_roofline(name, n_pts / (c / args.steps), m, peaks)
         r["traffic"] = traffic_tab.get(name)       # dram bytes read+written per launch, one ncu --set full capture
         r["traffic_source"] = "imported from profiles/traffic.json (an earlier ncu --set full capture of this command), not measured in this run"
+        r["timing"] = timing_src
         return r
 
     roofline = roof(dom)
@@ -571,7 +607,9 @@ def run_b200(args):
                              for k in sorted(kern) if k in BYTES_PER_POINT},
         "step_roofline": {"algorithmic_bytes_per_point": STEP_BYTES_PER_POINT, "achieved": step_achieved, "frac": step_achieved / peak,
                           "unit": "GB/s"},
-        "kernels_ms": {k: {"launches_per_step": c / args.steps, "mean_ms": m} for k, (c, m) in sorted(kern.items())},
+        "kernels_ms": {k: {"launches_per_step": c / args.steps, "mean_ms": m} for k, (c, m) in sorted(kern_eager.items())},
+        "kernels_ms_in_graph": ({k: {"launches_per_step": c / args.steps, "mean_ms": m} for k, (c, m) in sorted(kern_graph.items())}
+                                if kern_graph else {"unavailable": kern_graph_note or "graph off"}),
         "eager_wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
         "clocks": clk, "last_loss": loss_val,
     }
@@ -952,6 +990,8 @@ def main():
     ap.add_argument("--grid-res", type=int, default=512)
     ap.add_argument("--no-occupancy", action="store_true", help="skip the live-occupancy-grid leg (8f row 3)")
     ap.add_argument("--repeats", type=int, default=5, help="timed regions of K steps each; value = their median")
+    ap.add_argument("--no-graph-kernel-times", dest="graph_kernel_times", action="store_false",
+                    help="skip the per-kernel timing inside the replayed graph (external event nodes); rooflines then use the eager region's events")
     ap.add_argument("--no-c5", dest="c5", action="store_false", help="skip the configs[4] leg (T=2^22, 256 samples/ray hierarchical; N=1 only)")
     ap.add_argument("--no-c3", dest="c3", action="store_false", help="skip the configs[2] leg (2^20 rays/step global; 2^17 at N=1)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],

@@ -242,11 +242,21 @@ class _Stats:
         self.calls = {}
         self.timing = False
         self.events = []            # (name, start_event, end_event)
+        self.graph_events = []      # the same for calls made while a CUDA graph was being captured: EXTERNAL events, i.e. event
+                                    # record nodes of that graph -- every replay re-records them (read after a synchronize)
 
     def reset(self):
         self.launches = 0
         self.calls = {}
         self.events = []
+        self.graph_events = []
+
+    def graph_times(self):
+        """name -> [ms of each call of the last replay]; call after the replay has been synchronised."""
+        out = {}
+        for name, a, b in self.graph_events:
+            out.setdefault(name, []).append(a.elapsed_time(b))
+        return out
 
     def summary(self):
         """name -> (count, mean_ms); call after torch.cuda.synchronize()."""
@@ -271,13 +281,14 @@ class _Counted:
         st.launches += self.k
         st.calls[self.name] = st.calls.get(self.name, 0) + 1
         if st.timing and self.k:
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
+            ext = torch.cuda.is_current_stream_capturing()
+            e0 = torch.cuda.Event(enable_timing=True, external=ext)
+            e1 = torch.cuda.Event(enable_timing=True, external=ext)
             s = torch.cuda.current_stream()
             e0.record(s)
             rc = self.fn(*a)
             e1.record(s)
-            st.events.append((self.name, e0, e1))
+            (st.graph_events if ext else st.events).append((self.name, e0, e1))
             return rc
         return self.fn(*a)
 
