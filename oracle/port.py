@@ -351,6 +351,35 @@ def composite_sdf(rgb: torch.Tensor, sdf: torch.Tensor, b) -> Tuple[torch.Tensor
     return torch.sum(T[:, :, None] * alpha[:, :, None] * rgb, dim=-2), wts
 
 
+def composite_sdf_bwd(rgb: torch.Tensor, sdf: torch.Tensor, b, gC: torch.Tensor, gw: Optional[torch.Tensor] = None):
+    """Closed-form backward of composite_sdf (what autograd gives for helper.py:76-86,102-105), the derivation the CUDA
+    kernel follows: with c_i = gC . rgb_i + gw_i, r_i = phi_{i+1} / phi_i, suffix_i = sum_{k>i} w_k c_k,
+      e_i = alpha_i > 0 ? suffix_i - T_i c_i (1 - alpha_i) : 0        (= dL/dr_i * r_i; relu'(0) = 0)
+      dL/d(s_i b) = (1 - phi_i) (e_{i-1} - e_i),   e_{-1} = e_{S-1} = 0
+    Returns (d rgb (R,S,3), d sdf (R,S) -- 0 where the -10 clamp hit --, dL/db scalar)."""
+    s = sdf.clone()
+    keep = ~(s < -10)
+    s[~keep] = -10
+    phi = 1 / (1 + torch.exp(-s * b))
+    r = torch.ones_like(s)
+    r[..., :-1] = phi[..., 1:] / phi[..., :-1]
+    alpha = torch.clamp(1 - r, min=0)
+    alpha[..., -1] = 0
+    T = torch.ones_like(s)
+    T[..., 1:] = torch.cumprod(1 - alpha, -1)[..., :-1]
+    w = T * alpha
+    c = (rgb * gC[:, None, :]).sum(-1)
+    if gw is not None:
+        c = c + gw
+    wc = w * c
+    suffix = torch.flip(torch.cumsum(torch.flip(wc, [-1]), -1), [-1]) - wc
+    e = torch.where(alpha > 0, suffix - T * c * (1 - alpha), torch.zeros_like(s))
+    e_prev = torch.zeros_like(e)
+    e_prev[..., 1:] = e[..., :-1]
+    base = (1 - phi) * (e_prev - e)
+    return w[..., None] * gC[:, None, :], torch.where(keep, b * base, torch.zeros_like(s)), (s * base).sum()
+
+
 def vol_render_sdf(p_mlp, tables, mu, sigma, scales, rays_d, rays_o, t, b, min_bound, max_bound, num_freq=4):
     """Volume_Renderer.vol_render with use_sdf=True, hierarchical=False, all-True occupancy grid
     (vol_renderer.py:165-223 -> helper.py:80-89).  Returns (Cr, wts, eikonal norms (R*S,))."""

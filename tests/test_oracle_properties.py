@@ -5,6 +5,8 @@ full size, checked here on the restatement itself:
   * trilinear corner weights are a partition of unity; a constant table encodes to that constant;
   * the table gradient is linear in dy and its sum over the table equals sum(w * dy);
   * compositing: sum of weights = 1 - final transmittance, the closed-form backward == autograd;
+  * SDF compositing (8f row 4): weights in [0, 1], their sum = 1 - product of (1 - alpha), the closed-form backward the
+    CUDA kernel implements == autograd (d rgb, d sdf with the -10 clamp, dL/db, with and without a weight gradient);
   * hierarchical sampling returns sorted depths that contain every coarse depth."""
 import numpy as np
 import torch
@@ -96,3 +98,37 @@ def test_hier_sample_sorted_and_contains_coarse(seed, S):
     for r in range(R):
         assert all(bool((merged[r] == v).any()) for v in t)
     assert float(merged.min()) >= 2.0 - 1e-6 and float(merged.max()) <= 6.0 + 1e-6
+
+
+@SET
+@given(st.integers(0, 2 ** 31 - 1), st.integers(1, 48), st.sampled_from(["uniform", "walk", "wide"]), st.booleans())
+def test_sdf_composite_weights_and_closed_form_backward(seed, S, kind, with_gw):
+    g = torch.Generator().manual_seed(seed)
+    R = 4
+    if kind == "uniform":
+        sdf, bval = torch.rand(R, S, generator=g, dtype=torch.float64) * 2 - 1, 0.5
+    elif kind == "walk":
+        sdf, bval = torch.cumsum(torch.randn(R, S, generator=g, dtype=torch.float64) * 0.05, -1), 0.9
+    else:
+        sdf, bval = (torch.rand(R, S, generator=g, dtype=torch.float64) * 2 - 1) * 14, 1.3      # crosses the -10 clamp
+    rgb = torch.rand(R, S, 3, generator=g, dtype=torch.float64).requires_grad_(True)
+    sdf.requires_grad_(True)
+    b = torch.tensor(bval, dtype=torch.float64, requires_grad=True)
+    C, w = port.composite_sdf(rgb, sdf, b)
+    w2 = w[..., 0].detach()
+    assert bool((w2 >= 0).all()) and bool((w2 <= 1 + 1e-12).all())
+    s = torch.clamp(sdf.detach(), min=-10)
+    phi = 1 / (1 + torch.exp(-s * bval))
+    alpha = torch.zeros_like(s)
+    alpha[:, :-1] = torch.clamp(1 - phi[:, 1:] / phi[:, :-1], min=0)
+    assert torch.allclose(w2.sum(-1), 1 - torch.prod(1 - alpha, -1), rtol=1e-10, atol=1e-12)    # telescoping product
+    gC = torch.randn(R, 3, generator=g, dtype=torch.float64)
+    gw = torch.randn(R, S, generator=g, dtype=torch.float64) if with_gw else None
+    loss = (C * gC).sum() + ((w[..., 0] * gw).sum() if with_gw else 0)
+    loss.backward()
+    drgb, dsdf, db = port.composite_sdf_bwd(rgb.detach(), sdf.detach(), b.detach(), gC, gw)
+    assert torch.allclose(drgb, rgb.grad, rtol=1e-10, atol=1e-12)
+    scale = sdf.grad.abs().max() + 1.0
+    assert bool(((dsdf - sdf.grad).abs() <= 1e-9 * scale).all())
+    assert abs(float(db) - float(b.grad)) <= 1e-9 * (abs(float(b.grad)) + 1.0)
+    assert bool((dsdf[sdf.detach() < -10] == 0).all())
