@@ -516,7 +516,8 @@ def run_b200(args):
     #     with events too, but there the host needs ~1.1 ms to enqueue what the GPU runs in ~0.47 ms, so an interval also
     #     holds the wait for the launch to arrive; inside the graph it is the kernel (plus a node boundary).
     kern_graph, kern_graph_note = None, None
-    if gs is not None and args.graph_kernel_times:
+    if gs is not None and args.graph_kernel_times and world == 1:     # N>1: the eager region's events (the exchange kernel's
+                                                                       # cross-rank barriers stay out of a third capture)
         try:
             _lib.STATS.reset()
             _lib.STATS.timing = True
