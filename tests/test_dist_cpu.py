@@ -245,3 +245,32 @@ def test_small_params_broadcast_and_gradient_average(tmp_path):
         (g,) = torch.autograd.grad((1 / (1 + torch.exp(-x * b))).sum(), b)
         want = want + g / 2
     assert torch.equal(g0, g1) and torch.allclose(g0, want, rtol=1e-6)
+
+
+def _auto_attach_worker(rank, world, port_no, tmp):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    import human_body_reconstruction_b200 as h
+    torch.manual_seed(100 + rank)                                      # the unchanged trainer does not seed: ranks differ
+    enc = h.HashEncoder(N_min=16, N_max=64.0, L=4, F=2, T=64, dim=3, mu=torch.zeros(3), sigma=torch.tensor(1.0), device="cpu")
+    mlp = h.MLP_3D(num_sig=2, num_col=2, L=4, F=2, d_view=24)
+    var = h.helper.VarModel()
+    with torch.no_grad():
+        var.b.fill_(0.25 + rank)
+    red = hdist.auto_attach(enc, mlp, extra=var.parameters())
+    again = hdist.auto_attach(enc, mlp, extra=var.parameters())        # second call: nothing new, same exchange
+    torch.save({"table": enc._flat_table().clone(), "mlp": mlp._flat_params().clone(), "b": float(var.b),
+                "kind": type(red).__name__, "same": again is red, "attached": enc._dp is red and mlp._dp is red,
+                "hook": getattr(var.b, "_hbr_dp_hook", None) is not None}, os.path.join(tmp, f"aa{rank}.pt"))
+    tdist.barrier()
+    tdist.destroy_process_group()
+
+
+def test_auto_attach_broadcasts_rank0_parameters_and_takes_the_sdf_parameter_along(tmp_path):
+    """dist.auto_attach (launch_rank.py's zero-edit route): every rank ends with rank 0's tables, MLP parameters and --
+    SDF mode -- VarModel.b; the exchange is attached once (gloo ranks: the torch.distributed all-reduce flavour)."""
+    mp.spawn(_auto_attach_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    a, b = (torch.load(os.path.join(tmp_path, f"aa{r}.pt")) for r in range(2))
+    assert torch.equal(a["table"], b["table"]) and torch.equal(a["mlp"], b["mlp"]) and a["b"] == b["b"] == 0.25
+    for r in (a, b):
+        assert r["kind"] == "GradAllReduce" and r["same"] and r["attached"] and r["hook"]

@@ -100,3 +100,29 @@ def test_mlp_bounds_for_the_eikonal_stencil_follow_the_tensors():
     m.max_bound[1] = 5.0
     assert m._bounds_host()[1] == [1.0, 5.0, 3.0]
     assert h.MLP_3D(num_sig=2, num_col=2, L=16, F=2, d_view=24)._bounds_host() == ([-1.0] * 3, [1.0] * 3)
+
+
+def test_sdf_route_selection_is_by_module_type():
+    """Volume_Renderer._native_sdf: the dedicated SDF route needs the native encoder / direction encoder / MLP_3D AND the
+    reference's own VarModel (whose parameter the compositing kernel reads); anything else keeps the reference's data
+    flow (_generic), where calc_color decides per call."""
+    import human_body_reconstruction_b200 as h
+    enc = h.HashEncoder(N_min=16, N_max=64.0, L=4, F=2, T=64, dim=3, mu=torch.zeros(3), sigma=torch.tensor(1.0), device="cpu")
+    mlp = h.MLP_3D(num_sig=2, num_col=2, L=4, F=2, d_view=24)
+    pe = h.PositionalEncoder(3, 4)
+
+    def renderer(var, pos=enc):
+        return h.Volume_Renderer(H=4, W=4, K=torch.eye(3), near=torch.tensor(2.0), far=torch.tensor(6.0), device="cpu", Pos_encode=pos,
+                                 Dir_encode=pe, max_dim=16, sigma_val=torch.tensor(1.0), mu=torch.zeros(3), use_sdf=True, var_model=var)
+
+    class OtherVar(h.helper.VarModel):
+        def forward(self, x):
+            return torch.sigmoid(2 * x * self.b)
+
+    vr = renderer(h.helper.VarModel())
+    assert vr._native_sdf(mlp) is mlp and vr._native_sdf(torch.nn.DataParallel(mlp, device_ids=[0]) if torch.cuda.is_available() else mlp) is mlp
+    assert vr._native(mlp) is None                                     # never the NeRF-mode route
+    assert renderer(OtherVar())._native_sdf(mlp) is None               # a different phi: tensor expressions
+    assert renderer(h.helper.VarModel(), pos=torch.nn.Identity())._native_sdf(mlp) is None
+    assert renderer(h.helper.VarModel())._native_sdf(torch.nn.Linear(4, 4)) is None
+    assert vr.sdf_native is True and h.helper.SDF_KERNELS is True
