@@ -506,7 +506,7 @@ class Volume_Renderer:
         device = "cuda"
         if t is None:
             t = strat_sampler(near, far, num_samples, device=rays_d.device)                 # RNG draw #1
-        if self.use_sdf and self.sdf_native and hierarchical is not True and update_mask is not True:
+        if self.use_sdf and self.sdf_native and hierarchical is not True and update_mask is not True and t.shape[-1] <= 1024:
             sdf_mlp = self._native_sdf(model)
             if sdf_mlp is not None and self._grid_all_true():
                 self._auto_dp(sdf_mlp)
